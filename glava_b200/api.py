@@ -1,0 +1,265 @@
+"""ctypes binding of include/glava_b200.h."""
+import ctypes as C
+import os
+
+import numpy as np
+
+MODULES = ("bars", "radial", "circle", "graph", "wave", "test")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class GlavaError(RuntimeError):
+    pass
+
+
+class Color(C.Structure):
+    _fields_ = [("mode", C.c_int), ("lo", C.c_float * 4), ("hi", C.c_float * 4), ("gradient", C.c_float)]
+
+
+class Params(C.Structure):
+    """struct glava_b200_params (include/glava_b200.h) — same field order."""
+    _fields_ = [
+        ("n", C.c_int), ("fft_scale", C.c_float), ("fft_cutoff", C.c_float), ("gravity_step", C.c_float),
+        ("ur", C.c_float), ("avg_frames", C.c_int), ("avg_window", C.c_int), ("accel_fft", C.c_int),
+        ("smooth_pass", C.c_int), ("smooth_factor", C.c_float), ("sample_range", C.c_float),
+        ("sample_scale", C.c_float), ("hybrid_weight", C.c_float), ("sample_mode", C.c_int),
+        ("round_formula", C.c_int),
+        ("module", C.c_int), ("w", C.c_int), ("h", C.c_int), ("channels", C.c_int), ("premultiply_alpha", C.c_int),
+        ("bars_width", C.c_float), ("bars_gap", C.c_float), ("bars_outline_width", C.c_float), ("bars_amplify", C.c_float),
+        ("bars_color", Color), ("bars_outline_mode", C.c_int), ("bars_outline", C.c_float * 4),
+        ("bars_direction", C.c_int), ("bars_invert", C.c_int), ("bars_flip", C.c_int), ("bars_mirror_yx", C.c_int),
+        ("radial_radius", C.c_float), ("radial_line", C.c_float), ("radial_line_half", C.c_float),
+        ("radial_outline", C.c_float * 4), ("radial_nbars", C.c_int), ("radial_bar_width", C.c_float),
+        ("radial_amplify", C.c_float), ("radial_color", Color), ("radial_rotate", C.c_float), ("radial_invert", C.c_int),
+        ("radial_bar_alias", C.c_float), ("radial_c_alias", C.c_float), ("radial_off_x", C.c_float), ("radial_off_y", C.c_float),
+        ("circle_radius", C.c_float), ("circle_line", C.c_float), ("circle_outline", C.c_float * 4),
+        ("circle_amplify", C.c_float), ("circle_rotate", C.c_float), ("circle_invert", C.c_int),
+        ("circle_fill", C.c_int), ("circle_smooth", C.c_int),
+        ("graph_vscale", C.c_float), ("graph_direction", C.c_int), ("graph_color", Color),
+        ("graph_draw_outline", C.c_int), ("graph_draw_highlight", C.c_int), ("graph_outline", C.c_float * 4),
+        ("graph_invert", C.c_int),
+        ("wave_min_thickness", C.c_float), ("wave_max_thickness", C.c_float), ("wave_base_color", C.c_float * 4),
+        ("wave_amplify", C.c_float), ("wave_outline", C.c_float * 4),
+        ("rate_request", C.c_int), ("samplesize_request", C.c_int),
+        ("fb_slots", C.c_int), ("lazy_smooth", C.c_int),
+    ]
+
+    def copy(self):
+        q = Params()
+        C.memmove(C.byref(q), C.byref(self), C.sizeof(Params))
+        return q
+
+    @property
+    def module_name(self):
+        return MODULES[self.module]
+
+
+_lib = None
+
+
+def lib_path():
+    return os.path.join(_HERE, "libglava_b200.so")
+
+
+def lib():
+    """Load libglava_b200.so (built in-tree by __graft_entry__.build()).  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise GlavaError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "(the B200 path has no CPU fallback)")
+    L = C.CDLL(path)
+    vp, cp, i32 = C.c_void_p, C.c_char_p, C.c_int
+    L.glava_b200_last_error.restype = cp
+    L.glava_b200_version.restype = cp
+    L.glava_b200_default_params.argtypes = [C.POINTER(Params), cp]
+    L.glava_b200_load_config.argtypes = [C.POINTER(Params), C.POINTER(cp), cp, C.POINTER(cp), cp]
+    L.glava_b200_new.restype = vp
+    L.glava_b200_new.argtypes = [C.POINTER(Params), i32, i32]
+    L.glava_b200_destroy.argtypes = [vp]
+    L.glava_b200_get_params.argtypes = [vp, C.POINTER(Params)]
+    L.glava_b200_batch.argtypes = [vp]
+    L.glava_b200_module_name.argtypes = [vp]
+    L.glava_b200_module_name.restype = cp
+    L.glava_b200_host_alloc.restype = vp
+    L.glava_b200_host_alloc.argtypes = [C.c_size_t]
+    L.glava_b200_host_free.argtypes = [vp]
+    L.glava_b200_update.argtypes = [vp, vp, vp, C.c_size_t, i32]
+    L.glava_b200_update_device.argtypes = [vp, vp, vp, C.c_size_t, i32]
+    L.glava_b200_ingest_fifo.argtypes = [vp, vp, i32]
+    L.glava_b200_update_rings.argtypes = [vp, i32]
+    L.glava_b200_sync.argtypes = [vp]
+    L.glava_b200_readback.argtypes = [vp, i32, vp]
+    L.glava_b200_spectrum.argtypes = [vp, vp, vp]
+    L.glava_b200_textures.argtypes = [vp, vp, vp]
+    L.glava_b200_framebuffer_device.argtypes = [vp]
+    L.glava_b200_framebuffer_device.restype = vp
+    L.glava_b200_cuda_stream.argtypes = [vp]
+    L.glava_b200_cuda_stream.restype = vp
+    L.glava_b200_smooth_pass.argtypes = [vp, vp, vp, i32]
+    L.glava_b200_raster_textures.argtypes = [vp, vp, vp]
+    L.glava_b200_launch_count.argtypes = [vp]
+    L.glava_b200_launch_count.restype = C.c_uint64
+    L.glava_b200_set_abort_hook.argtypes = [vp]
+    _lib = L
+    # errors surface as Python exceptions; keep stderr quiet
+    _quiet = C.CFUNCTYPE(None, cp)(lambda msg: None)
+    L._quiet_hook = _quiet
+    L.glava_b200_set_abort_hook(C.cast(_quiet, vp))
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise GlavaError(lib().glava_b200_last_error().decode(errors="replace") or f"error {rc}")
+
+
+def default_params(module="bars", **overrides):
+    p = Params()
+    _check(lib().glava_b200_default_params(C.byref(p), module.encode()))
+    for k, v in overrides.items():
+        setattr(p, k, v)
+    return p
+
+
+def _cstr_array(items):
+    if items is None:
+        return None
+    arr = (C.c_char_p * (len(items) + 1))()
+    for i, s in enumerate(items):
+        arr[i] = s.encode()
+    arr[len(items)] = None
+    return arr
+
+
+def load_config(paths=None, entry="rc.glsl", requests=None, force_module=None):
+    """rd_new's config half (render.c:1322-1435): read `entry` from the first of `paths`, apply
+    `#request`s and `requests` (CLI --request strings), then the module's `#define`s."""
+    p = Params()
+    _check(lib().glava_b200_load_config(C.byref(p), _cstr_array(paths), entry.encode() if entry else None,
+                                        _cstr_array(requests), force_module.encode() if force_module else None))
+    return p
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by cudaHostAlloc'd memory (freed when the array is collected)."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    ptr = lib().glava_b200_host_alloc(nbytes)
+    if not ptr:
+        raise GlavaError("pinned allocation failed")
+    buf = (C.c_byte * nbytes).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    class _Owner:
+        def __init__(self, p): self.p = p
+        def __del__(self):
+            try: lib().glava_b200_host_free(self.p)
+            except Exception: pass
+    arr = arr.view()
+    _owners[id(buf)] = (_Owner(ptr), buf)
+    return arr
+
+
+_owners = {}
+
+
+class Renderer:
+    """Batched renderer handle: the role of struct glava_renderer (render.h:8-30)."""
+
+    def __init__(self, params, batch=1, device=0):
+        self._L = lib()
+        self._h = self._L.glava_b200_new(C.byref(params), int(batch), int(device))
+        if not self._h:
+            raise GlavaError(self._L.glava_b200_last_error().decode(errors="replace"))
+        self.params = Params()
+        _check(self._L.glava_b200_get_params(self._h, C.byref(self.params)))
+        self.batch = int(batch)
+        self.device = int(device)
+
+    # -- rd_update ---------------------------------------------------------------------------------
+    def update(self, lb, rb=None, modified=True):
+        """lb, rb: host float32 arrays [batch][n] (ring contents oldest-first)."""
+        lb = np.ascontiguousarray(lb, dtype=np.float32)
+        assert lb.shape == (self.batch, self.params.n), lb.shape
+        rp = None
+        if rb is not None:
+            rb = np.ascontiguousarray(rb, dtype=np.float32)
+            assert rb.shape == lb.shape
+            rp = rb.ctypes.data
+        _check(self._L.glava_b200_update(self._h, lb.ctypes.data, rp, self.params.n, 1 if modified else 0))
+
+    def update_device(self, d_lb, d_rb, modified=True):
+        """d_lb, d_rb: integer device addresses of [batch][n] float32 (e.g. torch tensor.data_ptr())."""
+        _check(self._L.glava_b200_update_device(self._h, d_lb, d_rb, self.params.n, 1 if modified else 0))
+
+    def ingest_fifo(self, chunks):
+        chunks = np.ascontiguousarray(chunks, dtype=np.int16)
+        assert chunks.ndim == 2 and chunks.shape[0] == self.batch and chunks.shape[1] % 2 == 0
+        _check(self._L.glava_b200_ingest_fifo(self._h, chunks.ctypes.data, chunks.shape[1] // 2))
+
+    def update_rings(self, modified=True):
+        _check(self._L.glava_b200_update_rings(self._h, 1 if modified else 0))
+
+    def sync(self):
+        _check(self._L.glava_b200_sync(self._h))
+
+    # -- outputs -----------------------------------------------------------------------------------
+    def readback(self, stream=0, out=None):
+        p = self.params
+        if out is None:
+            out = np.empty((p.h, p.w, 4), dtype=np.uint8)
+        _check(self._L.glava_b200_readback(self._h, int(stream), out.ctypes.data))
+        return out
+
+    def spectrum(self):
+        l = np.empty((self.batch, self.params.n), dtype=np.float32); r = np.empty_like(l)
+        _check(self._L.glava_b200_spectrum(self._h, l.ctypes.data, r.ctypes.data))
+        return l, r
+
+    def textures(self):
+        l = np.empty((self.batch, self.params.n), dtype=np.uint16); r = np.empty_like(l)
+        _check(self._L.glava_b200_textures(self._h, l.ctypes.data, r.ctypes.data))
+        return l, r
+
+    def smooth_pass(self, tex):
+        tex = np.ascontiguousarray(tex, dtype=np.uint16)
+        assert tex.ndim == 2 and tex.shape[1] == self.params.n
+        out = np.empty_like(tex)
+        _check(self._L.glava_b200_smooth_pass(self._h, tex.ctypes.data, out.ctypes.data, tex.shape[0]))
+        return out
+
+    def raster_textures(self, tex_l, tex_r=None):
+        tex_l = np.ascontiguousarray(tex_l, dtype=np.uint16)
+        assert tex_l.shape == (self.batch, self.params.n)
+        rp = None
+        if tex_r is not None:
+            tex_r = np.ascontiguousarray(tex_r, dtype=np.uint16)
+            rp = tex_r.ctypes.data
+        _check(self._L.glava_b200_raster_textures(self._h, tex_l.ctypes.data, rp))
+
+    @property
+    def framebuffer_device(self):
+        return self._L.glava_b200_framebuffer_device(self._h)
+
+    @property
+    def cuda_stream(self):
+        return self._L.glava_b200_cuda_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return int(self._L.glava_b200_launch_count(self._h))
+
+    # -- rd_destroy --------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.glava_b200_destroy(self._h)
+            self._h = None
+
+    def __enter__(self): return self
+    def __exit__(self, *a): self.close()
+    def __del__(self):
+        try: self.close()
+        except Exception: pass

@@ -1,0 +1,340 @@
+// capi.cu — the C ABI of include/glava_b200.h: renderer handle, device memory, streams.
+//
+// Plays the role of rd_new / rd_update / rd_destroy (reference glava/render.c:867,1743,2456)
+// for a batch of independent streams on one CUDA device.  All device state (PCM staging,
+// gravity/average state per stream and channel, R16 textures, framebuffers) is allocated once
+// in glava_b200_new and stays resident in HBM.
+#include "internal.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace glb {
+
+// ---- error plumbing -----------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static thread_local bool g_has_error = false;
+static void default_hook(const char* msg) { fprintf(stderr, "glava_b200: %s\n", msg); }
+static void (*g_hook)(const char*) = default_hook;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    g_last_error = buf; g_has_error = true;
+    if (g_hook) g_hook(buf);
+    return code;
+}
+void clear_error() { g_has_error = false; }
+bool has_error() { return g_has_error; }
+
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) return fail(GLAVA_B200_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+}  // namespace glb
+
+using namespace glb;
+
+struct glava_b200 {
+    glava_b200_params p;
+    int batch, device, slots;
+    cudaStream_t stream;
+    // inputs
+    float* d_pcm[2];            // H2D staging for glava_b200_update         [batch][n] x {l, r}
+    float* d_ring[2][2];        // FIFO rings, ping-pong                      [2][batch][n] x {l, r}
+    int    ring_cur;
+    int16_t* d_chunks; size_t chunks_cap;
+    // constants
+    double* d_window; float* d_twiddle; void* d_rowtab; int* d_need; int need_count;
+    // state + outputs
+    float* d_spec; float* d_applied; float* d_ring_f;
+    uint16_t* d_gr_store; uint16_t* d_ring_u; uint16_t* d_tex;
+    uint8_t* d_fb;
+    unsigned long long updates;
+    uint64_t launches;
+    std::vector<void*> allocs;
+};
+
+static int dev_alloc(glava_b200* r, void** out, size_t bytes, bool zero) {
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess)
+        return fail(GLAVA_B200_ECUDA, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+    r->allocs.push_back(*out);
+    if (zero) CU(cudaMemsetAsync(*out, 0, bytes, r->stream));
+    return 0;
+}
+
+extern "C" {
+
+void glava_b200_set_abort_hook(void (*hook)(const char*)) { g_hook = hook ? hook : default_hook; }
+const char* glava_b200_last_error(void) { return g_last_error.c_str(); }
+const char* glava_b200_version(void) { return "glava_b200 0.1 (sm_100a)"; }
+
+int glava_b200_default_params(glava_b200_params* out, const char* module) {
+    clear_error();
+    if (!out || !module) return fail(GLAVA_B200_EINVAL, "null argument");
+    int m = module_from_name(module);
+    if (m < 0) return fail(GLAVA_B200_ECONFIG, "Could not find module '%s'", module);
+    fill_defaults(out, m);
+    return GLAVA_B200_OK;
+}
+
+int glava_b200_load_config(glava_b200_params* out, const char* const* paths, const char* entry,
+                           const char* const* requests, const char* force_module) {
+    if (!out) return fail(GLAVA_B200_EINVAL, "null argument");
+    return load_config(out, paths, entry, requests, force_module);
+}
+
+void* glava_b200_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) {
+        fail(GLAVA_B200_ECUDA, "cudaHostAlloc(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+void glava_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+static int build(glava_b200* r) {
+    const glava_b200_params& p = r->p;
+    const size_t n = (size_t) p.n, planes = (size_t) r->batch * 2, F = (size_t) p.avg_frames;
+    CU(cudaSetDevice(r->device));
+    CU(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+    int rc;
+#define ALLOC(ptr, bytes, zero) if ((rc = dev_alloc(r, (void**) &(ptr), (bytes), (zero))) != 0) return rc
+    ALLOC(r->d_pcm[0], (size_t) r->batch * n * 4, true);  ALLOC(r->d_pcm[1], (size_t) r->batch * n * 4, true);
+    for (int i = 0; i < 2; ++i) for (int c = 0; c < 2; ++c) ALLOC(r->d_ring[i][c], (size_t) r->batch * n * 4, true);
+    ALLOC(r->d_window, n * 8, false); ALLOC(r->d_twiddle, n * 4, false);
+    ALLOC(r->d_spec, planes * n * 4, true);
+    if (p.accel_fft) { ALLOC(r->d_gr_store, planes * n * 2, true); ALLOC(r->d_ring_u, planes * F * n * 2, true); }
+    else             { ALLOC(r->d_applied, planes * n * 4, true);  ALLOC(r->d_ring_f, planes * F * n * 4, true); }
+    ALLOC(r->d_tex, planes * n * 2, true);
+    ALLOC(r->d_rowtab, (size_t) p.h * 8, true);
+    // framebuffers: [slots][h][w] RGBA8
+    size_t frame = (size_t) p.w * p.h * 4;
+    r->slots = (p.fb_slots > 0 && p.fb_slots < r->batch) ? p.fb_slots : r->batch;
+    ALLOC(r->d_fb, frame * r->slots, true);
+#undef ALLOC
+    // window LUT: render.c:660 macro as expanded at render.c:794 — cos(TWOPI*i/N - 1), double
+    std::vector<double> w(n);
+    for (size_t i = 0; i < n; ++i) w[i] = 0.53836 - (0.46164 * cos(6.28318530718 * (double) i / (double) n - 1));
+    CU(cudaMemcpyAsync(r->d_window, w.data(), n * 8, cudaMemcpyHostToDevice, r->stream));
+    // twiddles exp(-2*pi*i*k/M), M = n/2, evaluated in double
+    const size_t M = n / 2;
+    std::vector<float> tw(2 * M);
+    for (size_t k = 0; k < M; ++k) {
+        double ang = -2.0 * M_PI * (double) k / (double) M;
+        tw[2 * k] = (float) cos(ang); tw[2 * k + 1] = (float) sin(ang);
+    }
+    CU(cudaMemcpyAsync(r->d_twiddle, tw.data(), n * 4, cudaMemcpyHostToDevice, r->stream));
+    CU(cudaStreamSynchronize(r->stream));
+    if (p.module == GLAVA_B200_MOD_BARS) { if ((rc = launch_bars_rowtab(p, r->d_rowtab, r->stream)) != 0) return rc; ++r->launches; }
+    CU(cudaStreamSynchronize(r->stream));
+    return 0;
+}
+
+glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int device) {
+    clear_error();
+    if (!params || batch < 1) { fail(GLAVA_B200_EINVAL, "glava_b200_new: bad arguments"); return nullptr; }
+    if (validate_params(params) != 0) return nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        fail(GLAVA_B200_ECUDA, "no CUDA device available: the B200 path has no CPU fallback");
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) { fail(GLAVA_B200_EINVAL, "device %d out of range (%d devices)", device, ndev); return nullptr; }
+    glava_b200* r = new glava_b200();
+    r->p = *params; r->batch = batch; r->device = device;
+    r->stream = nullptr; r->ring_cur = 0; r->d_chunks = nullptr; r->chunks_cap = 0;
+    r->d_window = nullptr; r->d_twiddle = nullptr; r->d_rowtab = nullptr; r->d_need = nullptr; r->need_count = 0;
+    r->d_spec = r->d_applied = r->d_ring_f = nullptr; r->d_gr_store = r->d_ring_u = r->d_tex = nullptr; r->d_fb = nullptr;
+    r->d_pcm[0] = r->d_pcm[1] = nullptr;
+    r->updates = 0; r->launches = 0;
+    if (build(r) != 0) { glava_b200_destroy(r); return nullptr; }
+    return r;
+}
+
+void glava_b200_destroy(glava_b200* r) {
+    if (!r) return;
+    cudaSetDevice(r->device);
+    if (r->stream) cudaStreamSynchronize(r->stream);
+    for (void* p : r->allocs) cudaFree(p);
+    if (r->d_chunks) cudaFree(r->d_chunks);
+    if (r->stream) cudaStreamDestroy(r->stream);
+    delete r;
+}
+
+int glava_b200_get_params(const glava_b200* r, glava_b200_params* out) {
+    if (!r || !out) return fail(GLAVA_B200_EINVAL, "null argument");
+    *out = r->p; return 0;
+}
+int glava_b200_batch(const glava_b200* r) { return r ? r->batch : 0; }
+const char* glava_b200_module_name(const glava_b200* r) { return r ? module_name(r->p.module) : "?"; }
+const void* glava_b200_framebuffer_device(const glava_b200* r) { return r ? r->d_fb : nullptr; }
+void* glava_b200_cuda_stream(const glava_b200* r) { return r ? (void*) r->stream : nullptr; }
+uint64_t glava_b200_launch_count(const glava_b200* r) { return r ? r->launches : 0; }
+
+static int run_update(glava_b200* r, const float* d_l, const float* d_r, int modified) {
+    const glava_b200_params& p = r->p;
+    int rc;
+    if (modified) {
+        SpectrumArgs a;
+        memset(&a, 0, sizeof(a));
+        a.pcm_l = d_l; a.pcm_r = d_r; a.window = r->d_window; a.twiddle = r->d_twiddle;
+        a.spec = r->d_spec; a.applied = r->d_applied; a.ring_f = r->d_ring_f;
+        a.gr_store = r->d_gr_store; a.ring_u = r->d_ring_u; a.tex = r->d_tex;
+        a.need = (p.lazy_smooth && r->d_need) ? r->d_need : nullptr; a.need_count = r->need_count;
+        a.batch = r->batch; a.update = r->updates;
+        const int F = p.avg_frames;
+        for (int f = 0; f < F; ++f) {
+            // pipeline A: window_frame(f, avg_frames - 1) -> cos(TWOPI*f/F - 1), double (render.c:661,766)
+            a.avg_w_a[f] = 0.6 - (0.4 * cos(6.28318530718 * (double) f / (double) F - 1));
+            // pipeline B: window(I, _AVG_FRAMES - 1) -> cos(TWOPI*I/F - 1), GLSL float (average_pass.frag:41)
+            a.avg_w_b[f] = 0.53836f - (0.46164f * cosf(6.28318530718f * (float) f / (float) F - 1.0f));
+        }
+        a.avg_b_windowed = (p.avg_window && F != 2) ? 1 : 0;
+        const bool is_fft = p.module != GLAVA_B200_MOD_WAVE;
+        if ((rc = launch_spectrum(p, a, is_fft, r->stream)) != 0) return rc;
+        ++r->launches; ++r->updates;
+    }
+    RasterArgs ra;
+    ra.tex = r->d_tex; ra.fb = r->d_fb; ra.rowtab = (p.module == GLAVA_B200_MOD_BARS) ? r->d_rowtab : nullptr;
+    ra.batch = r->batch; ra.slots = r->slots; ra.stream0 = 0;
+    if ((rc = launch_raster(p, ra, r->stream)) != 0) return rc;
+    r->launches += (uint64_t) ((r->batch + 32767) / 32768);
+    return 0;
+}
+
+int glava_b200_update(glava_b200* r, const float* lb, const float* rb, size_t bsz, int modified) {
+    clear_error();
+    if (!r || !lb) return fail(GLAVA_B200_EINVAL, "glava_b200_update: null argument");
+    if (bsz != (size_t) r->p.n) return fail(GLAVA_B200_EINVAL, "glava_b200_update: bsz %zu != setbufsize %d", bsz, r->p.n);
+    CU(cudaSetDevice(r->device));
+    size_t bytes = (size_t) r->batch * bsz * 4;
+    if (modified) {
+        CU(cudaMemcpyAsync(r->d_pcm[0], lb, bytes, cudaMemcpyHostToDevice, r->stream));
+        if (rb && r->p.module != GLAVA_B200_MOD_WAVE)
+            CU(cudaMemcpyAsync(r->d_pcm[1], rb, bytes, cudaMemcpyHostToDevice, r->stream));
+    }
+    return run_update(r, r->d_pcm[0], r->d_pcm[1], modified);
+}
+
+int glava_b200_update_device(glava_b200* r, const float* d_lb, const float* d_rb, size_t bsz, int modified) {
+    clear_error();
+    if (!r || !d_lb) return fail(GLAVA_B200_EINVAL, "glava_b200_update_device: null argument");
+    if (bsz != (size_t) r->p.n) return fail(GLAVA_B200_EINVAL, "glava_b200_update_device: bsz %zu != setbufsize %d", bsz, r->p.n);
+    if (((uintptr_t) d_lb & 15) || ((uintptr_t) d_rb & 15)) return fail(GLAVA_B200_EINVAL, "device PCM pointers must be 16-byte aligned");
+    CU(cudaSetDevice(r->device));
+    return run_update(r, d_lb, d_rb ? d_rb : d_lb, modified);
+}
+
+int glava_b200_ingest_fifo(glava_b200* r, const int16_t* chunks, int frames) {
+    clear_error();
+    if (!r || !chunks) return fail(GLAVA_B200_EINVAL, "glava_b200_ingest_fifo: null argument");
+    if (frames < 1 || frames > r->p.n) return fail(GLAVA_B200_EINVAL, "glava_b200_ingest_fifo: frames %d out of range", frames);
+    CU(cudaSetDevice(r->device));
+    size_t bytes = (size_t) r->batch * frames * 2 * sizeof(int16_t);
+    if (bytes > r->chunks_cap) {
+        if (r->d_chunks) cudaFree(r->d_chunks);
+        r->d_chunks = nullptr; r->chunks_cap = 0;
+        CU(cudaMalloc((void**) &r->d_chunks, bytes));
+        r->chunks_cap = bytes;
+    }
+    CU(cudaMemcpyAsync(r->d_chunks, chunks, bytes, cudaMemcpyHostToDevice, r->stream));
+    int cur = r->ring_cur, nxt = cur ^ 1;
+    int rc = launch_fifo_ingest(r->p, r->d_chunks, frames, r->d_ring[cur][0], r->d_ring[cur][1],
+                                r->d_ring[nxt][0], r->d_ring[nxt][1], r->batch, r->stream);
+    if (rc) return rc;
+    ++r->launches;
+    r->ring_cur = nxt;
+    return 0;
+}
+
+int glava_b200_update_rings(glava_b200* r, int modified) {
+    clear_error();
+    if (!r) return fail(GLAVA_B200_EINVAL, "null argument");
+    CU(cudaSetDevice(r->device));
+    return run_update(r, r->d_ring[r->ring_cur][0], r->d_ring[r->ring_cur][1], modified);
+}
+
+int glava_b200_sync(glava_b200* r) {
+    if (!r) return fail(GLAVA_B200_EINVAL, "null argument");
+    CU(cudaSetDevice(r->device));
+    CU(cudaStreamSynchronize(r->stream));
+    return 0;
+}
+
+int glava_b200_readback(glava_b200* r, int stream, uint8_t* rgba) {
+    clear_error();
+    if (!r || !rgba || stream < 0 || stream >= r->batch) return fail(GLAVA_B200_EINVAL, "glava_b200_readback: bad arguments");
+    CU(cudaSetDevice(r->device));
+    size_t frame = (size_t) r->p.w * r->p.h * 4;
+    CU(cudaMemcpyAsync(rgba, r->d_fb + frame * (size_t) (stream % r->slots), frame, cudaMemcpyDeviceToHost, r->stream));
+    CU(cudaStreamSynchronize(r->stream));
+    return 0;
+}
+
+static int planes_to_host(glava_b200* r, const void* d, size_t elem, void* out_l, void* out_r) {
+    // device layout [batch][2][n] -> two host arrays [batch][n]
+    const size_t row = (size_t) r->p.n * elem;
+    if (out_l) CU(cudaMemcpy2DAsync(out_l, row, d, 2 * row, row, (size_t) r->batch, cudaMemcpyDeviceToHost, r->stream));
+    if (out_r) CU(cudaMemcpy2DAsync(out_r, row, (const char*) d + row, 2 * row, row, (size_t) r->batch, cudaMemcpyDeviceToHost, r->stream));
+    CU(cudaStreamSynchronize(r->stream));
+    return 0;
+}
+int glava_b200_spectrum(glava_b200* r, float* out_l, float* out_r) {
+    clear_error();
+    if (!r) return fail(GLAVA_B200_EINVAL, "null argument");
+    CU(cudaSetDevice(r->device));
+    return planes_to_host(r, r->d_spec, 4, out_l, out_r);
+}
+int glava_b200_textures(glava_b200* r, uint16_t* out_l, uint16_t* out_r) {
+    clear_error();
+    if (!r) return fail(GLAVA_B200_EINVAL, "null argument");
+    CU(cudaSetDevice(r->device));
+    return planes_to_host(r, r->d_tex, 2, out_l, out_r);
+}
+
+int glava_b200_smooth_pass(glava_b200* r, const uint16_t* in, uint16_t* out, int count) {
+    clear_error();
+    if (!r || !in || !out || count < 1) return fail(GLAVA_B200_EINVAL, "glava_b200_smooth_pass: bad arguments");
+    CU(cudaSetDevice(r->device));
+    size_t bytes = (size_t) count * r->p.n * 2;
+    uint16_t* d_in = nullptr; uint16_t* d_out = nullptr;
+    CU(cudaMalloc((void**) &d_in, bytes));
+    cudaError_t e = cudaMalloc((void**) &d_out, bytes);
+    if (e != cudaSuccess) { cudaFree(d_in); return fail(GLAVA_B200_ECUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    int rc = 0;
+    do {
+        if (cudaMemcpyAsync(d_in, in, bytes, cudaMemcpyHostToDevice, r->stream) != cudaSuccess) { rc = fail(GLAVA_B200_ECUDA, "H2D copy failed"); break; }
+        if ((rc = launch_smooth_only(r->p, d_in, d_out, count, r->stream)) != 0) break;
+        ++r->launches;
+        if (cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, r->stream) != cudaSuccess) { rc = fail(GLAVA_B200_ECUDA, "D2H copy failed"); break; }
+        cudaError_t se = cudaStreamSynchronize(r->stream);
+        if (se != cudaSuccess) rc = fail(GLAVA_B200_ECUDA, "smooth pass: %s", cudaGetErrorString(se));
+    } while (0);
+    cudaFree(d_in); cudaFree(d_out);
+    return rc;
+}
+
+int glava_b200_raster_textures(glava_b200* r, const uint16_t* tex_l, const uint16_t* tex_r) {
+    clear_error();
+    if (!r || !tex_l) return fail(GLAVA_B200_EINVAL, "glava_b200_raster_textures: null argument");
+    CU(cudaSetDevice(r->device));
+    const size_t row = (size_t) r->p.n * 2;
+    CU(cudaMemcpy2DAsync(r->d_tex, 2 * row, tex_l, row, row, (size_t) r->batch, cudaMemcpyHostToDevice, r->stream));
+    if (tex_r) CU(cudaMemcpy2DAsync((char*) r->d_tex + row, 2 * row, tex_r, row, row, (size_t) r->batch, cudaMemcpyHostToDevice, r->stream));
+    return run_update(r, nullptr, nullptr, 0);
+}
+
+}  // extern "C"

@@ -1,0 +1,536 @@
+// config.cpp — the `#request` / `#define` configuration surface of the hot path.
+//
+// Mirrors, for this path only, what rd_new does with the entry file and the module
+// config (reference: glava/render.c:1033-1314 request table, :1322-1435 entry + CLI
+// requests; glava/glsl_ext.c:228-300 request argument parsing, :489-514 colour literals,
+// :516-591 `@name:default` pipe binds).  It is a line-oriented reader, not a GLSL
+// preprocessor: module shaders are CUDA kernels here, so only the values of the
+// documented `#define`s of <module>.glsl / smooth_parameters.glsl are extracted.
+#include "internal.h"
+
+#include <cctype>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+namespace glb {
+
+static const float kPI = 3.14159265359f, kTWOPI = 6.28318530718f;   // bars/1.frag:33-34 literals
+
+// ---- colour literals: "#rrggbb[aa]" -> the "%.6f" decimals glsl_ext.c:505 emits ------------
+static float hex_channel(unsigned v) {
+    char buf[32];
+    snprintf(buf, sizeof(buf), "%.6f", (double) ((float) v / (float) 255));
+    return strtof(buf, nullptr);
+}
+bool parse_hex_color(const char* s, float out[4], bool literal_rounding) {
+    if (s[0] == '#') ++s;
+    if (s[0] == '0' && (s[1] == 'x' || s[1] == 'X')) s += 2;             // glsl_ext.c:92-95
+    size_t len = strlen(s);
+    if (len > 8) len = 8;
+    unsigned comp[4] = { 0, 0, 0, 255 };
+    size_t ncomp = 0;
+    for (size_t i = 0; i + 2 <= len && ncomp < 4; i += 2) {
+        unsigned v = 0;
+        for (int k = 0; k < 2; ++k) {
+            char c = s[i + k]; unsigned d;
+            if (c >= '0' && c <= '9') d = (unsigned) (c - '0');
+            else if (c >= 'a' && c <= 'f') d = (unsigned) (c - 'a') + 10;
+            else if (c >= 'A' && c <= 'F') d = (unsigned) (c - 'A') + 10;
+            else return false;
+            v = v * 16 + d;
+        }
+        comp[ncomp++] = v;
+    }
+    for (int i = 0; i < 4; ++i) {
+        if ((size_t) i < ncomp || i == 3)
+            out[i] = literal_rounding ? hex_channel(comp[i]) : (float) comp[i] / (float) 255;
+        else out[i] = 0.0f;
+    }
+    if (ncomp < 4) out[3] = 1.0f;                                           // glsl_ext.c:503
+    return true;
+}
+
+// ---- defaults: the shipped rc.glsl / smooth_parameters.glsl / <module>.glsl ------------------
+static void hex3(float* o, unsigned r, unsigned g, unsigned b) {
+    o[0] = hex_channel(r); o[1] = hex_channel(g); o[2] = hex_channel(b); o[3] = 1.0f;
+}
+
+int module_from_name(const char* name) {
+    static const char* names[] = { "bars", "radial", "circle", "graph", "wave", "test" };
+    for (int i = 0; i < 6; ++i) if (!strcmp(name, names[i])) return i;
+    return -1;
+}
+const char* module_name(int id) {
+    static const char* names[] = { "bars", "radial", "circle", "graph", "wave", "test" };
+    return (id >= 0 && id < 6) ? names[id] : "?";
+}
+
+void fill_defaults(glava_b200_params* p, int module) {
+    memset(p, 0, sizeof(*p));
+    p->n = 4096; p->fft_scale = 10.2f; p->fft_cutoff = 0.3f; p->gravity_step = 4.2f;
+    p->rate_request = 22050; p->samplesize_request = 1024;
+    p->ur = (float) p->rate_request / (float) (p->samplesize_request / 4);
+    p->avg_frames = 5; p->avg_window = 1; p->accel_fft = 1; p->smooth_pass = 1;
+    p->smooth_factor = 0.025f; p->sample_range = 0.9f; p->sample_scale = 8.0f;
+    p->hybrid_weight = 0.65f; p->sample_mode = 0; p->round_formula = 0;
+    p->module = module; p->w = 800; p->h = 600; p->channels = 2; p->premultiply_alpha = 1;
+    p->bars_width = 5; p->bars_gap = 1; p->bars_outline_width = 1; p->bars_amplify = 300;
+    p->bars_color.mode = 0; hex3(p->bars_color.lo, 0x33, 0x66, 0xb2); hex3(p->bars_color.hi, 0xa0, 0xa0, 0xb2);
+    p->bars_color.gradient = 80; p->bars_outline_mode = 0;
+    p->radial_radius = 128; p->radial_line = 2; p->radial_line_half = 1; hex3(p->radial_outline, 0x33, 0x33, 0x33);
+    p->radial_nbars = 160; p->radial_bar_width = 4.5f; p->radial_amplify = 300;
+    p->radial_color.mode = 0; hex3(p->radial_color.lo, 0xcc, 0x33, 0x33); hex3(p->radial_color.hi, 0xcc, 0xa0, 0xa0);
+    p->radial_color.gradient = 95; p->radial_rotate = kPI / 2; p->radial_bar_alias = 1.2f; p->radial_c_alias = 1.8f;
+    p->circle_radius = 128; p->circle_line = 1.5f; hex3(p->circle_outline, 0x33, 0x33, 0x33);
+    p->circle_amplify = 150; p->circle_rotate = kPI / 2; p->circle_smooth = 1;
+    p->graph_vscale = 300; p->graph_direction = 1;
+    p->graph_color.mode = 0; hex3(p->graph_color.lo, 0x80, 0x2a, 0x2a); hex3(p->graph_color.hi, 0x4f, 0x4f, 0x92);
+    p->graph_color.gradient = 75; p->graph_draw_highlight = 1; hex3(p->graph_outline, 0x26, 0x26, 0x26);
+    p->wave_min_thickness = 1; p->wave_max_thickness = 6; p->wave_amplify = 500;
+    p->wave_base_color[0] = 0.7f; p->wave_base_color[1] = 0.2f; p->wave_base_color[2] = 0.45f; p->wave_base_color[3] = 1;
+    p->wave_outline[0] = p->wave_outline[1] = p->wave_outline[2] = 0.15f; p->wave_outline[3] = 1;
+    p->fb_slots = 0; p->lazy_smooth = 0;
+}
+
+// ---- tiny expression evaluator for numeric #defines: + - * / ( ) literals PI TWOPI ---------
+struct Num { double v; bool is_int; };
+struct ExprParser {
+    const char* s; const std::map<std::string, std::string>* defs; int depth; bool ok;
+    void ws() { while (*s && isspace((unsigned char) *s)) ++s; }
+    Num primary() {
+        ws();
+        if (*s == '(') { ++s; Num r = expr(); ws(); if (*s == ')') ++s; else ok = false; return r; }
+        if (*s == '-') { ++s; Num r = primary(); r.v = -r.v; return r; }
+        if (*s == '+') { ++s; return primary(); }
+        if (isdigit((unsigned char) *s) || *s == '.') {
+            char* end; double v = strtod(s, &end);
+            bool is_int = true;
+            for (const char* c = s; c < end; ++c) if (*c == '.' || *c == 'e' || *c == 'E') is_int = false;
+            s = end;
+            if (*s == 'f' || *s == 'F') { ++s; is_int = false; }
+            if (!is_int) v = (double) (float) v;                            // GLSL float literal
+            return { v, is_int };
+        }
+        if (isalpha((unsigned char) *s) || *s == '_') {
+            std::string id;
+            while (isalnum((unsigned char) *s) || *s == '_') id += *s++;
+            if (id == "PI") return { (double) kPI, false };
+            if (id == "TWOPI") return { (double) kTWOPI, false };
+            if (id == "float" || id == "int") { Num r = primary(); if (id == "float") r.is_int = false; return r; }
+            auto it = defs ? defs->find(id) : decltype(defs->end())();
+            if (defs && it != defs->end() && depth < 8) {
+                ExprParser sub { it->second.c_str(), defs, depth + 1, true };
+                Num r = sub.expr(); sub.ws();
+                if (!sub.ok || *sub.s) ok = false;
+                return r;
+            }
+        }
+        ok = false; return { 0, true };
+    }
+    Num term() {
+        Num a = primary();
+        for (;;) {
+            ws();
+            if (*s == '*') { ++s; Num b = primary(); bool i = a.is_int && b.is_int;
+                a = { i ? (double) ((long) a.v * (long) b.v) : (double) ((float) a.v * (float) b.v), i }; }
+            else if (*s == '/') { ++s; Num b = primary(); bool i = a.is_int && b.is_int;
+                if (i) { if ((long) b.v == 0) { ok = false; return a; } a = { (double) ((long) a.v / (long) b.v), true }; }
+                else a = { (double) ((float) a.v / (float) b.v), false }; }
+            else return a;
+        }
+    }
+    Num expr() {
+        Num a = term();
+        for (;;) {
+            ws();
+            if (*s == '+') { ++s; Num b = term(); bool i = a.is_int && b.is_int;
+                a = { i ? a.v + b.v : (double) ((float) a.v + (float) b.v), i }; }
+            else if (*s == '-') { ++s; Num b = term(); bool i = a.is_int && b.is_int;
+                a = { i ? a.v - b.v : (double) ((float) a.v - (float) b.v), i }; }
+            else return a;
+        }
+    }
+};
+
+typedef std::map<std::string, std::string> Defs;
+
+static bool eval_num(const Defs& d, const char* name, Num* out) {
+    auto it = d.find(name);
+    if (it == d.end()) return false;
+    ExprParser p { it->second.c_str(), &d, 0, true };
+    Num r = p.expr(); p.ws();
+    if (!p.ok || *p.s) {
+        fail(GLAVA_B200_ECONFIG, "cannot evaluate '#define %s %s' as a number", name, it->second.c_str());
+        return false;
+    }
+    *out = r; return true;
+}
+static void getf(const Defs& d, const char* name, float* dst) { Num n; if (eval_num(d, name, &n)) *dst = (float) n.v; }
+static void geti(const Defs& d, const char* name, int* dst) { Num n; if (eval_num(d, name, &n)) *dst = (int) n.v; }
+
+// strip `@name:` pipe-bind prefix -> its default (glsl_ext.c:571-587 when no --pipe bind exists)
+static std::string strip_bind(const std::string& v) {
+    size_t i = 0; while (i < v.size() && isspace((unsigned char) v[i])) ++i;
+    if (i < v.size() && v[i] == '@') {
+        size_t c = v.find(':', i);
+        if (c != std::string::npos) return v.substr(c + 1);
+    }
+    return v.substr(i);
+}
+static std::string trim(const std::string& s) {
+    size_t a = 0, b = s.size();
+    while (a < b && isspace((unsigned char) s[a])) ++a;
+    while (b > a && isspace((unsigned char) s[b - 1])) --b;
+    return s.substr(a, b - a);
+}
+// split "f(a, b(c, d), e)" argument list at top-level commas
+static bool split_call(const std::string& s, const char* fn, std::vector<std::string>* args) {
+    std::string t = trim(s);
+    size_t fl = strlen(fn);
+    if (t.compare(0, fl, fn) != 0) return false;
+    size_t i = fl; while (i < t.size() && isspace((unsigned char) t[i])) ++i;
+    if (i >= t.size() || t[i] != '(' || t.back() != ')') return false;
+    std::string inner = t.substr(i + 1, t.size() - i - 2);
+    int depth = 0; std::string cur;
+    for (char c : inner) {
+        if (c == '(') ++depth;
+        if (c == ')') --depth;
+        if (c == ',' && depth == 0) { args->push_back(trim(cur)); cur.clear(); } else cur += c;
+    }
+    if (depth != 0) return false;
+    args->push_back(trim(cur));
+    return true;
+}
+static bool parse_const_color(const Defs& d, const std::string& s, float out[4]) {
+    std::string t = trim(s);
+    if (!t.empty() && t[0] == '#') return parse_hex_color(t.c_str(), out, true);
+    std::vector<std::string> a;
+    if (split_call(t, "vec4", &a) && a.size() == 4) {
+        for (int i = 0; i < 4; ++i) {
+            ExprParser p { a[i].c_str(), &d, 0, true };
+            Num n = p.expr(); p.ws();
+            if (!p.ok || *p.s) return false;
+            out[i] = (float) n.v;
+        }
+        return true;
+    }
+    return false;
+}
+// COLOR forms understood: constant colour | mix(<colour>, <colour>, clamp(<var> / <num>, 0, 1))
+static bool parse_color_macro(const Defs& d, const char* name, glava_b200_color* c) {
+    auto it = d.find(name);
+    if (it == d.end()) return true;
+    std::string v = strip_bind(it->second);
+    float k[4];
+    if (parse_const_color(d, v, k)) { c->mode = 1; memcpy(c->lo, k, sizeof(k)); memcpy(c->hi, k, sizeof(k)); return true; }
+    std::vector<std::string> a, b;
+    if (split_call(v, "mix", &a) && a.size() == 3 && parse_const_color(d, a[0], c->lo) && parse_const_color(d, a[1], c->hi)
+        && split_call(a[2], "clamp", &b) && b.size() == 3) {
+        size_t slash = b[0].find('/');
+        if (slash != std::string::npos) {
+            ExprParser p { b[0].c_str() + slash + 1, &d, 0, true };
+            Num n = p.expr(); p.ws();
+            if (p.ok && !*p.s) { c->mode = 0; c->gradient = (float) n.v; return true; }
+        }
+    }
+    fail(GLAVA_B200_ECONFIG, "unsupported colour expression in '#define %s %s' (supported: #rrggbb[aa], vec4(..), "
+         "mix(<colour>, <colour>, clamp(<x> / <n>, 0, 1)))", name, it->second.c_str());
+    return false;
+}
+static bool parse_plain_color(const Defs& d, const char* name, float out[4]) {
+    auto it = d.find(name);
+    if (it == d.end()) return true;
+    if (parse_const_color(d, strip_bind(it->second), out)) return true;
+    fail(GLAVA_B200_ECONFIG, "unsupported colour expression in '#define %s %s'", name, it->second.c_str());
+    return false;
+}
+
+// ---- file reading ---------------------------------------------------------------------------
+static bool read_file(const std::string& path, std::string* out) {
+    std::ifstream f(path.c_str(), std::ios::binary);
+    if (!f) return false;
+    std::stringstream ss; ss << f.rdbuf(); *out = ss.str();
+    return true;
+}
+// remove /* */ and // comments, keep newlines
+static std::string strip_comments(const std::string& in) {
+    std::string o; o.reserve(in.size());
+    for (size_t i = 0; i < in.size();) {
+        if (in[i] == '/' && i + 1 < in.size() && in[i + 1] == '*') {
+            i += 2;
+            while (i + 1 < in.size() && !(in[i] == '*' && in[i + 1] == '/')) { if (in[i] == '\n') o += '\n'; ++i; }
+            i += 2;
+        } else if (in[i] == '/' && i + 1 < in.size() && in[i + 1] == '/') {
+            while (i < in.size() && in[i] != '\n') ++i;
+        } else o += in[i++];
+    }
+    return o;
+}
+// tokens of a request line: whitespace separated, "quoted strings" kept whole (glsl_ext.c:228-300)
+static std::vector<std::string> tokenize(const std::string& line) {
+    std::vector<std::string> t; std::string cur; bool q = false, have = false;
+    for (char c : line) {
+        if (q) { if (c == '"') { q = false; } else cur += c; continue; }
+        if (c == '"') { q = true; have = true; continue; }
+        if (isspace((unsigned char) c)) { if (have) { t.push_back(cur); cur.clear(); have = false; } continue; }
+        cur += c; have = true;
+    }
+    if (have) t.push_back(cur);
+    return t;
+}
+
+static bool parse_bool(const std::string& s, bool* v) {                     // glsl_ext.c:266-288
+    if (s == "true" || s == "t" || s == "1") { *v = true; return true; }
+    if (s == "false" || s == "f" || s == "0") { *v = false; return true; }
+    return false;
+}
+
+struct Loader {
+    glava_b200_params* p;
+    std::string module;        // `#request mod`
+    bool module_forced;
+    bool failed;
+};
+
+// returns false on error (message already reported)
+static bool apply_request(Loader& L, const std::vector<std::string>& t, const char* where, int line) {
+    if (t.empty()) return true;
+    const std::string& name = t[0];
+    auto need = [&](size_t n) -> bool {
+        if (t.size() < 1 + n) {
+            fail(GLAVA_B200_ECONFIG, "[%s:%d] failed to execute request '%s': expected %d argument(s)", where, line,
+                 name.c_str(), (int) n);
+            return false;
+        }
+        return true;
+    };
+    auto as_int = [&](size_t i) { return (int) strtol(t[i].c_str(), nullptr, 0); };
+    auto as_f   = [&](size_t i) { return strtof(t[i].c_str(), nullptr); };
+    auto as_b   = [&](size_t i, bool* v) -> bool {
+        if (parse_bool(t[i], v)) return true;
+        fail(GLAVA_B200_ECONFIG, "[%s:%d] tried to parse invalid raw string into a boolean", where, line);
+        return false;
+    };
+    glava_b200_params* p = L.p;
+    bool b;
+    if (name == "mod") { if (!need(1)) return false; if (!L.module_forced) L.module = t[1]; }
+    else if (name == "setmirror") { if (!need(1) || !as_b(1, &b)) return false; p->channels = b ? 1 : 2; }
+    else if (name == "setopacity") {
+        if (!need(1)) return false;
+        if (t[1] == "native") p->premultiply_alpha = 1;
+        else if (t[1] == "xroot" || t[1] == "none") p->premultiply_alpha = 0;
+        else { fail(GLAVA_B200_ECONFIG, "Invalid opacity option: '%s'", t[1].c_str()); return false; }   // render.c:1047-1050
+    }
+    else if (name == "setgeometry") { if (!need(4)) return false; p->w = as_int(3); p->h = as_int(4); }
+    else if (name == "setbufsize") { if (!need(1)) return false; p->n = as_int(1); }
+    else if (name == "setsamplerate") { if (!need(1)) return false; p->rate_request = as_int(1); }
+    else if (name == "setsamplesize") { if (!need(1)) return false; p->samplesize_request = as_int(1); }
+    else if (name == "setaccelfft") { if (!need(1) || !as_b(1, &b)) return false; p->accel_fft = b; }
+    else if (name == "setavgframes") { if (!need(1)) return false; p->avg_frames = as_int(1); }
+    else if (name == "setavgwindow") { if (!need(1) || !as_b(1, &b)) return false; p->avg_window = b; }
+    else if (name == "setgravitystep") { if (!need(1)) return false; p->gravity_step = as_f(1); }
+    else if (name == "setsmoothpass") { if (!need(1) || !as_b(1, &b)) return false; p->smooth_pass = b; }
+    else if (name == "setsmoothfactor") { if (!need(1)) return false; p->smooth_factor = as_f(1); }
+    else if (name == "setfftscale") { if (!need(1)) return false; p->fft_scale = as_f(1); }
+    else if (name == "setfftcutoff") { if (!need(1)) return false; p->fft_cutoff = as_f(1); }
+    else if (name == "setbufscale") {
+        if (!need(1)) return false;
+        if (as_int(1) > 1) { fail(GLAVA_B200_ECONFIG, "setbufscale > 1 (deprecated in the reference) is not supported"); return false; }
+    }
+    else if (name == "setinterpolate") {
+        // CPU keyframe interpolation is force-disabled by the reference whenever accel_fft is
+        // active (render.c:2161-2168) and is off in the shipped rc.glsl:131; not implemented.
+        if (!need(1) || !as_b(1, &b)) return false;
+    }
+    else if (name == "setbg" || name == "setbgf") {
+        // clear colour: every module stage writes every pixel, so the clear never shows (blending
+        // is off in native mode, render.c:1467-1470).  Accepted and ignored.
+    }
+    else {
+        // window / desktop / pacing requests of the reference that have no meaning on this path
+        static const char* ignored[] = { "setfloating", "setdecorated", "setfocused", "setmaximized", "setversion",
+            "setshaderversion", "settitle", "setxwintype", "addxwinstate", "setclickthrough", "setsource", "setswap",
+            "setframerate", "setfullscreencheck", "setprintframes", "setforcegeometry", "setforceraised",
+            "setfullscreencheck", "timecycle", "settesteval", "setsmooth", "setsmoothratio", "nativeonly",
+            "uniform", "transform", nullptr };
+        bool known = false;
+        for (int i = 0; ignored[i]; ++i) if (name == ignored[i]) known = true;
+        if (!known) {
+            fail(GLAVA_B200_ECONFIG, "[%s:%d] unknown request type '%s'", where, line, name.c_str());   // glsl_ext.c:299
+            return false;
+        }
+    }
+    return true;
+}
+
+// scan a config file: dispatch `#request`s, collect `#define`s (later definitions override,
+// the effect of glsl_ext.c:143-159's auto-#undef)
+static bool scan_file(Loader& L, const std::string& path, Defs* defs, bool requests) {
+    std::string src;
+    if (!read_file(path, &src)) return true;      // optional file
+    src = strip_comments(src);
+    std::istringstream is(src);
+    std::string line; int ln = 0;
+    while (std::getline(is, line)) {
+        ++ln;
+        std::string t = trim(line);
+        if (t.empty() || t[0] != '#') continue;
+        std::string body = trim(t.substr(1));
+        if (body.compare(0, 7, "request") == 0 && requests) {
+            if (!apply_request(L, tokenize(body.substr(7)), path.c_str(), ln)) return false;
+        } else if (body.compare(0, 6, "define") == 0 && defs) {
+            std::string rest = trim(body.substr(6));
+            size_t i = 0; while (i < rest.size() && (isalnum((unsigned char) rest[i]) || rest[i] == '_')) ++i;
+            if (i == 0) continue;
+            if (i < rest.size() && rest[i] == '(') continue;   // function-like macro: not a setting
+            (*defs)[rest.substr(0, i)] = trim(rest.substr(i));
+        }
+    }
+    return true;
+}
+
+static bool file_exists(const std::string& p) { std::ifstream f(p.c_str()); return (bool) f; }
+
+static void apply_defines(glava_b200_params* p, const Defs& d) {
+    // smooth_parameters.glsl
+    auto it = d.find("ROUND_FORMULA");
+    if (it != d.end()) {
+        if (it->second == "sinusoidal") p->round_formula = 0; else if (it->second == "linear") p->round_formula = 1;
+        else if (it->second == "circular") p->round_formula = 2;
+        else fail(GLAVA_B200_ECONFIG, "unknown ROUND_FORMULA '%s'", it->second.c_str());
+    }
+    it = d.find("SAMPLE_MODE");
+    if (it != d.end()) {
+        if (it->second == "average") p->sample_mode = 0; else if (it->second == "maximum") p->sample_mode = 1;
+        else if (it->second == "hybrid") p->sample_mode = 2;
+        else fail(GLAVA_B200_ECONFIG, "unknown SAMPLE_MODE '%s'", it->second.c_str());
+    }
+    getf(d, "SAMPLE_SCALE", &p->sample_scale); getf(d, "SAMPLE_RANGE", &p->sample_range);
+    getf(d, "SAMPLE_HYBRID_WEIGHT", &p->hybrid_weight);
+    Num n;
+    switch (p->module) {
+        case GLAVA_B200_MOD_BARS:
+            getf(d, "BAR_WIDTH", &p->bars_width); getf(d, "BAR_GAP", &p->bars_gap);
+            getf(d, "BAR_OUTLINE_WIDTH", &p->bars_outline_width); getf(d, "AMPLIFY", &p->bars_amplify);
+            parse_color_macro(d, "COLOR", &p->bars_color);
+            if (p->bars_color.mode == 0 && eval_num(d, "GRADIENT", &n)) p->bars_color.gradient = (float) n.v;
+            if ((it = d.find("BAR_OUTLINE")) != d.end()) {
+                std::string v = strip_bind(it->second);
+                std::string squeezed; for (char c : v) if (!isspace((unsigned char) c)) squeezed += c;
+                if (squeezed == "vec4(COLOR.rgb*1.5,COLOR.a)") p->bars_outline_mode = 0;
+                else if (parse_const_color(d, v, p->bars_outline)) p->bars_outline_mode = 1;
+                else fail(GLAVA_B200_ECONFIG, "unsupported '#define BAR_OUTLINE %s'", it->second.c_str());
+            }
+            geti(d, "DIRECTION", &p->bars_direction); geti(d, "INVERT", &p->bars_invert);
+            geti(d, "FLIP", &p->bars_flip); geti(d, "MIRROR_YX", &p->bars_mirror_yx);
+            { int dm = 0; geti(d, "DISABLE_MONO", &dm); if (dm == 1) p->channels = 2; }          // bars/1.frag:36-38
+            break;
+        case GLAVA_B200_MOD_RADIAL:
+            getf(d, "C_RADIUS", &p->radial_radius);
+            if (eval_num(d, "C_LINE", &n)) {
+                p->radial_line = (float) n.v;
+                p->radial_line_half = n.is_int ? (float) ((long) n.v / 2) : (float) n.v / 2.0f;   // radial/1.frag:52 (C_LINE / 2)
+            }
+            parse_plain_color(d, "OUTLINE", p->radial_outline);
+            geti(d, "NBARS", &p->radial_nbars); getf(d, "BAR_WIDTH", &p->radial_bar_width);
+            getf(d, "AMPLIFY", &p->radial_amplify);
+            parse_color_macro(d, "COLOR", &p->radial_color);
+            if (p->radial_color.mode == 0 && eval_num(d, "GRADIENT", &n)) p->radial_color.gradient = (float) n.v;
+            getf(d, "ROTATE", &p->radial_rotate); geti(d, "INVERT", &p->radial_invert);
+            getf(d, "BAR_ALIAS_FACTOR", &p->radial_bar_alias); getf(d, "C_ALIAS_FACTOR", &p->radial_c_alias);
+            getf(d, "CENTER_OFFSET_X", &p->radial_off_x); getf(d, "CENTER_OFFSET_Y", &p->radial_off_y);
+            if (eval_num(d, "BAR_OUTLINE_WIDTH", &n) && n.v > 0)
+                fail(GLAVA_B200_ECONFIG, "radial: BAR_OUTLINE_WIDTH > 0 (deprecated, radial.glsl:33-36) is not supported");
+            break;
+        case GLAVA_B200_MOD_CIRCLE:
+            getf(d, "C_RADIUS", &p->circle_radius); getf(d, "C_LINE", &p->circle_line);
+            parse_plain_color(d, "OUTLINE", p->circle_outline);
+            getf(d, "AMPLIFY", &p->circle_amplify); getf(d, "ROTATE", &p->circle_rotate);
+            geti(d, "INVERT", &p->circle_invert); geti(d, "C_FILL", &p->circle_fill); geti(d, "C_SMOOTH", &p->circle_smooth);
+            break;
+        case GLAVA_B200_MOD_GRAPH:
+            getf(d, "VSCALE", &p->graph_vscale); geti(d, "DIRECTION", &p->graph_direction);
+            parse_color_macro(d, "COLOR", &p->graph_color);
+            if (p->graph_color.mode == 0 && eval_num(d, "GRADIENT", &n)) p->graph_color.gradient = (float) n.v;
+            geti(d, "DRAW_OUTLINE", &p->graph_draw_outline); geti(d, "DRAW_HIGHLIGHT", &p->graph_draw_highlight);
+            parse_plain_color(d, "OUTLINE", p->graph_outline); geti(d, "INVERT", &p->graph_invert);
+            if (eval_num(d, "ANTI_ALIAS", &n) && n.v != 0) fail(GLAVA_B200_ECONFIG, "graph: ANTI_ALIAS 1 (graph/3.frag) is not supported");
+            if (eval_num(d, "JOIN_CHANNELS", &n) && n.v != 0) fail(GLAVA_B200_ECONFIG, "graph: JOIN_CHANNELS 1 is not supported");
+            break;
+        case GLAVA_B200_MOD_WAVE:
+            getf(d, "MIN_THICKNESS", &p->wave_min_thickness); getf(d, "MAX_THICKNESS", &p->wave_max_thickness);
+            parse_plain_color(d, "BASE_COLOR", p->wave_base_color); getf(d, "AMPLIFY", &p->wave_amplify);
+            parse_plain_color(d, "OUTLINE", p->wave_outline);
+            break;
+        default: break;
+    }
+}
+
+int load_config(glava_b200_params* out, const char* const* paths, const char* entry,
+                const char* const* requests, const char* force_module) {
+    clear_error();
+    fill_defaults(out, GLAVA_B200_MOD_BARS);
+    Loader L { out, "bars", false, false };
+    if (force_module) { L.module = force_module; L.module_forced = true; }
+    std::vector<std::string> dirs;
+    if (paths) for (int i = 0; paths[i]; ++i) dirs.push_back(paths[i]);
+    if (!entry) entry = "rc.glsl";
+    // entry: first directory that has it (render.c:1322-1413)
+    std::string entry_dir;
+    for (auto& d : dirs) if (file_exists(d + "/" + entry)) { entry_dir = d; break; }
+    if (!dirs.empty() && entry_dir.empty()) {
+        fail(GLAVA_B200_ECONFIG, "Could not find entry point '%s' in any of the configuration paths", entry);
+        return GLAVA_B200_ECONFIG;
+    }
+    if (!entry_dir.empty() && !scan_file(L, entry_dir + "/" + entry, nullptr, true)) return GLAVA_B200_ECONFIG;
+    if (requests) {
+        for (int i = 0; requests[i]; ++i) {                                   // render.c:1415-1435
+            std::string r = requests[i];
+            if (!apply_request(L, tokenize(r), "--request", i + 1)) return GLAVA_B200_ECONFIG;
+        }
+    }
+    int mod = module_from_name(L.module.c_str());
+    if (mod < 0) {
+        fail(GLAVA_B200_ECONFIG, "Could not find module '%s' (B200 path implements: bars radial circle graph wave test)", L.module.c_str());
+        return GLAVA_B200_ECONFIG;
+    }
+    out->module = mod;
+    // `#include "@x.glsl"` then `#include ":x.glsl"` (e.g. bars/1.frag:9-10): defaults dir first,
+    // user dir second and winning.  dirs[] is user-first like glava.c:301, so walk it backwards.
+    Defs defs;
+    for (int i = (int) dirs.size() - 1; i >= 0; --i) {
+        if (!scan_file(L, dirs[i] + "/smooth_parameters.glsl", &defs, true)) return GLAVA_B200_ECONFIG;
+        if (!scan_file(L, dirs[i] + "/" + L.module + ".glsl", &defs, true)) return GLAVA_B200_ECONFIG;
+    }
+    // CLI requests are applied last in the reference too (after module load they would hit
+    // `loading_smooth_pass` guards); re-apply so they win over smooth_parameters.glsl.
+    if (requests) for (int i = 0; requests[i]; ++i) apply_request(L, tokenize(requests[i]), "--request", i + 1);
+    apply_defines(out, defs);
+    if (has_error()) return GLAVA_B200_ECONFIG;
+    out->ur = (float) out->rate_request / (float) (out->samplesize_request / 4);
+    return validate_params(out);
+}
+
+int validate_params(const glava_b200_params* p) {
+    auto bad = [&](const char* what) { fail(GLAVA_B200_EINVAL, "invalid parameter: %s", what); return GLAVA_B200_EINVAL; };
+    if (p->n < 256 || p->n > 16384 || (p->n & (p->n - 1))) return bad("setbufsize must be a power of two in [256, 16384]");
+    if (p->avg_frames < 1 || p->avg_frames > 16) return bad("setavgframes must be in [1, 16]");
+    if (p->w < 4 || p->h < 1 || p->w > 16384 || p->h > 16384) return bad("geometry");
+    if (p->module < 0 || p->module > GLAVA_B200_MOD_TEST) return bad("module");
+    if (!(p->ur > 0.0f)) return bad("ur must be > 0");
+    if (p->channels != 1 && p->channels != 2) return bad("channels");
+    if (p->sample_mode < 0 || p->sample_mode > 2 || p->round_formula < 0 || p->round_formula > 2) return bad("sample mode / round formula");
+    if (p->radial_nbars < 2) return bad("NBARS");
+    if (!(p->bars_width + p->bars_gap > 0.0f)) return bad("BAR_WIDTH + BAR_GAP");
+    return GLAVA_B200_OK;
+}
+
+}  // namespace glb

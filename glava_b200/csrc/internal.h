@@ -1,0 +1,69 @@
+// internal.h — shared declarations of libglava_b200 (host side + kernel launchers).
+#ifndef GLAVA_B200_INTERNAL_H
+#define GLAVA_B200_INTERNAL_H
+
+#include "../../include/glava_b200.h"
+
+#include <cstddef>
+#include <cstdint>
+
+namespace glb {
+
+// error reporting: stores the message, calls the abort hook (glava.h:17 analogue), returns `code`
+int  fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+void clear_error();
+bool has_error();
+
+// config.cpp
+void fill_defaults(glava_b200_params* p, int module);
+int  module_from_name(const char* name);
+const char* module_name(int id);
+bool parse_hex_color(const char* s, float out[4], bool literal_rounding);
+int  load_config(glava_b200_params* out, const char* const* paths, const char* entry,
+                 const char* const* requests, const char* force_module);
+int  validate_params(const glava_b200_params* p);
+
+#define GLB_MAX_AVG_FRAMES 16
+
+// ---- views handed to the kernels (all pointers are DEVICE pointers) ---------------------------
+// "channel plane" c = stream * 2 + ch (ch 0 = left, 1 = right); every per-channel array is
+// [batch*2][...] so one CTA of the spectrum kernel owns one contiguous plane.
+struct SpectrumArgs {
+    const float*  pcm_l;        // [batch][n]   ring contents, oldest first (glava.c:528-537 lb)
+    const float*  pcm_r;        // [batch][n]
+    const double* window;       // [n]          render.c:660,794 window LUT (double, as the macro evaluates)
+    const float*  twiddle;      // [n/2][2]     exp(-2*pi*i*k/(n/2)) as (re, im)
+    float*    spec;             // [batch*2][n] pipeline-A result, or raw transform_fft output (accel)
+    float*    applied;          // [batch*2][n] transform_gravity state (A), render.c:725
+    float*    ring_f;           // [batch*2][F][n] transform_average ring (A), slot = update index % F
+    uint16_t* gr_store;         // [batch*2][n] (B) render.c:2197
+    uint16_t* ring_u;           // [batch*2][F][n] (B) gr->out[], render.c:2232
+    uint16_t* tex;              // [batch*2][n] R16 texture the module samples
+    const int* need;            // lazy K5: texel indices to evaluate, nullptr = all n
+    int       need_count;
+    int       batch;
+    unsigned long long update;  // number of modified updates before this one (ring cursor)
+    double    avg_w_a[GLB_MAX_AVG_FRAMES];   // pipeline A weights, oldest first (render.c:661,766)
+    float     avg_w_b[GLB_MAX_AVG_FRAMES];   // pipeline B weights, newest first (average_pass.frag:41)
+    int       avg_b_windowed;                // average_pass.frag:27-29,38-42
+};
+
+struct RasterArgs {
+    const uint16_t* tex;        // [batch*2][n]
+    uint8_t*  fb;               // [slots][h][w][4]
+    const void* rowtab;         // module row table (bars: [h] {fill, outline} RGBA8 pairs), may be null
+    int       batch, slots, stream0;
+};
+
+// ---- kernel launchers (kernels.cu); `stream` is a cudaStream_t passed as void* ------------------
+int launch_spectrum(const glava_b200_params& p, const SpectrumArgs& a, bool is_fft, void* stream);
+int launch_smooth_only(const glava_b200_params& p, const uint16_t* d_in, uint16_t* d_out, int count, void* stream);
+int launch_raster(const glava_b200_params& p, const RasterArgs& a, void* stream);
+int launch_bars_rowtab(const glava_b200_params& p, void* d_rowtab, void* stream);
+int launch_fifo_ingest(const glava_b200_params& p, const int16_t* d_chunks, int frames, const float* src_l, const float* src_r,
+                       float* dst_l, float* dst_r, int batch, void* stream);
+int spectrum_smem_bytes(int n);
+
+}  // namespace glb
+
+#endif

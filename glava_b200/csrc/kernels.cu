@@ -1,0 +1,447 @@
+// kernels.cu — sm_100a kernels of the PCM -> spectrum -> pixels path.
+//
+//   spectrum_kernel   one CTA per (stream, channel): TMA bulk load of the PCM ring into shared
+//                     memory, window, (N/2)-point Stockham FFT in shared memory, |.|/log/ramp,
+//                     gravity + average (pipeline A float state or pipeline B R16 state in HBM),
+//                     K5 smoothing out of shared memory -> R16 texture.        [replaces render.c
+//                     transform_fft/gravity/average + util/{pass,gravity_pass,average_pass,
+//                     smooth_pass}.frag + 5 GL draws and 1 glTexImage1D per channel per frame]
+//   raster_*_kernel   one module frame per stream straight into the HBM framebuffer with 128-bit
+//                     streaming stores, all post stages fused.     [replaces the module .frag stages]
+//
+// Compiled with --fmad=false: results are bit-identical to the host build of the *_core.h maths.
+#include "internal.h"
+#include "raster_core.h"
+
+#include <cuda_runtime.h>
+
+namespace glb {
+
+// ---------------------------------------------------------------------------------------------
+// small PTX wrappers: mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n WAIT_%=:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// spectrum kernel
+template <int LOG2N> struct SpecCfg {
+    static constexpr int N = 1 << LOG2N, M = N / 2;
+    static constexpr int T = (M / 8 < 128) ? 128 : ((M / 8 > 512) ? 512 : M / 8);
+    static constexpr int BUF_CPX = fft_padded_size(M);
+    // cpx buffer (also the raw-PCM staging area, N floats = M cpx) | u16 av[N] | mbarrier
+    static constexpr int OFF_AV  = ((BUF_CPX * 8 + 15) / 16) * 16;
+    static constexpr int OFF_BAR = OFF_AV + N * 2;
+    static constexpr int SMEM    = OFF_BAR + 16;
+};
+
+template <int M, int T, int NS, class Loader>
+__device__ __forceinline__ void run_passes(cpx* buf, Loader first_loader, const cpx* __restrict__ tw, int tid) {
+    constexpr int REM = M / NS;                      // points still to be combined
+    if constexpr (REM > 1) {
+        constexpr int R = (REM >= 8) ? 8 : REM;      // 8, 8, ..., then 4 or 2
+        using Pass = StockhamPass<M, T, R, NS>;
+        cpx reg[Pass::PER][R];
+        if constexpr (NS == 1) Pass::load(first_loader, tw, tid, reg);
+        else Pass::load([buf](int i) { return buf[fft_pad(i)]; }, tw, tid, reg);
+        __syncthreads();
+        Pass::store(buf, tid, reg);
+        __syncthreads();
+        run_passes<M, T, NS * R>(buf, first_loader, tw, tid);
+    }
+}
+
+extern __shared__ __align__(16) unsigned char glb_smem[];
+
+template <int LOG2N, bool IS_FFT>
+__global__ void __launch_bounds__(SpecCfg<LOG2N>::T)
+spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ glava_b200_params p) {
+    using C = SpecCfg<LOG2N>;
+    constexpr int N = C::N, M = C::M, T = C::T;
+    const int tid = threadIdx.x;
+    const int c = blockIdx.x, stream = c >> 1, ch = c & 1;
+    if (!IS_FFT && ch == 1) return;                  // wave binds audio_l only (wave/1.frag:7)
+
+    cpx*      buf = reinterpret_cast<cpx*>(glb_smem);
+    float*    raw = reinterpret_cast<float*>(glb_smem);
+    uint16_t* av  = reinterpret_cast<uint16_t*>(glb_smem + C::OFF_AV);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(glb_smem + C::OFF_BAR);
+
+    // --- stage the PCM ring of this (stream, channel): one bulk async copy, N*4 bytes -------------
+    const float* pcm = (ch == 0 ? a.pcm_l : a.pcm_r) + (size_t) stream * N;
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) { mbar_expect_tx(bar, N * 4); bulk_g2s(raw, pcm, N * 4, bar); }
+    mbar_wait(bar, 0);
+
+    const size_t plane = (size_t) c * N;
+    const int F = p.avg_frames;
+
+    if constexpr (IS_FFT) {
+        // --- window (render.c:793-795: float * double -> float) folded into the first pass loads ----
+        const double2* w2 = reinterpret_cast<const double2*>(a.window);
+        auto first = [raw, w2](int i) {
+            float2 v = reinterpret_cast<const float2*>(raw)[i];
+            double2 w = __ldg(&w2[i]);
+            cpx r = { (float) ((double) v.x * w.x), (float) ((double) v.y * w.y) };
+            return r;
+        };
+        run_passes<M, T, 1>(buf, first, reinterpret_cast<const cpx*>(a.twiddle), tid);
+
+        if (!p.accel_fft) {
+            // --- pipeline A: render.c:2149-2156 --------------------------------------------------
+            const float g = p.gravity_step * (1.0f / p.ur);
+            const int newest = (int) (a.update % (unsigned long long) F);
+            for (int n = tid; n < N; n += T) {
+                cpx z = buf[fft_pad(n >> 1)];
+                float v = fft_post((n & 1) ? z.y : z.x, n, N, p.fft_scale, p.fft_cutoff);
+                v = gravity_a(v, &a.applied[plane + n], g);
+                float* ring = a.ring_f + plane * F;
+                ring[(size_t) newest * N + n] = v;
+                float acc = 0.0f;
+                for (int f = 0; f < F; ++f) {                      // oldest first, like the memmove'd ring
+                    int slot = newest + 1 + f; if (slot >= F) slot -= F;
+                    float b = (f == F - 1) ? v : ring[(size_t) slot * N + n];
+                    if (p.avg_window) acc = (float) ((double) acc + a.avg_w_a[f] * (double) b);
+                    else acc += b;
+                }
+                float out = acc / (float) F;
+                a.spec[plane + n] = out;
+                av[n] = (uint16_t) unorm16(out);                   // glTexImage1D GL_R16 upload, render.c:521-524
+            }
+        } else {
+            // --- pipeline B: render.c:2177-2267 ---------------------------------------------------
+            const float diff = p.gravity_step * (1.0f / p.ur);
+            const int out_idx = (int) (a.update % (unsigned long long) F);
+            for (int n = tid; n < N; n += T) {
+                cpx z = buf[fft_pad(n >> 1)];
+                float v = fft_post((n & 1) ? z.y : z.x, n, N, p.fft_scale, p.fft_cutoff);
+                a.spec[plane + n] = v;
+                uint32_t gq = gravity_b(unorm16(v), a.gr_store[plane + n], diff);
+                a.gr_store[plane + n] = (uint16_t) gq;
+                uint32_t texel = gq;
+                if (F > 1) {
+                    uint16_t* ring = a.ring_u + plane * F;
+                    ring[(size_t) out_idx * N + n] = (uint16_t) gq;
+                    float r = 0.0f;
+                    for (int i = 0; i < F; ++i) {                  // t0 = most recent (render.c:2250-2255)
+                        int fr = out_idx - i; if (fr < 0) fr += F;
+                        float tx = from16(i == 0 ? gq : (uint32_t) ring[(size_t) fr * N + n]);
+                        if (a.avg_b_windowed) r += a.avg_w_b[i] * tx; else r += tx;
+                    }
+                    texel = unorm16(r / (float) F);
+                }
+                av[n] = (uint16_t) texel;
+            }
+        }
+    } else {
+        // --- wave: "window" (no-op) + "wrange" (render.c:773-781), upload ---------------------------
+        for (int n = tid; n < N; n += T) {
+            float b = raw[n];
+            b += 1.0f; b /= 2.0f;
+            a.spec[plane + n] = b;
+            av[n] = (uint16_t) unorm16(b);
+        }
+    }
+    __syncthreads();
+
+    // --- K5 smooth pass out of shared memory (render.c:2276-2303) ----------------------------------
+    uint16_t* tex = a.tex + plane;
+    if (p.smooth_pass) {
+        const SmoothParams sp = smooth_params(p);
+        if (a.need) {
+            const int* need = a.need + (size_t) ch * a.need_count;
+            for (int k = tid; k < a.need_count; k += T) {
+                int x = need[k];
+                if (x >= 0 && x < N) tex[x] = (uint16_t) smooth_pass_texel(sp, av, N, x);
+            }
+        } else {
+            for (int x = tid; x < N; x += T) tex[x] = (uint16_t) smooth_pass_texel(sp, av, N, x);
+        }
+    } else {
+        for (int x = tid; x < N; x += T) tex[x] = av[x];
+    }
+}
+
+int spectrum_smem_bytes(int n) {
+    switch (n) {
+        case 256:   return SpecCfg<8>::SMEM;   case 512:   return SpecCfg<9>::SMEM;
+        case 1024:  return SpecCfg<10>::SMEM;  case 2048:  return SpecCfg<11>::SMEM;
+        case 4096:  return SpecCfg<12>::SMEM;  case 8192:  return SpecCfg<13>::SMEM;
+        case 16384: return SpecCfg<14>::SMEM;  default: return -1;
+    }
+}
+
+template <int LOG2N, bool IS_FFT>
+static int launch_spectrum_t(const glava_b200_params& p, const SpectrumArgs& a, cudaStream_t st) {
+    using C = SpecCfg<LOG2N>;
+    auto kern = spectrum_kernel<LOG2N, IS_FFT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "cudaFuncSetAttribute(spectrum): %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    kern<<<a.batch * 2, C::T, C::SMEM, st>>>(a, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "spectrum kernel launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int launch_spectrum(const glava_b200_params& p, const SpectrumArgs& a, bool is_fft, void* stream) {
+    cudaStream_t st = (cudaStream_t) stream;
+#define GLB_CASE(L) case (1 << L): return is_fft ? launch_spectrum_t<L, true>(p, a, st) : launch_spectrum_t<L, false>(p, a, st);
+    switch (p.n) {
+        GLB_CASE(8) GLB_CASE(9) GLB_CASE(10) GLB_CASE(11) GLB_CASE(12) GLB_CASE(13) GLB_CASE(14)
+        default: return fail(GLAVA_B200_EINVAL, "unsupported setbufsize %d", p.n);
+    }
+#undef GLB_CASE
+}
+
+// K5 alone (stage-wise entry point): count planes of n texels
+__global__ void smooth_only_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int n,
+                                   const __grid_constant__ glava_b200_params p) {
+    uint16_t* av = reinterpret_cast<uint16_t*>(glb_smem);
+    const uint16_t* src = in + (size_t) blockIdx.x * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) av[i] = src[i];
+    __syncthreads();
+    const SmoothParams sp = smooth_params(p);
+    for (int x = threadIdx.x; x < n; x += blockDim.x)
+        out[(size_t) blockIdx.x * n + x] = (uint16_t) smooth_pass_texel(sp, av, n, x);
+}
+int launch_smooth_only(const glava_b200_params& p, const uint16_t* d_in, uint16_t* d_out, int count, void* stream) {
+    smooth_only_kernel<<<count, 256, p.n * 2, (cudaStream_t) stream>>>(d_in, d_out, p.n, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "smooth kernel launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FIFO ingest (fifo.c:89-110): slide + append, ping-pong between two ring buffers
+__global__ void fifo_ingest_kernel(const int16_t* __restrict__ chunks, int frames, int n, int channels,
+                                   const float* __restrict__ src_l, const float* __restrict__ src_r,
+                                   float* __restrict__ dst_l, float* __restrict__ dst_r) {
+    const int s = blockIdx.y;
+    const size_t base = (size_t) s * n;
+    const int16_t* in = chunks + (size_t) s * frames * 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float l, r;
+        if (i < n - frames) { l = src_l[base + i + frames]; r = src_r[base + i + frames]; }
+        else {
+            int q = i - (n - frames);
+            int a = in[2 * q], b = in[2 * q + 1];
+            if (channels == 1) { float m = (float) ((a + b) / 2) / (float) 65535; l = m; r = m; }
+            else { l = (float) a / (float) 65535; r = (float) b / (float) 65535; }
+        }
+        dst_l[base + i] = l; dst_r[base + i] = r;
+    }
+}
+int launch_fifo_ingest(const glava_b200_params& p, const int16_t* d_chunks, int frames, const float* src_l, const float* src_r,
+                       float* dst_l, float* dst_r, int batch, void* stream) {
+    dim3 grid((p.n + 1023) / 1024, batch);
+    fifo_ingest_kernel<<<grid, 256, 0, (cudaStream_t) stream>>>(d_chunks, frames, p.n, p.channels, src_l, src_r, dst_l, dst_r);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "fifo ingest kernel launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// raster kernels.  Thread = 4 horizontally adjacent pixels = one 128-bit streaming store.
+__device__ __forceinline__ AudioTex make_tex(const glava_b200_params& p, const uint16_t* tex, int stream) {
+    AudioTex t;
+    t.l = tex + (size_t) (stream * 2) * p.n;
+    t.r = t.l + p.n;
+    t.n = p.n; t.pre_smoothed = p.smooth_pass; t.sp = smooth_params(p);
+    return t;
+}
+__device__ __forceinline__ void store4(uint32_t* row, int x, int w, const uint32_t px[4]) {
+    if (x + 3 < w) __stcs(reinterpret_cast<uint4*>(row + x), make_uint4(px[0], px[1], px[2], px[3]));
+    else for (int k = 0; k < 4 && x + k < w; ++k) row[x + k] = px[k];
+}
+
+// generic: every pixel through module_px() — reference semantics with no hoisting; also the
+// fallback for option combinations the specialised kernels do not cover.
+__global__ void __launch_bounds__(128)
+raster_generic_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__ glava_b200_params p, int rows_per_cta) {
+    const int stream = a.stream0 + blockIdx.z;
+    const AudioTex t = make_tex(p, a.tex, stream);
+    uint32_t* fb = reinterpret_cast<uint32_t*>(a.fb) + (size_t) (stream % a.slots) * p.w * p.h;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (x >= p.w) return;
+    const int y0 = blockIdx.y * rows_per_cta, y1 = min(p.h, y0 + rows_per_cta);
+    // polar modules: everything outside a disc around the centre is exactly 0
+    float reach = -1.0f, cx = 0.0f, cy = 0.0f;
+    if (p.module == GLAVA_B200_MOD_RADIAL) { reach = radial_reach(p); cx = (float) (p.w / 2) - p.radial_off_x; cy = (float) (p.h / 2) - p.radial_off_y; }
+    if (p.module == GLAVA_B200_MOD_CIRCLE) { reach = circle_reach(p); cx = (float) (p.w / 2); cy = (float) (p.h / 2); }
+    for (int y = y0; y < y1; ++y) {
+        uint32_t px[4] = { 0u, 0u, 0u, 0u };
+        bool live = true;
+        if (reach >= 0.0f) {
+            float dy = fabsf((float) y - cy) - 1.0f;
+            float dxa = (float) x - cx, dxb = (float) (x + 3) - cx;
+            float dxm = (dxa > 0.0f) ? dxa : ((dxb < 0.0f) ? -dxb : 0.0f);   // distance of the 4-pixel span from cx
+            dxm -= 1.0f;
+            if (dy < 0.0f) dy = 0.0f;
+            if (dxm < 0.0f) dxm = 0.0f;
+            live = (dxm * dxm + dy * dy) <= reach * reach;
+        }
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (x + k < p.w) px[k] = module_px(p, t, x + k, y);
+        }
+        store4(fb + (size_t) y * p.w, x, p.w, px);
+    }
+}
+
+// bars (default orientation): column state in registers, row colours from a per-renderer table
+__global__ void bars_rowtab_kernel(uint2* __restrict__ tab, const __grid_constant__ glava_b200_params p) {
+    int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= p.h) return;
+    float fy = (float) y + 0.5f;
+    float d = p.bars_flip ? (float) p.h - fy : fy;
+    BarsRow r = bars_row(p, d);
+    tab[y] = make_uint2(r.fill, r.outl);
+}
+int launch_bars_rowtab(const glava_b200_params& p, void* d_rowtab, void* stream) {
+    bars_rowtab_kernel<<<(p.h + 127) / 128, 128, 0, (cudaStream_t) stream>>>(reinterpret_cast<uint2*>(d_rowtab), p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "bars rowtab kernel launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+raster_bars_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__ glava_b200_params p, int rows_per_cta) {
+    const int stream = a.stream0 + blockIdx.z;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (x >= p.w) return;
+    const AudioTex t = make_tex(p, a.tex, stream);
+    uint32_t* fb = reinterpret_cast<uint32_t*>(a.fb) + (size_t) (stream % a.slots) * p.w * p.h;
+    const uint2* __restrict__ rowtab = reinterpret_cast<const uint2*>(a.rowtab);
+    BarsCol col[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (x + k < p.w) col[k] = bars_column(p, t, (float) (x + k) + 0.5f, p.w);
+        else { col[k].cls = 0; col[k].v = 0.0f; col[k].vm = 0.0f; }
+    }
+    const bool has_outline = p.bars_outline_width > 0.0f;
+    const int y0 = blockIdx.y * rows_per_cta, y1 = min(p.h, y0 + rows_per_cta);
+    for (int y = y0; y < y1; ++y) {
+        const uint2 rc = __ldg(&rowtab[y]);
+        const float fy = (float) y + 0.5f;
+        const float d = p.bars_flip ? (float) p.h - fy : fy;
+        uint32_t px[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t below = (col[k].cls == 1) ? rc.x : rc.y;
+            uint32_t v = (d < col[k].vm) ? below : ((has_outline && d <= col[k].v) ? rc.y : 0u);
+            px[k] = col[k].cls ? v : 0u;
+        }
+        store4(fb + (size_t) y * p.w, x, p.w, px);
+    }
+}
+
+// graph: heights of 6 columns in registers, rolling row colours
+__global__ void __launch_bounds__(256)
+raster_graph_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__ glava_b200_params p, int rows_per_cta) {
+    const int stream = a.stream0 + blockIdx.z;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (x >= p.w) return;
+    const AudioTex t = make_tex(p, a.tex, stream);
+    uint32_t* fb = reinterpret_cast<uint32_t*>(a.fb) + (size_t) (stream % a.slots) * p.w * p.h;
+    float s[6];                                        // columns x-1 .. x+4
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        int xc = x - 1 + k;
+        s[k] = (xc >= 0 && xc < p.w) ? graph_height(p, t, xc) : 0.0f;
+    }
+    const int y0 = blockIdx.y * rows_per_cta, y1 = min(p.h, y0 + rows_per_cta);
+    uint32_t row3[3];
+    row3[0] = y0 > 0 ? graph_row(p, y0 - 1) : 0u;
+    row3[1] = graph_row(p, y0);
+    for (int y = y0; y < y1; ++y) {
+        row3[2] = (y + 1 < p.h) ? graph_row(p, y + 1) : 0u;
+        uint32_t px[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float s3[3] = { s[k], s[k + 1], s[k + 2] };
+            px[k] = (x + k < p.w) ? graph_px_cols(p, s3, row3, x + k, y) : 0u;
+        }
+        store4(fb + (size_t) y * p.w, x, p.w, px);
+        row3[0] = row3[1]; row3[1] = row3[2];
+    }
+}
+
+// wave: 6 column descriptors in registers
+__global__ void __launch_bounds__(256)
+raster_wave_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__ glava_b200_params p, int rows_per_cta) {
+    const int stream = a.stream0 + blockIdx.z;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (x >= p.w) return;
+    const AudioTex t = make_tex(p, a.tex, stream);
+    uint32_t* fb = reinterpret_cast<uint32_t*>(a.fb) + (size_t) (stream % a.slots) * p.w * p.h;
+    WaveCol c[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        int xc = x - 1 + k;
+        xc = xc < 0 ? 0 : (xc >= p.w ? p.w - 1 : xc);   // clamped columns are masked by wave_px_cols
+        c[k] = wave_column(p, t, xc);
+    }
+    const int y0 = blockIdx.y * rows_per_cta, y1 = min(p.h, y0 + rows_per_cta);
+    for (int y = y0; y < y1; ++y) {
+        uint32_t px[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const WaveCol c3[3] = { c[k], c[k + 1], c[k + 2] };
+            px[k] = (x + k < p.w) ? wave_px_cols(p, c3, x + k, y) : 0u;
+        }
+        store4(fb + (size_t) y * p.w, x, p.w, px);
+    }
+}
+
+static int pick_block_x(int quads) {       // threads per row-segment: prefer an exact tiling of w/4
+    static const int cand[] = { 256, 192, 160, 128, 96, 64 };
+    for (int c : cand) if (quads % c == 0) return c;
+    return 128;
+}
+
+int launch_raster(const glava_b200_params& p, const RasterArgs& a, void* stream) {
+    cudaStream_t st = (cudaStream_t) stream;
+    const int quads = (p.w + 3) / 4;
+    const bool fast_bars  = p.module == GLAVA_B200_MOD_BARS && !p.bars_mirror_yx && a.rowtab;
+    const bool fast_graph = p.module == GLAVA_B200_MOD_GRAPH;
+    const bool fast_wave  = p.module == GLAVA_B200_MOD_WAVE;
+    int bx = (fast_bars || fast_graph || fast_wave) ? pick_block_x(quads) : 128;
+    if (bx > 256) bx = 256;
+    int rows = (fast_bars || fast_graph || fast_wave) ? 135 : 8;
+    if (rows > p.h) rows = p.h;
+    // z dimension limit 65535: chunk the batch
+    for (int s0 = 0; s0 < a.batch; s0 += 32768) {
+        RasterArgs b = a; b.stream0 = a.stream0 + s0;
+        int nz = a.batch - s0 < 32768 ? a.batch - s0 : 32768;
+        dim3 grid((quads + bx - 1) / bx, (p.h + rows - 1) / rows, nz);
+        if (fast_bars) raster_bars_kernel<<<grid, bx, 0, st>>>(b, p, rows);
+        else if (fast_graph) raster_graph_kernel<<<grid, bx, 0, st>>>(b, p, rows);
+        else if (fast_wave) raster_wave_kernel<<<grid, bx, 0, st>>>(b, p, rows);
+        else raster_generic_kernel<<<grid, bx, 0, st>>>(b, p, rows);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "raster kernel launch: %s", cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+}  // namespace glb

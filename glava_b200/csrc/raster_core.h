@@ -1,0 +1,354 @@
+// raster_core.h — the visualiser modules' per-pixel maths as __host__ __device__ functions.
+//
+// Each function restates one GLSL fragment shader of the reference (cited at the function)
+// under the GLSL semantics listed in DESIGN.md.  Column-only and row-only sub-expressions
+// are factored out (bars_column / bars_row, graph_height / graph_row, wave_column) so the
+// CUDA kernels can hoist them; the generic per-pixel entry points recombine them, so the
+// hoisted and the per-pixel evaluation are the same arithmetic by construction.
+//
+// All multi-stage modules are evaluated in ONE pass: stages that read the previous RGBA8
+// surface (premultiply, 8-neighbour stencils) are reproduced by re-deriving the neighbour's
+// 8-bit-quantised stage-1 value in registers — no intermediate surface touches HBM.
+#ifndef GLAVA_B200_RASTER_CORE_H
+#define GLAVA_B200_RASTER_CORE_H
+
+#include "spectrum_core.h"
+
+namespace glb {
+
+struct f4 { float r, g, b, a; };
+GLB_HD f4 mk4(float r, float g, float b, float a) { f4 v = { r, g, b, a }; return v; }
+GLB_HD f4 mk4a(const float* c) { return mk4(c[0], c[1], c[2], c[3]); }
+GLB_HD uint32_t pack8(f4 c) { return unorm8(c.r) | (unorm8(c.g) << 8) | (unorm8(c.b) << 16) | (unorm8(c.a) << 24); }
+GLB_HD f4 unpack8(uint32_t u) { return mk4(from8(u & 255u), from8((u >> 8) & 255u), from8((u >> 16) & 255u), from8(u >> 24)); }
+GLB_HD f4 g_mix(f4 a, f4 b, float t) {
+    float s = 1.0f - t;
+    return mk4(a.r * s + b.r * t, a.g * s + b.g * t, a.b * s + b.b * t, a.a * s + b.a * t);
+}
+GLB_HD f4 eval_color(const glava_b200_color& c, float x) {
+    if (c.mode == 1) return mk4a(c.lo);
+    return g_mix(mk4a(c.lo), mk4a(c.hi), g_clamp(x / c.gradient, 0.0f, 1.0f));
+}
+GLB_HD uint32_t premultiply8(uint32_t px) {                              // util/premultiply.frag:12-15
+    f4 f = unpack8(px);
+    return pack8(mk4(f.r * f.a, f.g * f.a, f.b * f.a, f.a));
+}
+
+// the 1-D textures bound as audio_l / audio_r for one stream
+struct AudioTex {
+    const uint16_t* l; const uint16_t* r;
+    int n; int pre_smoothed; SmoothParams sp;
+};
+// smooth_audio() as the module sees it (smooth.glsl:23-64 with _PRE_SMOOTHED_AUDIO, render.c:292)
+GLB_HD float sample_audio(const AudioTex& t, const uint16_t* tex, float idx) {
+    if (t.pre_smoothed) return fetch16(tex, t.n, (int) glm_rint(idx * (float) t.n));
+    return smooth_audio_raw(t.sp, tex, t.n, idx);
+}
+GLB_HD float sample_audio_adj(const AudioTex& t, const uint16_t* tex, float idx, float pixel) {   // smooth.glsl:67-73
+    float al = sample_audio(t, tex, g_max(idx - pixel, 0.0f)),
+          am = sample_audio(t, tex, idx),
+          ar = sample_audio(t, tex, g_min(idx + pixel, 1.0f));
+    return (al + am + ar) / 3.0f;
+}
+
+// =================================== bars (bars/1.frag:36-135) ===================================
+struct BarsCol { int cls; float v, vm; };      // cls 0: gap/out of range, 1: bar interior column, 2: bar edge column
+struct BarsRow { uint32_t fill, outl; };
+
+// ax = AREA_X (gl_FragCoord.x, or .y when MIRROR_YX), aw = AREA_WIDTH
+GLB_HD BarsCol bars_column(const glava_b200_params& p, const AudioTex& t, float ax, int aw) {
+    BarsCol c = { 0, 0.0f, 0.0f };
+    float dx;
+    if (p.channels == 2) dx = ax - (float) (aw / 2);
+    else dx = p.bars_invert == 1 ? (float) aw - ax : ax;
+    float section = p.bars_width + p.bars_gap;
+    float center = section / 2.0f;
+    float m = fabsf(g_mod(dx, section));
+    float md = m - center;
+    float nbars = floorf(((float) aw * 0.5f) / section) * 2.0f;
+    float hi = ceilf(p.bars_width / 2.0f), lo = -floorf(p.bars_width / 2.0f);
+    if (!(md < hi && md >= lo)) return c;
+    float s = dx / section;
+    float pp = (g_sign(s) == 1.0f ? ceilf(s) : floorf(s));
+    if (p.channels == 2) pp /= (nbars / 2.0f); else pp /= nbars;
+    pp += g_sign(pp) * ((0.5f + center) / (float) aw);
+    if (pp > 1.0f || pp < -1.0f) return c;
+    const uint16_t* tex;
+    if (pp > 0.0f) {
+        if (p.bars_direction == 1) pp = 1.0f - pp;
+        tex = (p.channels == 1 || p.bars_invert > 0) ? t.l : t.r;
+    } else {
+        pp = fabsf(pp);
+        if (p.bars_direction == 1) pp = 1.0f - pp;
+        tex = (p.channels == 1) ? t.l : (p.bars_invert > 0 ? t.r : t.l);
+    }
+    float v = sample_audio(t, tex, pp);
+    v *= p.bars_amplify;
+    c.v = v; c.vm = v - p.bars_outline_width;
+    bool inner = !(p.bars_outline_width > 0.0f) ||
+                 (md < hi - p.bars_outline_width && md >= lo + p.bars_outline_width);
+    c.cls = inner ? 1 : 2;
+    return c;
+}
+GLB_HD BarsRow bars_row(const glava_b200_params& p, float d) {
+    f4 col = eval_color(p.bars_color, d);
+    f4 outl = p.bars_outline_mode == 0 ? mk4(col.r * 1.5f, col.g * 1.5f, col.b * 1.5f, col.a) : mk4a(p.bars_outline);
+    BarsRow r = { pack8(col), pack8(outl) };
+    return r;
+}
+GLB_HD uint32_t bars_combine(const glava_b200_params& p, const BarsCol& c, const BarsRow& r, float d) {
+    if (c.cls == 0) return 0u;
+    if (d < c.vm) return c.cls == 1 ? r.fill : r.outl;
+    if (p.bars_outline_width > 0.0f && d <= c.v) return r.outl;
+    return 0u;
+}
+GLB_HD uint32_t bars_px(const glava_b200_params& p, const AudioTex& t, int x, int y) {
+    float fx = (float) x + 0.5f, fy = (float) y + 0.5f;
+    int   aw = p.bars_mirror_yx ? p.h : p.w, ah = p.bars_mirror_yx ? p.w : p.h;
+    float ax = p.bars_mirror_yx ? fy : fx,  ay = p.bars_mirror_yx ? fx : fy;
+    float d = p.bars_flip ? (float) ah - ay : ay;
+    return bars_combine(p, bars_column(p, t, ax, aw), bars_row(p, d), d);
+}
+
+// ================================= radial (radial/1.frag:32-116, 2.frag) =========================
+GLB_HD f4 apply_frag(f4 f, f4 c) {                                         // radial/1.frag:35 (_USE_ALPHA > 0)
+    float k = 1.0f - g_clamp(f.a, 0.0f, 1.0f);
+    return mk4(f.r * f.a + c.r * k, f.g * f.a + c.g * k, f.b * f.a + c.b * k, g_max(c.a, f.a));
+}
+GLB_HD uint32_t radial_px(const glava_b200_params& p, const AudioTex& t, int x, int y) {
+    f4 frag = mk4(0, 0, 0, 0);
+    float dx = ((float) x + 0.5f) - (float) (p.w / 2) + p.radial_off_x,
+          dy = ((float) y + 0.5f) - (float) (p.h / 2) + p.radial_off_y;
+    float theta = glm_atan2(dy, dx);
+    float d = sqrtf((dx * dx) + (dy * dy));
+    float R = p.radial_radius, hl = p.radial_line / 2.0f;
+    bool done = false;
+    if (d > R - hl && d < R + hl) {
+        frag = apply_frag(frag, mk4a(p.radial_outline));
+        frag.a *= g_clamp((p.radial_line_half - fabsf(R - d)) * p.radial_c_alias, 0.0f, 1.0f);
+    }
+    if (d > R) {
+        const float section = (GLB_TWOPI / (float) p.radial_nbars);
+        const float center = ((GLB_TWOPI / (float) p.radial_nbars) / 2.0f);
+        float m = g_mod(theta, section);
+        float ym = d * glm_sin(center - m);
+        if (fabsf(ym) < p.radial_bar_width / 2.0f) {
+            float idx = theta + p.radial_rotate;
+            float dir = g_mod(fabsf(idx), GLB_TWOPI);
+            if (dir > GLB_PI) idx = -g_sign(idx) * (GLB_TWOPI - dir);
+            if (p.radial_invert == 0) idx = -idx;
+            float pos = (float) (int) (fabsf(idx) / section) / (float) (p.radial_nbars / 2);
+            float v = sample_audio(t, idx > 0.0f ? t.l : t.r, pos);
+            v *= p.radial_amplify;
+            d -= R;
+            if (d <= v) {
+                f4 r = eval_color(p.radial_color, d);
+                r.a *= (((p.radial_bar_width / 2.0f) - fabsf(ym)) * p.radial_bar_alias);
+                frag = apply_frag(frag, r);
+                done = true;
+            }
+        }
+    }
+    if (!done) frag = apply_frag(frag, mk4(0, 0, 0, 0));
+    uint32_t px = pack8(frag);
+    return p.premultiply_alpha ? premultiply8(px) : px;                    // radial/2.frag
+}
+// conservative test: can pixel (x, y) be non-zero?  outside this disc radial_px() is exactly 0
+GLB_HD float radial_reach(const glava_b200_params& p) {
+    // bars reach d <= C_RADIUS + AMPLIFY * max(tex) with tex <= 1; ring reaches C_RADIUS + C_LINE/2
+    return p.radial_radius + g_max(fabsf(p.radial_amplify), fabsf(p.radial_line)) + 2.0f;
+}
+
+// ================================= circle (circle/1.frag, 2.frag, 3.frag) ========================
+GLB_HD float circle_apply_smooth(const glava_b200_params& p, const AudioTex& t, float theta) {   // circle/1.frag:34-49
+    float idx = theta + p.circle_rotate;
+    float dir = g_mod(fabsf(idx), GLB_TWOPI);
+    if (dir > GLB_PI) idx = -g_sign(idx) * (GLB_TWOPI - dir);
+    if (p.circle_invert > 0) idx = -idx;
+    float pos = fabsf(idx) / (GLB_PI + 0.001f);
+    float v = sample_audio(t, idx > 0.0f ? t.l : t.r, pos);
+    v *= p.circle_amplify;
+    return v;
+}
+// stage 1, pixel_center_integer (circle/1.frag:1,51-84): returns the RGBA8 value of the stage surface
+GLB_HD uint32_t circle_stage1(const glava_b200_params& p, const AudioTex& t, int x, int y) {
+    if (x < 0 || y < 0 || x >= p.w || y >= p.h) return 0u;                 // texelFetch outside the surface
+    float dx = (float) x - (float) (p.w / 2), dy = (float) y - (float) (p.h / 2);
+    float theta = glm_atan2(dy, dx);
+    float d = sqrtf((dx * dx) + (dy * dy));
+    float adv = (1.0f / d) * (p.circle_line * 0.5f);
+    float adj0 = theta + adv, adj1 = theta - adv;
+    d -= p.circle_radius;
+    float hl = p.circle_line / 2.0f;
+    if (d >= -hl) {
+        float v = circle_apply_smooth(p, t, theta);
+        adj0 = circle_apply_smooth(p, t, adj0) - v;
+        adj1 = circle_apply_smooth(p, t, adj1) - v;
+        float dmax = g_max(adj0, adj1), dmin = g_min(adj0, adj1);
+        d -= v;
+        bool in = p.circle_fill ? (d < hl) : ((d > -hl && d < hl) || (d <= dmax && d >= dmin));
+        if (in) return pack8(mk4a(p.circle_outline));
+    }
+    return 0u;
+}
+// 8-tap neighbour mean as written in circle/2.frag:18-27, graph/2.frag:21-30, wave/2.frag:18-27:
+// taps a3 and a7 repeat a0 and a4.  nb[] = stage values at (x+1,y) (x+1,y+1) (x,y+1) (x-1,y) (x-1,y-1) (x,y-1)
+GLB_HD f4 neigh_avg(const uint32_t nb[6]) {
+    f4 a0 = unpack8(nb[0]), a1 = unpack8(nb[1]), a2 = unpack8(nb[2]), a3 = a0,
+       a4 = unpack8(nb[3]), a5 = unpack8(nb[4]), a6 = unpack8(nb[5]), a7 = a4;
+    return mk4((a0.r + a1.r + a2.r + a3.r + a4.r + a5.r + a6.r + a7.r) / 8.0f,
+               (a0.g + a1.g + a2.g + a3.g + a4.g + a5.g + a6.g + a7.g) / 8.0f,
+               (a0.b + a1.b + a2.b + a3.b + a4.b + a5.b + a6.b + a7.b) / 8.0f,
+               (a0.a + a1.a + a2.a + a3.a + a4.a + a5.a + a6.a + a7.a) / 8.0f);
+}
+GLB_HD float neigh_avg_alpha(const uint32_t nb[6]) {
+    float a0 = from8(nb[0] >> 24), a1 = from8(nb[1] >> 24), a2 = from8(nb[2] >> 24),
+          a4 = from8(nb[3] >> 24), a5 = from8(nb[4] >> 24), a6 = from8(nb[5] >> 24);
+    return (a0 + a1 + a2 + a0 + a4 + a5 + a6 + a4) / 8.0f;
+}
+GLB_HD uint32_t circle_finish(const glava_b200_params& p, uint32_t own, const uint32_t nb[6]) {
+    uint32_t px = own;
+    if (p.circle_smooth) {                                                 // circle/2.frag:14-32
+        if ((own >> 24) == 0u) px = pack8(neigh_avg(nb));
+    }
+    return p.premultiply_alpha ? premultiply8(px) : px;                    // circle/3.frag
+}
+GLB_HD float circle_reach(const glava_b200_params& p) {
+    return p.circle_radius + fabsf(p.circle_amplify) + fabsf(p.circle_line) + 3.0f;
+}
+GLB_HD uint32_t circle_px(const glava_b200_params& p, const AudioTex& t, int x, int y) {
+    uint32_t nb[6] = { 0, 0, 0, 0, 0, 0 };
+    uint32_t own = circle_stage1(p, t, x, y);
+    if (p.circle_smooth && (own >> 24) == 0u) {
+        nb[0] = circle_stage1(p, t, x + 1, y);     nb[1] = circle_stage1(p, t, x + 1, y + 1);
+        nb[2] = circle_stage1(p, t, x, y + 1);     nb[3] = circle_stage1(p, t, x - 1, y);
+        nb[4] = circle_stage1(p, t, x - 1, y - 1); nb[5] = circle_stage1(p, t, x, y - 1);
+    }
+    return circle_finish(p, own, nb);
+}
+
+// ================================= graph (graph/1.frag, 2.frag) ==================================
+// column function: line height s(x), graph/1.frag:87-105 + side selection :124-132; pixel_center_integer
+GLB_HD float graph_height(const glava_b200_params& p, const AudioTex& t, int x) {
+    float fx = (float) x, W = (float) p.w;
+    float half_w = (float) (p.w / 2);
+    float pixel = 1.0f / W;
+    const uint16_t* tex; float idx;
+    if (fx < half_w) { tex = t.l; idx = p.graph_direction < 0 ? fx : (half_w - fx); }
+    else             { tex = t.r; idx = p.graph_direction < 0 ? (-fx + W) : (fx - half_w); }
+    float s = sample_audio_adj(t, tex, idx / half_w, pixel);
+    s *= p.graph_vscale;
+    float fact = g_clamp((fabsf((float) (p.w / 2) - fx) / W) * 48.0f, 0.0f, 1.0f);
+    s *= fact;
+    s *= g_clamp((g_min(fx, W - fx) / W) * 48.0f, 0.0f, 1.0f);
+    return s;
+}
+GLB_HD float graph_d(const glava_b200_params& p, int y) { return p.graph_invert > 0 ? (float) p.h - (float) y : (float) y; }
+GLB_HD uint32_t graph_row(const glava_b200_params& p, int y) { return pack8(eval_color(p.graph_color, graph_d(p, y))); }
+// stage-1 surface value at (x, y) given the column height s and the row colour
+GLB_HD uint32_t graph_stage1(const glava_b200_params& p, float s, uint32_t rowcol, int y) {
+    return (graph_d(p, y) + 1.5f <= s) ? rowcol : 0u;                       // graph/1.frag:116
+}
+GLB_HD uint32_t graph_finish(const glava_b200_params& p, uint32_t own, const uint32_t nb[6]) {   // graph/2.frag:19-44
+    if (!(p.graph_draw_outline || p.graph_draw_highlight)) return own;
+    float avg_a = neigh_avg_alpha(nb);
+    if (avg_a > 0.0f) {
+        f4 f = unpack8(own);
+        if (f.a <= 0.0f) { if (p.graph_draw_outline) return pack8(mk4a(p.graph_outline)); }
+        else if (avg_a < 1.0f) {
+            if (p.graph_draw_highlight) { float k = avg_a * 2.0f; return pack8(mk4(f.r * k, f.g * k, f.b * k, f.a)); }
+        }
+    }
+    return own;
+}
+// generic per-pixel: s3 = heights of columns x-1, x, x+1 (out-of-surface columns: any value, masked here)
+GLB_HD uint32_t graph_px_cols(const glava_b200_params& p, const float s3[3], const uint32_t row3[3], int x, int y) {
+    // row3 = row colours of y-1, y, y+1
+    bool xl = x - 1 >= 0, xr = x + 1 < p.w, yd = y - 1 >= 0, yu = y + 1 < p.h;
+    uint32_t own = graph_stage1(p, s3[1], row3[1], y);
+    uint32_t nb[6];
+    nb[0] = xr ? graph_stage1(p, s3[2], row3[1], y) : 0u;
+    nb[1] = (xr && yu) ? graph_stage1(p, s3[2], row3[2], y + 1) : 0u;
+    nb[2] = yu ? graph_stage1(p, s3[1], row3[2], y + 1) : 0u;
+    nb[3] = xl ? graph_stage1(p, s3[0], row3[1], y) : 0u;
+    nb[4] = (xl && yd) ? graph_stage1(p, s3[0], row3[0], y - 1) : 0u;
+    nb[5] = yd ? graph_stage1(p, s3[1], row3[0], y - 1) : 0u;
+    return graph_finish(p, own, nb);
+}
+GLB_HD uint32_t graph_px(const glava_b200_params& p, const AudioTex& t, int x, int y) {
+    float s3[3] = { x > 0 ? graph_height(p, t, x - 1) : 0.0f, graph_height(p, t, x), x + 1 < p.w ? graph_height(p, t, x + 1) : 0.0f };
+    uint32_t row3[3] = { y > 0 ? graph_row(p, y - 1) : 0u, graph_row(p, y), y + 1 < p.h ? graph_row(p, y + 1) : 0u };
+    return graph_px_cols(p, s3, row3, x, y);
+}
+
+// ================================= wave (wave/1.frag, 2.frag) ====================================
+struct WaveCol { float s, dmin, dmax, thick; uint32_t color; };
+GLB_HD float wave_tex(const AudioTex& t, float coord) {                     // texture(): NEAREST + REPEAT (render.c:514-517)
+    float u = coord * (float) t.n;
+    int i = (int) floorf(u);
+    i %= t.n; if (i < 0) i += t.n;
+    return from16(t.l[i]);
+}
+GLB_HD WaveCol wave_column(const glava_b200_params& p, const AudioTex& t, int x) {   // wave/1.frag:17-31, pixel_center_integer
+    float fx = (float) x, W = (float) p.w, H = (float) p.h;
+    float os   = ((wave_tex(t, (fx + 0.0f) / W) - 0.5f) * p.wave_amplify) + 0.5f;
+    float adj0 = ((wave_tex(t, (fx + -1.0f) / W) - 0.5f) * p.wave_amplify) + 0.5f;
+    float adj1 = ((wave_tex(t, (fx + 1.0f) / W) - 0.5f) * p.wave_amplify) + 0.5f;
+    float s0 = adj0 - os, s1 = adj1 - os;
+    WaveCol c;
+    c.dmax = g_max(s0, s1); c.dmin = g_min(s0, s1);
+    c.s = (os + (H * 0.5f) - 0.5f);
+    c.thick = g_clamp(fabsf(c.s - (H * 0.5f)) * 6.0f, p.wave_min_thickness, p.wave_max_thickness);
+    float k = (fabsf((H * 0.5f) - c.s) * 0.02f);
+    c.color = pack8(mk4(p.wave_base_color[0] + k, p.wave_base_color[1] + k, p.wave_base_color[2] + k, p.wave_base_color[3] + k));
+    return c;
+}
+GLB_HD uint32_t wave_stage1(const WaveCol& c, int y) {                      // wave/1.frag:32-38
+    float diff = (float) y - c.s;
+    return (fabsf(diff) < c.thick || (diff <= c.dmax && diff >= c.dmin)) ? c.color : 0u;
+}
+// c3 = columns x-1, x, x+1
+GLB_HD uint32_t wave_px_cols(const glava_b200_params& p, const WaveCol c3[3], int x, int y) {   // wave/2.frag:14-33
+    bool xl = x - 1 >= 0, xr = x + 1 < p.w, yd = y - 1 >= 0, yu = y + 1 < p.h;
+    uint32_t own = wave_stage1(c3[1], y);
+    uint32_t nb[6];
+    nb[0] = xr ? wave_stage1(c3[2], y) : 0u;
+    nb[1] = (xr && yu) ? wave_stage1(c3[2], y + 1) : 0u;
+    nb[2] = yu ? wave_stage1(c3[1], y + 1) : 0u;
+    nb[3] = xl ? wave_stage1(c3[0], y) : 0u;
+    nb[4] = (xl && yd) ? wave_stage1(c3[0], y - 1) : 0u;
+    nb[5] = yd ? wave_stage1(c3[1], y - 1) : 0u;
+    if (neigh_avg_alpha(nb) > 0.0f) {
+        if ((own >> 24) == 0u || x == 0 || x == p.w - 1) return pack8(mk4a(p.wave_outline));
+    }
+    return own;
+}
+GLB_HD uint32_t wave_px(const glava_b200_params& p, const AudioTex& t, int x, int y) {
+    WaveCol c3[3];
+    c3[1] = wave_column(p, t, x);
+    c3[0] = x > 0 ? wave_column(p, t, x - 1) : c3[1];
+    c3[2] = x + 1 < p.w ? wave_column(p, t, x + 1) : c3[1];
+    return wave_px_cols(p, c3, x, y);
+}
+
+// ================================= test (test/1.frag:32, 2.frag, 3.frag) ==========================
+GLB_HD uint32_t test_px(const glava_b200_params& p) {
+    uint32_t px = pack8(mk4(1.0f, 0.0f, 0.0f, (float) 1 / (float) 3));
+    px = pack8(unpack8(px));                                                // test/2.frag passthrough
+    return p.premultiply_alpha ? premultiply8(px) : px;                     // test/3.frag
+}
+
+// generic per-pixel dispatcher
+GLB_HD uint32_t module_px(const glava_b200_params& p, const AudioTex& t, int x, int y) {
+    switch (p.module) {
+        case GLAVA_B200_MOD_BARS:   return bars_px(p, t, x, y);
+        case GLAVA_B200_MOD_RADIAL: return radial_px(p, t, x, y);
+        case GLAVA_B200_MOD_CIRCLE: return circle_px(p, t, x, y);
+        case GLAVA_B200_MOD_GRAPH:  return graph_px(p, t, x, y);
+        case GLAVA_B200_MOD_WAVE:   return wave_px(p, t, x, y);
+        default:                    return test_px(p);
+    }
+}
+
+}  // namespace glb
+#endif

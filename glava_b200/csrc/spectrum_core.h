@@ -1,0 +1,118 @@
+// spectrum_core.h — element-wise maths of the spectrum path, shared by the CUDA kernel
+// and the host-emulation tests.  Compiled with --fmad=false (device) / -ffp-contract=off
+// (host): every float op is a separately rounded IEEE binary32 op.
+//
+// Reference for every function is cited at its definition.
+#ifndef GLAVA_B200_SPECTRUM_CORE_H
+#define GLAVA_B200_SPECTRUM_CORE_H
+
+#include "../../include/glava_b200.h"
+#include "fft_core.h"
+
+#include <math.h>
+
+namespace glb {
+
+// ---- GLSL helper semantics (DESIGN.md "GLSL semantics") ---------------------------------------
+GLB_HD float g_clamp(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+GLB_HD float g_min(float a, float b) { return b < a ? b : a; }
+GLB_HD float g_max(float a, float b) { return a < b ? b : a; }
+GLB_HD float g_mod(float x, float y) { return x - y * floorf(x / y); }
+GLB_HD float g_sign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
+// float -> unorm store, NaN -> 0
+GLB_HD uint32_t unorm8(float c)  { return c > 0.0f ? (c < 1.0f ? (uint32_t) (c * 255.0f + 0.5f) : 255u) : 0u; }
+GLB_HD uint32_t unorm16(float c) { return c > 0.0f ? (c < 1.0f ? (uint32_t) (c * 65535.0f + 0.5f) : 65535u) : 0u; }
+GLB_HD float from8(uint32_t u)  { return (float) u / 255.0f; }
+GLB_HD float from16(uint32_t u) { return (float) u / 65535.0f; }
+
+#define GLB_PI    3.14159265359f
+#define GLB_TWOPI 6.28318530718f
+
+// ---- transform_fft tail: |.|, log(x+1)/3, index ramp — render.c:842-846 ------------------------
+// `data[n] + 1` is a float add; log() and /3 are double; the product with the ramp is float.
+GLB_HD float fft_post(float v, int i, int n, float fft_scale, float fft_cutoff) {
+    v = fabsf(v);
+    v = (float) (log((double) (v + 1.0f)) / 3.0);
+    float ramp = (((float) i / (float) n) * fft_scale) + (1.0f - fft_cutoff);
+    return v * (ramp > 1.0f ? ramp : 1.0f);
+}
+
+// ---- pipeline A: transform_gravity (render.c:720-736) -------------------------------------------
+GLB_HD float gravity_a(float b, float* applied, float g) {
+    float a = *applied;
+    a = (b >= a) ? (b - g) : (a - g);
+    *applied = a;
+    return a;
+}
+// transform_average weight (render.c:661,766): window_frame(f, avg_frames - 1) expands to
+// 0.6 - 0.4*cos(TWOPI*f/F - 1), double.  Host-computed LUT, see make_avg_weights_a().
+
+// ---- pipeline B (R16 GL passes) ------------------------------------------------------------------
+// K1 + K2: GL_MAX blend into gr_store then gravity_pass.frag:8, render.c:2199-2228
+GLB_HD uint32_t gravity_b(uint32_t uploaded, uint32_t gr_store, float diff) {
+    uint32_t g = gr_store > uploaded ? gr_store : uploaded;
+    return unorm16(from16(g) - diff);
+}
+
+// ---- K5: util/smooth.glsl:13-64 via util/smooth_pass.frag:14-16 -----------------------------------
+struct SmoothParams {
+    float smooth_factor, sample_range, sample_scale, hybrid_weight;
+    int   sample_mode, round_formula;
+};
+GLB_HD SmoothParams smooth_params(const glava_b200_params& p) {
+    return { p.smooth_factor, p.sample_range, p.sample_scale, p.hybrid_weight, p.sample_mode, p.round_formula };
+}
+GLB_HD float scale_audio(const SmoothParams& p, float idx) {                 // smooth.glsl:13-15
+    return -glm_log((-(p.sample_range) * idx) + 1.0f) / p.sample_scale;
+}
+GLB_HD float round_formula(const SmoothParams& p, float x) {                 // common.glsl:17-21
+    switch (p.round_formula) {
+        case 1:  return x;
+        case 2:  return sqrtf(1.0f - ((x - 1.0f) * (x - 1.0f)));
+        default: return (0.5f * glm_sin((GLB_PI * x) - (GLB_PI / 2.0f))) + 0.5f;
+    }
+}
+// tex: R16 texels (n of them) as uint16; texelFetch out of range reads 0
+GLB_HD float fetch16(const uint16_t* tex, int n, int i) {
+    return (i < 0 || i >= n) ? 0.0f : from16(tex[i]);
+}
+GLB_HD float smooth_audio_raw(const SmoothParams& p, const uint16_t* tex, int n, float idx) {
+    float fn = (float) n;
+    float smin = scale_audio(p, g_clamp(idx - p.smooth_factor, 0.0f, 1.0f)) * fn;
+    float smax = scale_audio(p, g_clamp(idx + p.smooth_factor, 0.0f, 1.0f)) * fn;
+    float m = ((smax - smin) / 2.0f), s, w;
+    float rm = smin + m;
+    if (p.sample_mode == 0) {
+        float avg = 0.0f, weight = 0.0f;
+        for (s = smin; s <= smax; s += 1.0f) {
+            w = round_formula(p, g_clamp((m - fabsf(rm - s)) / m, 0.0f, 1.0f));
+            weight += w;
+            avg += fetch16(tex, n, (int) glm_rint(s)) * w;
+        }
+        return avg / weight;
+    } else if (p.sample_mode == 2) {
+        float vmax = 0.0f, avg = 0.0f, weight = 0.0f, v;
+        for (s = smin; s < smax; s += 1.0f) {
+            w = round_formula(p, g_clamp((m - fabsf(rm - s)) / m, 0.0f, 1.0f));
+            weight += w;
+            v = fetch16(tex, n, (int) glm_rint(s)) * w;
+            avg += v;
+            if (vmax < v) vmax = v;
+        }
+        return (vmax * (1.0f - p.hybrid_weight)) + ((avg / weight) * p.hybrid_weight);
+    } else {
+        float vmax = 0.0f;
+        for (s = smin; s < smax; s += 1.0f) {
+            w = fetch16(tex, n, (int) glm_rint(s)) * round_formula(p, g_clamp((m - fabsf(rm - s)) / m, 0.0f, 1.0f));
+            if (vmax < w) vmax = w;
+        }
+        return vmax;
+    }
+}
+// one output texel of the smooth pass: viewport n x 1, gl_FragCoord.x = x + 0.5, uniform w = n
+GLB_HD uint32_t smooth_pass_texel(const SmoothParams& p, const uint16_t* tex, int n, int x) {
+    return unorm16(smooth_audio_raw(p, tex, n, ((float) x + 0.5f) / (float) n));
+}
+
+}  // namespace glb
+#endif

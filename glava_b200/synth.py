@@ -1,0 +1,81 @@
+"""Synthetic FIFO input: 22050 Hz stereo int16 streams, deterministic per stream.
+
+K = 6 sines per channel, log-uniform in [40, 10000] Hz, amplitudes U[500, 6000] LSB, random
+phases, white noise sigma 300 LSB, 0.5-2 Hz tremolo; every 4th stream is "quiet" (amplitudes
+/ 32) so the unsaturated R16 range is exercised.  Pure numpy; used by tests and both bench arms.
+"""
+import numpy as np
+
+
+def synth_pcm_int16(stream, t0, frames, rate=22050):
+    """Interleaved stereo int16 [frames*2] for absolute frame indices [t0, t0+frames)."""
+    seed = (0x9E3779B9 * (int(stream) + 1)) & 0xFFFFFFFF
+    rng = np.random.default_rng(seed)
+    K = 6
+    freq = np.exp(rng.uniform(np.log(40.0), np.log(10000.0), size=(2, K)))
+    amp = rng.uniform(500.0, 6000.0, size=(2, K))
+    phase = rng.uniform(0.0, 2 * np.pi, size=(2, K))
+    trem_f = rng.uniform(0.5, 2.0, size=2)
+    trem_p = rng.uniform(0.0, 2 * np.pi, size=2)
+    if stream % 4 == 3:
+        amp = amp / 32.0
+    t = (np.arange(t0, t0 + frames, dtype=np.float64)) / float(rate)
+    out = np.empty((frames, 2), dtype=np.float64)
+    # noise must depend on absolute time, not on the chunking: one generator per 4096-frame block
+    noise = np.empty((frames, 2), dtype=np.float64)
+    blk = 4096
+    b0, b1 = t0 // blk, (t0 + frames - 1) // blk
+    pos = 0
+    for b in range(b0, b1 + 1):
+        nr = np.random.default_rng((seed * 2654435761 + b) & 0xFFFFFFFFFFFF)
+        blockn = nr.standard_normal((blk, 2)) * (300.0 / (32.0 if stream % 4 == 3 else 1.0))
+        lo = max(t0, b * blk) - b * blk
+        hi = min(t0 + frames, (b + 1) * blk) - b * blk
+        noise[pos:pos + hi - lo] = blockn[lo:hi]
+        pos += hi - lo
+    for ch in range(2):
+        sig = (amp[ch][None, :] * np.sin(2 * np.pi * freq[ch][None, :] * t[:, None] + phase[ch][None, :])).sum(axis=1)
+        trem = 0.75 + 0.25 * np.sin(2 * np.pi * trem_f[ch] * t + trem_p[ch])
+        out[:, ch] = sig * trem + noise[:, ch]
+    return np.clip(np.rint(out), -32768, 32767).astype(np.int16).reshape(-1)
+
+
+def fifo_to_float(chunk_int16):
+    """fifo.c:104-107: de-interleave and convert s16 / 65535.f -> (left, right) float32."""
+    c = np.asarray(chunk_int16, dtype=np.int16).reshape(-1, 2)
+    return (c[:, 0].astype(np.float32) / np.float32(65535), c[:, 1].astype(np.float32) / np.float32(65535))
+
+
+class StreamRings:
+    """Host-side sliding rings for a batch of synthetic streams: what the audio thread keeps in
+    audio_out_l / audio_out_r (fifo.c:89-110) and glava.c:528-537 copies into lb / rb."""
+
+    def __init__(self, batch, n, hop=256, rate=22050, first_stream=0, pinned=False):
+        self.batch, self.n, self.hop, self.rate, self.first = batch, n, hop, rate, first_stream
+        if pinned:
+            from .api import pinned_empty
+            self.lb = pinned_empty((batch, n), np.float32); self.rb = pinned_empty((batch, n), np.float32)
+            self.lb[:] = 0; self.rb[:] = 0
+        else:
+            self.lb = np.zeros((batch, n), np.float32); self.rb = np.zeros((batch, n), np.float32)
+        self.t = 0
+
+    def chunks(self):
+        """next hop of raw FIFO data for every stream: int16 [batch][hop*2]"""
+        out = np.empty((self.batch, self.hop * 2), dtype=np.int16)
+        for s in range(self.batch):
+            out[s] = synth_pcm_int16(self.first + s, self.t, self.hop, self.rate)
+        return out
+
+    def push(self, chunks):
+        h = self.hop
+        self.lb[:, :-h] = self.lb[:, h:].copy(); self.rb[:, :-h] = self.rb[:, h:].copy()
+        c = chunks.reshape(self.batch, h, 2)
+        self.lb[:, -h:] = c[:, :, 0].astype(np.float32) / np.float32(65535)
+        self.rb[:, -h:] = c[:, :, 1].astype(np.float32) / np.float32(65535)
+        self.t += h
+
+    def advance(self):
+        c = self.chunks()
+        self.push(c)
+        return c

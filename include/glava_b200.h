@@ -1,0 +1,178 @@
+/* glava_b200.h — C ABI of the B200-native GLava hot path (PCM -> spectrum -> pixels).
+ *
+ * Drop-in boundary: this is what a GLava maintainer binds instead of
+ *   rd_new / rd_update / rd_destroy            (glava/render.h:53-60, glava/render.c:867,1743,2456)
+ * for a BATCH of independent PCM streams.  Plain pointers and sizes only; no CUDA or
+ * torch types appear in any signature.  All device memory is owned by the handle.
+ * See INTEGRATION.md for the glava.c-side stub.
+ *
+ * Error behaviour: the reference has no error codes; fatal conditions call the
+ * overridable fn-ptr `glava_abort` (glava/glava.h:17, glava/glava.c:77-80).  Here every
+ * entry point returns 0 on success / negative GLAVA_B200_E* on failure AND reports the
+ * message through `glava_b200_set_abort_hook` (default hook: print to stderr, do NOT exit).
+ */
+#ifndef GLAVA_B200_H
+#define GLAVA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLAVA_B200_OK        0
+#define GLAVA_B200_EINVAL   -1   /* bad argument / unsupported configuration */
+#define GLAVA_B200_ECONFIG  -2   /* config file / #request error (reference: glava_abort) */
+#define GLAVA_B200_ECUDA    -3   /* CUDA runtime failure (no device, OOM, launch error)   */
+
+/* module ids: directory names under shaders/glava/ selected by `#request mod <name>`
+ * (render.c:1100-1110) or -m / force_module (glava.c:391) */
+enum { GLAVA_B200_MOD_BARS = 0, GLAVA_B200_MOD_RADIAL = 1, GLAVA_B200_MOD_CIRCLE = 2,
+       GLAVA_B200_MOD_GRAPH = 3, GLAVA_B200_MOD_WAVE = 4, GLAVA_B200_MOD_TEST = 5 };
+
+/* A colour macro of a module config: constant, or mix(lo, hi, clamp(X / gradient, 0, 1))
+ * (e.g. bars.glsl:20, radial.glsl:17, graph.glsl:11). */
+typedef struct {
+    int   mode;            /* 0 gradient mix, 1 constant (lo) */
+    float lo[4], hi[4];
+    float gradient;
+} glava_b200_color;
+
+/* Everything rc.glsl / smooth_parameters.glsl / <module>.glsl configure on this path.
+ * Field meaning follows the `#request` (render.c:1033-1314) or `#define` named in the
+ * comment.  Defaults = the shipped config files. */
+typedef struct {
+    /* spectrum */
+    int   n;                  /* setbufsize (rc.glsl:190): floats per channel, power of two 256..16384 */
+    float fft_scale;          /* setfftscale      smooth_parameters.glsl:46 */
+    float fft_cutoff;         /* setfftcutoff     :51 */
+    float gravity_step;       /* setgravitystep   :67 */
+    float ur;                 /* updates / second the gravity step is divided by (render.c:728,2224);
+                                 nominal setsamplerate / (setsamplesize / 4) */
+    int   avg_frames;         /* setavgframes     :56 (1..16) */
+    int   avg_window;         /* setavgwindow     :61 */
+    int   accel_fft;          /* setaccelfft      rc.glsl:211 — 0: pipeline A (render.c:2149-2156 float
+                                 chain), 1: pipeline B (R16 passes, render.c:2188-2267) */
+    int   smooth_pass;        /* setsmoothpass    :78 */
+    float smooth_factor;      /* setsmoothfactor  :72 */
+    float sample_range;       /* #define SAMPLE_RANGE :42 */
+    float sample_scale;       /* #define SAMPLE_SCALE :37 */
+    float hybrid_weight;      /* #define SAMPLE_HYBRID_WEIGHT :34 */
+    int   sample_mode;        /* #define SAMPLE_MODE: 0 average, 1 maximum, 2 hybrid */
+    int   round_formula;      /* #define ROUND_FORMULA: 0 sinusoidal, 1 linear, 2 circular */
+    /* raster, common */
+    int   module;             /* GLAVA_B200_MOD_* */
+    int   w, h;               /* setgeometry w h (rc.glsl:52) */
+    int   channels;           /* _CHANNELS: setmirror ? 1 : 2 (render.c:290) */
+    int   premultiply_alpha;  /* setopacity "native" (render.c:1036-1040) */
+    /* bars.glsl */
+    float bars_width, bars_gap, bars_outline_width, bars_amplify;
+    glava_b200_color bars_color;
+    int   bars_outline_mode;  /* 0: vec4(COLOR.rgb * 1.5, COLOR.a) (bars.glsl:22), 1: constant */
+    float bars_outline[4];
+    int   bars_direction, bars_invert, bars_flip, bars_mirror_yx;
+    /* radial.glsl */
+    float radial_radius, radial_line;
+    float radial_line_half;   /* value of the GLSL expression (C_LINE / 2), integer division for an int literal */
+    float radial_outline[4];
+    int   radial_nbars; float radial_bar_width, radial_amplify;
+    glava_b200_color radial_color;
+    float radial_rotate; int radial_invert;
+    float radial_bar_alias, radial_c_alias, radial_off_x, radial_off_y;
+    /* circle.glsl */
+    float circle_radius, circle_line, circle_outline[4], circle_amplify, circle_rotate;
+    int   circle_invert, circle_fill, circle_smooth;
+    /* graph.glsl */
+    float graph_vscale; int graph_direction; glava_b200_color graph_color;
+    int   graph_draw_outline, graph_draw_highlight; float graph_outline[4]; int graph_invert;
+    /* wave.glsl */
+    float wave_min_thickness, wave_max_thickness, wave_base_color[4], wave_amplify, wave_outline[4];
+    /* request read-backs the caller sizes its audio with (render.h:10-24, glava.c:487-514) */
+    int   rate_request;       /* setsamplerate  rc.glsl:203 */
+    int   samplesize_request; /* setsamplesize  rc.glsl:181 */
+    /* engine knobs (no reference equivalent) */
+    int   fb_slots;           /* framebuffers resident per device; 0 = one per stream (default),
+                                 K < batch = ring of K (stream s renders into slot s % K) */
+    int   lazy_smooth;        /* 1: K5 evaluates only the texels the module samples (same pixels,
+                                 texture read-back then holds only those texels); 0: all n texels */
+} glava_b200_params;
+
+typedef struct glava_b200 glava_b200;    /* plays the role of struct glava_renderer (render.h:8-30) */
+
+/* Fatal-error hook, the analogue of the `glava_abort` fn-ptr (glava.h:17). NULL restores the default. */
+void glava_b200_set_abort_hook(void (*hook)(const char* message));
+const char* glava_b200_last_error(void);
+
+/* Shipped-default parameters for a module name ("bars", "radial", "circle", "graph", "wave", "test"). */
+int glava_b200_default_params(glava_b200_params* out, const char* module);
+
+/* Config surface — the part of rd_new (render.c:1322-1435) that reads `entry` (rc.glsl) from the
+ * first directory in the NULL-terminated `paths` that has it, applies `#request`s, then the
+ * NULL-terminated `requests` strings (CLI --request, render.c:1415-1435), then reads
+ * smooth_parameters.glsl and <module>.glsl (`#define`s) with user-dir-over-system-dir precedence.
+ * `force_module` = the -m option (may be NULL).  paths may be NULL: shipped defaults. */
+int glava_b200_load_config(glava_b200_params* out, const char* const* paths, const char* entry,
+                           const char* const* requests, const char* force_module);
+
+/* rd_new (render.h:53-57): build a renderer for `batch` independent streams on CUDA device
+ * `device` with the given parameters (from glava_b200_load_config / _default_params). */
+glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int device);
+/* rd_destroy (render.h:60) */
+void glava_b200_destroy(glava_b200* r);
+
+int  glava_b200_get_params(const glava_b200* r, glava_b200_params* out);
+int  glava_b200_batch(const glava_b200* r);
+const char* glava_b200_module_name(const glava_b200* r);
+
+/* Pinned host memory for the PCM rings handed to glava_b200_update (so the H2D copy is a
+ * true async DMA).  Plain malloc'd memory is accepted too, just slower. */
+void* glava_b200_host_alloc(size_t bytes);
+void  glava_b200_host_free(void* p);
+
+/* rd_update (render.h:58-59; render.c:1743-2417), batched.
+ *   lb, rb : HOST, [batch][bsz] float32, ring contents oldest-first, exactly what glava.c:528-537
+ *            memcpy's into lb/rb for one stream.  NOT modified (the reference transforms them in
+ *            place, render.c:2140-2180).  rb is ignored by `wave` (audio_l only, wave/1.frag:7).
+ *   bsz    : must equal params.n (bufscale is 1)
+ *   modified: as rd_update's flag; 0 re-rasters the last spectrum (render.c:2268-2272)
+ * Copies H2D, runs the fused spectrum kernel and the module raster kernel on the handle's stream,
+ * returns after enqueueing (call glava_b200_sync to wait). */
+int glava_b200_update(glava_b200* r, const float* lb, const float* rb, size_t bsz, int modified);
+/* same with DEVICE pointers (inputs already resident in HBM) */
+int glava_b200_update_device(glava_b200* r, const float* d_lb, const float* d_rb, size_t bsz, int modified);
+
+/* FIFO-compatible ingest (fifo.c:89-110): `frames` new interleaved int16 L,R frames per stream,
+ * HOST [batch][frames*2]; slides every stream's device-resident ring and converts s16/65535.f
+ * (mono: integer mean first, fifo.c:98-102 when params.channels == 1).  Then
+ * glava_b200_update_rings() runs the update on the resident rings. */
+int glava_b200_ingest_fifo(glava_b200* r, const int16_t* chunks, int frames);
+int glava_b200_update_rings(glava_b200* r, int modified);
+
+int glava_b200_sync(glava_b200* r);
+
+/* Outputs.  Frame layout: RGBA8, [h][w][4] bytes, row 0 = bottom row (GL window coordinates),
+ * byte order R,G,B,A. */
+int glava_b200_readback(glava_b200* r, int stream, uint8_t* rgba);              /* one stream's frame -> HOST */
+int glava_b200_spectrum(glava_b200* r, float* out_l, float* out_r);             /* HOST [batch][n]: pipeline-A result
+                                                                                   (accel_fft 0) or raw transform_fft output (1) */
+int glava_b200_textures(glava_b200* r, uint16_t* out_l, uint16_t* out_r);       /* HOST [batch][n] R16 texels the module samples */
+const void* glava_b200_framebuffer_device(const glava_b200* r);                 /* DEVICE [fb_slots][h][w] RGBA8 */
+void* glava_b200_cuda_stream(const glava_b200* r);                              /* cudaStream_t, for event timing */
+
+/* Stage-wise entry points (used by the parity tests; same kernels as the fused path). */
+int glava_b200_smooth_pass(glava_b200* r, const uint16_t* in, uint16_t* out, int count);      /* K5 on HOST [count][n] */
+int glava_b200_raster_textures(glava_b200* r, const uint16_t* tex_l, const uint16_t* tex_r);  /* HOST [batch][n] -> raster */
+
+/* Kernel launch counters since creation (bench.py `gpu_launches`). */
+uint64_t glava_b200_launch_count(const glava_b200* r);
+
+/* ---- audio plug-in ABI kept verbatim from the reference (fifo.h:9-26) so a GLava audio
+ * backend can feed this renderer: see INTEGRATION.md. ---- */
+
+const char* glava_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLAVA_B200_H */

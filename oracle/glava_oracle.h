@@ -1,0 +1,115 @@
+/* TEST INFRASTRUCTURE — CPU restatement of the reference's PCM->spectrum->pixels path.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library.  The product (libglava_b200.so) never links or calls it.
+ *
+ * Parity status: the SPECTRUM half is pinned against the reference's own compiled code
+ * (oracle/_ref, built from /root/reference/glava/render.c by oracle/Makefile) and the
+ * golden vectors generated from it (tests/golden/).  The RASTER half restates GLSL
+ * fragment shaders; the reference ships no golden pixels except the `test` module's
+ * #55000055 known answer (shaders/glava/test_rc.glsl:27), and no GL implementation is
+ * available in this image, so apart from that KAT it is "parity unpinned".
+ */
+#ifndef GLAVA_ORACLE_H
+#define GLAVA_ORACLE_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { ORC_MOD_BARS = 0, ORC_MOD_RADIAL = 1, ORC_MOD_CIRCLE = 2, ORC_MOD_GRAPH = 3,
+       ORC_MOD_WAVE = 4, ORC_MOD_TEST = 5 };
+
+/* colour that is either a constant or mix(lo, hi, clamp(X / gradient, 0, 1)) */
+typedef struct {
+    int   mode;          /* 0 = gradient mix, 1 = constant (lo) */
+    float lo[4], hi[4];
+    float gradient;
+} orc_color;
+
+typedef struct {
+    /* ---- spectrum (render.c transforms, util/ *_pass.frag) ---- */
+    int   n;               /* setbufsize: floats per channel                          */
+    float fft_scale, fft_cutoff, gravity_step, ur;
+    int   avg_frames, avg_window;
+    int   accel_fft;       /* 0: pipeline A (CPU float chain), 1: pipeline B (R16 GL passes) */
+    int   smooth_pass;     /* K5 pre-smoothing pass on/off                            */
+    float smooth_factor, sample_range, sample_scale, hybrid_weight;
+    int   sample_mode;     /* 0 average, 1 maximum, 2 hybrid                          */
+    int   round_formula;   /* 0 sinusoidal, 1 linear, 2 circular                      */
+    /* ---- raster, common ---- */
+    int   module, w, h, channels, premultiply_alpha;
+    /* ---- bars ---- */
+    float bars_width, bars_gap, bars_outline_width, bars_amplify;
+    orc_color bars_color;
+    int   bars_outline_mode;   /* 0: vec4(COLOR.rgb*1.5, COLOR.a), 1: constant */
+    float bars_outline[4];
+    int   bars_direction, bars_invert, bars_flip, bars_mirror_yx;
+    /* ---- radial ---- */
+    float radial_radius, radial_line;
+    float radial_line_half;   /* value of `(C_LINE / 2)` as GLSL evaluates it (int division for an int literal) */
+    float radial_outline[4];
+    int   radial_nbars; float radial_bar_width, radial_amplify;
+    orc_color radial_color;
+    float radial_rotate; int radial_invert;
+    float radial_bar_alias, radial_c_alias, radial_off_x, radial_off_y;
+    /* ---- circle ---- */
+    float circle_radius, circle_line, circle_outline[4], circle_amplify, circle_rotate;
+    int   circle_invert, circle_fill, circle_smooth;
+    /* ---- graph ---- */
+    float graph_vscale; int graph_direction; orc_color graph_color;
+    int   graph_draw_outline, graph_draw_highlight; float graph_outline[4]; int graph_invert;
+    /* ---- wave ---- */
+    float wave_min_thickness, wave_max_thickness, wave_base_color[4], wave_amplify, wave_outline[4];
+} orc_params;
+
+void orc_default_params(orc_params* p, int module, int n, int w, int h);
+
+/* window LUT w[i] = 0.53836 - 0.46164*cos(2*pi*i/N - 1) as the macro at render.c:660
+ * expands at render.c:794 (double), i in [0, n). */
+void orc_window(double* w, int n);
+
+/* transform_fft (render.c:783-847) restated in float32 with the same float twiddle
+ * recurrence: intended to be bit-identical to the compiled reference. */
+void orc_fft_f32(const orc_params* p, float* buf);
+/* same maths, float64 arithmetic and exact twiddles ("truth" companion). in: float PCM,
+ * out: double spectrum. */
+void orc_fft_f64(const orc_params* p, const float* in, double* out);
+
+/* per (stream, channel) persistent state */
+typedef struct orc_chan orc_chan;
+orc_chan* orc_chan_new(const orc_params* p);
+void      orc_chan_free(orc_chan* c);
+
+/* One audio update for one channel.
+ *  pcm      : n floats (ring contents, oldest first), not modified
+ *  spec_f32 : n floats out — pipeline A result (after fft+gravity+average) when
+ *             accel_fft == 0; the raw transform_fft output when accel_fft == 1
+ *  tex_u16  : n texels out — the R16 1-D texture the module shader samples
+ *             (after upload quantisation, K1-K4 when accel, and K5 when smooth_pass)
+ *  is_fft   : 1 for fft modules; 0 for `wave` (transform chain window+wrange, wave/1.frag:7-10)
+ */
+void orc_chan_update(orc_chan* c, const orc_params* p, const float* pcm, int is_fft,
+                     float* spec_f32, uint16_t* tex_u16);
+
+/* K5 alone: smooth_pass.frag over an R16 texture */
+void orc_smooth_pass(const orc_params* p, const uint16_t* in, uint16_t* out);
+
+/* Module raster: all active stages of p->module.  tex_l / tex_r are the R16 textures
+ * bound as audio_l / audio_r.  out: h rows of w RGBA8 pixels, row 0 = bottom (GL). */
+void orc_raster(const orc_params* p, const uint16_t* tex_l, const uint16_t* tex_r, uint8_t* out);
+/* rows [y0, y1) only (for timing on bounded samples and for threading) */
+void orc_raster_rows(const orc_params* p, const uint16_t* tex_l, const uint16_t* tex_r,
+                     uint8_t* out, int y0, int y1);
+
+/* FIFO ingest (fifo.c:89-110): slide ring left by `frames`, append int16 interleaved */
+void orc_fifo_ingest(float* ring_l, float* ring_r, int n, const int16_t* interleaved,
+                     int frames, int channels);
+
+const char* orc_math_kind(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

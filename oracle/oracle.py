@@ -1,0 +1,203 @@
+"""TEST INFRASTRUCTURE — ctypes loader for the oracle libraries.
+
+  libglava_oracle.so     our C restatement, libm transcendentals (the independent checker)
+  libglava_oracle_pm.so  same restatement, transcendentals from glava_b200/csrc/gl_math.h
+                         (bit-exact comparisons against the CUDA kernels)
+  _ref/libglava_ref.so   the reference's own render.c transforms, compiled where they lie
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+MODULES = ("bars", "radial", "circle", "graph", "wave", "test")
+
+
+class OrcColor(C.Structure):
+    _fields_ = [("mode", C.c_int), ("lo", C.c_float * 4), ("hi", C.c_float * 4), ("gradient", C.c_float)]
+
+
+class OrcParams(C.Structure):
+    _fields_ = [
+        ("n", C.c_int), ("fft_scale", C.c_float), ("fft_cutoff", C.c_float), ("gravity_step", C.c_float),
+        ("ur", C.c_float), ("avg_frames", C.c_int), ("avg_window", C.c_int), ("accel_fft", C.c_int),
+        ("smooth_pass", C.c_int), ("smooth_factor", C.c_float), ("sample_range", C.c_float),
+        ("sample_scale", C.c_float), ("hybrid_weight", C.c_float), ("sample_mode", C.c_int),
+        ("round_formula", C.c_int),
+        ("module", C.c_int), ("w", C.c_int), ("h", C.c_int), ("channels", C.c_int), ("premultiply_alpha", C.c_int),
+        ("bars_width", C.c_float), ("bars_gap", C.c_float), ("bars_outline_width", C.c_float), ("bars_amplify", C.c_float),
+        ("bars_color", OrcColor), ("bars_outline_mode", C.c_int), ("bars_outline", C.c_float * 4),
+        ("bars_direction", C.c_int), ("bars_invert", C.c_int), ("bars_flip", C.c_int), ("bars_mirror_yx", C.c_int),
+        ("radial_radius", C.c_float), ("radial_line", C.c_float), ("radial_line_half", C.c_float),
+        ("radial_outline", C.c_float * 4), ("radial_nbars", C.c_int), ("radial_bar_width", C.c_float),
+        ("radial_amplify", C.c_float), ("radial_color", OrcColor), ("radial_rotate", C.c_float), ("radial_invert", C.c_int),
+        ("radial_bar_alias", C.c_float), ("radial_c_alias", C.c_float), ("radial_off_x", C.c_float), ("radial_off_y", C.c_float),
+        ("circle_radius", C.c_float), ("circle_line", C.c_float), ("circle_outline", C.c_float * 4),
+        ("circle_amplify", C.c_float), ("circle_rotate", C.c_float), ("circle_invert", C.c_int),
+        ("circle_fill", C.c_int), ("circle_smooth", C.c_int),
+        ("graph_vscale", C.c_float), ("graph_direction", C.c_int), ("graph_color", OrcColor),
+        ("graph_draw_outline", C.c_int), ("graph_draw_highlight", C.c_int), ("graph_outline", C.c_float * 4),
+        ("graph_invert", C.c_int),
+        ("wave_min_thickness", C.c_float), ("wave_max_thickness", C.c_float), ("wave_base_color", C.c_float * 4),
+        ("wave_amplify", C.c_float), ("wave_outline", C.c_float * 4),
+    ]
+
+
+def _copy_fields(dst, src):
+    """field-by-name copy between two ctypes structures (nested structs / arrays by bytes)."""
+    names = {f[0] for f in src._fields_}
+    for name, typ in dst._fields_:
+        if name not in names:
+            continue
+        v = getattr(src, name)
+        if isinstance(v, (C.Structure, C.Array)):
+            d = getattr(dst, name)
+            assert C.sizeof(d) == C.sizeof(v), name
+            C.memmove(C.byref(d), C.byref(v), C.sizeof(v))
+        else:
+            setattr(dst, name, v)
+    return dst
+
+
+def params_from(product_params):
+    """OrcParams with the same settings as a glava_b200.Params."""
+    return _copy_fields(OrcParams(), product_params)
+
+
+def build(force=False):
+    """make oracle (+ ref when /root/reference exists).  Building the checker is not using it."""
+    need = force or not all(os.path.exists(os.path.join(HERE, f)) for f in ("libglava_oracle.so", "libglava_oracle_pm.so"))
+    if need:
+        subprocess.run(["make", "-C", HERE, "oracle"], check=True, capture_output=True)
+    if os.path.exists("/root/reference/glava/render.c") and (force or not os.path.exists(os.path.join(HERE, "_ref", "libglava_ref.so"))):
+        subprocess.run(["make", "-C", HERE, "ref"], check=True, capture_output=True)
+
+
+class Oracle:
+    def __init__(self, kind="libm"):
+        build()
+        name = {"libm": "libglava_oracle.so", "pm": "libglava_oracle_pm.so"}[kind]
+        L = C.CDLL(os.path.join(HERE, name))
+        vp, i32 = C.c_void_p, C.c_int
+        PP = C.POINTER(OrcParams)
+        L.orc_default_params.argtypes = [PP, i32, i32, i32, i32]
+        L.orc_window.argtypes = [vp, i32]
+        L.orc_fft_f32.argtypes = [PP, vp]
+        L.orc_fft_f64.argtypes = [PP, vp, vp]
+        L.orc_chan_new.restype = vp
+        L.orc_chan_new.argtypes = [PP]
+        L.orc_chan_free.argtypes = [vp]
+        L.orc_chan_update.argtypes = [vp, PP, vp, i32, vp, vp]
+        L.orc_smooth_pass.argtypes = [PP, vp, vp]
+        L.orc_raster.argtypes = [PP, vp, vp, vp]
+        L.orc_raster_rows.argtypes = [PP, vp, vp, vp, i32, i32]
+        L.orc_fifo_ingest.argtypes = [vp, vp, i32, vp, i32, i32]
+        L.orc_math_kind.restype = C.c_char_p
+        self.L = L
+        self.kind = kind
+
+    def default_params(self, module="bars", n=4096, w=800, h=600, **over):
+        p = OrcParams()
+        self.L.orc_default_params(C.byref(p), MODULES.index(module), n, w, h)
+        for k, v in over.items():
+            setattr(p, k, v)
+        return p
+
+    def window(self, n):
+        w = np.empty(n, np.float64)
+        self.L.orc_window(w.ctypes.data, n)
+        return w
+
+    def fft_f32(self, p, pcm):
+        b = np.array(pcm, dtype=np.float32, copy=True)
+        self.L.orc_fft_f32(C.byref(p), b.ctypes.data)
+        return b
+
+    def fft_f64(self, p, pcm):
+        x = np.ascontiguousarray(pcm, dtype=np.float32)
+        out = np.empty(p.n, np.float64)
+        self.L.orc_fft_f64(C.byref(p), x.ctypes.data, out.ctypes.data)
+        return out
+
+    def smooth_pass(self, p, tex):
+        tex = np.ascontiguousarray(tex, dtype=np.uint16)
+        out = np.empty_like(tex)
+        self.L.orc_smooth_pass(C.byref(p), tex.ctypes.data, out.ctypes.data)
+        return out
+
+    def raster(self, p, tex_l, tex_r, rows=None):
+        tl = np.ascontiguousarray(tex_l, dtype=np.uint16)
+        tr = np.ascontiguousarray(tex_r if tex_r is not None else tex_l, dtype=np.uint16)
+        out = np.zeros((p.h, p.w, 4), dtype=np.uint8)
+        y0, y1 = rows if rows else (0, p.h)
+        self.L.orc_raster_rows(C.byref(p), tl.ctypes.data, tr.ctypes.data, out.ctypes.data, y0, y1)
+        return out
+
+    def fifo_ingest(self, ring_l, ring_r, chunk, channels=2):
+        chunk = np.ascontiguousarray(chunk, dtype=np.int16)
+        self.L.orc_fifo_ingest(ring_l.ctypes.data, ring_r.ctypes.data, ring_l.shape[0], chunk.ctypes.data,
+                               chunk.shape[0] // 2, channels)
+
+
+class OracleChannel:
+    """persistent per-(stream, channel) state + one-update entry point"""
+
+    def __init__(self, oracle, p):
+        self.o, self.p = oracle, p
+        self.h = oracle.L.orc_chan_new(C.byref(p))
+
+    def update(self, pcm, is_fft=True):
+        pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+        spec = np.empty(self.p.n, np.float32); tex = np.empty(self.p.n, np.uint16)
+        self.o.L.orc_chan_update(self.h, C.byref(self.p), pcm.ctypes.data, 1 if is_fft else 0, spec.ctypes.data, tex.ctypes.data)
+        return spec, tex
+
+    def __del__(self):
+        try: self.o.L.orc_chan_free(self.h)
+        except Exception: pass
+
+
+class Reference:
+    """The reference's own compiled transforms (oracle/_ref/libglava_ref.so)."""
+
+    @staticmethod
+    def available():
+        build()
+        return os.path.exists(os.path.join(HERE, "_ref", "libglava_ref.so"))
+
+    def __init__(self):
+        L = C.CDLL(os.path.join(HERE, "_ref", "libglava_ref.so"))
+        vp = C.c_void_p
+        L.ref_chan_new.restype = vp
+        L.ref_chan_new.argtypes = [C.c_float] * 4 + [C.c_int] * 2
+        L.ref_chan_free.argtypes = [vp]
+        for f in (L.ref_fft, L.ref_gravity, L.ref_average, L.ref_update_a):
+            f.argtypes = [vp, vp, C.c_size_t]
+        L.ref_wrange.argtypes = [vp, C.c_size_t]
+        L.ref_parse_color.argtypes = [C.c_char_p, vp]
+        self.L = L
+
+    def chan(self, p):
+        return self.L.ref_chan_new(p.fft_scale, p.fft_cutoff, p.gravity_step, p.ur, p.avg_frames, p.avg_window)
+
+    def fft(self, ch, pcm):
+        b = np.array(pcm, dtype=np.float32, copy=True)
+        self.L.ref_fft(ch, b.ctypes.data, b.shape[0])
+        return b
+
+    def update_a(self, ch, pcm):
+        b = np.array(pcm, dtype=np.float32, copy=True)
+        self.L.ref_update_a(ch, b.ctypes.data, b.shape[0])
+        return b
+
+    def wrange(self, pcm):
+        b = np.array(pcm, dtype=np.float32, copy=True)
+        self.L.ref_wrange(b.ctypes.data, b.shape[0])
+        return b
+
+    def parse_color(self, s):
+        out = np.zeros(4, np.float32); out[3] = 1.0
+        ok = self.L.ref_parse_color(s.encode(), out.ctypes.data)
+        return bool(ok), out

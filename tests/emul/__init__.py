@@ -1,0 +1,75 @@
+"""TEST INFRASTRUCTURE — host emulation of the CUDA kernels' arithmetic (see emul.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        so = os.path.join(HERE, "libglava_emul.so")
+        src = os.path.join(HERE, "emul.cpp")
+        csrc = os.path.join(HERE, "..", "..", "glava_b200", "csrc")
+        newest = max(os.path.getmtime(os.path.join(csrc, f)) for f in os.listdir(csrc) if f.endswith(".h"))
+        if not os.path.exists(so) or os.path.getmtime(so) < max(newest, os.path.getmtime(src)):
+            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas",
+                            "-o", so, src], check=True)
+        L = C.CDLL(so)
+        vp, i32 = C.c_void_p, C.c_int
+        L.emul_fft.argtypes = [i32, vp, vp, C.c_float, C.c_float]
+        L.emul_chan_new.restype = vp
+        L.emul_chan_new.argtypes = [vp]
+        L.emul_chan_free.argtypes = [vp]
+        L.emul_chan_update.argtypes = [vp, vp, vp, i32, vp, vp]
+        L.emul_smooth.argtypes = [vp, vp, vp]
+        L.emul_raster.argtypes = [vp, vp, vp, vp, i32, i32]
+        L.emul_raster_fast.argtypes = [vp, vp, vp, vp]
+        _lib = L
+    return _lib
+
+
+def fft(pcm, fft_scale=10.2, fft_cutoff=0.3):
+    x = np.ascontiguousarray(pcm, dtype=np.float32)
+    out = np.empty_like(x)
+    assert lib().emul_fft(x.shape[0], x.ctypes.data, out.ctypes.data, fft_scale, fft_cutoff) == 0
+    return out
+
+
+class Channel:
+    def __init__(self, params):
+        self.p = params
+        self.h = lib().emul_chan_new(C.addressof(params))
+
+    def update(self, pcm, is_fft=True):
+        x = np.ascontiguousarray(pcm, dtype=np.float32)
+        spec = np.empty(self.p.n, np.float32); tex = np.empty(self.p.n, np.uint16)
+        assert lib().emul_chan_update(self.h, C.addressof(self.p), x.ctypes.data, 1 if is_fft else 0,
+                                      spec.ctypes.data, tex.ctypes.data) == 0
+        return spec, tex
+
+    def __del__(self):
+        try: lib().emul_chan_free(self.h)
+        except Exception: pass
+
+
+def smooth(params, tex):
+    t = np.ascontiguousarray(tex, dtype=np.uint16)
+    out = np.empty_like(t)
+    lib().emul_smooth(C.addressof(params), t.ctypes.data, out.ctypes.data)
+    return out
+
+
+def raster(params, tex_l, tex_r, fast=False):
+    tl = np.ascontiguousarray(tex_l, dtype=np.uint16)
+    tr = np.ascontiguousarray(tex_r if tex_r is not None else tex_l, dtype=np.uint16)
+    out = np.zeros((params.h, params.w, 4), dtype=np.uint8)
+    if fast:
+        assert lib().emul_raster_fast(C.addressof(params), tl.ctypes.data, tr.ctypes.data, out.ctypes.data) == 0
+    else:
+        lib().emul_raster(C.addressof(params), tl.ctypes.data, tr.ctypes.data, out.ctypes.data, 0, params.h)
+    return out
