@@ -103,6 +103,8 @@ def lib():
     L.glava_b200_launch_count.argtypes = [vp]
     L.glava_b200_launch_count.restype = C.c_uint64
     L.glava_b200_set_abort_hook.argtypes = [vp]
+    L.glava_b200_set_timing.argtypes = [vp, i32]
+    L.glava_b200_kernel_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i32), C.POINTER(C.c_double), C.POINTER(i32)]
     _lib = L
     # errors surface as Python exceptions; keep stderr quiet
     _quiet = C.CFUNCTYPE(None, cp)(lambda msg: None)
@@ -143,27 +145,19 @@ def load_config(paths=None, entry="rc.glsl", requests=None, force_module=None):
     return p
 
 
+_pinned = []
+
+
 def pinned_empty(shape, dtype):
-    """numpy array backed by cudaHostAlloc'd memory (freed when the array is collected)."""
+    """numpy array backed by cudaHostAlloc'd (pinned) memory; lives until process exit."""
     dtype = np.dtype(dtype)
     nbytes = int(np.prod(shape)) * dtype.itemsize
     ptr = lib().glava_b200_host_alloc(nbytes)
     if not ptr:
         raise GlavaError("pinned allocation failed")
     buf = (C.c_byte * nbytes).from_address(ptr)
-    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
-
-    class _Owner:
-        def __init__(self, p): self.p = p
-        def __del__(self):
-            try: lib().glava_b200_host_free(self.p)
-            except Exception: pass
-    arr = arr.view()
-    _owners[id(buf)] = (_Owner(ptr), buf)
-    return arr
-
-
-_owners = {}
+    _pinned.append(buf)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
 
 class Renderer:
@@ -251,6 +245,16 @@ class Renderer:
     @property
     def launch_count(self):
         return int(self._L.glava_b200_launch_count(self._h))
+
+    def set_timing(self, enable=True):
+        _check(self._L.glava_b200_set_timing(self._h, 1 if enable else 0))
+
+    def kernel_times(self):
+        """-> dict(spectrum_ms, spectrum_launches, raster_ms, raster_launches) since set_timing(True)"""
+        s, q = C.c_double(), C.c_double()
+        ns, nq = C.c_int(), C.c_int()
+        _check(self._L.glava_b200_kernel_times(self._h, C.byref(s), C.byref(ns), C.byref(q), C.byref(nq)))
+        return dict(spectrum_ms=s.value, spectrum_launches=ns.value, raster_ms=q.value, raster_launches=nq.value)
 
     # -- rd_destroy --------------------------------------------------------------------------------
     def close(self):

@@ -5,6 +5,7 @@
 // gravity/average state per stream and channel, R16 textures, framebuffers) is allocated once
 // in glava_b200_new and stays resident in HBM.
 #include "internal.h"
+#include "raster_core.h"
 
 #include <cuda_runtime.h>
 
@@ -62,6 +63,10 @@ struct glava_b200 {
     unsigned long long updates;
     uint64_t launches;
     std::vector<void*> allocs;
+    // optional per-kernel device timing (glava_b200_set_timing): events around each launch
+    bool timing;
+    std::vector<cudaEvent_t> ev;      // triples: before spectrum, between, after raster
+    std::vector<int> ev_modified;
 };
 
 static int dev_alloc(glava_b200* r, void** out, size_t bytes, bool zero) {
@@ -105,6 +110,53 @@ void* glava_b200_host_alloc(size_t bytes) {
 }
 void glava_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
 
+// Lazy K5: the texels of the smoothed R16 texture the module's fragment shader can sample.
+// Built with the SAME coordinate helpers the kernels use (raster_core.h), on the host.
+// Returns false when every texel may be needed (circle: continuous angle -> position).
+static bool build_need_list(const glava_b200_params& p, std::vector<int>* lists /* [2] */) {
+    if (!p.smooth_pass) return false;
+    std::vector<char> mark[2];
+    mark[0].assign(p.n + 1, 0); mark[1].assign(p.n + 1, 0);
+    auto hit = [&](int chan, float coord) {
+        int i = (int) glm_rint(coord * (float) p.n);
+        if (i >= 0 && i < p.n) mark[chan][i] = 1;
+    };
+    switch (p.module) {
+        case GLAVA_B200_MOD_BARS: {
+            int aw = p.bars_mirror_yx ? p.h : p.w;
+            for (int x = 0; x < aw; ++x) {
+                int chan; float pp; bool inner;
+                if (bars_column_coord(p, (float) x + 0.5f, aw, &chan, &pp, &inner)) hit(chan, pp);
+            }
+            break;
+        }
+        case GLAVA_B200_MOD_RADIAL:
+            for (int k = 0; k <= p.radial_nbars; ++k) {
+                float pos = (float) k / (float) (p.radial_nbars / 2);
+                hit(0, pos); hit(1, pos);
+            }
+            break;
+        case GLAVA_B200_MOD_GRAPH: {
+            float pixel = 1.0f / (float) p.w;
+            for (int x = 0; x < p.w; ++x) {
+                int chan; float c = graph_column_coord(p, x, &chan);
+                hit(chan, g_max(c - pixel, 0.0f)); hit(chan, c); hit(chan, g_min(c + pixel, 1.0f));
+            }
+            break;
+        }
+        case GLAVA_B200_MOD_WAVE:
+            for (int x = -1; x <= p.w; ++x) mark[0][wave_tex_index(p.n, (float) x / (float) p.w)] = 1;
+            break;
+        case GLAVA_B200_MOD_TEST: break;            // samples nothing that reaches the output
+        default: return false;
+    }
+    for (int c = 0; c < 2; ++c) {
+        lists[c].clear();
+        for (int i = 0; i < p.n; ++i) if (mark[c][i]) lists[c].push_back(i);
+    }
+    return true;
+}
+
 static int build(glava_b200* r) {
     const glava_b200_params& p = r->p;
     const size_t n = (size_t) p.n, planes = (size_t) r->batch * 2, F = (size_t) p.avg_frames;
@@ -138,6 +190,19 @@ static int build(glava_b200* r) {
     }
     CU(cudaMemcpyAsync(r->d_twiddle, tw.data(), n * 4, cudaMemcpyHostToDevice, r->stream));
     CU(cudaStreamSynchronize(r->stream));
+    if (p.lazy_smooth) {
+        std::vector<int> lists[2];
+        if (build_need_list(p, lists)) {
+            size_t cnt = lists[0].size() > lists[1].size() ? lists[0].size() : lists[1].size();
+            if (cnt == 0) cnt = 1;
+            std::vector<int> flat(2 * cnt, -1);
+            for (int c = 0; c < 2; ++c) for (size_t i = 0; i < lists[c].size(); ++i) flat[c * cnt + i] = lists[c][i];
+            if ((rc = dev_alloc(r, (void**) &r->d_need, flat.size() * sizeof(int), false)) != 0) return rc;
+            CU(cudaMemcpyAsync(r->d_need, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, r->stream));
+            CU(cudaStreamSynchronize(r->stream));
+            r->need_count = (int) cnt;
+        }
+    }
     if (p.module == GLAVA_B200_MOD_BARS) { if ((rc = launch_bars_rowtab(p, r->d_rowtab, r->stream)) != 0) return rc; ++r->launches; }
     CU(cudaStreamSynchronize(r->stream));
     return 0;
@@ -159,7 +224,7 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     r->d_window = nullptr; r->d_twiddle = nullptr; r->d_rowtab = nullptr; r->d_need = nullptr; r->need_count = 0;
     r->d_spec = r->d_applied = r->d_ring_f = nullptr; r->d_gr_store = r->d_ring_u = r->d_tex = nullptr; r->d_fb = nullptr;
     r->d_pcm[0] = r->d_pcm[1] = nullptr;
-    r->updates = 0; r->launches = 0;
+    r->updates = 0; r->launches = 0; r->timing = false;
     if (build(r) != 0) { glava_b200_destroy(r); return nullptr; }
     return r;
 }
@@ -168,6 +233,7 @@ void glava_b200_destroy(glava_b200* r) {
     if (!r) return;
     cudaSetDevice(r->device);
     if (r->stream) cudaStreamSynchronize(r->stream);
+    for (cudaEvent_t e : r->ev) cudaEventDestroy(e);
     for (void* p : r->allocs) cudaFree(p);
     if (r->d_chunks) cudaFree(r->d_chunks);
     if (r->stream) cudaStreamDestroy(r->stream);
@@ -184,9 +250,18 @@ const void* glava_b200_framebuffer_device(const glava_b200* r) { return r ? r->d
 void* glava_b200_cuda_stream(const glava_b200* r) { return r ? (void*) r->stream : nullptr; }
 uint64_t glava_b200_launch_count(const glava_b200* r) { return r ? r->launches : 0; }
 
+static int timing_mark(glava_b200* r) {
+    cudaEvent_t e;
+    CU(cudaEventCreate(&e));
+    CU(cudaEventRecord(e, r->stream));
+    r->ev.push_back(e);
+    return 0;
+}
+
 static int run_update(glava_b200* r, const float* d_l, const float* d_r, int modified) {
     const glava_b200_params& p = r->p;
     int rc;
+    if (r->timing) { if ((rc = timing_mark(r)) != 0) return rc; r->ev_modified.push_back(modified ? 1 : 0); }
     if (modified) {
         SpectrumArgs a;
         memset(&a, 0, sizeof(a));
@@ -207,11 +282,13 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
         if ((rc = launch_spectrum(p, a, is_fft, r->stream)) != 0) return rc;
         ++r->launches; ++r->updates;
     }
+    if (r->timing && (rc = timing_mark(r)) != 0) return rc;
     RasterArgs ra;
     ra.tex = r->d_tex; ra.fb = r->d_fb; ra.rowtab = (p.module == GLAVA_B200_MOD_BARS) ? r->d_rowtab : nullptr;
     ra.batch = r->batch; ra.slots = r->slots; ra.stream0 = 0;
     if ((rc = launch_raster(p, ra, r->stream)) != 0) return rc;
     r->launches += (uint64_t) ((r->batch + 32767) / 32768);
+    if (r->timing && (rc = timing_mark(r)) != 0) return rc;
     return 0;
 }
 
@@ -265,6 +342,35 @@ int glava_b200_update_rings(glava_b200* r, int modified) {
     if (!r) return fail(GLAVA_B200_EINVAL, "null argument");
     CU(cudaSetDevice(r->device));
     return run_update(r, r->d_ring[r->ring_cur][0], r->d_ring[r->ring_cur][1], modified);
+}
+
+int glava_b200_set_timing(glava_b200* r, int enable) {
+    if (!r) return fail(GLAVA_B200_EINVAL, "null argument");
+    CU(cudaSetDevice(r->device));
+    CU(cudaStreamSynchronize(r->stream));
+    for (cudaEvent_t e : r->ev) cudaEventDestroy(e);
+    r->ev.clear(); r->ev_modified.clear();
+    r->timing = enable != 0;
+    return 0;
+}
+
+int glava_b200_kernel_times(glava_b200* r, double* spectrum_ms, int* spectrum_launches, double* raster_ms, int* raster_launches) {
+    if (!r) return fail(GLAVA_B200_EINVAL, "null argument");
+    CU(cudaSetDevice(r->device));
+    CU(cudaStreamSynchronize(r->stream));
+    double s = 0, q = 0; int ns = 0, nq = 0;
+    for (size_t i = 0; i + 2 < r->ev.size() + 0 && i / 3 < r->ev_modified.size(); i += 3) {
+        float a = 0, b = 0;
+        CU(cudaEventElapsedTime(&a, r->ev[i], r->ev[i + 1]));
+        CU(cudaEventElapsedTime(&b, r->ev[i + 1], r->ev[i + 2]));
+        if (r->ev_modified[i / 3]) { s += a; ++ns; }
+        q += b; ++nq;
+    }
+    if (spectrum_ms) *spectrum_ms = s;
+    if (spectrum_launches) *spectrum_launches = ns;
+    if (raster_ms) *raster_ms = q;
+    if (raster_launches) *raster_launches = nq;
+    return 0;
 }
 
 int glava_b200_sync(glava_b200* r) {

@@ -55,9 +55,10 @@ GLB_HD float sample_audio_adj(const AudioTex& t, const uint16_t* tex, float idx,
 struct BarsCol { int cls; float v, vm; };      // cls 0: gap/out of range, 1: bar interior column, 2: bar edge column
 struct BarsRow { uint32_t fill, outl; };
 
-// ax = AREA_X (gl_FragCoord.x, or .y when MIRROR_YX), aw = AREA_WIDTH
-GLB_HD BarsCol bars_column(const glava_b200_params& p, const AudioTex& t, float ax, int aw) {
-    BarsCol c = { 0, 0.0f, 0.0f };
+// ax = AREA_X (gl_FragCoord.x, or .y when MIRROR_YX), aw = AREA_WIDTH.
+// Geometry half of the column: which texture (0 = audio_l, 1 = audio_r) is sampled at which
+// normalised position pp; returns false in gaps / outside [-1, 1].  `md_inner` = interior column.
+GLB_HD bool bars_column_coord(const glava_b200_params& p, float ax, int aw, int* chan, float* pp_out, bool* md_inner) {
     float dx;
     if (p.channels == 2) dx = ax - (float) (aw / 2);
     else dx = p.bars_invert == 1 ? (float) aw - ax : ax;
@@ -67,26 +68,32 @@ GLB_HD BarsCol bars_column(const glava_b200_params& p, const AudioTex& t, float 
     float md = m - center;
     float nbars = floorf(((float) aw * 0.5f) / section) * 2.0f;
     float hi = ceilf(p.bars_width / 2.0f), lo = -floorf(p.bars_width / 2.0f);
-    if (!(md < hi && md >= lo)) return c;
+    if (!(md < hi && md >= lo)) return false;
     float s = dx / section;
     float pp = (g_sign(s) == 1.0f ? ceilf(s) : floorf(s));
     if (p.channels == 2) pp /= (nbars / 2.0f); else pp /= nbars;
     pp += g_sign(pp) * ((0.5f + center) / (float) aw);
-    if (pp > 1.0f || pp < -1.0f) return c;
-    const uint16_t* tex;
+    if (pp > 1.0f || pp < -1.0f) return false;
     if (pp > 0.0f) {
         if (p.bars_direction == 1) pp = 1.0f - pp;
-        tex = (p.channels == 1 || p.bars_invert > 0) ? t.l : t.r;
+        *chan = (p.channels == 1 || p.bars_invert > 0) ? 0 : 1;
     } else {
         pp = fabsf(pp);
         if (p.bars_direction == 1) pp = 1.0f - pp;
-        tex = (p.channels == 1) ? t.l : (p.bars_invert > 0 ? t.r : t.l);
+        *chan = (p.channels == 1) ? 0 : (p.bars_invert > 0 ? 1 : 0);
     }
-    float v = sample_audio(t, tex, pp);
+    *pp_out = pp;
+    *md_inner = !(p.bars_outline_width > 0.0f) ||
+                (md < hi - p.bars_outline_width && md >= lo + p.bars_outline_width);
+    return true;
+}
+GLB_HD BarsCol bars_column(const glava_b200_params& p, const AudioTex& t, float ax, int aw) {
+    BarsCol c = { 0, 0.0f, 0.0f };
+    int chan; float pp; bool inner;
+    if (!bars_column_coord(p, ax, aw, &chan, &pp, &inner)) return c;
+    float v = sample_audio(t, chan ? t.r : t.l, pp);
     v *= p.bars_amplify;
     c.v = v; c.vm = v - p.bars_outline_width;
-    bool inner = !(p.bars_outline_width > 0.0f) ||
-                 (md < hi - p.bars_outline_width && md >= lo + p.bars_outline_width);
     c.cls = inner ? 1 : 2;
     return c;
 }
@@ -229,14 +236,21 @@ GLB_HD uint32_t circle_px(const glava_b200_params& p, const AudioTex& t, int x, 
 
 // ================================= graph (graph/1.frag, 2.frag) ==================================
 // column function: line height s(x), graph/1.frag:87-105 + side selection :124-132; pixel_center_integer
-GLB_HD float graph_height(const glava_b200_params& p, const AudioTex& t, int x) {
+// which texture (0 = audio_l, 1 = audio_r) and which normalised position column x samples
+GLB_HD float graph_column_coord(const glava_b200_params& p, int x, int* chan) {
     float fx = (float) x, W = (float) p.w;
     float half_w = (float) (p.w / 2);
+    float idx;
+    if (fx < half_w) { *chan = 0; idx = p.graph_direction < 0 ? fx : (half_w - fx); }
+    else             { *chan = 1; idx = p.graph_direction < 0 ? (-fx + W) : (fx - half_w); }
+    return idx / half_w;
+}
+GLB_HD float graph_height(const glava_b200_params& p, const AudioTex& t, int x) {
+    float fx = (float) x, W = (float) p.w;
     float pixel = 1.0f / W;
-    const uint16_t* tex; float idx;
-    if (fx < half_w) { tex = t.l; idx = p.graph_direction < 0 ? fx : (half_w - fx); }
-    else             { tex = t.r; idx = p.graph_direction < 0 ? (-fx + W) : (fx - half_w); }
-    float s = sample_audio_adj(t, tex, idx / half_w, pixel);
+    int chan;
+    float coord = graph_column_coord(p, x, &chan);
+    float s = sample_audio_adj(t, chan ? t.r : t.l, coord, pixel);
     s *= p.graph_vscale;
     float fact = g_clamp((fabsf((float) (p.w / 2) - fx) / W) * 48.0f, 0.0f, 1.0f);
     s *= fact;
@@ -283,12 +297,13 @@ GLB_HD uint32_t graph_px(const glava_b200_params& p, const AudioTex& t, int x, i
 
 // ================================= wave (wave/1.frag, 2.frag) ====================================
 struct WaveCol { float s, dmin, dmax, thick; uint32_t color; };
-GLB_HD float wave_tex(const AudioTex& t, float coord) {                     // texture(): NEAREST + REPEAT (render.c:514-517)
-    float u = coord * (float) t.n;
+GLB_HD int wave_tex_index(int n, float coord) {                             // texture(): NEAREST + REPEAT (render.c:514-517)
+    float u = coord * (float) n;
     int i = (int) floorf(u);
-    i %= t.n; if (i < 0) i += t.n;
-    return from16(t.l[i]);
+    i %= n; if (i < 0) i += n;
+    return i;
 }
+GLB_HD float wave_tex(const AudioTex& t, float coord) { return from16(t.l[wave_tex_index(t.n, coord)]); }
 GLB_HD WaveCol wave_column(const glava_b200_params& p, const AudioTex& t, int x) {   // wave/1.frag:17-31, pixel_center_integer
     float fx = (float) x, W = (float) p.w, H = (float) p.h;
     float os   = ((wave_tex(t, (fx + 0.0f) / W) - 0.5f) * p.wave_amplify) + 0.5f;

@@ -6,38 +6,58 @@ phases, white noise sigma 300 LSB, 0.5-2 Hz tremolo; every 4th stream is "quiet"
 """
 import numpy as np
 
+_K = 6
+_BLK = 4096
 
-def synth_pcm_int16(stream, t0, frames, rate=22050):
-    """Interleaved stereo int16 [frames*2] for absolute frame indices [t0, t0+frames)."""
+
+def _stream_params(stream):
     seed = (0x9E3779B9 * (int(stream) + 1)) & 0xFFFFFFFF
     rng = np.random.default_rng(seed)
-    K = 6
-    freq = np.exp(rng.uniform(np.log(40.0), np.log(10000.0), size=(2, K)))
-    amp = rng.uniform(500.0, 6000.0, size=(2, K))
-    phase = rng.uniform(0.0, 2 * np.pi, size=(2, K))
+    freq = np.exp(rng.uniform(np.log(40.0), np.log(10000.0), size=(2, _K)))
+    amp = rng.uniform(500.0, 6000.0, size=(2, _K))
+    phase = rng.uniform(0.0, 2 * np.pi, size=(2, _K))
     trem_f = rng.uniform(0.5, 2.0, size=2)
     trem_p = rng.uniform(0.0, 2 * np.pi, size=2)
-    if stream % 4 == 3:
+    quiet = (int(stream) % 4 == 3)
+    if quiet:
         amp = amp / 32.0
-    t = (np.arange(t0, t0 + frames, dtype=np.float64)) / float(rate)
+    return seed, freq, amp, phase, trem_f, trem_p, quiet
+
+
+def _noise(seed, quiet, t0, frames):
+    """white noise that depends on absolute time only (one generator per 4096-frame block)"""
     out = np.empty((frames, 2), dtype=np.float64)
-    # noise must depend on absolute time, not on the chunking: one generator per 4096-frame block
-    noise = np.empty((frames, 2), dtype=np.float64)
-    blk = 4096
-    b0, b1 = t0 // blk, (t0 + frames - 1) // blk
+    b0, b1 = t0 // _BLK, (t0 + frames - 1) // _BLK
     pos = 0
     for b in range(b0, b1 + 1):
         nr = np.random.default_rng((seed * 2654435761 + b) & 0xFFFFFFFFFFFF)
-        blockn = nr.standard_normal((blk, 2)) * (300.0 / (32.0 if stream % 4 == 3 else 1.0))
-        lo = max(t0, b * blk) - b * blk
-        hi = min(t0 + frames, (b + 1) * blk) - b * blk
-        noise[pos:pos + hi - lo] = blockn[lo:hi]
+        blockn = nr.standard_normal((_BLK, 2)) * (300.0 / (32.0 if quiet else 1.0))
+        lo = max(t0, b * _BLK) - b * _BLK
+        hi = min(t0 + frames, (b + 1) * _BLK) - b * _BLK
+        out[pos:pos + hi - lo] = blockn[lo:hi]
         pos += hi - lo
+    return out
+
+
+def synth_pcm_int16(stream, t0, frames, rate=22050):
+    """Interleaved stereo int16 [frames*2] of stream `stream` for absolute frames [t0, t0+frames)."""
+    seed, freq, amp, phase, trem_f, trem_p, quiet = _stream_params(stream)
+    t = (np.arange(t0, t0 + frames, dtype=np.float64)) / float(rate)
+    noise = _noise(seed, quiet, t0, frames)
+    out = np.empty((frames, 2), dtype=np.float64)
     for ch in range(2):
         sig = (amp[ch][None, :] * np.sin(2 * np.pi * freq[ch][None, :] * t[:, None] + phase[ch][None, :])).sum(axis=1)
         trem = 0.75 + 0.25 * np.sin(2 * np.pi * trem_f[ch] * t + trem_p[ch])
         out[:, ch] = sig * trem + noise[:, ch]
     return np.clip(np.rint(out), -32768, 32767).astype(np.int16).reshape(-1)
+
+
+def synth_batch_int16(first_stream, batch, t0, frames, rate=22050):
+    """[batch][frames][2] int16 — same values as synth_pcm_int16 stream by stream."""
+    out = np.empty((batch, frames, 2), dtype=np.int16)
+    for s in range(batch):
+        out[s] = synth_pcm_int16(first_stream + s, t0, frames, rate).reshape(frames, 2)
+    return out
 
 
 def fifo_to_float(chunk_int16):
@@ -62,15 +82,12 @@ class StreamRings:
 
     def chunks(self):
         """next hop of raw FIFO data for every stream: int16 [batch][hop*2]"""
-        out = np.empty((self.batch, self.hop * 2), dtype=np.int16)
-        for s in range(self.batch):
-            out[s] = synth_pcm_int16(self.first + s, self.t, self.hop, self.rate)
-        return out
+        return synth_batch_int16(self.first, self.batch, self.t, self.hop, self.rate).reshape(self.batch, self.hop * 2)
 
     def push(self, chunks):
         h = self.hop
         self.lb[:, :-h] = self.lb[:, h:].copy(); self.rb[:, :-h] = self.rb[:, h:].copy()
-        c = chunks.reshape(self.batch, h, 2)
+        c = np.asarray(chunks).reshape(self.batch, h, 2)
         self.lb[:, -h:] = c[:, :, 0].astype(np.float32) / np.float32(65535)
         self.rb[:, -h:] = c[:, :, 1].astype(np.float32) / np.float32(65535)
         self.t += h

@@ -167,6 +167,13 @@ int glava_b200_raster_textures(glava_b200* r, const uint16_t* tex_l, const uint1
 /* Kernel launch counters since creation (bench.py `gpu_launches`). */
 uint64_t glava_b200_launch_count(const glava_b200* r);
 
+/* Per-kernel device timing: when enabled, CUDA events are recorded on the handle's stream around
+ * the spectrum kernel and the raster kernel of every update; glava_b200_kernel_times() synchronises
+ * and returns the summed durations (ms) and launch counts since timing was (re-)enabled. */
+int glava_b200_set_timing(glava_b200* r, int enable);
+int glava_b200_kernel_times(glava_b200* r, double* spectrum_ms, int* spectrum_launches,
+                            double* raster_ms, int* raster_launches);
+
 /* ---- audio plug-in ABI kept verbatim from the reference (fifo.h:9-26) so a GLava audio
  * backend can feed this renderer: see INTEGRATION.md. ---- */
 

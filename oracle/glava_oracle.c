@@ -345,10 +345,11 @@ void orc_chan_update(orc_chan* c, const orc_params* p, const float* pcm, int is_
         for (int t = 0; t < n; ++t) { b[t] += 1.0f; b[t] /= 2.0f; }
         for (int t = 0; t < n; ++t) tex[t] = unorm16(b[t]);                  /* render.c:521-524 */
     } else if (!p->accel_fft) {
-        orc_fft_f32(p, b); gravity_a(c, p, b); average_a(c, p, b);            /* render.c:2149-2156 */
+        if (is_fft != 2) orc_fft_f32(p, b);
+        gravity_a(c, p, b); average_a(c, p, b);                               /* render.c:2149-2156 */
         for (int t = 0; t < n; ++t) tex[t] = unorm16(b[t]);
     } else {
-        orc_fft_f32(p, b);                                                    /* render.c:2177-2180 */
+        if (is_fft != 2) orc_fft_f32(p, b);                                   /* render.c:2177-2180 */
         float diff = p->gravity_step * (1.0f / p->ur);                        /* render.c:2224 */
         for (int t = 0; t < n; ++t) {
             uint16_t u = unorm16(b[t]);                                       /* upload, render.c:2185 */

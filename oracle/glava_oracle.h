@@ -88,7 +88,8 @@ void      orc_chan_free(orc_chan* c);
  *             accel_fft == 0; the raw transform_fft output when accel_fft == 1
  *  tex_u16  : n texels out — the R16 1-D texture the module shader samples
  *             (after upload quantisation, K1-K4 when accel, and K5 when smooth_pass)
- *  is_fft   : 1 for fft modules; 0 for `wave` (transform chain window+wrange, wave/1.frag:7-10)
+ *  is_fft   : 1 for fft modules; 0 for `wave` (transform chain window+wrange, wave/1.frag:7-10);
+ *             2 = `pcm` already holds transform_fft's output (computed by oracle/_ref)
  */
 void orc_chan_update(orc_chan* c, const orc_params* p, const float* pcm, int is_fft,
                      float* spec_f32, uint16_t* tex_u16);

@@ -1,0 +1,118 @@
+"""`#request` / `#define` config surface (glava_b200/csrc/config.cpp) — no GPU needed."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import glava_b200 as g
+from tests.conftest import GOLDEN
+
+REF_SHADERS = "/root/reference/shaders/glava"
+OWN_CONFIG = os.path.join(os.path.dirname(g.__file__), "config")
+
+
+def _same(a, b, skip=()):
+    for name, _ in g.Params._fields_:
+        if name in skip:
+            continue
+        va, vb = getattr(a, name), getattr(b, name)
+        if isinstance(va, (C.Structure, C.Array)):
+            assert bytes(va) == bytes(vb), name
+        else:
+            assert va == vb, name
+
+
+def test_defaults_match_shipped_values(built):
+    p = g.default_params("bars")
+    assert (p.n, p.avg_frames, p.avg_window, p.accel_fft, p.smooth_pass) == (4096, 5, 1, 1, 1)
+    assert p.fft_scale == np.float32(10.2) and p.fft_cutoff == np.float32(0.3) and p.gravity_step == np.float32(4.2)
+    assert p.ur == np.float32(22050 / 256)
+    assert (p.w, p.h) == (800, 600) and p.channels == 2 and p.premultiply_alpha == 1
+    assert p.bars_amplify == 300 and p.radial_nbars == 160 and p.circle_amplify == 150 and p.graph_vscale == 300
+    # colour literals are the "%.6f" strings glsl_ext.c:505 emits: #3366b2 -> (0.200000, 0.400000, 0.698039)
+    assert list(p.bars_color.lo)[:3] == [np.float32(0.2), np.float32(0.4), np.float32(0.698039)]
+
+
+def test_unknown_module_is_an_error(built):
+    with pytest.raises(g.GlavaError, match="Could not find module"):
+        g.default_params("spiral")
+
+
+def test_hex_colours_match_reference_parser(built):
+    # golden: ext_parse_color (glsl_ext.c:88-122) run from the compiled reference
+    gold = np.load(os.path.join(GOLDEN, "colors.npz"))
+    for name, rgba in zip(gold["names"], gold["rgba"]):
+        d = os.path.join(os.environ.get("TMPDIR", "/tmp"), "glava_b200_cfg_col")
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "rc.glsl"), "w") as f:
+            f.write("#request mod circle\n")
+        lit = str(name)
+        if lit.startswith("0x") or len(lit) == 8:
+            continue                                  # OUTLINE takes #rrggbb; alpha / 0x forms are setbg-only
+        with open(os.path.join(d, "circle.glsl"), "w") as f:
+            f.write(f"#define OUTLINE #{lit}\n")
+        p = g.load_config([d])
+        want = [np.float32(f"{float(v):.6f}") for v in rgba[:3]]
+        assert list(p.circle_outline)[:3] == want, lit
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SHADERS), reason="reference tree not present")
+@pytest.mark.parametrize("module", ["bars", "radial", "circle", "graph", "wave"])
+def test_reference_shipped_config_parses_to_builtin_defaults(module, built):
+    """the reference's own rc.glsl + smooth_parameters.glsl + <module>.glsl, unmodified"""
+    p = g.load_config([REF_SHADERS], force_module=module)
+    _same(p, g.default_params(module))
+
+
+@pytest.mark.parametrize("module", ["bars", "radial", "circle", "graph", "wave"])
+def test_own_config_dir(module, built):
+    p = g.load_config([OWN_CONFIG], force_module=module)
+    _same(p, g.default_params(module))
+
+
+def test_requests_and_user_override(tmp_path, built):
+    user, system = tmp_path / "user", tmp_path / "sys"
+    user.mkdir(); system.mkdir()
+    (system / "rc.glsl").write_text('#request mod radial\n#request setbufsize 2048\n#request setgeometry 0 0 1280 720\n'
+                                    '#request setmirror true\n#request setopacity "none"\n')
+    (system / "radial.glsl").write_text("#define NBARS 120\n#define C_LINE 3\n#define COLOR @fg:#ff0000\n#define ROTATE (PI / 4)\n")
+    (user / "radial.glsl").write_text("/* user copy wins */\n#define NBARS 96 // trailing comment\n#define AMPLIFY 250.5F\n")
+    (system / "smooth_parameters.glsl").write_text("#define SAMPLE_MODE hybrid\n#request setavgframes 7\n#request setgravitystep 3.5\n")
+    p = g.load_config([str(user), str(system)], requests=["setsmoothfactor 0.05", 'setaccelfft false'])
+    assert p.module_name == "radial" and p.n == 2048 and (p.w, p.h) == (1280, 720)
+    assert p.channels == 1 and p.premultiply_alpha == 0
+    assert p.radial_nbars == 96 and p.radial_amplify == np.float32(250.5)
+    assert p.radial_line == 3 and p.radial_line_half == 1            # (C_LINE / 2) is integer division for `3`
+    assert p.radial_color.mode == 1 and list(p.radial_color.lo) == [1.0, 0.0, 0.0, 1.0]
+    assert p.radial_rotate == np.float32(np.float32(3.14159265359) / np.float32(4))
+    assert p.sample_mode == 2 and p.avg_frames == 7 and p.gravity_step == np.float32(3.5)
+    assert p.smooth_factor == np.float32(0.05) and p.accel_fft == 0
+    # -m / force_module beats `#request mod`
+    assert g.load_config([str(user), str(system)], force_module="wave").module_name == "wave"
+
+
+@pytest.mark.parametrize("text,match", [
+    ("#request frobnicate 1\n", "unknown request type 'frobnicate'"),
+    ("#request setbufsize\n", "failed to execute request 'setbufsize'"),
+    ("#request setmirror maybe\n", "invalid raw string into a boolean"),
+    ('#request setopacity "shiny"\n', "Invalid opacity option"),
+    ("#request mod spiral\n", "Could not find module 'spiral'"),
+    ("#request setbufsize 3000\n", "power of two"),
+])
+def test_config_errors_use_the_reference_wording(tmp_path, text, match, built):
+    (tmp_path / "rc.glsl").write_text(text)
+    with pytest.raises(g.GlavaError, match=match):
+        g.load_config([str(tmp_path)])
+
+
+def test_missing_entry(tmp_path, built):
+    with pytest.raises(g.GlavaError, match="Could not find entry point"):
+        g.load_config([str(tmp_path)])
+
+
+def test_unsupported_colour_expression(tmp_path, built):
+    (tmp_path / "rc.glsl").write_text("#request mod bars\n")
+    (tmp_path / "bars.glsl").write_text("#define COLOR vec4(sin(d), 0, 0, 1)\n")
+    with pytest.raises(g.GlavaError, match="unsupported colour expression"):
+        g.load_config([str(tmp_path)])

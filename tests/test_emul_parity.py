@@ -1,0 +1,96 @@
+"""CPU tier: the product's kernel maths (glava_b200/csrc/*_core.h, compiled for the host by
+tests/emul) against the oracle.  Same checks the -m gpu tests make through the C ABI, so that
+arithmetic bugs are caught before GPU time is spent."""
+import numpy as np
+import pytest
+
+import glava_b200 as g
+from oracle.oracle import OracleChannel, params_from
+from tests import emul
+
+
+def _tex(n, seed):
+    return (np.random.default_rng(seed).random(n) ** 2 * 65535).astype(np.uint16)
+
+
+@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096, 8192, 16384])
+def test_stockham_fft_vs_reference_restatement(orc_pm, n, built):
+    p = g.default_params("bars", n=n); op = params_from(p)
+    x = (np.random.default_rng(n).standard_normal(n) * 0.2).astype(np.float32)
+    got = emul.fft(x)
+    f32 = orc_pm.fft_f32(op, x); f64 = orc_pm.fft_f64(op, x)
+    # north_star tolerance: 1e-5 of peak against render.c's transform.  The reference's own float
+    # twiddle recurrence is 1.2e-5 / 1.6e-5 away from exact arithmetic at N = 8192 / 16384,
+    # so above 4096 the bar is 1e-5 against the float64 evaluation and 2.5e-5 against the float32 one.
+    assert np.abs(got - f64).max() / f64.max() <= 2e-6
+    assert np.abs(got - f32).max() / f32.max() <= (1e-5 if n <= 4096 else 2.5e-5)
+
+
+@pytest.mark.parametrize("accel", [0, 1])
+@pytest.mark.parametrize("n", [1024, 4096])
+def test_update_chain(orc_pm, accel, n, built):
+    p = g.default_params("bars", n=n, accel_fft=accel); op = params_from(p)
+    rings = g.StreamRings(1, n)
+    oc = OracleChannel(orc_pm, op); ec = emul.Channel(p)
+    for _ in range(n // 256 + 7):
+        rings.advance()
+        s0, t0 = oc.update(rings.lb[0]); s1, t1 = ec.update(rings.lb[0])
+    assert np.abs(s0 - s1).max() / np.abs(s0).max() <= 1e-5
+    assert np.abs(t0.astype(int) - t1.astype(int)).max() <= 2          # R16 texels: <= 2 LSB16 (3e-5)
+
+
+@pytest.mark.parametrize("mode,formula", [(0, 0), (1, 0), (2, 0), (0, 1), (0, 2)])
+def test_smooth_pass_bit_exact(orc_pm, mode, formula, built):
+    n = 2048
+    p = g.default_params("bars", n=n, sample_mode=mode, round_formula=formula); op = params_from(p)
+    tex = _tex(n, 5)
+    assert np.array_equal(orc_pm.smooth_pass(op, tex), emul.smooth(p, tex))
+
+
+def test_wave_chain_bit_exact(orc_pm, built):
+    n = 2048
+    p = g.default_params("wave", n=n); op = params_from(p)
+    x = (np.random.default_rng(1).standard_normal(n) * 0.2).astype(np.float32)
+    s0, t0 = OracleChannel(orc_pm, op).update(x, is_fft=False)
+    s1, t1 = emul.Channel(p).update(x, is_fft=False)
+    assert np.array_equal(s0, s1) and np.array_equal(t0, t1)
+
+
+@pytest.mark.parametrize("module", g.MODULES)
+@pytest.mark.parametrize("w,h", [(640, 360), (333, 97)])
+def test_raster_bit_exact(orc_pm, module, w, h, built):
+    n = 2048
+    p = g.default_params(module, n=n, w=w, h=h); op = params_from(p)
+    tl = orc_pm.smooth_pass(op, _tex(n, 1)); tr = orc_pm.smooth_pass(op, _tex(n, 2))
+    want = orc_pm.raster(op, tl, tr)
+    assert np.array_equal(want, emul.raster(p, tl, tr))
+    if module in ("bars", "graph", "wave"):
+        assert np.array_equal(want, emul.raster(p, tl, tr, fast=True))      # hoisted evaluation of the kernels
+
+
+@pytest.mark.parametrize("over", [dict(bars_direction=1), dict(bars_invert=1), dict(bars_flip=1), dict(bars_mirror_yx=1),
+                                  dict(channels=1), dict(channels=1, bars_invert=1), dict(bars_outline_width=0.0),
+                                  dict(bars_outline_mode=1), dict(bars_width=3.0, bars_gap=2.0), dict(smooth_pass=0)])
+def test_bars_options(orc_pm, over, built):
+    n = 1024
+    p = g.default_params("bars", n=n, w=320, h=200, **over)
+    if over.get("bars_outline_mode") == 1:
+        p.bars_outline[0], p.bars_outline[1], p.bars_outline[2], p.bars_outline[3] = 0.9, 0.1, 0.2, 1.0
+    op = params_from(p)
+    tl, tr = _tex(n, 3), _tex(n, 4)
+    want = orc_pm.raster(op, tl, tr)
+    assert np.array_equal(want, emul.raster(p, tl, tr))
+    if not over.get("bars_mirror_yx"):
+        assert np.array_equal(want, emul.raster(p, tl, tr, fast=True))
+
+
+@pytest.mark.parametrize("module,over", [("radial", dict(radial_invert=1)), ("radial", dict(premultiply_alpha=0)),
+                                         ("circle", dict(circle_fill=1)), ("circle", dict(circle_smooth=0)),
+                                         ("circle", dict(circle_invert=1)), ("graph", dict(graph_direction=-1)),
+                                         ("graph", dict(graph_invert=1)), ("graph", dict(graph_draw_outline=1)),
+                                         ("graph", dict(graph_draw_highlight=0))])
+def test_module_options(orc_pm, module, over, built):
+    n = 1024
+    p = g.default_params(module, n=n, w=400, h=300, **over); op = params_from(p)
+    tl, tr = _tex(n, 6), _tex(n, 7)
+    assert np.array_equal(orc_pm.raster(op, tl, tr), emul.raster(p, tl, tr))
