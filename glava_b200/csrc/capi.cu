@@ -203,7 +203,7 @@ static int build(glava_b200* r) {
             r->need_count = (int) cnt;
         }
     }
-    if (p.module == GLAVA_B200_MOD_BARS) { if ((rc = launch_bars_rowtab(p, r->d_rowtab, r->stream)) != 0) return rc; ++r->launches; }
+    if (p.module == GLAVA_B200_MOD_BARS || p.module == GLAVA_B200_MOD_GRAPH) { if ((rc = launch_bars_rowtab(p, r->d_rowtab, r->stream)) != 0) return rc; ++r->launches; }
     CU(cudaStreamSynchronize(r->stream));
     return 0;
 }
@@ -284,10 +284,13 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
     }
     if (r->timing && (rc = timing_mark(r)) != 0) return rc;
     RasterArgs ra;
-    ra.tex = r->d_tex; ra.fb = r->d_fb; ra.rowtab = (p.module == GLAVA_B200_MOD_BARS) ? r->d_rowtab : nullptr;
+    ra.tex = r->d_tex; ra.fb = r->d_fb; ra.rowtab = (p.module == GLAVA_B200_MOD_BARS || p.module == GLAVA_B200_MOD_GRAPH) ? r->d_rowtab : nullptr;
     ra.batch = r->batch; ra.slots = r->slots; ra.stream0 = 0;
     if ((rc = launch_raster(p, ra, r->stream)) != 0) return rc;
-    r->launches += (uint64_t) ((r->batch + 32767) / 32768);
+    {
+        const int chunk = r->slots < 32768 ? r->slots : 32768;          // see launch_raster
+        r->launches += (uint64_t) ((r->batch + chunk - 1) / chunk);
+    }
     if (r->timing && (rc = timing_mark(r)) != 0) return rc;
     return 0;
 }

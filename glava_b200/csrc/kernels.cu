@@ -15,6 +15,8 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 namespace glb {
 
 // ---------------------------------------------------------------------------------------------
@@ -270,7 +272,8 @@ __device__ __forceinline__ AudioTex make_tex(const glava_b200_params& p, const u
     return t;
 }
 __device__ __forceinline__ void store4(uint32_t* row, int x, int w, const uint32_t px[4]) {
-    if (x + 3 < w) __stcs(reinterpret_cast<uint4*>(row + x), make_uint4(px[0], px[1], px[2], px[3]));
+    // rows are 16-byte aligned only when w is a multiple of 4 (x always is)
+    if ((w & 3) == 0) __stcs(reinterpret_cast<uint4*>(row + x), make_uint4(px[0], px[1], px[2], px[3]));
     else for (int k = 0; k < 4 && x + k < w; ++k) row[x + k] = px[k];
 }
 
@@ -312,6 +315,7 @@ raster_generic_kernel(const __grid_constant__ RasterArgs a, const __grid_constan
 __global__ void bars_rowtab_kernel(uint2* __restrict__ tab, const __grid_constant__ glava_b200_params p) {
     int y = blockIdx.x * blockDim.x + threadIdx.x;
     if (y >= p.h) return;
+    if (p.module == GLAVA_B200_MOD_GRAPH) { tab[y] = make_uint2(graph_row(p, y), 0u); return; }
     float fy = (float) y + 0.5f;
     float d = p.bars_flip ? (float) p.h - fy : fy;
     BarsRow r = bars_row(p, d);
@@ -324,38 +328,67 @@ int launch_bars_rowtab(const glava_b200_params& p, void* d_rowtab, void* stream)
     return 0;
 }
 
+// Rows are addressed by t = distance from the bars' base line (t = y, or h-1-y with FLIP), for which
+// d = t + 0.5 exactly in float.  `d < lim` / `d <= lim` are monotone in t, so each column's two float
+// compares per pixel collapse into two integer row thresholds computed once (and corrected with the
+// exact float predicate, so the result is bit-identical to evaluating bars/1.frag per pixel).
+__device__ __forceinline__ int bars_rows_below(float lim, bool inclusive, int h) {
+    float e = ceilf(lim - 0.5f);
+    int t = (e > 0.0f) ? ((e < (float) h) ? (int) e : h) : 0;
+    while (t > 0 && !(inclusive ? ((float) (t - 1) + 0.5f <= lim) : ((float) (t - 1) + 0.5f < lim))) --t;
+    while (t < h && (inclusive ? ((float) t + 0.5f <= lim) : ((float) t + 0.5f < lim))) ++t;
+    return t;
+}
+
+// requires w % 4 == 0 (128-bit row alignment) and MIRROR_YX == 0
 __global__ void __launch_bounds__(256)
 raster_bars_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__ glava_b200_params p, int rows_per_cta) {
     const int stream = a.stream0 + blockIdx.z;
     const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (x >= p.w) return;
+    const bool valid = x < p.w;
     const AudioTex t = make_tex(p, a.tex, stream);
-    uint32_t* fb = reinterpret_cast<uint32_t*>(a.fb) + (size_t) (stream % a.slots) * p.w * p.h;
     const uint2* __restrict__ rowtab = reinterpret_cast<const uint2*>(a.rowtab);
-    BarsCol col[4];
+    const bool has_outline = p.bars_outline_width > 0.0f;
+    int ya[4], yb[4]; bool inner[4];
+    int tmax = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        if (x + k < p.w) col[k] = bars_column(p, t, (float) (x + k) + 0.5f, p.w);
-        else { col[k].cls = 0; col[k].v = 0.0f; col[k].vm = 0.0f; }
+        BarsCol c = { 0, 0.0f, 0.0f };
+        if (valid) c = bars_column(p, t, (float) (x + k) + 0.5f, p.w);
+        inner[k] = c.cls == 1;
+        ya[k] = c.cls ? bars_rows_below(c.vm, false, p.h) : 0;          // t <  ya : d <  v - outline  -> COLOR / BAR_OUTLINE by column
+        yb[k] = (c.cls && has_outline) ? bars_rows_below(c.v, true, p.h) : 0;   // t <  yb : d <= v            -> BAR_OUTLINE
+        tmax = max(tmax, max(ya[k], yb[k]));
     }
-    const bool has_outline = p.bars_outline_width > 0.0f;
+    tmax = __reduce_max_sync(0xffffffffu, tmax);                          // rows t >= tmax are 0 for the whole warp
     const int y0 = blockIdx.y * rows_per_cta, y1 = min(p.h, y0 + rows_per_cta);
-    for (int y = y0; y < y1; ++y) {
-        const uint2 rc = __ldg(&rowtab[y]);
-        const float fy = (float) y + 0.5f;
-        const float d = p.bars_flip ? (float) p.h - fy : fy;
-        uint32_t px[4];
+    const int stride = p.w >> 2;
+    uint4* const base = reinterpret_cast<uint4*>(a.fb) + (size_t) (stream % a.slots) * stride * p.h + (x >> 2);
+    // split the band into the rows that can hold bar pixels and the all-zero rest
+    int f0, f1, z0, z1;
+    if (!p.bars_flip) { f0 = y0; f1 = min(y1, tmax); z0 = max(y0, tmax); z1 = y1; }
+    else              { z0 = y0; z1 = min(y1, p.h - tmax); f0 = max(y0, p.h - tmax); f1 = y1; }
+    {
+        uint4* ptr = base + (size_t) z0 * stride;
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        for (int y = z0; y < z1; ++y, ptr += stride) if (valid) __stcs(ptr, zero);
+    }
+    {
+        uint4* ptr = base + (size_t) f0 * stride;
+        for (int y = f0; y < f1; ++y, ptr += stride) {
+            const uint2 rc = __ldg(&rowtab[y]);
+            const int tt = p.bars_flip ? (p.h - 1 - y) : y;
+            uint32_t px[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            uint32_t below = (col[k].cls == 1) ? rc.x : rc.y;
-            uint32_t v = (d < col[k].vm) ? below : ((has_outline && d <= col[k].v) ? rc.y : 0u);
-            px[k] = col[k].cls ? v : 0u;
+            for (int k = 0; k < 4; ++k) px[k] = (tt < ya[k]) ? (inner[k] ? rc.x : rc.y) : ((tt < yb[k]) ? rc.y : 0u);
+            if (valid) __stcs(ptr, make_uint4(px[0], px[1], px[2], px[3]));
         }
-        store4(fb + (size_t) y * p.w, x, p.w, px);
     }
 }
 
-// graph: heights of 6 columns in registers, rolling row colours
+// graph: heights of 6 columns in registers, rolling row colours.  Pixels whose whole 3x3
+// neighbourhood is filled (or empty) skip the stencil: exact, because then avg.a is exactly the row
+// alpha (or 0) and graph/2.frag changes nothing.
 __global__ void __launch_bounds__(256)
 raster_graph_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__ glava_b200_params p, int rows_per_cta) {
     const int stream = a.stream0 + blockIdx.z;
@@ -369,17 +402,34 @@ raster_graph_kernel(const __grid_constant__ RasterArgs a, const __grid_constant_
         int xc = x - 1 + k;
         s[k] = (xc >= 0 && xc < p.w) ? graph_height(p, t, xc) : 0.0f;
     }
+    float lo[4], hi[4]; bool inner_x[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        lo[k] = fminf(s[k], fminf(s[k + 1], s[k + 2]));
+        hi[k] = fmaxf(s[k], fmaxf(s[k + 1], s[k + 2]));
+        inner_x[k] = (x + k - 1 >= 0) && (x + k + 1 < p.w);
+    }
     const int y0 = blockIdx.y * rows_per_cta, y1 = min(p.h, y0 + rows_per_cta);
+    const uint2* __restrict__ rowtab = reinterpret_cast<const uint2*>(a.rowtab);   // [h] graph_row(y)
     uint32_t row3[3];
-    row3[0] = y0 > 0 ? graph_row(p, y0 - 1) : 0u;
-    row3[1] = graph_row(p, y0);
+    row3[0] = y0 > 0 ? __ldg(&rowtab[y0 - 1]).x : 0u;
+    row3[1] = __ldg(&rowtab[y0]).x;
     for (int y = y0; y < y1; ++y) {
-        row3[2] = (y + 1 < p.h) ? graph_row(p, y + 1) : 0u;
+        row3[2] = (y + 1 < p.h) ? __ldg(&rowtab[y + 1]).x : 0u;
+        const float dm = graph_d(p, y - 1), dc = graph_d(p, y), dp = graph_d(p, y + 1);
+        const float dhi = fmaxf(dm, dp) + 1.5f, dlo = fminf(dm, dp) + 1.5f;   // stage-1 test is d + 1.5 <= s
+        const bool inner_y = (y - 1 >= 0) && (y + 1 < p.h);
+        const bool opaque = ((row3[0] & row3[1] & row3[2]) >> 24) == 255u;
         uint32_t px[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float s3[3] = { s[k], s[k + 1], s[k + 2] };
-            px[k] = (x + k < p.w) ? graph_px_cols(p, s3, row3, x + k, y) : 0u;
+            if (dlo > hi[k]) px[k] = 0u;                                              // 3x3 all empty
+            else if (dhi <= lo[k] && inner_x[k] && inner_y && opaque) px[k] = row3[1]; // 3x3 all filled, alpha 1
+            else {
+                const float s3[3] = { s[k], s[k + 1], s[k + 2] };
+                px[k] = (x + k < p.w) ? graph_px_cols(p, s3, row3, x + k, y) : 0u;
+            }
+            (void) dc;
         }
         store4(fb + (size_t) y * p.w, x, p.w, px);
         row3[0] = row3[1]; row3[1] = row3[2];
@@ -401,20 +451,115 @@ raster_wave_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__
         xc = xc < 0 ? 0 : (xc >= p.w ? p.w - 1 : xc);   // clamped columns are masked by wave_px_cols
         c[k] = wave_column(p, t, xc);
     }
+    // rows where any of a pixel's three columns can be lit (+-1 row for the stencil), conservative
+    float ylo[4], yhi[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float l = 3.0e38f, h = -3.0e38f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const WaveCol& w = c[k + j];
+            l = fminf(l, fminf(w.s - w.thick, w.s + w.dmin));
+            h = fmaxf(h, fmaxf(w.s + w.thick, w.s + w.dmax));
+        }
+        ylo[k] = l - 2.0f; yhi[k] = h + 2.0f;
+    }
     const int y0 = blockIdx.y * rows_per_cta, y1 = min(p.h, y0 + rows_per_cta);
     for (int y = y0; y < y1; ++y) {
+        const float fy = (float) y;
         uint32_t px[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
+            if (fy < ylo[k] || fy > yhi[k] || x + k >= p.w) { px[k] = 0u; continue; }
             const WaveCol c3[3] = { c[k], c[k + 1], c[k + 2] };
-            px[k] = (x + k < p.w) ? wave_px_cols(p, c3, x + k, y) : 0u;
+            px[k] = wave_px_cols(p, c3, x + k, y);
+        }
+        store4(fb + (size_t) y * p.w, x, p.w, px);
+    }
+}
+
+// circle: stage 1 (polar line test) is evaluated once per pixel of a tile + 1-pixel halo into shared
+// memory, then stages 2 (8-neighbour fill-in) and 3 (premultiply) read the tile.  Pixels outside the
+// annulus [C_RADIUS - C_LINE/2, C_RADIUS + AMPLIFY + ...] are exactly 0 and skip the maths.
+#define CIRCLE_TW 128
+#define CIRCLE_TH 8
+__global__ void __launch_bounds__(256)
+raster_circle_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__ glava_b200_params p) {
+    __shared__ uint32_t tile[CIRCLE_TH + 2][CIRCLE_TW + 2];
+    const int stream = a.stream0 + blockIdx.z;
+    const AudioTex t = make_tex(p, a.tex, stream);
+    uint32_t* fb = reinterpret_cast<uint32_t*>(a.fb) + (size_t) (stream % a.slots) * p.w * p.h;
+    const int tx0 = blockIdx.x * CIRCLE_TW, ty0 = blockIdx.y * CIRCLE_TH;
+    const float cx = (float) (p.w / 2), cy = (float) (p.h / 2);
+    const float reach = circle_reach(p);
+    const float inner = p.circle_radius - p.circle_line / 2.0f - 2.0f;
+    // distance range of the tile (+halo) from the centre
+    const float bx0 = (float) (tx0 - 1) - cx, bx1 = (float) (tx0 + CIRCLE_TW) - cx;
+    const float by0 = (float) (ty0 - 1) - cy, by1 = (float) (ty0 + CIRCLE_TH) - cy;
+    const float nx = (bx0 > 0.0f) ? bx0 : ((bx1 < 0.0f) ? -bx1 : 0.0f), ny = (by0 > 0.0f) ? by0 : ((by1 < 0.0f) ? -by1 : 0.0f);
+    const float fxm = fmaxf(fabsf(bx0), fabsf(bx1)), fym = fmaxf(fabsf(by0), fabsf(by1));
+    const bool tile_dead = (nx * nx + ny * ny > reach * reach) || (inner > 0.0f && fxm * fxm + fym * fym < inner * inner);
+    if (!tile_dead) {
+        for (int i = threadIdx.x; i < (CIRCLE_TH + 2) * (CIRCLE_TW + 2); i += blockDim.x) {
+            const int ly = i / (CIRCLE_TW + 2), lx = i - ly * (CIRCLE_TW + 2);
+            const int gx = tx0 + lx - 1, gy = ty0 + ly - 1;
+            uint32_t v = 0u;
+            if (gx >= 0 && gy >= 0 && gx < p.w && gy < p.h) {
+                const float dx = (float) gx - cx, dy = (float) gy - cy;
+                const float d2 = dx * dx + dy * dy;
+                if (d2 <= reach * reach && !(inner > 0.0f && d2 < inner * inner)) v = circle_stage1(p, t, gx, gy);
+            }
+            tile[ly][lx] = v;
+        }
+        __syncthreads();
+    }
+    // 256 threads: 32 quads per row x 8 rows
+    const int qx = threadIdx.x & 31, qy = threadIdx.x >> 5;
+    const int x = tx0 + qx * 4, y = ty0 + qy;
+    if (x >= p.w || y >= p.h) return;
+    uint32_t px[4] = { 0u, 0u, 0u, 0u };
+    if (!tile_dead) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int lx = qx * 4 + k + 1, ly = qy + 1;
+            const uint32_t own = tile[ly][lx];
+            const uint32_t nb[6] = { tile[ly][lx + 1], tile[ly + 1][lx + 1], tile[ly + 1][lx],
+                                     tile[ly][lx - 1], tile[ly - 1][lx - 1], tile[ly - 1][lx] };
+            if (x + k < p.w) px[k] = ((own | nb[0] | nb[1] | nb[2] | nb[3] | nb[4] | nb[5]) == 0u) ? 0u : circle_finish(p, own, nb);
+        }
+    }
+    store4(fb + (size_t) y * p.w, x, p.w, px);
+}
+
+// radial: per-pixel polar maths (radial/1.frag + premultiply) with disc culling; same arithmetic as
+// raster_generic_kernel but without the module switch (no spills).
+__global__ void __launch_bounds__(128)
+raster_radial_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__ glava_b200_params p, int rows_per_cta) {
+    const int stream = a.stream0 + blockIdx.z;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (x >= p.w) return;
+    const AudioTex t = make_tex(p, a.tex, stream);
+    uint32_t* fb = reinterpret_cast<uint32_t*>(a.fb) + (size_t) (stream % a.slots) * p.w * p.h;
+    const float reach = radial_reach(p), r2 = reach * reach;
+    const float cx = (float) (p.w / 2) - p.radial_off_x, cy = (float) (p.h / 2) - p.radial_off_y;
+    const float dxa = (float) x - cx, dxb = (float) (x + 3) - cx;
+    float dxm = ((dxa > 0.0f) ? dxa : ((dxb < 0.0f) ? -dxb : 0.0f)) - 1.0f;     // span distance from cx, 1 px slack
+    if (dxm < 0.0f) dxm = 0.0f;
+    const int y0 = blockIdx.y * rows_per_cta, y1 = min(p.h, y0 + rows_per_cta);
+    for (int y = y0; y < y1; ++y) {
+        uint32_t px[4] = { 0u, 0u, 0u, 0u };
+        float dy = fabsf((float) y - cy) - 1.0f;
+        if (dy < 0.0f) dy = 0.0f;
+        if (dxm * dxm + dy * dy <= r2) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (x + k < p.w) px[k] = radial_px(p, t, x + k, y);
         }
         store4(fb + (size_t) y * p.w, x, p.w, px);
     }
 }
 
 static int pick_block_x(int quads) {       // threads per row-segment: prefer an exact tiling of w/4
-    static const int cand[] = { 256, 192, 160, 128, 96, 64 };
+    static const int cand[] = { 96, 160, 128, 192, 256, 64 };    // measured on B200: 96 >= 160 > 256 for the store-bound kernels
     for (int c : cand) if (quads % c == 0) return c;
     return 128;
 }
@@ -422,21 +567,33 @@ static int pick_block_x(int quads) {       // threads per row-segment: prefer an
 int launch_raster(const glava_b200_params& p, const RasterArgs& a, void* stream) {
     cudaStream_t st = (cudaStream_t) stream;
     const int quads = (p.w + 3) / 4;
-    const bool fast_bars  = p.module == GLAVA_B200_MOD_BARS && !p.bars_mirror_yx && a.rowtab;
-    const bool fast_graph = p.module == GLAVA_B200_MOD_GRAPH;
+    const bool fast_bars  = p.module == GLAVA_B200_MOD_BARS && !p.bars_mirror_yx && a.rowtab && (p.w & 3) == 0;
+    const bool fast_graph = p.module == GLAVA_B200_MOD_GRAPH && a.rowtab;
     const bool fast_wave  = p.module == GLAVA_B200_MOD_WAVE;
     int bx = (fast_bars || fast_graph || fast_wave) ? pick_block_x(quads) : 128;
     if (bx > 256) bx = 256;
-    int rows = (fast_bars || fast_graph || fast_wave) ? 135 : 8;
+    int rows = fast_bars ? 270 : ((fast_graph || fast_wave) ? 135 : 8);
+    // development overrides for tuning sweeps (tools/tune_raster.py); unset in normal use
+    if (const char* e = getenv("GLAVA_B200_ROWS")) { int v = atoi(e); if (v > 0) rows = v; }
+    if (const char* e = getenv("GLAVA_B200_BX")) { int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) bx = v; }
     if (rows > p.h) rows = p.h;
     // z dimension limit 65535: chunk the batch
-    for (int s0 = 0; s0 < a.batch; s0 += 32768) {
+    // one launch covers at most `slots` streams (and at most the grid z limit): with a framebuffer
+    // ring (fb_slots < batch) two streams of one launch must never share a slot, and launches on
+    // the same stream are ordered, so slot s % slots ends up holding the highest stream mapped to it.
+    const int chunk = a.slots < 32768 ? (a.slots > 0 ? a.slots : 1) : 32768;
+    for (int s0 = 0; s0 < a.batch; s0 += chunk) {
         RasterArgs b = a; b.stream0 = a.stream0 + s0;
-        int nz = a.batch - s0 < 32768 ? a.batch - s0 : 32768;
+        int nz = a.batch - s0 < chunk ? a.batch - s0 : chunk;
         dim3 grid((quads + bx - 1) / bx, (p.h + rows - 1) / rows, nz);
         if (fast_bars) raster_bars_kernel<<<grid, bx, 0, st>>>(b, p, rows);
         else if (fast_graph) raster_graph_kernel<<<grid, bx, 0, st>>>(b, p, rows);
         else if (fast_wave) raster_wave_kernel<<<grid, bx, 0, st>>>(b, p, rows);
+        else if (p.module == GLAVA_B200_MOD_RADIAL) raster_radial_kernel<<<grid, bx, 0, st>>>(b, p, rows);
+        else if (p.module == GLAVA_B200_MOD_CIRCLE) {
+            dim3 cgrid((p.w + CIRCLE_TW - 1) / CIRCLE_TW, (p.h + CIRCLE_TH - 1) / CIRCLE_TH, nz);
+            raster_circle_kernel<<<cgrid, 256, 0, st>>>(b, p);
+        }
         else raster_generic_kernel<<<grid, bx, 0, st>>>(b, p, rows);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "raster kernel launch: %s", cudaGetErrorString(e));

@@ -156,7 +156,11 @@ GLB_HD uint32_t radial_px(const glava_b200_params& p, const AudioTex& t, int x, 
             }
         }
     }
-    if (!done) frag = apply_frag(frag, mk4(0, 0, 0, 0));
+    if (!done) {
+        // neither ring nor bar: apply_frag(0, 0) = 0 and stage 2 keeps 0 — skip the arithmetic
+        if (frag.r == 0.0f && frag.g == 0.0f && frag.b == 0.0f && frag.a == 0.0f) return 0u;
+        frag = apply_frag(frag, mk4(0, 0, 0, 0));
+    }
     uint32_t px = pack8(frag);
     return p.premultiply_alpha ? premultiply8(px) : px;                    // radial/2.frag
 }

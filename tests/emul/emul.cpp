@@ -147,6 +147,14 @@ int emul_chan_update(emul_chan* c, const glava_b200_params* pp, const float* pcm
     return 0;
 }
 
+// exhaustive check helper: returns the number of u for which from8/from16 differ from true division
+int emul_unorm_fetch_mismatches(void) {
+    int bad = 0;
+    for (uint32_t u = 0; u < 256; ++u) { volatile float d = (float) u / 255.0f; if (from8(u) != d) ++bad; }
+    for (uint32_t u = 0; u < 65536; ++u) { volatile float d = (float) u / 65535.0f; if (from16(u) != d) ++bad; }
+    return bad;
+}
+
 void emul_smooth(const glava_b200_params* p, const uint16_t* in, uint16_t* out) {
     SmoothParams sp = smooth_params(*p);
     for (int x = 0; x < p->n; ++x) out[x] = (uint16_t) smooth_pass_texel(sp, in, p->n, x);

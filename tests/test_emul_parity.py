@@ -94,3 +94,8 @@ def test_module_options(orc_pm, module, over, built):
     p = g.default_params(module, n=n, w=400, h=300, **over); op = params_from(p)
     tl, tr = _tex(n, 6), _tex(n, 7)
     assert np.array_equal(orc_pm.raster(op, tl, tr), emul.raster(p, tl, tr))
+
+
+def test_unorm_fetch_is_exact_division(built):
+    """from8 / from16 use reciprocal + fma correction instead of a divide: must equal u / MAX for every u"""
+    assert emul.lib().emul_unorm_fetch_mismatches() == 0

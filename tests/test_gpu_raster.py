@@ -1,0 +1,105 @@
+"""-m gpu: module raster kernels through the C ABI, bit-exact against the oracle on identical textures."""
+import numpy as np
+import pytest
+
+import glava_b200 as g
+from oracle.oracle import OracleChannel, params_from
+
+pytestmark = pytest.mark.gpu
+
+
+def _textures(orc, op, n, batch, seed):
+    rng = np.random.default_rng(seed)
+    tl = np.stack([orc.smooth_pass(op, (rng.random(n) ** 2 * 65535).astype(np.uint16)) for _ in range(batch)])
+    tr = np.stack([orc.smooth_pass(op, (rng.random(n) ** 3 * 65535).astype(np.uint16)) for _ in range(batch)])
+    if batch > 2:
+        tl[1] = 0; tr[1] = 0                       # silence
+        tl[2] = 65535; tr[2] = 65535               # saturated R16
+    return tl, tr
+
+
+def _check(orc, p, batch=3, seed=0):
+    op = params_from(p)
+    tl, tr = _textures(orc, op, p.n, batch, seed)
+    if p.module == 4:
+        tl = np.clip(tl.astype(int) // 4 + 24576, 0, 65535).astype(np.uint16)      # PCM-like values around 0.5
+    with g.Renderer(p, batch=batch) as r:
+        r.raster_textures(tl, tr)
+        for s in range(batch):
+            got = r.readback(s)
+            want = orc.raster(op, tl[s], tr[s])
+            assert np.array_equal(got, want), (p.module_name, s, int((got != want).any(axis=2).sum()))
+
+
+@pytest.mark.parametrize("module", g.MODULES)
+@pytest.mark.parametrize("w,h", [(640, 360), (332, 97), (1920, 1080)])
+def test_modules_bit_exact(orc_pm, module, w, h, built):
+    _check(orc_pm, g.default_params(module, n=2048 if w < 1920 else 4096, w=w, h=h), batch=3 if w < 1920 else 2)
+
+
+@pytest.mark.parametrize("w", [333, 331, 6])
+def test_widths_not_multiple_of_four(orc_pm, w, built):
+    for module in ("bars", "graph", "wave", "radial"):
+        _check(orc_pm, g.default_params(module, n=1024, w=w, h=40), batch=1)
+
+
+@pytest.mark.parametrize("over", [dict(bars_direction=1), dict(bars_invert=1), dict(bars_flip=1), dict(bars_mirror_yx=1),
+                                  dict(channels=1), dict(channels=1, bars_invert=1), dict(bars_outline_width=0.0),
+                                  dict(bars_width=3.0, bars_gap=2.0), dict(smooth_pass=0)])
+def test_bars_options(orc_pm, over, built):
+    _check(orc_pm, g.default_params("bars", n=1024, w=320, h=200, **over), batch=2)
+
+
+@pytest.mark.parametrize("module,over", [("radial", dict(radial_invert=1)), ("radial", dict(premultiply_alpha=0)),
+                                         ("radial", dict(radial_off_x=40.0, radial_off_y=-25.0)),
+                                         ("circle", dict(circle_fill=1)), ("circle", dict(circle_smooth=0)),
+                                         ("circle", dict(circle_invert=1)), ("graph", dict(graph_direction=-1)),
+                                         ("graph", dict(graph_invert=1)), ("graph", dict(graph_draw_outline=1)),
+                                         ("graph", dict(graph_draw_highlight=0))])
+def test_module_options(orc_pm, module, over, built):
+    _check(orc_pm, g.default_params(module, n=1024, w=400, h=300, **over), batch=2)
+
+
+def test_reference_known_answer_on_gpu(built):
+    """the reference's only in-tree KAT: module `test` renders uniform #55000055 (test_rc.glsl:27)"""
+    p = g.default_params("test", n=4096, w=640, h=640)
+    rings = g.StreamRings(1, 4096)
+    with g.Renderer(p, batch=1) as r:
+        rings.advance(); r.update(rings.lb, rings.rb, True)
+        img = r.readback(0)
+    assert np.all(img == np.array([0x55, 0, 0, 0x55], np.uint8))
+
+
+def test_libm_oracle_within_one_lsb(orc, built):
+    """independent checker (libm transcendentals): <= 1 LSB per channel, bar a few hard-edge flips"""
+    for module in ("radial", "circle"):
+        p = g.default_params(module, n=2048, w=640, h=360); op = params_from(p)
+        tl, tr = _textures(orc, op, 2048, 1, 9)
+        with g.Renderer(p, batch=1) as r:
+            r.raster_textures(tl, tr); got = r.readback(0).astype(int)
+        want = orc.raster(op, tl[0], tr[0]).astype(int)
+        assert (np.abs(got - want).max(axis=2) > 1).sum() <= 8
+
+
+def test_fb_slots_ring_and_rerender(orc_pm, built):
+    n, batch = 1024, 5
+    p = g.default_params("bars", n=n, w=128, h=64, fb_slots=2); op = params_from(p)
+    tl, tr = _textures(orc_pm, op, n, batch, 4)
+    with g.Renderer(p, batch=batch) as r:
+        r.raster_textures(tl, tr)
+        # slot = stream % 2: the last stream mapped to each slot is what it holds
+        assert np.array_equal(r.readback(4), orc_pm.raster(op, tl[4], tr[4]))
+        assert np.array_equal(r.readback(3), orc_pm.raster(op, tl[3], tr[3]))
+
+
+def test_modified_false_rerasters_last_spectrum(built):
+    n = 1024
+    p = g.default_params("graph", n=n, w=256, h=128)
+    rings = g.StreamRings(2, n)
+    with g.Renderer(p, batch=2) as r:
+        for _ in range(6):
+            rings.advance(); r.update(rings.lb, rings.rb, True)
+        a = r.readback(1); t0 = r.textures()
+        rings.advance(); r.update(rings.lb, rings.rb, False)          # no audio update: render.c:2268-2272
+        b = r.readback(1); t1 = r.textures()
+    assert np.array_equal(a, b) and np.array_equal(t0[0], t1[0])
