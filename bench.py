@@ -221,8 +221,8 @@ def main():
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record(stream)
     for i in range(K):
-        r.update(host_l[i % nsnap], host_r[i % nsnap], True)
-        r.readback(i % batch, frame_pinned)
+        r.update(host_l[i % nsnap], host_r[i % nsnap], True)     # H2D (copy stream) + kernels
+        r.readback_async(i % batch, frame_pinned)                # D2H of one stream's frame, same stream as the kernels
     e3.record(stream)
     r.sync()
     barrier()

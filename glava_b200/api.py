@@ -92,6 +92,7 @@ def lib():
     L.glava_b200_update_rings.argtypes = [vp, i32]
     L.glava_b200_sync.argtypes = [vp]
     L.glava_b200_readback.argtypes = [vp, i32, vp]
+    L.glava_b200_readback_async.argtypes = [vp, i32, vp]
     L.glava_b200_spectrum.argtypes = [vp, vp, vp]
     L.glava_b200_textures.argtypes = [vp, vp, vp]
     L.glava_b200_framebuffer_device.argtypes = [vp]
@@ -207,6 +208,10 @@ class Renderer:
             out = np.empty((p.h, p.w, 4), dtype=np.uint8)
         _check(self._L.glava_b200_readback(self._h, int(stream), out.ctypes.data))
         return out
+
+    def readback_async(self, stream, out):
+        """enqueue the D2H copy of one frame into `out` (pinned uint8 [h][w][4]); valid after sync()"""
+        _check(self._L.glava_b200_readback_async(self._h, int(stream), out.ctypes.data))
 
     def spectrum(self):
         l = np.empty((self.batch, self.params.n), dtype=np.float32); r = np.empty_like(l)

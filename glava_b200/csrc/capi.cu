@@ -50,7 +50,10 @@ struct glava_b200 {
     int batch, device, slots;
     cudaStream_t stream;
     // inputs
-    float* d_pcm[2];            // H2D staging for glava_b200_update         [batch][n] x {l, r}
+    float* d_pcm[2][2];         // H2D staging for glava_b200_update, double-buffered  [2][batch][n] x {l, r}
+    int    stage_cur;
+    cudaStream_t copy_stream;   // H2D of update i+1 overlaps the kernels of update i
+    cudaEvent_t ev_copied[2], ev_free[2];
     float* d_ring[2][2];        // FIFO rings, ping-pong                      [2][batch][n] x {l, r}
     int    ring_cur;
     int16_t* d_chunks; size_t chunks_cap;
@@ -164,7 +167,12 @@ static int build(glava_b200* r) {
     CU(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
     int rc;
 #define ALLOC(ptr, bytes, zero) if ((rc = dev_alloc(r, (void**) &(ptr), (bytes), (zero))) != 0) return rc
-    ALLOC(r->d_pcm[0], (size_t) r->batch * n * 4, true);  ALLOC(r->d_pcm[1], (size_t) r->batch * n * 4, true);
+    CU(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        ALLOC(r->d_pcm[i][0], (size_t) r->batch * n * 4, true); ALLOC(r->d_pcm[i][1], (size_t) r->batch * n * 4, true);
+        CU(cudaEventCreateWithFlags(&r->ev_copied[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&r->ev_free[i], cudaEventDisableTiming));
+    }
     for (int i = 0; i < 2; ++i) for (int c = 0; c < 2; ++c) ALLOC(r->d_ring[i][c], (size_t) r->batch * n * 4, true);
     ALLOC(r->d_window, n * 8, false); ALLOC(r->d_twiddle, n * 4, false);
     ALLOC(r->d_spec, planes * n * 4, true);
@@ -223,7 +231,8 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     r->stream = nullptr; r->ring_cur = 0; r->d_chunks = nullptr; r->chunks_cap = 0;
     r->d_window = nullptr; r->d_twiddle = nullptr; r->d_rowtab = nullptr; r->d_need = nullptr; r->need_count = 0;
     r->d_spec = r->d_applied = r->d_ring_f = nullptr; r->d_gr_store = r->d_ring_u = r->d_tex = nullptr; r->d_fb = nullptr;
-    r->d_pcm[0] = r->d_pcm[1] = nullptr;
+    for (int i = 0; i < 2; ++i) { r->d_pcm[i][0] = r->d_pcm[i][1] = nullptr; r->ev_copied[i] = r->ev_free[i] = nullptr; }
+    r->stage_cur = 0; r->copy_stream = nullptr;
     r->updates = 0; r->launches = 0; r->timing = false;
     if (build(r) != 0) { glava_b200_destroy(r); return nullptr; }
     return r;
@@ -236,6 +245,8 @@ void glava_b200_destroy(glava_b200* r) {
     for (cudaEvent_t e : r->ev) cudaEventDestroy(e);
     for (void* p : r->allocs) cudaFree(p);
     if (r->d_chunks) cudaFree(r->d_chunks);
+    for (int i = 0; i < 2; ++i) { if (r->ev_copied[i]) cudaEventDestroy(r->ev_copied[i]); if (r->ev_free[i]) cudaEventDestroy(r->ev_free[i]); }
+    if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
     if (r->stream) cudaStreamDestroy(r->stream);
     delete r;
 }
@@ -301,12 +312,26 @@ int glava_b200_update(glava_b200* r, const float* lb, const float* rb, size_t bs
     if (bsz != (size_t) r->p.n) return fail(GLAVA_B200_EINVAL, "glava_b200_update: bsz %zu != setbufsize %d", bsz, r->p.n);
     CU(cudaSetDevice(r->device));
     size_t bytes = (size_t) r->batch * bsz * 4;
+    const int b = r->stage_cur;
     if (modified) {
-        CU(cudaMemcpyAsync(r->d_pcm[0], lb, bytes, cudaMemcpyHostToDevice, r->stream));
+        // Staging buffer b is free once the kernels that last read it have finished; the copy runs on
+        // its own stream so it overlaps the previous update's kernels.  The call returns after the
+        // copy has completed, so — like rd_update — the caller may reuse lb / rb immediately.
+        CU(cudaStreamWaitEvent(r->copy_stream, r->ev_free[b], 0));
+        CU(cudaMemcpyAsync(r->d_pcm[b][0], lb, bytes, cudaMemcpyHostToDevice, r->copy_stream));
         if (rb && r->p.module != GLAVA_B200_MOD_WAVE)
-            CU(cudaMemcpyAsync(r->d_pcm[1], rb, bytes, cudaMemcpyHostToDevice, r->stream));
+            CU(cudaMemcpyAsync(r->d_pcm[b][1], rb, bytes, cudaMemcpyHostToDevice, r->copy_stream));
+        CU(cudaEventRecord(r->ev_copied[b], r->copy_stream));
+        CU(cudaStreamWaitEvent(r->stream, r->ev_copied[b], 0));
     }
-    return run_update(r, r->d_pcm[0], r->d_pcm[1], modified);
+    int rc = run_update(r, r->d_pcm[b][0], r->d_pcm[b][1], modified);
+    if (rc) return rc;
+    if (modified) {
+        CU(cudaEventRecord(r->ev_free[b], r->stream));
+        r->stage_cur = b ^ 1;
+        CU(cudaEventSynchronize(r->ev_copied[b]));
+    }
+    return 0;
 }
 
 int glava_b200_update_device(glava_b200* r, const float* d_lb, const float* d_rb, size_t bsz, int modified) {
@@ -390,6 +415,15 @@ int glava_b200_readback(glava_b200* r, int stream, uint8_t* rgba) {
     size_t frame = (size_t) r->p.w * r->p.h * 4;
     CU(cudaMemcpyAsync(rgba, r->d_fb + frame * (size_t) (stream % r->slots), frame, cudaMemcpyDeviceToHost, r->stream));
     CU(cudaStreamSynchronize(r->stream));
+    return 0;
+}
+
+int glava_b200_readback_async(glava_b200* r, int stream, uint8_t* rgba) {
+    clear_error();
+    if (!r || !rgba || stream < 0 || stream >= r->batch) return fail(GLAVA_B200_EINVAL, "glava_b200_readback_async: bad arguments");
+    CU(cudaSetDevice(r->device));
+    size_t frame = (size_t) r->p.w * r->p.h * 4;
+    CU(cudaMemcpyAsync(rgba, r->d_fb + frame * (size_t) (stream % r->slots), frame, cudaMemcpyDeviceToHost, r->stream));
     return 0;
 }
 

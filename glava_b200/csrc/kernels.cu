@@ -315,7 +315,12 @@ raster_generic_kernel(const __grid_constant__ RasterArgs a, const __grid_constan
 __global__ void bars_rowtab_kernel(uint2* __restrict__ tab, const __grid_constant__ glava_b200_params p) {
     int y = blockIdx.x * blockDim.x + threadIdx.x;
     if (y >= p.h) return;
-    if (p.module == GLAVA_B200_MOD_GRAPH) { tab[y] = make_uint2(graph_row(p, y), 0u); return; }
+    if (p.module == GLAVA_B200_MOD_GRAPH) {
+        const uint32_t c = graph_row(p, y);
+        const uint32_t cm = y > 0 ? graph_row(p, y - 1) : 0u, cp = (y + 1 < p.h) ? graph_row(p, y + 1) : 0u;
+        tab[y] = make_uint2(c, (((c & cm & cp) >> 24) == 255u) ? 1u : 0u);     // .y: rows y-1, y, y+1 all have alpha 1
+        return;
+    }
     float fy = (float) y + 0.5f;
     float d = p.bars_flip ? (float) p.h - fy : fy;
     BarsRow r = bars_row(p, d);
@@ -386,9 +391,22 @@ raster_bars_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__
     }
 }
 
-// graph: heights of 6 columns in registers, rolling row colours.  Pixels whose whole 3x3
-// neighbourhood is filled (or empty) skip the stencil: exact, because then avg.a is exactly the row
-// alpha (or 0) and graph/2.frag changes nothing.
+// graph: heights of 6 columns in registers, row colours from a per-renderer table.  Pixels whose whole
+// 3x3 neighbourhood is filled (or empty) skip the stencil — exact, because then avg.a is exactly the
+// row alpha (or 0) and graph/2.frag changes nothing.  Without INVERT the fill test `y + 1.5 <= s` is
+// monotone in y, so a warp's band splits into [full | plain row-colour copy | full (edge band) | zero]
+// with warp-uniform integer row bounds; only the edge band pays for the stencil.
+__device__ __forceinline__ int graph_first_row(float lim, int off, bool strict_gt, int h) {
+    // first y in [0, h] for which  strict_gt ? ((float)(y + off) + 1.5f > lim) : !((float)(y + off) + 1.5f <= lim)
+    // (both forms are "not filled"; kept separate only to mirror the call sites)
+    float e = ceilf(lim - 1.5f - (float) off);
+    int y = (e > 0.0f) ? ((e < (float) h) ? (int) e : h) : 0;
+    (void) strict_gt;
+    while (y > 0 && ((float) (y - 1 + off) + 1.5f > lim)) --y;
+    while (y < h && !((float) (y + off) + 1.5f > lim)) ++y;
+    return y;
+}
+
 __global__ void __launch_bounds__(256)
 raster_graph_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__ glava_b200_params p, int rows_per_cta) {
     const int stream = a.stream0 + blockIdx.z;
@@ -410,30 +428,61 @@ raster_graph_kernel(const __grid_constant__ RasterArgs a, const __grid_constant_
         inner_x[k] = (x + k - 1 >= 0) && (x + k + 1 < p.w);
     }
     const int y0 = blockIdx.y * rows_per_cta, y1 = min(p.h, y0 + rows_per_cta);
-    const uint2* __restrict__ rowtab = reinterpret_cast<const uint2*>(a.rowtab);   // [h] graph_row(y)
-    uint32_t row3[3];
-    row3[0] = y0 > 0 ? __ldg(&rowtab[y0 - 1]).x : 0u;
-    row3[1] = __ldg(&rowtab[y0]).x;
-    for (int y = y0; y < y1; ++y) {
-        row3[2] = (y + 1 < p.h) ? __ldg(&rowtab[y + 1]).x : 0u;
-        const float dm = graph_d(p, y - 1), dc = graph_d(p, y), dp = graph_d(p, y + 1);
-        const float dhi = fmaxf(dm, dp) + 1.5f, dlo = fminf(dm, dp) + 1.5f;   // stage-1 test is d + 1.5 <= s
-        const bool inner_y = (y - 1 >= 0) && (y + 1 < p.h);
-        const bool opaque = ((row3[0] & row3[1] & row3[2]) >> 24) == 255u;
-        uint32_t px[4];
+    const uint2* __restrict__ rowtab = reinterpret_cast<const uint2*>(a.rowtab);   // [h] {graph_row(y), rows y-1..y+1 opaque}
+
+    auto full_rows = [&](int ya, int yb) {             // reference evaluation with per-pixel shortcuts
+        for (int y = ya; y < yb; ++y) {
+            uint32_t row3[3];
+            row3[0] = y > 0 ? __ldg(&rowtab[y - 1]).x : 0u;
+            const uint2 rc = __ldg(&rowtab[y]);
+            row3[1] = rc.x;
+            row3[2] = (y + 1 < p.h) ? __ldg(&rowtab[y + 1]).x : 0u;
+            const float dm = graph_d(p, y - 1), dp = graph_d(p, y + 1);
+            const float dhi = fmaxf(dm, dp) + 1.5f, dlo = fminf(dm, dp) + 1.5f;   // stage-1 test is d + 1.5 <= s
+            const bool inner_y = (y - 1 >= 0) && (y + 1 < p.h);
+            const bool opaque = rc.y != 0u;
+            uint32_t px[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (dlo > hi[k]) px[k] = 0u;                                              // 3x3 all empty
-            else if (dhi <= lo[k] && inner_x[k] && inner_y && opaque) px[k] = row3[1]; // 3x3 all filled, alpha 1
-            else {
-                const float s3[3] = { s[k], s[k + 1], s[k + 2] };
-                px[k] = (x + k < p.w) ? graph_px_cols(p, s3, row3, x + k, y) : 0u;
+            for (int k = 0; k < 4; ++k) {
+                if (dlo > hi[k]) px[k] = 0u;                                              // 3x3 all empty
+                else if (dhi <= lo[k] && inner_x[k] && inner_y && opaque) px[k] = row3[1]; // 3x3 all filled, alpha 1
+                else {
+                    const float s3[3] = { s[k], s[k + 1], s[k + 2] };
+                    px[k] = (x + k < p.w) ? graph_px_cols(p, s3, row3, x + k, y) : 0u;
+                }
             }
-            (void) dc;
+            store4(fb + (size_t) y * p.w, x, p.w, px);
         }
-        store4(fb + (size_t) y * p.w, x, p.w, px);
-        row3[0] = row3[1]; row3[1] = row3[2];
+    };
+
+    if (p.graph_invert > 0) { full_rows(y0, y1); return; }
+
+    // thread bounds: rows >= E are empty for all 4 pixels; rows < F (and >= 1, < h-1) are interior for all 4
+    int E = 0, F = p.h;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (x + k >= p.w) continue;
+        E = max(E, graph_first_row(hi[k], -1, true, p.h));                 // (y-1)+1.5 > hi  <=> 3x3 empty
+        F = min(F, inner_x[k] ? graph_first_row(lo[k], +1, false, p.h) : 0); // (y+1)+1.5 <= lo <=> 3x3 filled
     }
+    {
+        const unsigned m = __activemask();
+        E = __reduce_max_sync(m, E); F = __reduce_min_sync(m, F);
+    }
+    const int b1 = min(y1, max(y0, 1));
+    const int b2 = max(b1, min(y1, min(F, p.h - 1)));
+    const int b3 = max(b2, min(y1, E));
+    full_rows(y0, b1);
+    for (int y = b1; y < b2; ++y) {
+        const uint2 rc = __ldg(&rowtab[y]);
+        if (rc.y != 0u) {
+            const uint32_t px[4] = { rc.x, x + 1 < p.w ? rc.x : 0u, x + 2 < p.w ? rc.x : 0u, x + 3 < p.w ? rc.x : 0u };
+            store4(fb + (size_t) y * p.w, x, p.w, px);
+        } else full_rows(y, y + 1);
+    }
+    full_rows(b2, b3);
+    const uint32_t zero4[4] = { 0u, 0u, 0u, 0u };
+    for (int y = b3; y < y1; ++y) store4(fb + (size_t) y * p.w, x, p.w, zero4);
 }
 
 // wave: 6 column descriptors in registers
@@ -465,7 +514,17 @@ raster_wave_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__
         ylo[k] = l - 2.0f; yhi[k] = h + 2.0f;
     }
     const int y0 = blockIdx.y * rows_per_cta, y1 = min(p.h, y0 + rows_per_cta);
-    for (int y = y0; y < y1; ++y) {
+    // rows outside [ra, rb) are 0 for every pixel of this thread: run them as a bare zero-store loop
+    float lo4 = fminf(fminf(ylo[0], ylo[1]), fminf(ylo[2], ylo[3])), hi4 = fmaxf(fmaxf(yhi[0], yhi[1]), fmaxf(yhi[2], yhi[3]));
+    lo4 = fminf(fmaxf(lo4, -1.0f), 1.0e6f); hi4 = fminf(fmaxf(hi4, -1.0f), 1.0e6f);
+    int ra = min(y1, max(y0, (int) floorf(lo4))), rb = max(ra, min(y1, (int) ceilf(hi4) + 1));
+    {   // make the split warp-uniform (lanes past the right edge have already returned)
+        const unsigned m = __activemask();
+        ra = __reduce_min_sync(m, ra); rb = __reduce_max_sync(m, rb);
+    }
+    const uint32_t zero4[4] = { 0u, 0u, 0u, 0u };
+    for (int y = y0; y < ra; ++y) store4(fb + (size_t) y * p.w, x, p.w, zero4);
+    for (int y = ra; y < rb; ++y) {
         const float fy = (float) y;
         uint32_t px[4];
 #pragma unroll
@@ -476,6 +535,7 @@ raster_wave_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__
         }
         store4(fb + (size_t) y * p.w, x, p.w, px);
     }
+    for (int y = rb; y < y1; ++y) store4(fb + (size_t) y * p.w, x, p.w, zero4);
 }
 
 // circle: stage 1 (polar line test) is evaluated once per pixel of a tile + 1-pixel halo into shared

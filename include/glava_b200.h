@@ -136,8 +136,10 @@ void  glava_b200_host_free(void* p);
  *            place, render.c:2140-2180).  rb is ignored by `wave` (audio_l only, wave/1.frag:7).
  *   bsz    : must equal params.n (bufscale is 1)
  *   modified: as rd_update's flag; 0 re-rasters the last spectrum (render.c:2268-2272)
- * Copies H2D, runs the fused spectrum kernel and the module raster kernel on the handle's stream,
- * returns after enqueueing (call glava_b200_sync to wait). */
+ * Copies H2D on a dedicated copy stream (double-buffered staging: the copy of update i+1 overlaps the
+ * kernels of update i), runs the fused spectrum kernel and the module raster kernel on the handle's
+ * stream.  Returns once the host buffers have been consumed (they may be reused immediately) and the
+ * kernels are enqueued; call glava_b200_sync to wait for the frame. */
 int glava_b200_update(glava_b200* r, const float* lb, const float* rb, size_t bsz, int modified);
 /* same with DEVICE pointers (inputs already resident in HBM) */
 int glava_b200_update_device(glava_b200* r, const float* d_lb, const float* d_rb, size_t bsz, int modified);
@@ -154,6 +156,8 @@ int glava_b200_sync(glava_b200* r);
 /* Outputs.  Frame layout: RGBA8, [h][w][4] bytes, row 0 = bottom row (GL window coordinates),
  * byte order R,G,B,A. */
 int glava_b200_readback(glava_b200* r, int stream, uint8_t* rgba);              /* one stream's frame -> HOST */
+int glava_b200_readback_async(glava_b200* r, int stream, uint8_t* rgba);        /* same, enqueued on the handle's stream:
+                                                                                   rgba (pinned) is valid after glava_b200_sync */
 int glava_b200_spectrum(glava_b200* r, float* out_l, float* out_r);             /* HOST [batch][n]: pipeline-A result
                                                                                    (accel_fft 0) or raw transform_fft output (1) */
 int glava_b200_textures(glava_b200* r, uint16_t* out_l, uint16_t* out_r);       /* HOST [batch][n] R16 texels the module samples */

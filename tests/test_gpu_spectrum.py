@@ -123,7 +123,7 @@ def test_streams_are_independent_and_deterministic(built):
 
 def test_silence_and_gravity_decay(built):
     n = 1024
-    p = g.default_params("bars", n=n, w=64, h=16, accel_fft=0, avg_frames=1, smooth_pass=0)
+    p = g.default_params("bars", n=n, w=64, h=16, accel_fft=0, avg_frames=1, avg_window=0, smooth_pass=0)
     loud = (np.sin(np.arange(n) * 0.3) * 0.4).astype(np.float32)[None, :]
     zero = np.zeros((1, n), np.float32)
     gstep = np.float32(p.gravity_step) * (np.float32(1.0) / np.float32(p.ur))
