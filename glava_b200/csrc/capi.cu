@@ -48,7 +48,11 @@ using namespace glb;
 struct glava_b200 {
     glava_b200_params p;
     int batch, device, slots;
-    cudaStream_t stream;
+    cudaStream_t stream;        // raster kernels, read-backs (the stream glava_b200_cuda_stream returns)
+    cudaStream_t spec_stream;   // spectrum kernels + FIFO ingest, highest priority: the latency-bound spectrum
+                                // kernel of update i+1 co-runs with the HBM-bound raster kernel of update i
+    int    tex_cur;             // which half of d_tex the latest spectrum wrote / the raster reads
+    cudaEvent_t ev_spec_done[2], ev_raster_done[2];
     // inputs
     float* d_pcm[2][2];         // H2D staging for glava_b200_update, double-buffered  [2][batch][n] x {l, r}
     int    stage_cur;
@@ -59,6 +63,7 @@ struct glava_b200 {
     int16_t* d_chunks; size_t chunks_cap;
     // constants
     double* d_window; float* d_twiddle; void* d_rowtab; int* d_need; int need_count;
+    TapEntry* d_tap_tab; int* d_tap_cnt; float* d_tap_wsum; int tap_max;
     // state + outputs
     float* d_spec; float* d_applied; float* d_ring_f;
     uint16_t* d_gr_store; uint16_t* d_ring_u; uint16_t* d_tex;
@@ -68,8 +73,8 @@ struct glava_b200 {
     std::vector<void*> allocs;
     // optional per-kernel device timing (glava_b200_set_timing): events around each launch
     bool timing;
-    std::vector<cudaEvent_t> ev;      // triples: before spectrum, between, after raster
-    std::vector<int> ev_modified;
+    std::vector<cudaEvent_t> ev_spec; // pairs around each spectrum launch (spec_stream)
+    std::vector<cudaEvent_t> ev_ras;  // pairs around each raster launch (stream)
 };
 
 static int dev_alloc(glava_b200* r, void** out, size_t bytes, bool zero) {
@@ -165,6 +170,15 @@ static int build(glava_b200* r) {
     const size_t n = (size_t) p.n, planes = (size_t) r->batch * 2, F = (size_t) p.avg_frames;
     CU(cudaSetDevice(r->device));
     CU(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&r->spec_stream, cudaStreamNonBlocking, hi));
+    }
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaEventCreateWithFlags(&r->ev_spec_done[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&r->ev_raster_done[i], cudaEventDisableTiming));
+    }
     int rc;
 #define ALLOC(ptr, bytes, zero) if ((rc = dev_alloc(r, (void**) &(ptr), (bytes), (zero))) != 0) return rc
     CU(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
@@ -178,7 +192,7 @@ static int build(glava_b200* r) {
     ALLOC(r->d_spec, planes * n * 4, true);
     if (p.accel_fft) { ALLOC(r->d_gr_store, planes * n * 2, true); ALLOC(r->d_ring_u, planes * F * n * 2, true); }
     else             { ALLOC(r->d_applied, planes * n * 4, true);  ALLOC(r->d_ring_f, planes * F * n * 4, true); }
-    ALLOC(r->d_tex, planes * n * 2, true);
+    ALLOC(r->d_tex, 2 * planes * n * 2, true);          // double-buffered: spectrum i+1 writes one half while raster i reads the other
     ALLOC(r->d_rowtab, (size_t) p.h * 8, true);
     // framebuffers: [slots][h][w] RGBA8
     size_t frame = (size_t) p.w * p.h * 4;
@@ -209,6 +223,43 @@ static int build(glava_b200* r) {
             CU(cudaMemcpyAsync(r->d_need, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, r->stream));
             CU(cudaStreamSynchronize(r->stream));
             r->need_count = (int) cnt;
+            // K5 tap table: indices and weights of smooth_audio() for every needed texel.  They are a
+            // function of the parameters only, and gl_math.h evaluates bit-identically on host and
+            // device, so the table is built here once with the very code the kernel would run.
+            const SmoothParams sp = smooth_params(p);
+            std::vector<std::vector<TapEntry>> taps(2 * cnt);
+            std::vector<float> wsum(2 * cnt, 0.0f);
+            std::vector<int> tcnt(2 * cnt, 0);
+            size_t tap_max = 1;
+            for (size_t e = 0; e < 2 * cnt; ++e) {
+                const int x = flat[e];
+                if (x < 0) continue;
+                float weight = 0.0f;
+                std::vector<TapEntry>& v = taps[e];
+                smooth_enumerate(sp, p.n, ((float) x + 0.5f) / (float) p.n, [&](int i, float w) {
+                    weight += w;
+                    v.push_back(TapEntry { i, w });
+                });
+                wsum[e] = weight; tcnt[e] = (int) v.size();
+                if (v.size() > tap_max) tap_max = v.size();
+            }
+            const size_t tab_elems = 2 * tap_max * cnt;
+            if (tab_elems * sizeof(TapEntry) <= (size_t) 64 << 20 && !getenv("GLAVA_B200_NO_TAPTAB")) {
+                std::vector<TapEntry> tab(tab_elems, TapEntry { -1, 0.0f });
+                for (size_t c = 0; c < 2; ++c)
+                    for (size_t k = 0; k < cnt; ++k) {
+                        const std::vector<TapEntry>& v = taps[c * cnt + k];
+                        for (size_t j = 0; j < v.size(); ++j) tab[(c * tap_max + j) * cnt + k] = v[j];
+                    }
+                if ((rc = dev_alloc(r, (void**) &r->d_tap_tab, tab.size() * sizeof(TapEntry), false)) != 0) return rc;
+                if ((rc = dev_alloc(r, (void**) &r->d_tap_cnt, tcnt.size() * sizeof(int), false)) != 0) return rc;
+                if ((rc = dev_alloc(r, (void**) &r->d_tap_wsum, wsum.size() * sizeof(float), false)) != 0) return rc;
+                CU(cudaMemcpyAsync(r->d_tap_tab, tab.data(), tab.size() * sizeof(TapEntry), cudaMemcpyHostToDevice, r->stream));
+                CU(cudaMemcpyAsync(r->d_tap_cnt, tcnt.data(), tcnt.size() * sizeof(int), cudaMemcpyHostToDevice, r->stream));
+                CU(cudaMemcpyAsync(r->d_tap_wsum, wsum.data(), wsum.size() * sizeof(float), cudaMemcpyHostToDevice, r->stream));
+                CU(cudaStreamSynchronize(r->stream));
+                r->tap_max = (int) tap_max;
+            }
         }
     }
     if (p.module == GLAVA_B200_MOD_BARS || p.module == GLAVA_B200_MOD_GRAPH) { if ((rc = launch_bars_rowtab(p, r->d_rowtab, r->stream)) != 0) return rc; ++r->launches; }
@@ -228,8 +279,10 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     if (device < 0 || device >= ndev) { fail(GLAVA_B200_EINVAL, "device %d out of range (%d devices)", device, ndev); return nullptr; }
     glava_b200* r = new glava_b200();
     r->p = *params; r->batch = batch; r->device = device;
-    r->stream = nullptr; r->ring_cur = 0; r->d_chunks = nullptr; r->chunks_cap = 0;
+    r->stream = nullptr; r->spec_stream = nullptr; r->tex_cur = 0; r->ring_cur = 0;
+    for (int i = 0; i < 2; ++i) { r->ev_spec_done[i] = nullptr; r->ev_raster_done[i] = nullptr; } r->d_chunks = nullptr; r->chunks_cap = 0;
     r->d_window = nullptr; r->d_twiddle = nullptr; r->d_rowtab = nullptr; r->d_need = nullptr; r->need_count = 0;
+    r->d_tap_tab = nullptr; r->d_tap_cnt = nullptr; r->d_tap_wsum = nullptr; r->tap_max = 0;
     r->d_spec = r->d_applied = r->d_ring_f = nullptr; r->d_gr_store = r->d_ring_u = r->d_tex = nullptr; r->d_fb = nullptr;
     for (int i = 0; i < 2; ++i) { r->d_pcm[i][0] = r->d_pcm[i][1] = nullptr; r->ev_copied[i] = r->ev_free[i] = nullptr; }
     r->stage_cur = 0; r->copy_stream = nullptr;
@@ -241,8 +294,12 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
 void glava_b200_destroy(glava_b200* r) {
     if (!r) return;
     cudaSetDevice(r->device);
+    if (r->spec_stream) cudaStreamSynchronize(r->spec_stream);
     if (r->stream) cudaStreamSynchronize(r->stream);
-    for (cudaEvent_t e : r->ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : r->ev_spec) cudaEventDestroy(e);
+    for (cudaEvent_t e : r->ev_ras) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) { if (r->ev_spec_done[i]) cudaEventDestroy(r->ev_spec_done[i]); if (r->ev_raster_done[i]) cudaEventDestroy(r->ev_raster_done[i]); }
+    if (r->spec_stream) cudaStreamDestroy(r->spec_stream);
     for (void* p : r->allocs) cudaFree(p);
     if (r->d_chunks) cudaFree(r->d_chunks);
     for (int i = 0; i < 2; ++i) { if (r->ev_copied[i]) cudaEventDestroy(r->ev_copied[i]); if (r->ev_free[i]) cudaEventDestroy(r->ev_free[i]); }
@@ -261,25 +318,40 @@ const void* glava_b200_framebuffer_device(const glava_b200* r) { return r ? r->d
 void* glava_b200_cuda_stream(const glava_b200* r) { return r ? (void*) r->stream : nullptr; }
 uint64_t glava_b200_launch_count(const glava_b200* r) { return r ? r->launches : 0; }
 
-static int timing_mark(glava_b200* r) {
+static int timing_mark(std::vector<cudaEvent_t>& v, cudaStream_t st) {
     cudaEvent_t e;
     CU(cudaEventCreate(&e));
-    CU(cudaEventRecord(e, r->stream));
-    r->ev.push_back(e);
+    CU(cudaEventRecord(e, st));
+    v.push_back(e);
     return 0;
 }
 
+static uint16_t* tex_half(glava_b200* r, int b) { return r->d_tex + (size_t) b * r->batch * 2 * r->p.n; }
+static int sync_all(glava_b200* r) {
+    CU(cudaStreamSynchronize(r->spec_stream));
+    CU(cudaStreamSynchronize(r->stream));
+    return 0;
+}
+
+// One update = spectrum kernel on spec_stream (if modified) + raster kernel on stream.
+//   spectrum(i) waits for: its input (caller-provided event on spec_stream), spectrum(i-1) (same stream:
+//                          gravity / average state is read-modify-write), raster(i-2) (last reader of the
+//                          texture half it overwrites)
+//   raster(i)   waits for: spectrum(i)
+// so raster(i) and spectrum(i+1) run concurrently: one is HBM-store bound, the other latency bound.
 static int run_update(glava_b200* r, const float* d_l, const float* d_r, int modified) {
     const glava_b200_params& p = r->p;
     int rc;
-    if (r->timing) { if ((rc = timing_mark(r)) != 0) return rc; r->ev_modified.push_back(modified ? 1 : 0); }
     if (modified) {
+        const int b = r->tex_cur ^ 1;
+        CU(cudaStreamWaitEvent(r->spec_stream, r->ev_raster_done[b], 0));
         SpectrumArgs a;
         memset(&a, 0, sizeof(a));
         a.pcm_l = d_l; a.pcm_r = d_r; a.window = r->d_window; a.twiddle = r->d_twiddle;
         a.spec = r->d_spec; a.applied = r->d_applied; a.ring_f = r->d_ring_f;
-        a.gr_store = r->d_gr_store; a.ring_u = r->d_ring_u; a.tex = r->d_tex;
+        a.gr_store = r->d_gr_store; a.ring_u = r->d_ring_u; a.tex = tex_half(r, b);
         a.need = (p.lazy_smooth && r->d_need) ? r->d_need : nullptr; a.need_count = r->need_count;
+        a.tap_tab = a.need ? r->d_tap_tab : nullptr; a.tap_cnt = r->d_tap_cnt; a.tap_wsum = r->d_tap_wsum; a.tap_max = r->tap_max;
         a.batch = r->batch; a.update = r->updates;
         const int F = p.avg_frames;
         for (int f = 0; f < F; ++f) {
@@ -290,19 +362,27 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
         }
         a.avg_b_windowed = (p.avg_window && F != 2) ? 1 : 0;
         const bool is_fft = p.module != GLAVA_B200_MOD_WAVE;
-        if ((rc = launch_spectrum(p, a, is_fft, r->stream)) != 0) return rc;
+        if (r->timing && (rc = timing_mark(r->ev_spec, r->spec_stream)) != 0) return rc;
+        if ((rc = launch_spectrum(p, a, is_fft, r->spec_stream)) != 0) return rc;
+        if (r->timing && (rc = timing_mark(r->ev_spec, r->spec_stream)) != 0) return rc;
+        CU(cudaEventRecord(r->ev_spec_done[b], r->spec_stream));
+        r->tex_cur = b;
         ++r->launches; ++r->updates;
     }
-    if (r->timing && (rc = timing_mark(r)) != 0) return rc;
+    const int b = r->tex_cur;
+    CU(cudaStreamWaitEvent(r->stream, r->ev_spec_done[b], 0));
     RasterArgs ra;
-    ra.tex = r->d_tex; ra.fb = r->d_fb; ra.rowtab = (p.module == GLAVA_B200_MOD_BARS || p.module == GLAVA_B200_MOD_GRAPH) ? r->d_rowtab : nullptr;
+    ra.tex = tex_half(r, b); ra.fb = r->d_fb;
+    ra.rowtab = (p.module == GLAVA_B200_MOD_BARS || p.module == GLAVA_B200_MOD_GRAPH) ? r->d_rowtab : nullptr;
     ra.batch = r->batch; ra.slots = r->slots; ra.stream0 = 0;
+    if (r->timing && (rc = timing_mark(r->ev_ras, r->stream)) != 0) return rc;
     if ((rc = launch_raster(p, ra, r->stream)) != 0) return rc;
+    if (r->timing && (rc = timing_mark(r->ev_ras, r->stream)) != 0) return rc;
+    CU(cudaEventRecord(r->ev_raster_done[b], r->stream));
     {
         const int chunk = r->slots < 32768 ? r->slots : 32768;          // see launch_raster
         r->launches += (uint64_t) ((r->batch + chunk - 1) / chunk);
     }
-    if (r->timing && (rc = timing_mark(r)) != 0) return rc;
     return 0;
 }
 
@@ -314,20 +394,20 @@ int glava_b200_update(glava_b200* r, const float* lb, const float* rb, size_t bs
     size_t bytes = (size_t) r->batch * bsz * 4;
     const int b = r->stage_cur;
     if (modified) {
-        // Staging buffer b is free once the kernels that last read it have finished; the copy runs on
-        // its own stream so it overlaps the previous update's kernels.  The call returns after the
+        // Staging buffer b is free once the spectrum kernel that last read it has finished; the copy runs
+        // on its own stream so it overlaps the previous update's kernels.  The call returns after the
         // copy has completed, so — like rd_update — the caller may reuse lb / rb immediately.
         CU(cudaStreamWaitEvent(r->copy_stream, r->ev_free[b], 0));
         CU(cudaMemcpyAsync(r->d_pcm[b][0], lb, bytes, cudaMemcpyHostToDevice, r->copy_stream));
         if (rb && r->p.module != GLAVA_B200_MOD_WAVE)
             CU(cudaMemcpyAsync(r->d_pcm[b][1], rb, bytes, cudaMemcpyHostToDevice, r->copy_stream));
         CU(cudaEventRecord(r->ev_copied[b], r->copy_stream));
-        CU(cudaStreamWaitEvent(r->stream, r->ev_copied[b], 0));
+        CU(cudaStreamWaitEvent(r->spec_stream, r->ev_copied[b], 0));
     }
     int rc = run_update(r, r->d_pcm[b][0], r->d_pcm[b][1], modified);
     if (rc) return rc;
     if (modified) {
-        CU(cudaEventRecord(r->ev_free[b], r->stream));
+        CU(cudaEventRecord(r->ev_free[b], r->spec_stream));
         r->stage_cur = b ^ 1;
         CU(cudaEventSynchronize(r->ev_copied[b]));
     }
@@ -350,15 +430,17 @@ int glava_b200_ingest_fifo(glava_b200* r, const int16_t* chunks, int frames) {
     CU(cudaSetDevice(r->device));
     size_t bytes = (size_t) r->batch * frames * 2 * sizeof(int16_t);
     if (bytes > r->chunks_cap) {
+        CU(cudaStreamSynchronize(r->spec_stream));
         if (r->d_chunks) cudaFree(r->d_chunks);
         r->d_chunks = nullptr; r->chunks_cap = 0;
         CU(cudaMalloc((void**) &r->d_chunks, bytes));
         r->chunks_cap = bytes;
     }
-    CU(cudaMemcpyAsync(r->d_chunks, chunks, bytes, cudaMemcpyHostToDevice, r->stream));
+    // ordered with the spectrum kernels (they read the rings): same stream
+    CU(cudaMemcpyAsync(r->d_chunks, chunks, bytes, cudaMemcpyHostToDevice, r->spec_stream));
     int cur = r->ring_cur, nxt = cur ^ 1;
     int rc = launch_fifo_ingest(r->p, r->d_chunks, frames, r->d_ring[cur][0], r->d_ring[cur][1],
-                                r->d_ring[nxt][0], r->d_ring[nxt][1], r->batch, r->stream);
+                                r->d_ring[nxt][0], r->d_ring[nxt][1], r->batch, r->spec_stream);
     if (rc) return rc;
     ++r->launches;
     r->ring_cur = nxt;
@@ -375,9 +457,10 @@ int glava_b200_update_rings(glava_b200* r, int modified) {
 int glava_b200_set_timing(glava_b200* r, int enable) {
     if (!r) return fail(GLAVA_B200_EINVAL, "null argument");
     CU(cudaSetDevice(r->device));
-    CU(cudaStreamSynchronize(r->stream));
-    for (cudaEvent_t e : r->ev) cudaEventDestroy(e);
-    r->ev.clear(); r->ev_modified.clear();
+    int rc0 = sync_all(r); if (rc0) return rc0;
+    for (cudaEvent_t e : r->ev_spec) cudaEventDestroy(e);
+    for (cudaEvent_t e : r->ev_ras) cudaEventDestroy(e);
+    r->ev_spec.clear(); r->ev_ras.clear();
     r->timing = enable != 0;
     return 0;
 }
@@ -385,14 +468,13 @@ int glava_b200_set_timing(glava_b200* r, int enable) {
 int glava_b200_kernel_times(glava_b200* r, double* spectrum_ms, int* spectrum_launches, double* raster_ms, int* raster_launches) {
     if (!r) return fail(GLAVA_B200_EINVAL, "null argument");
     CU(cudaSetDevice(r->device));
-    CU(cudaStreamSynchronize(r->stream));
+    int rc0 = sync_all(r); if (rc0) return rc0;
     double s = 0, q = 0; int ns = 0, nq = 0;
-    for (size_t i = 0; i + 2 < r->ev.size() + 0 && i / 3 < r->ev_modified.size(); i += 3) {
-        float a = 0, b = 0;
-        CU(cudaEventElapsedTime(&a, r->ev[i], r->ev[i + 1]));
-        CU(cudaEventElapsedTime(&b, r->ev[i + 1], r->ev[i + 2]));
-        if (r->ev_modified[i / 3]) { s += a; ++ns; }
-        q += b; ++nq;
+    for (size_t i = 0; i + 1 < r->ev_spec.size(); i += 2) {
+        float a = 0; CU(cudaEventElapsedTime(&a, r->ev_spec[i], r->ev_spec[i + 1])); s += a; ++ns;
+    }
+    for (size_t i = 0; i + 1 < r->ev_ras.size(); i += 2) {
+        float a = 0; CU(cudaEventElapsedTime(&a, r->ev_ras[i], r->ev_ras[i + 1])); q += a; ++nq;
     }
     if (spectrum_ms) *spectrum_ms = s;
     if (spectrum_launches) *spectrum_launches = ns;
@@ -404,8 +486,7 @@ int glava_b200_kernel_times(glava_b200* r, double* spectrum_ms, int* spectrum_la
 int glava_b200_sync(glava_b200* r) {
     if (!r) return fail(GLAVA_B200_EINVAL, "null argument");
     CU(cudaSetDevice(r->device));
-    CU(cudaStreamSynchronize(r->stream));
-    return 0;
+    return sync_all(r);
 }
 
 int glava_b200_readback(glava_b200* r, int stream, uint8_t* rgba) {
@@ -430,6 +511,7 @@ int glava_b200_readback_async(glava_b200* r, int stream, uint8_t* rgba) {
 static int planes_to_host(glava_b200* r, const void* d, size_t elem, void* out_l, void* out_r) {
     // device layout [batch][2][n] -> two host arrays [batch][n]
     const size_t row = (size_t) r->p.n * elem;
+    CU(cudaStreamSynchronize(r->spec_stream));
     if (out_l) CU(cudaMemcpy2DAsync(out_l, row, d, 2 * row, row, (size_t) r->batch, cudaMemcpyDeviceToHost, r->stream));
     if (out_r) CU(cudaMemcpy2DAsync(out_r, row, (const char*) d + row, 2 * row, row, (size_t) r->batch, cudaMemcpyDeviceToHost, r->stream));
     CU(cudaStreamSynchronize(r->stream));
@@ -445,7 +527,7 @@ int glava_b200_textures(glava_b200* r, uint16_t* out_l, uint16_t* out_r) {
     clear_error();
     if (!r) return fail(GLAVA_B200_EINVAL, "null argument");
     CU(cudaSetDevice(r->device));
-    return planes_to_host(r, r->d_tex, 2, out_l, out_r);
+    return planes_to_host(r, tex_half(r, r->tex_cur), 2, out_l, out_r);
 }
 
 int glava_b200_smooth_pass(glava_b200* r, const uint16_t* in, uint16_t* out, int count) {
@@ -475,8 +557,10 @@ int glava_b200_raster_textures(glava_b200* r, const uint16_t* tex_l, const uint1
     if (!r || !tex_l) return fail(GLAVA_B200_EINVAL, "glava_b200_raster_textures: null argument");
     CU(cudaSetDevice(r->device));
     const size_t row = (size_t) r->p.n * 2;
-    CU(cudaMemcpy2DAsync(r->d_tex, 2 * row, tex_l, row, row, (size_t) r->batch, cudaMemcpyHostToDevice, r->stream));
-    if (tex_r) CU(cudaMemcpy2DAsync((char*) r->d_tex + row, 2 * row, tex_r, row, row, (size_t) r->batch, cudaMemcpyHostToDevice, r->stream));
+    CU(cudaStreamSynchronize(r->spec_stream));
+    char* dst = (char*) tex_half(r, r->tex_cur);
+    CU(cudaMemcpy2DAsync(dst, 2 * row, tex_l, row, row, (size_t) r->batch, cudaMemcpyHostToDevice, r->stream));
+    if (tex_r) CU(cudaMemcpy2DAsync(dst + row, 2 * row, tex_r, row, row, (size_t) r->batch, cudaMemcpyHostToDevice, r->stream));
     return run_update(r, nullptr, nullptr, 0);
 }
 

@@ -25,6 +25,8 @@ int  validate_params(const glava_b200_params* p);
 
 #define GLB_MAX_AVG_FRAMES 16
 
+struct alignas(8) TapEntry { int idx; float w; };   // one tap of the K5 smoothing sum: texel index, weight
+
 // ---- views handed to the kernels (all pointers are DEVICE pointers) ---------------------------
 // "channel plane" c = stream * 2 + ch (ch 0 = left, 1 = right); every per-channel array is
 // [batch*2][...] so one CTA of the spectrum kernel owns one contiguous plane.
@@ -39,8 +41,13 @@ struct SpectrumArgs {
     uint16_t* gr_store;         // [batch*2][n] (B) render.c:2197
     uint16_t* ring_u;           // [batch*2][F][n] (B) gr->out[], render.c:2232
     uint16_t* tex;              // [batch*2][n] R16 texture the module samples
-    const int* need;            // lazy K5: texel indices to evaluate, nullptr = all n
+    const int* need;            // lazy K5: texel indices to evaluate, [2][need_count] (-1 = unused), nullptr = all n
     int       need_count;
+    // precomputed K5 taps for the need-list (weights and indices do not depend on the audio):
+    const TapEntry* tap_tab;    // [2][tap_max][need_count], tap-major so a warp's loads coalesce; nullptr = evaluate directly
+    const int*   tap_cnt;       // [2][need_count]
+    const float* tap_wsum;      // [2][need_count]  sum of the weights in loop order
+    int       tap_max;
     int       batch;
     unsigned long long update;  // number of modified updates before this one (ring cursor)
     double    avg_w_a[GLB_MAX_AVG_FRAMES];   // pipeline A weights, oldest first (render.c:661,766)

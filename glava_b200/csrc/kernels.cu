@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 namespace glb {
 
@@ -76,23 +77,35 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
     using C = SpecCfg<LOG2N>;
     constexpr int N = C::N, M = C::M, T = C::T;
     const int tid = threadIdx.x;
-    const int c = blockIdx.x, stream = c >> 1, ch = c & 1;
-    if (!IS_FFT && ch == 1) return;                  // wave binds audio_l only (wave/1.frag:7)
 
     cpx*      buf = reinterpret_cast<cpx*>(glb_smem);
     float*    raw = reinterpret_cast<float*>(glb_smem);
     uint16_t* av  = reinterpret_cast<uint16_t*>(glb_smem + C::OFF_AV);
     uint64_t* bar = reinterpret_cast<uint64_t*>(glb_smem + C::OFF_BAR);
 
-    // --- stage the PCM ring of this (stream, channel): one bulk async copy, N*4 bytes -------------
-    const float* pcm = (ch == 0 ? a.pcm_l : a.pcm_r) + (size_t) stream * N;
+    // Persistent CTAs: work unit u = one (stream, channel) plane (wave: one stream, audio_l only,
+    // wave/1.frag:7); a CTA walks u = blockIdx.x, + gridDim.x, ...  The PCM ring of the NEXT unit is
+    // prefetched by the TMA engine while this unit's smoothing pass runs.
+    const int units = IS_FFT ? a.batch * 2 : a.batch;
+    auto issue_load = [&](int u) {                   // one bulk async copy, N*4 bytes, completes on `bar`
+        const int cc = IS_FFT ? u : 2 * u;
+        const float* pcm = ((cc & 1) == 0 ? a.pcm_l : a.pcm_r) + (size_t) (cc >> 1) * N;
+        // the buffer was last touched through the generic proxy (FFT passes): order those accesses
+        // before the async-proxy (TMA) write
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, N * 4);
+        bulk_g2s(raw, pcm, N * 4, bar);
+    };
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
-    if (tid == 0) { mbar_expect_tx(bar, N * 4); bulk_g2s(raw, pcm, N * 4, bar); }
-    mbar_wait(bar, 0);
-
-    const size_t plane = (size_t) c * N;
+    if (tid == 0 && (int) blockIdx.x < units) issue_load(blockIdx.x);
+    uint32_t parity = 0;
     const int F = p.avg_frames;
+
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    const int c = IS_FFT ? u : 2 * u, ch = c & 1;
+    mbar_wait(bar, parity); parity ^= 1u;
+    const size_t plane = (size_t) c * N;
 
     if constexpr (IS_FFT) {
         // --- window (render.c:793-795: float * double -> float) folded into the first pass loads ----
@@ -130,25 +143,57 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
             // --- pipeline B: render.c:2177-2267 ---------------------------------------------------
             const float diff = p.gravity_step * (1.0f / p.ur);
             const int out_idx = (int) (a.update % (unsigned long long) F);
-            for (int n = tid; n < N; n += T) {
-                cpx z = buf[fft_pad(n >> 1)];
-                float v = fft_post((n & 1) ? z.y : z.x, n, N, p.fft_scale, p.fft_cutoff);
-                a.spec[plane + n] = v;
-                uint32_t gq = gravity_b(unorm16(v), a.gr_store[plane + n], diff);
-                a.gr_store[plane + n] = (uint16_t) gq;
-                uint32_t texel = gq;
-                if (F > 1) {
-                    uint16_t* ring = a.ring_u + plane * F;
-                    ring[(size_t) out_idx * N + n] = (uint16_t) gq;
-                    float r = 0.0f;
-                    for (int i = 0; i < F; ++i) {                  // t0 = most recent (render.c:2250-2255)
-                        int fr = out_idx - i; if (fr < 0) fr += F;
-                        float tx = from16(i == 0 ? gq : (uint32_t) ring[(size_t) fr * N + n]);
-                        if (a.avg_b_windowed) r += a.avg_w_b[i] * tx; else r += tx;
+            float*    const spec = a.spec + plane;
+            uint16_t* const grs  = a.gr_store + plane;
+            uint16_t* const ring = a.ring_u + plane * F;
+            // FT = compile-time copy of F for the common small values: the slot offsets and the
+            // weights of the average live in registers and the tap loop is fully unrolled
+            auto epilogue = [&](auto ft) {
+                constexpr int FT = decltype(ft)::value;               // 0 = generic (runtime F)
+                const int FF = FT ? FT : F;
+                int off[FT ? FT : 1]; float wt[FT ? FT : 1];
+                if constexpr (FT > 0) {
+#pragma unroll
+                    for (int i = 0; i < FT; ++i) {
+                        int fr = out_idx - i; if (fr < 0) fr += FT;
+                        off[i] = fr * N; wt[i] = a.avg_w_b[i];
                     }
-                    texel = unorm16(r / (float) F);
                 }
-                av[n] = (uint16_t) texel;
+                for (int n = tid; n < N; n += T) {
+                    cpx z = buf[fft_pad(n >> 1)];
+                    float v = fft_post((n & 1) ? z.y : z.x, n, N, p.fft_scale, p.fft_cutoff);
+                    spec[n] = v;
+                    uint32_t gq = gravity_b(unorm16(v), grs[n], diff);
+                    grs[n] = (uint16_t) gq;
+                    uint32_t texel = gq;
+                    if (FF > 1) {
+                        float r = 0.0f;
+                        if constexpr (FT > 0) {
+                            ring[off[0] + n] = (uint16_t) gq;
+#pragma unroll
+                            for (int i = 0; i < FT; ++i) {             // t0 = most recent (render.c:2250-2255)
+                                float tx = from16(i == 0 ? gq : (uint32_t) ring[off[i] + n]);
+                                if (a.avg_b_windowed) r += wt[i] * tx; else r += tx;
+                            }
+                        } else {
+                            ring[(size_t) out_idx * N + n] = (uint16_t) gq;
+                            for (int i = 0; i < F; ++i) {
+                                int fr = out_idx - i; if (fr < 0) fr += F;
+                                float tx = from16(i == 0 ? gq : (uint32_t) ring[(size_t) fr * N + n]);
+                                if (a.avg_b_windowed) r += a.avg_w_b[i] * tx; else r += tx;
+                            }
+                        }
+                        texel = unorm16(r / (float) FF);
+                    }
+                    av[n] = (uint16_t) texel;
+                }
+            };
+            switch (F) {
+                case 5: epilogue(std::integral_constant<int, 5>()); break;       // shipped default (smooth_parameters.glsl:56)
+                case 6: epilogue(std::integral_constant<int, 6>()); break;       // compiled-in default (render.c:912)
+                case 3: epilogue(std::integral_constant<int, 3>()); break;
+                case 4: epilogue(std::integral_constant<int, 4>()); break;
+                default: epilogue(std::integral_constant<int, 0>()); break;
             }
         }
     } else {
@@ -161,12 +206,31 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
         }
     }
     __syncthreads();
+    // `raw`/`buf` are dead from here on: let the TMA engine fetch the next unit's PCM during K5
+    if (tid == 0 && u + (int) gridDim.x < units) issue_load(u + gridDim.x);
 
     // --- K5 smooth pass out of shared memory (render.c:2276-2303) ----------------------------------
     uint16_t* tex = a.tex + plane;
     if (p.smooth_pass) {
         const SmoothParams sp = smooth_params(p);
-        if (a.need) {
+        if (a.need && a.tap_tab) {
+            // weights / indices precomputed once (they depend on the parameters only): per tap one
+            // coalesced 8-byte load, one shared-memory texel fetch, a multiply and an add
+            const int* need = a.need + (size_t) ch * a.need_count;
+            const TapEntry* tab = a.tap_tab + (size_t) ch * a.tap_max * a.need_count;
+            for (int k = tid; k < a.need_count; k += T) {
+                const int x = need[k];
+                if (x < 0 || x >= N) continue;
+                const int cnt = a.tap_cnt[(size_t) ch * a.need_count + k];
+                SmoothAcc acc; acc.init();
+                for (int j = 0; j < cnt; ++j) {
+                    const int2 e = __ldg(reinterpret_cast<const int2*>(tab) + (size_t) j * a.need_count + k);
+                    acc.add_noweight(fetch16(av, N, e.x), __int_as_float(e.y));
+                }
+                acc.weight = a.tap_wsum[(size_t) ch * a.need_count + k];
+                tex[x] = (uint16_t) unorm16(acc.result(sp));
+            }
+        } else if (a.need) {
             const int* need = a.need + (size_t) ch * a.need_count;
             for (int k = tid; k < a.need_count; k += T) {
                 int x = need[k];
@@ -178,6 +242,8 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
     } else {
         for (int x = tid; x < N; x += T) tex[x] = av[x];
     }
+    __syncthreads();                                 // `av` may be overwritten by the next unit's epilogue
+  }
 }
 
 int spectrum_smem_bytes(int n) {
@@ -199,7 +265,16 @@ static int launch_spectrum_t(const glava_b200_params& p, const SpectrumArgs& a, 
         if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "cudaFuncSetAttribute(spectrum): %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    kern<<<a.batch * 2, C::T, C::SMEM, st>>>(a, p);
+    // Persistent grid: a few CTAs per SM.  Small on purpose — this kernel is latency bound and is meant
+    // to run UNDER the HBM-bound raster kernel of the previous update (capi.cu run_update) without taking
+    // its occupancy away.  GLAVA_B200_SPEC_CTAS_PER_SM overrides (0 = one CTA per work unit).
+    static int sm_count = 0;
+    if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); if (sm_count <= 0) sm_count = 148; }
+    int per_sm = 0;                                  // measured on B200: 0 (one CTA per unit) >= 4 > 3 > 2 > 1 for whole-step throughput
+    if (const char* e = getenv("GLAVA_B200_SPEC_CTAS_PER_SM")) per_sm = atoi(e);
+    const int units = IS_FFT ? a.batch * 2 : a.batch;
+    int grid = (per_sm > 0 && sm_count * per_sm < units) ? sm_count * per_sm : units;
+    kern<<<grid, C::T, C::SMEM, st>>>(a, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "spectrum kernel launch: %s", cudaGetErrorString(e));
     return 0;
@@ -632,7 +707,7 @@ int launch_raster(const glava_b200_params& p, const RasterArgs& a, void* stream)
     const bool fast_wave  = p.module == GLAVA_B200_MOD_WAVE;
     int bx = (fast_bars || fast_graph || fast_wave) ? pick_block_x(quads) : 128;
     if (bx > 256) bx = 256;
-    int rows = fast_bars ? 270 : ((fast_graph || fast_wave) ? 135 : 8);
+    int rows = (fast_bars || fast_graph || fast_wave) ? 135 : 8;   // bars: 135 >= 270 > 540 with the spectrum kernel co-running
     // development overrides for tuning sweeps (tools/tune_raster.py); unset in normal use
     if (const char* e = getenv("GLAVA_B200_ROWS")) { int v = atoi(e); if (v > 0) rows = v; }
     if (const char* e = getenv("GLAVA_B200_BX")) { int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) bx = v; }

@@ -90,38 +90,48 @@ GLB_HD float round_formula(const SmoothParams& p, float x) {                 // 
 GLB_HD float fetch16(const uint16_t* tex, int n, int i) {
     return (i < 0 || i >= n) ? 0.0f : from16(tex[i]);
 }
-GLB_HD float smooth_audio_raw(const SmoothParams& p, const uint16_t* tex, int n, float idx) {
+// The taps of smooth_audio() for one output position: texel index round(s) and weight
+// ROUND_FORMULA(clamp((m - |rm - s|) / m, 0, 1)) for s = smin, smin + 1, ... (<= smax in `average`
+// mode, < smax otherwise; smooth.glsl:33,44,55).  Index and weight depend only on the parameters and
+// on idx — NOT on the audio — which is what lets the kernel precompute them once (SmoothTable).
+template <class Tap>
+GLB_HD void smooth_enumerate(const SmoothParams& p, int n, float idx, Tap tap) {
     float fn = (float) n;
     float smin = scale_audio(p, g_clamp(idx - p.smooth_factor, 0.0f, 1.0f)) * fn;
     float smax = scale_audio(p, g_clamp(idx + p.smooth_factor, 0.0f, 1.0f)) * fn;
-    float m = ((smax - smin) / 2.0f), s, w;
+    float m = ((smax - smin) / 2.0f), s;
     float rm = smin + m;
     if (p.sample_mode == 0) {
-        float avg = 0.0f, weight = 0.0f;
-        for (s = smin; s <= smax; s += 1.0f) {
-            w = round_formula(p, g_clamp((m - fabsf(rm - s)) / m, 0.0f, 1.0f));
-            weight += w;
-            avg += fetch16(tex, n, (int) glm_rint(s)) * w;
-        }
-        return avg / weight;
-    } else if (p.sample_mode == 2) {
-        float vmax = 0.0f, avg = 0.0f, weight = 0.0f, v;
-        for (s = smin; s < smax; s += 1.0f) {
-            w = round_formula(p, g_clamp((m - fabsf(rm - s)) / m, 0.0f, 1.0f));
-            weight += w;
-            v = fetch16(tex, n, (int) glm_rint(s)) * w;
-            avg += v;
-            if (vmax < v) vmax = v;
-        }
-        return (vmax * (1.0f - p.hybrid_weight)) + ((avg / weight) * p.hybrid_weight);
+        for (s = smin; s <= smax; s += 1.0f) tap((int) glm_rint(s), round_formula(p, g_clamp((m - fabsf(rm - s)) / m, 0.0f, 1.0f)));
     } else {
-        float vmax = 0.0f;
-        for (s = smin; s < smax; s += 1.0f) {
-            w = fetch16(tex, n, (int) glm_rint(s)) * round_formula(p, g_clamp((m - fabsf(rm - s)) / m, 0.0f, 1.0f));
-            if (vmax < w) vmax = w;
-        }
+        for (s = smin; s < smax; s += 1.0f) tap((int) glm_rint(s), round_formula(p, g_clamp((m - fabsf(rm - s)) / m, 0.0f, 1.0f)));
+    }
+}
+// running state of the three SAMPLE_MODEs, fed tap by tap in the GLSL loop's order
+struct SmoothAcc {
+    float avg, weight, vmax;
+    GLB_HD void init() { avg = 0.0f; weight = 0.0f; vmax = 0.0f; }
+    GLB_HD void add(float texel, float w) {          // smooth.glsl:34-37 / 45-50 / 56-58
+        weight += w;
+        float v = texel * w;
+        avg += v;
+        if (vmax < v) vmax = v;
+    }
+    GLB_HD void add_noweight(float texel, float w) { // same, `weight` supplied separately (precomputed)
+        float v = texel * w;
+        avg += v;
+        if (vmax < v) vmax = v;
+    }
+    GLB_HD float result(const SmoothParams& p) const {
+        if (p.sample_mode == 0) return avg / weight;
+        if (p.sample_mode == 2) return (vmax * (1.0f - p.hybrid_weight)) + ((avg / weight) * p.hybrid_weight);
         return vmax;
     }
+};
+GLB_HD float smooth_audio_raw(const SmoothParams& p, const uint16_t* tex, int n, float idx) {
+    SmoothAcc acc; acc.init();
+    smooth_enumerate(p, n, idx, [&](int i, float w) { acc.add(fetch16(tex, n, i), w); });
+    return acc.result(p);
 }
 // one output texel of the smooth pass: viewport n x 1, gl_FragCoord.x = x + 0.5, uniform w = n
 GLB_HD uint32_t smooth_pass_texel(const SmoothParams& p, const uint16_t* tex, int n, int x) {
