@@ -64,6 +64,7 @@ struct glava_b200 {
     // constants
     double* d_window; float* d_twiddle; void* d_rowtab; int* d_need; int need_count;
     TapEntry* d_tap_tab; int* d_tap_cnt; float* d_tap_wsum; int tap_max;
+    void* d_geo; int geo_box[4];   // polar geometry cache (radial / circle), see kernels.cu
     // state + outputs
     float* d_spec; float* d_applied; float* d_ring_f;
     uint16_t* d_gr_store; uint16_t* d_ring_u; uint16_t* d_tex;
@@ -263,6 +264,16 @@ static int build(glava_b200* r) {
         }
     }
     if (p.module == GLAVA_B200_MOD_BARS || p.module == GLAVA_B200_MOD_GRAPH) { if ((rc = launch_bars_rowtab(p, r->d_rowtab, r->stream)) != 0) return rc; ++r->launches; }
+    // polar modules: cache the audio-independent per-pixel geometry (circle: only when the module samples a
+    // pre-smoothed texture, i.e. smooth_audio() is a single texelFetch)
+    if (p.module == GLAVA_B200_MOD_RADIAL || (p.module == GLAVA_B200_MOD_CIRCLE && p.smooth_pass)) {
+        const size_t bytes = polar_geo_box(p, r->geo_box);
+        if (bytes > 0 && bytes <= ((size_t) 512 << 20) && !getenv("GLAVA_B200_NO_GEO")) {
+            if ((rc = dev_alloc(r, &r->d_geo, bytes, false)) != 0) return rc;
+            if ((rc = launch_polar_geo(p, r->d_geo, r->geo_box, r->stream)) != 0) return rc;
+            ++r->launches;
+        }
+    }
     CU(cudaStreamSynchronize(r->stream));
     return 0;
 }
@@ -283,6 +294,7 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     for (int i = 0; i < 2; ++i) { r->ev_spec_done[i] = nullptr; r->ev_raster_done[i] = nullptr; } r->d_chunks = nullptr; r->chunks_cap = 0;
     r->d_window = nullptr; r->d_twiddle = nullptr; r->d_rowtab = nullptr; r->d_need = nullptr; r->need_count = 0;
     r->d_tap_tab = nullptr; r->d_tap_cnt = nullptr; r->d_tap_wsum = nullptr; r->tap_max = 0;
+    r->d_geo = nullptr; r->geo_box[0] = r->geo_box[1] = r->geo_box[2] = r->geo_box[3] = 0;
     r->d_spec = r->d_applied = r->d_ring_f = nullptr; r->d_gr_store = r->d_ring_u = r->d_tex = nullptr; r->d_fb = nullptr;
     for (int i = 0; i < 2; ++i) { r->d_pcm[i][0] = r->d_pcm[i][1] = nullptr; r->ev_copied[i] = r->ev_free[i] = nullptr; }
     r->stage_cur = 0; r->copy_stream = nullptr;
@@ -375,6 +387,7 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
     ra.tex = tex_half(r, b); ra.fb = r->d_fb;
     ra.rowtab = (p.module == GLAVA_B200_MOD_BARS || p.module == GLAVA_B200_MOD_GRAPH) ? r->d_rowtab : nullptr;
     ra.batch = r->batch; ra.slots = r->slots; ra.stream0 = 0;
+    ra.geo = r->d_geo; ra.gx0 = r->geo_box[0]; ra.gy0 = r->geo_box[1]; ra.gw = r->geo_box[2]; ra.gh = r->geo_box[3];
     if (r->timing && (rc = timing_mark(r->ev_ras, r->stream)) != 0) return rc;
     if ((rc = launch_raster(p, ra, r->stream)) != 0) return rc;
     if (r->timing && (rc = timing_mark(r->ev_ras, r->stream)) != 0) return rc;

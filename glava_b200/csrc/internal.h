@@ -60,6 +60,10 @@ struct RasterArgs {
     uint8_t*  fb;               // [slots][h][w][4]
     const void* rowtab;         // module row table (bars: [h] {fill, outline} RGBA8 pairs), may be null
     int       batch, slots, stream0;
+    // polar modules: per-renderer cache of the audio-independent per-pixel geometry (RadialGeo /
+    // CircleGeo, 16 bytes each) over the bounding box of the disc that can be non-zero; may be null
+    const void* geo;
+    int       gx0, gy0, gw, gh;  // box origin and size in pixels (gx0, gw multiples of 4)
 };
 
 // ---- kernel launchers (kernels.cu); `stream` is a cudaStream_t passed as void* ------------------
@@ -67,6 +71,9 @@ int launch_spectrum(const glava_b200_params& p, const SpectrumArgs& a, bool is_f
 int launch_smooth_only(const glava_b200_params& p, const uint16_t* d_in, uint16_t* d_out, int count, void* stream);
 int launch_raster(const glava_b200_params& p, const RasterArgs& a, void* stream);
 int launch_bars_rowtab(const glava_b200_params& p, void* d_rowtab, void* stream);
+// geometry cache of the polar modules: box = {x0, y0, w, h}; returns bytes needed when d_geo == nullptr
+size_t polar_geo_box(const glava_b200_params& p, int box[4]);
+int launch_polar_geo(const glava_b200_params& p, void* d_geo, const int box[4], void* stream);
 int launch_fifo_ingest(const glava_b200_params& p, const int16_t* d_chunks, int frames, const float* src_l, const float* src_r,
                        float* dst_l, float* dst_r, int batch, void* stream);
 int spectrum_smem_bytes(int n);

@@ -619,51 +619,70 @@ raster_wave_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__
 #define CIRCLE_TW 128
 #define CIRCLE_TH 8
 __global__ void __launch_bounds__(256)
-raster_circle_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__ glava_b200_params p) {
+raster_circle_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__ glava_b200_params p, int tiles_per_cta) {
     __shared__ uint32_t tile[CIRCLE_TH + 2][CIRCLE_TW + 2];
     const int stream = a.stream0 + blockIdx.z;
     const AudioTex t = make_tex(p, a.tex, stream);
     uint32_t* fb = reinterpret_cast<uint32_t*>(a.fb) + (size_t) (stream % a.slots) * p.w * p.h;
-    const int tx0 = blockIdx.x * CIRCLE_TW, ty0 = blockIdx.y * CIRCLE_TH;
+    const int tx0 = blockIdx.x * CIRCLE_TW;
     const float cx = (float) (p.w / 2), cy = (float) (p.h / 2);
     const float reach = circle_reach(p);
     const float inner = p.circle_radius - p.circle_line / 2.0f - 2.0f;
-    // distance range of the tile (+halo) from the centre
     const float bx0 = (float) (tx0 - 1) - cx, bx1 = (float) (tx0 + CIRCLE_TW) - cx;
-    const float by0 = (float) (ty0 - 1) - cy, by1 = (float) (ty0 + CIRCLE_TH) - cy;
-    const float nx = (bx0 > 0.0f) ? bx0 : ((bx1 < 0.0f) ? -bx1 : 0.0f), ny = (by0 > 0.0f) ? by0 : ((by1 < 0.0f) ? -by1 : 0.0f);
-    const float fxm = fmaxf(fabsf(bx0), fabsf(bx1)), fym = fmaxf(fabsf(by0), fabsf(by1));
-    const bool tile_dead = (nx * nx + ny * ny > reach * reach) || (inner > 0.0f && fxm * fxm + fym * fym < inner * inner);
-    if (!tile_dead) {
-        for (int i = threadIdx.x; i < (CIRCLE_TH + 2) * (CIRCLE_TW + 2); i += blockDim.x) {
-            const int ly = i / (CIRCLE_TW + 2), lx = i - ly * (CIRCLE_TW + 2);
-            const int gx = tx0 + lx - 1, gy = ty0 + ly - 1;
-            uint32_t v = 0u;
-            if (gx >= 0 && gy >= 0 && gx < p.w && gy < p.h) {
-                const float dx = (float) gx - cx, dy = (float) gy - cy;
-                const float d2 = dx * dx + dy * dy;
-                if (d2 <= reach * reach && !(inner > 0.0f && d2 < inner * inner)) v = circle_stage1(p, t, gx, gy);
-            }
-            tile[ly][lx] = v;
-        }
-        __syncthreads();
-    }
+    const float nx = (bx0 > 0.0f) ? bx0 : ((bx1 < 0.0f) ? -bx1 : 0.0f);
+    const float fxm = fmaxf(fabsf(bx0), fabsf(bx1));
     // 256 threads: 32 quads per row x 8 rows
     const int qx = threadIdx.x & 31, qy = threadIdx.x >> 5;
-    const int x = tx0 + qx * 4, y = ty0 + qy;
-    if (x >= p.w || y >= p.h) return;
-    uint32_t px[4] = { 0u, 0u, 0u, 0u };
-    if (!tile_dead) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int lx = qx * 4 + k + 1, ly = qy + 1;
-            const uint32_t own = tile[ly][lx];
-            const uint32_t nb[6] = { tile[ly][lx + 1], tile[ly + 1][lx + 1], tile[ly + 1][lx],
-                                     tile[ly][lx - 1], tile[ly - 1][lx - 1], tile[ly - 1][lx] };
-            if (x + k < p.w) px[k] = ((own | nb[0] | nb[1] | nb[2] | nb[3] | nb[4] | nb[5]) == 0u) ? 0u : circle_finish(p, own, nb);
+    const int x = tx0 + qx * 4;
+    // a CTA walks `tiles_per_cta` vertically adjacent 128x8 tiles (a tile per CTA is too little work:
+    // most tiles are outside the annulus and only store 4 KB of zeros)
+    for (int it = 0; it < tiles_per_cta; ++it) {
+        const int ty0 = (blockIdx.y * tiles_per_cta + it) * CIRCLE_TH;
+        if (ty0 >= p.h) break;
+        // distance range of the tile (+halo) from the centre
+        const float by0 = (float) (ty0 - 1) - cy, by1 = (float) (ty0 + CIRCLE_TH) - cy;
+        const float ny = (by0 > 0.0f) ? by0 : ((by1 < 0.0f) ? -by1 : 0.0f);
+        const float fym = fmaxf(fabsf(by0), fabsf(by1));
+        const bool tile_dead = (nx * nx + ny * ny > reach * reach) || (inner > 0.0f && fxm * fxm + fym * fym < inner * inner);
+        if (!tile_dead) {
+            for (int i = threadIdx.x; i < (CIRCLE_TH + 2) * (CIRCLE_TW + 2); i += blockDim.x) {
+                const int ly = i / (CIRCLE_TW + 2), lx = i - ly * (CIRCLE_TW + 2);
+                const int gx = tx0 + lx - 1, gy = ty0 + ly - 1;
+                uint32_t v = 0u;
+                if (gx >= 0 && gy >= 0 && gx < p.w && gy < p.h) {
+                    const float dx = (float) gx - cx, dy = (float) gy - cy;
+                    const float d2 = dx * dx + dy * dy;
+                    if (d2 <= reach * reach && !(inner > 0.0f && d2 < inner * inner)) {
+                        const int bxi = gx - a.gx0, byi = gy - a.gy0;
+                        if (a.geo && bxi >= 0 && byi >= 0 && bxi < a.gw && byi < a.gh) {
+                            // cached geometry: three texel references + d, no transcendental per frame
+                            const int4 e = __ldg(reinterpret_cast<const int4*>(a.geo) + (size_t) byi * a.gw + bxi);
+                            CircleGeo g; g.dR = __int_as_float(e.x); g.e0 = e.y; g.e1 = e.z; g.e2 = e.w;
+                            v = circle_stage1_geo(p, t, g);
+                        } else v = circle_stage1(p, t, gx, gy);
+                    }
+                }
+                tile[ly][lx] = v;
+            }
+            __syncthreads();
         }
+        const int y = ty0 + qy;
+        if (x < p.w && y < p.h) {
+            uint32_t px[4] = { 0u, 0u, 0u, 0u };
+            if (!tile_dead) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int lx = qx * 4 + k + 1, ly = qy + 1;
+                    const uint32_t own = tile[ly][lx];
+                    const uint32_t nb[6] = { tile[ly][lx + 1], tile[ly + 1][lx + 1], tile[ly + 1][lx],
+                                             tile[ly][lx - 1], tile[ly - 1][lx - 1], tile[ly - 1][lx] };
+                    if (x + k < p.w) px[k] = ((own | nb[0] | nb[1] | nb[2] | nb[3] | nb[4] | nb[5]) == 0u) ? 0u : circle_finish(p, own, nb);
+                }
+            }
+            store4(fb + (size_t) y * p.w, x, p.w, px);
+        }
+        if (!tile_dead) __syncthreads();             // the tile is rewritten by the next iteration
     }
-    store4(fb + (size_t) y * p.w, x, p.w, px);
 }
 
 // radial: per-pixel polar maths (radial/1.frag + premultiply) with disc culling; same arithmetic as
@@ -693,6 +712,94 @@ raster_radial_kernel(const __grid_constant__ RasterArgs a, const __grid_constant
     }
 }
 
+// ---- polar geometry cache ------------------------------------------------------------------------
+// radial and circle spend almost all their arithmetic (atan, sqrt, sin, mod, colour ramp, blending,
+// premultiply) on quantities that depend on the pixel position and the parameters only.  They are
+// evaluated ONCE per renderer over the bounding box of the disc that can be non-zero (the same core
+// functions, so nothing changes numerically) and every frame of every stream reuses them out of L2.
+size_t polar_geo_box(const glava_b200_params& p, int box[4]) {
+    float reach, cx, cy;
+    if (p.module == GLAVA_B200_MOD_RADIAL) { reach = radial_reach(p); cx = (float) (p.w / 2) - p.radial_off_x; cy = (float) (p.h / 2) - p.radial_off_y; }
+    else if (p.module == GLAVA_B200_MOD_CIRCLE) { reach = circle_reach(p); cx = (float) (p.w / 2); cy = (float) (p.h / 2); }
+    else { box[0] = box[1] = box[2] = box[3] = 0; return 0; }
+    const int wpad = (p.w + 3) & ~3;
+    int x0 = (int) floorf(cx - reach) - 3, x1 = (int) ceilf(cx + reach) + 4;
+    int y0 = (int) floorf(cy - reach) - 3, y1 = (int) ceilf(cy + reach) + 4;
+    x0 = x0 < 0 ? 0 : (x0 & ~3); x1 = x1 > wpad ? wpad : ((x1 + 3) & ~3);
+    y0 = y0 < 0 ? 0 : y0; y1 = y1 > p.h ? p.h : y1;
+    if (x1 <= x0 || y1 <= y0) { box[0] = box[1] = box[2] = box[3] = 0; return 0; }
+    box[0] = x0; box[1] = y0; box[2] = x1 - x0; box[3] = y1 - y0;
+    return (size_t) box[2] * box[3] * 16;
+}
+
+__global__ void polar_geo_kernel(int4* __restrict__ geo, int gx0, int gy0, int gw, int gh, const __grid_constant__ glava_b200_params p) {
+    const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y;
+    if (bx >= gw || by >= gh) return;
+    const int x = gx0 + bx, y = gy0 + by;
+    int4 out;
+    if (p.module == GLAVA_B200_MOD_RADIAL) {
+        RadialGeo g = { 0u, 0u, 0.0f, -1 };
+        if (x < p.w) g = radial_geometry(p, x, y);
+        out = make_int4((int) g.lit, (int) g.unlit, __float_as_int(g.dR), g.bar);
+    } else {
+        CircleGeo g = circle_geometry(p, x, y);          // handles x >= w
+        out = make_int4(__float_as_int(g.dR), g.e0, g.e1, g.e2);
+    }
+    geo[(size_t) by * gw + bx] = out;
+}
+int launch_polar_geo(const glava_b200_params& p, void* d_geo, const int box[4], void* stream) {
+    dim3 grid((box[2] + 127) / 128, box[3]);
+    polar_geo_kernel<<<grid, 128, 0, (cudaStream_t) stream>>>(reinterpret_cast<int4*>(d_geo), box[0], box[1], box[2], box[3], p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "polar geometry kernel launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// radial from the geometry cache: per pixel one 16-byte load, one compare against the bar's height
+// (160 heights per stream, in shared memory), one select.
+#define RADIAL_MAX_BARS 1024
+__global__ void __launch_bounds__(128)
+raster_radial_geo_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__ glava_b200_params p, int rows_per_cta) {
+    __shared__ float vbar[2][RADIAL_MAX_BARS / 2 + 2];
+    const int stream = a.stream0 + blockIdx.z;
+    const AudioTex t = make_tex(p, a.tex, stream);
+    const int nk = p.radial_nbars / 2 + 2;               // k = int(|idx| / section) <= NBARS / 2 (+1 for rounding)
+    const int y0 = blockIdx.y * rows_per_cta, y1 = min(p.h, y0 + rows_per_cta);
+    const bool band_live = (y1 > a.gy0) && (y0 < a.gy0 + a.gh);
+    if (band_live) {
+        for (int i = threadIdx.x; i < 2 * nk; i += blockDim.x) {
+            const int side = i / nk, k = i - side * nk;
+            vbar[side][k] = radial_bar_value(p, t, (side << 16) | k);
+        }
+        __syncthreads();
+    }
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (x >= p.w) return;
+    uint32_t* fb = reinterpret_cast<uint32_t*>(a.fb) + (size_t) (stream % a.slots) * p.w * p.h;
+    const int4* __restrict__ geo = reinterpret_cast<const int4*>(a.geo);
+    const int bxi = x - a.gx0;
+    const bool col_live = bxi >= 0 && bxi < a.gw;        // gx0, gw multiples of 4: the quad is inside or outside as a whole
+    for (int y = y0; y < y1; ++y) {
+        uint32_t px[4] = { 0u, 0u, 0u, 0u };
+        const int byi = y - a.gy0;
+        if (col_live && byi >= 0 && byi < a.gh) {
+            const int4* g = geo + (size_t) byi * a.gw + bxi;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int4 e = __ldg(g + k);               // {lit, unlit, dR, bar}
+                uint32_t v = (uint32_t) e.y;
+                if (e.w >= 0) {
+                    const int kk = e.w & 0xffff;
+                    const float vb = kk < nk ? vbar[e.w >> 16][kk] : radial_bar_value(p, t, e.w);
+                    if (__int_as_float(e.z) <= vb) v = (uint32_t) e.x;
+                }
+                px[k] = v;
+            }
+        }
+        store4(fb + (size_t) y * p.w, x, p.w, px);
+    }
+}
+
 static int pick_block_x(int quads) {       // threads per row-segment: prefer an exact tiling of w/4
     static const int cand[] = { 96, 160, 128, 192, 256, 64 };    // measured on B200: 96 >= 160 > 256 for the store-bound kernels
     for (int c : cand) if (quads % c == 0) return c;
@@ -705,9 +812,12 @@ int launch_raster(const glava_b200_params& p, const RasterArgs& a, void* stream)
     const bool fast_bars  = p.module == GLAVA_B200_MOD_BARS && !p.bars_mirror_yx && a.rowtab && (p.w & 3) == 0;
     const bool fast_graph = p.module == GLAVA_B200_MOD_GRAPH && a.rowtab;
     const bool fast_wave  = p.module == GLAVA_B200_MOD_WAVE;
+    const bool geo_radial = p.module == GLAVA_B200_MOD_RADIAL && a.geo && p.radial_nbars <= RADIAL_MAX_BARS;
     int bx = (fast_bars || fast_graph || fast_wave) ? pick_block_x(quads) : 128;
     if (bx > 256) bx = 256;
-    int rows = (fast_bars || fast_graph || fast_wave) ? 135 : 8;   // bars: 135 >= 270 > 540 with the spectrum kernel co-running
+    // rows per CTA, measured on B200: bars 135 >= 270 > 540 (with the spectrum kernel co-running);
+    // graph / wave pay a per-thread column set-up, so whole columns (720 > 360 > 135); radial-from-cache 45 > 135
+    int rows = fast_bars ? 135 : ((fast_graph || fast_wave) ? 720 : (geo_radial ? 45 : 8));
     // development overrides for tuning sweeps (tools/tune_raster.py); unset in normal use
     if (const char* e = getenv("GLAVA_B200_ROWS")) { int v = atoi(e); if (v > 0) rows = v; }
     if (const char* e = getenv("GLAVA_B200_BX")) { int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) bx = v; }
@@ -724,10 +834,15 @@ int launch_raster(const glava_b200_params& p, const RasterArgs& a, void* stream)
         if (fast_bars) raster_bars_kernel<<<grid, bx, 0, st>>>(b, p, rows);
         else if (fast_graph) raster_graph_kernel<<<grid, bx, 0, st>>>(b, p, rows);
         else if (fast_wave) raster_wave_kernel<<<grid, bx, 0, st>>>(b, p, rows);
+        else if (p.module == GLAVA_B200_MOD_RADIAL && a.geo && p.radial_nbars <= RADIAL_MAX_BARS)
+            raster_radial_geo_kernel<<<grid, bx, 0, st>>>(b, p, rows);
         else if (p.module == GLAVA_B200_MOD_RADIAL) raster_radial_kernel<<<grid, bx, 0, st>>>(b, p, rows);
         else if (p.module == GLAVA_B200_MOD_CIRCLE) {
-            dim3 cgrid((p.w + CIRCLE_TW - 1) / CIRCLE_TW, (p.h + CIRCLE_TH - 1) / CIRCLE_TH, nz);
-            raster_circle_kernel<<<cgrid, 256, 0, st>>>(b, p);
+            int tiles = 16;                                   // 128 rows per CTA
+            if (const char* e = getenv("GLAVA_B200_CIRCLE_TILES")) { int v = atoi(e); if (v > 0) tiles = v; }
+            const int ntile_y = (p.h + CIRCLE_TH - 1) / CIRCLE_TH;
+            dim3 cgrid((p.w + CIRCLE_TW - 1) / CIRCLE_TW, (ntile_y + tiles - 1) / tiles, nz);
+            raster_circle_kernel<<<cgrid, 256, 0, st>>>(b, p, tiles);
         }
         else raster_generic_kernel<<<grid, bx, 0, st>>>(b, p, rows);
         cudaError_t e = cudaGetLastError();

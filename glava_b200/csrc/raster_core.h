@@ -122,14 +122,28 @@ GLB_HD f4 apply_frag(f4 f, f4 c) {                                         // ra
     float k = 1.0f - g_clamp(f.a, 0.0f, 1.0f);
     return mk4(f.r * f.a + c.r * k, f.g * f.a + c.g * k, f.b * f.a + c.b * k, g_max(c.a, f.a));
 }
-GLB_HD uint32_t radial_px(const glava_b200_params& p, const AudioTex& t, int x, int y) {
+// Everything radial/1.frag + radial/2.frag compute for a pixel EXCEPT the audio lookup: the only
+// audio-dependent step is the test `d <= v` for a pixel inside a bar, so a pixel is fully described by
+// its two possible final RGBA8 values, the bar it belongs to and its d (= distance - C_RADIUS).
+// raster_radial_kernel caches this per renderer (the same for every stream and frame).
+struct RadialGeo {
+    uint32_t lit;      // final value if the bar reaches this pixel (d <= v)
+    uint32_t unlit;    // final value otherwise (ring or 0)
+    float    dR;       // d - C_RADIUS
+    int      bar;      // -1: not on a bar; else (side << 16) | k with side 0 = audio_l, 1 = audio_r, pos = k / (NBARS/2)
+};
+GLB_HD uint32_t radial_finish(const glava_b200_params& p, f4 frag) {
+    uint32_t px = pack8(frag);
+    return p.premultiply_alpha ? premultiply8(px) : px;                    // radial/2.frag
+}
+GLB_HD RadialGeo radial_geometry(const glava_b200_params& p, int x, int y) {
+    RadialGeo g = { 0u, 0u, 0.0f, -1 };
     f4 frag = mk4(0, 0, 0, 0);
     float dx = ((float) x + 0.5f) - (float) (p.w / 2) + p.radial_off_x,
           dy = ((float) y + 0.5f) - (float) (p.h / 2) + p.radial_off_y;
     float theta = glm_atan2(dy, dx);
     float d = sqrtf((dx * dx) + (dy * dy));
     float R = p.radial_radius, hl = p.radial_line / 2.0f;
-    bool done = false;
     if (d > R - hl && d < R + hl) {
         frag = apply_frag(frag, mk4a(p.radial_outline));
         frag.a *= g_clamp((p.radial_line_half - fabsf(R - d)) * p.radial_c_alias, 0.0f, 1.0f);
@@ -144,25 +158,29 @@ GLB_HD uint32_t radial_px(const glava_b200_params& p, const AudioTex& t, int x, 
             float dir = g_mod(fabsf(idx), GLB_TWOPI);
             if (dir > GLB_PI) idx = -g_sign(idx) * (GLB_TWOPI - dir);
             if (p.radial_invert == 0) idx = -idx;
-            float pos = (float) (int) (fabsf(idx) / section) / (float) (p.radial_nbars / 2);
-            float v = sample_audio(t, idx > 0.0f ? t.l : t.r, pos);
-            v *= p.radial_amplify;
+            g.bar = ((idx > 0.0f ? 0 : 1) << 16) | (int) (fabsf(idx) / section);
             d -= R;
-            if (d <= v) {
-                f4 r = eval_color(p.radial_color, d);
-                r.a *= (((p.radial_bar_width / 2.0f) - fabsf(ym)) * p.radial_bar_alias);
-                frag = apply_frag(frag, r);
-                done = true;
-            }
+            g.dR = d;
+            f4 r = eval_color(p.radial_color, d);
+            r.a *= (((p.radial_bar_width / 2.0f) - fabsf(ym)) * p.radial_bar_alias);
+            g.lit = radial_finish(p, apply_frag(frag, r));
         }
     }
-    if (!done) {
-        // neither ring nor bar: apply_frag(0, 0) = 0 and stage 2 keeps 0 — skip the arithmetic
-        if (frag.r == 0.0f && frag.g == 0.0f && frag.b == 0.0f && frag.a == 0.0f) return 0u;
-        frag = apply_frag(frag, mk4(0, 0, 0, 0));
-    }
-    uint32_t px = pack8(frag);
-    return p.premultiply_alpha ? premultiply8(px) : px;                    // radial/2.frag
+    // neither ring nor lit bar: apply_frag(0, 0) = 0 and stage 2 keeps 0 — skip the arithmetic
+    if (frag.r == 0.0f && frag.g == 0.0f && frag.b == 0.0f && frag.a == 0.0f) g.unlit = 0u;
+    else g.unlit = radial_finish(p, apply_frag(frag, mk4(0, 0, 0, 0)));
+    return g;
+}
+// bar height of bar `bar` (radial/1.frag:68-73): pos = int(abs(idx) / section) / float(NBARS / 2)
+GLB_HD float radial_bar_value(const glava_b200_params& p, const AudioTex& t, int bar) {
+    float pos = (float) (bar & 0xffff) / (float) (p.radial_nbars / 2);
+    float v = sample_audio(t, (bar >> 16) ? t.r : t.l, pos);
+    return v * p.radial_amplify;
+}
+GLB_HD uint32_t radial_px(const glava_b200_params& p, const AudioTex& t, int x, int y) {
+    RadialGeo g = radial_geometry(p, x, y);
+    if (g.bar < 0) return g.unlit;
+    return (g.dR <= radial_bar_value(p, t, g.bar)) ? g.lit : g.unlit;
 }
 // conservative test: can pixel (x, y) be non-zero?  outside this disc radial_px() is exactly 0
 GLB_HD float radial_reach(const glava_b200_params& p) {
@@ -201,6 +219,54 @@ GLB_HD uint32_t circle_stage1(const glava_b200_params& p, const AudioTex& t, int
         if (in) return pack8(mk4a(p.circle_outline));
     }
     return 0u;
+}
+// The audio-independent part of circle/1.frag for one pixel (valid when the textures are pre-smoothed,
+// i.e. smooth_audio() is a single texelFetch): d - C_RADIUS and, for the three angles theta,
+// theta +- adv, which texel of which channel apply_smooth() fetches.  Cached per renderer by
+// raster_circle_kernel.  e* = -1: pixel cannot be lit (inside the inner circle / outside the surface);
+// else (channel << 30) | texel, texel == 0x3fffffff meaning "out of range, reads 0".
+struct CircleGeo { float dR; int e0, e1, e2; };
+GLB_HD int circle_texel_ref(const glava_b200_params& p, float theta) {     // circle/1.frag:34-45 without the fetch
+    float idx = theta + p.circle_rotate;
+    float dir = g_mod(fabsf(idx), GLB_TWOPI);
+    if (dir > GLB_PI) idx = -g_sign(idx) * (GLB_TWOPI - dir);
+    if (p.circle_invert > 0) idx = -idx;
+    float pos = fabsf(idx) / (GLB_PI + 0.001f);
+    int i = (int) glm_rint(pos * (float) p.n);
+    if (i < 0 || i >= p.n) i = 0x3fffffff;
+    return ((idx > 0.0f ? 0 : 1) << 30) | i;
+}
+GLB_HD CircleGeo circle_geometry(const glava_b200_params& p, int x, int y) {
+    CircleGeo g = { 0.0f, -1, -1, -1 };
+    if (x < 0 || y < 0 || x >= p.w || y >= p.h) return g;
+    float dx = (float) x - (float) (p.w / 2), dy = (float) y - (float) (p.h / 2);
+    float theta = glm_atan2(dy, dx);
+    float d = sqrtf((dx * dx) + (dy * dy));
+    float adv = (1.0f / d) * (p.circle_line * 0.5f);
+    float adj0 = theta + adv, adj1 = theta - adv;
+    d -= p.circle_radius;
+    if (d >= -(p.circle_line / 2.0f)) {
+        g.dR = d;
+        g.e0 = circle_texel_ref(p, theta); g.e1 = circle_texel_ref(p, adj0); g.e2 = circle_texel_ref(p, adj1);
+    }
+    return g;
+}
+GLB_HD float circle_ref_value(const glava_b200_params& p, const AudioTex& t, int e) {
+    const int i = e & 0x3fffffff;
+    const uint16_t* tex = (e >> 30) ? t.r : t.l;
+    float v = (i >= t.n) ? 0.0f : from16(tex[i]);
+    return v * p.circle_amplify;
+}
+GLB_HD uint32_t circle_stage1_geo(const glava_b200_params& p, const AudioTex& t, const CircleGeo& g) {
+    if (g.e0 < 0) return 0u;
+    float hl = p.circle_line / 2.0f;
+    float v = circle_ref_value(p, t, g.e0);
+    float adj0 = circle_ref_value(p, t, g.e1) - v;
+    float adj1 = circle_ref_value(p, t, g.e2) - v;
+    float dmax = g_max(adj0, adj1), dmin = g_min(adj0, adj1);
+    float d = g.dR - v;
+    bool in = p.circle_fill ? (d < hl) : ((d > -hl && d < hl) || (d <= dmax && d >= dmin));
+    return in ? pack8(mk4a(p.circle_outline)) : 0u;
 }
 // 8-tap neighbour mean as written in circle/2.frag:18-27, graph/2.frag:21-30, wave/2.frag:18-27:
 // taps a3 and a7 repeat a0 and a4.  nb[] = stage values at (x+1,y) (x+1,y+1) (x,y+1) (x-1,y) (x-1,y-1) (x,y-1)

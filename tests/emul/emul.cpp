@@ -200,6 +200,17 @@ int emul_raster_fast(const glava_b200_params* pp, const uint16_t* tl, const uint
         }
         return 0;
     }
+    if (p.module == GLAVA_B200_MOD_CIRCLE && p.smooth_pass) {
+        // raster_circle_kernel: stage 1 from the cached geometry (texel references), stages 2-3 from the tile
+        std::vector<uint32_t> s1((size_t) (p.w + 2) * (p.h + 2), 0u);
+        auto at = [&](int x, int y) -> uint32_t& { return s1[(size_t) (y + 1) * (p.w + 2) + (x + 1)]; };
+        for (int y = 0; y < p.h; ++y) for (int x = 0; x < p.w; ++x) at(x, y) = circle_stage1_geo(p, t, circle_geometry(p, x, y));
+        for (int y = 0; y < p.h; ++y) for (int x = 0; x < p.w; ++x) {
+            const uint32_t nb[6] = { at(x + 1, y), at(x + 1, y + 1), at(x, y + 1), at(x - 1, y), at(x - 1, y - 1), at(x, y - 1) };
+            dst[(size_t) y * p.w + x] = circle_finish(p, at(x, y), nb);
+        }
+        return 0;
+    }
     if (p.module == GLAVA_B200_MOD_WAVE) {
         std::vector<WaveCol> c(p.w + 2);
         for (int x = -1; x <= p.w; ++x) { int xc = x < 0 ? 0 : (x >= p.w ? p.w - 1 : x); c[x + 1] = wave_column(p, t, xc); }

@@ -64,7 +64,7 @@ def test_raster_bit_exact(orc_pm, module, w, h, built):
     tl = orc_pm.smooth_pass(op, _tex(n, 1)); tr = orc_pm.smooth_pass(op, _tex(n, 2))
     want = orc_pm.raster(op, tl, tr)
     assert np.array_equal(want, emul.raster(p, tl, tr))
-    if module in ("bars", "graph", "wave"):
+    if module in ("bars", "graph", "wave", "circle"):
         assert np.array_equal(want, emul.raster(p, tl, tr, fast=True))      # hoisted evaluation of the kernels
 
 

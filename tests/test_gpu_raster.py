@@ -103,3 +103,44 @@ def test_modified_false_rerasters_last_spectrum(built):
         rings.advance(); r.update(rings.lb, rings.rb, False)          # no audio update: render.c:2268-2272
         b = r.readback(1); t1 = r.textures()
     assert np.array_equal(a, b) and np.array_equal(t0[0], t1[0])
+
+
+@pytest.mark.parametrize("module", ["radial", "circle"])
+def test_polar_geometry_cache_equals_direct_evaluation(orc_pm, module, monkeypatch, built):
+    """radial / circle normally run from the per-renderer geometry cache; GLAVA_B200_NO_GEO=1 selects the
+    kernels that evaluate the shader maths per pixel.  Both must give the oracle's pixels."""
+    p = g.default_params(module, n=2048, w=900, h=700); op = params_from(p)
+    tl, tr = _textures(orc_pm, op, 2048, 2, 21)
+    frames = []
+    for no_geo in ("", "1"):
+        if no_geo:
+            monkeypatch.setenv("GLAVA_B200_NO_GEO", "1")
+        else:
+            monkeypatch.delenv("GLAVA_B200_NO_GEO", raising=False)
+        with g.Renderer(p, batch=2) as r:
+            r.raster_textures(tl, tr)
+            frames.append([r.readback(s) for s in range(2)])
+    for s in range(2):
+        want = orc_pm.raster(op, tl[s], tr[s])
+        assert np.array_equal(frames[0][s], want) and np.array_equal(frames[1][s], want)
+
+
+def test_tap_table_equals_direct_k5(built, monkeypatch):
+    """lazy K5 runs from a precomputed (index, weight) table; GLAVA_B200_NO_TAPTAB=1 evaluates the weights
+    in the kernel.  Same textures at the sampled texels, hence same frames."""
+    n, batch = 4096, 2
+    rings = g.StreamRings(batch, n)
+    for _ in range(20):
+        rings.advance()
+    out = []
+    for flag in ("", "1"):
+        if flag:
+            monkeypatch.setenv("GLAVA_B200_NO_TAPTAB", "1")
+        else:
+            monkeypatch.delenv("GLAVA_B200_NO_TAPTAB", raising=False)
+        p = g.default_params("bars", n=n, w=1920, h=120, lazy_smooth=1)
+        with g.Renderer(p, batch=batch) as r:
+            r.update(rings.lb, rings.rb, True)
+            out.append([r.readback(s) for s in range(batch)])
+    for s in range(batch):
+        assert np.array_equal(out[0][s], out[1][s])
