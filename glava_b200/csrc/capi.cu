@@ -174,7 +174,15 @@ static int build(glava_b200* r) {
     {
         int lo = 0, hi = 0;
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CU(cudaStreamCreateWithPriority(&r->spec_stream, cudaStreamNonBlocking, hi));
+        // Spectrum stream priority.  Measured on B200 (bars, 1024 streams/GPU, whole step): low/equal 705 k
+        // frames/s with the raster kernel at 0.96 of the HBM peak while co-running; high 703 k with the
+        // raster kernel at 0.89 (the spectrum CTAs then grab most of each SM's registers first); no
+        // overlap at all 680 k.  Default: lowest.  GLAVA_B200_SPEC_PRIO=high|equal overrides.
+        const char* pr = getenv("GLAVA_B200_SPEC_PRIO");
+        int prio = lo;
+        if (pr && !strcmp(pr, "high")) prio = hi; else if (pr && !strcmp(pr, "equal")) prio = 0;
+        if (getenv("GLAVA_B200_NO_OVERLAP")) r->spec_stream = r->stream;   // tuning aid: serialise spectrum and raster
+        else CU(cudaStreamCreateWithPriority(&r->spec_stream, cudaStreamNonBlocking, prio));
     }
     for (int i = 0; i < 2; ++i) {
         CU(cudaEventCreateWithFlags(&r->ev_spec_done[i], cudaEventDisableTiming));
@@ -191,8 +199,39 @@ static int build(glava_b200* r) {
     for (int i = 0; i < 2; ++i) for (int c = 0; c < 2; ++c) ALLOC(r->d_ring[i][c], (size_t) r->batch * n * 4, true);
     ALLOC(r->d_window, n * 8, false); ALLOC(r->d_twiddle, n * 4, false);
     ALLOC(r->d_spec, planes * n * 4, true);
-    if (p.accel_fft) { ALLOC(r->d_gr_store, planes * n * 2, true); ALLOC(r->d_ring_u, planes * F * n * 2, true); }
-    else             { ALLOC(r->d_applied, planes * n * 4, true);  ALLOC(r->d_ring_f, planes * F * n * 4, true); }
+    // gravity + average state: ONE allocation, so a single L2 access-policy window can cover it (below)
+    char* state = nullptr; size_t state_bytes = 0;
+    if (p.accel_fft) {
+        state_bytes = planes * n * 2 * (1 + F);
+        ALLOC(state, state_bytes, true);
+        r->d_gr_store = (uint16_t*) state; r->d_ring_u = (uint16_t*) (state + planes * n * 2);
+    } else {
+        state_bytes = planes * n * 4 * (1 + F);
+        ALLOC(state, state_bytes, true);
+        r->d_applied = (float*) state; r->d_ring_f = (float*) (state + planes * n * 4);
+    }
+    // EXPERIMENT, off by default (GLAVA_B200_L2_PERSIST=1): pin the spectrum kernel's read-modify-write
+    // state in the 126 MB L2 with a persisting access window, so that its DRAM reads do not get mixed into
+    // the raster kernel's write stream.  Measured on B200: the persisting carve-out takes L2 away from
+    // the raster kernel's write-back path and HALVES its store bandwidth (1.03 -> 0.44 of the HBM peak,
+    // 702 k -> 328 k frames/s).  Kept only so the negative result is reproducible.
+    if (getenv("GLAVA_B200_L2_PERSIST")) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, r->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+            size_t want = state_bytes < (size_t) prop.persistingL2CacheMaxSize ? state_bytes : (size_t) prop.persistingL2CacheMaxSize;
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof(attr));
+            size_t win = state_bytes < (size_t) prop.accessPolicyMaxWindowSize ? state_bytes : (size_t) prop.accessPolicyMaxWindowSize;
+            attr.accessPolicyWindow.base_ptr = state;
+            attr.accessPolicyWindow.num_bytes = win;
+            attr.accessPolicyWindow.hitRatio = win > 0 ? (float) ((double) want / (double) win) : 0.0f;
+            if (attr.accessPolicyWindow.hitRatio > 1.0f) attr.accessPolicyWindow.hitRatio = 1.0f;
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (cudaStreamSetAttribute(r->spec_stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+        }
+    }
     ALLOC(r->d_tex, 2 * planes * n * 2, true);          // double-buffered: spectrum i+1 writes one half while raster i reads the other
     ALLOC(r->d_rowtab, (size_t) p.h * 8, true);
     // framebuffers: [slots][h][w] RGBA8
@@ -311,7 +350,7 @@ void glava_b200_destroy(glava_b200* r) {
     for (cudaEvent_t e : r->ev_spec) cudaEventDestroy(e);
     for (cudaEvent_t e : r->ev_ras) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) { if (r->ev_spec_done[i]) cudaEventDestroy(r->ev_spec_done[i]); if (r->ev_raster_done[i]) cudaEventDestroy(r->ev_raster_done[i]); }
-    if (r->spec_stream) cudaStreamDestroy(r->spec_stream);
+    if (r->spec_stream && r->spec_stream != r->stream) cudaStreamDestroy(r->spec_stream);
     for (void* p : r->allocs) cudaFree(p);
     if (r->d_chunks) cudaFree(r->d_chunks);
     for (int i = 0; i < 2; ++i) { if (r->ev_copied[i]) cudaEventDestroy(r->ev_copied[i]); if (r->ev_free[i]) cudaEventDestroy(r->ev_free[i]); }

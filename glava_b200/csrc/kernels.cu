@@ -104,8 +104,19 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
 
   for (int u = blockIdx.x; u < units; u += gridDim.x) {
     const int c = IS_FFT ? u : 2 * u, ch = c & 1;
-    mbar_wait(bar, parity); parity ^= 1u;
     const size_t plane = (size_t) c * N;
+    if (IS_FFT && p.accel_fft) {
+        // while the PCM load is in flight: pull this plane's gravity / average state (1 + F planes of
+        // u16, HBM-resident) towards L2, so the epilogue's loads after the FFT are L2 hits
+        const char* g0 = reinterpret_cast<const char*>(a.gr_store + plane);
+        const char* r0 = reinterpret_cast<const char*>(a.ring_u + plane * F);
+        const int lines_g = (N * 2) / 128, lines_r = (N * 2 * F) / 128;
+        for (int i = tid; i < lines_g + lines_r; i += T) {
+            const char* ptr = i < lines_g ? g0 + (size_t) i * 128 : r0 + (size_t) (i - lines_g) * 128;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+        }
+    }
+    mbar_wait(bar, parity); parity ^= 1u;
 
     if constexpr (IS_FFT) {
         // --- window (render.c:793-795: float * double -> float) folded into the first pass loads ----
@@ -158,6 +169,44 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
                         int fr = out_idx - i; if (fr < 0) fr += FT;
                         off[i] = fr * N; wt[i] = a.avg_w_b[i];
                     }
+                }
+                if constexpr (FT > 0) {
+                    // 4 elements per trip: all their state loads (1 + FT-1 each) are issued before the
+                    // first dependent use, so the global-load latency is paid once per trip, not per element
+                    constexpr int U = (N / T) % 4 == 0 ? 4 : ((N / T) % 2 == 0 ? 2 : 1);
+                    static_assert((N / T) % U == 0, "N / T must be a multiple of the epilogue unroll");
+                    for (int n0 = tid; n0 < N; n0 += U * T) {
+                        uint32_t g_old[U], rg[U][FT];
+#pragma unroll
+                        for (int e = 0; e < U; ++e) {
+                            const int n = n0 + e * T;
+                            g_old[e] = grs[n];
+#pragma unroll
+                            for (int i = 1; i < FT; ++i) rg[e][i] = ring[off[i] + n];
+                        }
+#pragma unroll
+                        for (int e = 0; e < U; ++e) {
+                            const int n = n0 + e * T;
+                            cpx z = buf[fft_pad(n >> 1)];
+                            float v = fft_post((n & 1) ? z.y : z.x, n, N, p.fft_scale, p.fft_cutoff);
+                            spec[n] = v;
+                            uint32_t gq = gravity_b(unorm16(v), g_old[e], diff);
+                            grs[n] = (uint16_t) gq;
+                            uint32_t texel = gq;
+                            if (FT > 1) {
+                                ring[off[0] + n] = (uint16_t) gq;
+                                float r = 0.0f;
+#pragma unroll
+                                for (int i = 0; i < FT; ++i) {         // t0 = most recent (render.c:2250-2255)
+                                    float tx = from16(i == 0 ? gq : rg[e][i]);
+                                    if (a.avg_b_windowed) r += wt[i] * tx; else r += tx;
+                                }
+                                texel = unorm16(r / (float) FT);
+                            }
+                            av[n] = (uint16_t) texel;
+                        }
+                    }
+                    return;
                 }
                 for (int n = tid; n < N; n += T) {
                     cpx z = buf[fft_pad(n >> 1)];
@@ -259,11 +308,20 @@ template <int LOG2N, bool IS_FFT>
 static int launch_spectrum_t(const glava_b200_params& p, const SpectrumArgs& a, cudaStream_t st) {
     using C = SpecCfg<LOG2N>;
     auto kern = spectrum_kernel<LOG2N, IS_FFT>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    // Residency cap (tuning aid, off): the kernel co-runs with the raster kernel (capi.cu run_update) and
+    // at full occupancy (5 CTAs x 256 threads x 48 registers per SM) takes most of the register file.
+    // Requesting more dynamic shared memory than needed caps it at `cap` CTAs per SM.  Measured on B200
+    // (whole step, 1024 streams): no cap 705 k frames/s > cap 3: 686 k > cap 2: 647 k > cap 1: 540 k —
+    // the stretched spectrum kernel (and the L1 it takes from the raster kernel) costs more than it frees.
+    static int smem_req = 0;
+    if (!smem_req) {
+        int cap = 0;
+        if (const char* e = getenv("GLAVA_B200_SPEC_RESIDENT")) cap = atoi(e);
+        smem_req = C::SMEM;
+        if (cap > 0) { int want = (227 * 1024) / cap - 1024; if (want > smem_req) smem_req = want; }
+        if (smem_req > 227 * 1024) smem_req = 227 * 1024;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req);
         if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "cudaFuncSetAttribute(spectrum): %s", cudaGetErrorString(e));
-        attr_set = true;
     }
     // Persistent grid: a few CTAs per SM.  Small on purpose — this kernel is latency bound and is meant
     // to run UNDER the HBM-bound raster kernel of the previous update (capi.cu run_update) without taking
@@ -274,7 +332,7 @@ static int launch_spectrum_t(const glava_b200_params& p, const SpectrumArgs& a, 
     if (const char* e = getenv("GLAVA_B200_SPEC_CTAS_PER_SM")) per_sm = atoi(e);
     const int units = IS_FFT ? a.batch * 2 : a.batch;
     int grid = (per_sm > 0 && sm_count * per_sm < units) ? sm_count * per_sm : units;
-    kern<<<grid, C::T, C::SMEM, st>>>(a, p);
+    kern<<<grid, C::T, smem_req, st>>>(a, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "spectrum kernel launch: %s", cudaGetErrorString(e));
     return 0;
