@@ -206,35 +206,26 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
                             av[n] = (uint16_t) texel;
                         }
                     }
-                    return;
-                }
-                for (int n = tid; n < N; n += T) {
-                    cpx z = buf[fft_pad(n >> 1)];
-                    float v = fft_post((n & 1) ? z.y : z.x, n, N, p.fft_scale, p.fft_cutoff);
-                    spec[n] = v;
-                    uint32_t gq = gravity_b(unorm16(v), grs[n], diff);
-                    grs[n] = (uint16_t) gq;
-                    uint32_t texel = gq;
-                    if (FF > 1) {
-                        float r = 0.0f;
-                        if constexpr (FT > 0) {
-                            ring[off[0] + n] = (uint16_t) gq;
-#pragma unroll
-                            for (int i = 0; i < FT; ++i) {             // t0 = most recent (render.c:2250-2255)
-                                float tx = from16(i == 0 ? gq : (uint32_t) ring[off[i] + n]);
-                                if (a.avg_b_windowed) r += wt[i] * tx; else r += tx;
-                            }
-                        } else {
+                } else {
+                    for (int n = tid; n < N; n += T) {                 // any F: runtime loop
+                        cpx z = buf[fft_pad(n >> 1)];
+                        float v = fft_post((n & 1) ? z.y : z.x, n, N, p.fft_scale, p.fft_cutoff);
+                        spec[n] = v;
+                        uint32_t gq = gravity_b(unorm16(v), grs[n], diff);
+                        grs[n] = (uint16_t) gq;
+                        uint32_t texel = gq;
+                        if (FF > 1) {
+                            float r = 0.0f;
                             ring[(size_t) out_idx * N + n] = (uint16_t) gq;
                             for (int i = 0; i < F; ++i) {
                                 int fr = out_idx - i; if (fr < 0) fr += F;
                                 float tx = from16(i == 0 ? gq : (uint32_t) ring[(size_t) fr * N + n]);
                                 if (a.avg_b_windowed) r += a.avg_w_b[i] * tx; else r += tx;
                             }
+                            texel = unorm16(r / (float) FF);
                         }
-                        texel = unorm16(r / (float) FF);
+                        av[n] = (uint16_t) texel;
                     }
-                    av[n] = (uint16_t) texel;
                 }
             };
             switch (F) {
@@ -692,6 +683,21 @@ raster_circle_kernel(const __grid_constant__ RasterArgs a, const __grid_constant
     // 256 threads: 32 quads per row x 8 rows
     const int qx = threadIdx.x & 31, qy = threadIdx.x >> 5;
     const int x = tx0 + qx * 4;
+    // whole CTA region (its 128 columns x tiles_per_cta*8 rows, + halo) outside the disc: bare zero-store loop
+    {
+        const int Y0 = blockIdx.y * tiles_per_cta * CIRCLE_TH, Y1 = min(p.h, Y0 + tiles_per_cta * CIRCLE_TH);
+        const float cb0 = (float) (Y0 - 1) - cy, cb1 = (float) Y1 - cy;
+        const float cny = (cb0 > 0.0f) ? cb0 : ((cb1 < 0.0f) ? -cb1 : 0.0f);
+        if (nx * nx + cny * cny > reach * reach && (p.w & 3) == 0) {
+            if (x < p.w) {
+                const int stride = p.w >> 2;
+                uint4* ptr = reinterpret_cast<uint4*>(fb) + (size_t) (Y0 + qy) * stride + (x >> 2);
+                const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+                for (int y = Y0 + qy; y < Y1; y += CIRCLE_TH, ptr += (size_t) CIRCLE_TH * stride) __stcs(ptr, zero);
+            }
+            return;
+        }
+    }
     // a CTA walks `tiles_per_cta` vertically adjacent 128x8 tiles (a tile per CTA is too little work:
     // most tiles are outside the annulus and only store 4 KB of zeros)
     for (int it = 0; it < tiles_per_cta; ++it) {
@@ -703,6 +709,8 @@ raster_circle_kernel(const __grid_constant__ RasterArgs a, const __grid_constant
         const float fym = fmaxf(fabsf(by0), fabsf(by1));
         const bool tile_dead = (nx * nx + ny * ny > reach * reach) || (inner > 0.0f && fxm * fxm + fym * fym < inner * inner);
         if (!tile_dead) {
+            // (batching the geometry loads of a thread's 5-6 cells ahead of the dependent texel fetches was
+            // measured slower: 64 -> 106 registers, half the resident warps)
             for (int i = threadIdx.x; i < (CIRCLE_TH + 2) * (CIRCLE_TW + 2); i += blockDim.x) {
                 const int ly = i / (CIRCLE_TW + 2), lx = i - ly * (CIRCLE_TW + 2);
                 const int gx = tx0 + lx - 1, gy = ty0 + ly - 1;
@@ -787,7 +795,9 @@ size_t polar_geo_box(const glava_b200_params& p, int box[4]) {
     y0 = y0 < 0 ? 0 : y0; y1 = y1 > p.h ? p.h : y1;
     if (x1 <= x0 || y1 <= y0) { box[0] = box[1] = box[2] = box[3] = 0; return 0; }
     box[0] = x0; box[1] = y0; box[2] = x1 - x0; box[3] = y1 - y0;
-    return (size_t) box[2] * box[3] * 16;
+    // radial: [full 16 B/px][{lit, dR} 8 B/px][class code 1 B/px]; circle: 16 B/px
+    const size_t px = (size_t) box[2] * box[3];
+    return p.module == GLAVA_B200_MOD_RADIAL ? px * 25 : px * 16;
 }
 
 __global__ void polar_geo_kernel(int4* __restrict__ geo, int gx0, int gy0, int gw, int gh, const __grid_constant__ glava_b200_params p) {
@@ -799,6 +809,22 @@ __global__ void polar_geo_kernel(int4* __restrict__ geo, int gx0, int gy0, int g
         RadialGeo g = { 0u, 0u, 0.0f, -1 };
         if (x < p.w) g = radial_geometry(p, x, y);
         out = make_int4((int) g.lit, (int) g.unlit, __float_as_int(g.dR), g.bar);
+        // compact levels read by raster_radial_geo_kernel: 1-byte class code per pixel
+        //   0        pixel is always 0
+        //   1..254   plain bar pixel (unlit value 0): 1 + side * nk + k, its {lit, dR} in the 8-byte level
+        //   255      anything else (ring zone, bar id that does not fit): full 16-byte entry
+        const size_t npx = (size_t) gw * gh, at = (size_t) by * gw + bx;
+        int2* bar8 = reinterpret_cast<int2*>(geo + npx);
+        unsigned char* code = reinterpret_cast<unsigned char*>(bar8 + npx);
+        const int nk = p.radial_nbars / 2 + 2;
+        int c;
+        if (g.bar < 0) c = (g.unlit == 0u) ? 0 : 255;
+        else {
+            const int id = 1 + (g.bar >> 16) * nk + (g.bar & 0xffff);
+            c = (g.unlit == 0u && (g.bar & 0xffff) < nk && id <= 254) ? id : 255;
+        }
+        bar8[at] = make_int2((int) g.lit, __float_as_int(g.dR));
+        code[at] = (unsigned char) c;
     } else {
         CircleGeo g = circle_geometry(p, x, y);          // handles x >= w
         out = make_int4(__float_as_int(g.dR), g.e0, g.e1, g.e2);
@@ -818,7 +844,7 @@ int launch_polar_geo(const glava_b200_params& p, void* d_geo, const int box[4], 
 #define RADIAL_MAX_BARS 1024
 __global__ void __launch_bounds__(128)
 raster_radial_geo_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__ glava_b200_params p, int rows_per_cta) {
-    __shared__ float vbar[2][RADIAL_MAX_BARS / 2 + 2];
+    __shared__ float vflat[RADIAL_MAX_BARS + 4];        // bar heights, index side * nk + k (== class code - 1)
     const int stream = a.stream0 + blockIdx.z;
     const AudioTex t = make_tex(p, a.tex, stream);
     const int nk = p.radial_nbars / 2 + 2;               // k = int(|idx| / section) <= NBARS / 2 (+1 for rounding)
@@ -827,31 +853,52 @@ raster_radial_geo_kernel(const __grid_constant__ RasterArgs a, const __grid_cons
     if (band_live) {
         for (int i = threadIdx.x; i < 2 * nk; i += blockDim.x) {
             const int side = i / nk, k = i - side * nk;
-            vbar[side][k] = radial_bar_value(p, t, (side << 16) | k);
+            vflat[i] = radial_bar_value(p, t, (side << 16) | k);
         }
         __syncthreads();
     }
     const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (x >= p.w) return;
     uint32_t* fb = reinterpret_cast<uint32_t*>(a.fb) + (size_t) (stream % a.slots) * p.w * p.h;
-    const int4* __restrict__ geo = reinterpret_cast<const int4*>(a.geo);
+    const size_t npx = (size_t) a.gw * a.gh;
+    const int4* __restrict__ geo = reinterpret_cast<const int4*>(a.geo);                    // full entries
+    const int2* __restrict__ bar8 = reinterpret_cast<const int2*>(geo + npx);               // {lit, dR}
+    const unsigned char* __restrict__ code = reinterpret_cast<const unsigned char*>(bar8 + npx);
     const int bxi = x - a.gx0;
     const bool col_live = bxi >= 0 && bxi < a.gw;        // gx0, gw multiples of 4: the quad is inside or outside as a whole
+    // One row per trip on purpose: batching the loads of 4 rows (more memory-level parallelism per warp)
+    // was measured 2x SLOWER on B200 — it took the kernel from 64 to 94 registers and halved the resident
+    // warps, and even the pure zero-store rows outside the box need the occupancy.
     for (int y = y0; y < y1; ++y) {
         uint32_t px[4] = { 0u, 0u, 0u, 0u };
         const int byi = y - a.gy0;
         if (col_live && byi >= 0 && byi < a.gh) {
-            const int4* g = geo + (size_t) byi * a.gw + bxi;
+            const size_t at = (size_t) byi * a.gw + bxi;
+            // codes and {lit, dR} are fetched together (independent addresses): one L2 round trip per
+            // row instead of two dependent ones — the row loop is latency x occupancy bound
+            const uint32_t codes = __ldg(reinterpret_cast<const uint32_t*>(code + at));       // 4 pixels
+            const int4 e01 = __ldg(reinterpret_cast<const int4*>(bar8 + at));                 // pixels 0, 1
+            const int4 e23 = __ldg(reinterpret_cast<const int4*>(bar8 + at) + 1);             // pixels 2, 3
+            if (codes != 0u) {
+                const int2 e8[4] = { make_int2(e01.x, e01.y), make_int2(e01.z, e01.w), make_int2(e23.x, e23.y), make_int2(e23.z, e23.w) };
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int4 e = __ldg(g + k);               // {lit, unlit, dR, bar}
-                uint32_t v = (uint32_t) e.y;
-                if (e.w >= 0) {
-                    const int kk = e.w & 0xffff;
-                    const float vb = kk < nk ? vbar[e.w >> 16][kk] : radial_bar_value(p, t, e.w);
-                    if (__int_as_float(e.z) <= vb) v = (uint32_t) e.x;
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t c = (codes >> (8 * k)) & 255u;
+                    if (c == 0u) continue;
+                    if (c != 255u) {
+                        const int2 e = e8[k];
+                        if (__int_as_float(e.y) <= vflat[c - 1u]) px[k] = (uint32_t) e.x;
+                    } else {
+                        const int4 e = __ldg(geo + at + k);            // {lit, unlit, dR, bar}
+                        uint32_t v = (uint32_t) e.y;
+                        if (e.w >= 0) {
+                            const int kk = e.w & 0xffff;
+                            const float vb = kk < nk ? vflat[(e.w >> 16) * nk + kk] : radial_bar_value(p, t, e.w);
+                            if (__int_as_float(e.z) <= vb) v = (uint32_t) e.x;
+                        }
+                        px[k] = v;
+                    }
                 }
-                px[k] = v;
             }
         }
         store4(fb + (size_t) y * p.w, x, p.w, px);
