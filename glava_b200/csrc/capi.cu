@@ -63,7 +63,7 @@ struct glava_b200 {
     int16_t* d_chunks; size_t chunks_cap;
     // constants
     double* d_window; float* d_twiddle; void* d_rowtab; int* d_need; int need_count;
-    TapEntry* d_tap_tab; int* d_tap_cnt; float* d_tap_wsum; int tap_max;
+    TapEntry* d_tap_tab; int* d_tap_cnt; float* d_tap_wsum; int tap_max; int epi_n;
     void* d_geo; int geo_box[4];   // polar geometry cache (radial / circle), see kernels.cu
     // state + outputs
     float* d_spec; float* d_applied; float* d_ring_f;
@@ -282,7 +282,9 @@ static int build(glava_b200* r) {
                 });
                 wsum[e] = weight; tcnt[e] = (int) v.size();
                 if (v.size() > tap_max) tap_max = v.size();
+                for (const TapEntry& te : v) if (te.idx >= 0 && te.idx < p.n && te.idx + 1 > r->epi_n) r->epi_n = te.idx + 1;
             }
+            if (getenv("GLAVA_B200_NO_EPI_PRUNE")) r->epi_n = 0;
             const size_t tab_elems = 2 * tap_max * cnt;
             if (tab_elems * sizeof(TapEntry) <= (size_t) 64 << 20 && !getenv("GLAVA_B200_NO_TAPTAB")) {
                 std::vector<TapEntry> tab(tab_elems, TapEntry { -1, 0.0f });
@@ -332,7 +334,7 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     r->stream = nullptr; r->spec_stream = nullptr; r->tex_cur = 0; r->ring_cur = 0;
     for (int i = 0; i < 2; ++i) { r->ev_spec_done[i] = nullptr; r->ev_raster_done[i] = nullptr; } r->d_chunks = nullptr; r->chunks_cap = 0;
     r->d_window = nullptr; r->d_twiddle = nullptr; r->d_rowtab = nullptr; r->d_need = nullptr; r->need_count = 0;
-    r->d_tap_tab = nullptr; r->d_tap_cnt = nullptr; r->d_tap_wsum = nullptr; r->tap_max = 0;
+    r->d_tap_tab = nullptr; r->d_tap_cnt = nullptr; r->d_tap_wsum = nullptr; r->tap_max = 0; r->epi_n = 0;
     r->d_geo = nullptr; r->geo_box[0] = r->geo_box[1] = r->geo_box[2] = r->geo_box[3] = 0;
     r->d_spec = r->d_applied = r->d_ring_f = nullptr; r->d_gr_store = r->d_ring_u = r->d_tex = nullptr; r->d_fb = nullptr;
     for (int i = 0; i < 2; ++i) { r->d_pcm[i][0] = r->d_pcm[i][1] = nullptr; r->ev_copied[i] = r->ev_free[i] = nullptr; }
@@ -403,6 +405,7 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
         a.gr_store = r->d_gr_store; a.ring_u = r->d_ring_u; a.tex = tex_half(r, b);
         a.need = (p.lazy_smooth && r->d_need) ? r->d_need : nullptr; a.need_count = r->need_count;
         a.tap_tab = a.need ? r->d_tap_tab : nullptr; a.tap_cnt = r->d_tap_cnt; a.tap_wsum = r->d_tap_wsum; a.tap_max = r->tap_max;
+        a.epi_n = a.need ? r->epi_n : 0;
         a.batch = r->batch; a.update = r->updates;
         const int F = p.avg_frames;
         for (int f = 0; f < F; ++f) {

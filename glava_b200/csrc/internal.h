@@ -48,6 +48,7 @@ struct SpectrumArgs {
     const int*   tap_cnt;       // [2][need_count]
     const float* tap_wsum;      // [2][need_count]  sum of the weights in loop order
     int       tap_max;
+    int       epi_n;            // lazy K5: number of leading bins whose gravity/average state can reach a sampled texel (0 = all)
     int       batch;
     unsigned long long update;  // number of modified updates before this one (ring cursor)
     double    avg_w_a[GLB_MAX_AVG_FRAMES];   // pipeline A weights, oldest first (render.c:661,766)

@@ -110,7 +110,7 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
         // u16, HBM-resident) towards L2, so the epilogue's loads after the FFT are L2 hits
         const char* g0 = reinterpret_cast<const char*>(a.gr_store + plane);
         const char* r0 = reinterpret_cast<const char*>(a.ring_u + plane * F);
-        const int lines_g = (N * 2) / 128, lines_r = (N * 2 * F) / 128;
+        const int lines_g = (N * 2) / 128, lines_r = (N * 2 * F) / 128;   // (whole planes: cheap, and epi_n varies)
         for (int i = tid; i < lines_g + lines_r; i += T) {
             const char* ptr = i < lines_g ? g0 + (size_t) i * 128 : r0 + (size_t) (i - lines_g) * 128;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
@@ -154,6 +154,7 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
             // --- pipeline B: render.c:2177-2267 ---------------------------------------------------
             const float diff = p.gravity_step * (1.0f / p.ur);
             const int out_idx = (int) (a.update % (unsigned long long) F);
+            const int epi_n = (a.epi_n > 0 && a.epi_n < N) ? ((a.epi_n + T - 1) / T) * T : N;
             float*    const spec = a.spec + plane;
             uint16_t* const grs  = a.gr_store + plane;
             uint16_t* const ring = a.ring_u + plane * F;
@@ -175,11 +176,14 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
                     // first dependent use, so the global-load latency is paid once per trip, not per element
                     constexpr int U = (N / T) % 4 == 0 ? 4 : ((N / T) % 2 == 0 ? 2 : 1);
                     static_assert((N / T) % U == 0, "N / T must be a multiple of the epilogue unroll");
-                    for (int n0 = tid; n0 < N; n0 += U * T) {
+                    // epi_n (multiple of T): with lazy K5 only the leading bins that some sampled texel's
+                    // taps can reach are post-processed (their state is all that can influence a pixel)
+                    for (int n0 = tid; n0 < epi_n; n0 += U * T) {
                         uint32_t g_old[U], rg[U][FT];
 #pragma unroll
                         for (int e = 0; e < U; ++e) {
                             const int n = n0 + e * T;
+                            if (n >= epi_n) continue;
                             g_old[e] = grs[n];
 #pragma unroll
                             for (int i = 1; i < FT; ++i) rg[e][i] = ring[off[i] + n];
@@ -187,6 +191,7 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
 #pragma unroll
                         for (int e = 0; e < U; ++e) {
                             const int n = n0 + e * T;
+                            if (n >= epi_n) continue;
                             cpx z = buf[fft_pad(n >> 1)];
                             float v = fft_post((n & 1) ? z.y : z.x, n, N, p.fft_scale, p.fft_cutoff);
                             spec[n] = v;
@@ -207,7 +212,7 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
                         }
                     }
                 } else {
-                    for (int n = tid; n < N; n += T) {                 // any F: runtime loop
+                    for (int n = tid; n < epi_n; n += T) {             // any F: runtime loop
                         cpx z = buf[fft_pad(n >> 1)];
                         float v = fft_post((n & 1) ? z.y : z.x, n, N, p.fft_scale, p.fft_cutoff);
                         spec[n] = v;
