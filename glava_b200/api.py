@@ -76,6 +76,8 @@ def lib():
     L.glava_b200_version.restype = cp
     L.glava_b200_default_params.argtypes = [C.POINTER(Params), cp]
     L.glava_b200_load_config.argtypes = [C.POINTER(Params), C.POINTER(cp), cp, C.POINTER(cp), cp]
+    L.glava_b200_load_config_binds.argtypes = [C.POINTER(Params), C.POINTER(cp), cp, C.POINTER(cp), cp, C.POINTER(cp)]
+    L.glava_b200_reconfigure.argtypes = [vp, C.POINTER(Params)]
     L.glava_b200_new.restype = vp
     L.glava_b200_new.argtypes = [C.POINTER(Params), i32, i32]
     L.glava_b200_destroy.argtypes = [vp]
@@ -137,12 +139,15 @@ def _cstr_array(items):
     return arr
 
 
-def load_config(paths=None, entry="rc.glsl", requests=None, force_module=None):
+def load_config(paths=None, entry="rc.glsl", requests=None, force_module=None, binds=None):
     """rd_new's config half (render.c:1322-1435): read `entry` from the first of `paths`, apply
-    `#request`s and `requests` (CLI --request strings), then the module's `#define`s."""
+    `#request`s and `requests` (CLI --request strings), then the module's `#define`s.
+    binds: {"fg": "#ff0000", ...} — `--pipe` binds resolving `@name:default` macros."""
     p = Params()
-    _check(lib().glava_b200_load_config(C.byref(p), _cstr_array(paths), entry.encode() if entry else None,
-                                        _cstr_array(requests), force_module.encode() if force_module else None))
+    bl = [f"{k}={v}" for k, v in binds.items()] if binds else None
+    _check(lib().glava_b200_load_config_binds(C.byref(p), _cstr_array(paths), entry.encode() if entry else None,
+                                              _cstr_array(requests), force_module.encode() if force_module else None,
+                                              _cstr_array(bl)))
     return p
 
 
@@ -185,6 +190,11 @@ class Renderer:
             assert rb.shape == lb.shape
             rp = rb.ctypes.data
         _check(self._L.glava_b200_update(self._h, lb.ctypes.data, rp, self.params.n, 1 if modified else 0))
+
+    def reconfigure(self, params):
+        """live parameter update (colours, amplify, smoothing...): the `--pipe` analogue"""
+        _check(self._L.glava_b200_reconfigure(self._h, C.byref(params)))
+        _check(self._L.glava_b200_get_params(self._h, C.byref(self.params)))
 
     def update_device(self, d_lb, d_rb, modified=True):
         """d_lb, d_rb: integer device addresses of [batch][n] float32 (e.g. torch tensor.data_ptr())."""

@@ -106,7 +106,13 @@ int glava_b200_default_params(glava_b200_params* out, const char* module) {
 int glava_b200_load_config(glava_b200_params* out, const char* const* paths, const char* entry,
                            const char* const* requests, const char* force_module) {
     if (!out) return fail(GLAVA_B200_EINVAL, "null argument");
-    return load_config(out, paths, entry, requests, force_module);
+    return load_config(out, paths, entry, requests, force_module, nullptr);
+}
+
+int glava_b200_load_config_binds(glava_b200_params* out, const char* const* paths, const char* entry,
+                                 const char* const* requests, const char* force_module, const char* const* binds) {
+    if (!out) return fail(GLAVA_B200_EINVAL, "null argument");
+    return load_config(out, paths, entry, requests, force_module, binds);
 }
 
 void* glava_b200_host_alloc(size_t bytes) {
@@ -164,6 +170,88 @@ static bool build_need_list(const glava_b200_params& p, std::vector<int>* lists 
         for (int i = 0; i < p.n; ++i) if (mark[c][i]) lists[c].push_back(i);
     }
     return true;
+}
+
+static void dev_free(glava_b200* r, void* ptr) {
+    if (!ptr) return;
+    for (size_t i = 0; i < r->allocs.size(); ++i) if (r->allocs[i] == ptr) { r->allocs.erase(r->allocs.begin() + i); break; }
+    cudaFree(ptr);
+}
+
+// Everything derived from the parameters that does not depend on the audio: the lazy-K5 need-list and tap
+// table, the bars / graph row-colour table, the polar geometry cache.  Called at creation and again by
+// glava_b200_reconfigure (the analogue of a `--pipe` uniform update, render.c:1846-2005).
+static int build_tables(glava_b200* r) {
+    const glava_b200_params& p = r->p;
+    int rc;
+    dev_free(r, r->d_need); dev_free(r, r->d_tap_tab); dev_free(r, r->d_tap_cnt); dev_free(r, r->d_tap_wsum); dev_free(r, r->d_geo);
+    r->d_need = nullptr; r->need_count = 0; r->d_tap_tab = nullptr; r->d_tap_cnt = nullptr; r->d_tap_wsum = nullptr;
+    r->tap_max = 0; r->epi_n = 0; r->d_geo = nullptr; r->geo_box[0] = r->geo_box[1] = r->geo_box[2] = r->geo_box[3] = 0;
+    if (p.lazy_smooth) {
+        std::vector<int> lists[2];
+        if (build_need_list(p, lists)) {
+            size_t cnt = lists[0].size() > lists[1].size() ? lists[0].size() : lists[1].size();
+            if (cnt == 0) cnt = 1;
+            std::vector<int> flat(2 * cnt, -1);
+            for (int c = 0; c < 2; ++c) for (size_t i = 0; i < lists[c].size(); ++i) flat[c * cnt + i] = lists[c][i];
+            if ((rc = dev_alloc(r, (void**) &r->d_need, flat.size() * sizeof(int), false)) != 0) return rc;
+            CU(cudaMemcpyAsync(r->d_need, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, r->stream));
+            CU(cudaStreamSynchronize(r->stream));
+            r->need_count = (int) cnt;
+            // K5 tap table: indices and weights of smooth_audio() for every needed texel.  They are a
+            // function of the parameters only, and gl_math.h evaluates bit-identically on host and
+            // device, so the table is built here once with the very code the kernel would run.
+            const SmoothParams sp = smooth_params(p);
+            std::vector<std::vector<TapEntry>> taps(2 * cnt);
+            std::vector<float> wsum(2 * cnt, 0.0f);
+            std::vector<int> tcnt(2 * cnt, 0);
+            size_t tap_max = 1;
+            for (size_t e = 0; e < 2 * cnt; ++e) {
+                const int x = flat[e];
+                if (x < 0) continue;
+                float weight = 0.0f;
+                std::vector<TapEntry>& v = taps[e];
+                smooth_enumerate(sp, p.n, ((float) x + 0.5f) / (float) p.n, [&](int i, float w) {
+                    weight += w;
+                    v.push_back(TapEntry { i, w });
+                });
+                wsum[e] = weight; tcnt[e] = (int) v.size();
+                if (v.size() > tap_max) tap_max = v.size();
+                for (const TapEntry& te : v) if (te.idx >= 0 && te.idx < p.n && te.idx + 1 > r->epi_n) r->epi_n = te.idx + 1;
+            }
+            if (getenv("GLAVA_B200_NO_EPI_PRUNE")) r->epi_n = 0;
+            const size_t tab_elems = 2 * tap_max * cnt;
+            if (tab_elems * sizeof(TapEntry) <= (size_t) 64 << 20 && !getenv("GLAVA_B200_NO_TAPTAB")) {
+                std::vector<TapEntry> tab(tab_elems, TapEntry { -1, 0.0f });
+                for (size_t c = 0; c < 2; ++c)
+                    for (size_t k = 0; k < cnt; ++k) {
+                        const std::vector<TapEntry>& v = taps[c * cnt + k];
+                        for (size_t j = 0; j < v.size(); ++j) tab[(c * tap_max + j) * cnt + k] = v[j];
+                    }
+                if ((rc = dev_alloc(r, (void**) &r->d_tap_tab, tab.size() * sizeof(TapEntry), false)) != 0) return rc;
+                if ((rc = dev_alloc(r, (void**) &r->d_tap_cnt, tcnt.size() * sizeof(int), false)) != 0) return rc;
+                if ((rc = dev_alloc(r, (void**) &r->d_tap_wsum, wsum.size() * sizeof(float), false)) != 0) return rc;
+                CU(cudaMemcpyAsync(r->d_tap_tab, tab.data(), tab.size() * sizeof(TapEntry), cudaMemcpyHostToDevice, r->stream));
+                CU(cudaMemcpyAsync(r->d_tap_cnt, tcnt.data(), tcnt.size() * sizeof(int), cudaMemcpyHostToDevice, r->stream));
+                CU(cudaMemcpyAsync(r->d_tap_wsum, wsum.data(), wsum.size() * sizeof(float), cudaMemcpyHostToDevice, r->stream));
+                CU(cudaStreamSynchronize(r->stream));
+                r->tap_max = (int) tap_max;
+            }
+        }
+    }
+    if (p.module == GLAVA_B200_MOD_BARS || p.module == GLAVA_B200_MOD_GRAPH) { if ((rc = launch_bars_rowtab(p, r->d_rowtab, r->stream)) != 0) return rc; ++r->launches; }
+    // polar modules: cache the audio-independent per-pixel geometry (circle: only when the module samples a
+    // pre-smoothed texture, i.e. smooth_audio() is a single texelFetch)
+    if (p.module == GLAVA_B200_MOD_RADIAL || (p.module == GLAVA_B200_MOD_CIRCLE && p.smooth_pass)) {
+        const size_t bytes = polar_geo_box(p, r->geo_box);
+        if (bytes > 0 && bytes <= ((size_t) 512 << 20) && !getenv("GLAVA_B200_NO_GEO")) {
+            if ((rc = dev_alloc(r, &r->d_geo, bytes, false)) != 0) return rc;
+            if ((rc = launch_polar_geo(p, r->d_geo, r->geo_box, r->stream)) != 0) return rc;
+            ++r->launches;
+        }
+    }
+    CU(cudaStreamSynchronize(r->stream));
+    return 0;
 }
 
 static int build(glava_b200* r) {
@@ -252,69 +340,7 @@ static int build(glava_b200* r) {
     }
     CU(cudaMemcpyAsync(r->d_twiddle, tw.data(), n * 4, cudaMemcpyHostToDevice, r->stream));
     CU(cudaStreamSynchronize(r->stream));
-    if (p.lazy_smooth) {
-        std::vector<int> lists[2];
-        if (build_need_list(p, lists)) {
-            size_t cnt = lists[0].size() > lists[1].size() ? lists[0].size() : lists[1].size();
-            if (cnt == 0) cnt = 1;
-            std::vector<int> flat(2 * cnt, -1);
-            for (int c = 0; c < 2; ++c) for (size_t i = 0; i < lists[c].size(); ++i) flat[c * cnt + i] = lists[c][i];
-            if ((rc = dev_alloc(r, (void**) &r->d_need, flat.size() * sizeof(int), false)) != 0) return rc;
-            CU(cudaMemcpyAsync(r->d_need, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, r->stream));
-            CU(cudaStreamSynchronize(r->stream));
-            r->need_count = (int) cnt;
-            // K5 tap table: indices and weights of smooth_audio() for every needed texel.  They are a
-            // function of the parameters only, and gl_math.h evaluates bit-identically on host and
-            // device, so the table is built here once with the very code the kernel would run.
-            const SmoothParams sp = smooth_params(p);
-            std::vector<std::vector<TapEntry>> taps(2 * cnt);
-            std::vector<float> wsum(2 * cnt, 0.0f);
-            std::vector<int> tcnt(2 * cnt, 0);
-            size_t tap_max = 1;
-            for (size_t e = 0; e < 2 * cnt; ++e) {
-                const int x = flat[e];
-                if (x < 0) continue;
-                float weight = 0.0f;
-                std::vector<TapEntry>& v = taps[e];
-                smooth_enumerate(sp, p.n, ((float) x + 0.5f) / (float) p.n, [&](int i, float w) {
-                    weight += w;
-                    v.push_back(TapEntry { i, w });
-                });
-                wsum[e] = weight; tcnt[e] = (int) v.size();
-                if (v.size() > tap_max) tap_max = v.size();
-                for (const TapEntry& te : v) if (te.idx >= 0 && te.idx < p.n && te.idx + 1 > r->epi_n) r->epi_n = te.idx + 1;
-            }
-            if (getenv("GLAVA_B200_NO_EPI_PRUNE")) r->epi_n = 0;
-            const size_t tab_elems = 2 * tap_max * cnt;
-            if (tab_elems * sizeof(TapEntry) <= (size_t) 64 << 20 && !getenv("GLAVA_B200_NO_TAPTAB")) {
-                std::vector<TapEntry> tab(tab_elems, TapEntry { -1, 0.0f });
-                for (size_t c = 0; c < 2; ++c)
-                    for (size_t k = 0; k < cnt; ++k) {
-                        const std::vector<TapEntry>& v = taps[c * cnt + k];
-                        for (size_t j = 0; j < v.size(); ++j) tab[(c * tap_max + j) * cnt + k] = v[j];
-                    }
-                if ((rc = dev_alloc(r, (void**) &r->d_tap_tab, tab.size() * sizeof(TapEntry), false)) != 0) return rc;
-                if ((rc = dev_alloc(r, (void**) &r->d_tap_cnt, tcnt.size() * sizeof(int), false)) != 0) return rc;
-                if ((rc = dev_alloc(r, (void**) &r->d_tap_wsum, wsum.size() * sizeof(float), false)) != 0) return rc;
-                CU(cudaMemcpyAsync(r->d_tap_tab, tab.data(), tab.size() * sizeof(TapEntry), cudaMemcpyHostToDevice, r->stream));
-                CU(cudaMemcpyAsync(r->d_tap_cnt, tcnt.data(), tcnt.size() * sizeof(int), cudaMemcpyHostToDevice, r->stream));
-                CU(cudaMemcpyAsync(r->d_tap_wsum, wsum.data(), wsum.size() * sizeof(float), cudaMemcpyHostToDevice, r->stream));
-                CU(cudaStreamSynchronize(r->stream));
-                r->tap_max = (int) tap_max;
-            }
-        }
-    }
-    if (p.module == GLAVA_B200_MOD_BARS || p.module == GLAVA_B200_MOD_GRAPH) { if ((rc = launch_bars_rowtab(p, r->d_rowtab, r->stream)) != 0) return rc; ++r->launches; }
-    // polar modules: cache the audio-independent per-pixel geometry (circle: only when the module samples a
-    // pre-smoothed texture, i.e. smooth_audio() is a single texelFetch)
-    if (p.module == GLAVA_B200_MOD_RADIAL || (p.module == GLAVA_B200_MOD_CIRCLE && p.smooth_pass)) {
-        const size_t bytes = polar_geo_box(p, r->geo_box);
-        if (bytes > 0 && bytes <= ((size_t) 512 << 20) && !getenv("GLAVA_B200_NO_GEO")) {
-            if ((rc = dev_alloc(r, &r->d_geo, bytes, false)) != 0) return rc;
-            if ((rc = launch_polar_geo(p, r->d_geo, r->geo_box, r->stream)) != 0) return rc;
-            ++r->launches;
-        }
-    }
+    if ((rc = build_tables(r)) != 0) return rc;
     CU(cudaStreamSynchronize(r->stream));
     return 0;
 }
@@ -359,6 +385,23 @@ void glava_b200_destroy(glava_b200* r) {
     if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
     if (r->stream) cudaStreamDestroy(r->stream);
     delete r;
+}
+
+int glava_b200_reconfigure(glava_b200* r, const glava_b200_params* params) {
+    clear_error();
+    if (!r || !params) return fail(GLAVA_B200_EINVAL, "glava_b200_reconfigure: null argument");
+    int rc = validate_params(params);
+    if (rc) return rc;
+    const glava_b200_params& o = r->p;
+    if (params->n != o.n || params->w != o.w || params->h != o.h || params->module != o.module || params->accel_fft != o.accel_fft ||
+        params->avg_frames != o.avg_frames || params->fb_slots != o.fb_slots)
+        return fail(GLAVA_B200_EINVAL, "glava_b200_reconfigure: setbufsize, geometry, module, setaccelfft, setavgframes and fb_slots "
+                                       "size the device state and cannot change on a live renderer; create a new one");
+    CU(cudaSetDevice(r->device));
+    CU(cudaStreamSynchronize(r->spec_stream));
+    CU(cudaStreamSynchronize(r->stream));
+    r->p = *params;
+    return build_tables(r);
 }
 
 int glava_b200_get_params(const glava_b200* r, glava_b200_params* out) {

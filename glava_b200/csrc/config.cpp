@@ -162,6 +162,13 @@ struct ExprParser {
 
 typedef std::map<std::string, std::string> Defs;
 
+static std::string trim_copy(const std::string& s) {
+    size_t a = 0, b = s.size();
+    while (a < b && isspace((unsigned char) s[a])) ++a;
+    while (b > a && isspace((unsigned char) s[b - 1])) --b;
+    return s.substr(a, b - a);
+}
+
 static bool eval_num(const Defs& d, const char* name, Num* out) {
     auto it = d.find(name);
     if (it == d.end()) return false;
@@ -177,11 +184,25 @@ static void getf(const Defs& d, const char* name, float* dst) { Num n; if (eval_
 static void geti(const Defs& d, const char* name, int* dst) { Num n; if (eval_num(d, name, &n)) *dst = (int) n.v; }
 
 // strip `@name:` pipe-bind prefix -> its default (glsl_ext.c:571-587 when no --pipe bind exists)
+// `--pipe` binds (glava.c:421-436, glsl_ext.c:516-591): "name" -> value the bound uniform currently holds.
+// A macro written `@name:default` takes the bound value when `name` is bound, else `default`.
+static thread_local const std::map<std::string, std::string>* g_binds = nullptr;
+
 static std::string strip_bind(const std::string& v) {
     size_t i = 0; while (i < v.size() && isspace((unsigned char) v[i])) ++i;
     if (i < v.size() && v[i] == '@') {
         size_t c = v.find(':', i);
-        if (c != std::string::npos) return v.substr(c + 1);
+        if (c != std::string::npos) {
+            if (g_binds) {
+                auto it = g_binds->find(v.substr(i + 1, c - i - 1));
+                if (it != g_binds->end()) return it->second;
+            }
+            return v.substr(c + 1);
+        }
+        if (g_binds) {                                   // `@name` without a default (glsl_ext.c:571-587)
+            auto it = g_binds->find(trim_copy(v.substr(i + 1)));
+            if (it != g_binds->end()) return it->second;
+        }
     }
     return v.substr(i);
 }
@@ -475,8 +496,16 @@ static void apply_defines(glava_b200_params* p, const Defs& d) {
 }
 
 int load_config(glava_b200_params* out, const char* const* paths, const char* entry,
-                const char* const* requests, const char* force_module) {
+                const char* const* requests, const char* force_module, const char* const* binds) {
     clear_error();
+    std::map<std::string, std::string> bind_map;
+    if (binds) for (int i = 0; binds[i]; ++i) {           // "name=value" (value: #rrggbb[aa] or vec4(...))
+        std::string b = binds[i];
+        size_t eq = b.find('=');
+        if (eq == std::string::npos) { fail(GLAVA_B200_ECONFIG, "bind '%s': expected name=value", binds[i]); return GLAVA_B200_ECONFIG; }
+        bind_map[trim_copy(b.substr(0, eq))] = trim_copy(b.substr(eq + 1));
+    }
+    struct BindScope { BindScope(const std::map<std::string, std::string>* m) { g_binds = m; } ~BindScope() { g_binds = nullptr; } } scope(&bind_map);
     fill_defaults(out, GLAVA_B200_MOD_BARS);
     Loader L { out, "bars", false, false };
     if (force_module) { L.module = force_module; L.module_forced = true; }

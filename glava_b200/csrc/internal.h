@@ -20,7 +20,7 @@ int  module_from_name(const char* name);
 const char* module_name(int id);
 bool parse_hex_color(const char* s, float out[4], bool literal_rounding);
 int  load_config(glava_b200_params* out, const char* const* paths, const char* entry,
-                 const char* const* requests, const char* force_module);
+                 const char* const* requests, const char* force_module, const char* const* binds);
 int  validate_params(const glava_b200_params* p);
 
 #define GLB_MAX_AVG_FRAMES 16

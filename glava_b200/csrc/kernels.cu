@@ -316,14 +316,17 @@ static int launch_spectrum_t(const glava_b200_params& p, const SpectrumArgs& a, 
         smem_req = C::SMEM;
         if (cap > 0) { int want = (227 * 1024) / cap - 1024; if (want > smem_req) smem_req = want; }
         if (smem_req > 227 * 1024) smem_req = 227 * 1024;
+    }
+    if (smem_req > 48 * 1024) {
+        // per-device function attribute: set on every launch (handles on several devices may live in one process)
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req);
         if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "cudaFuncSetAttribute(spectrum): %s", cudaGetErrorString(e));
     }
     // Persistent grid: a few CTAs per SM.  Small on purpose — this kernel is latency bound and is meant
     // to run UNDER the HBM-bound raster kernel of the previous update (capi.cu run_update) without taking
     // its occupancy away.  GLAVA_B200_SPEC_CTAS_PER_SM overrides (0 = one CTA per work unit).
-    static int sm_count = 0;
-    if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); if (sm_count <= 0) sm_count = 148; }
+    int sm_count = 148;
+    { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); if (sm_count <= 0) sm_count = 148; }
     int per_sm = 0;                                  // measured on B200: 0 (one CTA per unit) >= 4 > 3 > 2 > 1 for whole-step throughput
     if (const char* e = getenv("GLAVA_B200_SPEC_CTAS_PER_SM")) per_sm = atoi(e);
     const int units = IS_FFT ? a.batch * 2 : a.batch;

@@ -115,12 +115,21 @@ int glava_b200_default_params(glava_b200_params* out, const char* module);
 int glava_b200_load_config(glava_b200_params* out, const char* const* paths, const char* entry,
                            const char* const* requests, const char* force_module);
 
+/* Same, with `--pipe` binds (glava.c:421-436): NULL-terminated "name=value" strings; a config macro written
+ * `@name:default` (glsl_ext.c:516-591) takes `value` (#rrggbb[aa] or vec4(...)) when `name` is bound. */
+int glava_b200_load_config_binds(glava_b200_params* out, const char* const* paths, const char* entry,
+                                 const char* const* requests, const char* force_module, const char* const* binds);
+
 /* rd_new (render.h:53-57): build a renderer for `batch` independent streams on CUDA device
  * `device` with the given parameters (from glava_b200_load_config / _default_params). */
 glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int device);
 /* rd_destroy (render.h:60) */
 void glava_b200_destroy(glava_b200* r);
 
+/* Live parameter update — the analogue of a `--pipe` uniform write (render.c:1846-2005): colours, AMPLIFY,
+ * gradient, smoothing parameters ... take effect from the next update.  Everything that sizes device state
+ * (setbufsize, geometry, module, setaccelfft, setavgframes, fb_slots) must be unchanged. */
+int  glava_b200_reconfigure(glava_b200* r, const glava_b200_params* params);
 int  glava_b200_get_params(const glava_b200* r, glava_b200_params* out);
 int  glava_b200_batch(const glava_b200* r);
 const char* glava_b200_module_name(const glava_b200* r);

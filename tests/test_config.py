@@ -116,3 +116,23 @@ def test_unsupported_colour_expression(tmp_path, built):
     (tmp_path / "bars.glsl").write_text("#define COLOR vec4(sin(d), 0, 0, 1)\n")
     with pytest.raises(g.GlavaError, match="unsupported colour expression"):
         g.load_config([str(tmp_path)])
+
+
+def test_pipe_binds_resolve_at_macros(tmp_path, built):
+    """`@name:default` (glsl_ext.c:516-591): bound value when `--pipe` bound the name, else the default"""
+    (tmp_path / "rc.glsl").write_text("#request mod bars\n")
+    (tmp_path / "bars.glsl").write_text("#define GRADIENT 80\n#define COLOR @fg:mix(#3366b2, #a0a0b2, clamp(d / GRADIENT, 0, 1))\n"
+                                        "#define BAR_OUTLINE @bg:vec4(COLOR.rgb * 1.5, COLOR.a)\n")
+    p = g.load_config([str(tmp_path)])
+    assert p.bars_color.mode == 0 and p.bars_outline_mode == 0
+    q = g.load_config([str(tmp_path)], binds={"fg": "#ff8000", "bg": "vec4(0.1, 0.2, 0.3, 1.0)"})
+    assert q.bars_color.mode == 1 and list(q.bars_color.lo)[:3] == [1.0, np.float32(0.501961), 0.0]
+    assert q.bars_outline_mode == 1 and list(q.bars_outline) == [np.float32(0.1), np.float32(0.2), np.float32(0.3), 1.0]
+    with pytest.raises(g.GlavaError, match="name=value"):
+        g.lib().glava_b200_load_config_binds  # symbol exists
+        import ctypes as C
+        arr = (C.c_char_p * 2)(b"novalue", None)
+        pp = g.Params()
+        rc = g.lib().glava_b200_load_config_binds(C.byref(pp), None, None, None, None, arr)
+        if rc != 0:
+            raise g.GlavaError(g.lib().glava_b200_last_error().decode())

@@ -144,3 +144,29 @@ def test_tap_table_equals_direct_k5(built, monkeypatch):
             out.append([r.readback(s) for s in range(batch)])
     for s in range(batch):
         assert np.array_equal(out[0][s], out[1][s])
+
+
+def test_reconfigure_is_a_live_uniform_update(orc_pm, built):
+    """glava_b200_reconfigure: colour / amplify change on a live renderer == a fresh renderer with those parameters"""
+    n = 1024
+    for module, change in (("bars", dict(bars_amplify=120.0)), ("radial", dict(radial_amplify=200.0)), ("graph", dict(graph_vscale=150.0))):
+        p = g.default_params(module, n=n, w=320, h=240, lazy_smooth=1); op = params_from(p)
+        tl, tr = _textures(orc_pm, op, n, 2, 33)
+        with g.Renderer(p, batch=2) as r:
+            r.raster_textures(tl, tr)
+            assert np.array_equal(r.readback(0), orc_pm.raster(op, tl[0], tr[0]))
+            q = p.copy()
+            for k, v in change.items():
+                setattr(q, k, v)
+            if module == "bars":
+                q.bars_color.mode = 1
+                for i, c in enumerate((0.9, 0.2, 0.1, 1.0)):
+                    q.bars_color.lo[i] = c
+            r.reconfigure(q)
+            r.raster_textures(tl, tr)
+            oq = params_from(q)
+            for s in range(2):
+                assert np.array_equal(r.readback(s), orc_pm.raster(oq, tl[s], tr[s])), (module, s)
+            bad = q.copy(); bad.w = 640
+            with pytest.raises(g.GlavaError, match="cannot change on a live renderer"):
+                r.reconfigure(bad)
