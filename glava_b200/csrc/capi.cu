@@ -68,6 +68,7 @@ struct glava_b200 {
     // state + outputs
     float* d_spec; float* d_applied; float* d_ring_f;
     uint16_t* d_gr_store; uint16_t* d_ring_u; uint16_t* d_tex;
+    uint16_t* d_av;             // pre-smoothing textures [batch*2][n] (full-plane K5 runs as its own kernel)
     uint8_t* d_fb;
     unsigned long long updates;
     uint64_t launches;
@@ -320,7 +321,8 @@ static int build(glava_b200* r) {
             if (cudaStreamSetAttribute(r->spec_stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
         }
     }
-    ALLOC(r->d_tex, 2 * planes * n * 2, true);          // double-buffered: spectrum i+1 writes one half while raster i reads the other
+    ALLOC(r->d_tex, 2 * planes * n * 2, true);
+    ALLOC(r->d_av, planes * n * 2, true);          // double-buffered: spectrum i+1 writes one half while raster i reads the other
     ALLOC(r->d_rowtab, (size_t) p.h * 8, true);
     // framebuffers: [slots][h][w] RGBA8
     size_t frame = (size_t) p.w * p.h * 4;
@@ -362,7 +364,7 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     r->d_window = nullptr; r->d_twiddle = nullptr; r->d_rowtab = nullptr; r->d_need = nullptr; r->need_count = 0;
     r->d_tap_tab = nullptr; r->d_tap_cnt = nullptr; r->d_tap_wsum = nullptr; r->tap_max = 0; r->epi_n = 0;
     r->d_geo = nullptr; r->geo_box[0] = r->geo_box[1] = r->geo_box[2] = r->geo_box[3] = 0;
-    r->d_spec = r->d_applied = r->d_ring_f = nullptr; r->d_gr_store = r->d_ring_u = r->d_tex = nullptr; r->d_fb = nullptr;
+    r->d_spec = r->d_applied = r->d_ring_f = nullptr; r->d_gr_store = r->d_ring_u = r->d_tex = nullptr; r->d_av = nullptr; r->d_fb = nullptr;
     for (int i = 0; i < 2; ++i) { r->d_pcm[i][0] = r->d_pcm[i][1] = nullptr; r->ev_copied[i] = r->ev_free[i] = nullptr; }
     r->stage_cur = 0; r->copy_stream = nullptr;
     r->updates = 0; r->launches = 0; r->timing = false;
@@ -460,7 +462,16 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
         a.avg_b_windowed = (p.avg_window && F != 2) ? 1 : 0;
         const bool is_fft = p.module != GLAVA_B200_MOD_WAVE;
         if (r->timing && (rc = timing_mark(r->ev_spec, r->spec_stream)) != 0) return rc;
+        // full-plane smoothing (every texel wanted): the spectrum kernel exports the pre-smoothing texture and
+        // a second kernel smooths all planes, sharing the tap weights between planes
+        const bool split_k5 = p.smooth_pass && !a.need && !getenv("GLAVA_B200_FUSED_K5");
+        a.av_out = split_k5 ? r->d_av : nullptr;
         if ((rc = launch_spectrum(p, a, is_fft, r->spec_stream)) != 0) return rc;
+        if (split_k5) {
+            // wave uses plane 0 of each stream only; smoothing the (zero) odd planes too keeps the launch simple
+            if ((rc = launch_smooth_only(p, r->d_av, a.tex, r->batch * 2, r->spec_stream)) != 0) return rc;
+            ++r->launches;
+        }
         if (r->timing && (rc = timing_mark(r->ev_spec, r->spec_stream)) != 0) return rc;
         CU(cudaEventRecord(r->ev_spec_done[b], r->spec_stream));
         r->tex_cur = b;

@@ -41,6 +41,7 @@ struct SpectrumArgs {
     uint16_t* gr_store;         // [batch*2][n] (B) render.c:2197
     uint16_t* ring_u;           // [batch*2][F][n] (B) gr->out[], render.c:2232
     uint16_t* tex;              // [batch*2][n] R16 texture the module samples
+    uint16_t* av_out;           // non-null: export the pre-smoothing texture here and skip K5 (k5_planes_kernel follows)
     const int* need;            // lazy K5: texel indices to evaluate, [2][need_count] (-1 = unused), nullptr = all n
     int       need_count;
     // precomputed K5 taps for the need-list (weights and indices do not depend on the audio):

@@ -281,6 +281,11 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
                 int x = need[k];
                 if (x >= 0 && x < N) tex[x] = (uint16_t) smooth_pass_texel(sp, av, N, x);
             }
+        } else if (a.av_out) {
+            // all n texels wanted: export the pre-smoothing texture; k5_planes_kernel (below) smooths it,
+            // sharing every tap weight between several planes instead of recomputing it per plane
+            uint16_t* dst = a.av_out + plane;
+            for (int x = tid; x < N; x += T) dst[x] = av[x];
         } else {
             for (int x = tid; x < N; x += T) tex[x] = (uint16_t) smooth_pass_texel(sp, av, N, x);
         }
@@ -347,19 +352,73 @@ int launch_spectrum(const glava_b200_params& p, const SpectrumArgs& a, bool is_f
 #undef GLB_CASE
 }
 
-// K5 alone (stage-wise entry point): count planes of n texels
-__global__ void smooth_only_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int n,
-                                   const __grid_constant__ glava_b200_params p) {
-    uint16_t* av = reinterpret_cast<uint16_t*>(glb_smem);
-    const uint16_t* src = in + (size_t) blockIdx.x * n;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) av[i] = src[i];
-    __syncthreads();
+// K5 for whole planes (all n output texels): util/smooth_pass.frag over `count` R16 planes.
+// The tap indices and weights of an output texel depend on the parameters only, so one thread computes
+// them once (the expensive part: log, divide, sine) and applies them to K5_S planes held in shared
+// memory; per plane and tap only a fetch, a multiply and an add remain.  Per-plane arithmetic and
+// summation order are exactly smooth_audio()'s.
+#define K5_S  8
+#define K5_XT 128
+__global__ void __launch_bounds__(K5_XT)
+k5_planes_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int n, int count,
+                 const __grid_constant__ glava_b200_params p) {
+    uint16_t* seg = reinterpret_cast<uint16_t*>(glb_smem);           // [K5_S][span]
     const SmoothParams sp = smooth_params(p);
-    for (int x = threadIdx.x; x < n; x += blockDim.x)
-        out[(size_t) blockIdx.x * n + x] = (uint16_t) smooth_pass_texel(sp, av, n, x);
+    const int x0 = blockIdx.x * K5_XT, x1 = min(n, x0 + K5_XT);
+    const int pl0 = blockIdx.y * K5_S, npl = min(K5_S, count - pl0);
+    // input index range any tap of this block's texels can touch (scale_audio is increasing)
+    const float fn = (float) n;
+    const float lo_f = scale_audio(sp, g_clamp(((float) x0 + 0.5f) / fn - sp.smooth_factor, 0.0f, 1.0f)) * fn;
+    const float hi_f = scale_audio(sp, g_clamp(((float) (x1 - 1) + 0.5f) / fn + sp.smooth_factor, 0.0f, 1.0f)) * fn;
+    int lo = (int) floorf(lo_f) - 2, hi = (int) ceilf(hi_f) + 3;
+    lo = lo < 0 ? 0 : lo; hi = hi > n ? n : hi;
+    const int span = hi > lo ? hi - lo : 0;
+    for (int i = threadIdx.x; i < npl * span; i += K5_XT) {
+        const int pl = i / span, k = i - pl * span;
+        seg[pl * span + k] = in[(size_t) (pl0 + pl) * n + lo + k];
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x;
+    if (x >= x1) return;
+    SmoothAcc acc[K5_S];
+#pragma unroll
+    for (int s = 0; s < K5_S; ++s) acc[s].init();
+    smooth_enumerate(sp, n, ((float) x + 0.5f) / fn, [&](int i, float w) {
+        const int k = i - lo;
+        const bool valid = (i >= 0 && i < n);                          // outside [0, n): texelFetch reads 0
+        const bool staged = valid && k >= 0 && k < span;               // (always, unless the range estimate is off)
+#pragma unroll
+        for (int s = 0; s < K5_S; ++s) {
+            float texel = 0.0f;
+            if (valid && s < npl) texel = from16(staged ? seg[s * span + k] : in[(size_t) (pl0 + s) * n + i]);
+            acc[s].add(texel, w);
+        }
+    });
+#pragma unroll
+    for (int s = 0; s < K5_S; ++s)
+        if (s < npl) out[(size_t) (pl0 + s) * n + x] = (uint16_t) unorm16(acc[s].result(sp));
 }
 int launch_smooth_only(const glava_b200_params& p, const uint16_t* d_in, uint16_t* d_out, int count, void* stream) {
-    smooth_only_kernel<<<count, 256, p.n * 2, (cudaStream_t) stream>>>(d_in, d_out, p.n, p);
+    // worst-case span: the last block's taps, bounded by the whole plane
+    const SmoothParams sp = smooth_params(p);
+    const float fn = (float) p.n;
+    int span = 0;
+    for (int x0 = 0; x0 < p.n; x0 += K5_XT) {
+        const int x1 = (x0 + K5_XT < p.n) ? x0 + K5_XT : p.n;
+        const float lo_f = scale_audio(sp, g_clamp(((float) x0 + 0.5f) / fn - sp.smooth_factor, 0.0f, 1.0f)) * fn;
+        const float hi_f = scale_audio(sp, g_clamp(((float) (x1 - 1) + 0.5f) / fn + sp.smooth_factor, 0.0f, 1.0f)) * fn;
+        int lo = (int) floorf(lo_f) - 2, hi = (int) ceilf(hi_f) + 3;
+        lo = lo < 0 ? 0 : lo; hi = hi > p.n ? p.n : hi;
+        if (hi - lo > span) span = hi - lo;
+    }
+    const size_t smem = (size_t) K5_S * (span > 0 ? span : 1) * sizeof(uint16_t);
+    if (smem > 200 * 1024) return fail(GLAVA_B200_EINVAL, "smooth pass: tap span %d too large for shared memory", span);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k5_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "cudaFuncSetAttribute(k5): %s", cudaGetErrorString(e));
+    }
+    dim3 grid((p.n + K5_XT - 1) / K5_XT, (count + K5_S - 1) / K5_S);
+    k5_planes_kernel<<<grid, K5_XT, smem, (cudaStream_t) stream>>>(d_in, d_out, p.n, count, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "smooth kernel launch: %s", cudaGetErrorString(e));
     return 0;
