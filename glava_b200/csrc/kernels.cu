@@ -51,6 +51,9 @@ template <int LOG2N> struct SpecCfg {
     static constexpr int OFF_AV  = ((BUF_CPX * 8 + 15) / 16) * 16;
     static constexpr int OFF_BAR = OFF_AV + N * 2;
     static constexpr int SMEM    = OFF_BAR + 16;
+    // resident CTAs per SM the register allocation must allow: the kernel waits on memory a lot (TMA load,
+    // state loads), so occupancy is worth more than the last registers (128 regs -> 2 CTAs/SM was measured)
+    static constexpr int MIN_CTAS = T >= 512 ? 1 : 3;   // T = 512 (N >= 8192): capping at 64 registers spills in the FFT passes and was measured slower
 };
 
 template <int M, int T, int NS, class Loader>
@@ -72,7 +75,7 @@ __device__ __forceinline__ void run_passes(cpx* buf, Loader first_loader, const 
 extern __shared__ __align__(16) unsigned char glb_smem[];
 
 template <int LOG2N, bool IS_FFT>
-__global__ void __launch_bounds__(SpecCfg<LOG2N>::T)
+__global__ void __launch_bounds__(SpecCfg<LOG2N>::T, SpecCfg<LOG2N>::MIN_CTAS)
 spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ glava_b200_params p) {
     using C = SpecCfg<LOG2N>;
     constexpr int N = C::N, M = C::M, T = C::T;
@@ -174,7 +177,7 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
                 if constexpr (FT > 0) {
                     // 4 elements per trip: all their state loads (1 + FT-1 each) are issued before the
                     // first dependent use, so the global-load latency is paid once per trip, not per element
-                    constexpr int U = (N / T) % 4 == 0 ? 4 : ((N / T) % 2 == 0 ? 2 : 1);
+                    constexpr int U = (N / T) % 2 == 0 ? 2 : 1;   // 4 was measured to cost registers (spills under the occupancy cap) for no gain
                     static_assert((N / T) % U == 0, "N / T must be a multiple of the epilogue unroll");
                     // epi_n (multiple of T): with lazy K5 only the leading bins that some sampled texel's
                     // taps can reach are post-processed (their state is all that can influence a pixel)
