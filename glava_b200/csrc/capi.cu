@@ -49,8 +49,8 @@ struct glava_b200 {
     glava_b200_params p;
     int batch, device, slots;
     cudaStream_t stream;        // raster kernels, read-backs (the stream glava_b200_cuda_stream returns)
-    cudaStream_t spec_stream;   // spectrum kernels + FIFO ingest, highest priority: the latency-bound spectrum
-                                // kernel of update i+1 co-runs with the HBM-bound raster kernel of update i
+    cudaStream_t spec_stream;   // spectrum kernels + FIFO ingest, lowest priority: the latency-bound spectrum
+                                // kernel of update i+1 runs under the HBM-bound raster kernel of update i
     int    tex_cur;             // which half of d_tex the latest spectrum wrote / the raster reads
     cudaEvent_t ev_spec_done[2], ev_raster_done[2];
     // inputs
