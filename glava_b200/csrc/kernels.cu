@@ -753,6 +753,7 @@ raster_circle_kernel(const __grid_constant__ RasterArgs a, const __grid_constant
     // 256 threads: 32 quads per row x 8 rows
     const int qx = threadIdx.x & 31, qy = threadIdx.x >> 5;
     const int x = tx0 + qx * 4;
+    const CircleConsts cc = circle_consts(p);
     // whole CTA region (its 128 columns x tiles_per_cta*8 rows, + halo) outside the disc: bare zero-store loop
     {
         const int Y0 = blockIdx.y * tiles_per_cta * CIRCLE_TH, Y1 = min(p.h, Y0 + tiles_per_cta * CIRCLE_TH);
@@ -781,6 +782,25 @@ raster_circle_kernel(const __grid_constant__ RasterArgs a, const __grid_constant
         if (!tile_dead) {
             // (batching the geometry loads of a thread's 5-6 cells ahead of the dependent texel fetches was
             // measured slower: 64 -> 106 registers, half the resident warps)
+            if (a.geo) {
+                // cached geometry: a cell is either outside the cache box (0) or a 16-byte entry with three
+                // texel references + d; entries that cannot be lit carry e0 = -1.  No per-cell float culling,
+                // no transcendental, constants hoisted (the kernel was instruction bound: ncu issue-active 71 %).
+                const int4* __restrict__ geo = reinterpret_cast<const int4*>(a.geo);
+                int ly = threadIdx.x / (CIRCLE_TW + 2), lx = threadIdx.x - ly * (CIRCLE_TW + 2);
+                for (; ly < CIRCLE_TH + 2; ) {
+                    const int bxi = tx0 + lx - 1 - a.gx0, byi = ty0 + ly - 1 - a.gy0;
+                    uint32_t v = 0u;
+                    if (bxi >= 0 && byi >= 0 && bxi < a.gw && byi < a.gh) {
+                        const int4 e = __ldg(geo + (size_t) byi * a.gw + bxi);
+                        CircleGeo g; g.dR = __int_as_float(e.x); g.e0 = e.y; g.e1 = e.z; g.e2 = e.w;
+                        v = circle_stage1_c(cc, t.l, t.r, t.n, g);
+                    }
+                    tile[ly][lx] = v;
+                    lx += 256 - (CIRCLE_TW + 2); ly += 1;               // advance by 256 cells: 256 = 130 + 126
+                    if (lx >= CIRCLE_TW + 2) { lx -= CIRCLE_TW + 2; ly += 1; }
+                }
+            } else
             for (int i = threadIdx.x; i < (CIRCLE_TH + 2) * (CIRCLE_TW + 2); i += blockDim.x) {
                 const int ly = i / (CIRCLE_TW + 2), lx = i - ly * (CIRCLE_TW + 2);
                 const int gx = tx0 + lx - 1, gy = ty0 + ly - 1;
@@ -788,15 +808,7 @@ raster_circle_kernel(const __grid_constant__ RasterArgs a, const __grid_constant
                 if (gx >= 0 && gy >= 0 && gx < p.w && gy < p.h) {
                     const float dx = (float) gx - cx, dy = (float) gy - cy;
                     const float d2 = dx * dx + dy * dy;
-                    if (d2 <= reach * reach && !(inner > 0.0f && d2 < inner * inner)) {
-                        const int bxi = gx - a.gx0, byi = gy - a.gy0;
-                        if (a.geo && bxi >= 0 && byi >= 0 && bxi < a.gw && byi < a.gh) {
-                            // cached geometry: three texel references + d, no transcendental per frame
-                            const int4 e = __ldg(reinterpret_cast<const int4*>(a.geo) + (size_t) byi * a.gw + bxi);
-                            CircleGeo g; g.dR = __int_as_float(e.x); g.e0 = e.y; g.e1 = e.z; g.e2 = e.w;
-                            v = circle_stage1_geo(p, t, g);
-                        } else v = circle_stage1(p, t, gx, gy);
-                    }
+                    if (d2 <= reach * reach && !(inner > 0.0f && d2 < inner * inner)) v = circle_stage1(p, t, gx, gy);
                 }
                 tile[ly][lx] = v;
             }

@@ -257,16 +257,30 @@ GLB_HD float circle_ref_value(const glava_b200_params& p, const AudioTex& t, int
     float v = (i >= t.n) ? 0.0f : from16(tex[i]);
     return v * p.circle_amplify;
 }
-GLB_HD uint32_t circle_stage1_geo(const glava_b200_params& p, const AudioTex& t, const CircleGeo& g) {
+// the per-frame constants of stage 1, hoisted out of the per-cell path by the kernel
+struct CircleConsts { float amplify, hl; int fill; uint32_t outline_px; };
+GLB_HD CircleConsts circle_consts(const glava_b200_params& p) {
+    CircleConsts c = { p.circle_amplify, p.circle_line / 2.0f, p.circle_fill, pack8(mk4a(p.circle_outline)) };
+    return c;
+}
+GLB_HD float circle_ref_value_c(const CircleConsts& c, const uint16_t* tl, const uint16_t* tr, int n, int e) {
+    const int i = e & 0x3fffffff;
+    const uint16_t* tex = (e >> 30) ? tr : tl;
+    float v = (i >= n) ? 0.0f : from16(tex[i]);
+    return v * c.amplify;
+}
+GLB_HD uint32_t circle_stage1_c(const CircleConsts& c, const uint16_t* tl, const uint16_t* tr, int n, const CircleGeo& g) {
     if (g.e0 < 0) return 0u;
-    float hl = p.circle_line / 2.0f;
-    float v = circle_ref_value(p, t, g.e0);
-    float adj0 = circle_ref_value(p, t, g.e1) - v;
-    float adj1 = circle_ref_value(p, t, g.e2) - v;
+    float v = circle_ref_value_c(c, tl, tr, n, g.e0);
+    float adj0 = circle_ref_value_c(c, tl, tr, n, g.e1) - v;
+    float adj1 = circle_ref_value_c(c, tl, tr, n, g.e2) - v;
     float dmax = g_max(adj0, adj1), dmin = g_min(adj0, adj1);
     float d = g.dR - v;
-    bool in = p.circle_fill ? (d < hl) : ((d > -hl && d < hl) || (d <= dmax && d >= dmin));
-    return in ? pack8(mk4a(p.circle_outline)) : 0u;
+    bool in = c.fill ? (d < c.hl) : ((d > -c.hl && d < c.hl) || (d <= dmax && d >= dmin));
+    return in ? c.outline_px : 0u;
+}
+GLB_HD uint32_t circle_stage1_geo(const glava_b200_params& p, const AudioTex& t, const CircleGeo& g) {
+    return circle_stage1_c(circle_consts(p), t.l, t.r, t.n, g);
 }
 // 8-tap neighbour mean as written in circle/2.frag:18-27, graph/2.frag:21-30, wave/2.frag:18-27:
 // taps a3 and a7 repeat a0 and a4.  nb[] = stage values at (x+1,y) (x+1,y+1) (x,y+1) (x-1,y) (x-1,y-1) (x,y-1)
