@@ -64,7 +64,7 @@ struct glava_b200 {
     // constants
     double* d_window; float* d_twiddle; void* d_rowtab; int* d_need; int need_count;
     TapEntry* d_tap_tab; int* d_tap_cnt; float* d_tap_wsum; int tap_max; int epi_n;
-    void* d_geo; int geo_box[4];   // polar geometry cache (radial / circle), see kernels.cu
+    void* d_geo; int geo_box[4];   // polar geometry cache (radial / circle), see raster_kernels.cu
     // state + outputs
     float* d_spec; float* d_applied; float* d_ring_f;
     uint16_t* d_gr_store; uint16_t* d_ring_u; uint16_t* d_tex;

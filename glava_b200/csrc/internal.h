@@ -68,7 +68,7 @@ struct RasterArgs {
     int       gx0, gy0, gw, gh;  // box origin and size in pixels (gx0, gw multiples of 4)
 };
 
-// ---- kernel launchers (kernels.cu); `stream` is a cudaStream_t passed as void* ------------------
+// ---- kernel launchers (spectrum_kernels.cu, raster_kernels.cu); `stream` is a cudaStream_t passed as void* ------------------
 int launch_spectrum(const glava_b200_params& p, const SpectrumArgs& a, bool is_fft, void* stream);
 int launch_smooth_only(const glava_b200_params& p, const uint16_t* d_in, uint16_t* d_out, int count, void* stream);
 int launch_raster(const glava_b200_params& p, const RasterArgs& a, void* stream);

@@ -1,0 +1,459 @@
+// spectrum_kernels.cu — sm_100a kernels of the PCM -> R16 texture half of the path.
+//
+//   spectrum_kernel    one work unit per (stream, channel): TMA bulk load of the PCM ring into shared memory,
+//                      window, (N/2)-point Stockham FFT in shared memory, |.|/log/ramp, gravity + average
+//                      (pipeline A float state or pipeline B R16 state in HBM), lazy K5 smoothing out of
+//                      shared memory -> R16 texture.   [replaces render.c transform_fft/gravity/average +
+//                      util/{pass,gravity_pass,average_pass,smooth_pass}.frag + 5 GL draws and one
+//                      glTexImage1D per channel per frame]
+//   k5_planes_kernel   K5 for whole planes, tap weights shared between 8 planes
+//   fifo_ingest_kernel fifo.c:89-110 on the device-resident rings
+//
+// Compiled with --fmad=false: results are bit-identical to the host build of the *_core.h maths.
+#include "internal.h"
+#include "raster_core.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+#include <type_traits>
+
+namespace glb {
+
+// ---------------------------------------------------------------------------------------------
+// small PTX wrappers: mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n WAIT_%=:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// spectrum kernel
+template <int LOG2N> struct SpecCfg {
+    static constexpr int N = 1 << LOG2N, M = N / 2;
+    static constexpr int T = (M / 8 < 128) ? 128 : ((M / 8 > 512) ? 512 : M / 8);
+    static constexpr int BUF_CPX = fft_padded_size(M);
+    // cpx buffer (also the raw-PCM staging area, N floats = M cpx) | u16 av[N] | mbarrier
+    static constexpr int OFF_AV  = ((BUF_CPX * 8 + 15) / 16) * 16;
+    static constexpr int OFF_BAR = OFF_AV + N * 2;
+    static constexpr int SMEM    = OFF_BAR + 16;
+    // resident CTAs per SM the register allocation must allow: the kernel waits on memory a lot (TMA load,
+    // state loads), so occupancy is worth more than the last registers (128 regs -> 2 CTAs/SM was measured)
+    static constexpr int MIN_CTAS = T >= 512 ? 1 : 3;   // T = 512 (N >= 8192): capping at 64 registers spills in the FFT passes and was measured slower
+};
+
+template <int M, int T, int NS, class Loader>
+__device__ __forceinline__ void run_passes(cpx* buf, Loader first_loader, const cpx* __restrict__ tw, int tid) {
+    constexpr int REM = M / NS;                      // points still to be combined
+    if constexpr (REM > 1) {
+        constexpr int R = (REM >= 8) ? 8 : REM;      // 8, 8, ..., then 4 or 2
+        using Pass = StockhamPass<M, T, R, NS>;
+        cpx reg[Pass::PER][R];
+        if constexpr (NS == 1) Pass::load(first_loader, tw, tid, reg);
+        else Pass::load([buf](int i) { return buf[fft_pad(i)]; }, tw, tid, reg);
+        __syncthreads();
+        Pass::store(buf, tid, reg);
+        __syncthreads();
+        run_passes<M, T, NS * R>(buf, first_loader, tw, tid);
+    }
+}
+
+extern __shared__ __align__(16) unsigned char glb_smem[];
+
+template <int LOG2N, bool IS_FFT>
+__global__ void __launch_bounds__(SpecCfg<LOG2N>::T, SpecCfg<LOG2N>::MIN_CTAS)
+spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ glava_b200_params p) {
+    using C = SpecCfg<LOG2N>;
+    constexpr int N = C::N, M = C::M, T = C::T;
+    const int tid = threadIdx.x;
+
+    cpx*      buf = reinterpret_cast<cpx*>(glb_smem);
+    float*    raw = reinterpret_cast<float*>(glb_smem);
+    uint16_t* av  = reinterpret_cast<uint16_t*>(glb_smem + C::OFF_AV);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(glb_smem + C::OFF_BAR);
+
+    // Persistent CTAs: work unit u = one (stream, channel) plane (wave: one stream, audio_l only,
+    // wave/1.frag:7); a CTA walks u = blockIdx.x, + gridDim.x, ...  The PCM ring of the NEXT unit is
+    // prefetched by the TMA engine while this unit's smoothing pass runs.
+    const int units = IS_FFT ? a.batch * 2 : a.batch;
+    auto issue_load = [&](int u) {                   // one bulk async copy, N*4 bytes, completes on `bar`
+        const int cc = IS_FFT ? u : 2 * u;
+        const float* pcm = ((cc & 1) == 0 ? a.pcm_l : a.pcm_r) + (size_t) (cc >> 1) * N;
+        // the buffer was last touched through the generic proxy (FFT passes): order those accesses
+        // before the async-proxy (TMA) write
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, N * 4);
+        bulk_g2s(raw, pcm, N * 4, bar);
+    };
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0 && (int) blockIdx.x < units) issue_load(blockIdx.x);
+    uint32_t parity = 0;
+    const int F = p.avg_frames;
+
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    const int c = IS_FFT ? u : 2 * u, ch = c & 1;
+    const size_t plane = (size_t) c * N;
+    if (IS_FFT && p.accel_fft) {
+        // while the PCM load is in flight: pull this plane's gravity / average state (1 + F planes of
+        // u16, HBM-resident) towards L2, so the epilogue's loads after the FFT are L2 hits
+        const char* g0 = reinterpret_cast<const char*>(a.gr_store + plane);
+        const char* r0 = reinterpret_cast<const char*>(a.ring_u + plane * F);
+        const int lines_g = (N * 2) / 128, lines_r = (N * 2 * F) / 128;   // (whole planes: cheap, and epi_n varies)
+        for (int i = tid; i < lines_g + lines_r; i += T) {
+            const char* ptr = i < lines_g ? g0 + (size_t) i * 128 : r0 + (size_t) (i - lines_g) * 128;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+        }
+    }
+    mbar_wait(bar, parity); parity ^= 1u;
+
+    if constexpr (IS_FFT) {
+        // --- window (render.c:793-795: float * double -> float) folded into the first pass loads ----
+        const double2* w2 = reinterpret_cast<const double2*>(a.window);
+        auto first = [raw, w2](int i) {
+            float2 v = reinterpret_cast<const float2*>(raw)[i];
+            double2 w = __ldg(&w2[i]);
+            cpx r = { (float) ((double) v.x * w.x), (float) ((double) v.y * w.y) };
+            return r;
+        };
+        run_passes<M, T, 1>(buf, first, reinterpret_cast<const cpx*>(a.twiddle), tid);
+
+        if (!p.accel_fft) {
+            // --- pipeline A: render.c:2149-2156 --------------------------------------------------
+            const float g = p.gravity_step * (1.0f / p.ur);
+            const int newest = (int) (a.update % (unsigned long long) F);
+            for (int n = tid; n < N; n += T) {
+                cpx z = buf[fft_pad(n >> 1)];
+                float v = fft_post((n & 1) ? z.y : z.x, n, N, p.fft_scale, p.fft_cutoff);
+                v = gravity_a(v, &a.applied[plane + n], g);
+                float* ring = a.ring_f + plane * F;
+                ring[(size_t) newest * N + n] = v;
+                float acc = 0.0f;
+                for (int f = 0; f < F; ++f) {                      // oldest first, like the memmove'd ring
+                    int slot = newest + 1 + f; if (slot >= F) slot -= F;
+                    float b = (f == F - 1) ? v : ring[(size_t) slot * N + n];
+                    if (p.avg_window) acc = (float) ((double) acc + a.avg_w_a[f] * (double) b);
+                    else acc += b;
+                }
+                float out = acc / (float) F;
+                a.spec[plane + n] = out;
+                av[n] = (uint16_t) unorm16(out);                   // glTexImage1D GL_R16 upload, render.c:521-524
+            }
+        } else {
+            // --- pipeline B: render.c:2177-2267 ---------------------------------------------------
+            const float diff = p.gravity_step * (1.0f / p.ur);
+            const int out_idx = (int) (a.update % (unsigned long long) F);
+            const int epi_n = (a.epi_n > 0 && a.epi_n < N) ? ((a.epi_n + T - 1) / T) * T : N;
+            float*    const spec = a.spec + plane;
+            uint16_t* const grs  = a.gr_store + plane;
+            uint16_t* const ring = a.ring_u + plane * F;
+            // FT = compile-time copy of F for the common small values: the slot offsets and the
+            // weights of the average live in registers and the tap loop is fully unrolled
+            auto epilogue = [&](auto ft) {
+                constexpr int FT = decltype(ft)::value;               // 0 = generic (runtime F)
+                const int FF = FT ? FT : F;
+                int off[FT ? FT : 1]; float wt[FT ? FT : 1];
+                if constexpr (FT > 0) {
+#pragma unroll
+                    for (int i = 0; i < FT; ++i) {
+                        int fr = out_idx - i; if (fr < 0) fr += FT;
+                        off[i] = fr * N; wt[i] = a.avg_w_b[i];
+                    }
+                }
+                if constexpr (FT > 0) {
+                    // 4 elements per trip: all their state loads (1 + FT-1 each) are issued before the
+                    // first dependent use, so the global-load latency is paid once per trip, not per element
+                    constexpr int U = (N / T) % 2 == 0 ? 2 : 1;   // 4 was measured to cost registers (spills under the occupancy cap) for no gain
+                    static_assert((N / T) % U == 0, "N / T must be a multiple of the epilogue unroll");
+                    // epi_n (multiple of T): with lazy K5 only the leading bins that some sampled texel's
+                    // taps can reach are post-processed (their state is all that can influence a pixel)
+                    for (int n0 = tid; n0 < epi_n; n0 += U * T) {
+                        uint32_t g_old[U], rg[U][FT];
+#pragma unroll
+                        for (int e = 0; e < U; ++e) {
+                            const int n = n0 + e * T;
+                            if (n >= epi_n) continue;
+                            g_old[e] = grs[n];
+#pragma unroll
+                            for (int i = 1; i < FT; ++i) rg[e][i] = ring[off[i] + n];
+                        }
+#pragma unroll
+                        for (int e = 0; e < U; ++e) {
+                            const int n = n0 + e * T;
+                            if (n >= epi_n) continue;
+                            cpx z = buf[fft_pad(n >> 1)];
+                            float v = fft_post((n & 1) ? z.y : z.x, n, N, p.fft_scale, p.fft_cutoff);
+                            spec[n] = v;
+                            uint32_t gq = gravity_b(unorm16(v), g_old[e], diff);
+                            grs[n] = (uint16_t) gq;
+                            uint32_t texel = gq;
+                            if (FT > 1) {
+                                ring[off[0] + n] = (uint16_t) gq;
+                                float r = 0.0f;
+#pragma unroll
+                                for (int i = 0; i < FT; ++i) {         // t0 = most recent (render.c:2250-2255)
+                                    float tx = from16(i == 0 ? gq : rg[e][i]);
+                                    if (a.avg_b_windowed) r += wt[i] * tx; else r += tx;
+                                }
+                                texel = unorm16(r / (float) FT);
+                            }
+                            av[n] = (uint16_t) texel;
+                        }
+                    }
+                } else {
+                    for (int n = tid; n < epi_n; n += T) {             // any F: runtime loop
+                        cpx z = buf[fft_pad(n >> 1)];
+                        float v = fft_post((n & 1) ? z.y : z.x, n, N, p.fft_scale, p.fft_cutoff);
+                        spec[n] = v;
+                        uint32_t gq = gravity_b(unorm16(v), grs[n], diff);
+                        grs[n] = (uint16_t) gq;
+                        uint32_t texel = gq;
+                        if (FF > 1) {
+                            float r = 0.0f;
+                            ring[(size_t) out_idx * N + n] = (uint16_t) gq;
+                            for (int i = 0; i < F; ++i) {
+                                int fr = out_idx - i; if (fr < 0) fr += F;
+                                float tx = from16(i == 0 ? gq : (uint32_t) ring[(size_t) fr * N + n]);
+                                if (a.avg_b_windowed) r += a.avg_w_b[i] * tx; else r += tx;
+                            }
+                            texel = unorm16(r / (float) FF);
+                        }
+                        av[n] = (uint16_t) texel;
+                    }
+                }
+            };
+            switch (F) {
+                case 5: epilogue(std::integral_constant<int, 5>()); break;       // shipped default (smooth_parameters.glsl:56)
+                case 6: epilogue(std::integral_constant<int, 6>()); break;       // compiled-in default (render.c:912)
+                case 3: epilogue(std::integral_constant<int, 3>()); break;
+                case 4: epilogue(std::integral_constant<int, 4>()); break;
+                default: epilogue(std::integral_constant<int, 0>()); break;
+            }
+        }
+    } else {
+        // --- wave: "window" (no-op) + "wrange" (render.c:773-781), upload ---------------------------
+        for (int n = tid; n < N; n += T) {
+            float b = raw[n];
+            b += 1.0f; b /= 2.0f;
+            a.spec[plane + n] = b;
+            av[n] = (uint16_t) unorm16(b);
+        }
+    }
+    __syncthreads();
+    // `raw`/`buf` are dead from here on: let the TMA engine fetch the next unit's PCM during K5
+    if (tid == 0 && u + (int) gridDim.x < units) issue_load(u + gridDim.x);
+
+    // --- K5 smooth pass out of shared memory (render.c:2276-2303) ----------------------------------
+    uint16_t* tex = a.tex + plane;
+    if (p.smooth_pass) {
+        const SmoothParams sp = smooth_params(p);
+        if (a.need && a.tap_tab) {
+            // weights / indices precomputed once (they depend on the parameters only): per tap one
+            // coalesced 8-byte load, one shared-memory texel fetch, a multiply and an add
+            const int* need = a.need + (size_t) ch * a.need_count;
+            const TapEntry* tab = a.tap_tab + (size_t) ch * a.tap_max * a.need_count;
+            for (int k = tid; k < a.need_count; k += T) {
+                const int x = need[k];
+                if (x < 0 || x >= N) continue;
+                const int cnt = a.tap_cnt[(size_t) ch * a.need_count + k];
+                SmoothAcc acc; acc.init();
+                for (int j = 0; j < cnt; ++j) {
+                    const int2 e = __ldg(reinterpret_cast<const int2*>(tab) + (size_t) j * a.need_count + k);
+                    acc.add_noweight(fetch16(av, N, e.x), __int_as_float(e.y));
+                }
+                acc.weight = a.tap_wsum[(size_t) ch * a.need_count + k];
+                tex[x] = (uint16_t) unorm16(acc.result(sp));
+            }
+        } else if (a.need) {
+            const int* need = a.need + (size_t) ch * a.need_count;
+            for (int k = tid; k < a.need_count; k += T) {
+                int x = need[k];
+                if (x >= 0 && x < N) tex[x] = (uint16_t) smooth_pass_texel(sp, av, N, x);
+            }
+        } else if (a.av_out) {
+            // all n texels wanted: export the pre-smoothing texture; k5_planes_kernel (below) smooths it,
+            // sharing every tap weight between several planes instead of recomputing it per plane
+            uint16_t* dst = a.av_out + plane;
+            for (int x = tid; x < N; x += T) dst[x] = av[x];
+        } else {
+            for (int x = tid; x < N; x += T) tex[x] = (uint16_t) smooth_pass_texel(sp, av, N, x);
+        }
+    } else {
+        for (int x = tid; x < N; x += T) tex[x] = av[x];
+    }
+    __syncthreads();                                 // `av` may be overwritten by the next unit's epilogue
+  }
+}
+
+int spectrum_smem_bytes(int n) {
+    switch (n) {
+        case 256:   return SpecCfg<8>::SMEM;   case 512:   return SpecCfg<9>::SMEM;
+        case 1024:  return SpecCfg<10>::SMEM;  case 2048:  return SpecCfg<11>::SMEM;
+        case 4096:  return SpecCfg<12>::SMEM;  case 8192:  return SpecCfg<13>::SMEM;
+        case 16384: return SpecCfg<14>::SMEM;  default: return -1;
+    }
+}
+
+template <int LOG2N, bool IS_FFT>
+static int launch_spectrum_t(const glava_b200_params& p, const SpectrumArgs& a, cudaStream_t st) {
+    using C = SpecCfg<LOG2N>;
+    auto kern = spectrum_kernel<LOG2N, IS_FFT>;
+    // Residency cap (tuning aid, off): the kernel co-runs with the raster kernel (capi.cu run_update) and
+    // at full occupancy (5 CTAs x 256 threads x 48 registers per SM) takes most of the register file.
+    // Requesting more dynamic shared memory than needed caps it at `cap` CTAs per SM.  Measured on B200
+    // (whole step, 1024 streams): no cap 705 k frames/s > cap 3: 686 k > cap 2: 647 k > cap 1: 540 k —
+    // the stretched spectrum kernel (and the L1 it takes from the raster kernel) costs more than it frees.
+    static int smem_req = 0;
+    if (!smem_req) {
+        int cap = 0;
+        if (const char* e = getenv("GLAVA_B200_SPEC_RESIDENT")) cap = atoi(e);
+        smem_req = C::SMEM;
+        if (cap > 0) { int want = (227 * 1024) / cap - 1024; if (want > smem_req) smem_req = want; }
+        if (smem_req > 227 * 1024) smem_req = 227 * 1024;
+    }
+    if (smem_req > 48 * 1024) {
+        // per-device function attribute: set on every launch (handles on several devices may live in one process)
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req);
+        if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "cudaFuncSetAttribute(spectrum): %s", cudaGetErrorString(e));
+    }
+    // Persistent grid: a few CTAs per SM.  Small on purpose — this kernel is latency bound and is meant
+    // to run UNDER the HBM-bound raster kernel of the previous update (capi.cu run_update) without taking
+    // its occupancy away.  GLAVA_B200_SPEC_CTAS_PER_SM overrides (0 = one CTA per work unit).
+    int sm_count = 148;
+    { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); if (sm_count <= 0) sm_count = 148; }
+    int per_sm = 0;                                  // measured on B200: 0 (one CTA per unit) >= 4 > 3 > 2 > 1 for whole-step throughput
+    if (const char* e = getenv("GLAVA_B200_SPEC_CTAS_PER_SM")) per_sm = atoi(e);
+    const int units = IS_FFT ? a.batch * 2 : a.batch;
+    int grid = (per_sm > 0 && sm_count * per_sm < units) ? sm_count * per_sm : units;
+    kern<<<grid, C::T, smem_req, st>>>(a, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "spectrum kernel launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int launch_spectrum(const glava_b200_params& p, const SpectrumArgs& a, bool is_fft, void* stream) {
+    cudaStream_t st = (cudaStream_t) stream;
+#define GLB_CASE(L) case (1 << L): return is_fft ? launch_spectrum_t<L, true>(p, a, st) : launch_spectrum_t<L, false>(p, a, st);
+    switch (p.n) {
+        GLB_CASE(8) GLB_CASE(9) GLB_CASE(10) GLB_CASE(11) GLB_CASE(12) GLB_CASE(13) GLB_CASE(14)
+        default: return fail(GLAVA_B200_EINVAL, "unsupported setbufsize %d", p.n);
+    }
+#undef GLB_CASE
+}
+
+// K5 for whole planes (all n output texels): util/smooth_pass.frag over `count` R16 planes.
+// The tap indices and weights of an output texel depend on the parameters only, so one thread computes
+// them once (the expensive part: log, divide, sine) and applies them to K5_S planes held in shared
+// memory; per plane and tap only a fetch, a multiply and an add remain.  Per-plane arithmetic and
+// summation order are exactly smooth_audio()'s.
+#define K5_S  8
+#define K5_XT 128
+__global__ void __launch_bounds__(K5_XT)
+k5_planes_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int n, int count,
+                 const __grid_constant__ glava_b200_params p) {
+    uint16_t* seg = reinterpret_cast<uint16_t*>(glb_smem);           // [K5_S][span]
+    const SmoothParams sp = smooth_params(p);
+    const int x0 = blockIdx.x * K5_XT, x1 = min(n, x0 + K5_XT);
+    const int pl0 = blockIdx.y * K5_S, npl = min(K5_S, count - pl0);
+    // input index range any tap of this block's texels can touch (scale_audio is increasing)
+    const float fn = (float) n;
+    const float lo_f = scale_audio(sp, g_clamp(((float) x0 + 0.5f) / fn - sp.smooth_factor, 0.0f, 1.0f)) * fn;
+    const float hi_f = scale_audio(sp, g_clamp(((float) (x1 - 1) + 0.5f) / fn + sp.smooth_factor, 0.0f, 1.0f)) * fn;
+    int lo = (int) floorf(lo_f) - 2, hi = (int) ceilf(hi_f) + 3;
+    lo = lo < 0 ? 0 : lo; hi = hi > n ? n : hi;
+    const int span = hi > lo ? hi - lo : 0;
+    for (int i = threadIdx.x; i < npl * span; i += K5_XT) {
+        const int pl = i / span, k = i - pl * span;
+        seg[pl * span + k] = in[(size_t) (pl0 + pl) * n + lo + k];
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x;
+    if (x >= x1) return;
+    SmoothAcc acc[K5_S];
+#pragma unroll
+    for (int s = 0; s < K5_S; ++s) acc[s].init();
+    smooth_enumerate(sp, n, ((float) x + 0.5f) / fn, [&](int i, float w) {
+        const int k = i - lo;
+        const bool valid = (i >= 0 && i < n);                          // outside [0, n): texelFetch reads 0
+        const bool staged = valid && k >= 0 && k < span;               // (always, unless the range estimate is off)
+#pragma unroll
+        for (int s = 0; s < K5_S; ++s) {
+            float texel = 0.0f;
+            if (valid && s < npl) texel = from16(staged ? seg[s * span + k] : in[(size_t) (pl0 + s) * n + i]);
+            acc[s].add(texel, w);
+        }
+    });
+#pragma unroll
+    for (int s = 0; s < K5_S; ++s)
+        if (s < npl) out[(size_t) (pl0 + s) * n + x] = (uint16_t) unorm16(acc[s].result(sp));
+}
+int launch_smooth_only(const glava_b200_params& p, const uint16_t* d_in, uint16_t* d_out, int count, void* stream) {
+    // worst-case span: the last block's taps, bounded by the whole plane
+    const SmoothParams sp = smooth_params(p);
+    const float fn = (float) p.n;
+    int span = 0;
+    for (int x0 = 0; x0 < p.n; x0 += K5_XT) {
+        const int x1 = (x0 + K5_XT < p.n) ? x0 + K5_XT : p.n;
+        const float lo_f = scale_audio(sp, g_clamp(((float) x0 + 0.5f) / fn - sp.smooth_factor, 0.0f, 1.0f)) * fn;
+        const float hi_f = scale_audio(sp, g_clamp(((float) (x1 - 1) + 0.5f) / fn + sp.smooth_factor, 0.0f, 1.0f)) * fn;
+        int lo = (int) floorf(lo_f) - 2, hi = (int) ceilf(hi_f) + 3;
+        lo = lo < 0 ? 0 : lo; hi = hi > p.n ? p.n : hi;
+        if (hi - lo > span) span = hi - lo;
+    }
+    const size_t smem = (size_t) K5_S * (span > 0 ? span : 1) * sizeof(uint16_t);
+    if (smem > 200 * 1024) return fail(GLAVA_B200_EINVAL, "smooth pass: tap span %d too large for shared memory", span);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k5_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "cudaFuncSetAttribute(k5): %s", cudaGetErrorString(e));
+    }
+    dim3 grid((p.n + K5_XT - 1) / K5_XT, (count + K5_S - 1) / K5_S);
+    k5_planes_kernel<<<grid, K5_XT, smem, (cudaStream_t) stream>>>(d_in, d_out, p.n, count, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "smooth kernel launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FIFO ingest (fifo.c:89-110): slide + append, ping-pong between two ring buffers
+__global__ void fifo_ingest_kernel(const int16_t* __restrict__ chunks, int frames, int n, int channels,
+                                   const float* __restrict__ src_l, const float* __restrict__ src_r,
+                                   float* __restrict__ dst_l, float* __restrict__ dst_r) {
+    const int s = blockIdx.y;
+    const size_t base = (size_t) s * n;
+    const int16_t* in = chunks + (size_t) s * frames * 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float l, r;
+        if (i < n - frames) { l = src_l[base + i + frames]; r = src_r[base + i + frames]; }
+        else {
+            int q = i - (n - frames);
+            int a = in[2 * q], b = in[2 * q + 1];
+            if (channels == 1) { float m = (float) ((a + b) / 2) / (float) 65535; l = m; r = m; }
+            else { l = (float) a / (float) 65535; r = (float) b / (float) 65535; }
+        }
+        dst_l[base + i] = l; dst_r[base + i] = r;
+    }
+}
+int launch_fifo_ingest(const glava_b200_params& p, const int16_t* d_chunks, int frames, const float* src_l, const float* src_r,
+                       float* dst_l, float* dst_r, int batch, void* stream) {
+    dim3 grid((p.n + 1023) / 1024, batch);
+    fifo_ingest_kernel<<<grid, 256, 0, (cudaStream_t) stream>>>(d_chunks, frames, p.n, p.channels, src_l, src_r, dst_l, dst_r);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "fifo ingest kernel launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+}  // namespace glb

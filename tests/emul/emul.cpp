@@ -89,7 +89,7 @@ emul_chan* emul_chan_new(const glava_b200_params* p) {
 }
 void emul_chan_free(emul_chan* c) { delete c; }
 
-// mirrors spectrum_kernel's epilogue + K5 (kernels.cu) for one plane
+// mirrors spectrum_kernel's epilogue + K5 (spectrum_kernels.cu) for one plane
 int emul_chan_update(emul_chan* c, const glava_b200_params* pp, const float* pcm, int is_fft, float* spec, uint16_t* tex) {
     const glava_b200_params& p = *pp;
     const int N = p.n, F = p.avg_frames;
