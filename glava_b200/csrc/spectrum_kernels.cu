@@ -45,7 +45,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // spectrum kernel
 template <int LOG2N> struct SpecCfg {
     static constexpr int N = 1 << LOG2N, M = N / 2;
-    static constexpr int T = (M / 8 < 128) ? 128 : ((M / 8 > 512) ? 512 : M / 8);
+    static constexpr int T = (M / 8 < 128) ? 128 : ((M / 8 > 512) ? 512 : M / 8);   // (1024 threads at N = 16384 was measured 2x slower)
     static constexpr int BUF_CPX = fft_padded_size(M);
     // cpx buffer (also the raw-PCM staging area, N floats = M cpx) | u16 av[N] | mbarrier
     static constexpr int OFF_AV  = ((BUF_CPX * 8 + 15) / 16) * 16;
