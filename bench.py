@@ -196,6 +196,7 @@ def main():
         r.update_device(dev_l[i % nsnap].data_ptr(), dev_r[i % nsnap].data_ptr(), True)
     r.sync()
     sampler = ClockSampler(local); sampler.start()
+    t_sampler = time.perf_counter()
     time.sleep(0.25)
     r.set_timing(True)
     launches0 = r.launch_count
@@ -252,8 +253,16 @@ def main():
     r.sync()
     barrier()
     ms_fifo = max_over_ranks(e4.elapsed_time(e5))
+    # nvidia-smi samples every 100 ms and short runs (small --steps) end sooner than that: keep the SAME load
+    # running, untimed, until the sampler has seen about 2 s of it, so the clocks line describes the load
+    soak = 0
+    while time.perf_counter() - t_sampler < 2.25:
+        for i in range(16):
+            r.update_device(dev_l[i % nsnap].data_ptr(), dev_r[i % nsnap].data_ptr(), True)
+        r.sync(); soak += 16
     time.sleep(0.1)
     clocks = sampler.stop()
+    clocks["untimed_soak_steps"] = soak
     frame[:] = frame_pinned
     checksum = int(frame.astype(np.uint32).sum())
 
