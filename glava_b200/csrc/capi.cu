@@ -65,6 +65,7 @@ struct glava_b200 {
     double* d_window; float* d_twiddle; void* d_rowtab; int* d_need; int need_count;
     TapEntry* d_tap_tab; int* d_tap_cnt; float* d_tap_wsum; int tap_max; int epi_n;
     void* d_geo; int geo_box[4];   // polar geometry cache (radial / circle), see raster_kernels.cu
+    uint32_t* d_texmm;             // circle: per-plane {min, max} of the sampled texture, refreshed before each raster
     // state + outputs
     float* d_spec; float* d_applied; float* d_ring_f;
     uint16_t* d_gr_store; uint16_t* d_ring_u; uint16_t* d_tex;
@@ -322,7 +323,8 @@ static int build(glava_b200* r) {
         }
     }
     ALLOC(r->d_tex, 2 * planes * n * 2, true);
-    ALLOC(r->d_av, planes * n * 2, true);          // double-buffered: spectrum i+1 writes one half while raster i reads the other
+    ALLOC(r->d_av, planes * n * 2, true);
+    ALLOC(r->d_texmm, planes * 2 * sizeof(uint32_t), true);          // double-buffered: spectrum i+1 writes one half while raster i reads the other
     ALLOC(r->d_rowtab, (size_t) p.h * 8, true);
     // framebuffers: [slots][h][w] RGBA8
     size_t frame = (size_t) p.w * p.h * 4;
@@ -364,7 +366,7 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     r->d_window = nullptr; r->d_twiddle = nullptr; r->d_rowtab = nullptr; r->d_need = nullptr; r->need_count = 0;
     r->d_tap_tab = nullptr; r->d_tap_cnt = nullptr; r->d_tap_wsum = nullptr; r->tap_max = 0; r->epi_n = 0;
     r->d_geo = nullptr; r->geo_box[0] = r->geo_box[1] = r->geo_box[2] = r->geo_box[3] = 0;
-    r->d_spec = r->d_applied = r->d_ring_f = nullptr; r->d_gr_store = r->d_ring_u = r->d_tex = nullptr; r->d_av = nullptr; r->d_fb = nullptr;
+    r->d_spec = r->d_applied = r->d_ring_f = nullptr; r->d_gr_store = r->d_ring_u = r->d_tex = nullptr; r->d_av = nullptr; r->d_texmm = nullptr; r->d_fb = nullptr;
     for (int i = 0; i < 2; ++i) { r->d_pcm[i][0] = r->d_pcm[i][1] = nullptr; r->ev_copied[i] = r->ev_free[i] = nullptr; }
     r->stage_cur = 0; r->copy_stream = nullptr;
     r->updates = 0; r->launches = 0; r->timing = false;
@@ -484,6 +486,12 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
     ra.rowtab = (p.module == GLAVA_B200_MOD_BARS || p.module == GLAVA_B200_MOD_GRAPH) ? r->d_rowtab : nullptr;
     ra.batch = r->batch; ra.slots = r->slots; ra.stream0 = 0;
     ra.geo = r->d_geo; ra.gx0 = r->geo_box[0]; ra.gy0 = r->geo_box[1]; ra.gw = r->geo_box[2]; ra.gh = r->geo_box[3];
+    ra.texmm = nullptr;
+    if (p.module == GLAVA_B200_MOD_CIRCLE && r->d_geo && !getenv("GLAVA_B200_NO_TEXMM")) {
+        if ((rc = launch_texmm(p, ra.tex, r->d_texmm, r->batch * 2, r->stream)) != 0) return rc;
+        ++r->launches;
+        ra.texmm = r->d_texmm;
+    }
     if (r->timing && (rc = timing_mark(r->ev_ras, r->stream)) != 0) return rc;
     if ((rc = launch_raster(p, ra, r->stream)) != 0) return rc;
     if (r->timing && (rc = timing_mark(r->ev_ras, r->stream)) != 0) return rc;

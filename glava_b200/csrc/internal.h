@@ -66,6 +66,7 @@ struct RasterArgs {
     // CircleGeo, 16 bytes each) over the bounding box of the disc that can be non-zero; may be null
     const void* geo;
     int       gx0, gy0, gw, gh;  // box origin and size in pixels (gx0, gw multiples of 4)
+    const uint32_t* texmm;       // circle: [batch*2][2] {min, max} texel of each plane of `tex` (may be null)
 };
 
 // ---- kernel launchers (spectrum_kernels.cu, raster_kernels.cu); `stream` is a cudaStream_t passed as void* ------------------
@@ -75,6 +76,7 @@ int launch_raster(const glava_b200_params& p, const RasterArgs& a, void* stream)
 int launch_bars_rowtab(const glava_b200_params& p, void* d_rowtab, void* stream);
 // geometry cache of the polar modules: box = {x0, y0, w, h}; returns bytes needed when d_geo == nullptr
 size_t polar_geo_box(const glava_b200_params& p, int box[4]);
+int launch_texmm(const glava_b200_params& p, const uint16_t* d_tex, uint32_t* d_out, int planes, void* stream);
 int launch_polar_geo(const glava_b200_params& p, void* d_geo, const int box[4], void* stream);
 int launch_fifo_ingest(const glava_b200_params& p, const int16_t* d_chunks, int frames, const float* src_l, const float* src_r,
                        float* dst_l, float* dst_r, int batch, void* stream);

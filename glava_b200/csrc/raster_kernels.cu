@@ -301,8 +301,20 @@ raster_circle_kernel(const __grid_constant__ RasterArgs a, const __grid_constant
     uint32_t* fb = reinterpret_cast<uint32_t*>(a.fb) + (size_t) (stream % a.slots) * p.w * p.h;
     const int tx0 = blockIdx.x * CIRCLE_TW;
     const float cx = (float) (p.w / 2), cy = (float) (p.h / 2);
-    const float reach = circle_reach(p);
-    const float inner = p.circle_radius - p.circle_line / 2.0f - 2.0f;
+    // Static bounds of the annulus that can be lit, tightened per stream: a pixel is lit only if
+    // d - C_RADIUS lies within [min(v) - C_LINE/2, max(v) + C_LINE/2] (circle/1.frag:72-80; v = AMPLIFY * texel over
+    // the three fetched texels, 0 for out-of-range fetches), so the stream's texel range bounds its annulus.
+    float reach = circle_reach(p);
+    float inner = p.circle_radius - p.circle_line / 2.0f - 2.0f;
+    if (a.texmm) {
+        const uint32_t* mm = a.texmm + (size_t) stream * 4;             // {min, max} of plane l, {min, max} of plane r
+        const float f0 = from16(min(__ldg(mm + 0), __ldg(mm + 2))) * p.circle_amplify;
+        const float f1 = from16(max(__ldg(mm + 1), __ldg(mm + 3))) * p.circle_amplify;
+        const float vlo = fminf(fminf(f0, f1), 0.0f), vhi = fmaxf(fmaxf(f0, f1), 0.0f);
+        const float hl3 = fabsf(p.circle_line) / 2.0f + 3.0f;
+        reach = fminf(reach, p.circle_radius + vhi + hl3);
+        if (!p.circle_fill) inner = fmaxf(inner, p.circle_radius + vlo - hl3);
+    }
     const float bx0 = (float) (tx0 - 1) - cx, bx1 = (float) (tx0 + CIRCLE_TW) - cx;
     const float nx = (bx0 > 0.0f) ? bx0 : ((bx1 < 0.0f) ? -bx1 : 0.0f);
     const float fxm = fmaxf(fabsf(bx0), fabsf(bx1));
@@ -348,9 +360,13 @@ raster_circle_kernel(const __grid_constant__ RasterArgs a, const __grid_constant
                     const int bxi = tx0 + lx - 1 - a.gx0, byi = ty0 + ly - 1 - a.gy0;
                     uint32_t v = 0u;
                     if (bxi >= 0 && byi >= 0 && bxi < a.gw && byi < a.gh) {
-                        const int4 e = __ldg(geo + (size_t) byi * a.gw + bxi);
-                        CircleGeo g; g.dR = __int_as_float(e.x); g.e0 = e.y; g.e1 = e.z; g.e2 = e.w;
-                        v = circle_stage1_c(cc, t.l, t.r, t.n, g);
+                        const float dx = (float) (tx0 + lx - 1) - cx, dy = (float) (ty0 + ly - 1) - cy;
+                        const float d2 = dx * dx + dy * dy;
+                        if (d2 <= reach * reach && !(inner > 0.0f && d2 < inner * inner)) {   // per-stream annulus
+                            const int4 e = __ldg(geo + (size_t) byi * a.gw + bxi);
+                            CircleGeo g; g.dR = __int_as_float(e.x); g.e0 = e.y; g.e1 = e.z; g.e2 = e.w;
+                            v = circle_stage1_c(cc, t.l, t.r, t.n, g);
+                        }
                     }
                     tile[ly][lx] = v;
                     lx += 256 - (CIRCLE_TW + 2); ly += 1;               // advance by 256 cells: 256 = 130 + 126
@@ -414,6 +430,28 @@ raster_radial_kernel(const __grid_constant__ RasterArgs a, const __grid_constant
         }
         store4(fb + (size_t) y * p.w, x, p.w, px);
     }
+}
+
+// per-plane {min, max} of the R16 texture the module samples (circle: bounds the stream's annulus)
+__global__ void texmm_kernel(const uint16_t* __restrict__ tex, int n, uint32_t* __restrict__ out) {
+    __shared__ uint32_t smin[8], smax[8];
+    const uint16_t* t = tex + (size_t) blockIdx.x * n;
+    uint32_t lo = 65535u, hi = 0u;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { const uint32_t v = t[i]; lo = min(lo, v); hi = max(hi, v); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int) (blockDim.x >> 5); ++w) { lo = min(lo, smin[w]); hi = max(hi, smax[w]); }
+        out[2 * blockIdx.x] = lo; out[2 * blockIdx.x + 1] = hi;
+    }
+}
+int launch_texmm(const glava_b200_params& p, const uint16_t* d_tex, uint32_t* d_out, int planes, void* stream) {
+    texmm_kernel<<<planes, 256, 0, (cudaStream_t) stream>>>(d_tex, p.n, d_out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "texmm kernel launch: %s", cudaGetErrorString(e));
+    return 0;
 }
 
 // ---- polar geometry cache ------------------------------------------------------------------------
@@ -483,6 +521,7 @@ int launch_polar_geo(const glava_b200_params& p, void* d_geo, const int box[4], 
 __global__ void __launch_bounds__(128)
 raster_radial_geo_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__ glava_b200_params p, int rows_per_cta) {
     __shared__ float vflat[RADIAL_MAX_BARS + 4];        // bar heights, index side * nk + k (== class code - 1)
+    __shared__ float vmax_s;                             // tallest bar of this stream
     const int stream = a.stream0 + blockIdx.z;
     const AudioTex t = make_tex(p, a.tex, stream);
     const int nk = p.radial_nbars / 2 + 2;               // k = int(|idx| / section) <= NBARS / 2 (+1 for rounding)
@@ -494,9 +533,26 @@ raster_radial_geo_kernel(const __grid_constant__ RasterArgs a, const __grid_cons
             vflat[i] = radial_bar_value(p, t, (side << 16) | k);
         }
         __syncthreads();
+        if (threadIdx.x < 32) {                          // tallest bar: nothing beyond C_RADIUS + vmax can be lit
+            float m = 0.0f;
+            for (int i = threadIdx.x; i < 2 * nk; i += 32) m = fmaxf(m, vflat[i]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (threadIdx.x == 0) vmax_s = m;
+        }
+        __syncthreads();
     }
     const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (x >= p.w) return;
+    // per-stream reach: a bar pixel is lit only if d - C_RADIUS <= v <= vmax; beyond that (and beyond the ring) the
+    // frame is 0 for THIS stream, so those quads skip the geometry loads (typical spectra reach a third of AMPLIFY)
+    const float rcull = band_live ? p.radial_radius + fmaxf(fmaxf(vmax_s, 0.0f), fabsf(p.radial_line)) + 2.0f : 0.0f;
+    const float ccx = (float) (p.w / 2) - p.radial_off_x, ccy = (float) (p.h / 2) - p.radial_off_y;
+    float qdx; {
+        const float dxa = (float) x - ccx, dxb = (float) (x + 4) - ccx;          // pixel centres are at +0.5: [x, x+4) covers them
+        qdx = (dxa > 0.0f) ? dxa : ((dxb < 0.0f) ? -dxb : 0.0f);
+        qdx = fmaxf(qdx - 1.0f, 0.0f);
+    }
     uint32_t* fb = reinterpret_cast<uint32_t*>(a.fb) + (size_t) (stream % a.slots) * p.w * p.h;
     const size_t npx = (size_t) a.gw * a.gh;
     const int4* __restrict__ geo = reinterpret_cast<const int4*>(a.geo);                    // full entries
@@ -510,7 +566,8 @@ raster_radial_geo_kernel(const __grid_constant__ RasterArgs a, const __grid_cons
     for (int y = y0; y < y1; ++y) {
         uint32_t px[4] = { 0u, 0u, 0u, 0u };
         const int byi = y - a.gy0;
-        if (col_live && byi >= 0 && byi < a.gh) {
+        const float qdy = fmaxf(fabsf((float) y + 0.5f - ccy) - 1.0f, 0.0f);
+        if (col_live && byi >= 0 && byi < a.gh && qdx * qdx + qdy * qdy <= rcull * rcull) {
             const size_t at = (size_t) byi * a.gw + bxi;
             // codes and {lit, dR} are fetched together (independent addresses): one L2 round trip per
             // row instead of two dependent ones — the row loop is latency x occupancy bound

@@ -125,6 +125,27 @@ def test_polar_geometry_cache_equals_direct_evaluation(orc_pm, module, monkeypat
         assert np.array_equal(frames[0][s], want) and np.array_equal(frames[1][s], want)
 
 
+@pytest.mark.parametrize("module,over", [("radial", {}), ("radial", dict(radial_amplify=-120.0)), ("circle", {}),
+                                         ("circle", dict(circle_fill=1)), ("circle", dict(circle_amplify=-150.0)),
+                                         ("circle", dict(circle_line=9.0))])
+def test_polar_per_stream_reach_cull(orc_pm, module, over, built):
+    """radial / circle skip the cells beyond what THIS stream's largest (and, for circle, smallest) value can
+    light.  Streams whose values sit in narrow, different bands exercise every bound of that cull."""
+    p = g.default_params(module, n=1024, w=800, h=600)
+    for k, v in over.items():
+        setattr(p, k, v)
+    op = params_from(p)
+    rng = np.random.default_rng(5)
+    bands = [(0, 1), (0, 700), (3000, 3400), (20000, 21000), (64000, 65535), (100, 40000)]
+    tl = np.stack([rng.integers(lo, hi + 1, 1024).astype(np.uint16) for lo, hi in bands])
+    tr = np.stack([rng.integers(lo, hi + 1, 1024).astype(np.uint16) for lo, hi in reversed(bands)])
+    with g.Renderer(p, batch=len(bands)) as r:
+        r.raster_textures(tl, tr)
+        for s in range(len(bands)):
+            want = orc_pm.raster(op, tl[s], tr[s])
+            assert np.array_equal(r.readback(s), want), (module, over, s)
+
+
 def test_tap_table_equals_direct_k5(built, monkeypatch):
     """lazy K5 runs from a precomputed (index, weight) table; GLAVA_B200_NO_TAPTAB=1 evaluates the weights
     in the kernel.  Same textures at the sampled texels, hence same frames."""
