@@ -42,6 +42,8 @@ class Params(C.Structure):
         ("wave_amplify", C.c_float), ("wave_outline", C.c_float * 4),
         ("rate_request", C.c_int), ("samplesize_request", C.c_int),
         ("fb_slots", C.c_int), ("lazy_smooth", C.c_int),
+        ("bufscale", C.c_int), ("interpolate", C.c_int), ("fr", C.c_float), ("transform_smooth", C.c_int),
+        ("smooth_distance", C.c_float), ("smooth_ratio", C.c_float),
     ]
 
     def copy(self):
@@ -103,6 +105,8 @@ def lib():
     L.glava_b200_cuda_stream.restype = vp
     L.glava_b200_smooth_pass.argtypes = [vp, vp, vp, i32]
     L.glava_b200_raster_textures.argtypes = [vp, vp, vp]
+    L.glava_b200_transform_smooth.argtypes = [vp, vp, i32]
+    L.glava_b200_spectrum_size.argtypes = [vp]
     L.glava_b200_launch_count.argtypes = [vp]
     L.glava_b200_launch_count.restype = C.c_uint64
     L.glava_b200_set_abort_hook.argtypes = [vp]
@@ -178,6 +182,7 @@ class Renderer:
         _check(self._L.glava_b200_get_params(self._h, C.byref(self.params)))
         self.batch = int(batch)
         self.device = int(device)
+        self.nsz = int(self._L.glava_b200_spectrum_size(self._h))      # params.n / bufscale: spectrum / texture entries
 
     # -- rd_update ---------------------------------------------------------------------------------
     def update(self, lb, rb=None, modified=True):
@@ -224,25 +229,32 @@ class Renderer:
         _check(self._L.glava_b200_readback_async(self._h, int(stream), out.ctypes.data))
 
     def spectrum(self):
-        l = np.empty((self.batch, self.params.n), dtype=np.float32); r = np.empty_like(l)
+        l = np.empty((self.batch, self.nsz), dtype=np.float32); r = np.empty_like(l)
         _check(self._L.glava_b200_spectrum(self._h, l.ctypes.data, r.ctypes.data))
         return l, r
 
     def textures(self):
-        l = np.empty((self.batch, self.params.n), dtype=np.uint16); r = np.empty_like(l)
+        l = np.empty((self.batch, self.nsz), dtype=np.uint16); r = np.empty_like(l)
         _check(self._L.glava_b200_textures(self._h, l.ctypes.data, r.ctypes.data))
         return l, r
 
     def smooth_pass(self, tex):
         tex = np.ascontiguousarray(tex, dtype=np.uint16)
-        assert tex.ndim == 2 and tex.shape[1] == self.params.n
+        assert tex.ndim == 2 and tex.shape[1] == self.nsz
         out = np.empty_like(tex)
         _check(self._L.glava_b200_smooth_pass(self._h, tex.ctypes.data, out.ctypes.data, tex.shape[0]))
         return out
 
+    def transform_smooth(self, planes):
+        """transform_smooth (render.c:694-718) on host float32 [count][nsz]; returns the transformed copy"""
+        b = np.array(planes, dtype=np.float32, copy=True)
+        assert b.ndim == 2 and b.shape[1] == self.nsz
+        _check(self._L.glava_b200_transform_smooth(self._h, b.ctypes.data, b.shape[0]))
+        return b
+
     def raster_textures(self, tex_l, tex_r=None):
         tex_l = np.ascontiguousarray(tex_l, dtype=np.uint16)
-        assert tex_l.shape == (self.batch, self.params.n)
+        assert tex_l.shape == (self.batch, self.nsz)
         rp = None
         if tex_r is not None:
             tex_r = np.ascontiguousarray(tex_r, dtype=np.uint16)

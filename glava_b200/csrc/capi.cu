@@ -46,7 +46,18 @@ bool has_error() { return g_has_error; }
 using namespace glb;
 
 struct glava_b200 {
-    glava_b200_params p;
+    glava_b200_params p;        // EFFECTIVE parameters the kernels run with: n = setbufsize / setbufscale, accel_fft
+                                // cleared when a transform follows "fft" (render.c:2143-2154)
+    glava_b200_params p_user;   // as given (glava_b200_get_params)
+    int n_in;                   // setbufsize: floats per channel the caller hands to glava_b200_update
+    bool post_chain;            // transform_smooth and / or keyframe lerp: the spectrum kernel stops at the float chain
+                                // result; upload + K5 run as separate kernels
+    bool interp_on;             // keyframe interpolation active (render.c:1761-1763, 2161-2168)
+    int  kcounter;              // frames since the last modified update (render.c:2380-2383)
+    float* d_scaled[2];         // bufscale output [batch][n] x {l, r}
+    float* d_key[3]; int key_start, key_end;   // keyframe buffers [batch*2][n] (start, end, the one being written)
+    float* d_spec_cur;          // latest post-transform buffer (glava_b200_spectrum)
+    void* d_ts_tab; int ts_asz, ts_lim;        // transform_smooth {smin, smax} table
     int batch, device, slots;
     cudaStream_t stream;        // raster kernels, read-backs (the stream glava_b200_cuda_stream returns)
     cudaStream_t spec_stream;   // spectrum kernels + FIFO ingest, lowest priority: the latency-bound spectrum
@@ -79,6 +90,18 @@ struct glava_b200 {
     std::vector<cudaEvent_t> ev_spec; // pairs around each spectrum launch (spec_stream)
     std::vector<cudaEvent_t> ev_ras;  // pairs around each raster launch (stream)
 };
+
+// effective parameters and mode flags from the user's parameters
+static void derive(glava_b200* r) {
+    r->p = r->p_user;
+    r->n_in = r->p_user.n;
+    r->p.n = r->p_user.n / r->p_user.bufscale;
+    const bool is_fft = r->p.module != GLAVA_B200_MOD_WAVE;
+    if (r->p.transform_smooth && is_fft) r->p.accel_fft = 0;
+    const float fr = r->p.fr > 0.0f ? r->p.fr : r->p.ur;
+    r->interp_on = r->p.interpolate && !(r->p.accel_fft && is_fft) && (r->p.ur / fr) <= 0.9f;
+    r->post_chain = r->p.transform_smooth || r->interp_on;
+}
 
 static int dev_alloc(glava_b200* r, void** out, size_t bytes, bool zero) {
     if (bytes == 0) bytes = 16;
@@ -189,7 +212,29 @@ static int build_tables(glava_b200* r) {
     dev_free(r, r->d_need); dev_free(r, r->d_tap_tab); dev_free(r, r->d_tap_cnt); dev_free(r, r->d_tap_wsum); dev_free(r, r->d_geo);
     r->d_need = nullptr; r->need_count = 0; r->d_tap_tab = nullptr; r->d_tap_cnt = nullptr; r->d_tap_wsum = nullptr;
     r->tap_max = 0; r->epi_n = 0; r->d_geo = nullptr; r->geo_box[0] = r->geo_box[1] = r->geo_box[2] = r->geo_box[3] = 0;
-    if (p.lazy_smooth) {
+    if (p.transform_smooth) {
+        // transform_smooth's sampling window of output t (render.c:700-707) depends on t and the parameters only:
+        // evaluated here once, with the same libm calls and types as the reference (log -> float, powf, floor, ceil)
+        const double E = 2.7182818284590452353;                              // render.c:692
+        const int sz = p.n;
+        int asz = (int) ceil(sz / p.smooth_ratio);
+        if (asz > sz) asz = sz;
+        std::vector<int2> tab((size_t) sz);
+        int lim = asz;
+        for (int t = 0; t < asz; ++t) {
+            float db = log(t);
+            float lo = db - p.smooth_distance; if (!(lo > 0)) lo = 0;
+            int smin = (int) floor(powf(E, lo));
+            int smax = (int) ceil(powf(E, db + p.smooth_distance));
+            if (smax > sz - 1) smax = sz - 1;
+            tab[t] = make_int2(smin, smax);
+            if (smax + 1 > lim) lim = smax + 1;
+        }
+        r->ts_asz = asz; r->ts_lim = lim;
+        CU(cudaMemcpyAsync(r->d_ts_tab, tab.data(), (size_t) sz * sizeof(int2), cudaMemcpyHostToDevice, r->stream));
+        CU(cudaStreamSynchronize(r->stream));
+    }
+    if (p.lazy_smooth && !r->post_chain) {
         std::vector<int> lists[2];
         if (build_need_list(p, lists)) {
             size_t cnt = lists[0].size() > lists[1].size() ? lists[0].size() : lists[1].size();
@@ -281,14 +326,22 @@ static int build(glava_b200* r) {
     int rc;
 #define ALLOC(ptr, bytes, zero) if ((rc = dev_alloc(r, (void**) &(ptr), (bytes), (zero))) != 0) return rc
     CU(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
+    const size_t n_in = (size_t) r->n_in;
     for (int i = 0; i < 2; ++i) {
-        ALLOC(r->d_pcm[i][0], (size_t) r->batch * n * 4, true); ALLOC(r->d_pcm[i][1], (size_t) r->batch * n * 4, true);
+        ALLOC(r->d_pcm[i][0], (size_t) r->batch * n_in * 4, true); ALLOC(r->d_pcm[i][1], (size_t) r->batch * n_in * 4, true);
         CU(cudaEventCreateWithFlags(&r->ev_copied[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&r->ev_free[i], cudaEventDisableTiming));
     }
-    for (int i = 0; i < 2; ++i) for (int c = 0; c < 2; ++c) ALLOC(r->d_ring[i][c], (size_t) r->batch * n * 4, true);
+    for (int i = 0; i < 2; ++i) for (int c = 0; c < 2; ++c) ALLOC(r->d_ring[i][c], (size_t) r->batch * n_in * 4, true);
+    if (r->p_user.bufscale > 1) { ALLOC(r->d_scaled[0], (size_t) r->batch * n * 4, true); ALLOC(r->d_scaled[1], (size_t) r->batch * n * 4, true); }
+    if (r->interp_on) {
+        for (int i = 0; i < 3; ++i) ALLOC(r->d_key[i], planes * n * 4, true);      // keyframes start at 0 (render.c:1681 calloc)
+        r->key_start = 0; r->key_end = 1;
+    }
+    if (r->p.transform_smooth) ALLOC(r->d_ts_tab, n * sizeof(int2), true);
     ALLOC(r->d_window, n * 8, false); ALLOC(r->d_twiddle, n * 4, false);
     ALLOC(r->d_spec, planes * n * 4, true);
+    r->d_spec_cur = r->d_spec;
     // gravity + average state: ONE allocation, so a single L2 access-policy window can cover it (below)
     char* state = nullptr; size_t state_bytes = 0;
     if (p.accel_fft) {
@@ -360,7 +413,10 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     }
     if (device < 0 || device >= ndev) { fail(GLAVA_B200_EINVAL, "device %d out of range (%d devices)", device, ndev); return nullptr; }
     glava_b200* r = new glava_b200();
-    r->p = *params; r->batch = batch; r->device = device;
+    r->p_user = *params; r->batch = batch; r->device = device;
+    derive(r);
+    r->kcounter = 0; r->d_scaled[0] = r->d_scaled[1] = nullptr; r->d_key[0] = r->d_key[1] = r->d_key[2] = nullptr;
+    r->key_start = 0; r->key_end = 1; r->d_spec_cur = nullptr; r->d_ts_tab = nullptr; r->ts_asz = r->ts_lim = 0;
     r->stream = nullptr; r->spec_stream = nullptr; r->tex_cur = 0; r->ring_cur = 0;
     for (int i = 0; i < 2; ++i) { r->ev_spec_done[i] = nullptr; r->ev_raster_done[i] = nullptr; } r->d_chunks = nullptr; r->chunks_cap = 0;
     r->d_window = nullptr; r->d_twiddle = nullptr; r->d_rowtab = nullptr; r->d_need = nullptr; r->need_count = 0;
@@ -396,24 +452,29 @@ int glava_b200_reconfigure(glava_b200* r, const glava_b200_params* params) {
     if (!r || !params) return fail(GLAVA_B200_EINVAL, "glava_b200_reconfigure: null argument");
     int rc = validate_params(params);
     if (rc) return rc;
-    const glava_b200_params& o = r->p;
+    const glava_b200_params& o = r->p_user;
+    glava_b200 probe; probe.p_user = *params; derive(&probe);
     if (params->n != o.n || params->w != o.w || params->h != o.h || params->module != o.module || params->accel_fft != o.accel_fft ||
-        params->avg_frames != o.avg_frames || params->fb_slots != o.fb_slots)
-        return fail(GLAVA_B200_EINVAL, "glava_b200_reconfigure: setbufsize, geometry, module, setaccelfft, setavgframes and fb_slots "
-                                       "size the device state and cannot change on a live renderer; create a new one");
+        params->avg_frames != o.avg_frames || params->fb_slots != o.fb_slots || params->bufscale != o.bufscale ||
+        params->transform_smooth != o.transform_smooth || probe.interp_on != r->interp_on)
+        return fail(GLAVA_B200_EINVAL, "glava_b200_reconfigure: setbufsize, setbufscale, geometry, module, setaccelfft, setavgframes, "
+                                       "fb_slots, the \"smooth\" transform and whether interpolation is active size the device "
+                                       "state and cannot change on a live renderer; create a new one");
     CU(cudaSetDevice(r->device));
     CU(cudaStreamSynchronize(r->spec_stream));
     CU(cudaStreamSynchronize(r->stream));
-    r->p = *params;
+    r->p_user = *params;
+    derive(r);
     return build_tables(r);
 }
 
 int glava_b200_get_params(const glava_b200* r, glava_b200_params* out) {
     if (!r || !out) return fail(GLAVA_B200_EINVAL, "null argument");
-    *out = r->p; return 0;
+    *out = r->p_user; return 0;
 }
 int glava_b200_batch(const glava_b200* r) { return r ? r->batch : 0; }
 const char* glava_b200_module_name(const glava_b200* r) { return r ? module_name(r->p.module) : "?"; }
+int glava_b200_spectrum_size(const glava_b200* r) { return r ? r->p.n : 0; }
 const void* glava_b200_framebuffer_device(const glava_b200* r) { return r ? r->d_fb : nullptr; }
 void* glava_b200_cuda_stream(const glava_b200* r) { return r ? (void*) r->stream : nullptr; }
 uint64_t glava_b200_launch_count(const glava_b200* r) { return r ? r->launches : 0; }
@@ -439,16 +500,30 @@ static int sync_all(glava_b200* r) {
 //                          texture half it overwrites)
 //   raster(i)   waits for: spectrum(i)
 // so raster(i) and spectrum(i+1) run concurrently: one is HBM-store bound, the other latency bound.
-static int run_update(glava_b200* r, const float* d_l, const float* d_r, int modified) {
+static int run_update(glava_b200* r, const float* d_l, const float* d_r, int modified, bool raster_only = false) {
     const glava_b200_params& p = r->p;
     int rc;
+    const bool new_tex = !raster_only && (modified || r->interp_on);   // an interpolated frame has a new texture without new audio
+    const int planes = r->batch * 2;
+    const size_t total = (size_t) planes * p.n;
+    if (new_tex) CU(cudaStreamWaitEvent(r->spec_stream, r->ev_raster_done[r->tex_cur ^ 1], 0));
+    if (modified && r->p_user.bufscale > 1) {
+        const int chans = p.module == GLAVA_B200_MOD_WAVE ? 1 : 2;
+        if ((rc = launch_bufscale(d_l, d_r, r->d_scaled[0], r->d_scaled[1], r->batch, r->n_in, r->p_user.bufscale, chans, r->spec_stream)) != 0) return rc;
+        ++r->launches;
+        d_l = r->d_scaled[0]; d_r = r->d_scaled[1];
+    }
+    float* chain_out = r->d_spec;                         // where the float chain result of this update goes
+    if (r->interp_on) {
+        int nxt = 0; while (nxt == r->key_start || nxt == r->key_end) ++nxt;
+        chain_out = r->d_key[nxt];
+    }
     if (modified) {
         const int b = r->tex_cur ^ 1;
-        CU(cudaStreamWaitEvent(r->spec_stream, r->ev_raster_done[b], 0));
         SpectrumArgs a;
         memset(&a, 0, sizeof(a));
         a.pcm_l = d_l; a.pcm_r = d_r; a.window = r->d_window; a.twiddle = r->d_twiddle;
-        a.spec = r->d_spec; a.applied = r->d_applied; a.ring_f = r->d_ring_f;
+        a.spec = chain_out; a.skip_tex = r->post_chain ? 1 : 0; a.applied = r->d_applied; a.ring_f = r->d_ring_f;
         a.gr_store = r->d_gr_store; a.ring_u = r->d_ring_u; a.tex = tex_half(r, b);
         a.need = (p.lazy_smooth && r->d_need) ? r->d_need : nullptr; a.need_count = r->need_count;
         a.tap_tab = a.need ? r->d_tap_tab : nullptr; a.tap_cnt = r->d_tap_cnt; a.tap_wsum = r->d_tap_wsum; a.tap_max = r->tap_max;
@@ -466,7 +541,7 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
         if (r->timing && (rc = timing_mark(r->ev_spec, r->spec_stream)) != 0) return rc;
         // full-plane smoothing (every texel wanted): the spectrum kernel exports the pre-smoothing texture and
         // a second kernel smooths all planes, sharing the tap weights between planes
-        const bool split_k5 = p.smooth_pass && !a.need && !getenv("GLAVA_B200_FUSED_K5");
+        const bool split_k5 = p.smooth_pass && !a.need && !r->post_chain && !getenv("GLAVA_B200_FUSED_K5");
         a.av_out = split_k5 ? r->d_av : nullptr;
         if ((rc = launch_spectrum(p, a, is_fft, r->spec_stream)) != 0) return rc;
         if (split_k5) {
@@ -474,11 +549,48 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
             if ((rc = launch_smooth_only(p, r->d_av, a.tex, r->batch * 2, r->spec_stream)) != 0) return rc;
             ++r->launches;
         }
-        if (r->timing && (rc = timing_mark(r->ev_spec, r->spec_stream)) != 0) return rc;
+        if (r->post_chain && p.transform_smooth) {                          // render.c:694-718, after the module's chain
+            if ((rc = launch_transform_smooth(chain_out, p.n, r->d_ts_tab, r->ts_asz, r->ts_lim, planes, r->spec_stream)) != 0) return rc;
+            ++r->launches;
+        }
+        if (!r->post_chain) {
+            if (r->timing && (rc = timing_mark(r->ev_spec, r->spec_stream)) != 0) return rc;
+            CU(cudaEventRecord(r->ev_spec_done[b], r->spec_stream));
+            r->tex_cur = b;
+        }
+        ++r->launches; ++r->updates;
+        r->d_spec_cur = chain_out;
+    }
+    if (r->post_chain && new_tex) {
+        // R16 upload of the buffer this frame shows (render.c:2185) and K5 (render.c:2276-2303).  With keyframe
+        // interpolation that is the lerp of the two PREVIOUS post-transform buffers (render.c:1792-1809): the
+        // update just computed becomes visible one update later (rc.glsl:129-130).
+        const int b = r->tex_cur ^ 1;
+        uint16_t* dst = p.smooth_pass ? r->d_av : tex_half(r, b);
+        if (r->interp_on) {
+            const float fr = p.fr > 0.0f ? p.fr : p.ur;
+            const float uratio = p.ur / fr;                                   // render.c:1761
+            float mod = uratio * (float) r->kcounter;                         // render.c:1804
+            if (mod > 1.0f) mod = 1.0f;
+            rc = launch_upload(r->d_key[r->key_start], r->d_key[r->key_end], mod, dst, total, r->spec_stream);
+        } else {
+            rc = launch_upload(chain_out, nullptr, 0.0f, dst, total, r->spec_stream);
+        }
+        if (rc) return rc;
+        ++r->launches;
+        if (p.smooth_pass) {
+            if ((rc = launch_smooth_only(p, r->d_av, tex_half(r, b), planes, r->spec_stream)) != 0) return rc;
+            ++r->launches;
+        }
+        if (modified && r->timing && (rc = timing_mark(r->ev_spec, r->spec_stream)) != 0) return rc;
         CU(cudaEventRecord(r->ev_spec_done[b], r->spec_stream));
         r->tex_cur = b;
-        ++r->launches; ++r->updates;
+        if (r->interp_on && modified) {                                       // render.c:2347-2353: start <- end <- this update
+            int nxt = 0; while (nxt == r->key_start || nxt == r->key_end) ++nxt;
+            r->key_start = r->key_end; r->key_end = nxt;
+        }
     }
+    if (!raster_only) r->kcounter = modified ? 0 : r->kcounter + 1;           // render.c:2380-2383
     const int b = r->tex_cur;
     CU(cudaStreamWaitEvent(r->stream, r->ev_spec_done[b], 0));
     RasterArgs ra;
@@ -506,7 +618,7 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
 int glava_b200_update(glava_b200* r, const float* lb, const float* rb, size_t bsz, int modified) {
     clear_error();
     if (!r || !lb) return fail(GLAVA_B200_EINVAL, "glava_b200_update: null argument");
-    if (bsz != (size_t) r->p.n) return fail(GLAVA_B200_EINVAL, "glava_b200_update: bsz %zu != setbufsize %d", bsz, r->p.n);
+    if (bsz != (size_t) r->n_in) return fail(GLAVA_B200_EINVAL, "glava_b200_update: bsz %zu != setbufsize %d", bsz, r->n_in);
     CU(cudaSetDevice(r->device));
     size_t bytes = (size_t) r->batch * bsz * 4;
     const int b = r->stage_cur;
@@ -534,7 +646,7 @@ int glava_b200_update(glava_b200* r, const float* lb, const float* rb, size_t bs
 int glava_b200_update_device(glava_b200* r, const float* d_lb, const float* d_rb, size_t bsz, int modified) {
     clear_error();
     if (!r || !d_lb) return fail(GLAVA_B200_EINVAL, "glava_b200_update_device: null argument");
-    if (bsz != (size_t) r->p.n) return fail(GLAVA_B200_EINVAL, "glava_b200_update_device: bsz %zu != setbufsize %d", bsz, r->p.n);
+    if (bsz != (size_t) r->n_in) return fail(GLAVA_B200_EINVAL, "glava_b200_update_device: bsz %zu != setbufsize %d", bsz, r->n_in);
     if (((uintptr_t) d_lb & 15) || ((uintptr_t) d_rb & 15)) return fail(GLAVA_B200_EINVAL, "device PCM pointers must be 16-byte aligned");
     CU(cudaSetDevice(r->device));
     return run_update(r, d_lb, d_rb ? d_rb : d_lb, modified);
@@ -543,7 +655,7 @@ int glava_b200_update_device(glava_b200* r, const float* d_lb, const float* d_rb
 int glava_b200_ingest_fifo(glava_b200* r, const int16_t* chunks, int frames) {
     clear_error();
     if (!r || !chunks) return fail(GLAVA_B200_EINVAL, "glava_b200_ingest_fifo: null argument");
-    if (frames < 1 || frames > r->p.n) return fail(GLAVA_B200_EINVAL, "glava_b200_ingest_fifo: frames %d out of range", frames);
+    if (frames < 1 || frames > r->n_in) return fail(GLAVA_B200_EINVAL, "glava_b200_ingest_fifo: frames %d out of range", frames);
     CU(cudaSetDevice(r->device));
     size_t bytes = (size_t) r->batch * frames * 2 * sizeof(int16_t);
     if (bytes > r->chunks_cap) {
@@ -556,7 +668,7 @@ int glava_b200_ingest_fifo(glava_b200* r, const int16_t* chunks, int frames) {
     // ordered with the spectrum kernels (they read the rings): same stream
     CU(cudaMemcpyAsync(r->d_chunks, chunks, bytes, cudaMemcpyHostToDevice, r->spec_stream));
     int cur = r->ring_cur, nxt = cur ^ 1;
-    int rc = launch_fifo_ingest(r->p, r->d_chunks, frames, r->d_ring[cur][0], r->d_ring[cur][1],
+    int rc = launch_fifo_ingest(r->p_user, r->d_chunks, frames, r->d_ring[cur][0], r->d_ring[cur][1],
                                 r->d_ring[nxt][0], r->d_ring[nxt][1], r->batch, r->spec_stream);
     if (rc) return rc;
     ++r->launches;
@@ -638,7 +750,7 @@ int glava_b200_spectrum(glava_b200* r, float* out_l, float* out_r) {
     clear_error();
     if (!r) return fail(GLAVA_B200_EINVAL, "null argument");
     CU(cudaSetDevice(r->device));
-    return planes_to_host(r, r->d_spec, 4, out_l, out_r);
+    return planes_to_host(r, r->d_spec_cur, 4, out_l, out_r);
 }
 int glava_b200_textures(glava_b200* r, uint16_t* out_l, uint16_t* out_r) {
     clear_error();
@@ -678,7 +790,28 @@ int glava_b200_raster_textures(glava_b200* r, const uint16_t* tex_l, const uint1
     char* dst = (char*) tex_half(r, r->tex_cur);
     CU(cudaMemcpy2DAsync(dst, 2 * row, tex_l, row, row, (size_t) r->batch, cudaMemcpyHostToDevice, r->stream));
     if (tex_r) CU(cudaMemcpy2DAsync(dst + row, 2 * row, tex_r, row, row, (size_t) r->batch, cudaMemcpyHostToDevice, r->stream));
-    return run_update(r, nullptr, nullptr, 0);
+    return run_update(r, nullptr, nullptr, 0, true);
+}
+
+int glava_b200_transform_smooth(glava_b200* r, float* planes, int count) {
+    clear_error();
+    if (!r || !planes || count < 1) return fail(GLAVA_B200_EINVAL, "glava_b200_transform_smooth: bad arguments");
+    if (!r->p.transform_smooth) return fail(GLAVA_B200_EINVAL, "glava_b200_transform_smooth: the renderer was not created with transform_smooth");
+    CU(cudaSetDevice(r->device));
+    const size_t bytes = (size_t) count * r->p.n * 4;
+    float* d = nullptr;
+    CU(cudaMalloc((void**) &d, bytes));
+    int rc = 0;
+    do {
+        if (cudaMemcpyAsync(d, planes, bytes, cudaMemcpyHostToDevice, r->stream) != cudaSuccess) { rc = fail(GLAVA_B200_ECUDA, "H2D copy failed"); break; }
+        if ((rc = launch_transform_smooth(d, r->p.n, r->d_ts_tab, r->ts_asz, r->ts_lim, count, r->stream)) != 0) break;
+        ++r->launches;
+        if (cudaMemcpyAsync(planes, d, bytes, cudaMemcpyDeviceToHost, r->stream) != cudaSuccess) { rc = fail(GLAVA_B200_ECUDA, "D2H copy failed"); break; }
+        cudaError_t se = cudaStreamSynchronize(r->stream);
+        if (se != cudaSuccess) rc = fail(GLAVA_B200_ECUDA, "transform_smooth: %s", cudaGetErrorString(se));
+    } while (0);
+    cudaFree(d);
+    return rc;
 }
 
 }  // extern "C"

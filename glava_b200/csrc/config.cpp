@@ -98,6 +98,8 @@ void fill_defaults(glava_b200_params* p, int module) {
     p->wave_base_color[0] = 0.7f; p->wave_base_color[1] = 0.2f; p->wave_base_color[2] = 0.45f; p->wave_base_color[3] = 1;
     p->wave_outline[0] = p->wave_outline[1] = p->wave_outline[2] = 0.15f; p->wave_outline[3] = 1;
     p->fb_slots = 0; p->lazy_smooth = 0;
+    p->bufscale = 1; p->interpolate = 0; p->fr = 0.0f;                       // render.c:908, rc.glsl:131
+    p->transform_smooth = 0; p->smooth_distance = 0.01f; p->smooth_ratio = 4.0f;   // render.c:917-918
 }
 
 // ---- tiny expression evaluator for numeric #defines: + - * / ( ) literals PI TWOPI ---------
@@ -362,14 +364,24 @@ static bool apply_request(Loader& L, const std::vector<std::string>& t, const ch
     else if (name == "setsmoothfactor") { if (!need(1)) return false; p->smooth_factor = as_f(1); }
     else if (name == "setfftscale") { if (!need(1)) return false; p->fft_scale = as_f(1); }
     else if (name == "setfftcutoff") { if (!need(1)) return false; p->fft_cutoff = as_f(1); }
-    else if (name == "setbufscale") {
-        if (!need(1)) return false;
-        if (as_int(1) > 1) { fail(GLAVA_B200_ECONFIG, "setbufscale > 1 (deprecated in the reference) is not supported"); return false; }
-    }
-    else if (name == "setinterpolate") {
-        // CPU keyframe interpolation is force-disabled by the reference whenever accel_fft is
-        // active (render.c:2161-2168) and is off in the shipped rc.glsl:131; not implemented.
-        if (!need(1) || !as_b(1, &b)) return false;
+    else if (name == "setbufscale") { if (!need(1)) return false; p->bufscale = as_int(1); }          // render.c:1178
+    else if (name == "setinterpolate") { if (!need(1) || !as_b(1, &b)) return false; p->interpolate = b; }   // render.c:1207
+    else if (name == "setsmooth") { if (!need(1)) return false; p->smooth_distance = as_f(1); }       // render.c:1201
+    else if (name == "setsmoothratio") { if (!need(1)) return false; p->smooth_ratio = as_f(1); }     // render.c:1204
+    else if (name == "setframerate") { if (!need(1)) return false; if (as_int(1) > 0) p->fr = (float) as_int(1); }   // render.c:2361: pacing target
+    else if (name == "transform") {
+        // render.c:1218-1286.  The module fixes its own chain (fft [+gravity +avg] or window + wrange); the one
+        // transform a request can add on this path is "smooth", applied after that chain.
+        if (!need(2)) return false;
+        static const char* chain[] = { "window", "fft", "wrange", "avg", "gravity", nullptr };
+        bool known = false;
+        for (int i = 0; chain[i]; ++i) if (t[2] == chain[i]) known = true;
+        if (t[2] == "smooth") p->transform_smooth = 1;
+        else if (!known) {
+            fail(GLAVA_B200_ECONFIG, "Cannot add transformation '%s' to uniform '%s': transform function does not exist!",
+                 t[2].c_str(), t[1].c_str());
+            return false;
+        }
     }
     else if (name == "setbg" || name == "setbgf") {
         // clear colour: every module stage writes every pixel, so the clear never shows (blending
@@ -379,9 +391,9 @@ static bool apply_request(Loader& L, const std::vector<std::string>& t, const ch
         // window / desktop / pacing requests of the reference that have no meaning on this path
         static const char* ignored[] = { "setfloating", "setdecorated", "setfocused", "setmaximized", "setversion",
             "setshaderversion", "settitle", "setxwintype", "addxwinstate", "setclickthrough", "setsource", "setswap",
-            "setframerate", "setfullscreencheck", "setprintframes", "setforcegeometry", "setforceraised",
-            "setfullscreencheck", "timecycle", "settesteval", "setsmooth", "setsmoothratio", "nativeonly",
-            "uniform", "transform", nullptr };
+            "setfullscreencheck", "setprintframes", "setforcegeometry", "setforceraised",
+            "setfullscreencheck", "timecycle", "settesteval", "nativeonly",
+            "uniform", nullptr };
         bool known = false;
         for (int i = 0; ignored[i]; ++i) if (name == ignored[i]) known = true;
         if (!known) {
@@ -559,6 +571,10 @@ int validate_params(const glava_b200_params* p) {
     if (p->sample_mode < 0 || p->sample_mode > 2 || p->round_formula < 0 || p->round_formula > 2) return bad("sample mode / round formula");
     if (p->radial_nbars < 2) return bad("NBARS");
     if (!(p->bars_width + p->bars_gap > 0.0f)) return bad("BAR_WIDTH + BAR_GAP");
+    if (p->bufscale < 1 || p->n % p->bufscale || p->n / p->bufscale < 256 || ((p->n / p->bufscale) & (p->n / p->bufscale - 1)))
+        return bad("setbufsize / setbufscale must be a power of two >= 256");
+    if (p->fr < 0.0f) return bad("fr must be >= 0");
+    if (p->transform_smooth && !(p->smooth_ratio > 0.0f)) return bad("setsmoothratio must be > 0");
     return GLAVA_B200_OK;
 }
 

@@ -50,6 +50,7 @@ struct SpectrumArgs {
     const float* tap_wsum;      // [2][need_count]  sum of the weights in loop order
     int       tap_max;
     int       epi_n;            // lazy K5: number of leading bins whose gravity/average state can reach a sampled texel (0 = all)
+    int       skip_tex;         // 1: produce `spec` only (transform_smooth / keyframe lerp / upload / K5 follow as kernels)
     int       batch;
     unsigned long long update;  // number of modified updates before this one (ring cursor)
     double    avg_w_a[GLB_MAX_AVG_FRAMES];   // pipeline A weights, oldest first (render.c:661,766)
@@ -81,6 +82,11 @@ int launch_polar_geo(const glava_b200_params& p, void* d_geo, const int box[4], 
 int launch_fifo_ingest(const glava_b200_params& p, const int16_t* d_chunks, int frames, const float* src_l, const float* src_r,
                        float* dst_l, float* dst_r, int batch, void* stream);
 int spectrum_smem_bytes(int n);
+// chain_kernels.cu: optional stages of rd_update (bufscale, transform_smooth, keyframe lerp + R16 upload)
+int launch_bufscale(const float* in_l, const float* in_r, float* out_l, float* out_r, int batch, int n_in, int k,
+                    int channels, void* stream);
+int launch_transform_smooth(float* d_planes, int n, const void* d_tab, int asz, int lim, int count, void* stream);
+int launch_upload(const float* d_s, const float* d_e, float mod, uint16_t* d_out, size_t total, void* stream);
 
 }  // namespace glb
 

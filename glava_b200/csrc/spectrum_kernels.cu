@@ -256,6 +256,7 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
     __syncthreads();
     // `raw`/`buf` are dead from here on: let the TMA engine fetch the next unit's PCM during K5
     if (tid == 0 && u + (int) gridDim.x < units) issue_load(u + gridDim.x);
+    if (a.skip_tex) continue;                        // chain result only (`spec`): the texture is produced downstream
 
     // --- K5 smooth pass out of shared memory (render.c:2276-2303) ----------------------------------
     uint16_t* tex = a.tex + plane;

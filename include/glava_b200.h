@@ -96,6 +96,20 @@ typedef struct {
                                  K < batch = ring of K (stream s renders into slot s % K) */
     int   lazy_smooth;        /* 1: K5 evaluates only the texels the module samples (same pixels,
                                  texture read-back then holds only those texels); 0: all n texels */
+    /* optional stages of rd_update that the shipped configuration leaves off */
+    int   bufscale;           /* setbufscale (rc.glsl:236, deprecated): box-average `bufscale` PCM samples
+                                 before anything else (render.c:1765-1790); textures then have n / bufscale texels */
+    int   interpolate;        /* setinterpolate (rc.glsl:131): keyframe lerp between the last two post-transform
+                                 buffers (render.c:1792-1809, 2347-2353).  As in the reference it is inactive when
+                                 ur / fr > 0.9 (render.c:1761-1763) and for an fft module under setaccelfft
+                                 (render.c:2161-2168) */
+    float fr;                 /* glava_b200_update calls per second, the reference's measured gl->fr
+                                 (render.c:2386); setframerate when > 0; 0 = same as ur */
+    int   transform_smooth;   /* `#request transform <uniform> "smooth"` appended to the module's chain:
+                                 transform_smooth (render.c:694-718); forces the CPU-order chain (pipeline A,
+                                 render.c:2143-2154) */
+    float smooth_distance;    /* setsmooth       (render.c:917,1201) */
+    float smooth_ratio;       /* setsmoothratio  (render.c:918,1204) */
 } glava_b200_params;
 
 typedef struct glava_b200 glava_b200;    /* plays the role of struct glava_renderer (render.h:8-30) */
@@ -143,8 +157,9 @@ void  glava_b200_host_free(void* p);
  *   lb, rb : HOST, [batch][bsz] float32, ring contents oldest-first, exactly what glava.c:528-537
  *            memcpy's into lb/rb for one stream.  NOT modified (the reference transforms them in
  *            place, render.c:2140-2180).  rb is ignored by `wave` (audio_l only, wave/1.frag:7).
- *   bsz    : must equal params.n (bufscale is 1)
- *   modified: as rd_update's flag; 0 re-rasters the last spectrum (render.c:2268-2272)
+ *   bsz    : must equal params.n (setbufsize; with setbufscale k the spectrum has n / k entries)
+ *   modified: as rd_update's flag; 0 re-rasters the last spectrum (render.c:2268-2272), or, with keyframe
+ *            interpolation active, the next interpolated one
  * Copies H2D on a dedicated copy stream (double-buffered staging: the copy of update i+1 overlaps the
  * kernels of update i), runs the fused spectrum kernel and the module raster kernel on the handle's
  * stream.  Returns once the host buffers have been consumed (they may be reused immediately) and the
@@ -168,7 +183,9 @@ int glava_b200_readback(glava_b200* r, int stream, uint8_t* rgba);              
 int glava_b200_readback_async(glava_b200* r, int stream, uint8_t* rgba);        /* same, enqueued on the handle's stream:
                                                                                    rgba (pinned) is valid after glava_b200_sync */
 int glava_b200_spectrum(glava_b200* r, float* out_l, float* out_r);             /* HOST [batch][n]: pipeline-A result
-                                                                                   (accel_fft 0) or raw transform_fft output (1) */
+                                                                                   (accel_fft 0) or raw transform_fft output (1);
+                                                                                   n / bufscale entries per stream */
+int glava_b200_spectrum_size(const glava_b200* r);                              /* entries per channel of spectra / textures */
 int glava_b200_textures(glava_b200* r, uint16_t* out_l, uint16_t* out_r);       /* HOST [batch][n] R16 texels the module samples */
 const void* glava_b200_framebuffer_device(const glava_b200* r);                 /* DEVICE [fb_slots][h][w] RGBA8 */
 void* glava_b200_cuda_stream(const glava_b200* r);                              /* cudaStream_t, for event timing */
@@ -176,6 +193,7 @@ void* glava_b200_cuda_stream(const glava_b200* r);                              
 /* Stage-wise entry points (used by the parity tests; same kernels as the fused path). */
 int glava_b200_smooth_pass(glava_b200* r, const uint16_t* in, uint16_t* out, int count);      /* K5 on HOST [count][n] */
 int glava_b200_raster_textures(glava_b200* r, const uint16_t* tex_l, const uint16_t* tex_r);  /* HOST [batch][n] -> raster */
+int glava_b200_transform_smooth(glava_b200* r, float* planes, int count);                     /* transform_smooth in place on HOST [count][n] */
 
 /* Kernel launch counters since creation (bench.py `gpu_launches`). */
 uint64_t glava_b200_launch_count(const glava_b200* r);

@@ -383,6 +383,127 @@ void orc_chan_update(orc_chan* c, const orc_params* p, const float* pcm, int is_
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* optional stages of rd_update (off in the shipped configuration)                        */
+
+void orc_bufscale(const float* in, int n_in, int k, float* out) {           /* render.c:1765-1790 */
+    int nsz = n_in / k;
+    for (int t = 0; t < nsz; ++t) {
+        float accum = 0.0F;
+        for (int a = 0; a < k; ++a) accum += in[t * k + a];
+        accum /= (float) k;
+        out[t] = accum;
+    }
+}
+
+void orc_transform_smooth(float* b, int sz, float smooth_distance, float smooth_ratio) {   /* render.c:694-718 */
+    const double E = 2.7182818284590452353;                                  /* render.c:692 */
+    size_t asz = (size_t) ceil(sz / smooth_ratio);
+    for (int t = 0; t < (int) asz; ++t) {
+        float db = log(t), avg = 0;                                          /* log(0) = -inf at t = 0 */
+        float lo = db - smooth_distance; if (!(lo > 0)) lo = 0;              /* max(db - distance, 0) */
+        int smin = (int) floor(powf(E, lo));
+        int smax = (int) ceil(powf(E, db + smooth_distance));
+        if (smax > sz - 1) smax = sz - 1;
+        int count = 0;
+        for (int s = smin; s <= smax; ++s)
+            if (b[s]) { avg += b[s]; count++; }
+        avg /= count;                                                        /* 0/0 = NaN when nothing was summed */
+        b[t] = avg;
+    }
+}
+
+void orc_interp(const float* s, const float* e, int n, float ur, float fr, int kcounter, float* out) {
+    float uratio = ur / fr;                                                  /* render.c:1761 */
+    for (int t = 0; t < n; ++t) {
+        float mod = uratio * kcounter;                                       /* render.c:1804 */
+        if (mod > 1.0F) mod = 1.0F;
+        out[t] = s[t] + ((e[t] - s[t]) * mod);
+    }
+}
+
+struct orc_stream {
+    orc_params p;            /* effective: n = setbufsize / bufscale, accel_fft as the bind ends up using it */
+    orc_ext x;
+    int n_in, is_fft, post_chain, interp_on, kcounter;
+    orc_chan* ch[2];
+    float* key[2][2];        /* [channel][start, end] keyframes, render.c:1683-1689 */
+    float* last[2];          /* post-transform buffer of the last modified update (what lb / rb hold) */
+    uint16_t* tex[2];        /* texture of the previous frame (kept on unmodified frames) */
+    float* scaled; float* work;
+};
+
+orc_stream* orc_stream_new(const orc_params* p, const orc_ext* x) {
+    orc_stream* s = calloc(1, sizeof(*s));
+    s->p = *p; s->x = *x;
+    if (s->x.bufscale < 1) s->x.bufscale = 1;
+    s->n_in = p->n; s->p.n = p->n / s->x.bufscale;
+    s->is_fft = p->module != ORC_MOD_WAVE;
+    /* a transform after "fft" makes the bind fall back to the CPU chain (render.c:2143-2154) */
+    if (s->x.transform_smooth && s->is_fft) s->p.accel_fft = 0;
+    /* interpolation is forced off when the fft chain is pushed to the GPU passes (render.c:2161-2168)
+       and when the update rate is close to the frame rate (render.c:1761-1763) */
+    float fr = s->x.fr > 0 ? s->x.fr : p->ur;
+    s->x.fr = fr;
+    s->interp_on = s->x.interpolate && !(s->p.accel_fft && s->is_fft) && (p->ur / fr) <= 0.9F;
+    s->post_chain = s->x.transform_smooth || s->interp_on;
+    size_t n = (size_t) s->p.n;
+    for (int c = 0; c < 2; ++c) {
+        s->ch[c] = orc_chan_new(&s->p);
+        s->key[c][0] = calloc(n, sizeof(float)); s->key[c][1] = calloc(n, sizeof(float));
+        s->last[c] = calloc(n, sizeof(float)); s->tex[c] = calloc(n, sizeof(uint16_t));
+    }
+    s->scaled = calloc((size_t) s->n_in, sizeof(float)); s->work = calloc(n, sizeof(float));
+    return s;
+}
+void orc_stream_free(orc_stream* s) {
+    for (int c = 0; c < 2; ++c) {
+        orc_chan_free(s->ch[c]); free(s->key[c][0]); free(s->key[c][1]); free(s->last[c]); free(s->tex[c]);
+    }
+    free(s->scaled); free(s->work); free(s);
+}
+int orc_stream_n(const orc_stream* s) { return s->p.n; }
+
+void orc_stream_update(orc_stream* s, const float* lb, const float* rb, int modified,
+                       float* spec_l, float* spec_r, uint16_t* tex_l, uint16_t* tex_r) {
+    const int n = s->p.n;
+    const float* in[2] = { lb, rb };
+    float* spec[2] = { spec_l, spec_r };
+    uint16_t* texo[2] = { tex_l, tex_r };
+    uint16_t* pre = malloc(sizeof(uint16_t) * (size_t) n);
+    for (int c = 0; c < 2; ++c) {
+        /* keyframe lerp first, from the keyframes of the PREVIOUS updates (render.c:1792-1809) */
+        if (s->interp_on)
+            orc_interp(s->key[c][0], s->key[c][1], n, s->p.ur, s->x.fr, s->kcounter, s->work);
+        if (modified) {
+            const float* src = in[c];
+            if (s->x.bufscale > 1) { orc_bufscale(in[c], s->n_in, s->x.bufscale, s->scaled); src = s->scaled; }
+            if (!s->post_chain) {
+                orc_chan_update(s->ch[c], &s->p, src, s->is_fft, s->last[c], s->tex[c]);
+            } else {
+                orc_params q = s->p; q.smooth_pass = 0;                     /* chain only; upload + K5 below */
+                orc_chan_update(s->ch[c], &q, src, s->is_fft, s->last[c], pre);
+                if (s->x.transform_smooth)
+                    orc_transform_smooth(s->last[c], n, s->x.smooth_distance, s->x.smooth_ratio);
+            }
+        }
+        if (s->post_chain && (modified || s->interp_on)) {
+            const float* up = s->interp_on ? s->work : s->last[c];          /* render.c:2185 */
+            for (int t = 0; t < n; ++t) pre[t] = unorm16(up[t]);
+            if (s->p.smooth_pass) orc_smooth_pass(&s->p, pre, s->tex[c]);
+            else memcpy(s->tex[c], pre, sizeof(uint16_t) * (size_t) n);
+        }
+        if (s->interp_on && modified) {                                     /* render.c:2347-2353 */
+            memcpy(s->key[c][0], s->key[c][1], sizeof(float) * (size_t) n);
+            memcpy(s->key[c][1], s->last[c], sizeof(float) * (size_t) n);
+        }
+        if (spec[c]) memcpy(spec[c], s->last[c], sizeof(float) * (size_t) n);
+        if (texo[c]) memcpy(texo[c], s->tex[c], sizeof(uint16_t) * (size_t) n);
+    }
+    free(pre);
+    s->kcounter = modified ? 0 : s->kcounter + 1;                            /* render.c:2380-2383 */
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* FIFO ingest — fifo.c:89-110                                                           */
 void orc_fifo_ingest(float* rl, float* rr, int n, const int16_t* in, int frames, int channels) {
     memmove(rl, rl + frames, sizeof(float) * (size_t) (n - frames));

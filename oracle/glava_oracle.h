@@ -94,6 +94,33 @@ void      orc_chan_free(orc_chan* c);
 void orc_chan_update(orc_chan* c, const orc_params* p, const float* pcm, int is_fft,
                      float* spec_f32, uint16_t* tex_u16);
 
+/* ---- optional stages of rd_update that the shipped configuration leaves off ---------------- */
+/* bufscale (render.c:1765-1790): box-average `k` consecutive samples, out has n_in / k floats */
+void orc_bufscale(const float* in, int n_in, int k, float* out);
+/* transform_smooth (render.c:694-718): in place; b[0] becomes NaN (0/0), as in the reference */
+void orc_transform_smooth(float* b, int sz, float smooth_distance, float smooth_ratio);
+/* keyframe interpolation (render.c:1792-1809): out = s + (e - s) * min(ur / fr * kcounter, 1) */
+void orc_interp(const float* s, const float* e, int n, float ur, float fr, int kcounter, float* out);
+
+typedef struct {
+    int   bufscale;          /* setbufscale */
+    int   interpolate;       /* setinterpolate */
+    float fr;                /* frame rate (rd_update calls per second); <= 0: same as ur */
+    int   transform_smooth;  /* "smooth" appended to the module's transform chain */
+    float smooth_distance, smooth_ratio;   /* setsmooth, setsmoothratio (render.c:917-918) */
+} orc_ext;
+
+/* One stream (both channels) through a whole rd_update, including the optional stages:
+ * bufscale -> transform chain (-> transform_smooth) -> keyframe lerp -> R16 upload -> K1-K5.
+ * p->n is setbufsize (what the caller passes as bsz); textures / spectra have p->n / bufscale entries.
+ * Call order and state follow render.c:1761-1809, 2113-2309, 2347-2353, 2380-2383. */
+typedef struct orc_stream orc_stream;
+orc_stream* orc_stream_new(const orc_params* p, const orc_ext* x);
+void        orc_stream_free(orc_stream* s);
+int         orc_stream_n(const orc_stream* s);
+void orc_stream_update(orc_stream* s, const float* lb, const float* rb, int modified,
+                       float* spec_l, float* spec_r, uint16_t* tex_l, uint16_t* tex_r);
+
 /* K5 alone: smooth_pass.frag over an R16 texture */
 void orc_smooth_pass(const orc_params* p, const uint16_t* in, uint16_t* out);
 

@@ -66,6 +66,23 @@ def params_from(product_params):
     return _copy_fields(OrcParams(), product_params)
 
 
+class OrcExt(C.Structure):
+    """optional rd_update stages (orc_ext in glava_oracle.h)"""
+    _fields_ = [("bufscale", C.c_int), ("interpolate", C.c_int), ("fr", C.c_float), ("transform_smooth", C.c_int),
+                ("smooth_distance", C.c_float), ("smooth_ratio", C.c_float)]
+
+
+def ext_from(product_params=None, **over):
+    x = OrcExt(1, 0, 0.0, 0, 0.01, 4.0)                      # render.c:908,912(rc.glsl:131),917,918
+    if product_params is not None:
+        for name, _ in OrcExt._fields_:
+            if hasattr(product_params, name):
+                setattr(x, name, getattr(product_params, name))
+    for k, v in over.items():
+        setattr(x, k, v)
+    return x
+
+
 def build(force=False):
     """make oracle (+ ref when /root/reference exists).  Building the checker is not using it."""
     need = force or not all(os.path.exists(os.path.join(HERE, f)) for f in ("libglava_oracle.so", "libglava_oracle_pm.so"))
@@ -95,6 +112,14 @@ class Oracle:
         L.orc_raster_rows.argtypes = [PP, vp, vp, vp, i32, i32]
         L.orc_fifo_ingest.argtypes = [vp, vp, i32, vp, i32, i32]
         L.orc_math_kind.restype = C.c_char_p
+        L.orc_bufscale.argtypes = [vp, i32, i32, vp]
+        L.orc_transform_smooth.argtypes = [vp, i32, C.c_float, C.c_float]
+        L.orc_interp.argtypes = [vp, vp, i32, C.c_float, C.c_float, i32, vp]
+        L.orc_stream_new.restype = vp
+        L.orc_stream_new.argtypes = [PP, C.POINTER(OrcExt)]
+        L.orc_stream_free.argtypes = [vp]
+        L.orc_stream_n.argtypes = [vp]
+        L.orc_stream_update.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
         self.L = L
         self.kind = kind
 
@@ -135,6 +160,23 @@ class Oracle:
         self.L.orc_raster_rows(C.byref(p), tl.ctypes.data, tr.ctypes.data, out.ctypes.data, y0, y1)
         return out
 
+    def bufscale(self, pcm, k):
+        x = np.ascontiguousarray(pcm, dtype=np.float32)
+        out = np.empty(x.shape[0] // k, np.float32)
+        self.L.orc_bufscale(x.ctypes.data, x.shape[0], k, out.ctypes.data)
+        return out
+
+    def transform_smooth(self, buf, smooth_distance=0.01, smooth_ratio=4.0):
+        b = np.array(buf, dtype=np.float32, copy=True)
+        self.L.orc_transform_smooth(b.ctypes.data, b.shape[0], smooth_distance, smooth_ratio)
+        return b
+
+    def interp(self, start, end, ur, fr, kcounter):
+        s = np.ascontiguousarray(start, dtype=np.float32); e = np.ascontiguousarray(end, dtype=np.float32)
+        out = np.empty_like(s)
+        self.L.orc_interp(s.ctypes.data, e.ctypes.data, s.shape[0], ur, fr, kcounter, out.ctypes.data)
+        return out
+
     def fifo_ingest(self, ring_l, ring_r, chunk, channels=2):
         chunk = np.ascontiguousarray(chunk, dtype=np.int16)
         self.L.orc_fifo_ingest(ring_l.ctypes.data, ring_r.ctypes.data, ring_l.shape[0], chunk.ctypes.data,
@@ -159,6 +201,27 @@ class OracleChannel:
         except Exception: pass
 
 
+class OracleStream:
+    """one stream through whole rd_update calls, optional stages included (orc_stream_*)"""
+
+    def __init__(self, oracle, p, ext):
+        self.o, self.p, self.x = oracle, p, ext
+        self.h = oracle.L.orc_stream_new(C.byref(p), C.byref(ext))
+        self.n = oracle.L.orc_stream_n(self.h)
+
+    def update(self, lb, rb, modified=True):
+        lb = np.ascontiguousarray(lb, dtype=np.float32); rb = np.ascontiguousarray(rb, dtype=np.float32)
+        sl = np.empty(self.n, np.float32); sr = np.empty(self.n, np.float32)
+        tl = np.empty(self.n, np.uint16); tr = np.empty(self.n, np.uint16)
+        self.o.L.orc_stream_update(self.h, lb.ctypes.data, rb.ctypes.data, 1 if modified else 0,
+                                   sl.ctypes.data, sr.ctypes.data, tl.ctypes.data, tr.ctypes.data)
+        return sl, sr, tl, tr
+
+    def __del__(self):
+        try: self.o.L.orc_stream_free(self.h)
+        except Exception: pass
+
+
 class Reference:
     """The reference's own compiled transforms (oracle/_ref/libglava_ref.so)."""
 
@@ -177,6 +240,7 @@ class Reference:
             f.argtypes = [vp, vp, C.c_size_t]
         L.ref_wrange.argtypes = [vp, C.c_size_t]
         L.ref_parse_color.argtypes = [C.c_char_p, vp]
+        L.ref_smooth.argtypes = [vp, C.c_size_t, C.c_float, C.c_float]
         self.L = L
 
     def chan(self, p):
@@ -195,6 +259,11 @@ class Reference:
     def wrange(self, pcm):
         b = np.array(pcm, dtype=np.float32, copy=True)
         self.L.ref_wrange(b.ctypes.data, b.shape[0])
+        return b
+
+    def smooth(self, buf, smooth_distance=0.01, smooth_ratio=4.0):
+        b = np.array(buf, dtype=np.float32, copy=True)
+        self.L.ref_smooth(b.ctypes.data, b.shape[0], smooth_distance, smooth_ratio)
         return b
 
     def parse_color(self, s):

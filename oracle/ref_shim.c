@@ -9,6 +9,7 @@
  *   transform_gravity  render.c:720-736
  *   transform_average  render.c:738-771
  *   transform_wrange   render.c:773-781
+ *   transform_smooth   render.c:694-718
  *
  * The shim needs render.c's private `struct gl_data` / `struct gl_sampler_data`
  * (render.c:116-119,166-207), hence the #include of the .c file.  No reference
@@ -69,6 +70,16 @@ void ref_average(void* p, float* buf, size_t sz) {
 void ref_wrange(float* buf, size_t sz) {
     struct gl_sampler_data s = { .buf = buf, .sz = sz };
     transform_wrange(NULL, NULL, &s);
+}
+
+/* transform_smooth (render.c:694-718): registered as "smooth", requested by no shipped module. */
+void ref_smooth(float* buf, size_t sz, float smooth_distance, float smooth_ratio) {
+    struct gl_data d;
+    memset(&d, 0, sizeof(d));
+    d.smooth_distance = smooth_distance;
+    d.smooth_ratio    = smooth_ratio;
+    struct gl_sampler_data s = { .buf = buf, .sz = sz };
+    transform_smooth(&d, NULL, &s);
 }
 
 /* The CPU chain rd_update runs with `setaccelfft false` (render.c:2149-2156). */

@@ -10,6 +10,8 @@ Fixtures (all seeded, small):
                         plus the raw transform_fft output of update 12.
   fft_kat.npz           transform_fft on a 64-cycle sine and on an impulse, N = 1024
   wrange.npz            transform_wrange on a ramp
+  smooth.npz            transform_smooth (render.c:694-718) on a seeded spectrum-like buffer with zeros, N = 1024 and
+                        4096, default (0.01, 4) and a wide (0.2, 2) setting
   colors.npz            ext_parse_color (glsl_ext.c:88-122) on the colour literals the shipped modules use
 """
 import os
@@ -56,6 +58,14 @@ def main():
                         impulse=imp, impulse_out=ref.fft(ref.chan(p), imp))
     ramp = np.linspace(-0.5, 0.5, 1024, dtype=np.float32)
     np.savez_compressed(os.path.join(HERE, "wrange.npz"), ramp=ramp, out=ref.wrange(ramp))
+    rng = np.random.default_rng(99)
+    sm = {}
+    for n in (1024, 4096):
+        x = (rng.random(n) ** 3).astype(np.float32); x[rng.random(n) < 0.2] = 0
+        sm[f"in_{n}"] = x
+        sm[f"out_{n}_default"] = ref.smooth(x, 0.01, 4.0)
+        sm[f"out_{n}_wide"] = ref.smooth(x, 0.2, 2.0)
+    np.savez_compressed(os.path.join(HERE, "smooth.npz"), **sm)
     names = ["3366b2", "a0a0b2", "333333", "cc3333", "cca0a0", "802A2A", "4F4F92", "262626", "00000000", "55000055", "0xff8000"]
     vals = np.stack([ref.parse_color(s)[1] for s in names])
     np.savez_compressed(os.path.join(HERE, "colors.npz"), names=np.array(names), rgba=vals)
