@@ -106,6 +106,13 @@ def lib():
     L.glava_b200_smooth_pass.argtypes = [vp, vp, vp, i32]
     L.glava_b200_raster_textures.argtypes = [vp, vp, vp]
     L.glava_b200_transform_smooth.argtypes = [vp, vp, i32]
+    L.glava_b200_sizereq.argtypes = [vp, i32, i32]
+    L.glava_b200_wait_frame.argtypes = [vp]
+    L.glava_b200_frame_event.argtypes = [vp]
+    L.glava_b200_frame_event.restype = vp
+    L.glava_b200_frame_device.argtypes = [vp, i32]
+    L.glava_b200_frame_device.restype = vp
+    L.glava_b200_framebuffer_ipc.argtypes = [vp, vp, C.c_size_t]
     L.glava_b200_spectrum_size.argtypes = [vp]
     L.glava_b200_launch_count.argtypes = [vp]
     L.glava_b200_launch_count.restype = C.c_uint64
@@ -195,6 +202,12 @@ class Renderer:
             assert rb.shape == lb.shape
             rp = rb.ctypes.data
         _check(self._L.glava_b200_update(self._h, lb.ctypes.data, rp, self.params.n, 1 if modified else 0))
+        self._after_update()
+
+    def _after_update(self):
+        if getattr(self, "_resize_pending", False):          # a glava_b200_sizereq was applied by this update
+            self._resize_pending = False
+            self.refresh_params()
 
     def reconfigure(self, params):
         """live parameter update (colours, amplify, smoothing...): the `--pipe` analogue"""
@@ -204,6 +217,7 @@ class Renderer:
     def update_device(self, d_lb, d_rb, modified=True):
         """d_lb, d_rb: integer device addresses of [batch][n] float32 (e.g. torch tensor.data_ptr())."""
         _check(self._L.glava_b200_update_device(self._h, d_lb, d_rb, self.params.n, 1 if modified else 0))
+        self._after_update()
 
     def ingest_fifo(self, chunks):
         chunks = np.ascontiguousarray(chunks, dtype=np.int16)
@@ -212,6 +226,7 @@ class Renderer:
 
     def update_rings(self, modified=True):
         _check(self._L.glava_b200_update_rings(self._h, 1 if modified else 0))
+        self._after_update()
 
     def sync(self):
         _check(self._L.glava_b200_sync(self._h))
@@ -260,6 +275,31 @@ class Renderer:
             tex_r = np.ascontiguousarray(tex_r, dtype=np.uint16)
             rp = tex_r.ctypes.data
         _check(self._L.glava_b200_raster_textures(self._h, tex_l.ctypes.data, rp))
+
+    # -- offscreen hand-off (glava_sizereq / glava_wait / glava_tex) ---------------------------------
+    def sizereq(self, w, h):
+        """resize request, applied at the start of the next update"""
+        _check(self._L.glava_b200_sizereq(self._h, int(w), int(h)))
+        self._resize_pending = True
+
+    def refresh_params(self):
+        _check(self._L.glava_b200_get_params(self._h, C.byref(self.params)))
+        return self.params
+
+    def wait_frame(self):
+        _check(self._L.glava_b200_wait_frame(self._h))
+
+    @property
+    def frame_event(self):
+        return self._L.glava_b200_frame_event(self._h)
+
+    def frame_device(self, stream):
+        return self._L.glava_b200_frame_device(self._h, int(stream))
+
+    def framebuffer_ipc(self):
+        buf = (C.c_ubyte * 64)()
+        _check(self._L.glava_b200_framebuffer_ipc(self._h, buf, 64))
+        return bytes(buf)
 
     @property
     def framebuffer_device(self):

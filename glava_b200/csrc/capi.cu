@@ -9,6 +9,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -58,6 +59,7 @@ struct glava_b200 {
     float* d_key[3]; int key_start, key_end;   // keyframe buffers [batch*2][n] (start, end, the one being written)
     float* d_spec_cur;          // latest post-transform buffer (glava_b200_spectrum)
     void* d_ts_tab; int ts_asz, ts_lim;        // transform_smooth {smin, smax} table
+    std::atomic<unsigned long long> sizereq;   // pending glava_b200_sizereq: (1 << 63) | w << 32 | h, 0 = none
     int batch, device, slots;
     cudaStream_t stream;        // raster kernels, read-backs (the stream glava_b200_cuda_stream returns)
     cudaStream_t spec_stream;   // spectrum kernels + FIFO ingest, lowest priority: the latency-bound spectrum
@@ -415,6 +417,7 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     glava_b200* r = new glava_b200();
     r->p_user = *params; r->batch = batch; r->device = device;
     derive(r);
+    r->sizereq.store(0);
     r->kcounter = 0; r->d_scaled[0] = r->d_scaled[1] = nullptr; r->d_key[0] = r->d_key[1] = r->d_key[2] = nullptr;
     r->key_start = 0; r->key_end = 1; r->d_spec_cur = nullptr; r->d_ts_tab = nullptr; r->ts_asz = r->ts_lim = 0;
     r->stream = nullptr; r->spec_stream = nullptr; r->tex_cur = 0; r->ring_cur = 0;
@@ -494,6 +497,24 @@ static int sync_all(glava_b200* r) {
     return 0;
 }
 
+// Runtime resize (render.c:1811-1830 resizes the stage FBOs when the framebuffer size changed; offscreen consumers ask
+// through glava_sizereq, glava.c:263-267).  Spectrum state is untouched; the framebuffers and every table that depends
+// on the geometry (row colours, polar geometry cache, lazy-K5 need-list) are rebuilt.
+static int apply_resize(glava_b200* r, int w, int h) {
+    glava_b200_params q = r->p_user;
+    q.w = w; q.h = h;
+    int rc = validate_params(&q);
+    if (rc) return rc;
+    if ((rc = sync_all(r)) != 0) return rc;
+    dev_free(r, r->d_fb); dev_free(r, r->d_rowtab);
+    r->d_fb = nullptr; r->d_rowtab = nullptr;
+    r->p_user = q;
+    derive(r);
+    if ((rc = dev_alloc(r, (void**) &r->d_rowtab, (size_t) q.h * 8, true)) != 0) return rc;
+    if ((rc = dev_alloc(r, (void**) &r->d_fb, (size_t) q.w * q.h * 4 * r->slots, true)) != 0) return rc;
+    return build_tables(r);
+}
+
 // One update = spectrum kernel on spec_stream (if modified) + raster kernel on stream.
 //   spectrum(i) waits for: its input (caller-provided event on spec_stream), spectrum(i-1) (same stream:
 //                          gravity / average state is read-modify-write), raster(i-2) (last reader of the
@@ -501,8 +522,12 @@ static int sync_all(glava_b200* r) {
 //   raster(i)   waits for: spectrum(i)
 // so raster(i) and spectrum(i+1) run concurrently: one is HBM-store bound, the other latency bound.
 static int run_update(glava_b200* r, const float* d_l, const float* d_r, int modified, bool raster_only = false) {
-    const glava_b200_params& p = r->p;
     int rc;
+    if (unsigned long long req = r->sizereq.exchange(0)) {                  // render.c:1811-1815: at the start of a frame
+        if ((rc = apply_resize(r, (int) ((req >> 32) & 0x7fffffffu), (int) (req & 0xffffffffu))) != 0) return rc;
+    }
+    if (!r->d_fb) return fail(GLAVA_B200_ECUDA, "renderer has no framebuffer (a resize failed)");
+    const glava_b200_params& p = r->p;
     const bool new_tex = !raster_only && (modified || r->interp_on);   // an interpolated frame has a new texture without new audio
     const int planes = r->batch * 2;
     const size_t total = (size_t) planes * p.n;
@@ -681,6 +706,33 @@ int glava_b200_update_rings(glava_b200* r, int modified) {
     if (!r) return fail(GLAVA_B200_EINVAL, "null argument");
     CU(cudaSetDevice(r->device));
     return run_update(r, r->d_ring[r->ring_cur][0], r->d_ring[r->ring_cur][1], modified);
+}
+
+// ---- offscreen hand-off (glava.h:16-25, glava.c:244-267) -----------------------------------------------------------
+int glava_b200_sizereq(glava_b200* r, int w, int h) {
+    if (!r || w < 1 || h < 1 || w > 0x7fffffff) return fail(GLAVA_B200_EINVAL, "glava_b200_sizereq: bad arguments");
+    r->sizereq.store((1ull << 63) | ((unsigned long long) (unsigned) w << 32) | (unsigned) h);
+    return 0;
+}
+int glava_b200_wait_frame(glava_b200* r) {
+    if (!r) return fail(GLAVA_B200_EINVAL, "null argument");
+    CU(cudaSetDevice(r->device));
+    CU(cudaEventSynchronize(r->ev_raster_done[r->tex_cur]));
+    return 0;
+}
+void* glava_b200_frame_event(const glava_b200* r) { return r ? (void*) r->ev_raster_done[r->tex_cur] : nullptr; }
+const void* glava_b200_frame_device(const glava_b200* r, int stream) {
+    if (!r || stream < 0 || stream >= r->batch || !r->d_fb) return nullptr;
+    return r->d_fb + (size_t) r->p.w * r->p.h * 4 * (size_t) (stream % r->slots);
+}
+int glava_b200_framebuffer_ipc(glava_b200* r, void* handle, size_t handle_bytes) {
+    clear_error();
+    if (!r || !handle || handle_bytes < sizeof(cudaIpcMemHandle_t)) return fail(GLAVA_B200_EINVAL, "glava_b200_framebuffer_ipc: need a %zu-byte buffer", sizeof(cudaIpcMemHandle_t));
+    CU(cudaSetDevice(r->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, r->d_fb));
+    memcpy(handle, &h, sizeof(h));
+    return 0;
 }
 
 int glava_b200_set_timing(glava_b200* r, int enable) {

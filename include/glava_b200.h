@@ -190,6 +190,22 @@ int glava_b200_textures(glava_b200* r, uint16_t* out_l, uint16_t* out_r);       
 const void* glava_b200_framebuffer_device(const glava_b200* r);                 /* DEVICE [fb_slots][h][w] RGBA8 */
 void* glava_b200_cuda_stream(const glava_b200* r);                              /* cudaStream_t, for event timing */
 
+/* Offscreen hand-off — the analogues of glava_sizereq / glava_wait / glava_tex (glava.h:22-24, glava.c:244-267) for a
+ * consumer (compositor, encoder) that takes frames straight from HBM:
+ *   glava_b200_sizereq         thread-safe resize request, applied at the start of the next update (render.c:1811-1830);
+ *                              spectrum state is kept, framebuffers and geometry tables are rebuilt
+ *   glava_b200_wait_frame      host-blocks until the latest frame is complete (glava_wait)
+ *   glava_b200_frame_event     cudaEvent_t recorded after the latest raster: cudaStreamWaitEvent(consumer, ev) orders a
+ *                              consumer stream after the frame without a host round trip (glava_tex hands out the GL
+ *                              texture id; here the "texture" is glava_b200_frame_device / _framebuffer_device)
+ *   glava_b200_framebuffer_ipc cudaIpcMemHandle_t (64 bytes) of the framebuffer array, for a consumer in another
+ *                              process (the OBS-plugin situation, glava-obs/entry.c:141-214) */
+int   glava_b200_sizereq(glava_b200* r, int w, int h);
+int   glava_b200_wait_frame(glava_b200* r);
+void* glava_b200_frame_event(const glava_b200* r);
+const void* glava_b200_frame_device(const glava_b200* r, int stream);
+int   glava_b200_framebuffer_ipc(glava_b200* r, void* handle, size_t handle_bytes);
+
 /* Stage-wise entry points (used by the parity tests; same kernels as the fused path). */
 int glava_b200_smooth_pass(glava_b200* r, const uint16_t* in, uint16_t* out, int count);      /* K5 on HOST [count][n] */
 int glava_b200_raster_textures(glava_b200* r, const uint16_t* tex_l, const uint16_t* tex_r);  /* HOST [batch][n] -> raster */

@@ -143,3 +143,54 @@ def test_reconfigure_keeps_optional_stage_layout(built):
             r.reconfigure(g.default_params("bars", n=1024, w=320, h=200, transform_smooth=0))
         with pytest.raises(g.GlavaError):
             r.reconfigure(g.default_params("bars", n=1024, w=320, h=200, transform_smooth=1, bufscale=2))
+
+
+# ---- offscreen hand-off: glava_sizereq / glava_wait / glava_tex analogues (glava.h:22-24) -------------------------
+@pytest.mark.parametrize("module", ["bars", "radial", "circle", "graph", "wave"])
+def test_sizereq_resizes_at_the_next_update_and_keeps_the_spectrum_state(module, built):
+    n, batch = 1024, 3
+    small = g.default_params(module, n=n, w=320, h=200, lazy_smooth=1)
+    big = g.default_params(module, n=n, w=804, h=601, lazy_smooth=1)
+    rings = g.StreamRings(batch, n)
+    with g.Renderer(small, batch=batch) as a, g.Renderer(big, batch=batch) as b:
+        for i in range(7):
+            rings.advance()
+            if i == 5:
+                a.sizereq(804, 601)
+                assert a.params.w == 320                                  # not yet: applied by the next update
+            a.update(rings.lb, rings.rb, True); b.update(rings.lb, rings.rb, True)
+        assert (a.params.w, a.params.h) == (804, 601)
+        for s in range(batch):
+            assert np.array_equal(a.readback(s), b.readback(s)), (module, s)   # same gravity / average history
+        a.sizereq(100000, 10)                                             # invalid geometry: the update reports it
+        with pytest.raises(g.GlavaError):
+            a.update(rings.lb, rings.rb, True)
+
+
+def test_frame_event_wait_and_device_pointers(built):
+    """a consumer stream ordered after the frame by the event alone (no host sync) copies a frame straight out of the
+    framebuffer array — what a compositor / encoder does with glava_tex()'s texture in the reference"""
+    import ctypes as C
+    rt = C.CDLL("libcudart.so.12")
+    p = g.default_params("bars", n=1024, w=320, h=200, fb_slots=2)
+    rings = g.StreamRings(4, 1024)
+    frame = 320 * 200 * 4
+    with g.Renderer(p, batch=4) as r:
+        for _ in range(6):
+            rings.advance(); r.update(rings.lb, rings.rb, True)
+        ev = r.frame_event
+        assert ev
+        consumer = C.c_void_p()
+        assert rt.cudaStreamCreateWithFlags(C.byref(consumer), 1) == 0            # cudaStreamNonBlocking
+        assert rt.cudaStreamWaitEvent(consumer, C.c_void_p(ev), 0) == 0
+        out = g.pinned_empty((200, 320, 4), np.uint8)
+        assert rt.cudaMemcpyAsync(C.c_void_p(out.ctypes.data), C.c_void_p(r.frame_device(3)), C.c_size_t(frame), 2, consumer) == 0
+        assert rt.cudaStreamSynchronize(consumer) == 0
+        assert np.array_equal(out, r.readback(3))
+        rt.cudaStreamDestroy(consumer)
+        r.wait_frame()
+        base = r.framebuffer_device
+        assert r.frame_device(0) == base and r.frame_device(1) == base + frame and r.frame_device(3) == base + frame   # ring of 2
+        assert r.frame_device(4) is None
+        h = r.framebuffer_ipc()
+        assert len(h) == 64 and any(h)
