@@ -404,11 +404,21 @@ static bool apply_request(Loader& L, const std::vector<std::string>& t, const ch
     return true;
 }
 
+// Directory context of `#include` (glsl_ext.c:161-183): plain targets are relative to `cd`; ":x" switches `cd` to
+// the config dir `cfd` (only when one is set), "@x" to the defaults dir `dd` (an error when none is set).  The
+// switch is sticky for the rest of the including file and inherited by the included one, as in the reference.
+struct IncCtx { std::string cd, cfd, dd; bool has_cfd, has_dd; };
+
 // scan a config file: dispatch `#request`s, collect `#define`s (later definitions override,
-// the effect of glsl_ext.c:143-159's auto-#undef)
-static bool scan_file(Loader& L, const std::string& path, Defs* defs, bool requests) {
+// the effect of glsl_ext.c:143-159's auto-#undef), follow `#include`s
+static bool scan_file(Loader& L, const std::string& path, Defs* defs, bool requests, IncCtx ctx, int depth = 0, bool optional = true) {
     std::string src;
-    if (!read_file(path, &src)) return true;      // optional file
+    if (!read_file(path, &src)) {
+        if (optional) return true;                // smooth_parameters.glsl / <module>.glsl need not exist in every dir
+        fail(GLAVA_B200_ECONFIG, "failed to load GLSL shader source specified by #include directive '%s'", path.c_str());   // glsl_ext.c:187
+        return false;
+    }
+    if (depth > 32) { fail(GLAVA_B200_ECONFIG, "[%s] #include nesting too deep", path.c_str()); return false; }
     src = strip_comments(src);
     std::istringstream is(src);
     std::string line; int ln = 0;
@@ -419,6 +429,20 @@ static bool scan_file(Loader& L, const std::string& path, Defs* defs, bool reque
         std::string body = trim(t.substr(1));
         if (body.compare(0, 7, "request") == 0 && requests) {
             if (!apply_request(L, tokenize(body.substr(7)), path.c_str(), ln)) return false;
+        } else if (body.compare(0, 7, "include") == 0) {
+            std::vector<std::string> a = tokenize(body.substr(7));
+            if (a.empty()) { fail(GLAVA_B200_ECONFIG, "[%s:%d] No arguments provided to #include directive!", path.c_str(), ln); return false; }   // glsl_ext.c:163
+            std::string target = a[0];
+            if (!target.empty() && target[0] == ':' && ctx.has_cfd) { target = target.substr(1); ctx.cd = ctx.cfd; }
+            if (!target.empty() && target[0] == '@') {
+                if (!ctx.has_dd) {
+                    fail(GLAVA_B200_ECONFIG, "[%s:%d] encountered '@' path specifier while no default directory is available in the current context",
+                         path.c_str(), ln);                                                      // glsl_ext.c:176
+                    return false;
+                }
+                target = target.substr(1); ctx.cd = ctx.dd;
+            }
+            if (!scan_file(L, ctx.cd + "/" + target, defs, requests, ctx, depth + 1, false)) return false;
         } else if (body.compare(0, 6, "define") == 0 && defs) {
             std::string rest = trim(body.substr(6));
             size_t i = 0; while (i < rest.size() && (isalnum((unsigned char) rest[i]) || rest[i] == '_')) ++i;
@@ -531,7 +555,9 @@ int load_config(glava_b200_params* out, const char* const* paths, const char* en
         fail(GLAVA_B200_ECONFIG, "Could not find entry point '%s' in any of the configuration paths", entry);
         return GLAVA_B200_ECONFIG;
     }
-    if (!entry_dir.empty() && !scan_file(L, entry_dir + "/" + entry, nullptr, true)) return GLAVA_B200_ECONFIG;
+    // rc.glsl: cd = the directory it was found in, no config / defaults dir (render.c:1356-1361)
+    IncCtx rc_ctx { entry_dir, "", "", false, false };
+    if (!entry_dir.empty() && !scan_file(L, entry_dir + "/" + entry, nullptr, true, rc_ctx)) return GLAVA_B200_ECONFIG;
     if (requests) {
         for (int i = 0; requests[i]; ++i) {                                   // render.c:1415-1435
             std::string r = requests[i];
@@ -544,12 +570,18 @@ int load_config(glava_b200_params* out, const char* const* paths, const char* en
         return GLAVA_B200_ECONFIG;
     }
     out->module = mod;
-    // `#include "@x.glsl"` then `#include ":x.glsl"` (e.g. bars/1.frag:9-10): defaults dir first,
-    // user dir second and winning.  dirs[] is user-first like glava.c:301, so walk it backwards.
+    // The module's shaders do `#include "@x.glsl"` then `#include ":x.glsl"` (e.g. bars/1.frag:9-10, util/smooth.glsl:6-7):
+    // the defaults dir `dd` = LAST path (render.c:1327) first, then the config dir = where the entry was found
+    // (render.c:1472-1476, shaderbuild(gl, shaders, data, dd, ...)), whose definitions win.
     Defs defs;
-    for (int i = (int) dirs.size() - 1; i >= 0; --i) {
-        if (!scan_file(L, dirs[i] + "/smooth_parameters.glsl", &defs, true)) return GLAVA_B200_ECONFIG;
-        if (!scan_file(L, dirs[i] + "/" + L.module + ".glsl", &defs, true)) return GLAVA_B200_ECONFIG;
+    if (!dirs.empty()) {
+        const std::string dd = dirs.back();
+        IncCtx dctx { dd, entry_dir, dd, true, true };
+        IncCtx cctx { entry_dir, entry_dir, dd, true, true };
+        for (const std::string& f : { std::string("smooth_parameters.glsl"), L.module + ".glsl" }) {
+            if (!scan_file(L, dd + "/" + f, &defs, true, dctx)) return GLAVA_B200_ECONFIG;
+            if (!scan_file(L, entry_dir + "/" + f, &defs, true, cctx)) return GLAVA_B200_ECONFIG;
+        }
     }
     // CLI requests are applied last in the reference too (after module load they would hit
     // `loading_smooth_pass` guards); re-apply so they win over smooth_parameters.glsl.

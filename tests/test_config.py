@@ -74,8 +74,10 @@ def test_own_config_dir(module, built):
 def test_requests_and_user_override(tmp_path, built):
     user, system = tmp_path / "user", tmp_path / "sys"
     user.mkdir(); system.mkdir()
-    (system / "rc.glsl").write_text('#request mod radial\n#request setbufsize 2048\n#request setgeometry 0 0 1280 720\n'
-                                    '#request setmirror true\n#request setopacity "none"\n')
+    (system / "rc.glsl").write_text('#request mod bars\n')
+    # the first path that has the entry is THE config dir (render.c:1328-1351); `glava --copy-config` puts rc.glsl there
+    (user / "rc.glsl").write_text('#request mod radial\n#request setbufsize 2048\n#request setgeometry 0 0 1280 720\n'
+                                  '#request setmirror true\n#request setopacity "none"\n')
     (system / "radial.glsl").write_text("#define NBARS 120\n#define C_LINE 3\n#define COLOR @fg:#ff0000\n#define ROTATE (PI / 4)\n")
     (user / "radial.glsl").write_text("/* user copy wins */\n#define NBARS 96 // trailing comment\n#define AMPLIFY 250.5F\n")
     (system / "smooth_parameters.glsl").write_text("#define SAMPLE_MODE hybrid\n#request setavgframes 7\n#request setgravitystep 3.5\n")
@@ -90,6 +92,40 @@ def test_requests_and_user_override(tmp_path, built):
     assert p.smooth_factor == np.float32(0.05) and p.accel_fft == 0
     # -m / force_module beats `#request mod`
     assert g.load_config([str(user), str(system)], force_module="wave").module_name == "wave"
+
+
+def test_include_rules_and_config_dir_selection(tmp_path, built):
+    """glsl_ext.c:161-183: plain includes are relative to the current dir, ":x" to the config dir (= where the entry
+    was found), "@x" to the defaults dir (= last path); a path without the entry is not a config dir at all."""
+    user, system = tmp_path / "user", tmp_path / "sys"
+    user.mkdir(); system.mkdir(); (user / "extra").mkdir()
+    (system / "rc.glsl").write_text("#request mod bars\n")
+    (system / "bars.glsl").write_text("#define BAR_WIDTH 7\n#define AMPLIFY 111\n")
+    (user / "bars.glsl").write_text('#include "extra/tweaks.glsl"\n#define BAR_GAP 3\n#include "@shared.glsl"\n#include ":late.glsl"\n')
+    (user / "extra" / "tweaks.glsl").write_text("#define AMPLIFY 222\n#request setavgframes 3\n")
+    (system / "shared.glsl").write_text("#define BAR_OUTLINE_WIDTH 2\n")
+    (user / "late.glsl").write_text("#define BAR_WIDTH 9\n")
+    # user dir has no rc.glsl: skipped entirely, the system dir is both config and defaults dir
+    p = g.load_config([str(user), str(system)])
+    assert (p.bars_width, p.bars_gap, p.bars_amplify, p.avg_frames) == (7, 1, 111, 5)
+    # with the entry copied to the user dir its files take part, includes resolved per the three rules
+    (user / "rc.glsl").write_text('#request mod bars\n#include "more_rc.glsl"\n')
+    (user / "more_rc.glsl").write_text("#request setbufsize 1024\n")
+    p = g.load_config([str(user), str(system)])
+    assert (p.bars_width, p.bars_gap, p.bars_amplify, p.bars_outline_width, p.avg_frames, p.n) == (9, 3, 222, 2, 3, 1024)
+    # errors: missing include target; '@' / ':' inside rc.glsl, which has no defaults / config dir (render.c:1356-1361)
+    (user / "rc.glsl").write_text('#request mod bars\n#include "nope.glsl"\n')
+    with pytest.raises(g.GlavaError, match="#include directive"):
+        g.load_config([str(user), str(system)])
+    (user / "rc.glsl").write_text('#request mod bars\n#include "@shared.glsl"\n')
+    with pytest.raises(g.GlavaError, match="no default directory"):
+        g.load_config([str(user), str(system)])
+    (user / "rc.glsl").write_text('#request mod bars\n#include ":late.glsl"\n')
+    with pytest.raises(g.GlavaError, match="#include directive"):          # no config dir: the ':' stays in the file name
+        g.load_config([str(user), str(system)])
+    (user / "rc.glsl").write_text('#request mod bars\n#include\n')
+    with pytest.raises(g.GlavaError, match="No arguments provided to #include"):
+        g.load_config([str(user), str(system)])
 
 
 @pytest.mark.parametrize("text,match", [
