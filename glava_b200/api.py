@@ -106,6 +106,7 @@ def lib():
     L.glava_b200_smooth_pass.argtypes = [vp, vp, vp, i32]
     L.glava_b200_raster_textures.argtypes = [vp, vp, vp]
     L.glava_b200_transform_smooth.argtypes = [vp, vp, i32]
+    L.glava_b200_timeline.argtypes = [vp, vp, i32, C.POINTER(i32), C.POINTER(i32)]
     L.glava_b200_sizereq.argtypes = [vp, i32, i32]
     L.glava_b200_wait_frame.argtypes = [vp]
     L.glava_b200_frame_event.argtypes = [vp]
@@ -275,6 +276,12 @@ class Renderer:
             tex_r = np.ascontiguousarray(tex_r, dtype=np.uint16)
             rp = tex_r.ctypes.data
         _check(self._L.glava_b200_raster_textures(self._h, tex_l.ctypes.data, rp))
+
+    def timeline(self, cap=4096):
+        """(spectrum [k][2], raster [m][2]) start/end ms of the timed launches (set_timing(True) first)"""
+        out = np.zeros((cap, 2), np.float64); ns, nq = C.c_int(), C.c_int()
+        _check(self._L.glava_b200_timeline(self._h, out.ctypes.data, cap, C.byref(ns), C.byref(nq)))
+        return out[: ns.value].copy(), out[ns.value: ns.value + nq.value].copy()
 
     # -- offscreen hand-off (glava_sizereq / glava_wait / glava_tex) ---------------------------------
     def sizereq(self, w, h):

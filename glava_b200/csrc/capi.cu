@@ -77,6 +77,7 @@ struct glava_b200 {
     // constants
     double* d_window; float* d_twiddle; void* d_rowtab; int* d_need; int need_count;
     TapEntry* d_tap_tab; int* d_tap_cnt; float* d_tap_wsum; int tap_max; int epi_n;
+    unsigned char* d_csr; int csr_bytes, csr_idx_off, csr_off_off;   // the same taps, texel-major, for the shared-memory path
     void* d_geo; int geo_box[4];   // polar geometry cache (radial / circle), see raster_kernels.cu
     uint32_t* d_texmm;             // circle: per-plane {min, max} of the sampled texture, refreshed before each raster
     // state + outputs
@@ -212,6 +213,7 @@ static int build_tables(glava_b200* r) {
     const glava_b200_params& p = r->p;
     int rc;
     dev_free(r, r->d_need); dev_free(r, r->d_tap_tab); dev_free(r, r->d_tap_cnt); dev_free(r, r->d_tap_wsum); dev_free(r, r->d_geo);
+    dev_free(r, r->d_csr); r->d_csr = nullptr; r->csr_bytes = r->csr_idx_off = r->csr_off_off = 0;
     r->d_need = nullptr; r->need_count = 0; r->d_tap_tab = nullptr; r->d_tap_cnt = nullptr; r->d_tap_wsum = nullptr;
     r->tap_max = 0; r->epi_n = 0; r->d_geo = nullptr; r->geo_box[0] = r->geo_box[1] = r->geo_box[2] = r->geo_box[3] = 0;
     if (p.transform_smooth) {
@@ -285,6 +287,40 @@ static int build_tables(glava_b200* r) {
                 CU(cudaMemcpyAsync(r->d_tap_wsum, wsum.data(), wsum.size() * sizeof(float), cudaMemcpyHostToDevice, r->stream));
                 CU(cudaStreamSynchronize(r->stream));
                 r->tap_max = (int) tap_max;
+                // Texel-major copy of the same taps, one blob per channel: [float w[total]] [u16 idx[total]] [int off[cnt + 1]].
+                // When it is small enough for two CTAs per SM to hold their channel's blob in shared memory next to the FFT
+                // buffers, the kernel's serial per-texel sums read their taps from there (no L2 round trips on the chain).
+                size_t total = 0;
+                for (size_t c = 0; c < 2; ++c) { size_t t = 0; for (size_t k = 0; k < cnt; ++k) t += taps[c * cnt + k].size(); if (t > total) total = t; }
+                const size_t w_bytes = ((total * 4 + 15) / 16) * 16, i_bytes = ((total * 2 + 15) / 16) * 16, o_bytes = (((cnt + 1) * 4 + 15) / 16) * 16;
+                const size_t blob = w_bytes + i_bytes + o_bytes;
+                const int base = spectrum_smem_bytes(p.n);
+                if (base > 0 && base + blob <= (size_t) 112 * 1024 && !getenv("GLAVA_B200_NO_SMEM_TAPS")) {
+                    std::vector<unsigned char> host(2 * blob, 0);
+                    for (size_t c = 0; c < 2; ++c) {
+                        float* w = reinterpret_cast<float*>(host.data() + c * blob);
+                        uint16_t* ix = reinterpret_cast<uint16_t*>(host.data() + c * blob + w_bytes);
+                        int* off = reinterpret_cast<int*>(host.data() + c * blob + w_bytes + i_bytes);
+                        size_t at = 0;
+                        for (size_t k = 0; k < cnt; ++k) {
+                            off[k] = (int) at;
+                            for (const TapEntry& te : taps[c * cnt + k]) {
+                                // a tap outside the texture fetches 0 (texelFetch): texel * w = +0 either way, so it is
+                                // stored as (index 0, weight 0) and the kernel needs no range test; its weight still
+                                // counts in tap_wsum
+                                const bool inside = te.idx >= 0 && te.idx < p.n;
+                                w[at] = inside ? te.w : 0.0f;
+                                ix[at] = inside ? (uint16_t) te.idx : (uint16_t) 0;
+                                ++at;
+                            }
+                        }
+                        off[cnt] = (int) at;
+                    }
+                    if ((rc = dev_alloc(r, (void**) &r->d_csr, host.size(), false)) != 0) return rc;
+                    CU(cudaMemcpyAsync(r->d_csr, host.data(), host.size(), cudaMemcpyHostToDevice, r->stream));
+                    CU(cudaStreamSynchronize(r->stream));
+                    r->csr_bytes = (int) blob; r->csr_idx_off = (int) w_bytes; r->csr_off_off = (int) (w_bytes + i_bytes);
+                }
             }
         }
     }
@@ -424,6 +460,7 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     for (int i = 0; i < 2; ++i) { r->ev_spec_done[i] = nullptr; r->ev_raster_done[i] = nullptr; } r->d_chunks = nullptr; r->chunks_cap = 0;
     r->d_window = nullptr; r->d_twiddle = nullptr; r->d_rowtab = nullptr; r->d_need = nullptr; r->need_count = 0;
     r->d_tap_tab = nullptr; r->d_tap_cnt = nullptr; r->d_tap_wsum = nullptr; r->tap_max = 0; r->epi_n = 0;
+    r->d_csr = nullptr; r->csr_bytes = r->csr_idx_off = r->csr_off_off = 0;
     r->d_geo = nullptr; r->geo_box[0] = r->geo_box[1] = r->geo_box[2] = r->geo_box[3] = 0;
     r->d_spec = r->d_applied = r->d_ring_f = nullptr; r->d_gr_store = r->d_ring_u = r->d_tex = nullptr; r->d_av = nullptr; r->d_texmm = nullptr; r->d_fb = nullptr;
     for (int i = 0; i < 2; ++i) { r->d_pcm[i][0] = r->d_pcm[i][1] = nullptr; r->ev_copied[i] = r->ev_free[i] = nullptr; }
@@ -553,6 +590,7 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
         a.need = (p.lazy_smooth && r->d_need) ? r->d_need : nullptr; a.need_count = r->need_count;
         a.tap_tab = a.need ? r->d_tap_tab : nullptr; a.tap_cnt = r->d_tap_cnt; a.tap_wsum = r->d_tap_wsum; a.tap_max = r->tap_max;
         a.epi_n = a.need ? r->epi_n : 0;
+        a.csr = (a.need && a.tap_tab) ? r->d_csr : nullptr; a.csr_bytes = r->csr_bytes; a.csr_idx_off = r->csr_idx_off; a.csr_off_off = r->csr_off_off;
         a.batch = r->batch; a.update = r->updates;
         const int F = p.avg_frames;
         for (int f = 0; f < F; ++f) {
@@ -761,6 +799,22 @@ int glava_b200_kernel_times(glava_b200* r, double* spectrum_ms, int* spectrum_la
     if (spectrum_launches) *spectrum_launches = ns;
     if (raster_ms) *raster_ms = q;
     if (raster_launches) *raster_launches = nq;
+    return 0;
+}
+
+// Event timeline of the timed launches, in ms relative to the first spectrum mark: out = [start, end] pairs, spectrum
+// launches first (n_spec pairs) then raster launches.  Development aid for looking at the overlap of the two streams.
+int glava_b200_timeline(glava_b200* r, double* out, int cap_pairs, int* n_spec, int* n_ras) {
+    if (!r || !out) return fail(GLAVA_B200_EINVAL, "null argument");
+    CU(cudaSetDevice(r->device));
+    int rc0 = sync_all(r); if (rc0) return rc0;
+    const int ns = (int) r->ev_spec.size() / 2, nq = (int) r->ev_ras.size() / 2;
+    if (ns + nq > cap_pairs || ns == 0) return fail(GLAVA_B200_EINVAL, "glava_b200_timeline: %d pairs, capacity %d", ns + nq, cap_pairs);
+    cudaEvent_t t0 = r->ev_spec[0];
+    for (int i = 0; i < 2 * ns; ++i) { float a = 0; CU(cudaEventElapsedTime(&a, t0, r->ev_spec[i])); out[i] = a; }
+    for (int i = 0; i < 2 * nq; ++i) { float a = 0; CU(cudaEventElapsedTime(&a, t0, r->ev_ras[i])); out[2 * ns + i] = a; }
+    if (n_spec) *n_spec = ns;
+    if (n_ras) *n_ras = nq;
     return 0;
 }
 

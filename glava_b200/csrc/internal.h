@@ -50,6 +50,11 @@ struct SpectrumArgs {
     const float* tap_wsum;      // [2][need_count]  sum of the weights in loop order
     int       tap_max;
     int       epi_n;            // lazy K5: number of leading bins whose gravity/average state can reach a sampled texel (0 = all)
+    // the same taps as one blob per channel, small enough to live in shared memory (loaded by the TMA engine while the
+    // FFT runs): [float w[csr_total]] [uint16 idx[csr_total]] [int off[need_count + 1]], texel-major ("CSR"); nullptr = unused
+    const unsigned char* csr;   // [2][csr_bytes]
+    int       csr_bytes;        // bytes per channel (multiple of 16)
+    int       csr_idx_off, csr_off_off;   // byte offsets of idx[] and off[] inside a blob
     int       skip_tex;         // 1: produce `spec` only (transform_smooth / keyframe lerp / upload / K5 follow as kernels)
     int       batch;
     unsigned long long update;  // number of modified updates before this one (ring cursor)
@@ -82,6 +87,7 @@ int launch_polar_geo(const glava_b200_params& p, void* d_geo, const int box[4], 
 int launch_fifo_ingest(const glava_b200_params& p, const int16_t* d_chunks, int frames, const float* src_l, const float* src_r,
                        float* dst_l, float* dst_r, int batch, void* stream);
 int spectrum_smem_bytes(int n);
+int spectrum_threads(int n);
 // chain_kernels.cu: optional stages of rd_update (bufscale, transform_smooth, keyframe lerp + R16 upload)
 int launch_bufscale(const float* in_l, const float* in_r, float* out_l, float* out_r, int batch, int n_in, int k,
                     int channels, void* stream);

@@ -99,9 +99,26 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
         mbar_expect_tx(bar, N * 4);
         bulk_g2s(raw, pcm, N * 4, bar);
     };
-    if (tid == 0) mbar_init(bar, 1);
+    // K5 tap table of this CTA's channel in shared memory (behind the fixed regions): one more bulk copy, in flight
+    // during the FFT and the epilogue
+    unsigned char* tapsm = glb_smem + C::SMEM;
+    uint64_t* bar2 = bar + 1;
+    auto issue_tab = [&](int ch) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar2, (uint32_t) a.csr_bytes);
+        const unsigned char* src = a.csr + (size_t) ch * a.csr_bytes;
+        for (int o = 0; o < a.csr_bytes; o += 32768)
+            bulk_g2s(tapsm + o, src + o, (uint32_t) min(32768, a.csr_bytes - o), bar2);
+    };
+    if (tid == 0) { mbar_init(bar, 1); mbar_init(bar2, 1); }
     __syncthreads();
     if (tid == 0 && (int) blockIdx.x < units) issue_load(blockIdx.x);
+    int tab_ch = -1; bool tab_pending = false; uint32_t parity2 = 0;
+    if (a.csr && a.need && (int) blockIdx.x < units && !a.skip_tex && p.smooth_pass) {
+        tab_ch = IS_FFT ? ((int) blockIdx.x & 1) : 0;
+        if (tid == 0) issue_tab(tab_ch);
+        tab_pending = true;
+    }
     uint32_t parity = 0;
     const int F = p.avg_frames;
 
@@ -262,7 +279,42 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
     uint16_t* tex = a.tex + plane;
     if (p.smooth_pass) {
         const SmoothParams sp = smooth_params(p);
-        if (a.need && a.tap_tab) {
+        if (a.need && a.csr) {
+            // taps from shared memory: per tap two LDS + the texel fetch, no global-memory latency on the serial sum
+            if (tab_ch != ch) {                      // persistent CTA whose unit changed channel (odd grid): reload
+                if (tid == 0) issue_tab(ch);
+                tab_ch = ch; tab_pending = true;
+            }
+            if (tab_pending) { mbar_wait(bar2, parity2); parity2 ^= 1u; tab_pending = false; }
+            const float*    tw = reinterpret_cast<const float*>(tapsm);
+            const uint16_t* ti = reinterpret_cast<const uint16_t*>(tapsm + a.csr_idx_off);
+            const int*      to = reinterpret_cast<const int*>(tapsm + a.csr_off_off);
+            const int* need = a.need + (size_t) ch * a.need_count;
+            for (int k = tid; k < a.need_count; k += T) {
+                const int x = need[k];
+                if (x < 0 || x >= N) continue;
+                const int o0 = to[k], o1 = to[k + 1];
+                SmoothAcc acc; acc.init();
+                // the sum is serial in the tap order (smooth.glsl:33-37), but its operands are not: fetch KU taps' index,
+                // weight and texel (two dependent shared-memory round trips) before the KU dependent adds
+                constexpr int KU = 8;
+                int o = o0;
+                for (; o + KU <= o1; o += KU) {
+                    int ii[KU]; float ww[KU], tx[KU];
+#pragma unroll
+                    for (int q = 0; q < KU; ++q) { ii[q] = ti[o + q]; ww[q] = tw[o + q]; }
+#pragma unroll
+                    for (int q = 0; q < KU; ++q) tx[q] = from16(av[ii[q]]);      // (a tap outside the texture is stored as index 0, weight 0)
+#pragma unroll
+                    for (int q = 0; q < KU; ++q) acc.add_noweight(tx[q], ww[q]);
+                }
+                for (; o < o1; ++o) {
+                    acc.add_noweight(from16(av[ti[o]]), tw[o]);
+                }
+                acc.weight = a.tap_wsum[(size_t) ch * a.need_count + k];
+                tex[x] = (uint16_t) unorm16(acc.result(sp));
+            }
+        } else if (a.need && a.tap_tab) {
             // weights / indices precomputed once (they depend on the parameters only): per tap one
             // coalesced 8-byte load, one shared-memory texel fetch, a multiply and an add
             const int* need = a.need + (size_t) ch * a.need_count;
@@ -272,8 +324,20 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
                 if (x < 0 || x >= N) continue;
                 const int cnt = a.tap_cnt[(size_t) ch * a.need_count + k];
                 SmoothAcc acc; acc.init();
-                for (int j = 0; j < cnt; ++j) {
-                    const int2 e = __ldg(reinterpret_cast<const int2*>(tab) + (size_t) j * a.need_count + k);
+                // a thread's taps are a serial float sum, but the table loads are independent of it: fetch KU entries
+                // (one L2 round trip) before consuming them, in the GLSL loop's order
+                constexpr int KU = 8;
+                const int2* col = reinterpret_cast<const int2*>(tab) + k;
+                int j = 0;
+                for (; j + KU <= cnt; j += KU) {
+                    int2 e[KU];
+#pragma unroll
+                    for (int q = 0; q < KU; ++q) e[q] = __ldg(col + (size_t) (j + q) * a.need_count);
+#pragma unroll
+                    for (int q = 0; q < KU; ++q) acc.add_noweight(fetch16(av, N, e[q].x), __int_as_float(e[q].y));
+                }
+                for (; j < cnt; ++j) {
+                    const int2 e = __ldg(col + (size_t) j * a.need_count);
                     acc.add_noweight(fetch16(av, N, e.x), __int_as_float(e.y));
                 }
                 acc.weight = a.tap_wsum[(size_t) ch * a.need_count + k];
@@ -300,6 +364,14 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
   }
 }
 
+int spectrum_threads(int n) {
+    switch (n) {
+        case 256:   return SpecCfg<8>::T;   case 512:   return SpecCfg<9>::T;
+        case 1024:  return SpecCfg<10>::T;  case 2048:  return SpecCfg<11>::T;
+        case 4096:  return SpecCfg<12>::T;  case 8192:  return SpecCfg<13>::T;
+        case 16384: return SpecCfg<14>::T;  default: return -1;
+    }
+}
 int spectrum_smem_bytes(int n) {
     switch (n) {
         case 256:   return SpecCfg<8>::SMEM;   case 512:   return SpecCfg<9>::SMEM;
@@ -318,11 +390,10 @@ static int launch_spectrum_t(const glava_b200_params& p, const SpectrumArgs& a, 
     // Requesting more dynamic shared memory than needed caps it at `cap` CTAs per SM.  Measured on B200
     // (whole step, 1024 streams): no cap 705 k frames/s > cap 3: 686 k > cap 2: 647 k > cap 1: 540 k —
     // the stretched spectrum kernel (and the L1 it takes from the raster kernel) costs more than it frees.
-    static int smem_req = 0;
-    if (!smem_req) {
-        int cap = 0;
-        if (const char* e = getenv("GLAVA_B200_SPEC_RESIDENT")) cap = atoi(e);
-        smem_req = C::SMEM;
+    int smem_req = C::SMEM + (a.csr ? a.csr_bytes : 0);          // + the K5 tap table of one channel (shared-memory K5 path)
+    {
+        static int cap = -1;
+        if (cap < 0) { cap = 0; if (const char* e = getenv("GLAVA_B200_SPEC_RESIDENT")) cap = atoi(e); }
         if (cap > 0) { int want = (227 * 1024) / cap - 1024; if (want > smem_req) smem_req = want; }
         if (smem_req > 227 * 1024) smem_req = 227 * 1024;
     }
@@ -336,10 +407,14 @@ static int launch_spectrum_t(const glava_b200_params& p, const SpectrumArgs& a, 
     // its occupancy away.  GLAVA_B200_SPEC_CTAS_PER_SM overrides (0 = one CTA per work unit).
     int sm_count = 148;
     { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); if (sm_count <= 0) sm_count = 148; }
-    int per_sm = 0;                                  // measured on B200: 0 (one CTA per unit) >= 4 > 3 > 2 > 1 for whole-step throughput
+    // Global-memory tap table: one CTA per unit was measured best (0 >= 4 > 3 > 2 > 1).  Shared-memory tap table: a
+    // persistent grid at the kernel's residency (2 CTAs per SM) loads the table once per CTA and lets the TMA engine
+    // prefetch the next unit's PCM during K5 — measured 765 k frames/s against 751 k (0), 757 k (4), 724 k (1).
+    int per_sm = a.csr ? 2 : 0;
     if (const char* e = getenv("GLAVA_B200_SPEC_CTAS_PER_SM")) per_sm = atoi(e);
     const int units = IS_FFT ? a.batch * 2 : a.batch;
     int grid = (per_sm > 0 && sm_count * per_sm < units) ? sm_count * per_sm : units;
+    if (a.csr && IS_FFT && grid < units && (grid & 1)) ++grid;      // even stride: a persistent CTA stays on one channel (one tap-table load)
     kern<<<grid, C::T, smem_req, st>>>(a, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "spectrum kernel launch: %s", cudaGetErrorString(e));

@@ -220,6 +220,8 @@ uint64_t glava_b200_launch_count(const glava_b200* r);
 int glava_b200_set_timing(glava_b200* r, int enable);
 int glava_b200_kernel_times(glava_b200* r, double* spectrum_ms, int* spectrum_launches,
                             double* raster_ms, int* raster_launches);
+/* development aid: [start, end] ms of every timed launch relative to the first one (spectrum pairs, then raster pairs) */
+int glava_b200_timeline(glava_b200* r, double* out, int cap_pairs, int* n_spec, int* n_ras);
 
 /* ---- audio plug-in ABI kept verbatim from the reference (fifo.h:9-26) so a GLava audio
  * backend can feed this renderer: see INTEGRATION.md. ---- */
