@@ -228,7 +228,8 @@ def main():
     e2.record(stream)
     for i in range(K):
         r.update(host_l[i % nsnap], host_r[i % nsnap], True)     # H2D (copy stream) + kernels
-        r.readback_async(i % batch, frame_pinned)                # D2H of one stream's frame, same stream as the kernels
+        r.readback_async(i % batch, frame_pinned)                # D2H of one stream's frame (snapshot + separate copy-out stream)
+    r.readback_fence()                                           # e3 is ordered after the last frame's D2H
     e3.record(stream)
     r.sync()
     barrier()
@@ -249,6 +250,7 @@ def main():
         r.ingest_fifo(fifo_chunks[i % nsnap])
         r.update_rings(True)
         r.readback_async(i % batch, frame_pinned)
+    r.readback_fence()
     e5.record(stream)
     r.sync()
     barrier()

@@ -97,6 +97,7 @@ def lib():
     L.glava_b200_sync.argtypes = [vp]
     L.glava_b200_readback.argtypes = [vp, i32, vp]
     L.glava_b200_readback_async.argtypes = [vp, i32, vp]
+    L.glava_b200_readback_fence.argtypes = [vp]
     L.glava_b200_spectrum.argtypes = [vp, vp, vp]
     L.glava_b200_textures.argtypes = [vp, vp, vp]
     L.glava_b200_framebuffer_device.argtypes = [vp]
@@ -243,6 +244,10 @@ class Renderer:
     def readback_async(self, stream, out):
         """enqueue the D2H copy of one frame into `out` (pinned uint8 [h][w][4]); valid after sync()"""
         _check(self._L.glava_b200_readback_async(self._h, int(stream), out.ctypes.data))
+
+    def readback_fence(self):
+        """order later work on cuda_stream after the read-backs issued so far (their D2H runs on a separate stream)"""
+        _check(self._L.glava_b200_readback_fence(self._h))
 
     def spectrum(self):
         l = np.empty((self.batch, self.nsz), dtype=np.float32); r = np.empty_like(l)

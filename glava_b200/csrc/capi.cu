@@ -70,6 +70,10 @@ struct glava_b200 {
     float* d_pcm[2][2];         // H2D staging for glava_b200_update, double-buffered  [2][batch][n] x {l, r}
     int    stage_cur;
     cudaStream_t copy_stream;   // H2D of update i+1 overlaps the kernels of update i
+    // asynchronous frame read-back: D2D into a staging frame on the raster stream (microseconds), D2H from there on its
+    // own stream — the PCIe copy of frame i runs under raster i+1 instead of in front of it
+    cudaStream_t out_stream; uint8_t* d_stage[2]; size_t stage_bytes; int out_cur;
+    cudaEvent_t ev_stage_ready[2], ev_stage_free[2];
     cudaEvent_t ev_copied[2], ev_free[2];
     float* d_ring[2][2];        // FIFO rings, ping-pong                      [2][batch][n] x {l, r}
     int    ring_cur;
@@ -465,6 +469,8 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     r->d_spec = r->d_applied = r->d_ring_f = nullptr; r->d_gr_store = r->d_ring_u = r->d_tex = nullptr; r->d_av = nullptr; r->d_texmm = nullptr; r->d_fb = nullptr;
     for (int i = 0; i < 2; ++i) { r->d_pcm[i][0] = r->d_pcm[i][1] = nullptr; r->ev_copied[i] = r->ev_free[i] = nullptr; }
     r->stage_cur = 0; r->copy_stream = nullptr;
+    r->out_stream = nullptr; r->d_stage[0] = r->d_stage[1] = nullptr; r->stage_bytes = 0; r->out_cur = 0;
+    for (int i = 0; i < 2; ++i) { r->ev_stage_ready[i] = nullptr; r->ev_stage_free[i] = nullptr; }
     r->updates = 0; r->launches = 0; r->timing = false;
     if (build(r) != 0) { glava_b200_destroy(r); return nullptr; }
     return r;
@@ -483,6 +489,12 @@ void glava_b200_destroy(glava_b200* r) {
     if (r->d_chunks) cudaFree(r->d_chunks);
     for (int i = 0; i < 2; ++i) { if (r->ev_copied[i]) cudaEventDestroy(r->ev_copied[i]); if (r->ev_free[i]) cudaEventDestroy(r->ev_free[i]); }
     if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
+    if (r->out_stream) { cudaStreamSynchronize(r->out_stream); cudaStreamDestroy(r->out_stream); }
+    for (int i = 0; i < 2; ++i) {
+        if (r->d_stage[i]) cudaFree(r->d_stage[i]);
+        if (r->ev_stage_ready[i]) cudaEventDestroy(r->ev_stage_ready[i]);
+        if (r->ev_stage_free[i]) cudaEventDestroy(r->ev_stage_free[i]);
+    }
     if (r->stream) cudaStreamDestroy(r->stream);
     delete r;
 }
@@ -531,6 +543,7 @@ static uint16_t* tex_half(glava_b200* r, int b) { return r->d_tex + (size_t) b *
 static int sync_all(glava_b200* r) {
     CU(cudaStreamSynchronize(r->spec_stream));
     CU(cudaStreamSynchronize(r->stream));
+    if (r->out_stream) CU(cudaStreamSynchronize(r->out_stream));
     return 0;
 }
 
@@ -838,8 +851,41 @@ int glava_b200_readback_async(glava_b200* r, int stream, uint8_t* rgba) {
     clear_error();
     if (!r || !rgba || stream < 0 || stream >= r->batch) return fail(GLAVA_B200_EINVAL, "glava_b200_readback_async: bad arguments");
     CU(cudaSetDevice(r->device));
-    size_t frame = (size_t) r->p.w * r->p.h * 4;
-    CU(cudaMemcpyAsync(rgba, r->d_fb + frame * (size_t) (stream % r->slots), frame, cudaMemcpyDeviceToHost, r->stream));
+    const size_t frame = (size_t) r->p.w * r->p.h * 4;
+    if (!r->out_stream) {
+        CU(cudaStreamCreateWithFlags(&r->out_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventCreateWithFlags(&r->ev_stage_ready[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&r->ev_stage_free[i], cudaEventDisableTiming));
+        }
+    }
+    if (r->stage_bytes != frame) {                       // first use, or the geometry changed (glava_b200_sizereq)
+        CU(cudaStreamSynchronize(r->out_stream));
+        for (int i = 0; i < 2; ++i) { if (r->d_stage[i]) cudaFree(r->d_stage[i]); r->d_stage[i] = nullptr; }
+        r->stage_bytes = 0;
+        for (int i = 0; i < 2; ++i) CU(cudaMalloc((void**) &r->d_stage[i], frame));
+        r->stage_bytes = frame;
+    }
+    const int i = r->out_cur;
+    // the frame is snapshotted on the raster stream (ordered after the raster that produced it, before the next one
+    // overwrites the slot); the slow PCIe leg then runs from the snapshot on its own stream
+    CU(cudaStreamWaitEvent(r->stream, r->ev_stage_free[i], 0));
+    CU(cudaMemcpyAsync(r->d_stage[i], r->d_fb + frame * (size_t) (stream % r->slots), frame, cudaMemcpyDeviceToDevice, r->stream));
+    CU(cudaEventRecord(r->ev_stage_ready[i], r->stream));
+    CU(cudaStreamWaitEvent(r->out_stream, r->ev_stage_ready[i], 0));
+    CU(cudaMemcpyAsync(rgba, r->d_stage[i], frame, cudaMemcpyDeviceToHost, r->out_stream));
+    CU(cudaEventRecord(r->ev_stage_free[i], r->out_stream));
+    r->out_cur = i ^ 1;
+    return 0;
+}
+
+// Orders everything enqueued on the handle's stream from now on after the read-backs issued so far (their PCIe leg runs
+// on a separate stream): an event recorded on glava_b200_cuda_stream() after this call covers them.
+int glava_b200_readback_fence(glava_b200* r) {
+    if (!r) return fail(GLAVA_B200_EINVAL, "null argument");
+    if (!r->out_stream) return 0;
+    CU(cudaSetDevice(r->device));
+    for (int i = 0; i < 2; ++i) CU(cudaStreamWaitEvent(r->stream, r->ev_stage_free[i], 0));
     return 0;
 }
 

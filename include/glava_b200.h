@@ -180,8 +180,12 @@ int glava_b200_sync(glava_b200* r);
 /* Outputs.  Frame layout: RGBA8, [h][w][4] bytes, row 0 = bottom row (GL window coordinates),
  * byte order R,G,B,A. */
 int glava_b200_readback(glava_b200* r, int stream, uint8_t* rgba);              /* one stream's frame -> HOST */
-int glava_b200_readback_async(glava_b200* r, int stream, uint8_t* rgba);        /* same, enqueued on the handle's stream:
-                                                                                   rgba (pinned) is valid after glava_b200_sync */
+int glava_b200_readback_async(glava_b200* r, int stream, uint8_t* rgba);        /* same, asynchronous: the frame is snapshotted on the
+                                                                                   handle's stream (D2D) and copied out on a separate
+                                                                                   one, under the next update's kernels; rgba (pinned)
+                                                                                   is valid after glava_b200_sync */
+int glava_b200_readback_fence(glava_b200* r);                                   /* orders later work on glava_b200_cuda_stream() after
+                                                                                   the read-backs issued so far (for event timing) */
 int glava_b200_spectrum(glava_b200* r, float* out_l, float* out_r);             /* HOST [batch][n]: pipeline-A result
                                                                                    (accel_fft 0) or raw transform_fft output (1);
                                                                                    n / bufscale entries per stream */

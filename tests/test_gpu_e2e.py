@@ -65,3 +65,25 @@ def test_device_pointer_entry_point_matches_host_entry_point(built):
         for s in (0, 7):
             assert np.array_equal(a.readback(s), b.readback(s))
         assert a.launch_count >= 2 and b.launch_count >= 2
+
+
+def test_async_readback_snapshots_each_frame_before_the_next_update_overwrites_it(built):
+    """readback_async copies out on its own stream while the next update's kernels run: every step's frame must still be
+    the frame of THAT step (snapshot on the raster stream), for more read-backs in flight than staging buffers"""
+    n, batch, steps = 1024, 2, 7
+    p = g.default_params("bars", n=n, w=640, h=360, lazy_smooth=1)
+    rings_a, rings_b = g.StreamRings(batch, n), g.StreamRings(batch, n)
+    bufs = [g.pinned_empty((360, 640, 4), np.uint8) for _ in range(steps)]
+    want = []
+    with g.Renderer(p, batch=batch) as a, g.Renderer(p, batch=batch) as b:
+        for i in range(steps):
+            rings_a.advance(); rings_b.advance()
+            a.update(rings_a.lb, rings_a.rb, True)
+            a.readback_async(i % batch, bufs[i])
+            b.update(rings_b.lb, rings_b.rb, True)
+            want.append(b.readback(i % batch).copy())
+        a.readback_fence()
+        a.sync()
+        for i in range(steps):
+            assert np.array_equal(bufs[i], want[i]), i
+        assert not np.array_equal(want[0], want[2])                        # the frames do differ from step to step
