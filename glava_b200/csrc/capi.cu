@@ -277,11 +277,16 @@ static int build_tables(glava_b200* r) {
             if (getenv("GLAVA_B200_NO_EPI_PRUNE")) r->epi_n = 0;
             const size_t tab_elems = 2 * tap_max * cnt;
             if (tab_elems * sizeof(TapEntry) <= (size_t) 64 << 20 && !getenv("GLAVA_B200_NO_TAPTAB")) {
-                std::vector<TapEntry> tab(tab_elems, TapEntry { -1, 0.0f });
+                std::vector<TapEntry> tab(tab_elems, TapEntry { 0, 0.0f });
                 for (size_t c = 0; c < 2; ++c)
                     for (size_t k = 0; k < cnt; ++k) {
                         const std::vector<TapEntry>& v = taps[c * cnt + k];
-                        for (size_t j = 0; j < v.size(); ++j) tab[(c * tap_max + j) * cnt + k] = v[j];
+                        for (size_t j = 0; j < v.size(); ++j) {
+                            // a tap outside the texture fetches 0: texel * w = +0 either way, so it is stored as (index 0,
+                            // weight 0) and the kernels need no range test; its weight still counts in tap_wsum
+                            const bool inside = v[j].idx >= 0 && v[j].idx < p.n;
+                            tab[(c * tap_max + j) * cnt + k] = inside ? v[j] : TapEntry { 0, 0.0f };
+                        }
                     }
                 if ((rc = dev_alloc(r, (void**) &r->d_tap_tab, tab.size() * sizeof(TapEntry), false)) != 0) return rc;
                 if ((rc = dev_alloc(r, (void**) &r->d_tap_cnt, tcnt.size() * sizeof(int), false)) != 0) return rc;
@@ -603,6 +608,7 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
         a.need = (p.lazy_smooth && r->d_need) ? r->d_need : nullptr; a.need_count = r->need_count;
         a.tap_tab = a.need ? r->d_tap_tab : nullptr; a.tap_cnt = r->d_tap_cnt; a.tap_wsum = r->d_tap_wsum; a.tap_max = r->tap_max;
         a.epi_n = a.need ? r->epi_n : 0;
+        { static int ku = -1; if (ku < 0) { const char* e = getenv("GLAVA_B200_TAP_KU"); ku = e ? atoi(e) : 8; } a.tap_ku = ku; }
         a.csr = (a.need && a.tap_tab) ? r->d_csr : nullptr; a.csr_bytes = r->csr_bytes; a.csr_idx_off = r->csr_idx_off; a.csr_off_off = r->csr_off_off;
         a.batch = r->batch; a.update = r->updates;
         const int F = p.avg_frames;

@@ -49,6 +49,7 @@ struct SpectrumArgs {
     const int*   tap_cnt;       // [2][need_count]
     const float* tap_wsum;      // [2][need_count]  sum of the weights in loop order
     int       tap_max;
+    int       tap_ku;           // table entries a thread keeps in flight (8, 4 or 2)
     int       epi_n;            // lazy K5: number of leading bins whose gravity/average state can reach a sampled texel (0 = all)
     // the same taps as one blob per channel, small enough to live in shared memory (loaded by the TMA engine while the
     // FFT runs): [float w[csr_total]] [uint16 idx[csr_total]] [int off[need_count + 1]], texel-major ("CSR"); nullptr = unused

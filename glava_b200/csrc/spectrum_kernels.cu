@@ -319,30 +319,36 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
             // coalesced 8-byte load, one shared-memory texel fetch, a multiply and an add
             const int* need = a.need + (size_t) ch * a.need_count;
             const TapEntry* tab = a.tap_tab + (size_t) ch * a.tap_max * a.need_count;
-            for (int k = tid; k < a.need_count; k += T) {
-                const int x = need[k];
-                if (x < 0 || x >= N) continue;
-                const int cnt = a.tap_cnt[(size_t) ch * a.need_count + k];
-                SmoothAcc acc; acc.init();
-                // a thread's taps are a serial float sum, but the table loads are independent of it: fetch KU entries
-                // (one L2 round trip) before consuming them, in the GLSL loop's order
-                constexpr int KU = 8;
-                const int2* col = reinterpret_cast<const int2*>(tab) + k;
-                int j = 0;
-                for (; j + KU <= cnt; j += KU) {
-                    int2 e[KU];
+            // a thread's taps are a serial float sum, but the table loads are independent of it: fetch KU entries (one
+            // L2 round trip) before consuming them, in the GLSL loop's order.  (A tap outside the texture is stored as
+            // index 0 / weight 0: no range test on the chain.)
+            auto sums = [&](auto ku_tag) {
+                constexpr int KU = decltype(ku_tag)::value;
+                for (int k = tid; k < a.need_count; k += T) {
+                    const int x = need[k];
+                    if (x < 0 || x >= N) continue;
+                    const int cnt = a.tap_cnt[(size_t) ch * a.need_count + k];
+                    SmoothAcc acc; acc.init();
+                    const int2* col = reinterpret_cast<const int2*>(tab) + k;
+                    int j = 0;
+                    for (; j + KU <= cnt; j += KU) {
+                        int2 e[KU];
 #pragma unroll
-                    for (int q = 0; q < KU; ++q) e[q] = __ldg(col + (size_t) (j + q) * a.need_count);
+                        for (int q = 0; q < KU; ++q) e[q] = __ldg(col + (size_t) (j + q) * a.need_count);
 #pragma unroll
-                    for (int q = 0; q < KU; ++q) acc.add_noweight(fetch16(av, N, e[q].x), __int_as_float(e[q].y));
+                        for (int q = 0; q < KU; ++q) acc.add_noweight(from16(av[e[q].x]), __int_as_float(e[q].y));
+                    }
+                    for (; j < cnt; ++j) {
+                        const int2 e = __ldg(col + (size_t) j * a.need_count);
+                        acc.add_noweight(from16(av[e.x]), __int_as_float(e.y));
+                    }
+                    acc.weight = a.tap_wsum[(size_t) ch * a.need_count + k];
+                    tex[x] = (uint16_t) unorm16(acc.result(sp));
                 }
-                for (; j < cnt; ++j) {
-                    const int2 e = __ldg(col + (size_t) j * a.need_count);
-                    acc.add_noweight(fetch16(av, N, e.x), __int_as_float(e.y));
-                }
-                acc.weight = a.tap_wsum[(size_t) ch * a.need_count + k];
-                tex[x] = (uint16_t) unorm16(acc.result(sp));
-            }
+            };
+            if (a.tap_ku >= 8) sums(std::integral_constant<int, 8>());
+            else if (a.tap_ku >= 4) sums(std::integral_constant<int, 4>());
+            else sums(std::integral_constant<int, 2>());
         } else if (a.need) {
             const int* need = a.need + (size_t) ch * a.need_count;
             for (int k = tid; k < a.need_count; k += T) {

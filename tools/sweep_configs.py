@@ -18,7 +18,7 @@ except Exception:
 FB_BUDGET = 48e9          # bytes of framebuffer kept resident per GPU; beyond that a ring of slots
 
 
-def run(module, n, w, h, batch, steps=8):
+def run(module, n, w, h, batch, steps=16):
     p = g.default_params(module, n=n, w=w, h=h, lazy_smooth=1)
     frame = w * h * 4
     if batch * frame > FB_BUDGET:
@@ -28,11 +28,11 @@ def run(module, n, w, h, batch, steps=8):
     x = (torch.rand(batch, n, device="cuda") - 0.5) * 0.2
     y = (torch.rand(batch, n, device="cuda") - 0.5) * 0.2
     torch.cuda.synchronize()
-    for _ in range(3):
+    for _ in range(5):
         r.update_device(x.data_ptr(), y.data_ptr(), True)
     r.sync()
     r.set_timing(True)
-    for _ in range(4):
+    for _ in range(10):
         r.update_device(x.data_ptr(), y.data_ptr(), False)
     iso = r.kernel_times()
     r.set_timing(False)
