@@ -156,7 +156,19 @@ def main():
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL writes its banner ("NCCL version ...") straight to fd 1 when the communicator is created; stdout must
+        # carry the one JSON line only, so communicator creation (init + first collective) runs with fd 1 -> fd 2
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier(device_ids=[local])
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     batch, K, Wm = args.batch, args.steps, args.warmup
     p = g.default_params(MODULE, n=N, w=W, h=H)
