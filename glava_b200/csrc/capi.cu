@@ -6,6 +6,7 @@
 // in glava_b200_new and stays resident in HBM.
 #include "internal.h"
 #include "raster_core.h"
+#include "chain_core.h"
 
 #include <cuda_runtime.h>
 
@@ -222,24 +223,11 @@ static int build_tables(glava_b200* r) {
     r->tap_max = 0; r->epi_n = 0; r->d_geo = nullptr; r->geo_box[0] = r->geo_box[1] = r->geo_box[2] = r->geo_box[3] = 0;
     if (p.transform_smooth) {
         // transform_smooth's sampling window of output t (render.c:700-707) depends on t and the parameters only:
-        // evaluated here once, with the same libm calls and types as the reference (log -> float, powf, floor, ceil)
-        const double E = 2.7182818284590452353;                              // render.c:692
+        // evaluated once on the host (chain_core.h), with the same libm calls and types as the reference
         const int sz = p.n;
-        int asz = (int) ceil(sz / p.smooth_ratio);
-        if (asz > sz) asz = sz;
-        std::vector<int2> tab((size_t) sz);
-        int lim = asz;
-        for (int t = 0; t < asz; ++t) {
-            float db = log(t);
-            float lo = db - p.smooth_distance; if (!(lo > 0)) lo = 0;
-            int smin = (int) floor(powf(E, lo));
-            int smax = (int) ceil(powf(E, db + p.smooth_distance));
-            if (smax > sz - 1) smax = sz - 1;
-            tab[t] = make_int2(smin, smax);
-            if (smax + 1 > lim) lim = smax + 1;
-        }
-        r->ts_asz = asz; r->ts_lim = lim;
-        CU(cudaMemcpyAsync(r->d_ts_tab, tab.data(), (size_t) sz * sizeof(int2), cudaMemcpyHostToDevice, r->stream));
+        std::vector<SmoothWin> tab;
+        r->ts_asz = transform_smooth_windows(sz, p.smooth_distance, p.smooth_ratio, &tab, &r->ts_lim);
+        CU(cudaMemcpyAsync(r->d_ts_tab, tab.data(), (size_t) sz * sizeof(SmoothWin), cudaMemcpyHostToDevice, r->stream));
         CU(cudaStreamSynchronize(r->stream));
     }
     if (p.lazy_smooth && !r->post_chain) {
@@ -650,10 +638,7 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
         const int b = r->tex_cur ^ 1;
         uint16_t* dst = p.smooth_pass ? r->d_av : tex_half(r, b);
         if (r->interp_on) {
-            const float fr = p.fr > 0.0f ? p.fr : p.ur;
-            const float uratio = p.ur / fr;                                   // render.c:1761
-            float mod = uratio * (float) r->kcounter;                         // render.c:1804
-            if (mod > 1.0f) mod = 1.0f;
+            const float mod = keyframe_mod(p.ur, p.fr > 0.0f ? p.fr : p.ur, r->kcounter);   // render.c:1761,1804
             rc = launch_upload(r->d_key[r->key_start], r->d_key[r->key_end], mod, dst, total, r->spec_stream);
         } else {
             rc = launch_upload(chain_out, nullptr, 0.0f, dst, total, r->spec_stream);

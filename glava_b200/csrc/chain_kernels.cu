@@ -5,7 +5,7 @@
 // They are small, off the headline path, and run as their own kernels between the fused spectrum kernel
 // (which then only produces the float chain result) and the K5 smoothing kernel.
 #include "internal.h"
-#include "spectrum_core.h"
+#include "chain_core.h"
 
 #include <cuda_runtime.h>
 
@@ -19,10 +19,7 @@ __global__ void bufscale_kernel(const float* __restrict__ in_l, const float* __r
     const float* in = blockIdx.y ? in_r : in_l;
     float* out = blockIdx.y ? out_r : out_l;
     // [batch][n_in] -> [batch][n_in / k]: n_in is a multiple of k, so output i reads inputs [i*k, i*k + k)
-    const float* src = in + i * (size_t) k;
-    float accum = 0.0f;
-    for (int a = 0; a < k; ++a) accum += src[a];
-    out[i] = accum / (float) k;
+    out[i] = bufscale_mean(in + i * (size_t) k, k);
 }
 
 int launch_bufscale(const float* in_l, const float* in_r, float* out_l, float* out_r, int batch, int n_in, int k,
@@ -40,24 +37,12 @@ int launch_bufscale(const float* in_l, const float* in_r, float* out_l, float* o
 // each mean is a float sum in index order.  {smin, smax} depend on t and the parameters only (host table).
 // One CTA per plane: the lanes stage the plane's head in shared memory, one thread walks it.
 __global__ void __launch_bounds__(32)
-transform_smooth_kernel(float* __restrict__ planes, int n, const int2* __restrict__ tab, int asz, int lim) {
+transform_smooth_kernel(float* __restrict__ planes, int n, const SmoothWin* __restrict__ tab, int asz, int lim) {
     extern __shared__ float ts_sm[];
     float* b = planes + (size_t) blockIdx.x * n;
     for (int i = threadIdx.x; i < lim; i += 32) ts_sm[i] = b[i];
     __syncwarp();
-    if (threadIdx.x == 0) {
-        for (int t = 0; t < asz; ++t) {
-            const int2 e = __ldg(tab + t);
-            float avg = 0.0f;
-            int count = 0;
-            for (int s = e.x; s <= e.y; ++s) {
-                const float v = ts_sm[s];
-                if (v != 0.0f) { avg += v; ++count; }      // `if (b[s])`: true for NaN, false for +-0
-            }
-            avg = avg / (float) count;                       // count == 0: 0/0 = NaN, as the reference (t = 0 always)
-            ts_sm[t] = avg;
-        }
-    }
+    if (threadIdx.x == 0) transform_smooth_serial(ts_sm, tab, asz);
     __syncwarp();
     for (int i = threadIdx.x; i < asz; i += 32) b[i] = ts_sm[i];
 }
@@ -68,7 +53,7 @@ int launch_transform_smooth(float* d_planes, int n, const void* d_tab, int asz, 
         cudaError_t e = cudaFuncSetAttribute(transform_smooth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "transform_smooth smem attribute: %s", cudaGetErrorString(e));
     }
-    transform_smooth_kernel<<<count, 32, smem, (cudaStream_t) stream>>>(d_planes, n, (const int2*) d_tab, asz, lim);
+    transform_smooth_kernel<<<count, 32, smem, (cudaStream_t) stream>>>(d_planes, n, (const SmoothWin*) d_tab, asz, lim);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "transform_smooth kernel launch: %s", cudaGetErrorString(e));
     return 0;
@@ -81,8 +66,8 @@ __global__ void upload_kernel(const float* __restrict__ s, const float* __restri
     const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     float v = s[i];
-    if (e) v = v + ((e[i] - v) * mod);
-    out[i] = (uint16_t) unorm16(v);
+    if (e) v = keyframe_lerp(v, e[i], mod);
+    out[i] = (uint16_t) upload_texel(v);
 }
 
 int launch_upload(const float* d_s, const float* d_e, float mod, uint16_t* d_out, size_t total, void* stream) {

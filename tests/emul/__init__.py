@@ -29,6 +29,9 @@ def lib():
         L.emul_smooth.argtypes = [vp, vp, vp]
         L.emul_raster.argtypes = [vp, vp, vp, vp, i32, i32]
         L.emul_raster_fast.argtypes = [vp, vp, vp, vp]
+        L.emul_bufscale.argtypes = [vp, i32, i32, vp]
+        L.emul_transform_smooth.argtypes = [vp, i32, C.c_float, C.c_float]
+        L.emul_upload.argtypes = [vp, vp, i32, C.c_float, C.c_float, i32, vp]
         _lib = L
     return _lib
 
@@ -72,4 +75,25 @@ def raster(params, tex_l, tex_r, fast=False):
         assert lib().emul_raster_fast(C.addressof(params), tl.ctypes.data, tr.ctypes.data, out.ctypes.data) == 0
     else:
         lib().emul_raster(C.addressof(params), tl.ctypes.data, tr.ctypes.data, out.ctypes.data, 0, params.h)
+    return out
+
+
+def bufscale(pcm, k):
+    x = np.ascontiguousarray(pcm, dtype=np.float32)
+    out = np.empty(x.shape[0] // k, np.float32)
+    lib().emul_bufscale(x.ctypes.data, x.shape[0], k, out.ctypes.data)
+    return out
+
+
+def transform_smooth(buf, smooth_distance=0.01, smooth_ratio=4.0):
+    b = np.array(buf, dtype=np.float32, copy=True)
+    lib().emul_transform_smooth(b.ctypes.data, b.shape[0], smooth_distance, smooth_ratio)
+    return b
+
+
+def upload(start, end, ur, fr, kcounter):
+    s = np.ascontiguousarray(start, dtype=np.float32)
+    e = None if end is None else np.ascontiguousarray(end, dtype=np.float32)
+    out = np.empty(s.shape[0], np.uint16)
+    lib().emul_upload(s.ctypes.data, None if e is None else e.ctypes.data, s.shape[0], ur, fr, kcounter, out.ctypes.data)
     return out

@@ -5,6 +5,7 @@
 // loop per __syncthreads phase).  Lets the CPU-only test tier check the kernels' maths against
 // the oracle before any GPU time is spent.  NOT part of libglava_b200.so and never loaded by it.
 #include "../../glava_b200/csrc/raster_core.h"
+#include "../../glava_b200/csrc/chain_core.h"
 
 #include <cmath>
 #include <cstring>
@@ -221,6 +222,22 @@ int emul_raster_fast(const glava_b200_params* pp, const uint16_t* tl, const uint
         return 0;
     }
     return -1;
+}
+
+// ---- optional rd_update stages (chain_core.h): the kernels' per-element functions driven the way the kernels do ----
+void emul_bufscale(const float* in, int n_in, int k, float* out) {
+    for (int i = 0; i < n_in / k; ++i) out[i] = bufscale_mean(in + (size_t) i * k, k);       // bufscale_kernel: thread i
+}
+void emul_transform_smooth(float* b, int sz, float smooth_distance, float smooth_ratio) {
+    std::vector<SmoothWin> tab; int lim = 0;
+    const int asz = transform_smooth_windows(sz, smooth_distance, smooth_ratio, &tab, &lim);   // capi.cu build_tables
+    std::vector<float> sm(b, b + lim);                                                         // kernel: head staged in smem
+    transform_smooth_serial(sm.data(), tab.data(), asz);
+    for (int i = 0; i < asz; ++i) b[i] = sm[i];
+}
+void emul_upload(const float* s, const float* e, int n, float ur, float fr, int kcounter, uint16_t* out) {
+    const float mod = keyframe_mod(ur, fr, kcounter);
+    for (int i = 0; i < n; ++i) out[i] = (uint16_t) upload_texel(e ? keyframe_lerp(s[i], e[i], mod) : s[i]);
 }
 
 }  // extern "C"

@@ -99,3 +99,39 @@ def test_module_options(orc_pm, module, over, built):
 def test_unorm_fetch_is_exact_division(built):
     """from8 / from16 use reciprocal + fma correction instead of a divide: must equal u / MAX for every u"""
     assert emul.lib().emul_unorm_fetch_mismatches() == 0
+
+
+# ---- optional rd_update stages: the product's chain_core.h arithmetic on the host against the oracle -------------
+def test_chain_core_bufscale_and_transform_smooth_bit_exact(orc, built):
+    from tests import emul
+    rng = np.random.default_rng(11)
+    for n in (256, 4096, 16384):
+        x = ((rng.random(n) - 0.5) * 0.9).astype(np.float32)
+        for k in (2, 4, 8):
+            assert np.array_equal(emul.bufscale(x, k), orc.bufscale(x, k))
+        y = (rng.random(n) ** 3).astype(np.float32); y[rng.random(n) < 0.25] = 0
+        for d, ratio in ((0.01, 4.0), (0.2, 2.0), (0.3, 1.0)):
+            assert np.array_equal(emul.transform_smooth(y, d, ratio), orc.transform_smooth(y, d, ratio), equal_nan=True)
+        z = np.zeros(n, np.float32)
+        assert np.array_equal(emul.transform_smooth(z), orc.transform_smooth(z), equal_nan=True)
+
+
+def test_chain_core_transform_smooth_vs_compiled_reference(ref, built):
+    from tests import emul
+    rng = np.random.default_rng(12)
+    y = (rng.random(2048) ** 2).astype(np.float32); y[rng.random(2048) < 0.3] = 0
+    assert np.array_equal(emul.transform_smooth(y, 0.05, 3.0), ref.smooth(y, 0.05, 3.0), equal_nan=True)
+
+
+def test_chain_core_keyframe_upload_bit_exact(orc, built):
+    from tests import emul
+    rng = np.random.default_rng(13)
+    s = (rng.random(1024) * 1.2 - 0.1).astype(np.float32); e = (rng.random(1024) * 1.2 - 0.1).astype(np.float32)
+    s[5] = np.nan
+    q = lambda v: np.where(v > 0, np.where(v < 1, (v * np.float32(65535.0) + np.float32(0.5)).astype(np.int64), 65535), 0).astype(np.uint16)
+    ur, fr = np.float32(86.1328125), np.float32(240.0)
+    for k in (0, 1, 2, 5):
+        with np.errstate(invalid="ignore"):
+            assert np.array_equal(emul.upload(s, e, ur, fr, k), q(orc.interp(s, e, ur, fr, k)))
+    with np.errstate(invalid="ignore"):
+        assert np.array_equal(emul.upload(s, None, ur, fr, 0), q(s)) and emul.upload(s, None, ur, fr, 0)[5] == 0   # NaN -> 0
