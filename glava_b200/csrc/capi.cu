@@ -82,6 +82,7 @@ struct glava_b200 {
     // constants
     double* d_window; float* d_twiddle; void* d_rowtab; int* d_need; int need_count;
     TapEntry* d_tap_tab; int* d_tap_cnt; float* d_tap_wsum; int tap_max; int epi_n;
+    K5Table k5; void* d_k5_blk; void* d_k5_ent; void* d_k5_wsum;   // full-plane K5 tap table (null: evaluate taps in the kernel)
     unsigned char* d_csr; int csr_bytes, csr_idx_off, csr_off_off;   // the same taps, texel-major, for the shared-memory path
     void* d_geo; int geo_box[4];   // polar geometry cache (radial / circle), see raster_kernels.cu
     uint32_t* d_texmm;             // circle: per-plane {min, max} of the sampled texture, refreshed before each raster
@@ -211,6 +212,63 @@ static void dev_free(glava_b200* r, void* ptr) {
     cudaFree(ptr);
 }
 
+// Full-plane K5 (every texel wanted: lazy_smooth = 0, circle, the optional-stage path): the taps of ALL n output
+// texels, evaluated once here with the code the kernel would run per tap (smooth_enumerate: a log, a divide and a sine
+// each), laid out per block of K5_BLOCK texels, tap-major, padded with zero-weight taps to the block's longest sum.
+static int build_k5_table(glava_b200* r) {
+    const glava_b200_params& p = r->p;
+    const SmoothParams sp = smooth_params(p);
+    const int n = p.n, nblk = (n + K5_BLOCK - 1) / K5_BLOCK;
+    std::vector<int4> blk((size_t) nblk);
+    std::vector<int2> ent;
+    std::vector<float> wsum((size_t) n, 0.0f);
+    std::vector<std::vector<TapEntry>> taps(K5_BLOCK);
+    int max_span = 1;
+    for (int b = 0; b < nblk; ++b) {
+        int lo = n, hi = -1; size_t longest = 0;
+        for (int t = 0; t < K5_BLOCK; ++t) {
+            taps[t].clear();
+            const int x = b * K5_BLOCK + t;
+            if (x >= n) continue;
+            float weight = 0.0f;
+            smooth_enumerate(sp, n, ((float) x + 0.5f) / (float) n, [&](int i, float w) {
+                weight += w;
+                // a tap outside the texture fetches 0: texel * w = +0 either way -> weight 0 (it still counts in wsum)
+                const bool inside = i >= 0 && i < n;
+                taps[t].push_back(TapEntry { inside ? i : -1, inside ? w : 0.0f });
+                if (inside) { if (i < lo) lo = i; if (i > hi) hi = i; }
+            });
+            wsum[x] = weight;
+            if (taps[t].size() > longest) longest = taps[t].size();
+        }
+        if (hi < lo) { lo = 0; hi = 0; }
+        const int span = hi - lo + 1;
+        if (span > max_span) max_span = span;
+        blk[b] = make_int4((int) ent.size(), (int) longest, lo, span);
+        const size_t base = ent.size();
+        ent.resize(base + longest * K5_BLOCK, make_int2(0, 0));                // padding: first staged texel, weight +0
+        for (int t = 0; t < K5_BLOCK; ++t)
+            for (size_t j = 0; j < taps[t].size(); ++j) {
+                const TapEntry& te = taps[t][j];
+                int wbits; memcpy(&wbits, &te.w, 4);
+                ent[base + j * K5_BLOCK + t] = make_int2(te.idx >= 0 ? te.idx - lo : 0, wbits);
+            }
+    }
+    const size_t smem = (size_t) K5_S_PLANES * max_span * sizeof(float);
+    if (smem > 200 * 1024 || ent.size() * sizeof(int2) > ((size_t) 256 << 20)) return 0;     // keep the in-kernel evaluation
+    int rc;
+    if ((rc = dev_alloc(r, &r->d_k5_blk, blk.size() * sizeof(int4), false)) != 0) return rc;
+    if ((rc = dev_alloc(r, &r->d_k5_ent, (ent.empty() ? 1 : ent.size()) * sizeof(int2), false)) != 0) return rc;
+    if ((rc = dev_alloc(r, &r->d_k5_wsum, wsum.size() * sizeof(float), false)) != 0) return rc;
+    CU(cudaMemcpyAsync(r->d_k5_blk, blk.data(), blk.size() * sizeof(int4), cudaMemcpyHostToDevice, r->stream));
+    if (!ent.empty()) CU(cudaMemcpyAsync(r->d_k5_ent, ent.data(), ent.size() * sizeof(int2), cudaMemcpyHostToDevice, r->stream));
+    CU(cudaMemcpyAsync(r->d_k5_wsum, wsum.data(), wsum.size() * sizeof(float), cudaMemcpyHostToDevice, r->stream));
+    CU(cudaStreamSynchronize(r->stream));
+    r->k5.blk = (const int4*) r->d_k5_blk; r->k5.ent = (const int2*) r->d_k5_ent; r->k5.wsum = (const float*) r->d_k5_wsum;
+    r->k5.smem_bytes = (int) smem;
+    return 0;
+}
+
 // Everything derived from the parameters that does not depend on the audio: the lazy-K5 need-list and tap
 // table, the bars / graph row-colour table, the polar geometry cache.  Called at creation and again by
 // glava_b200_reconfigure (the analogue of a `--pipe` uniform update, render.c:1846-2005).
@@ -218,6 +276,8 @@ static int build_tables(glava_b200* r) {
     const glava_b200_params& p = r->p;
     int rc;
     dev_free(r, r->d_need); dev_free(r, r->d_tap_tab); dev_free(r, r->d_tap_cnt); dev_free(r, r->d_tap_wsum); dev_free(r, r->d_geo);
+    dev_free(r, r->d_k5_blk); dev_free(r, r->d_k5_ent); dev_free(r, r->d_k5_wsum);
+    r->d_k5_blk = r->d_k5_ent = r->d_k5_wsum = nullptr; memset(&r->k5, 0, sizeof(r->k5));
     dev_free(r, r->d_csr); r->d_csr = nullptr; r->csr_bytes = r->csr_idx_off = r->csr_off_off = 0;
     r->d_need = nullptr; r->need_count = 0; r->d_tap_tab = nullptr; r->d_tap_cnt = nullptr; r->d_tap_wsum = nullptr;
     r->tap_max = 0; r->epi_n = 0; r->d_geo = nullptr; r->geo_box[0] = r->geo_box[1] = r->geo_box[2] = r->geo_box[3] = 0;
@@ -320,6 +380,9 @@ static int build_tables(glava_b200* r) {
                 }
             }
         }
+    }
+    if (p.smooth_pass && (!r->d_need || r->post_chain) && !getenv("GLAVA_B200_NO_K5_TABLE")) {
+        if ((rc = build_k5_table(r)) != 0) return rc;
     }
     if (p.module == GLAVA_B200_MOD_BARS || p.module == GLAVA_B200_MOD_GRAPH) { if ((rc = launch_bars_rowtab(p, r->d_rowtab, r->stream)) != 0) return rc; ++r->launches; }
     // polar modules: cache the audio-independent per-pixel geometry (circle: only when the module samples a
@@ -458,6 +521,7 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     r->d_window = nullptr; r->d_twiddle = nullptr; r->d_rowtab = nullptr; r->d_need = nullptr; r->need_count = 0;
     r->d_tap_tab = nullptr; r->d_tap_cnt = nullptr; r->d_tap_wsum = nullptr; r->tap_max = 0; r->epi_n = 0;
     r->d_csr = nullptr; r->csr_bytes = r->csr_idx_off = r->csr_off_off = 0;
+    r->d_k5_blk = r->d_k5_ent = r->d_k5_wsum = nullptr; memset(&r->k5, 0, sizeof(r->k5));
     r->d_geo = nullptr; r->geo_box[0] = r->geo_box[1] = r->geo_box[2] = r->geo_box[3] = 0;
     r->d_spec = r->d_applied = r->d_ring_f = nullptr; r->d_gr_store = r->d_ring_u = r->d_tex = nullptr; r->d_av = nullptr; r->d_texmm = nullptr; r->d_fb = nullptr;
     for (int i = 0; i < 2; ++i) { r->d_pcm[i][0] = r->d_pcm[i][1] = nullptr; r->ev_copied[i] = r->ev_free[i] = nullptr; }
@@ -616,7 +680,7 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
         if ((rc = launch_spectrum(p, a, is_fft, r->spec_stream)) != 0) return rc;
         if (split_k5) {
             // wave uses plane 0 of each stream only; smoothing the (zero) odd planes too keeps the launch simple
-            if ((rc = launch_smooth_only(p, r->d_av, a.tex, r->batch * 2, r->spec_stream)) != 0) return rc;
+            if ((rc = launch_smooth_only(p, r->d_av, a.tex, r->batch * 2, r->spec_stream, &r->k5)) != 0) return rc;
             ++r->launches;
         }
         if (r->post_chain && p.transform_smooth) {                          // render.c:694-718, after the module's chain
@@ -646,7 +710,7 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
         if (rc) return rc;
         ++r->launches;
         if (p.smooth_pass) {
-            if ((rc = launch_smooth_only(p, r->d_av, tex_half(r, b), planes, r->spec_stream)) != 0) return rc;
+            if ((rc = launch_smooth_only(p, r->d_av, tex_half(r, b), planes, r->spec_stream, &r->k5)) != 0) return rc;
             ++r->launches;
         }
         if (modified && r->timing && (rc = timing_mark(r->ev_spec, r->spec_stream)) != 0) return rc;
@@ -914,7 +978,7 @@ int glava_b200_smooth_pass(glava_b200* r, const uint16_t* in, uint16_t* out, int
     int rc = 0;
     do {
         if (cudaMemcpyAsync(d_in, in, bytes, cudaMemcpyHostToDevice, r->stream) != cudaSuccess) { rc = fail(GLAVA_B200_ECUDA, "H2D copy failed"); break; }
-        if ((rc = launch_smooth_only(r->p, d_in, d_out, count, r->stream)) != 0) break;
+        if ((rc = launch_smooth_only(r->p, d_in, d_out, count, r->stream, &r->k5)) != 0) break;
         ++r->launches;
         if (cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, r->stream) != cudaSuccess) { rc = fail(GLAVA_B200_ECUDA, "D2H copy failed"); break; }
         cudaError_t se = cudaStreamSynchronize(r->stream);

@@ -78,7 +78,19 @@ struct RasterArgs {
 
 // ---- kernel launchers (spectrum_kernels.cu, raster_kernels.cu); `stream` is a cudaStream_t passed as void* ------------------
 int launch_spectrum(const glava_b200_params& p, const SpectrumArgs& a, bool is_fft, void* stream);
-int launch_smooth_only(const glava_b200_params& p, const uint16_t* d_in, uint16_t* d_out, int count, void* stream);
+// Full-plane K5 tap table (built once per parameter set, capi.cu): for every block of K5_BLOCK output texels the taps of
+// all its texels, tap-major and padded to the block's longest sum with zero-weight entries, so a warp's loads coalesce
+// and the tap loop is uniform.
+struct K5Table {
+    const int4*  blk;      // [n / K5_BLOCK] {first entry, taps per texel (padded), first input index, input span}
+    const int2*  ent;      // entries {input index - first input index, weight bits}
+    const float* wsum;     // [n] sum of a texel's weights in loop order
+    int smem_bytes;        // dynamic shared memory the kernel needs: K5_S * max span * sizeof(float)
+};
+#define K5_BLOCK 128
+#define K5_S_PLANES 8        // planes that share one tap (K5_S in spectrum_kernels.cu)
+int launch_smooth_only(const glava_b200_params& p, const uint16_t* d_in, uint16_t* d_out, int count, void* stream,
+                       const K5Table* table = nullptr);
 int launch_raster(const glava_b200_params& p, const RasterArgs& a, void* stream);
 int launch_bars_rowtab(const glava_b200_params& p, void* d_rowtab, void* stream);
 // geometry cache of the polar modules: box = {x0, y0, w, h}; returns bytes needed when d_geo == nullptr

@@ -483,7 +483,61 @@ k5_planes_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, in
     for (int s = 0; s < K5_S; ++s)
         if (s < npl) out[(size_t) (pl0 + s) * n + x] = (uint16_t) unorm16(acc[s].result(sp));
 }
-int launch_smooth_only(const glava_b200_params& p, const uint16_t* d_in, uint16_t* d_out, int count, void* stream) {
+// The same pass from the precomputed table (K5Table): no log / divide / sine per tap, the staged input converted to
+// float once; per tap one coalesced 8-byte load, then per plane a shared-memory fetch, a multiply and the ordered add.
+static_assert(K5_S == K5_S_PLANES && K5_XT == K5_BLOCK, "K5 table layout and kernel tile must agree");
+template <bool AVG_ONLY>
+__global__ void __launch_bounds__(K5_BLOCK)
+k5_table_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int n, int count, const K5Table tb,
+                const SmoothParams sp) {
+    float* seg = reinterpret_cast<float*>(glb_smem);                  // [K5_S][span] texels as float
+    const int4 d = __ldg(tb.blk + blockIdx.x);
+    const int base = d.x, taps = d.y, lo = d.z, span = d.w;
+    const int pl0 = blockIdx.y * K5_S, npl = min(K5_S, count - pl0);
+    for (int i = threadIdx.x; i < K5_S * span; i += K5_BLOCK) {
+        const int pl = i / span, k = i - pl * span;
+        seg[i] = pl < npl ? from16(in[(size_t) (pl0 + pl) * n + lo + k]) : 0.0f;
+    }
+    __syncthreads();
+    const int x = blockIdx.x * K5_BLOCK + threadIdx.x;
+    if (x >= n) return;
+    SmoothAcc acc[K5_S];
+#pragma unroll
+    for (int s = 0; s < K5_S; ++s) acc[s].init();
+    const int2* col = tb.ent + base + threadIdx.x;
+    for (int j = 0; j < taps; ++j) {
+        const int2 e = __ldg(col + (size_t) j * K5_BLOCK);
+        const float w = __int_as_float(e.y);
+#pragma unroll
+        for (int s = 0; s < K5_S; ++s) {
+            const float v = seg[s * span + e.x] * w;
+            acc[s].avg += v;
+            if (!AVG_ONLY) { if (acc[s].vmax < v) acc[s].vmax = v; }
+        }
+    }
+    const float weight = __ldg(tb.wsum + x);
+#pragma unroll
+    for (int s = 0; s < K5_S; ++s) {
+        acc[s].weight = weight;
+        if (s < npl) out[(size_t) (pl0 + s) * n + x] = (uint16_t) unorm16(acc[s].result(sp));
+    }
+}
+
+int launch_smooth_only(const glava_b200_params& p, const uint16_t* d_in, uint16_t* d_out, int count, void* stream,
+                       const K5Table* table) {
+    if (table && table->blk) {
+        const SmoothParams sp = smooth_params(p);
+        auto kern = sp.sample_mode == 0 ? k5_table_kernel<true> : k5_table_kernel<false>;
+        if (table->smem_bytes > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, table->smem_bytes);
+            if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "cudaFuncSetAttribute(k5 table): %s", cudaGetErrorString(e));
+        }
+        dim3 grid((p.n + K5_BLOCK - 1) / K5_BLOCK, (count + K5_S - 1) / K5_S);
+        kern<<<grid, K5_BLOCK, table->smem_bytes, (cudaStream_t) stream>>>(d_in, d_out, p.n, count, *table, sp);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "smooth (table) kernel launch: %s", cudaGetErrorString(e));
+        return 0;
+    }
     // worst-case span: the last block's taps, bounded by the whole plane
     const SmoothParams sp = smooth_params(p);
     const float fn = (float) p.n;
