@@ -7,6 +7,7 @@
 #include "internal.h"
 #include "raster_core.h"
 #include "chain_core.h"
+#include "tables.h"
 
 #include <cuda_runtime.h>
 
@@ -159,53 +160,6 @@ void* glava_b200_host_alloc(size_t bytes) {
 }
 void glava_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
 
-// Lazy K5: the texels of the smoothed R16 texture the module's fragment shader can sample.
-// Built with the SAME coordinate helpers the kernels use (raster_core.h), on the host.
-// Returns false when every texel may be needed (circle: continuous angle -> position).
-static bool build_need_list(const glava_b200_params& p, std::vector<int>* lists /* [2] */) {
-    if (!p.smooth_pass) return false;
-    std::vector<char> mark[2];
-    mark[0].assign(p.n + 1, 0); mark[1].assign(p.n + 1, 0);
-    auto hit = [&](int chan, float coord) {
-        int i = (int) glm_rint(coord * (float) p.n);
-        if (i >= 0 && i < p.n) mark[chan][i] = 1;
-    };
-    switch (p.module) {
-        case GLAVA_B200_MOD_BARS: {
-            int aw = p.bars_mirror_yx ? p.h : p.w;
-            for (int x = 0; x < aw; ++x) {
-                int chan; float pp; bool inner;
-                if (bars_column_coord(p, (float) x + 0.5f, aw, &chan, &pp, &inner)) hit(chan, pp);
-            }
-            break;
-        }
-        case GLAVA_B200_MOD_RADIAL:
-            for (int k = 0; k <= p.radial_nbars; ++k) {
-                float pos = (float) k / (float) (p.radial_nbars / 2);
-                hit(0, pos); hit(1, pos);
-            }
-            break;
-        case GLAVA_B200_MOD_GRAPH: {
-            float pixel = 1.0f / (float) p.w;
-            for (int x = 0; x < p.w; ++x) {
-                int chan; float c = graph_column_coord(p, x, &chan);
-                hit(chan, g_max(c - pixel, 0.0f)); hit(chan, c); hit(chan, g_min(c + pixel, 1.0f));
-            }
-            break;
-        }
-        case GLAVA_B200_MOD_WAVE:
-            for (int x = -1; x <= p.w; ++x) mark[0][wave_tex_index(p.n, (float) x / (float) p.w)] = 1;
-            break;
-        case GLAVA_B200_MOD_TEST: break;            // samples nothing that reaches the output
-        default: return false;
-    }
-    for (int c = 0; c < 2; ++c) {
-        lists[c].clear();
-        for (int i = 0; i < p.n; ++i) if (mark[c][i]) lists[c].push_back(i);
-    }
-    return true;
-}
-
 static void dev_free(glava_b200* r, void* ptr) {
     if (!ptr) return;
     for (size_t i = 0; i < r->allocs.size(); ++i) if (r->allocs[i] == ptr) { r->allocs.erase(r->allocs.begin() + i); break; }
@@ -213,56 +167,20 @@ static void dev_free(glava_b200* r, void* ptr) {
 }
 
 // Full-plane K5 (every texel wanted: lazy_smooth = 0, circle, the optional-stage path): the taps of ALL n output
-// texels, evaluated once here with the code the kernel would run per tap (smooth_enumerate: a log, a divide and a sine
-// each), laid out per block of K5_BLOCK texels, tap-major, padded with zero-weight taps to the block's longest sum.
+// texels (tables.h build_k5_table_host), uploaded for k5_table_kernel.
 static int build_k5_table(glava_b200* r) {
-    const glava_b200_params& p = r->p;
-    const SmoothParams sp = smooth_params(p);
-    const int n = p.n, nblk = (n + K5_BLOCK - 1) / K5_BLOCK;
-    std::vector<int4> blk((size_t) nblk);
-    std::vector<int2> ent;
-    std::vector<float> wsum((size_t) n, 0.0f);
-    std::vector<std::vector<TapEntry>> taps(K5_BLOCK);
-    int max_span = 1;
-    for (int b = 0; b < nblk; ++b) {
-        int lo = n, hi = -1; size_t longest = 0;
-        for (int t = 0; t < K5_BLOCK; ++t) {
-            taps[t].clear();
-            const int x = b * K5_BLOCK + t;
-            if (x >= n) continue;
-            float weight = 0.0f;
-            smooth_enumerate(sp, n, ((float) x + 0.5f) / (float) n, [&](int i, float w) {
-                weight += w;
-                // a tap outside the texture fetches 0: texel * w = +0 either way -> weight 0 (it still counts in wsum)
-                const bool inside = i >= 0 && i < n;
-                taps[t].push_back(TapEntry { inside ? i : -1, inside ? w : 0.0f });
-                if (inside) { if (i < lo) lo = i; if (i > hi) hi = i; }
-            });
-            wsum[x] = weight;
-            if (taps[t].size() > longest) longest = taps[t].size();
-        }
-        if (hi < lo) { lo = 0; hi = 0; }
-        const int span = hi - lo + 1;
-        if (span > max_span) max_span = span;
-        blk[b] = make_int4((int) ent.size(), (int) longest, lo, span);
-        const size_t base = ent.size();
-        ent.resize(base + longest * K5_BLOCK, make_int2(0, 0));                // padding: first staged texel, weight +0
-        for (int t = 0; t < K5_BLOCK; ++t)
-            for (size_t j = 0; j < taps[t].size(); ++j) {
-                const TapEntry& te = taps[t][j];
-                int wbits; memcpy(&wbits, &te.w, 4);
-                ent[base + j * K5_BLOCK + t] = make_int2(te.idx >= 0 ? te.idx - lo : 0, wbits);
-            }
-    }
-    const size_t smem = (size_t) K5_S_PLANES * max_span * sizeof(float);
-    if (smem > 200 * 1024 || ent.size() * sizeof(int2) > ((size_t) 256 << 20)) return 0;     // keep the in-kernel evaluation
+    K5TableHost t;
+    build_k5_table_host(r->p, &t);
+    const size_t smem = (size_t) K5_S_PLANES * t.max_span * sizeof(float);
+    if (smem > 200 * 1024 || t.ent.size() * sizeof(K5Ent) > ((size_t) 256 << 20)) return 0;   // keep the in-kernel evaluation
+    static_assert(sizeof(K5Blk) == sizeof(int4) && sizeof(K5Ent) == sizeof(int2), "table records are read as int4 / int2");
     int rc;
-    if ((rc = dev_alloc(r, &r->d_k5_blk, blk.size() * sizeof(int4), false)) != 0) return rc;
-    if ((rc = dev_alloc(r, &r->d_k5_ent, (ent.empty() ? 1 : ent.size()) * sizeof(int2), false)) != 0) return rc;
-    if ((rc = dev_alloc(r, &r->d_k5_wsum, wsum.size() * sizeof(float), false)) != 0) return rc;
-    CU(cudaMemcpyAsync(r->d_k5_blk, blk.data(), blk.size() * sizeof(int4), cudaMemcpyHostToDevice, r->stream));
-    if (!ent.empty()) CU(cudaMemcpyAsync(r->d_k5_ent, ent.data(), ent.size() * sizeof(int2), cudaMemcpyHostToDevice, r->stream));
-    CU(cudaMemcpyAsync(r->d_k5_wsum, wsum.data(), wsum.size() * sizeof(float), cudaMemcpyHostToDevice, r->stream));
+    if ((rc = dev_alloc(r, &r->d_k5_blk, t.blk.size() * sizeof(K5Blk), false)) != 0) return rc;
+    if ((rc = dev_alloc(r, &r->d_k5_ent, (t.ent.empty() ? 1 : t.ent.size()) * sizeof(K5Ent), false)) != 0) return rc;
+    if ((rc = dev_alloc(r, &r->d_k5_wsum, t.wsum.size() * sizeof(float), false)) != 0) return rc;
+    CU(cudaMemcpyAsync(r->d_k5_blk, t.blk.data(), t.blk.size() * sizeof(K5Blk), cudaMemcpyHostToDevice, r->stream));
+    if (!t.ent.empty()) CU(cudaMemcpyAsync(r->d_k5_ent, t.ent.data(), t.ent.size() * sizeof(K5Ent), cudaMemcpyHostToDevice, r->stream));
+    CU(cudaMemcpyAsync(r->d_k5_wsum, t.wsum.data(), t.wsum.size() * sizeof(float), cudaMemcpyHostToDevice, r->stream));
     CU(cudaStreamSynchronize(r->stream));
     r->k5.blk = (const int4*) r->d_k5_blk; r->k5.ent = (const int2*) r->d_k5_ent; r->k5.wsum = (const float*) r->d_k5_wsum;
     r->k5.smem_bytes = (int) smem;
@@ -293,90 +211,31 @@ static int build_tables(glava_b200* r) {
     if (p.lazy_smooth && !r->post_chain) {
         std::vector<int> lists[2];
         if (build_need_list(p, lists)) {
-            size_t cnt = lists[0].size() > lists[1].size() ? lists[0].size() : lists[1].size();
-            if (cnt == 0) cnt = 1;
-            std::vector<int> flat(2 * cnt, -1);
-            for (int c = 0; c < 2; ++c) for (size_t i = 0; i < lists[c].size(); ++i) flat[c * cnt + i] = lists[c][i];
-            if ((rc = dev_alloc(r, (void**) &r->d_need, flat.size() * sizeof(int), false)) != 0) return rc;
-            CU(cudaMemcpyAsync(r->d_need, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, r->stream));
+            // need-list, K5 tap table (tap-major, for the L2 path) and its texel-major blob (tables.h)
+            LazyTables t;
+            build_lazy_tables(p, lists, &t);
+            if ((rc = dev_alloc(r, (void**) &r->d_need, t.need.size() * sizeof(int), false)) != 0) return rc;
+            CU(cudaMemcpyAsync(r->d_need, t.need.data(), t.need.size() * sizeof(int), cudaMemcpyHostToDevice, r->stream));
             CU(cudaStreamSynchronize(r->stream));
-            r->need_count = (int) cnt;
-            // K5 tap table: indices and weights of smooth_audio() for every needed texel.  They are a
-            // function of the parameters only, and gl_math.h evaluates bit-identically on host and
-            // device, so the table is built here once with the very code the kernel would run.
-            const SmoothParams sp = smooth_params(p);
-            std::vector<std::vector<TapEntry>> taps(2 * cnt);
-            std::vector<float> wsum(2 * cnt, 0.0f);
-            std::vector<int> tcnt(2 * cnt, 0);
-            size_t tap_max = 1;
-            for (size_t e = 0; e < 2 * cnt; ++e) {
-                const int x = flat[e];
-                if (x < 0) continue;
-                float weight = 0.0f;
-                std::vector<TapEntry>& v = taps[e];
-                smooth_enumerate(sp, p.n, ((float) x + 0.5f) / (float) p.n, [&](int i, float w) {
-                    weight += w;
-                    v.push_back(TapEntry { i, w });
-                });
-                wsum[e] = weight; tcnt[e] = (int) v.size();
-                if (v.size() > tap_max) tap_max = v.size();
-                for (const TapEntry& te : v) if (te.idx >= 0 && te.idx < p.n && te.idx + 1 > r->epi_n) r->epi_n = te.idx + 1;
-            }
-            if (getenv("GLAVA_B200_NO_EPI_PRUNE")) r->epi_n = 0;
-            const size_t tab_elems = 2 * tap_max * cnt;
-            if (tab_elems * sizeof(TapEntry) <= (size_t) 64 << 20 && !getenv("GLAVA_B200_NO_TAPTAB")) {
-                std::vector<TapEntry> tab(tab_elems, TapEntry { 0, 0.0f });
-                for (size_t c = 0; c < 2; ++c)
-                    for (size_t k = 0; k < cnt; ++k) {
-                        const std::vector<TapEntry>& v = taps[c * cnt + k];
-                        for (size_t j = 0; j < v.size(); ++j) {
-                            // a tap outside the texture fetches 0: texel * w = +0 either way, so it is stored as (index 0,
-                            // weight 0) and the kernels need no range test; its weight still counts in tap_wsum
-                            const bool inside = v[j].idx >= 0 && v[j].idx < p.n;
-                            tab[(c * tap_max + j) * cnt + k] = inside ? v[j] : TapEntry { 0, 0.0f };
-                        }
-                    }
-                if ((rc = dev_alloc(r, (void**) &r->d_tap_tab, tab.size() * sizeof(TapEntry), false)) != 0) return rc;
-                if ((rc = dev_alloc(r, (void**) &r->d_tap_cnt, tcnt.size() * sizeof(int), false)) != 0) return rc;
-                if ((rc = dev_alloc(r, (void**) &r->d_tap_wsum, wsum.size() * sizeof(float), false)) != 0) return rc;
-                CU(cudaMemcpyAsync(r->d_tap_tab, tab.data(), tab.size() * sizeof(TapEntry), cudaMemcpyHostToDevice, r->stream));
-                CU(cudaMemcpyAsync(r->d_tap_cnt, tcnt.data(), tcnt.size() * sizeof(int), cudaMemcpyHostToDevice, r->stream));
-                CU(cudaMemcpyAsync(r->d_tap_wsum, wsum.data(), wsum.size() * sizeof(float), cudaMemcpyHostToDevice, r->stream));
+            r->need_count = (int) t.cnt;
+            r->epi_n = getenv("GLAVA_B200_NO_EPI_PRUNE") ? 0 : t.epi_n;
+            if (t.tab.size() * sizeof(TapEntry) <= (size_t) 64 << 20 && !getenv("GLAVA_B200_NO_TAPTAB")) {
+                if ((rc = dev_alloc(r, (void**) &r->d_tap_tab, t.tab.size() * sizeof(TapEntry), false)) != 0) return rc;
+                if ((rc = dev_alloc(r, (void**) &r->d_tap_cnt, t.tcnt.size() * sizeof(int), false)) != 0) return rc;
+                if ((rc = dev_alloc(r, (void**) &r->d_tap_wsum, t.wsum.size() * sizeof(float), false)) != 0) return rc;
+                CU(cudaMemcpyAsync(r->d_tap_tab, t.tab.data(), t.tab.size() * sizeof(TapEntry), cudaMemcpyHostToDevice, r->stream));
+                CU(cudaMemcpyAsync(r->d_tap_cnt, t.tcnt.data(), t.tcnt.size() * sizeof(int), cudaMemcpyHostToDevice, r->stream));
+                CU(cudaMemcpyAsync(r->d_tap_wsum, t.wsum.data(), t.wsum.size() * sizeof(float), cudaMemcpyHostToDevice, r->stream));
                 CU(cudaStreamSynchronize(r->stream));
-                r->tap_max = (int) tap_max;
-                // Texel-major copy of the same taps, one blob per channel: [float w[total]] [u16 idx[total]] [int off[cnt + 1]].
-                // When it is small enough for two CTAs per SM to hold their channel's blob in shared memory next to the FFT
+                r->tap_max = (int) t.tap_max;
+                // When one channel's blob is small enough for two CTAs per SM to hold it in shared memory next to the FFT
                 // buffers, the kernel's serial per-texel sums read their taps from there (no L2 round trips on the chain).
-                size_t total = 0;
-                for (size_t c = 0; c < 2; ++c) { size_t t = 0; for (size_t k = 0; k < cnt; ++k) t += taps[c * cnt + k].size(); if (t > total) total = t; }
-                const size_t w_bytes = ((total * 4 + 15) / 16) * 16, i_bytes = ((total * 2 + 15) / 16) * 16, o_bytes = (((cnt + 1) * 4 + 15) / 16) * 16;
-                const size_t blob = w_bytes + i_bytes + o_bytes;
                 const int base = spectrum_smem_bytes(p.n);
-                if (base > 0 && base + blob <= (size_t) 112 * 1024 && !getenv("GLAVA_B200_NO_SMEM_TAPS")) {
-                    std::vector<unsigned char> host(2 * blob, 0);
-                    for (size_t c = 0; c < 2; ++c) {
-                        float* w = reinterpret_cast<float*>(host.data() + c * blob);
-                        uint16_t* ix = reinterpret_cast<uint16_t*>(host.data() + c * blob + w_bytes);
-                        int* off = reinterpret_cast<int*>(host.data() + c * blob + w_bytes + i_bytes);
-                        size_t at = 0;
-                        for (size_t k = 0; k < cnt; ++k) {
-                            off[k] = (int) at;
-                            for (const TapEntry& te : taps[c * cnt + k]) {
-                                // a tap outside the texture fetches 0 (texelFetch): texel * w = +0 either way, so it is
-                                // stored as (index 0, weight 0) and the kernel needs no range test; its weight still
-                                // counts in tap_wsum
-                                const bool inside = te.idx >= 0 && te.idx < p.n;
-                                w[at] = inside ? te.w : 0.0f;
-                                ix[at] = inside ? (uint16_t) te.idx : (uint16_t) 0;
-                                ++at;
-                            }
-                        }
-                        off[cnt] = (int) at;
-                    }
-                    if ((rc = dev_alloc(r, (void**) &r->d_csr, host.size(), false)) != 0) return rc;
-                    CU(cudaMemcpyAsync(r->d_csr, host.data(), host.size(), cudaMemcpyHostToDevice, r->stream));
+                if (base > 0 && base + t.blob <= (size_t) 112 * 1024 && !getenv("GLAVA_B200_NO_SMEM_TAPS")) {
+                    if ((rc = dev_alloc(r, (void**) &r->d_csr, t.csr.size(), false)) != 0) return rc;
+                    CU(cudaMemcpyAsync(r->d_csr, t.csr.data(), t.csr.size(), cudaMemcpyHostToDevice, r->stream));
                     CU(cudaStreamSynchronize(r->stream));
-                    r->csr_bytes = (int) blob; r->csr_idx_off = (int) w_bytes; r->csr_off_off = (int) (w_bytes + i_bytes);
+                    r->csr_bytes = (int) t.blob; r->csr_idx_off = (int) t.idx_off; r->csr_off_off = (int) t.off_off;
                 }
             }
         }

@@ -25,7 +25,10 @@ int  validate_params(const glava_b200_params* p);
 
 #define GLB_MAX_AVG_FRAMES 16
 
+#ifndef GLB_TAPENTRY_DEFINED
+#define GLB_TAPENTRY_DEFINED
 struct alignas(8) TapEntry { int idx; float w; };   // one tap of the K5 smoothing sum: texel index, weight
+#endif
 
 // ---- views handed to the kernels (all pointers are DEVICE pointers) ---------------------------
 // "channel plane" c = stream * 2 + ch (ch 0 = left, 1 = right); every per-channel array is
@@ -87,7 +90,9 @@ struct K5Table {
     const float* wsum;     // [n] sum of a texel's weights in loop order
     int smem_bytes;        // dynamic shared memory the kernel needs: K5_S * max span * sizeof(float)
 };
+#ifndef K5_BLOCK
 #define K5_BLOCK 128
+#endif
 #define K5_S_PLANES 8        // planes that share one tap (K5_S in spectrum_kernels.cu)
 int launch_smooth_only(const glava_b200_params& p, const uint16_t* d_in, uint16_t* d_out, int count, void* stream,
                        const K5Table* table = nullptr);

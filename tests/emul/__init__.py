@@ -29,6 +29,9 @@ def lib():
         L.emul_smooth.argtypes = [vp, vp, vp]
         L.emul_raster.argtypes = [vp, vp, vp, vp, i32, i32]
         L.emul_raster_fast.argtypes = [vp, vp, vp, vp]
+        L.emul_lazy_k5.argtypes = [vp, i32, i32, vp, vp, vp]
+        L.emul_lazy_epi_n.argtypes = [vp]
+        L.emul_k5_table.argtypes = [vp, vp, vp]
         L.emul_bufscale.argtypes = [vp, i32, i32, vp]
         L.emul_transform_smooth.argtypes = [vp, i32, C.c_float, C.c_float]
         L.emul_upload.argtypes = [vp, vp, i32, C.c_float, C.c_float, i32, vp]
@@ -96,4 +99,27 @@ def upload(start, end, ur, fr, kcounter):
     e = None if end is None else np.ascontiguousarray(end, dtype=np.float32)
     out = np.empty(s.shape[0], np.uint16)
     lib().emul_upload(s.ctypes.data, None if e is None else e.ctypes.data, s.shape[0], ur, fr, kcounter, out.ctypes.data)
+    return out
+
+
+def lazy_k5(p, chan, path, av):
+    """(texel indices, values) of the need-list texels of channel `chan`, through the tap-major table (path 0) or the
+    texel-major blob (path 1)"""
+    av = np.ascontiguousarray(av, dtype=np.uint16)
+    out = np.zeros(p.n, np.uint16); need = np.zeros(p.n, np.int32)
+    cnt = lib().emul_lazy_k5(C.byref(p), chan, path, av.ctypes.data, out.ctypes.data, need.ctypes.data)
+    if cnt < 0:
+        return None, None
+    idx = need[:cnt].copy()
+    return idx, out[idx]
+
+
+def lazy_epi_n(p):
+    return lib().emul_lazy_epi_n(C.byref(p))
+
+
+def k5_table(p, tex):
+    tex = np.ascontiguousarray(tex, dtype=np.uint16)
+    out = np.empty_like(tex)
+    lib().emul_k5_table(C.byref(p), tex.ctypes.data, out.ctypes.data)
     return out

@@ -6,6 +6,7 @@
 // the oracle before any GPU time is spent.  NOT part of libglava_b200.so and never loaded by it.
 #include "../../glava_b200/csrc/raster_core.h"
 #include "../../glava_b200/csrc/chain_core.h"
+#include "../../glava_b200/csrc/tables.h"
 
 #include <cmath>
 #include <cstring>
@@ -238,6 +239,76 @@ void emul_transform_smooth(float* b, int sz, float smooth_distance, float smooth
 void emul_upload(const float* s, const float* e, int n, float ur, float fr, int kcounter, uint16_t* out) {
     const float mod = keyframe_mod(ur, fr, kcounter);
     for (int i = 0; i < n; ++i) out[i] = (uint16_t) upload_texel(e ? keyframe_lerp(s[i], e[i], mod) : s[i]);
+}
+
+// ---- K5 from the precomputed tables (tables.h), walked the way the kernels walk them ------------------------------------
+// lazy K5 of one channel: out[x] for the need-list texels only (others left untouched); path 0 = tap-major table (the
+// spectrum kernel's L2 path), 1 = texel-major blob (its shared-memory path).  Returns the number of texels written.
+int emul_lazy_k5(const glava_b200_params* pp, int chan, int path, const uint16_t* av, uint16_t* out, int* need_out) {
+    const glava_b200_params& p = *pp;
+    std::vector<int> lists[2];
+    if (!build_need_list(p, lists)) return -1;
+    LazyTables t;
+    build_lazy_tables(p, lists, &t);
+    const SmoothParams sp = smooth_params(p);
+    const int N = p.n;
+    int written = 0;
+    for (size_t k = 0; k < t.cnt; ++k) {                                   // kernel: thread k (+ T, ...)
+        const int x = t.need[chan * t.cnt + k];
+        if (x < 0 || x >= N) continue;
+        SmoothAcc acc; acc.init();
+        if (path == 0) {
+            const TapEntry* col = t.tab.data() + (size_t) chan * t.tap_max * t.cnt + k;
+            const int cnt = t.tcnt[chan * t.cnt + k];
+            for (int j = 0; j < cnt; ++j) { const TapEntry e = col[(size_t) j * t.cnt]; acc.add_noweight(from16(av[e.idx]), e.w); }
+        } else {
+            const unsigned char* blob = t.csr.data() + (size_t) chan * t.blob;
+            const float* tw = reinterpret_cast<const float*>(blob);
+            const uint16_t* ti = reinterpret_cast<const uint16_t*>(blob + t.idx_off);
+            const int* to = reinterpret_cast<const int*>(blob + t.off_off);
+            for (int o = to[k]; o < to[k + 1]; ++o) acc.add_noweight(from16(av[ti[o]]), tw[o]);
+        }
+        acc.weight = t.wsum[chan * t.cnt + k];
+        out[x] = (uint16_t) unorm16(acc.result(sp));
+        if (need_out) need_out[written] = x;
+        ++written;
+    }
+    return written;
+}
+int emul_lazy_epi_n(const glava_b200_params* pp) {
+    std::vector<int> lists[2];
+    if (!build_need_list(*pp, lists)) return -1;
+    LazyTables t;
+    build_lazy_tables(*pp, lists, &t);
+    return t.epi_n;
+}
+// full-plane K5 of one plane through the per-block table, as k5_table_kernel does it (float staging, padded uniform loop)
+void emul_k5_table(const glava_b200_params* pp, const uint16_t* in, uint16_t* out) {
+    const glava_b200_params& p = *pp;
+    K5TableHost t;
+    build_k5_table_host(p, &t);
+    const SmoothParams sp = smooth_params(p);
+    const bool avg_only = sp.sample_mode == 0;
+    std::vector<float> seg;
+    for (size_t b = 0; b < t.blk.size(); ++b) {
+        const K5Blk d = t.blk[b];
+        seg.resize((size_t) d.span);
+        for (int k = 0; k < d.span; ++k) seg[k] = from16(in[d.lo + k]);
+        for (int tid = 0; tid < K5_BLOCK; ++tid) {
+            const int x = (int) b * K5_BLOCK + tid;
+            if (x >= p.n) continue;
+            SmoothAcc acc; acc.init();
+            for (int j = 0; j < d.taps; ++j) {
+                const K5Ent e = t.ent[(size_t) d.base + (size_t) j * K5_BLOCK + tid];
+                float w; memcpy(&w, &e.wbits, 4);
+                const float v = seg[e.idx] * w;
+                acc.avg += v;
+                if (!avg_only) { if (acc.vmax < v) acc.vmax = v; }
+            }
+            acc.weight = t.wsum[x];
+            out[x] = (uint16_t) unorm16(acc.result(sp));
+        }
+    }
 }
 
 }  // extern "C"

@@ -135,3 +135,57 @@ def test_chain_core_keyframe_upload_bit_exact(orc, built):
             assert np.array_equal(emul.upload(s, e, ur, fr, k), q(orc.interp(s, e, ur, fr, k)))
     with np.errstate(invalid="ignore"):
         assert np.array_equal(emul.upload(s, None, ur, fr, 0), q(s)) and emul.upload(s, None, ur, fr, 0)[5] == 0   # NaN -> 0
+
+
+# ---- K5 from the precomputed tables (glava_b200/csrc/tables.h), walked as the kernels walk them ---------------------
+@pytest.mark.parametrize("mode,formula", [(0, 0), (1, 0), (2, 0), (0, 1), (0, 2), (2, 2)])
+@pytest.mark.parametrize("n", [256, 1024, 4096])
+def test_full_plane_k5_table_bit_exact(orc_pm, n, mode, formula, built):
+    p = g.default_params("bars", n=n, sample_mode=mode, round_formula=formula)
+    op = params_from(p)
+    for seed in (1, 2):
+        tex = _tex(n, seed)
+        assert np.array_equal(emul.k5_table(p, tex), orc_pm.smooth_pass(op, tex)), (n, mode, formula, seed)
+    for const in (0, 65535):
+        tex = np.full(n, const, np.uint16)
+        assert np.array_equal(emul.k5_table(p, tex), orc_pm.smooth_pass(op, tex))
+
+
+def test_full_plane_k5_table_wide_window(orc_pm, built):
+    """a smoothing factor large enough that taps run past the texture (texelFetch reads 0 there)"""
+    p = g.default_params("bars", n=512, smooth_factor=0.3, sample_range=0.999, sample_scale=2.0)
+    op = params_from(p)
+    tex = _tex(512, 5)
+    assert np.array_equal(emul.k5_table(p, tex), orc_pm.smooth_pass(op, tex))
+
+
+@pytest.mark.parametrize("module,n,w,h", [("bars", 4096, 1920, 1080), ("bars", 1024, 333, 200), ("radial", 2048, 800, 600),
+                                          ("graph", 2048, 1280, 720), ("wave", 2048, 1280, 720)])
+def test_lazy_k5_tables_give_the_oracle_texels(orc_pm, module, n, w, h, built):
+    """need-list + tap table: every texel the module samples equals the oracle's smooth pass there, through both table
+    layouts, and the pruning bound epi_n covers every input a tap reads"""
+    p = g.default_params(module, n=n, w=w, h=h, lazy_smooth=1)
+    op = params_from(p)
+    epi = emul.lazy_epi_n(p)
+    assert 0 < epi <= n
+    for chan in (0, 1):
+        tex = _tex(n, 7 + chan)
+        want = orc_pm.smooth_pass(op, tex)
+        got = {}
+        for path in (0, 1):
+            idx, val = emul.lazy_k5(p, chan, path, tex)
+            if module == "wave" and chan == 1:
+                assert idx is not None and len(idx) == 0               # audio_r is never sampled (wave/1.frag:7)
+                continue
+            assert len(idx) > 0 and np.array_equal(val, want[idx]), (module, chan, path)
+            got[path] = (idx, val)
+        if got:
+            assert np.array_equal(got[0][0], got[1][0])
+            # inputs at or beyond epi_n cannot influence a sampled texel
+            tex2 = tex.copy(); tex2[epi:] = 0
+            assert np.array_equal(emul.lazy_k5(p, chan, 1, tex2)[1], got[1][1])
+
+
+def test_circle_has_no_need_list(built):
+    p = g.default_params("circle", n=1024, w=320, h=240, lazy_smooth=1)
+    assert emul.lazy_k5(p, 0, 0, _tex(1024, 1))[0] is None
