@@ -62,6 +62,7 @@ struct glava_b200 {
     float* d_spec_cur;          // latest post-transform buffer (glava_b200_spectrum)
     void* d_ts_tab; int ts_asz, ts_lim;        // transform_smooth {smin, smax} table
     std::atomic<unsigned long long> sizereq;   // pending glava_b200_sizereq: (1 << 63) | w << 32 | h, 0 = none
+    int tap_ku; bool fused_k5, no_texmm;       // environment knobs, read once at creation
     int batch, device, slots;
     cudaStream_t stream;        // raster kernels, read-backs (the stream glava_b200_cuda_stream returns)
     cudaStream_t spec_stream;   // spectrum kernels + FIFO ingest, lowest priority: the latency-bound spectrum
@@ -373,6 +374,9 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     r->p_user = *params; r->batch = batch; r->device = device;
     derive(r);
     r->sizereq.store(0);
+    { const char* e = getenv("GLAVA_B200_TAP_KU"); r->tap_ku = e ? atoi(e) : 8; }
+    r->fused_k5 = getenv("GLAVA_B200_FUSED_K5") != nullptr;
+    r->no_texmm = getenv("GLAVA_B200_NO_TEXMM") != nullptr;
     r->kcounter = 0; r->d_scaled[0] = r->d_scaled[1] = nullptr; r->d_key[0] = r->d_key[1] = r->d_key[2] = nullptr;
     r->key_start = 0; r->key_end = 1; r->d_spec_cur = nullptr; r->d_ts_tab = nullptr; r->ts_asz = r->ts_lim = 0;
     r->stream = nullptr; r->spec_stream = nullptr; r->tex_cur = 0; r->ring_cur = 0;
@@ -519,7 +523,7 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
         a.need = (p.lazy_smooth && r->d_need) ? r->d_need : nullptr; a.need_count = r->need_count;
         a.tap_tab = a.need ? r->d_tap_tab : nullptr; a.tap_cnt = r->d_tap_cnt; a.tap_wsum = r->d_tap_wsum; a.tap_max = r->tap_max;
         a.epi_n = a.need ? r->epi_n : 0;
-        { static int ku = -1; if (ku < 0) { const char* e = getenv("GLAVA_B200_TAP_KU"); ku = e ? atoi(e) : 8; } a.tap_ku = ku; }
+        a.tap_ku = r->tap_ku;
         a.csr = (a.need && a.tap_tab) ? r->d_csr : nullptr; a.csr_bytes = r->csr_bytes; a.csr_idx_off = r->csr_idx_off; a.csr_off_off = r->csr_off_off;
         a.batch = r->batch; a.update = r->updates;
         const int F = p.avg_frames;
@@ -534,7 +538,7 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
         if (r->timing && (rc = timing_mark(r->ev_spec, r->spec_stream)) != 0) return rc;
         // full-plane smoothing (every texel wanted): the spectrum kernel exports the pre-smoothing texture and
         // a second kernel smooths all planes, sharing the tap weights between planes
-        const bool split_k5 = p.smooth_pass && !a.need && !r->post_chain && !getenv("GLAVA_B200_FUSED_K5");
+        const bool split_k5 = p.smooth_pass && !a.need && !r->post_chain && !r->fused_k5;
         a.av_out = split_k5 ? r->d_av : nullptr;
         if ((rc = launch_spectrum(p, a, is_fft, r->spec_stream)) != 0) return rc;
         if (split_k5) {
@@ -589,7 +593,7 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
     ra.batch = r->batch; ra.slots = r->slots; ra.stream0 = 0;
     ra.geo = r->d_geo; ra.gx0 = r->geo_box[0]; ra.gy0 = r->geo_box[1]; ra.gw = r->geo_box[2]; ra.gh = r->geo_box[3];
     ra.texmm = nullptr;
-    if (p.module == GLAVA_B200_MOD_CIRCLE && r->d_geo && !getenv("GLAVA_B200_NO_TEXMM")) {
+    if (p.module == GLAVA_B200_MOD_CIRCLE && r->d_geo && !r->no_texmm) {
         if ((rc = launch_texmm(p, ra.tex, r->d_texmm, r->batch * 2, r->stream)) != 0) return rc;
         ++r->launches;
         ra.texmm = r->d_texmm;
