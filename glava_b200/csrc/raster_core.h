@@ -312,8 +312,10 @@ GLB_HD uint32_t circle_px(const glava_b200_params& p, const AudioTex& t, int x, 
     uint32_t own = circle_stage1(p, t, x, y);
     if (p.circle_smooth && (own >> 24) == 0u) {
         nb[0] = circle_stage1(p, t, x + 1, y);     nb[1] = circle_stage1(p, t, x + 1, y + 1);
-        nb[2] = circle_stage1(p, t, x, y + 1);     nb[3] = circle_stage1(p, t, x - 1, y);
-        nb[4] = circle_stage1(p, t, x - 1, y - 1); nb[5] = circle_stage1(p, t, x, y - 1);
+        // circle/2.frag: half-integer gl_FragCoord, ivec2(x + 0.5 - 1) = 0 at x = 0 (see graph_px_cols)
+        const int xm = x > 0 ? x - 1 : x, ym = y > 0 ? y - 1 : y;
+        nb[2] = circle_stage1(p, t, x, y + 1);     nb[3] = circle_stage1(p, t, xm, y);
+        nb[4] = circle_stage1(p, t, xm, ym);       nb[5] = circle_stage1(p, t, x, ym);
     }
     return circle_finish(p, own, nb);
 }
@@ -362,15 +364,21 @@ GLB_HD uint32_t graph_finish(const glava_b200_params& p, uint32_t own, const uin
 // generic per-pixel: s3 = heights of columns x-1, x, x+1 (out-of-surface columns: any value, masked here)
 GLB_HD uint32_t graph_px_cols(const glava_b200_params& p, const float s3[3], const uint32_t row3[3], int x, int y) {
     // row3 = row colours of y-1, y, y+1
-    bool xl = x - 1 >= 0, xr = x + 1 < p.w, yd = y - 1 >= 0, yu = y + 1 < p.h;
+    // graph/2.frag addresses its taps as ivec2(gl_FragCoord.x - 1, gl_FragCoord.y - 1) with the DEFAULT half-integer
+    // gl_FragCoord (stage 2 does not declare pixel_center_integer): at x = 0 that is int(-0.5) = 0 — float -> int drops
+    // the fraction (GLSL 3.30 5.4.1) — so the "x - 1" / "y - 1" taps of column 0 / row 0 read column 0 / row 0
+    // themselves; only the "+ 1" taps can leave the surface.
+    bool xr = x + 1 < p.w, yu = y + 1 < p.h;
+    const int cl = x > 0 ? 0 : 1, rd = y > 0 ? 0 : 1;                       // s3 / row3 slot of the "- 1" taps
+    const int ym = y > 0 ? y - 1 : y;
     uint32_t own = graph_stage1(p, s3[1], row3[1], y);
     uint32_t nb[6];
     nb[0] = xr ? graph_stage1(p, s3[2], row3[1], y) : 0u;
     nb[1] = (xr && yu) ? graph_stage1(p, s3[2], row3[2], y + 1) : 0u;
     nb[2] = yu ? graph_stage1(p, s3[1], row3[2], y + 1) : 0u;
-    nb[3] = xl ? graph_stage1(p, s3[0], row3[1], y) : 0u;
-    nb[4] = (xl && yd) ? graph_stage1(p, s3[0], row3[0], y - 1) : 0u;
-    nb[5] = yd ? graph_stage1(p, s3[1], row3[0], y - 1) : 0u;
+    nb[3] = graph_stage1(p, s3[cl], row3[1], y);
+    nb[4] = graph_stage1(p, s3[cl], row3[rd], ym);
+    nb[5] = graph_stage1(p, s3[1], row3[rd], ym);
     return graph_finish(p, own, nb);
 }
 GLB_HD uint32_t graph_px(const glava_b200_params& p, const AudioTex& t, int x, int y) {

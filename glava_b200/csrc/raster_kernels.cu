@@ -393,9 +393,11 @@ raster_circle_kernel(const __grid_constant__ RasterArgs a, const __grid_constant
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int lx = qx * 4 + k + 1, ly = qy + 1;
+                    // circle/2.frag's "- 1" taps at column 0 / row 0 read column 0 / row 0 (int(-0.5) = 0, see circle_px)
+                    const int lxm = (x + k > 0) ? lx - 1 : lx, lym = (y > 0) ? ly - 1 : ly;
                     const uint32_t own = tile[ly][lx];
                     const uint32_t nb[6] = { tile[ly][lx + 1], tile[ly + 1][lx + 1], tile[ly + 1][lx],
-                                             tile[ly][lx - 1], tile[ly - 1][lx - 1], tile[ly - 1][lx] };
+                                             tile[ly][lxm], tile[lym][lxm], tile[lym][lx] };
                     if (x + k < p.w) px[k] = ((own | nb[0] | nb[1] | nb[2] | nb[3] | nb[4] | nb[5]) == 0u) ? 0u : circle_finish(p, own, nb);
                 }
             }

@@ -713,10 +713,17 @@ static inline vec4 sfetch(const surf* s, int x, int y) {
     return unpack8(s->px[(size_t) (y - s->y0) * s->w + x]);
 }
 /* the 8-tap neighbour mean written out in circle/2.frag:18-26, graph/2.frag:21-29,
- * wave/2.frag:18-26 — taps a3 and a7 repeat a0 and a4 in the source. */
-static inline vec4 neigh_avg(const surf* s, int x, int y) {
+ * wave/2.frag:18-26 — taps a3 and a7 repeat a0 and a4 in the source.
+ * The taps are addressed as ivec2(gl_FragCoord.x - 1, gl_FragCoord.y - 1).  wave/2.frag declares
+ * layout(pixel_center_integer): x - 1 is exactly -1 at the left edge, outside the surface.  circle/2.frag and
+ * graph/2.frag use the default half-integer gl_FragCoord: x + 0.5 - 1 = -0.5 at x = 0, and float -> int conversion
+ * drops the fraction (GLSL 3.30 5.4.1), i.e. 0 — the "x - 1" / "y - 1" taps of column 0 / row 0 read column 0 / row 0.
+ * (Found by running the reference's shader text through oracle/glsl_interp.py.) */
+static inline vec4 neigh_avg(const surf* s, int x, int y, int half_integer_coords) {
+    int xm = x - 1, ym = y - 1;
+    if (half_integer_coords) { if (xm < 0) xm = 0; if (ym < 0) ym = 0; }
     vec4 a0 = sfetch(s, x + 1, y), a1 = sfetch(s, x + 1, y + 1), a2 = sfetch(s, x, y + 1), a3 = sfetch(s, x + 1, y),
-         a4 = sfetch(s, x - 1, y), a5 = sfetch(s, x - 1, y - 1), a6 = sfetch(s, x, y - 1), a7 = sfetch(s, x - 1, y);
+         a4 = sfetch(s, xm, y), a5 = sfetch(s, xm, ym), a6 = sfetch(s, x, ym), a7 = sfetch(s, xm, y);
     vec4 r;
     r.r = (a0.r + a1.r + a2.r + a3.r + a4.r + a5.r + a6.r + a7.r) / 8.0f;
     r.g = (a0.g + a1.g + a2.g + a3.g + a4.g + a5.g + a6.g + a7.g) / 8.0f;
@@ -750,7 +757,7 @@ void orc_raster_rows(const orc_params* p, const uint16_t* tl, const uint16_t* tr
                 case ORC_MOD_CIRCLE: {
                     vec4 f = unpack8(px);
                     if (p->circle_smooth) {                                 /* circle/2.frag:14-32 */
-                        vec4 avg = neigh_avg(&S, x, y);
+                        vec4 avg = neigh_avg(&S, x, y, 1);
                         if (f.a == 0.0f) f = avg;
                         px = pack8(f); f = unpack8(px);
                     }
@@ -760,7 +767,7 @@ void orc_raster_rows(const orc_params* p, const uint16_t* tl, const uint16_t* tr
                 case ORC_MOD_GRAPH: {
                     if (p->graph_draw_outline || p->graph_draw_highlight) { /* graph/2.frag:19-44 */
                         vec4 f = unpack8(px);
-                        vec4 avg = neigh_avg(&S, x, y);
+                        vec4 avg = neigh_avg(&S, x, y, 1);
                         if (avg.a > 0.0f) {
                             if (f.a <= 0.0f) { if (p->graph_draw_outline) f = v4a(p->graph_outline); }
                             else if (avg.a < 1.0f) {
@@ -773,7 +780,7 @@ void orc_raster_rows(const orc_params* p, const uint16_t* tl, const uint16_t* tr
                 }
                 case ORC_MOD_WAVE: {                                        /* wave/2.frag:14-33 */
                     vec4 f = unpack8(px);
-                    vec4 avg = neigh_avg(&S, x, y);
+                    vec4 avg = neigh_avg(&S, x, y, 0);
                     if (avg.a > 0.0f) {
                         if (f.a <= 0.0f || x == 0 || x == w - 1) f = v4a(p->wave_outline);
                     }

@@ -208,7 +208,8 @@ int emul_raster_fast(const glava_b200_params* pp, const uint16_t* tl, const uint
         auto at = [&](int x, int y) -> uint32_t& { return s1[(size_t) (y + 1) * (p.w + 2) + (x + 1)]; };
         for (int y = 0; y < p.h; ++y) for (int x = 0; x < p.w; ++x) at(x, y) = circle_stage1_geo(p, t, circle_geometry(p, x, y));
         for (int y = 0; y < p.h; ++y) for (int x = 0; x < p.w; ++x) {
-            const uint32_t nb[6] = { at(x + 1, y), at(x + 1, y + 1), at(x, y + 1), at(x - 1, y), at(x - 1, y - 1), at(x, y - 1) };
+            const int xm = x > 0 ? x - 1 : x, ym = y > 0 ? y - 1 : y;       // the kernel's lxm / lym: int(-0.5) = 0 at the border
+            const uint32_t nb[6] = { at(x + 1, y), at(x + 1, y + 1), at(x, y + 1), at(xm, y), at(xm, ym), at(x, ym) };
             dst[(size_t) y * p.w + x] = circle_finish(p, at(x, y), nb);
         }
         return 0;

@@ -1,0 +1,114 @@
+"""Golden pixels computed FROM THE REFERENCE'S OWN SHADER SOURCES: oracle/glsl_interp.py reads
+/root/reference/shaders/glava/<module>/<n>.frag (+ util/*.frag, <module>.glsl, smooth_parameters.glsl), applies GLava's
+source extensions and injected header, and evaluates every fragment of a small surface in float32.  The frames written
+here pin the C restatement (oracle/glava_oracle.c), the product arithmetic and the kernels to the reference's shader
+text on machines where neither the reference tree nor OpenGL exists.  Run in the build container only:
+
+    python tests/golden/make_glsl_golden.py
+
+Cases: per module the shipped configuration scaled to the small surface, plus one variant exercising the module's
+options.  Each case stores the GLSL macro overrides, the equivalent parameter overrides (JSON), the two R16 textures and
+the interpreter's RGBA8 frame.  util passes: smooth_pass.frag (K5) in the three SAMPLE_MODEs, gravity_pass.frag,
+average_pass.frag (windowed, 5 and 3 frames; unwindowed 2 frames) and pass.frag on small R16 textures.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import glsl_interp as gi  # noqa: E402
+from oracle.oracle import Oracle  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SHADERS = "/root/reference/shaders/glava"
+W, H, N = 96, 54, 512
+
+# (case name, module, GLSL macro overrides, parameter overrides, header overrides)
+CASES = [
+    ("bars", "bars", {"AMPLIFY": "40"}, dict(bars_amplify=40.0), {}),
+    ("bars_opts", "bars", {"AMPLIFY": "45", "DIRECTION": "1", "INVERT": "1", "FLIP": "1", "BAR_WIDTH": "4", "BAR_GAP": "2", "BAR_OUTLINE_WIDTH": "0"},
+     dict(bars_amplify=45.0, bars_direction=1, bars_invert=1, bars_flip=1, bars_width=4.0, bars_gap=2.0, bars_outline_width=0.0), {}),
+    ("bars_mono", "bars", {"AMPLIFY": "40"}, dict(bars_amplify=40.0, channels=1), {"channels": 1}),
+    ("radial", "radial", {"C_RADIUS": "12", "AMPLIFY": "30", "NBARS": "40"}, dict(radial_radius=12.0, radial_amplify=30.0, radial_nbars=40), {}),
+    ("radial_opts", "radial", {"C_RADIUS": "10", "AMPLIFY": "28", "NBARS": "24", "INVERT": "1", "C_LINE": "3", "BAR_WIDTH": "3.5",
+                               "CENTER_OFFSET_X": "5", "CENTER_OFFSET_Y": "-3", "ROTATE": "(PI / 3)"},
+     dict(radial_radius=10.0, radial_amplify=28.0, radial_nbars=24, radial_invert=1, radial_line=3.0, radial_line_half=1.0,
+          radial_bar_width=3.5, radial_off_x=5.0, radial_off_y=-3.0, radial_rotate=float(np.float32(np.float32(3.14159265359) / np.float32(3)))), {}),
+    ("circle", "circle", {"C_RADIUS": "12", "AMPLIFY": "20"}, dict(circle_radius=12.0, circle_amplify=20.0), {}),
+    ("circle_big", "circle", {"C_RADIUS": "22", "AMPLIFY": "30", "C_LINE": "2.5", "INVERT": "1"},
+     dict(circle_radius=22.0, circle_amplify=30.0, circle_line=2.5, circle_invert=1), {}),
+    ("circle_fill", "circle", {"C_RADIUS": "10", "AMPLIFY": "18", "C_FILL": "1", "C_SMOOTH": "0"},
+     dict(circle_radius=10.0, circle_amplify=18.0, circle_fill=1, circle_smooth=0), {}),
+    ("graph", "graph", {"VSCALE": "40"}, dict(graph_vscale=40.0), {}),
+    ("graph_opts", "graph", {"VSCALE": "45", "INVERT": "1", "DIRECTION": "-1", "DRAW_OUTLINE": "1", "DRAW_HIGHLIGHT": "0"},
+     dict(graph_vscale=45.0, graph_invert=1, graph_direction=-1, graph_draw_outline=1, graph_draw_highlight=0), {}),
+    ("wave", "wave", {"AMPLIFY": "40"}, dict(wave_amplify=40.0), {}),
+    ("wave_thick", "wave", {"AMPLIFY": "25", "MIN_THICKNESS": "2", "MAX_THICKNESS": "4"},
+     dict(wave_amplify=25.0, wave_min_thickness=2.0, wave_max_thickness=4.0), {}),
+    ("test", "test", {}, {}, {}),
+    ("radial_nopremult", "radial", {"C_RADIUS": "12", "AMPLIFY": "30", "NBARS": "40"},
+     dict(radial_radius=12.0, radial_amplify=30.0, radial_nbars=40, premultiply_alpha=0), {"premultiply_alpha": 0}),
+]
+
+
+def textures(orc, p, module, seed):
+    rng = np.random.default_rng(seed)
+    tl = orc.smooth_pass(p, (rng.random(N) ** 2 * 65535).astype(np.uint16))
+    tr = orc.smooth_pass(p, (rng.random(N) ** 3 * 65535).astype(np.uint16))
+    if module == "wave":
+        tl = np.clip(tl.astype(int) // 4 + 24576, 0, 65535).astype(np.uint16)
+    return tl, tr
+
+
+def main():
+    orc = Oracle("libm")
+    out = {"case_names": np.array([c[0] for c in CASES])}
+    for i, (name, module, gl_over, p_over, hdr) in enumerate(CASES):
+        p = orc.default_params(module, n=N, w=W, h=H)
+        tl, tr = textures(orc, p, module, 100 + i)
+        prog = gi.ModuleProgram(SHADERS, module, W, H, tl, tr, overrides=gl_over, **hdr)
+        frame = np.zeros((H, W, 4), np.uint8)
+        for y in range(H):
+            for x in range(W):
+                frame[y, x] = prog.pixel(x, y)
+        out[f"{name}_module"] = np.array(module)
+        out[f"{name}_params"] = np.array(json.dumps(p_over))
+        out[f"{name}_tl"] = tl; out[f"{name}_tr"] = tr; out[f"{name}_frame"] = frame
+        print(name, "stages", len(prog.stages), "lit", int(frame.any(axis=2).sum()), flush=True)
+    # ---- util passes on 1-D R16 targets ---------------------------------------------------------------------------------
+    n = 256
+    rng = np.random.default_rng(7)
+    tex = (rng.random(n) ** 2 * 65535).astype(np.uint16)
+    out["k5_in"] = tex
+    util = os.path.join(SHADERS, "util")
+    for mode in ("average", "maximum", "hybrid"):
+        for formula in ("sinusoidal", "linear", "circular"):
+            if mode != "average" and formula != "sinusoidal":
+                continue
+            sh_over = {"SAMPLE_MODE": mode, "ROUND_FORMULA": formula}
+            sh = gi.load_stage(os.path.join(util, "smooth_pass.frag"), SHADERS, sh_over)
+            res = np.zeros(n, np.uint16)
+            for x in range(n):
+                g = sh.run({"tex": gi.Sampler1D(tex), "sz": n, "w": n}, x, 0)
+                res[x] = gi.unorm16(g["fragment"].v[0])
+            out[f"k5_{mode}_{formula}"] = res
+            print("k5", mode, formula, flush=True)
+    diff = np.float32(4.2) * (np.float32(1.0) / np.float32(86.1328125))
+    out["gravity_diff"] = np.float32(diff)
+    out["gravity_out"] = gi.run_1d_pass(os.path.join(util, "gravity_pass.frag"), SHADERS, n, {"tex": gi.Sampler1D(tex), "diff": diff})
+    out["pass_out"] = gi.run_1d_pass(os.path.join(util, "pass.frag"), SHADERS, n, {"tex": gi.Sampler1D(tex)})
+    frames = [(rng.random(n) ** 2 * 65535).astype(np.uint16) for _ in range(5)]
+    out["avg_frames_in"] = np.stack(frames)
+    for F, win in ((5, 1), (3, 1), (2, 1), (5, 0)):
+        uni = {f"t{i}": gi.Sampler1D(frames[i]) for i in range(F)}                 # t0 = most recent (render.c:2250-2255)
+        out[f"avg_F{F}_w{win}"] = gi.run_1d_pass(os.path.join(util, "average_pass.frag"), SHADERS, n, uni, avg_frames=F, avg_window=win)
+    np.savez_compressed(os.path.join(HERE, "glsl_golden.npz"), **out)
+    print("wrote glsl_golden.npz")
+
+
+if __name__ == "__main__":
+    main()

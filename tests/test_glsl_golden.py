@@ -1,0 +1,162 @@
+"""Frames computed from the REFERENCE'S OWN SHADER TEXT (tests/golden/glsl_golden.npz, made by
+tests/golden/make_glsl_golden.py with oracle/glsl_interp.py) against the C restatement (oracle), the product arithmetic
+compiled for the host (tests/emul) and — -m gpu — the kernels.  This is what pins the raster half and the GL passes
+K2 / K4 / K5 to the reference: the interpreter takes macro precedence, int / float typing, operand order, stage chaining
+and quantisation from the .frag / .glsl files themselves."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import glava_b200 as g
+from oracle.oracle import params_from
+from tests.conftest import GOLDEN
+
+W, H, N = 96, 54, 512
+REF_SHADERS = "/root/reference/shaders/glava"
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLDEN, "glsl_golden.npz"))
+
+
+def _cases():
+    z = np.load(os.path.join(GOLDEN, "glsl_golden.npz"))
+    return [str(c) for c in z["case_names"]]
+
+
+def _params(gold, case):
+    module = str(gold[f"{case}_module"])
+    over = json.loads(str(gold[f"{case}_params"]))
+    return module, g.default_params(module, n=N, w=W, h=H, **over)
+
+
+def _lsb(a, b):
+    return int(np.abs(a.astype(int) - b.astype(int)).max())
+
+
+@pytest.mark.parametrize("case", _cases())
+def test_oracle_equals_the_reference_shader_frames(orc, orc_pm, gold, case, built):
+    module, p = _params(gold, case)
+    op = params_from(p)
+    tl, tr, want = gold[f"{case}_tl"], gold[f"{case}_tr"], gold[f"{case}_frame"]
+    assert want.any()
+    got = orc.raster(op, tl, tr)
+    assert np.array_equal(got, want), (case, int((got != want).any(axis=2).sum()))      # same libm as the interpreter: exact
+    assert _lsb(orc_pm.raster(op, tl, tr), want) <= 1                                      # product-maths build
+
+
+@pytest.mark.parametrize("case", _cases())
+def test_product_arithmetic_equals_the_reference_shader_frames(orc_pm, gold, case, built):
+    from tests import emul
+    module, p = _params(gold, case)
+    tl, tr, want = gold[f"{case}_tl"], gold[f"{case}_tr"], gold[f"{case}_frame"]
+    got = emul.raster(p, tl, tr)
+    assert _lsb(got, want) <= 1 and (got != want).any(axis=2).sum() <= 0.002 * W * H, case
+    if module in ("bars", "graph", "wave", "circle") and not p.bars_mirror_yx:
+        assert np.array_equal(emul.raster(p, tl, tr, fast=True), got)                      # the kernels' hoisted evaluation
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", _cases())
+def test_kernels_equal_the_reference_shader_frames(orc_pm, gold, case, built):
+    module, p = _params(gold, case)
+    tl, tr, want = gold[f"{case}_tl"], gold[f"{case}_tr"], gold[f"{case}_frame"]
+    with g.Renderer(p, batch=2) as r:
+        r.raster_textures(np.stack([tl, tl]), np.stack([tr, tr]))
+        got = r.readback(1)
+    assert _lsb(got, want) <= 1 and (got != want).any(axis=2).sum() <= 0.002 * W * H, case
+
+
+# ---- the GL passes on 1-D R16 textures --------------------------------------------------------------------------------------
+MODES = {"average": 0, "maximum": 1, "hybrid": 2}
+FORMULAS = {"sinusoidal": 0, "linear": 1, "circular": 2}
+
+
+@pytest.mark.parametrize("mode,formula", [("average", "sinusoidal"), ("average", "linear"), ("average", "circular"),
+                                          ("maximum", "sinusoidal"), ("hybrid", "sinusoidal")])
+def test_k5_smooth_pass_equals_smooth_pass_frag(orc, orc_pm, gold, mode, formula, built):
+    from tests import emul
+    tex, want = gold["k5_in"], gold[f"k5_{mode}_{formula}"]
+    p = g.default_params("bars", n=len(tex), sample_mode=MODES[mode], round_formula=FORMULAS[formula])
+    op = params_from(p)
+    assert _lsb(orc.smooth_pass(op, tex), want) <= 1                       # same libm as the interpreter
+    # product maths (gl_math.h log / sin polynomials, <= 1 ulp from libm): 1 LSB16, except `circular`, whose
+    # sqrt(1 - (x - 1)^2) has an infinite slope at the window edge and turns an ulp of the log into tens of LSB16 of one
+    # edge tap's weight (still < 0.2 LSB of an 8-bit pixel)
+    tol = 64 if formula == "circular" else 1
+    assert _lsb(orc_pm.smooth_pass(op, tex), want) <= tol
+    assert _lsb(emul.smooth(p, tex), want) <= tol and _lsb(emul.k5_table(p, tex), want) <= tol
+
+
+def _from16(u):
+    return (u.astype(np.float32) / np.float32(65535.0)).astype(np.float32)
+
+
+def _unorm16(v):
+    v = np.asarray(v, np.float32)
+    q = (v * np.float32(65535.0) + np.float32(0.5)).astype(np.float32)
+    return np.where(v > 0, np.where(v < 1, q.astype(np.int64), 65535), 0).astype(np.uint16)
+
+
+def test_gravity_and_pass_frag(gold):
+    """K2 = texel - diff, K1 / K3 = copy (the restatement in oracle/glava_oracle.c orc_chan_update and the kernel's
+    gravity_b use exactly this arithmetic)"""
+    tex = gold["k5_in"]
+    assert np.array_equal(gold["pass_out"], tex)
+    assert np.array_equal(gold["gravity_out"], _unorm16(_from16(tex) - np.float32(gold["gravity_diff"])))
+
+
+@pytest.mark.parametrize("F,win", [(5, 1), (3, 1), (2, 1), (5, 0)])
+def test_average_pass_frag(gold, F, win):
+    """K4: r += window(I, _AVG_FRAMES - 1) * t_I with the macro expanding to cos(TWOPI * I / F - 1), newest frame first;
+    no window for two frames (average_pass.frag:27-29); r / F without normalising the window"""
+    frames = gold["avg_frames_in"][:F]
+    r = np.zeros(frames.shape[1], np.float32)
+    windowed = win and F != 2
+    for i in range(F):
+        tx = _from16(frames[i])
+        if windowed:
+            w = np.float32(0.53836) - np.float32(0.46164) * np.cos(np.float32(np.float32(6.28318530718) * np.float32(i) / np.float32(F)) - np.float32(1.0), dtype=np.float32)
+            r = (r + (np.float32(w) * tx).astype(np.float32)).astype(np.float32)
+        else:
+            r = (r + tx).astype(np.float32)
+    want = gold[f"avg_F{F}_w{win}"]
+    assert _lsb(_unorm16(r / np.float32(F)), want) <= 1
+
+
+# ---- live: the interpreter against the oracle on a fresh configuration (build container only) ---------------------------------
+@pytest.mark.skipif(not os.path.isdir(REF_SHADERS), reason="reference tree not present")
+@pytest.mark.parametrize("module,gl_over,p_over", [
+    ("bars", {"AMPLIFY": "30", "BAR_WIDTH": "3", "BAR_GAP": "1"}, dict(bars_amplify=30.0, bars_width=3.0, bars_gap=1.0)),
+    ("radial", {"C_RADIUS": "9", "AMPLIFY": "20", "NBARS": "32"}, dict(radial_radius=9.0, radial_amplify=20.0, radial_nbars=32)),
+    ("circle", {"C_RADIUS": "15", "AMPLIFY": "25"}, dict(circle_radius=15.0, circle_amplify=25.0)),
+    ("graph", {"VSCALE": "30"}, dict(graph_vscale=30.0)),
+    ("wave", {"AMPLIFY": "30"}, dict(wave_amplify=30.0)),
+])
+def test_interpreter_live_against_the_oracle(orc, module, gl_over, p_over, built):
+    from oracle import glsl_interp as gi
+    w, h, n = 64, 40, 256
+    p = orc.default_params(module, n=n, w=w, h=h, **p_over)
+    rng = np.random.default_rng(hash(module) % 1000)
+    tl = orc.smooth_pass(p, (rng.random(n) ** 2 * 65535).astype(np.uint16))
+    tr = orc.smooth_pass(p, (rng.random(n) ** 3 * 65535).astype(np.uint16))
+    if module == "wave":
+        tl = np.clip(tl.astype(int) // 4 + 24576, 0, 65535).astype(np.uint16)
+    want = orc.raster(p, tl, tr)
+    prog = gi.ModuleProgram(REF_SHADERS, module, w, h, tl, tr, overrides=gl_over)
+    got = np.zeros_like(want)
+    for y in range(h):
+        for x in range(w):
+            got[y, x] = prog.pixel(x, y)
+    assert np.array_equal(got, want), (module, int((got != want).any(axis=2).sum()))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SHADERS), reason="reference tree not present")
+def test_interpreter_reproduces_the_reference_known_answer(built):
+    from oracle import glsl_interp as gi
+    z = np.zeros(256, np.uint16)
+    prog = gi.ModuleProgram(REF_SHADERS, "test", 8, 4, z, z)
+    assert len(prog.stages) == 3 and prog.pixel(3, 2) == (0x55, 0, 0, 0x55)              # test_rc.glsl:27
