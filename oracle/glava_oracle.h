@@ -2,12 +2,17 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load this library.  The product (libglava_b200.so) never links or calls it.
  *
- * Parity status: the SPECTRUM half is pinned against the reference's own compiled code
- * (oracle/_ref, built from /root/reference/glava/render.c by oracle/Makefile) and the
- * golden vectors generated from it (tests/golden/).  The RASTER half restates GLSL
- * fragment shaders; the reference ships no golden pixels except the `test` module's
- * #55000055 known answer (shaders/glava/test_rc.glsl:27), and no GL implementation is
- * available in this image, so apart from that KAT it is "parity unpinned".
+ * Parity status: the SPECTRUM half (and transform_smooth) is pinned against the reference's
+ * own compiled code (oracle/_ref, built from /root/reference/glava/render.c by oracle/Makefile)
+ * and the golden vectors generated from it (tests/golden/).  The RASTER half and the GL
+ * passes K2 / K4 / K5 restate GLSL; no GL implementation is available in this image, so
+ * they are pinned one level down: oracle/glsl_interp.py EXECUTES the reference's own shader
+ * sources (with GLava's source extensions and injected header) in float32, and this
+ * restatement equals its frames bit for bit (tests/golden/glsl_golden.npz: 14 module
+ * configurations, the three SAMPLE_MODEs of smooth_pass.frag, gravity / average / pass;
+ * plus the `test` module's #55000055 known answer, shaders/glava/test_rc.glsl:27).  What
+ * GLSL leaves implementation-defined (transcendental ulps, round() ties, out-of-range
+ * texelFetch, unorm rounding) is fixed by convention, not by the reference.
  */
 #ifndef GLAVA_ORACLE_H
 #define GLAVA_ORACLE_H
