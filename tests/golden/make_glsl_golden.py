@@ -50,6 +50,11 @@ CASES = [
     ("wave_thick", "wave", {"AMPLIFY": "25", "MIN_THICKNESS": "2", "MAX_THICKNESS": "4"},
      dict(wave_amplify=25.0, wave_min_thickness=2.0, wave_max_thickness=4.0), {}),
     ("test", "test", {}, {}, {}),
+    ("bars_mirror_yx", "bars", {"AMPLIFY": "60", "MIRROR_YX": "1"}, dict(bars_amplify=60.0, bars_mirror_yx=1), {}),
+    # setsmoothpass false: the module shader itself runs smooth_audio()'s tap loop per fragment (_PRE_SMOOTHED_AUDIO 0)
+    ("bars_nosmoothpass", "bars", {"AMPLIFY": "40"}, dict(bars_amplify=40.0, smooth_pass=0), {"pre_smoothed": 0}),
+    ("radial_nosmoothpass", "radial", {"C_RADIUS": "12", "AMPLIFY": "30", "NBARS": "40"},
+     dict(radial_radius=12.0, radial_amplify=30.0, radial_nbars=40, smooth_pass=0), {"pre_smoothed": 0}),
     ("radial_nopremult", "radial", {"C_RADIUS": "12", "AMPLIFY": "30", "NBARS": "40"},
      dict(radial_radius=12.0, radial_amplify=30.0, radial_nbars=40, premultiply_alpha=0), {"premultiply_alpha": 0}),
 ]
