@@ -64,8 +64,11 @@ def _strip_comments(src):
 
 
 class ExtCtx:
-    def __init__(self, cd, cfd, dd, efuncs):
-        self.cd, self.cfd, self.dd, self.efuncs = cd, cfd, dd, efuncs
+    """include context of glsl_ext.c:161-183.  `fallback`: a user config directory normally holds a full copy of the
+    shader tree (glava --copy-config); tests give one with only the files they changed, the rest is taken from here."""
+
+    def __init__(self, cd, cfd, dd, efuncs, fallback=None):
+        self.cd, self.cfd, self.dd, self.efuncs, self.fallback = cd, cfd, dd, efuncs, fallback
 
 
 def ext_process(path, ctx, depth=0):
@@ -87,7 +90,10 @@ def ext_process(path, ctx, depth=0):
                     target = target[1:]; ctx.cd = ctx.cfd
                 if target.startswith("@"):
                     target = target[1:]; ctx.cd = ctx.dd
-                out += ext_process(os.path.join(ctx.cd, target), ctx, depth + 1)
+                path2 = os.path.join(ctx.cd, target)
+                if not os.path.exists(path2) and ctx.fallback:
+                    path2 = os.path.join(ctx.fallback, target)
+                out += ext_process(path2, ctx, depth + 1)
                 continue
             if word == "expand":
                 _, macro, arg = body.split()[:3]
@@ -879,11 +885,11 @@ def header_macros(pp, smooth_factor=0.025, avg_frames=5, avg_window=1, premultip
     pp.define("_PRE_SMOOTHED_AUDIO", str(pre_smoothed))
 
 
-def load_stage(path, root, overrides=None, **hdr):
+def load_stage(path, root, overrides=None, config_dir=None, **hdr):
     """preprocess + parse one shader file; overrides: {macro: text} applied AFTER the module's config includes, the way a
     user's copy of <module>.glsl would redefine them.  Raises DisabledStage for `#error __disablestage`."""
     efuncs = {"_AVG_FRAMES": hdr.get("avg_frames", 5)}
-    ctx = ExtCtx(os.path.dirname(path), root, root, efuncs)
+    ctx = ExtCtx(os.path.dirname(path), config_dir or root, root, efuncs, fallback=root)
     lines = ext_process(path, ctx)
     pp = Preprocessor()
     header_macros(pp, **hdr)
@@ -903,13 +909,13 @@ def load_stage(path, root, overrides=None, **hdr):
 class ModuleProgram:
     """the stage chain of one module (render.c stage loading: 1.frag, 2.frag, ... until a file is missing)"""
 
-    def __init__(self, root, module, w, h, tex_l, tex_r, overrides=None, **hdr):
+    def __init__(self, root, module, w, h, tex_l, tex_r, overrides=None, config_dir=None, **hdr):
         self.w, self.h = w, h
         self.stages = []
         k = 1
         while os.path.exists(os.path.join(root, module, "%d.frag" % k)):
             try:
-                self.stages.append(load_stage(os.path.join(root, module, "%d.frag" % k), root, overrides, **hdr))
+                self.stages.append(load_stage(os.path.join(root, module, "%d.frag" % k), root, overrides, config_dir, **hdr))
             except DisabledStage:
                 pass
             k += 1

@@ -160,3 +160,81 @@ def test_interpreter_reproduces_the_reference_known_answer(built):
     z = np.zeros(256, np.uint16)
     prog = gi.ModuleProgram(REF_SHADERS, "test", 8, 4, z, z)
     assert len(prog.stages) == 3 and prog.pixel(3, 2) == (0x55, 0, 0, 0x55)              # test_rc.glsl:27
+
+
+# ---- live: the config reader (glava_b200/csrc/config.cpp) against the shader semantics of the same config text ---------------
+USER_CONFIGS = {
+    "bars": """
+#define BAR_WIDTH 3
+#define BAR_GAP 2
+#define BAR_OUTLINE_WIDTH 1
+#define AMPLIFY (20 + 15)
+#define GRADIENT 30
+#define COLOR mix(#ff8000, #2040ff, clamp(d / GRADIENT, 0, 1))
+#define BAR_OUTLINE #20c040
+#define DIRECTION 1
+""",
+    "radial": """
+#define C_RADIUS 11
+#define C_LINE 3
+#define OUTLINE #808020
+#define NBARS 36
+#define BAR_WIDTH 2.5
+#define AMPLIFY 25
+#define GRADIENT 12
+#define COLOR mix(#10e0e0, #e010e0, clamp(d / GRADIENT, 0, 1))
+#define ROTATE (PI / 4)
+#define INVERT 1
+""",
+    "circle": """
+#define C_RADIUS 14
+#define C_LINE 2
+#define OUTLINE vec4(0.9, 0.5, 0.1, 1)
+#define AMPLIFY 22
+#define ROTATE (TWOPI / 3)
+""",
+    "graph": """
+#define VSCALE 35
+#define GRADIENT 20
+#define COLOR mix(#a0ff20, #2020c0, clamp(pos / GRADIENT, 0, 1))
+#define DRAW_OUTLINE 1
+#define OUTLINE #ff00ff
+#define DIRECTION -1
+""",
+    "wave": """
+#define MIN_THICKNESS 2
+#define MAX_THICKNESS 5
+#define BASE_COLOR vec4(0.2, 0.6, 0.3, 1)
+#define AMPLIFY 35
+#define OUTLINE #101010
+""",
+}
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SHADERS), reason="reference tree not present")
+@pytest.mark.parametrize("module", sorted(USER_CONFIGS))
+def test_config_reader_agrees_with_the_shaders_on_a_user_config(orc, tmp_path, module, built):
+    """a user's <module>.glsl goes (a) through glava_b200_load_config -> parameters -> oracle raster and (b) as text through
+    the reference's shaders in the interpreter: same pixels.  Covers colour literals / mix() gradients / constant
+    vec4 colours / integer vs float macro values / parenthesised arithmetic in #defines."""
+    from oracle import glsl_interp as gi
+    w, h, n = 72, 44, 256
+    user = tmp_path / "user"
+    user.mkdir()
+    (user / "rc.glsl").write_text("#request mod %s\n#request setbufsize %d\n#request setgeometry 0 0 %d %d\n" % (module, n, w, h))
+    (user / (module + ".glsl")).write_text(USER_CONFIGS[module])
+    p = g.load_config([str(user), REF_SHADERS])
+    assert p.module_name == module and (p.w, p.h, p.n) == (w, h, n)
+    op = params_from(p)
+    rng = np.random.default_rng(len(module))
+    tl = orc.smooth_pass(op, (rng.random(n) ** 2 * 65535).astype(np.uint16))
+    tr = orc.smooth_pass(op, (rng.random(n) ** 3 * 65535).astype(np.uint16))
+    if module == "wave":
+        tl = np.clip(tl.astype(int) // 4 + 24576, 0, 65535).astype(np.uint16)
+    want = orc.raster(op, tl, tr)
+    prog = gi.ModuleProgram(REF_SHADERS, module, w, h, tl, tr, config_dir=str(user))
+    got = np.zeros_like(want)
+    for y in range(h):
+        for x in range(w):
+            got[y, x] = prog.pixel(x, y)
+    assert want.any() and np.array_equal(got, want), (module, int((got != want).any(axis=2).sum()))
