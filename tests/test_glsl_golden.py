@@ -3,6 +3,7 @@ tests/golden/make_glsl_golden.py with oracle/glsl_interp.py) against the C resta
 compiled for the host (tests/emul) and — -m gpu — the kernels.  This is what pins the raster half and the GL passes
 K2 / K4 / K5 to the reference: the interpreter takes macro precedence, int / float typing, operand order, stage chaining
 and quantisation from the .frag / .glsl files themselves."""
+import ctypes as C
 import json
 import os
 
@@ -238,3 +239,51 @@ def test_config_reader_agrees_with_the_shaders_on_a_user_config(orc, tmp_path, m
         for x in range(w):
             got[y, x] = prog.pixel(x, y)
     assert want.any() and np.array_equal(got, want), (module, int((got != want).any(axis=2).sum()))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SHADERS), reason="reference tree not present")
+@pytest.mark.parametrize("F,win", [(5, 1), (3, 1), (2, 1), (1, 1), (4, 0)])
+def test_pipeline_b_chain_through_the_reference_pass_shaders(orc, F, win, built):
+    """the accelerated chain of one channel over several updates — R16 upload, K1 GL_MAX into gr_store, K2
+    gravity_pass.frag in place, K3 pass.frag into the ring slot, K4 average_pass.frag over the ring newest-first,
+    K5 smooth_pass.frag (render.c:2188-2303) — with every shader pass EXECUTED from the reference's source by the
+    interpreter, against orc_chan_update's restatement of the same chain: identical textures after every update."""
+    from oracle import glsl_interp as gi
+    from oracle.oracle import OracleChannel
+    n = 128
+    util = os.path.join(REF_SHADERS, "util")
+    p = orc.default_params("bars", n=n, accel_fft=1, avg_frames=F, avg_window=win)
+    ch = OracleChannel(orc, p)
+    rng = np.random.default_rng(F * 10 + win)
+    hdr = dict(avg_frames=F, avg_window=win)
+    grav = gi.load_stage(os.path.join(util, "gravity_pass.frag"), REF_SHADERS, None, **hdr)
+    copy = gi.load_stage(os.path.join(util, "pass.frag"), REF_SHADERS, None, **hdr)
+    avg = gi.load_stage(os.path.join(util, "average_pass.frag"), REF_SHADERS, None, **hdr) if F > 1 else None
+    k5 = gi.load_stage(os.path.join(util, "smooth_pass.frag"), REF_SHADERS, None, **hdr)
+
+    def run(sh, uniforms):
+        out = np.zeros(n, np.uint16)
+        for x in range(n):
+            out[x] = gi.unorm16(sh.run(dict(uniforms), x, 0)["fragment"].v[0])
+        return out
+
+    diff = np.float32(p.gravity_step) * (np.float32(1.0) / np.float32(p.ur))          # render.c:2224
+    gr_store = np.zeros(n, np.uint16)
+    ring = [np.zeros(n, np.uint16) for _ in range(F)]
+    out_idx = 0
+    for u in range(2 * F + 3):
+        b = (rng.random(n) ** 2 * (1.3 if u % 3 else 0.2)).astype(np.float32)        # "transform_fft output", some > 1
+        spec = np.empty(n, np.float32); tex_o = np.empty(n, np.uint16)
+        orc.L.orc_chan_update(ch.h, C.byref(p), b.ctypes.data, 2, spec.ctypes.data, tex_o.ctypes.data)   # 2: `b` is transform_fft's output
+        upload = _unorm16(b)                                                          # glTexImage1D GL_R16, render.c:521-524
+        gr_store = np.maximum(gr_store, run(copy, {"tex": gi.Sampler1D(upload)}))     # K1: pass.frag blended with GL_MAX
+        gr_store = run(grav, {"tex": gi.Sampler1D(gr_store), "diff": diff})           # K2 in place
+        tex = gr_store
+        if F > 1:
+            ring[out_idx] = run(copy, {"tex": gi.Sampler1D(gr_store)})                # K3
+            uni = {f"t{t}": gi.Sampler1D(ring[(out_idx - t) % F]) for t in range(F)}  # t0 = most recent (render.c:2250-2255)
+            tex = run(avg, uni)                                                       # K4
+            out_idx = (out_idx + 1) % F
+        got = run(k5, {"tex": gi.Sampler1D(tex), "sz": n, "w": n})                    # K5
+        assert np.abs(got.astype(int) - tex_o.astype(int)).max() <= 1, (F, win, u)
+        assert (got != tex_o).mean() < 0.02
