@@ -55,6 +55,15 @@ CASES = [
     ("bars_nosmoothpass", "bars", {"AMPLIFY": "40"}, dict(bars_amplify=40.0, smooth_pass=0), {"pre_smoothed": 0}),
     ("radial_nosmoothpass", "radial", {"C_RADIUS": "12", "AMPLIFY": "30", "NBARS": "40"},
      dict(radial_radius=12.0, radial_amplify=30.0, radial_nbars=40, smooth_pass=0), {"pre_smoothed": 0}),
+    ("bars_mono_invert", "bars", {"AMPLIFY": "40", "INVERT": "1"}, dict(bars_amplify=40.0, channels=1, bars_invert=1), {"channels": 1}),
+    ("graph_both", "graph", {"VSCALE": "42", "DRAW_OUTLINE": "1", "DRAW_HIGHLIGHT": "1"},
+     dict(graph_vscale=42.0, graph_draw_outline=1, graph_draw_highlight=1), {}),
+    # odd surface sizes: screen.x / 2 and screen.y / 2 are INTEGER divisions in the shaders
+    ("bars_odd", "bars", {"AMPLIFY": "40"}, dict(bars_amplify=40.0), {}, (95, 53)),
+    ("radial_odd", "radial", {"C_RADIUS": "12", "AMPLIFY": "30", "NBARS": "40"}, dict(radial_radius=12.0, radial_amplify=30.0, radial_nbars=40), {}, (95, 53)),
+    ("circle_odd", "circle", {"C_RADIUS": "12", "AMPLIFY": "20"}, dict(circle_radius=12.0, circle_amplify=20.0), {}, (93, 51)),
+    ("graph_odd", "graph", {"VSCALE": "40"}, dict(graph_vscale=40.0), {}, (95, 53)),
+    ("wave_odd", "wave", {"AMPLIFY": "40"}, dict(wave_amplify=40.0), {}, (95, 53)),
     ("radial_nopremult", "radial", {"C_RADIUS": "12", "AMPLIFY": "30", "NBARS": "40"},
      dict(radial_radius=12.0, radial_amplify=30.0, radial_nbars=40, premultiply_alpha=0), {"premultiply_alpha": 0}),
 ]
@@ -72,14 +81,17 @@ def textures(orc, p, module, seed):
 def main():
     orc = Oracle("libm")
     out = {"case_names": np.array([c[0] for c in CASES])}
-    for i, (name, module, gl_over, p_over, hdr) in enumerate(CASES):
-        p = orc.default_params(module, n=N, w=W, h=H)
+    for i, case in enumerate(CASES):
+        name, module, gl_over, p_over, hdr = case[:5]
+        w, h = case[5] if len(case) > 5 else (W, H)
+        p = orc.default_params(module, n=N, w=w, h=h)
         tl, tr = textures(orc, p, module, 100 + i)
-        prog = gi.ModuleProgram(SHADERS, module, W, H, tl, tr, overrides=gl_over, **hdr)
-        frame = np.zeros((H, W, 4), np.uint8)
-        for y in range(H):
-            for x in range(W):
+        prog = gi.ModuleProgram(SHADERS, module, w, h, tl, tr, overrides=gl_over, **hdr)
+        frame = np.zeros((h, w, 4), np.uint8)
+        for y in range(h):
+            for x in range(w):
                 frame[y, x] = prog.pixel(x, y)
+        out[f"{name}_size"] = np.array([w, h])
         out[f"{name}_module"] = np.array(module)
         out[f"{name}_params"] = np.array(json.dumps(p_over))
         out[f"{name}_tl"] = tl; out[f"{name}_tr"] = tr; out[f"{name}_frame"] = frame
