@@ -8,7 +8,7 @@
  * passes K2 / K4 / K5 restate GLSL; no GL implementation is available in this image, so
  * they are pinned one level down: oracle/glsl_interp.py EXECUTES the reference's own shader
  * sources (with GLava's source extensions and injected header) in float32, and this
- * restatement equals its frames bit for bit (tests/golden/glsl_golden.npz: 14 module
+ * restatement equals its frames bit for bit (tests/golden/glsl_golden.npz: 24 module
  * configurations, the three SAMPLE_MODEs of smooth_pass.frag, gravity / average / pass;
  * plus the `test` module's #55000055 known answer, shaders/glava/test_rc.glsl:27).  What
  * GLSL leaves implementation-defined (transcendental ulps, round() ties, out-of-range
