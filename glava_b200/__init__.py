@@ -13,7 +13,8 @@ raises.
 """
 from .api import (Params, Color, Renderer, GlavaError, default_params, load_config, lib, lib_path,
                   MODULES, pinned_empty)
+from . import audio
 from .synth import synth_pcm_int16, fifo_to_float, StreamRings
 
-__all__ = ["Params", "Color", "Renderer", "GlavaError", "default_params", "load_config", "lib",
+__all__ = ["audio", "Params", "Color", "Renderer", "GlavaError", "default_params", "load_config", "lib",
            "lib_path", "MODULES", "pinned_empty", "synth_pcm_int16", "fifo_to_float", "StreamRings"]

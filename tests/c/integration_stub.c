@@ -9,9 +9,15 @@
 #include <string.h>
 
 #include "glava_b200.h"
+#include "glava_b200_audio.h"
 
 static int hook_calls = 0;
 static void on_fatal(const char* msg) { ++hook_calls; fprintf(stderr, "[hook] %s\n", msg); }
+
+/* a backend written against GLava's plug-in ABI (fifo.h:22-26) */
+static void  null_init(struct audio_data* d) { d->format = 7; }
+static void* null_entry(void* d) { (void) d; return NULL; }
+static struct audio_impl null_backend = { "null", null_init, null_entry };
 
 int main(void) {
     glava_b200_params prm;
@@ -27,6 +33,20 @@ int main(void) {
         int calls = hook_calls;
         if (glava_b200_load_config(&tmp, NULL, NULL, bad, NULL) == 0) return 12;
         if (hook_calls != calls + 1 || !strstr(glava_b200_last_error(), "unknown request type")) return 13;
+    }
+
+    /* audio plug-in ABI: the native "fifo" backend is there, an unknown `-a NAME` reports like glava.c:476-479,
+       a backend of the reference's shape registers, starts one thread per stream and stops */
+    {
+        int calls = hook_calls;
+        glava_b200_audio* au;
+        if (!glava_b200_audio_find("fifo")) return 21;
+        if (glava_b200_audio_find("pulseaudio") || hook_calls != calls + 1 ||
+            !strstr(glava_b200_last_error(), "The specified audio backend (\"pulseaudio\") is not available.")) return 22;
+        if (glava_b200_audio_register(&null_backend) != 0 || glava_b200_audio_find("null") != &null_backend) return 23;
+        au = glava_b200_audio_start("null", NULL, 2, 1024, 1024, 22050, 2);
+        if (!au || glava_b200_audio_stream(au, 1)->format != 7 || glava_b200_audio_stream(au, 1)->audio_buf_sz != 1024) return 24;
+        if (glava_b200_audio_stop(au) != 0) return 25;
     }
 
     enum { BATCH = 3 };
