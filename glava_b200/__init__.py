@@ -12,9 +12,9 @@ There is no CPU fallback: constructing a Renderer without the CUDA library or wi
 raises.
 """
 from .api import (Params, Color, Renderer, GlavaError, default_params, load_config, lib, lib_path,
-                  MODULES, pinned_empty)
+                  MODULES, pinned_empty, Pipe)
 from . import audio
 from .synth import synth_pcm_int16, fifo_to_float, StreamRings
 
 __all__ = ["audio", "Params", "Color", "Renderer", "GlavaError", "default_params", "load_config", "lib",
-           "lib_path", "MODULES", "pinned_empty", "synth_pcm_int16", "fifo_to_float", "StreamRings"]
+           "lib_path", "MODULES", "pinned_empty", "Pipe", "synth_pcm_int16", "fifo_to_float", "StreamRings"]

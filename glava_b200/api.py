@@ -121,6 +121,14 @@ def lib():
     L.glava_b200_set_abort_hook.argtypes = [vp]
     L.glava_b200_set_timing.argtypes = [vp, i32]
     L.glava_b200_kernel_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i32), C.POINTER(C.c_double), C.POINTER(i32)]
+    L.glava_b200_pipe_new.restype = vp
+    L.glava_b200_pipe_new.argtypes = [C.POINTER(cp), cp, C.POINTER(cp), cp, C.POINTER(cp)]
+    L.glava_b200_pipe_feed.argtypes = [vp, cp, C.c_size_t]
+    L.glava_b200_pipe_params.argtypes = [vp, C.POINTER(Params)]
+    L.glava_b200_pipe_bind_count.argtypes = [vp]
+    L.glava_b200_pipe_bind.argtypes = [vp, i32, C.POINTER(cp), C.POINTER(cp), C.POINTER(C.c_float)]
+    L.glava_b200_pipe_apply.argtypes = [vp, vp]
+    L.glava_b200_pipe_free.argtypes = [vp]
     _lib = L
     # errors surface as Python exceptions; keep stderr quiet
     _quiet = C.CFUNCTYPE(None, cp)(lambda msg: None)
@@ -162,6 +170,51 @@ def load_config(paths=None, entry="rc.glsl", requests=None, force_module=None, b
                                               _cstr_array(requests), force_module.encode() if force_module else None,
                                               _cstr_array(bl)))
     return p
+
+
+class Pipe:
+    """live `--pipe NAME[:TYPE]` binds fed with stdin text (glava.c:338-411, render.c:1846-2100)"""
+
+    def __init__(self, pipe_args, paths=None, entry="rc.glsl", requests=None, force_module=None):
+        self._L = lib()
+        self._h = self._L.glava_b200_pipe_new(_cstr_array(paths), entry.encode() if entry else None, _cstr_array(requests),
+                                              force_module.encode() if force_module else None, _cstr_array(list(pipe_args)))
+        if not self._h:
+            raise GlavaError(self._L.glava_b200_last_error().decode(errors="replace"))
+        self.messages = []
+
+    def feed(self, text):
+        """-> number of binds that took a new value; parse complaints (reference wording) are appended to .messages"""
+        data = text.encode() if isinstance(text, str) else bytes(text)
+        n = self._L.glava_b200_pipe_feed(self._h, data, len(data))
+        if n < 0:
+            raise GlavaError(self._L.glava_b200_last_error().decode(errors="replace"))
+        return n
+
+    def params(self):
+        p = Params()
+        _check(self._L.glava_b200_pipe_params(self._h, C.byref(p)))
+        return p
+
+    def binds(self):
+        out = {}
+        for i in range(self._L.glava_b200_pipe_bind_count(self._h)):
+            name, typ, val = C.c_char_p(), C.c_char_p(), (C.c_float * 4)()
+            _check(self._L.glava_b200_pipe_bind(self._h, i, C.byref(name), C.byref(typ), val))
+            out[name.value.decode()] = (typ.value.decode(), tuple(val))
+        return out
+
+    def apply(self, renderer):
+        _check(self._L.glava_b200_pipe_apply(self._h, renderer._h))
+        _check(self._L.glava_b200_get_params(renderer._h, C.byref(renderer.params)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.glava_b200_pipe_free(self._h)
+            self._h = None
+
+    def __enter__(self): return self
+    def __exit__(self, *a): self.close()
 
 
 _pinned = []

@@ -104,6 +104,7 @@ void fill_defaults(glava_b200_params* p, int module) {
 
 // ---- tiny expression evaluator for numeric #defines: + - * / ( ) literals PI TWOPI ---------
 struct Num { double v; bool is_int; };
+static std::string strip_bind(const std::string& v);      // `@name:default` -> bound value or default (below)
 struct ExprParser {
     const char* s; const std::map<std::string, std::string>* defs; int depth; bool ok;
     void ws() { while (*s && isspace((unsigned char) *s)) ++s; }
@@ -129,7 +130,8 @@ struct ExprParser {
             if (id == "float" || id == "int") { Num r = primary(); if (id == "float") r.is_int = false; return r; }
             auto it = defs ? defs->find(id) : decltype(defs->end())();
             if (defs && it != defs->end() && depth < 8) {
-                ExprParser sub { it->second.c_str(), defs, depth + 1, true };
+                const std::string body = strip_bind(it->second);
+                ExprParser sub { body.c_str(), defs, depth + 1, true };
                 Num r = sub.expr(); sub.ws();
                 if (!sub.ok || *sub.s) ok = false;
                 return r;
@@ -174,7 +176,8 @@ static std::string trim_copy(const std::string& s) {
 static bool eval_num(const Defs& d, const char* name, Num* out) {
     auto it = d.find(name);
     if (it == d.end()) return false;
-    ExprParser p { it->second.c_str(), &d, 0, true };
+    const std::string body = strip_bind(it->second);
+    ExprParser p { body.c_str(), &d, 0, true };
     Num r = p.expr(); p.ws();
     if (!p.ok || *p.s) {
         fail(GLAVA_B200_ECONFIG, "cannot evaluate '#define %s %s' as a number", name, it->second.c_str());
@@ -581,6 +584,25 @@ int load_config(glava_b200_params* out, const char* const* paths, const char* en
         for (const std::string& f : { std::string("smooth_parameters.glsl"), L.module + ".glsl" }) {
             if (!scan_file(L, dd + "/" + f, &defs, true, dctx)) return GLAVA_B200_ECONFIG;
             if (!scan_file(L, entry_dir + "/" + f, &defs, true, cctx)) return GLAVA_B200_ECONFIG;
+        }
+    }
+    else if (!bind_map.empty()) {
+        // no config directory: the shipped module configs still carry their `@fg:` / `@bg:` macros, so a `--pipe` bind
+        // reaches them (bars.glsl:18-22, radial.glsl:7,15-17, circle.glsl:6, graph.glsl:8-11,21, wave.glsl:6,10)
+        switch (mod) {
+            case GLAVA_B200_MOD_BARS:
+                defs["GRADIENT"] = "80"; defs["COLOR"] = "@fg:mix(#3366b2, #a0a0b2, clamp(d / GRADIENT, 0, 1))";
+                defs["BAR_OUTLINE"] = "@bg:vec4(COLOR.rgb * 1.5, COLOR.a)"; break;
+            case GLAVA_B200_MOD_RADIAL:
+                defs["GRADIENT"] = "95"; defs["COLOR"] = "@fg:mix(#cc3333, #cca0a0, clamp(d / GRADIENT, 0, 1))";
+                defs["OUTLINE"] = "@bg:#333333"; break;
+            case GLAVA_B200_MOD_CIRCLE: defs["OUTLINE"] = "@fg:#333333"; break;
+            case GLAVA_B200_MOD_GRAPH:
+                defs["GRADIENT"] = "75"; defs["COLOR"] = "@fg:mix(#802A2A, #4F4F92, clamp(pos / GRADIENT, 0, 1))";
+                defs["OUTLINE"] = "@bg:#262626"; break;
+            case GLAVA_B200_MOD_WAVE:
+                defs["BASE_COLOR"] = "@fg:vec4(0.7, 0.2, 0.45, 1)"; defs["OUTLINE"] = "@bg:vec4(0.15, 0.15, 0.15, 1)"; break;
+            default: break;
         }
     }
     // CLI requests are applied last in the reference too (after module load they would hit

@@ -134,6 +134,26 @@ int glava_b200_load_config(glava_b200_params* out, const char* const* paths, con
 int glava_b200_load_config_binds(glava_b200_params* out, const char* const* paths, const char* entry,
                                  const char* const* requests, const char* force_module, const char* const* binds);
 
+/* Live `--pipe` binds (glava.c:338-411, render.c:1846-2100).  pipe_args: NULL-terminated "NAME[:TYPE]" strings exactly
+ * as given to `--pipe` (TYPE one of int, float, bool, vec2, vec3, vec4; default vec4; a NULL-equivalent name is "_"),
+ * validated with the reference's messages.  The other arguments are those of glava_b200_load_config and are copied.
+ *   _feed    bytes as they arrive on stdin; every complete line `name = value` (or just `value` for the first bind)
+ *            is parsed with the reference's rules — prefix match of the name, "#rrggbb[aa]" or "r,g,b,a" for vec4,
+ *            true/TRUE/True/1 for bool ... — and its messages ("Bad assignment format", "Variable name not bound",
+ *            "Bad format for color string").  Returns the number of binds that took a new value.
+ *   _params  the configuration re-evaluated with every `@name:default` macro of a bound name reading the bind's current
+ *            value (0 / vec4(0) until its first line, like an unwritten GL uniform).
+ *   _apply   _params + glava_b200_reconfigure when a bind changed since the last call: the uniform write of
+ *            render.c:2071-2100.  Call once per frame after _feed. */
+typedef struct glava_b200_pipe glava_b200_pipe;
+glava_b200_pipe* glava_b200_pipe_new(const char* const* paths, const char* entry, const char* const* requests,
+                                     const char* force_module, const char* const* pipe_args);
+int  glava_b200_pipe_feed(glava_b200_pipe* p, const char* bytes, size_t len);
+int  glava_b200_pipe_params(glava_b200_pipe* p, glava_b200_params* out);
+int  glava_b200_pipe_bind_count(const glava_b200_pipe* p);
+int  glava_b200_pipe_bind(const glava_b200_pipe* p, int index, const char** name, const char** type, float value[4]);
+void glava_b200_pipe_free(glava_b200_pipe* p);
+
 /* rd_new (render.h:53-57): build a renderer for `batch` independent streams on CUDA device
  * `device` with the given parameters (from glava_b200_load_config / _default_params). */
 glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int device);
@@ -145,6 +165,7 @@ void glava_b200_destroy(glava_b200* r);
  * (setbufsize, geometry, module, setaccelfft, setavgframes, fb_slots) must be unchanged. */
 int  glava_b200_reconfigure(glava_b200* r, const glava_b200_params* params);
 int  glava_b200_get_params(const glava_b200* r, glava_b200_params* out);
+int  glava_b200_pipe_apply(glava_b200_pipe* p, glava_b200* r);   /* see glava_b200_pipe_new */
 int  glava_b200_batch(const glava_b200* r);
 const char* glava_b200_module_name(const glava_b200* r);
 
