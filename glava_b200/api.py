@@ -16,6 +16,15 @@ class Color(C.Structure):
     _fields_ = [("mode", C.c_int), ("lo", C.c_float * 4), ("hi", C.c_float * 4), ("gradient", C.c_float)]
 
 
+class ColorOp(C.Structure):
+    _fields_ = [("op", C.c_uint8), ("dst", C.c_uint8), ("a", C.c_uint8), ("b", C.c_uint8), ("imm", C.c_float)]
+
+
+class ColorProg(C.Structure):
+    """glava_b200_color_prog: a compiled colour expression (mode 2 of the colour it belongs to)"""
+    _fields_ = [("n_ops", C.c_int), ("result", C.c_int), ("ops", ColorOp * 64)]
+
+
 class Params(C.Structure):
     """struct glava_b200_params (include/glava_b200.h) — same field order."""
     _fields_ = [
@@ -44,6 +53,8 @@ class Params(C.Structure):
         ("fb_slots", C.c_int), ("lazy_smooth", C.c_int),
         ("bufscale", C.c_int), ("interpolate", C.c_int), ("fr", C.c_float), ("transform_smooth", C.c_int),
         ("smooth_distance", C.c_float), ("smooth_ratio", C.c_float),
+        ("bars_color_prog", ColorProg), ("bars_outline_prog", ColorProg), ("radial_color_prog", ColorProg),
+        ("graph_color_prog", ColorProg),
     ]
 
     def copy(self):

@@ -7,6 +7,7 @@
 // preprocessor: module shaders are CUDA kernels here, so only the values of the
 // documented `#define`s of <module>.glsl / smooth_parameters.glsl are extracted.
 #include "internal.h"
+#include "raster_core.h"      // eval_color_prog: constant colour expressions are evaluated at config time
 
 #include <cctype>
 #include <cmath>
@@ -250,33 +251,73 @@ static bool parse_const_color(const Defs& d, const std::string& s, float out[4])
     }
     return false;
 }
-// COLOR forms understood: constant colour | mix(<colour>, <colour>, clamp(<var> / <num>, 0, 1))
-static bool parse_color_macro(const Defs& d, const char* name, glava_b200_color* c) {
+}  // namespace glb
+#include "color_compile.h"
+namespace glb {
+
+// COLOR forms: constant colour (mode 1) | mix(<colour>, <colour>, clamp(<var> / <num>, 0, 1)) (mode 0, the shipped form)
+// | any other expression color_compile.h can compile (mode 2, program in *prog).  `vars`: names of the per-pixel variable.
+static bool compile_color_text(const Defs& d, const char* name, const std::string& text, std::vector<std::string> vars,
+                               glava_b200_color_prog* prog, bool* uses_var) {
+    ColorCompiler cc(&d, std::move(vars));
+    if (!cc.compile(text, prog)) {
+        fail(GLAVA_B200_ECONFIG, "unsupported colour expression in '#define %s %s': %s", name, text.c_str(), cc.err.c_str());
+        return false;
+    }
+    if (uses_var) *uses_var = cc.uses_var;
+    return true;
+}
+static bool const_equals(const Defs& d, const std::string& text, double want) {
+    ExprParser p { text.c_str(), &d, 0, true };
+    Num n = p.expr(); p.ws();
+    return p.ok && !*p.s && n.v == want;
+}
+static bool parse_color_macro(const Defs& d, const char* name, glava_b200_color* c, glava_b200_color_prog* prog,
+                              std::vector<std::string> vars) {
     auto it = d.find(name);
     if (it == d.end()) return true;
     std::string v = strip_bind(it->second);
+    prog->n_ops = 0;
     float k[4];
     if (parse_const_color(d, v, k)) { c->mode = 1; memcpy(c->lo, k, sizeof(k)); memcpy(c->hi, k, sizeof(k)); return true; }
     std::vector<std::string> a, b;
-    if (split_call(v, "mix", &a) && a.size() == 3 && parse_const_color(d, a[0], c->lo) && parse_const_color(d, a[1], c->hi)
-        && split_call(a[2], "clamp", &b) && b.size() == 3) {
+    float lo[4], hi[4];
+    if (split_call(v, "mix", &a) && a.size() == 3 && parse_const_color(d, a[0], lo) && parse_const_color(d, a[1], hi)
+        && split_call(a[2], "clamp", &b) && b.size() == 3 && const_equals(d, b[1], 0.0) && const_equals(d, b[2], 1.0)) {
         size_t slash = b[0].find('/');
-        if (slash != std::string::npos) {
+        bool var_ok = false;
+        if (slash != std::string::npos) for (const std::string& x : vars) var_ok |= trim(b[0].substr(0, slash)) == x;
+        if (var_ok) {
             ExprParser p { b[0].c_str() + slash + 1, &d, 0, true };
             Num n = p.expr(); p.ws();
-            if (p.ok && !*p.s) { c->mode = 0; c->gradient = (float) n.v; return true; }
+            if (p.ok && !*p.s) {
+                c->mode = 0; c->gradient = (float) n.v;
+                memcpy(c->lo, lo, sizeof(lo)); memcpy(c->hi, hi, sizeof(hi));
+                return true;
+            }
         }
     }
-    fail(GLAVA_B200_ECONFIG, "unsupported colour expression in '#define %s %s' (supported: #rrggbb[aa], vec4(..), "
-         "mix(<colour>, <colour>, clamp(<x> / <n>, 0, 1)))", name, it->second.c_str());
-    return false;
+    bool uses_var = false;
+    if (!compile_color_text(d, name, v, vars, prog, &uses_var)) return false;
+    if (!uses_var) {                                         // a constant after all: fold it
+        const f4 r = eval_color_prog(*prog, 0.0f);
+        c->mode = 1; c->lo[0] = c->hi[0] = r.r; c->lo[1] = c->hi[1] = r.g; c->lo[2] = c->hi[2] = r.b; c->lo[3] = c->hi[3] = r.a;
+        prog->n_ops = 0;
+        return true;
+    }
+    c->mode = 2;
+    return true;
 }
 static bool parse_plain_color(const Defs& d, const char* name, float out[4]) {
     auto it = d.find(name);
     if (it == d.end()) return true;
-    if (parse_const_color(d, strip_bind(it->second), out)) return true;
-    fail(GLAVA_B200_ECONFIG, "unsupported colour expression in '#define %s %s'", name, it->second.c_str());
-    return false;
+    const std::string v = strip_bind(it->second);
+    if (parse_const_color(d, v, out)) return true;
+    glava_b200_color_prog prog; bool uses_var = false;
+    if (!compile_color_text(d, name, v, {}, &prog, &uses_var)) return false;      // no variable is in scope: constants only
+    const f4 r = eval_color_prog(prog, 0.0f);
+    out[0] = r.r; out[1] = r.g; out[2] = r.b; out[3] = r.a;
+    return true;
 }
 
 // ---- file reading ---------------------------------------------------------------------------
@@ -480,14 +521,25 @@ static void apply_defines(glava_b200_params* p, const Defs& d) {
         case GLAVA_B200_MOD_BARS:
             getf(d, "BAR_WIDTH", &p->bars_width); getf(d, "BAR_GAP", &p->bars_gap);
             getf(d, "BAR_OUTLINE_WIDTH", &p->bars_outline_width); getf(d, "AMPLIFY", &p->bars_amplify);
-            parse_color_macro(d, "COLOR", &p->bars_color);
+            parse_color_macro(d, "COLOR", &p->bars_color, &p->bars_color_prog, { "d" });
             if (p->bars_color.mode == 0 && eval_num(d, "GRADIENT", &n)) p->bars_color.gradient = (float) n.v;
             if ((it = d.find("BAR_OUTLINE")) != d.end()) {
                 std::string v = strip_bind(it->second);
                 std::string squeezed; for (char c : v) if (!isspace((unsigned char) c)) squeezed += c;
                 if (squeezed == "vec4(COLOR.rgb*1.5,COLOR.a)") p->bars_outline_mode = 0;
                 else if (parse_const_color(d, v, p->bars_outline)) p->bars_outline_mode = 1;
-                else fail(GLAVA_B200_ECONFIG, "unsupported '#define BAR_OUTLINE %s'", it->second.c_str());
+                else {                                       // any other expression of d (COLOR expands textually inside it)
+                    bool uses_var = false;
+                    p->bars_outline_prog.n_ops = 0;
+                    if (compile_color_text(d, "BAR_OUTLINE", v, { "d" }, &p->bars_outline_prog, &uses_var)) {
+                        if (uses_var) p->bars_outline_mode = 2;
+                        else {
+                            const f4 r = eval_color_prog(p->bars_outline_prog, 0.0f);
+                            p->bars_outline[0] = r.r; p->bars_outline[1] = r.g; p->bars_outline[2] = r.b; p->bars_outline[3] = r.a;
+                            p->bars_outline_mode = 1; p->bars_outline_prog.n_ops = 0;
+                        }
+                    }
+                }
             }
             geti(d, "DIRECTION", &p->bars_direction); geti(d, "INVERT", &p->bars_invert);
             geti(d, "FLIP", &p->bars_flip); geti(d, "MIRROR_YX", &p->bars_mirror_yx);
@@ -502,7 +554,7 @@ static void apply_defines(glava_b200_params* p, const Defs& d) {
             parse_plain_color(d, "OUTLINE", p->radial_outline);
             geti(d, "NBARS", &p->radial_nbars); getf(d, "BAR_WIDTH", &p->radial_bar_width);
             getf(d, "AMPLIFY", &p->radial_amplify);
-            parse_color_macro(d, "COLOR", &p->radial_color);
+            parse_color_macro(d, "COLOR", &p->radial_color, &p->radial_color_prog, { "d" });
             if (p->radial_color.mode == 0 && eval_num(d, "GRADIENT", &n)) p->radial_color.gradient = (float) n.v;
             getf(d, "ROTATE", &p->radial_rotate); geti(d, "INVERT", &p->radial_invert);
             getf(d, "BAR_ALIAS_FACTOR", &p->radial_bar_alias); getf(d, "C_ALIAS_FACTOR", &p->radial_c_alias);
@@ -518,7 +570,7 @@ static void apply_defines(glava_b200_params* p, const Defs& d) {
             break;
         case GLAVA_B200_MOD_GRAPH:
             getf(d, "VSCALE", &p->graph_vscale); geti(d, "DIRECTION", &p->graph_direction);
-            parse_color_macro(d, "COLOR", &p->graph_color);
+            parse_color_macro(d, "COLOR", &p->graph_color, &p->graph_color_prog, { "pos", "d" });
             if (p->graph_color.mode == 0 && eval_num(d, "GRADIENT", &n)) p->graph_color.gradient = (float) n.v;
             geti(d, "DRAW_OUTLINE", &p->graph_draw_outline); geti(d, "DRAW_HIGHLIGHT", &p->graph_draw_highlight);
             parse_plain_color(d, "OUTLINE", p->graph_outline); geti(d, "INVERT", &p->graph_invert);
@@ -624,6 +676,22 @@ int validate_params(const glava_b200_params* p) {
     if (p->channels != 1 && p->channels != 2) return bad("channels");
     if (p->sample_mode < 0 || p->sample_mode > 2 || p->round_formula < 0 || p->round_formula > 2) return bad("sample mode / round formula");
     if (p->radial_nbars < 2) return bad("NBARS");
+    const glava_b200_color* cols[3] = { &p->bars_color, &p->radial_color, &p->graph_color };
+    const glava_b200_color_prog* progs[4] = { &p->bars_color_prog, &p->radial_color_prog, &p->graph_color_prog, &p->bars_outline_prog };
+    for (int i = 0; i < 3; ++i) {
+        if (cols[i]->mode < 0 || cols[i]->mode > 2) return bad("colour mode");
+        if (cols[i]->mode == 2 && progs[i]->n_ops < 1) return bad("colour mode 2 without a compiled expression");
+    }
+    if (p->bars_outline_mode < 0 || p->bars_outline_mode > 2 || (p->bars_outline_mode == 2 && p->bars_outline_prog.n_ops < 1)) return bad("bars_outline_mode");
+    for (int i = 0; i < 4; ++i) {
+        if (progs[i]->n_ops < 0 || progs[i]->n_ops > GLAVA_B200_COLOR_OPS || progs[i]->result < 0 || progs[i]->result >= GLAVA_B200_COLOR_REGS)
+            return bad("colour program size");
+        for (int k = 0; k < progs[i]->n_ops; ++k) {
+            const glava_b200_color_op& o = progs[i]->ops[k];
+            if (o.op >= GLAVA_B200_COP_COUNT || o.dst >= GLAVA_B200_COLOR_REGS || o.a >= GLAVA_B200_COLOR_REGS || o.b >= GLAVA_B200_COLOR_REGS)
+                return bad("colour program instruction");
+        }
+    }
     if (!(p->bars_width + p->bars_gap > 0.0f)) return bad("BAR_WIDTH + BAR_GAP");
     if (p->bufscale < 1 || p->n % p->bufscale || p->n / p->bufscale < 256 || ((p->n / p->bufscale) & (p->n / p->bufscale - 1)))
         return bad("setbufsize / setbufscale must be a power of two >= 256");

@@ -25,8 +25,71 @@ GLB_HD f4 g_mix(f4 a, f4 b, float t) {
     float s = 1.0f - t;
     return mk4(a.r * s + b.r * t, a.g * s + b.g * t, a.b * s + b.b * t, a.a * s + b.a * t);
 }
-GLB_HD f4 eval_color(const glava_b200_color& c, float x) {
+// ---- compiled colour expressions (glava_b200_color_prog): any COLOR / BAR_OUTLINE macro the closed forms do not cover ----
+// One instruction = one lane-wise float operation, each individually rounded like the GLSL it was compiled from.
+#define GLB_COP1(expr) { const f4 A = reg[o.a]; float v; f4 R; \
+    v = A.r; R.r = (expr); v = A.g; R.g = (expr); v = A.b; R.b = (expr); v = A.a; R.a = (expr); reg[o.dst] = R; } break
+#define GLB_COP2(expr) { const f4 A = reg[o.a], B = reg[o.b]; float v, w; f4 R; \
+    v = A.r; w = B.r; R.r = (expr); v = A.g; w = B.g; R.g = (expr); v = A.b; w = B.b; R.b = (expr); v = A.a; w = B.a; R.a = (expr); \
+    reg[o.dst] = R; } break
+#define GLB_COP3(expr) { const f4 A = reg[o.a], B = reg[o.b], Cc = reg[((int) o.imm) & (GLAVA_B200_COLOR_REGS - 1)]; float v, w, u; f4 R; \
+    v = A.r; w = B.r; u = Cc.r; R.r = (expr); v = A.g; w = B.g; u = Cc.g; R.g = (expr); \
+    v = A.b; w = B.b; u = Cc.b; R.b = (expr); v = A.a; w = B.a; u = Cc.a; R.a = (expr); reg[o.dst] = R; } break
+GLB_HD float cop_smoothstep(float e0, float e1, float x) {
+    const float t = g_clamp((x - e0) / (e1 - e0), 0.0f, 1.0f);
+    return (t * t) * (3.0f - (2.0f * t));
+}
+GLB_HD float& cop_lane(f4& r, int k) { return k == 0 ? r.r : (k == 1 ? r.g : (k == 2 ? r.b : r.a)); }
+GLB_HD f4 eval_color_prog(const glava_b200_color_prog& c, float x) {
+    f4 reg[GLAVA_B200_COLOR_REGS];
+    for (int i = 0; i < GLAVA_B200_COLOR_REGS; ++i) reg[i] = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+    const int n = c.n_ops < GLAVA_B200_COLOR_OPS ? c.n_ops : GLAVA_B200_COLOR_OPS;
+    for (int i = 0; i < n; ++i) {
+        glava_b200_color_op o = c.ops[i];
+        o.dst &= GLAVA_B200_COLOR_REGS - 1; o.a &= GLAVA_B200_COLOR_REGS - 1; o.b &= GLAVA_B200_COLOR_REGS - 1;
+        switch (o.op) {
+            case GLAVA_B200_COP_SPLAT: reg[o.dst] = mk4(o.imm, o.imm, o.imm, o.imm); break;
+            case GLAVA_B200_COP_VAR:   reg[o.dst] = mk4(x, x, x, x); break;
+            case GLAVA_B200_COP_LANE:  cop_lane(reg[o.dst], o.a & 3) = o.imm; break;
+            case GLAVA_B200_COP_SHUF: {
+                const f4 A = reg[o.a]; f4 R = reg[o.dst];
+                const int m = (int) o.imm;
+                for (int k = 0; k < 4; ++k) {
+                    const int sel = (m >> (3 * k)) & 7;
+                    if (sel < 4) { f4 T = A; cop_lane(R, k) = cop_lane(T, sel); }
+                }
+                reg[o.dst] = R;
+            } break;
+            case GLAVA_B200_COP_ADD:   GLB_COP2(v + w);
+            case GLAVA_B200_COP_SUB:   GLB_COP2(v - w);
+            case GLAVA_B200_COP_MUL:   GLB_COP2(v * w);
+            case GLAVA_B200_COP_DIV:   GLB_COP2(v / w);
+            case GLAVA_B200_COP_MIN:   GLB_COP2(g_min(v, w));
+            case GLAVA_B200_COP_MAX:   GLB_COP2(g_max(v, w));
+            case GLAVA_B200_COP_MOD:   GLB_COP2(g_mod(v, w));
+            case GLAVA_B200_COP_STEP:  GLB_COP2(w < v ? 0.0f : 1.0f);
+            case GLAVA_B200_COP_NEG:   GLB_COP1(-v);
+            case GLAVA_B200_COP_ABS:   GLB_COP1(fabsf(v));
+            case GLAVA_B200_COP_FLOOR: GLB_COP1(floorf(v));
+            case GLAVA_B200_COP_CEIL:  GLB_COP1(ceilf(v));
+            case GLAVA_B200_COP_FRACT: GLB_COP1(v - floorf(v));
+            case GLAVA_B200_COP_SQRT:  GLB_COP1(sqrtf(v));
+            case GLAVA_B200_COP_SIN:   GLB_COP1(glm_sin(v));
+            case GLAVA_B200_COP_COS:   GLB_COP1(glm_sin(v + (GLB_PI / 2.0f)));
+            case GLAVA_B200_COP_LOG:   GLB_COP1(glm_log(v));
+            case GLAVA_B200_COP_SIGN:  GLB_COP1(g_sign(v));
+            case GLAVA_B200_COP_TRUNC: GLB_COP1(truncf(v));
+            case GLAVA_B200_COP_MIX:   GLB_COP3((v * (1.0f - u)) + (w * u));
+            case GLAVA_B200_COP_CLAMP: GLB_COP3(g_min(g_max(v, w), u));
+            case GLAVA_B200_COP_SMOOTHSTEP: GLB_COP3(cop_smoothstep(v, w, u));
+            default: break;
+        }
+    }
+    return reg[c.result & (GLAVA_B200_COLOR_REGS - 1)];
+}
+GLB_HD f4 eval_color(const glava_b200_color& c, const glava_b200_color_prog& prog, float x) {
     if (c.mode == 1) return mk4a(c.lo);
+    if (c.mode == 2) return eval_color_prog(prog, x);
     return g_mix(mk4a(c.lo), mk4a(c.hi), g_clamp(x / c.gradient, 0.0f, 1.0f));
 }
 GLB_HD uint32_t premultiply8(uint32_t px) {                              // util/premultiply.frag:12-15
@@ -98,8 +161,9 @@ GLB_HD BarsCol bars_column(const glava_b200_params& p, const AudioTex& t, float 
     return c;
 }
 GLB_HD BarsRow bars_row(const glava_b200_params& p, float d) {
-    f4 col = eval_color(p.bars_color, d);
-    f4 outl = p.bars_outline_mode == 0 ? mk4(col.r * 1.5f, col.g * 1.5f, col.b * 1.5f, col.a) : mk4a(p.bars_outline);
+    f4 col = eval_color(p.bars_color, p.bars_color_prog, d);
+    f4 outl = p.bars_outline_mode == 0 ? mk4(col.r * 1.5f, col.g * 1.5f, col.b * 1.5f, col.a)
+            : (p.bars_outline_mode == 2 ? eval_color_prog(p.bars_outline_prog, d) : mk4a(p.bars_outline));
     BarsRow r = { pack8(col), pack8(outl) };
     return r;
 }
@@ -161,7 +225,7 @@ GLB_HD RadialGeo radial_geometry(const glava_b200_params& p, int x, int y) {
             g.bar = ((idx > 0.0f ? 0 : 1) << 16) | (int) (fabsf(idx) / section);
             d -= R;
             g.dR = d;
-            f4 r = eval_color(p.radial_color, d);
+            f4 r = eval_color(p.radial_color, p.radial_color_prog, d);
             r.a *= (((p.radial_bar_width / 2.0f) - fabsf(ym)) * p.radial_bar_alias);
             g.lit = radial_finish(p, apply_frag(frag, r));
         }
@@ -344,7 +408,7 @@ GLB_HD float graph_height(const glava_b200_params& p, const AudioTex& t, int x) 
     return s;
 }
 GLB_HD float graph_d(const glava_b200_params& p, int y) { return p.graph_invert > 0 ? (float) p.h - (float) y : (float) y; }
-GLB_HD uint32_t graph_row(const glava_b200_params& p, int y) { return pack8(eval_color(p.graph_color, graph_d(p, y))); }
+GLB_HD uint32_t graph_row(const glava_b200_params& p, int y) { return pack8(eval_color(p.graph_color, p.graph_color_prog, graph_d(p, y))); }
 // stage-1 surface value at (x, y) given the column height s and the row colour
 GLB_HD uint32_t graph_stage1(const glava_b200_params& p, float s, uint32_t rowcol, int y) {
     return (graph_d(p, y) + 1.5f <= s) ? rowcol : 0u;                       // graph/1.frag:116

@@ -31,13 +31,37 @@ extern "C" {
 enum { GLAVA_B200_MOD_BARS = 0, GLAVA_B200_MOD_RADIAL = 1, GLAVA_B200_MOD_CIRCLE = 2,
        GLAVA_B200_MOD_GRAPH = 3, GLAVA_B200_MOD_WAVE = 4, GLAVA_B200_MOD_TEST = 5 };
 
-/* A colour macro of a module config: constant, or mix(lo, hi, clamp(X / gradient, 0, 1))
- * (e.g. bars.glsl:20, radial.glsl:17, graph.glsl:11). */
+/* A colour macro of a module config (e.g. bars.glsl:20, radial.glsl:17, graph.glsl:11):
+ *   mode 1  constant (lo)
+ *   mode 0  mix(lo, hi, clamp(X / gradient, 0, 1))           — the shipped form, evaluated in closed form
+ *   mode 2  any other GLSL expression of the per-pixel variable X (`d`; `pos` in graph) that the config reader could
+ *           compile: the module's glava_b200_color_prog at the end of glava_b200_params is evaluated instead. */
 typedef struct {
-    int   mode;            /* 0 gradient mix, 1 constant (lo) */
+    int   mode;
     float lo[4], hi[4];
     float gradient;
 } glava_b200_color;
+
+/* Compiled colour expression: a straight-line program over 8 four-lane float registers (a scalar lives splat in all
+ * four lanes, so scalar-vector arithmetic is lane-wise as in GLSL).  The value of the expression is register `result`.
+ * Produced by glava_b200_load_config from the macro's text; every instruction is one individually rounded float op. */
+enum { GLAVA_B200_COP_SPLAT = 0,   /* dst = imm in every lane                                   */
+       GLAVA_B200_COP_VAR,         /* dst = X in every lane                                     */
+       GLAVA_B200_COP_LANE,        /* dst.lane[a] = imm                                         */
+       GLAVA_B200_COP_SHUF,        /* dst.lane[k] = reg[a].lane[(imm >> 3k) & 7] unless that selector is 7 */
+       GLAVA_B200_COP_ADD, GLAVA_B200_COP_SUB, GLAVA_B200_COP_MUL, GLAVA_B200_COP_DIV,   /* dst = a op b */
+       GLAVA_B200_COP_MIN, GLAVA_B200_COP_MAX, GLAVA_B200_COP_MOD, GLAVA_B200_COP_STEP,  /* step(edge = a, x = b) */
+       GLAVA_B200_COP_NEG, GLAVA_B200_COP_ABS, GLAVA_B200_COP_FLOOR, GLAVA_B200_COP_CEIL, GLAVA_B200_COP_FRACT,
+       GLAVA_B200_COP_SQRT, GLAVA_B200_COP_SIN, GLAVA_B200_COP_COS, GLAVA_B200_COP_LOG, GLAVA_B200_COP_SIGN,
+       GLAVA_B200_COP_TRUNC,       /* dst = f(a)                                                */
+       GLAVA_B200_COP_MIX,         /* dst = a * (1 - c) + b * c,            c = reg[(int) imm]  */
+       GLAVA_B200_COP_CLAMP,       /* dst = min(max(a, b), c)                                   */
+       GLAVA_B200_COP_SMOOTHSTEP,  /* edges a, b, x = c                                         */
+       GLAVA_B200_COP_COUNT };
+#define GLAVA_B200_COLOR_OPS  64
+#define GLAVA_B200_COLOR_REGS 8
+typedef struct { uint8_t op, dst, a, b; float imm; } glava_b200_color_op;
+typedef struct { int n_ops, result; glava_b200_color_op ops[GLAVA_B200_COLOR_OPS]; } glava_b200_color_prog;
 
 /* Everything rc.glsl / smooth_parameters.glsl / <module>.glsl configure on this path.
  * Field meaning follows the `#request` (render.c:1033-1314) or `#define` named in the
@@ -69,7 +93,7 @@ typedef struct {
     /* bars.glsl */
     float bars_width, bars_gap, bars_outline_width, bars_amplify;
     glava_b200_color bars_color;
-    int   bars_outline_mode;  /* 0: vec4(COLOR.rgb * 1.5, COLOR.a) (bars.glsl:22), 1: constant */
+    int   bars_outline_mode;  /* 0: vec4(COLOR.rgb * 1.5, COLOR.a) (bars.glsl:22), 1: constant, 2: bars_outline_prog */
     float bars_outline[4];
     int   bars_direction, bars_invert, bars_flip, bars_mirror_yx;
     /* radial.glsl */
@@ -110,6 +134,8 @@ typedef struct {
                                  render.c:2143-2154) */
     float smooth_distance;    /* setsmooth       (render.c:917,1201) */
     float smooth_ratio;       /* setsmoothratio  (render.c:918,1204) */
+    /* compiled colour expressions (mode 2 of the colour they belong to; n_ops == 0 otherwise) */
+    glava_b200_color_prog bars_color_prog, bars_outline_prog, radial_color_prog, graph_color_prog;
 } glava_b200_params;
 
 typedef struct glava_b200 glava_b200;    /* plays the role of struct glava_renderer (render.h:8-30) */

@@ -594,6 +594,12 @@ def _clamp(x, lo, hi):
     return min(max(x, lo), hi)
 
 
+def _smoothstep(e0, e1, x):
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = _clamp(F32(F32(x - e0) / F32(e1 - e0)), F32(0.0), F32(1.0))
+    return F32(F32(t * t) * F32(F32(3.0) - F32(F32(2.0) * t)))
+
+
 def _sign(x):
     return F32(1.0) if x > 0 else (F32(-1.0) if x < 0 else F32(0.0))
 
@@ -613,6 +619,7 @@ BUILTINS = {
     "max": lambda a, b: componentwise(lambda p, q: max(p, q), a, b),
     "clamp": lambda x, lo, hi: componentwise(_clamp, x, lo, hi),
     "mix": lambda a, b, t: componentwise(_mix, a, b, t),
+    "smoothstep": lambda e0, e1, x: componentwise(_smoothstep, e0, e1, x),
     "pow": lambda a, b: componentwise(_m2("powf"), a, b),
     "atan": lambda *a: componentwise(_m2("atan2f"), *a) if len(a) == 2 else componentwise(_m1("atanf"), *a),
     "step": lambda e, x: componentwise(lambda p, q: F32(0.0) if q < p else F32(1.0), e, x),

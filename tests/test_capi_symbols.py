@@ -41,7 +41,7 @@ def test_params_struct_layout_matches_header(built):
         decl = decl.strip()
         if not decl or decl.startswith("typedef"):
             continue
-        decl = re.sub(r"^(int|float|glava_b200_color)\s+", "", decl)
+        decl = re.sub(r"^(int|float|glava_b200_color_prog|glava_b200_color)\s+", "", decl)
         for part in decl.split(","):
             fields.append(re.sub(r"\[.*\]", "", part).strip().split()[-1])
     assert fields == [f[0] for f in g.Params._fields_]

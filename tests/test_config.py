@@ -149,7 +149,7 @@ def test_missing_entry(tmp_path, built):
 
 def test_unsupported_colour_expression(tmp_path, built):
     (tmp_path / "rc.glsl").write_text("#request mod bars\n")
-    (tmp_path / "bars.glsl").write_text("#define COLOR vec4(sin(d), 0, 0, 1)\n")
+    (tmp_path / "bars.glsl").write_text("#define COLOR vec4(texture(audio_l, d).r, 0, 0, 1)\n")
     with pytest.raises(g.GlavaError, match="unsupported colour expression"):
         g.load_config([str(tmp_path)])
 
