@@ -55,6 +55,7 @@ class Params(C.Structure):
         ("smooth_distance", C.c_float), ("smooth_ratio", C.c_float),
         ("bars_color_prog", ColorProg), ("bars_outline_prog", ColorProg), ("radial_color_prog", ColorProg),
         ("graph_color_prog", ColorProg),
+        ("clear_color", C.c_float * 4),
     ]
 
     def copy(self):
@@ -157,6 +158,8 @@ def default_params(module="bars", **overrides):
     p = Params()
     _check(lib().glava_b200_default_params(C.byref(p), module.encode()))
     for k, v in overrides.items():
+        if isinstance(v, (list, tuple)):
+            v = type(getattr(p, k))(*v)
         setattr(p, k, v)
     return p
 

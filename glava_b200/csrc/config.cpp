@@ -427,9 +427,27 @@ static bool apply_request(Loader& L, const std::vector<std::string>& t, const ch
             return false;
         }
     }
-    else if (name == "setbg" || name == "setbgf") {
-        // clear colour: every module stage writes every pixel, so the clear never shows (blending
-        // is off in native mode, render.c:1467-1470).  Accepted and ignored.
+    else if (name == "setbg") {                                            // render.c:1062-1075
+        // ext_parse_color (glsl_ext.c:88-122): two hex digits per component, optional 0x, up to 8 digits; components the
+        // string does not reach keep their value (`setbg ff0000` leaves the alpha at its default 0)
+        if (!need(1)) return false;
+        const char* h = t[1].c_str();
+        size_t len = strlen(h);
+        if (len >= 2 && h[0] == '0' && (h[1] == 'x' || h[1] == 'X')) { h += 2; len -= 2; }
+        unsigned acc = 0; int have = 0, comp = 0;
+        for (size_t k = 0; k < len && k < 8; ++k) {
+            const char c = h[k]; unsigned v;
+            if (c >= 'a' && c <= 'f') v = (unsigned) (c - 'a') + 10;
+            else if (c >= 'A' && c <= 'F') v = (unsigned) (c - 'A') + 10;
+            else if (c >= '0' && c <= '9') v = (unsigned) (c - '0');
+            else { fail(GLAVA_B200_ECONFIG, "Invalid value for `setbg` request: '%s'", t[1].c_str()); return false; }
+            acc = (acc << 4) | v;
+            if (++have == 2) { p->clear_color[comp++] = (float) acc / (float) 255; acc = 0; have = 0; }
+        }
+    }
+    else if (name == "setbgf") {                                           // render.c:1092-1099
+        if (!need(4)) return false;
+        for (int k = 0; k < 4; ++k) p->clear_color[k] = as_f(k + 1);
     }
     else {
         // window / desktop / pacing requests of the reference that have no meaning on this path

@@ -97,6 +97,21 @@ GLB_HD uint32_t premultiply8(uint32_t px) {                              // util
     return pack8(mk4(f.r * f.a, f.g * f.a, f.b * f.a, f.a));
 }
 
+// ---- non-native opacity (`setopacity "none"` / "xroot": premultiply_alpha == 0) --------------------------------------
+// The reference then enables GL_BLEND with glBlendFunc(GL_SRC_ALPHA, GL_ONE_MINUS_SRC_ALPHA) for every module stage
+// (render.c:1467-1470), each drawn into a target glClear'd to the `setbg` colour (render.c:1700, 2028), and skips the
+// premultiply stages (util/premultiply.frag:2-4).  Fixed-function blending restated in float32: fragment clamped to [0, 1],
+// destination read back from the RGBA8 target, C = Cs * As + Cd * (1 - As) for all four channels, each op rounded.
+// NATIVE = true is the shipped mode and compiles to exactly the code it was before this existed.
+GLB_HD uint32_t blend_store(const glava_b200_params& p, f4 s) {
+    s = mk4(g_clamp(s.r, 0.0f, 1.0f), g_clamp(s.g, 0.0f, 1.0f), g_clamp(s.b, 0.0f, 1.0f), g_clamp(s.a, 0.0f, 1.0f));
+    const f4 d = unpack8(pack8(mk4a(p.clear_color)));
+    const float k = 1.0f - s.a;
+    return pack8(mk4((s.r * s.a) + (d.r * k), (s.g * s.a) + (d.g * k), (s.b * s.a) + (d.b * k), (s.a * s.a) + (d.a * k)));
+}
+template <bool NATIVE> GLB_HD uint32_t stage_store(const glava_b200_params& p, f4 s) { return NATIVE ? pack8(s) : blend_store(p, s); }
+template <bool NATIVE> GLB_HD uint32_t stage_bg(const glava_b200_params& p) { return NATIVE ? 0u : blend_store(p, mk4(0.0f, 0.0f, 0.0f, 0.0f)); }
+
 // the 1-D textures bound as audio_l / audio_r for one stream
 struct AudioTex {
     const uint16_t* l; const uint16_t* r;
@@ -160,24 +175,27 @@ GLB_HD BarsCol bars_column(const glava_b200_params& p, const AudioTex& t, float 
     c.cls = inner ? 1 : 2;
     return c;
 }
-GLB_HD BarsRow bars_row(const glava_b200_params& p, float d) {
+template <bool NATIVE> GLB_HD BarsRow bars_row_t(const glava_b200_params& p, float d) {
     f4 col = eval_color(p.bars_color, p.bars_color_prog, d);
     f4 outl = p.bars_outline_mode == 0 ? mk4(col.r * 1.5f, col.g * 1.5f, col.b * 1.5f, col.a)
             : (p.bars_outline_mode == 2 ? eval_color_prog(p.bars_outline_prog, d) : mk4a(p.bars_outline));
-    BarsRow r = { pack8(col), pack8(outl) };
+    BarsRow r = { stage_store<NATIVE>(p, col), stage_store<NATIVE>(p, outl) };
     return r;
 }
-GLB_HD uint32_t bars_combine(const glava_b200_params& p, const BarsCol& c, const BarsRow& r, float d) {
-    if (c.cls == 0) return 0u;
+GLB_HD BarsRow bars_row(const glava_b200_params& p, float d) { return bars_row_t<true>(p, d); }
+// bg: what a fragment left at vec4(0) stores (0 natively, the blended clear colour otherwise)
+GLB_HD uint32_t bars_combine(const glava_b200_params& p, const BarsCol& c, const BarsRow& r, float d, uint32_t bg = 0u) {
+    if (c.cls == 0) return bg;
     if (d < c.vm) return c.cls == 1 ? r.fill : r.outl;
     if (p.bars_outline_width > 0.0f && d <= c.v) return r.outl;
-    return 0u;
+    return bg;
 }
 GLB_HD uint32_t bars_px(const glava_b200_params& p, const AudioTex& t, int x, int y) {
     float fx = (float) x + 0.5f, fy = (float) y + 0.5f;
     int   aw = p.bars_mirror_yx ? p.h : p.w, ah = p.bars_mirror_yx ? p.w : p.h;
     float ax = p.bars_mirror_yx ? fy : fx,  ay = p.bars_mirror_yx ? fx : fy;
     float d = p.bars_flip ? (float) ah - ay : ay;
+    if (!p.premultiply_alpha) return bars_combine(p, bars_column(p, t, ax, aw), bars_row_t<false>(p, d), d, stage_bg<false>(p));
     return bars_combine(p, bars_column(p, t, ax, aw), bars_row(p, d), d);
 }
 
@@ -197,8 +215,8 @@ struct RadialGeo {
     int      bar;      // -1: not on a bar; else (side << 16) | k with side 0 = audio_l, 1 = audio_r, pos = k / (NBARS/2)
 };
 GLB_HD uint32_t radial_finish(const glava_b200_params& p, f4 frag) {
-    uint32_t px = pack8(frag);
-    return p.premultiply_alpha ? premultiply8(px) : px;                    // radial/2.frag
+    if (!p.premultiply_alpha) return blend_store(p, frag);                 // stage 1 blended, radial/2.frag skipped
+    return premultiply8(pack8(frag));                                      // radial/2.frag
 }
 GLB_HD RadialGeo radial_geometry(const glava_b200_params& p, int x, int y) {
     RadialGeo g = { 0u, 0u, 0.0f, -1 };
@@ -231,7 +249,7 @@ GLB_HD RadialGeo radial_geometry(const glava_b200_params& p, int x, int y) {
         }
     }
     // neither ring nor lit bar: apply_frag(0, 0) = 0 and stage 2 keeps 0 — skip the arithmetic
-    if (frag.r == 0.0f && frag.g == 0.0f && frag.b == 0.0f && frag.a == 0.0f) g.unlit = 0u;
+    if (p.premultiply_alpha && frag.r == 0.0f && frag.g == 0.0f && frag.b == 0.0f && frag.a == 0.0f) g.unlit = 0u;
     else g.unlit = radial_finish(p, apply_frag(frag, mk4(0, 0, 0, 0)));
     return g;
 }
@@ -264,7 +282,7 @@ GLB_HD float circle_apply_smooth(const glava_b200_params& p, const AudioTex& t, 
     return v;
 }
 // stage 1, pixel_center_integer (circle/1.frag:1,51-84): returns the RGBA8 value of the stage surface
-GLB_HD uint32_t circle_stage1(const glava_b200_params& p, const AudioTex& t, int x, int y) {
+template <bool NATIVE> GLB_HD uint32_t circle_stage1_t(const glava_b200_params& p, const AudioTex& t, int x, int y) {
     if (x < 0 || y < 0 || x >= p.w || y >= p.h) return 0u;                 // texelFetch outside the surface
     float dx = (float) x - (float) (p.w / 2), dy = (float) y - (float) (p.h / 2);
     float theta = glm_atan2(dy, dx);
@@ -280,10 +298,11 @@ GLB_HD uint32_t circle_stage1(const glava_b200_params& p, const AudioTex& t, int
         float dmax = g_max(adj0, adj1), dmin = g_min(adj0, adj1);
         d -= v;
         bool in = p.circle_fill ? (d < hl) : ((d > -hl && d < hl) || (d <= dmax && d >= dmin));
-        if (in) return pack8(mk4a(p.circle_outline));
+        if (in) return stage_store<NATIVE>(p, mk4a(p.circle_outline));
     }
-    return 0u;
+    return stage_bg<NATIVE>(p);
 }
+GLB_HD uint32_t circle_stage1(const glava_b200_params& p, const AudioTex& t, int x, int y) { return circle_stage1_t<true>(p, t, x, y); }
 // The audio-independent part of circle/1.frag for one pixel (valid when the textures are pre-smoothed,
 // i.e. smooth_audio() is a single texelFetch): d - C_RADIUS and, for the three angles theta,
 // theta +- adv, which texel of which channel apply_smooth() fetches.  Cached per renderer by
@@ -371,17 +390,25 @@ GLB_HD uint32_t circle_finish(const glava_b200_params& p, uint32_t own, const ui
 GLB_HD float circle_reach(const glava_b200_params& p) {
     return p.circle_radius + fabsf(p.circle_amplify) + fabsf(p.circle_line) + 3.0f;
 }
-GLB_HD uint32_t circle_px(const glava_b200_params& p, const AudioTex& t, int x, int y) {
+// non-native: stage 2 (when C_SMOOTH) is blended like stage 1, stage 3 (premultiply) is skipped
+GLB_HD uint32_t circle_finish_blend(const glava_b200_params& p, uint32_t own, const uint32_t nb[6]) {
+    if (!p.circle_smooth) return own;                                      // circle/2.frag disabled: stage 1 is the frame
+    return blend_store(p, (own >> 24) == 0u ? neigh_avg(nb) : unpack8(own));
+}
+template <bool NATIVE> GLB_HD uint32_t circle_px_t(const glava_b200_params& p, const AudioTex& t, int x, int y) {
     uint32_t nb[6] = { 0, 0, 0, 0, 0, 0 };
-    uint32_t own = circle_stage1(p, t, x, y);
+    uint32_t own = circle_stage1_t<NATIVE>(p, t, x, y);
     if (p.circle_smooth && (own >> 24) == 0u) {
-        nb[0] = circle_stage1(p, t, x + 1, y);     nb[1] = circle_stage1(p, t, x + 1, y + 1);
+        nb[0] = circle_stage1_t<NATIVE>(p, t, x + 1, y);     nb[1] = circle_stage1_t<NATIVE>(p, t, x + 1, y + 1);
         // circle/2.frag: half-integer gl_FragCoord, ivec2(x + 0.5 - 1) = 0 at x = 0 (see graph_px_cols)
         const int xm = x > 0 ? x - 1 : x, ym = y > 0 ? y - 1 : y;
-        nb[2] = circle_stage1(p, t, x, y + 1);     nb[3] = circle_stage1(p, t, xm, y);
-        nb[4] = circle_stage1(p, t, xm, ym);       nb[5] = circle_stage1(p, t, x, ym);
+        nb[2] = circle_stage1_t<NATIVE>(p, t, x, y + 1);     nb[3] = circle_stage1_t<NATIVE>(p, t, xm, y);
+        nb[4] = circle_stage1_t<NATIVE>(p, t, xm, ym);       nb[5] = circle_stage1_t<NATIVE>(p, t, x, ym);
     }
-    return circle_finish(p, own, nb);
+    return NATIVE ? circle_finish(p, own, nb) : circle_finish_blend(p, own, nb);
+}
+GLB_HD uint32_t circle_px(const glava_b200_params& p, const AudioTex& t, int x, int y) {
+    return p.premultiply_alpha ? circle_px_t<true>(p, t, x, y) : circle_px_t<false>(p, t, x, y);
 }
 
 // ================================= graph (graph/1.frag, 2.frag) ==================================
@@ -408,10 +435,13 @@ GLB_HD float graph_height(const glava_b200_params& p, const AudioTex& t, int x) 
     return s;
 }
 GLB_HD float graph_d(const glava_b200_params& p, int y) { return p.graph_invert > 0 ? (float) p.h - (float) y : (float) y; }
-GLB_HD uint32_t graph_row(const glava_b200_params& p, int y) { return pack8(eval_color(p.graph_color, p.graph_color_prog, graph_d(p, y))); }
-// stage-1 surface value at (x, y) given the column height s and the row colour
-GLB_HD uint32_t graph_stage1(const glava_b200_params& p, float s, uint32_t rowcol, int y) {
-    return (graph_d(p, y) + 1.5f <= s) ? rowcol : 0u;                       // graph/1.frag:116
+template <bool NATIVE> GLB_HD uint32_t graph_row_t(const glava_b200_params& p, int y) {
+    return stage_store<NATIVE>(p, eval_color(p.graph_color, p.graph_color_prog, graph_d(p, y)));
+}
+GLB_HD uint32_t graph_row(const glava_b200_params& p, int y) { return graph_row_t<true>(p, y); }
+// stage-1 surface value at (x, y) given the column height s and the row colour (bg: what `fragment = vec4(0)` stores)
+GLB_HD uint32_t graph_stage1(const glava_b200_params& p, float s, uint32_t rowcol, int y, uint32_t bg = 0u) {
+    return (graph_d(p, y) + 1.5f <= s) ? rowcol : bg;                       // graph/1.frag:116
 }
 GLB_HD uint32_t graph_finish(const glava_b200_params& p, uint32_t own, const uint32_t nb[6]) {   // graph/2.frag:19-44
     if (!(p.graph_draw_outline || p.graph_draw_highlight)) return own;
@@ -425,28 +455,49 @@ GLB_HD uint32_t graph_finish(const glava_b200_params& p, uint32_t own, const uin
     }
     return own;
 }
+// non-native: stage 2's result is blended over the clear colour like stage 1's
+GLB_HD uint32_t graph_finish_blend(const glava_b200_params& p, uint32_t own, const uint32_t nb[6]) {
+    if (!(p.graph_draw_outline || p.graph_draw_highlight)) return own;     // graph/2.frag disabled
+    f4 f = unpack8(own);
+    const float avg_a = neigh_avg_alpha(nb);
+    if (avg_a > 0.0f) {
+        if (f.a <= 0.0f) { if (p.graph_draw_outline) f = mk4a(p.graph_outline); }
+        else if (avg_a < 1.0f) {
+            if (p.graph_draw_highlight) { const float k = avg_a * 2.0f; f = mk4(f.r * k, f.g * k, f.b * k, f.a); }
+        }
+    }
+    return blend_store(p, f);
+}
 // generic per-pixel: s3 = heights of columns x-1, x, x+1 (out-of-surface columns: any value, masked here)
-GLB_HD uint32_t graph_px_cols(const glava_b200_params& p, const float s3[3], const uint32_t row3[3], int x, int y) {
+template <bool NATIVE> GLB_HD uint32_t graph_px_cols_t(const glava_b200_params& p, const float s3[3], const uint32_t row3[3], int x, int y) {
     // row3 = row colours of y-1, y, y+1
     // graph/2.frag addresses its taps as ivec2(gl_FragCoord.x - 1, gl_FragCoord.y - 1) with the DEFAULT half-integer
     // gl_FragCoord (stage 2 does not declare pixel_center_integer): at x = 0 that is int(-0.5) = 0 — float -> int drops
     // the fraction (GLSL 3.30 5.4.1) — so the "x - 1" / "y - 1" taps of column 0 / row 0 read column 0 / row 0
     // themselves; only the "+ 1" taps can leave the surface.
+    const uint32_t bg = stage_bg<NATIVE>(p);
     bool xr = x + 1 < p.w, yu = y + 1 < p.h;
     const int cl = x > 0 ? 0 : 1, rd = y > 0 ? 0 : 1;                       // s3 / row3 slot of the "- 1" taps
     const int ym = y > 0 ? y - 1 : y;
-    uint32_t own = graph_stage1(p, s3[1], row3[1], y);
+    uint32_t own = graph_stage1(p, s3[1], row3[1], y, bg);
     uint32_t nb[6];
-    nb[0] = xr ? graph_stage1(p, s3[2], row3[1], y) : 0u;
-    nb[1] = (xr && yu) ? graph_stage1(p, s3[2], row3[2], y + 1) : 0u;
-    nb[2] = yu ? graph_stage1(p, s3[1], row3[2], y + 1) : 0u;
-    nb[3] = graph_stage1(p, s3[cl], row3[1], y);
-    nb[4] = graph_stage1(p, s3[cl], row3[rd], ym);
-    nb[5] = graph_stage1(p, s3[1], row3[rd], ym);
-    return graph_finish(p, own, nb);
+    nb[0] = xr ? graph_stage1(p, s3[2], row3[1], y, bg) : 0u;
+    nb[1] = (xr && yu) ? graph_stage1(p, s3[2], row3[2], y + 1, bg) : 0u;
+    nb[2] = yu ? graph_stage1(p, s3[1], row3[2], y + 1, bg) : 0u;
+    nb[3] = graph_stage1(p, s3[cl], row3[1], y, bg);
+    nb[4] = graph_stage1(p, s3[cl], row3[rd], ym, bg);
+    nb[5] = graph_stage1(p, s3[1], row3[rd], ym, bg);
+    return NATIVE ? graph_finish(p, own, nb) : graph_finish_blend(p, own, nb);
+}
+GLB_HD uint32_t graph_px_cols(const glava_b200_params& p, const float s3[3], const uint32_t row3[3], int x, int y) {
+    return graph_px_cols_t<true>(p, s3, row3, x, y);
 }
 GLB_HD uint32_t graph_px(const glava_b200_params& p, const AudioTex& t, int x, int y) {
     float s3[3] = { x > 0 ? graph_height(p, t, x - 1) : 0.0f, graph_height(p, t, x), x + 1 < p.w ? graph_height(p, t, x + 1) : 0.0f };
+    if (!p.premultiply_alpha) {
+        uint32_t rowb[3] = { y > 0 ? graph_row_t<false>(p, y - 1) : 0u, graph_row_t<false>(p, y), y + 1 < p.h ? graph_row_t<false>(p, y + 1) : 0u };
+        return graph_px_cols_t<false>(p, s3, rowb, x, y);
+    }
     uint32_t row3[3] = { y > 0 ? graph_row(p, y - 1) : 0u, graph_row(p, y), y + 1 < p.h ? graph_row(p, y + 1) : 0u };
     return graph_px_cols(p, s3, row3, x, y);
 }
@@ -474,28 +525,44 @@ GLB_HD WaveCol wave_column(const glava_b200_params& p, const AudioTex& t, int x)
     c.color = pack8(mk4(p.wave_base_color[0] + k, p.wave_base_color[1] + k, p.wave_base_color[2] + k, p.wave_base_color[3] + k));
     return c;
 }
-GLB_HD uint32_t wave_stage1(const WaveCol& c, int y) {                      // wave/1.frag:32-38
+GLB_HD uint32_t wave_stage1(const WaveCol& c, int y, uint32_t bg = 0u) {     // wave/1.frag:32-38
     float diff = (float) y - c.s;
-    return (fabsf(diff) < c.thick || (diff <= c.dmax && diff >= c.dmin)) ? c.color : 0u;
+    return (fabsf(diff) < c.thick || (diff <= c.dmax && diff >= c.dmin)) ? c.color : bg;
 }
 // c3 = columns x-1, x, x+1
-GLB_HD uint32_t wave_px_cols(const glava_b200_params& p, const WaveCol c3[3], int x, int y) {   // wave/2.frag:14-33
+template <bool NATIVE> GLB_HD uint32_t wave_px_cols_t(const glava_b200_params& p, const WaveCol c3[3], int x, int y) {   // wave/2.frag:14-33
+    const uint32_t bg = stage_bg<NATIVE>(p);
     bool xl = x - 1 >= 0, xr = x + 1 < p.w, yd = y - 1 >= 0, yu = y + 1 < p.h;
-    uint32_t own = wave_stage1(c3[1], y);
+    uint32_t own = wave_stage1(c3[1], y, bg);
     uint32_t nb[6];
-    nb[0] = xr ? wave_stage1(c3[2], y) : 0u;
-    nb[1] = (xr && yu) ? wave_stage1(c3[2], y + 1) : 0u;
-    nb[2] = yu ? wave_stage1(c3[1], y + 1) : 0u;
-    nb[3] = xl ? wave_stage1(c3[0], y) : 0u;
-    nb[4] = (xl && yd) ? wave_stage1(c3[0], y - 1) : 0u;
-    nb[5] = yd ? wave_stage1(c3[1], y - 1) : 0u;
+    nb[0] = xr ? wave_stage1(c3[2], y, bg) : 0u;
+    nb[1] = (xr && yu) ? wave_stage1(c3[2], y + 1, bg) : 0u;
+    nb[2] = yu ? wave_stage1(c3[1], y + 1, bg) : 0u;
+    nb[3] = xl ? wave_stage1(c3[0], y, bg) : 0u;
+    nb[4] = (xl && yd) ? wave_stage1(c3[0], y - 1, bg) : 0u;
+    nb[5] = yd ? wave_stage1(c3[1], y - 1, bg) : 0u;
     if (neigh_avg_alpha(nb) > 0.0f) {
-        if ((own >> 24) == 0u || x == 0 || x == p.w - 1) return pack8(mk4a(p.wave_outline));
+        if ((own >> 24) == 0u || x == 0 || x == p.w - 1) return stage_store<NATIVE>(p, mk4a(p.wave_outline));
     }
-    return own;
+    return NATIVE ? own : blend_store(p, unpack8(own));                    // stage 2 is drawn (and blended) for every pixel
+}
+GLB_HD uint32_t wave_px_cols(const glava_b200_params& p, const WaveCol c3[3], int x, int y) { return wave_px_cols_t<true>(p, c3, x, y); }
+// non-native: the column's stage-1 colour goes through the blend before it is stored
+GLB_HD WaveCol wave_column_blend(const glava_b200_params& p, const AudioTex& t, int x) {
+    WaveCol c = wave_column(p, t, x);
+    const float H = (float) p.h;
+    const float k = (fabsf((H * 0.5f) - c.s) * 0.02f);
+    c.color = blend_store(p, mk4(p.wave_base_color[0] + k, p.wave_base_color[1] + k, p.wave_base_color[2] + k, p.wave_base_color[3] + k));
+    return c;
 }
 GLB_HD uint32_t wave_px(const glava_b200_params& p, const AudioTex& t, int x, int y) {
     WaveCol c3[3];
+    if (!p.premultiply_alpha) {
+        c3[1] = wave_column_blend(p, t, x);
+        c3[0] = x > 0 ? wave_column_blend(p, t, x - 1) : c3[1];
+        c3[2] = x + 1 < p.w ? wave_column_blend(p, t, x + 1) : c3[1];
+        return wave_px_cols_t<false>(p, c3, x, y);
+    }
     c3[1] = wave_column(p, t, x);
     c3[0] = x > 0 ? wave_column(p, t, x - 1) : c3[1];
     c3[2] = x + 1 < p.w ? wave_column(p, t, x + 1) : c3[1];
@@ -504,9 +571,11 @@ GLB_HD uint32_t wave_px(const glava_b200_params& p, const AudioTex& t, int x, in
 
 // ================================= test (test/1.frag:32, 2.frag, 3.frag) ==========================
 GLB_HD uint32_t test_px(const glava_b200_params& p) {
+    if (!p.premultiply_alpha)                                               // stages 1 and 2 blended, test/3.frag skipped
+        return blend_store(p, unpack8(blend_store(p, mk4(1.0f, 0.0f, 0.0f, (float) 1 / (float) 3))));
     uint32_t px = pack8(mk4(1.0f, 0.0f, 0.0f, (float) 1 / (float) 3));
     px = pack8(unpack8(px));                                                // test/2.frag passthrough
-    return p.premultiply_alpha ? premultiply8(px) : px;                     // test/3.frag
+    return premultiply8(px);                                                // test/3.frag
 }
 
 // generic per-pixel dispatcher

@@ -39,9 +39,11 @@ raster_generic_kernel(const __grid_constant__ RasterArgs a, const __grid_constan
     if (x >= p.w) return;
     const int y0 = blockIdx.y * rows_per_cta, y1 = min(p.h, y0 + rows_per_cta);
     // polar modules: everything outside a disc around the centre is exactly 0
+    // (native opacity only: with blending the far field is the blended clear colour, evaluated per pixel)
     float reach = -1.0f, cx = 0.0f, cy = 0.0f;
-    if (p.module == GLAVA_B200_MOD_RADIAL) { reach = radial_reach(p); cx = (float) (p.w / 2) - p.radial_off_x; cy = (float) (p.h / 2) - p.radial_off_y; }
-    if (p.module == GLAVA_B200_MOD_CIRCLE) { reach = circle_reach(p); cx = (float) (p.w / 2); cy = (float) (p.h / 2); }
+    if (!p.premultiply_alpha) { }
+    else if (p.module == GLAVA_B200_MOD_RADIAL) { reach = radial_reach(p); cx = (float) (p.w / 2) - p.radial_off_x; cy = (float) (p.h / 2) - p.radial_off_y; }
+    else if (p.module == GLAVA_B200_MOD_CIRCLE) { reach = circle_reach(p); cx = (float) (p.w / 2); cy = (float) (p.h / 2); }
     for (int y = y0; y < y1; ++y) {
         uint32_t px[4] = { 0u, 0u, 0u, 0u };
         bool live = true;
@@ -611,10 +613,13 @@ static int pick_block_x(int quads) {       // threads per row-segment: prefer an
 int launch_raster(const glava_b200_params& p, const RasterArgs& a, void* stream) {
     cudaStream_t st = (cudaStream_t) stream;
     const int quads = (p.w + 3) / 4;
-    const bool fast_bars  = p.module == GLAVA_B200_MOD_BARS && !p.bars_mirror_yx && a.rowtab && (p.w & 3) == 0;
-    const bool fast_graph = p.module == GLAVA_B200_MOD_GRAPH && a.rowtab;
-    const bool fast_wave  = p.module == GLAVA_B200_MOD_WAVE;
-    const bool geo_radial = p.module == GLAVA_B200_MOD_RADIAL && a.geo && p.radial_nbars <= RADIAL_MAX_BARS;
+    // The specialised kernels assume native opacity (a fragment left at vec4(0) stores 0, whole zero rows / discs are skipped);
+    // with GL blending (premultiply_alpha == 0) every stage output is blended over the clear colour: generic kernel.
+    const bool native = p.premultiply_alpha != 0;
+    const bool fast_bars  = native && p.module == GLAVA_B200_MOD_BARS && !p.bars_mirror_yx && a.rowtab && (p.w & 3) == 0;
+    const bool fast_graph = native && p.module == GLAVA_B200_MOD_GRAPH && a.rowtab;
+    const bool fast_wave  = native && p.module == GLAVA_B200_MOD_WAVE;
+    const bool geo_radial = native && p.module == GLAVA_B200_MOD_RADIAL && a.geo && p.radial_nbars <= RADIAL_MAX_BARS;
     int bx = (fast_bars || fast_graph || fast_wave) ? pick_block_x(quads) : 128;
     if (bx > 256) bx = 256;
     // rows per CTA, measured on B200: bars 135 >= 270 > 540 (with the spectrum kernel co-running);
@@ -636,10 +641,9 @@ int launch_raster(const glava_b200_params& p, const RasterArgs& a, void* stream)
         if (fast_bars) raster_bars_kernel<<<grid, bx, 0, st>>>(b, p, rows);
         else if (fast_graph) raster_graph_kernel<<<grid, bx, 0, st>>>(b, p, rows);
         else if (fast_wave) raster_wave_kernel<<<grid, bx, 0, st>>>(b, p, rows);
-        else if (p.module == GLAVA_B200_MOD_RADIAL && a.geo && p.radial_nbars <= RADIAL_MAX_BARS)
-            raster_radial_geo_kernel<<<grid, bx, 0, st>>>(b, p, rows);
-        else if (p.module == GLAVA_B200_MOD_RADIAL) raster_radial_kernel<<<grid, bx, 0, st>>>(b, p, rows);
-        else if (p.module == GLAVA_B200_MOD_CIRCLE) {
+        else if (geo_radial) raster_radial_geo_kernel<<<grid, bx, 0, st>>>(b, p, rows);
+        else if (native && p.module == GLAVA_B200_MOD_RADIAL) raster_radial_kernel<<<grid, bx, 0, st>>>(b, p, rows);
+        else if (native && p.module == GLAVA_B200_MOD_CIRCLE) {
             int tiles = 16;                                   // 128 rows per CTA
             if (const char* e = getenv("GLAVA_B200_CIRCLE_TILES")) { int v = atoi(e); if (v > 0) tiles = v; }
             const int ntile_y = (p.h + CIRCLE_TH - 1) / CIRCLE_TH;

@@ -89,7 +89,7 @@ typedef struct {
     int   module;             /* GLAVA_B200_MOD_* */
     int   w, h;               /* setgeometry w h (rc.glsl:52) */
     int   channels;           /* _CHANNELS: setmirror ? 1 : 2 (render.c:290) */
-    int   premultiply_alpha;  /* setopacity "native" (render.c:1036-1040) */
+    int   premultiply_alpha;  /* setopacity "native" (render.c:1036-1040); 0: per-stage GL blending over clear_color */
     /* bars.glsl */
     float bars_width, bars_gap, bars_outline_width, bars_amplify;
     glava_b200_color bars_color;
@@ -136,6 +136,10 @@ typedef struct {
     float smooth_ratio;       /* setsmoothratio  (render.c:918,1204) */
     /* compiled colour expressions (mode 2 of the colour they belong to; n_ops == 0 otherwise) */
     glava_b200_color_prog bars_color_prog, bars_outline_prog, radial_color_prog, graph_color_prog;
+    /* setbg / setbgf (render.c:1062-1099; rc.glsl:56 `setbg 00000000`): the glClear colour.  Native opacity never shows
+     * it (blending is off and every stage writes every pixel); with premultiply_alpha == 0 (setopacity "none" / "xroot")
+     * every module stage is blended over it with SRC_ALPHA / ONE_MINUS_SRC_ALPHA (render.c:1467-1470) */
+    float clear_color[4];
 } glava_b200_params;
 
 typedef struct glava_b200 glava_b200;    /* plays the role of struct glava_renderer (render.h:8-30) */

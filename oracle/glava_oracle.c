@@ -693,14 +693,27 @@ static vec4 wave_px(const rctx* c, int x, int y) {                       /* wave
     return v4(0, 0, 0, 0);
 }
 
+/* What a stage's `fragment` becomes in its RGBA8 target.  setopacity "native": blending is off (render.c:1467-1470), plain
+ * unorm8 conversion.  Any other opacity: GL_BLEND with glBlendFunc(GL_SRC_ALPHA, GL_ONE_MINUS_SRC_ALPHA) over the target
+ * glClear'd to the `setbg` colour (render.c:1700, 2028) — fixed-function blending restated in float32: source clamped to
+ * [0, 1], destination read back from the 8-bit target, C = Cs * As + Cd * (1 - As) on all four channels. */
+static inline float clamp01(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
+static uint32_t store8(const orc_params* p, vec4 s) {
+    if (p->premultiply_alpha) return pack8(s);
+    s = v4(clamp01(s.r), clamp01(s.g), clamp01(s.b), clamp01(s.a));
+    vec4 d = unpack8(pack8(v4a(p->clear_color)));
+    float k = 1.0f - s.a;
+    return pack8(v4((s.r * s.a) + (d.r * k), (s.g * s.a) + (d.g * k), (s.b * s.a) + (d.b * k), (s.a * s.a) + (d.a * k)));
+}
+
 static uint32_t stage1(const rctx* c, int x, int y) {
     switch (c->p->module) {
-        case ORC_MOD_BARS:   return pack8(bars_px(c, x, y));
-        case ORC_MOD_RADIAL: return pack8(radial_px(c, x, y));
-        case ORC_MOD_CIRCLE: return pack8(circle_px(c, x, y));
-        case ORC_MOD_GRAPH:  return pack8(graph_px(c, x, y));
-        case ORC_MOD_WAVE:   return pack8(wave_px(c, x, y));
-        default:             return pack8(v4(1.0f, 0.0f, 0.0f, (float) 1 / (float) 3));   /* test/1.frag:32 */
+        case ORC_MOD_BARS:   return store8(c->p, bars_px(c, x, y));
+        case ORC_MOD_RADIAL: return store8(c->p, radial_px(c, x, y));
+        case ORC_MOD_CIRCLE: return store8(c->p, circle_px(c, x, y));
+        case ORC_MOD_GRAPH:  return store8(c->p, graph_px(c, x, y));
+        case ORC_MOD_WAVE:   return store8(c->p, wave_px(c, x, y));
+        default:             return store8(c->p, v4(1.0f, 0.0f, 0.0f, (float) 1 / (float) 3));   /* test/1.frag:32 */
     }
 }
 
@@ -759,7 +772,7 @@ void orc_raster_rows(const orc_params* p, const uint16_t* tl, const uint16_t* tr
                     if (p->circle_smooth) {                                 /* circle/2.frag:14-32 */
                         vec4 avg = neigh_avg(&S, x, y, 1);
                         if (f.a == 0.0f) f = avg;
-                        px = pack8(f); f = unpack8(px);
+                        px = store8(p, f); f = unpack8(px);
                     }
                     if (p->premultiply_alpha) px = pack8(premultiply(f));   /* circle/3.frag */
                     break;
@@ -774,7 +787,7 @@ void orc_raster_rows(const orc_params* p, const uint16_t* tl, const uint16_t* tr
                                 if (p->graph_draw_highlight) { float k = avg.a * 2.0f; f.r *= k; f.g *= k; f.b *= k; }
                             }
                         }
-                        px = pack8(f);
+                        px = store8(p, f);
                     }
                     break;                                                  /* graph/3,4.frag disabled (ANTI_ALIAS 0) */
                 }
@@ -784,11 +797,11 @@ void orc_raster_rows(const orc_params* p, const uint16_t* tl, const uint16_t* tr
                     if (avg.a > 0.0f) {
                         if (f.a <= 0.0f || x == 0 || x == w - 1) f = v4a(p->wave_outline);
                     }
-                    px = pack8(f);
+                    px = store8(p, f);
                     break;
                 }
                 default: {                                                  /* test/2.frag, test/3.frag */
-                    px = pack8(unpack8(px));
+                    px = store8(p, unpack8(px));
                     if (p->premultiply_alpha) px = pack8(premultiply(unpack8(px)));
                     break;
                 }

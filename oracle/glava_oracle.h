@@ -67,6 +67,7 @@ typedef struct {
     int   graph_draw_outline, graph_draw_highlight; float graph_outline[4]; int graph_invert;
     /* ---- wave ---- */
     float wave_min_thickness, wave_max_thickness, wave_base_color[4], wave_amplify, wave_outline[4];
+    float clear_color[4];            /* setbg / setbgf (render.c:1062-1099); only visible when premultiply_alpha == 0 */
 } orc_params;
 
 void orc_default_params(orc_params* p, int module, int n, int w, int h);

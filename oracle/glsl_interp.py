@@ -916,8 +916,14 @@ def load_stage(path, root, overrides=None, config_dir=None, **hdr):
 class ModuleProgram:
     """the stage chain of one module (render.c stage loading: 1.frag, 2.frag, ... until a file is missing)"""
 
-    def __init__(self, root, module, w, h, tex_l, tex_r, overrides=None, config_dir=None, **hdr):
+    def __init__(self, root, module, w, h, tex_l, tex_r, overrides=None, config_dir=None, clear_color=(0.0, 0.0, 0.0, 0.0), **hdr):
         self.w, self.h = w, h
+        # setopacity other than "native" (premultiply_alpha = 0): every stage is drawn with GL_BLEND enabled,
+        # glBlendFunc(GL_SRC_ALPHA, GL_ONE_MINUS_SRC_ALPHA), over the target glClear'd to `setbg` (render.c:1467-1470,
+        # 1700, 2028).  Fixed-function blending restated in float32: fragment clamped to [0, 1], destination read back from
+        # the RGBA8 target, every operation individually rounded.
+        self.blend = hdr.get("premultiply_alpha", 1) == 0
+        self.clear8 = tuple(unorm8(F32(c)) for c in clear_color)
         self.stages = []
         k = 1
         while os.path.exists(os.path.join(root, module, "%d.frag" % k)):
@@ -939,7 +945,14 @@ class ModuleProgram:
             if k > 0:
                 u["tex"] = Sampler2D(self.w, self.h, lambda px, py: self.stage_pixel(k - 1, px, py))
             g = self.stages[k].run(u, x, y)
-            c[key] = tuple(unorm8(v) for v in g["fragment"].v)
+            frag = [to_float(v) for v in g["fragment"].v]
+            if self.blend:
+                src = [min(max(v, F32(0.0)), F32(1.0)) for v in frag]
+                dst = [F32(F32(d) / F32(255.0)) for d in self.clear8]
+                a = src[3]
+                k1 = F32(F32(1.0) - a)
+                frag = [F32(F32(src[i] * a) + F32(dst[i] * k1)) for i in range(4)]
+            c[key] = tuple(unorm8(v) for v in frag)
         return c[key]
 
     def pixel(self, x, y):

@@ -42,6 +42,7 @@ class OrcParams(C.Structure):
         ("graph_invert", C.c_int),
         ("wave_min_thickness", C.c_float), ("wave_max_thickness", C.c_float), ("wave_base_color", C.c_float * 4),
         ("wave_amplify", C.c_float), ("wave_outline", C.c_float * 4),
+        ("clear_color", C.c_float * 4),
     ]
 
 
@@ -127,6 +128,8 @@ class Oracle:
         p = OrcParams()
         self.L.orc_default_params(C.byref(p), MODULES.index(module), n, w, h)
         for k, v in over.items():
+            if isinstance(v, (list, tuple)):
+                v = type(getattr(p, k))(*v)
             setattr(p, k, v)
         return p
 

@@ -64,8 +64,24 @@ CASES = [
     ("circle_odd", "circle", {"C_RADIUS": "12", "AMPLIFY": "20"}, dict(circle_radius=12.0, circle_amplify=20.0), {}, (93, 51)),
     ("graph_odd", "graph", {"VSCALE": "40"}, dict(graph_vscale=40.0), {}, (95, 53)),
     ("wave_odd", "wave", {"AMPLIFY": "40"}, dict(wave_amplify=40.0), {}, (95, 53)),
+    # setopacity "none": every stage blended (SRC_ALPHA, ONE_MINUS_SRC_ALPHA) over the glClear colour, premultiply stages skipped
     ("radial_nopremult", "radial", {"C_RADIUS": "12", "AMPLIFY": "30", "NBARS": "40"},
      dict(radial_radius=12.0, radial_amplify=30.0, radial_nbars=40, premultiply_alpha=0), {"premultiply_alpha": 0}),
+    ("radial_blend", "radial", {"C_RADIUS": "12", "AMPLIFY": "30", "NBARS": "40"},
+     dict(radial_radius=12.0, radial_amplify=30.0, radial_nbars=40, premultiply_alpha=0, clear_color=[0.1, 0.3, 0.2, 0.6]),
+     {"premultiply_alpha": 0, "clear_color": (0.1, 0.3, 0.2, 0.6)}),
+    ("bars_blend", "bars", {"AMPLIFY": "40"}, dict(bars_amplify=40.0, premultiply_alpha=0, clear_color=[0.2, 0.4, 0.6, 0.5]),
+     {"premultiply_alpha": 0, "clear_color": (0.2, 0.4, 0.6, 0.5)}),
+    ("circle_blend", "circle", {"C_RADIUS": "12", "AMPLIFY": "20"}, dict(circle_radius=12.0, circle_amplify=20.0, premultiply_alpha=0, clear_color=[0.5, 0.25, 0.75, 0.0]),
+     {"premultiply_alpha": 0, "clear_color": (0.5, 0.25, 0.75, 0.0)}),
+    ("circle_blend_opaque", "circle", {"C_RADIUS": "12", "AMPLIFY": "20"}, dict(circle_radius=12.0, circle_amplify=20.0, premultiply_alpha=0, clear_color=[0.0, 0.0, 0.5, 1.0]),
+     {"premultiply_alpha": 0, "clear_color": (0.0, 0.0, 0.5, 1.0)}),
+    ("graph_blend", "graph", {"VSCALE": "42", "DRAW_OUTLINE": "1", "DRAW_HIGHLIGHT": "1"},
+     dict(graph_vscale=42.0, graph_draw_outline=1, graph_draw_highlight=1, premultiply_alpha=0, clear_color=[0.3, 0.3, 0.3, 0.0]),
+     {"premultiply_alpha": 0, "clear_color": (0.3, 0.3, 0.3, 0.0)}),
+    ("wave_blend", "wave", {"AMPLIFY": "40"}, dict(wave_amplify=40.0, premultiply_alpha=0, clear_color=[0.9, 0.8, 0.1, 0.25]),
+     {"premultiply_alpha": 0, "clear_color": (0.9, 0.8, 0.1, 0.25)}),
+    ("test_blend", "test", {}, dict(premultiply_alpha=0, clear_color=[0.0, 1.0, 0.0, 0.5]), {"premultiply_alpha": 0, "clear_color": (0.0, 1.0, 0.0, 0.5)}),
 ]
 
 

@@ -172,3 +172,16 @@ def test_pipe_binds_resolve_at_macros(tmp_path, built):
         rc = g.lib().glava_b200_load_config_binds(C.byref(pp), None, None, None, None, arr)
         if rc != 0:
             raise g.GlavaError(g.lib().glava_b200_last_error().decode())
+
+
+def test_setbg_and_setbgf(tmp_path, built):
+    """render.c:1062-1099: setbg takes hex digits without '#'; components the string does not reach keep their value"""
+    assert list(g.load_config().clear_color) == [0, 0, 0, 0]
+    p = g.load_config(requests=["setbg ff8000"])
+    assert list(p.clear_color) == [1.0, np.float32(128 / 255), 0.0, 0.0]              # alpha stays at its default 0
+    p = g.load_config(requests=["setbg 0x10203040"])
+    assert np.allclose(list(p.clear_color), [16 / 255, 32 / 255, 48 / 255, 64 / 255], atol=1e-7)
+    p = g.load_config(requests=["setbgf 0.25 0.5 0.75 1.0", 'setopacity "none"'])
+    assert list(p.clear_color) == [0.25, 0.5, 0.75, 1.0] and p.premultiply_alpha == 0
+    with pytest.raises(g.GlavaError, match="Invalid value for `setbg` request: 'zz0000'"):
+        g.load_config(requests=["setbg zz0000"])

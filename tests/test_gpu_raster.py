@@ -50,7 +50,8 @@ def test_bars_options(orc_pm, over, built):
     _check(orc_pm, g.default_params("bars", n=1024, w=320, h=200, **over), batch=2)
 
 
-@pytest.mark.parametrize("module,over", [("radial", dict(radial_invert=1)), ("radial", dict(premultiply_alpha=0)),
+# (non-native opacity — premultiply_alpha = 0, GL blending over the clear colour — is covered by tests/test_zz_gpu_blend.py)
+@pytest.mark.parametrize("module,over", [("radial", dict(radial_invert=1)),
                                          ("radial", dict(radial_off_x=40.0, radial_off_y=-25.0)),
                                          ("circle", dict(circle_fill=1)), ("circle", dict(circle_smooth=0)),
                                          ("circle", dict(circle_invert=1)), ("graph", dict(graph_direction=-1)),

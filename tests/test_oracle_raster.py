@@ -63,16 +63,22 @@ def test_modules_draw_something_and_silence_is_flat(orc, module):
         assert ys.min() >= h // 2 - 4 and ys.max() <= h // 2 + 4        # flat line + outline at mid height
 
 
-def test_premultiply_stage(orc):
-    # radial stage 2 multiplies rgb by alpha of the 8-bit quantised stage 1 (premultiply.frag:12-15)
+def test_premultiply_stage_and_blending_over_transparent_black(orc):
+    # native: radial stage 2 multiplies rgb by the alpha of the 8-bit quantised stage 1 (premultiply.frag:12-15).
+    # setopacity "none" with the default clear colour 00000000: stage 1 is blended SRC_ALPHA / ONE_MINUS_SRC_ALPHA over
+    # transparent black (render.c:1467-1470) — rgb * a as well (from the unquantised fragment), alpha a * a; stage 2 skipped.
     n = 1024
     p = orc.default_params("radial", n=n, w=400, h=400)
     q = orc.default_params("radial", n=n, w=400, h=400, premultiply_alpha=0)
     tl, tr = _tex(n, 7), _tex(n, 8)
     a = orc.raster(p, tl, tr).astype(np.float32); b = orc.raster(q, tl, tr).astype(np.float32)
-    want = np.floor(b[..., :3] / 255 * (b[..., 3:4] / 255) * 255 + 0.5)
-    assert np.abs(a[..., :3] - want).max() <= 1
-    assert np.array_equal(a[..., 3], b[..., 3])
+    assert a.any() and np.abs(a[..., :3] - b[..., :3]).max() <= 1
+    assert np.abs(b[..., 3] - np.floor((a[..., 3] / 255) ** 2 * 255 + 0.5)).max() <= 1
+    # an opaque clear colour shows wherever nothing is drawn, and under translucent fragments
+    q2 = orc.default_params("radial", n=n, w=400, h=400, premultiply_alpha=0, clear_color=[0.0, 0.0, 1.0, 1.0])
+    c = orc.raster(q2, tl, tr)
+    # (alpha uses the same factors: a * a + 1 * (1 - a) dips to 0.75 under half-transparent edge fragments)
+    assert (c[..., 3] >= 191).all() and (c[..., 3] < 255).any() and (c[0, 0] == [0, 0, 255, 255]).all() and (c[..., 0] > 0).any()
 
 
 def test_rows_api_matches_full_frame(orc):

@@ -1,0 +1,54 @@
+"""-m gpu: setopacity other than "native" (premultiply_alpha = 0).  The reference then draws every module stage with
+GL_BLEND, glBlendFunc(GL_SRC_ALPHA, GL_ONE_MINUS_SRC_ALPHA), over the target glClear'd to the `setbg` colour and skips the
+premultiply stages (render.c:1467-1470, 1700, 2028).  Kernels (the generic per-pixel path: launch_raster's rule) against
+frames computed from the reference's shader text with that blend state (tests/golden/glsl_golden.npz, *_blend cases),
+against the oracle, and against the host build of the same arithmetic."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import glava_b200 as g
+from oracle.oracle import params_from
+from tests.conftest import GOLDEN
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+N = 512
+
+
+def _blend_cases():
+    z = np.load(os.path.join(GOLDEN, "glsl_golden.npz"))
+    return [str(c) for c in z["case_names"] if str(c).endswith(("_blend", "_blend_opaque", "_nopremult"))]
+
+
+@pytest.mark.parametrize("case", _blend_cases())
+def test_kernels_blend_every_stage_over_the_clear_colour(orc_pm, case, built):
+    from tests import emul
+    z = np.load(os.path.join(GOLDEN, "glsl_golden.npz"))
+    module = str(z[f"{case}_module"]); w, h = (int(v) for v in z[f"{case}_size"])
+    p = g.default_params(module, n=N, w=w, h=h, **json.loads(str(z[f"{case}_params"])))
+    assert p.premultiply_alpha == 0
+    tl, tr, want = z[f"{case}_tl"], z[f"{case}_tr"], z[f"{case}_frame"]
+    with g.Renderer(p, batch=2) as r:
+        r.raster_textures(np.stack([tl, tr]), np.stack([tr, tl]))
+        got, swapped = r.readback(0), r.readback(1)
+    assert np.array_equal(got, emul.raster(p, tl, tr)) and np.array_equal(swapped, emul.raster(p, tr, tl))
+    assert np.array_equal(got, orc_pm.raster(params_from(p), tl, tr))
+    assert int(np.abs(got.astype(int) - want.astype(int)).max()) <= 1
+    assert (got != want).any(axis=2).sum() <= 0.002 * w * h
+
+
+def test_full_size_non_native_frame(orc_pm, built):
+    """1920x1080 bars over an opaque background: rows spot-checked against the oracle"""
+    p = g.default_params("bars", n=4096, w=1920, h=1080, premultiply_alpha=0, clear_color=[0.05, 0.05, 0.1, 1.0])
+    op = params_from(p)
+    rng = np.random.default_rng(12)
+    tl = orc_pm.smooth_pass(op, (rng.random(4096) ** 2 * 65535).astype(np.uint16))
+    tr = orc_pm.smooth_pass(op, (rng.random(4096) ** 3 * 65535).astype(np.uint16))
+    with g.Renderer(p, batch=1) as r:
+        r.raster_textures(tl[None], tr[None])
+        got = r.readback(0)
+    for y0, y1 in ((0, 4), (100, 104), (298, 304), (1076, 1080)):
+        assert np.array_equal(got[y0:y1], orc_pm.raster(op, tl, tr, rows=(y0, y1))[y0:y1])
+    assert (got[1079, 0] == [13, 13, 26, 255]).all()
