@@ -29,6 +29,7 @@ def lib():
         L.emul_smooth.argtypes = [vp, vp, vp]
         L.emul_raster.argtypes = [vp, vp, vp, vp, i32, i32]
         L.emul_raster_fast.argtypes = [vp, vp, vp, vp]
+        L.emul_eval_color.argtypes = [vp, C.c_float, vp]
         L.emul_lazy_k5.argtypes = [vp, i32, i32, vp, vp, vp]
         L.emul_lazy_epi_n.argtypes = [vp]
         L.emul_k5_table.argtypes = [vp, vp, vp]
@@ -122,4 +123,11 @@ def k5_table(p, tex):
     tex = np.ascontiguousarray(tex, dtype=np.uint16)
     out = np.empty_like(tex)
     lib().emul_k5_table(C.byref(p), tex.ctypes.data, out.ctypes.data)
+    return out
+
+
+def eval_color(prog, x):
+    """a compiled colour expression (glava_b200.api.ColorProg) at X -> float32[4]"""
+    out = np.zeros(4, np.float32)
+    lib().emul_eval_color(C.byref(prog), float(x), out.ctypes.data)
     return out

@@ -162,6 +162,12 @@ void emul_smooth(const glava_b200_params* p, const uint16_t* in, uint16_t* out) 
     for (int x = 0; x < p->n; ++x) out[x] = (uint16_t) smooth_pass_texel(sp, in, p->n, x);
 }
 
+// one compiled colour expression at X (the interpreter the kernels run: raster_core.h eval_color_prog)
+void emul_eval_color(const glava_b200_color_prog* prog, float x, float out[4]) {
+    const f4 r = eval_color_prog(*prog, x);
+    out[0] = r.r; out[1] = r.g; out[2] = r.b; out[3] = r.a;
+}
+
 // per-pixel reference semantics (raster_generic_kernel)
 void emul_raster(const glava_b200_params* pp, const uint16_t* tl, const uint16_t* tr, uint8_t* out, int y0, int y1) {
     const glava_b200_params& p = *pp;

@@ -112,3 +112,88 @@ def test_hand_built_params_are_validated(built):
     p.bars_color.mode = 2                                                # mode 2 without a program
     with pytest.raises(g.GlavaError):
         g.Renderer(p, batch=1)
+
+
+# ---- differential fuzz: random expressions through the config compiler + eval_color_prog vs the GLSL interpreter ---------------
+class _Gen:
+    """random, well-typed GLSL colour expressions over the variable `d`, restricted to operations that are exactly
+    rounded in both implementations (no transcendentals) and to denominators / radicands that stay away from 0"""
+
+    def __init__(self, rng):
+        self.r = rng
+
+    def lit(self):
+        k = self.r.integers(0, 4)
+        if k == 0:
+            return str(int(self.r.integers(1, 9)))                      # int literal
+        if k == 1:
+            return "%.3f" % self.r.uniform(0.05, 4.0)
+        if k == 2:
+            return "%d.%d" % (self.r.integers(0, 3), self.r.integers(1, 10))
+        return "%.2f" % self.r.uniform(0.1, 2.0)
+
+    def scalar(self, depth):
+        if depth <= 0:
+            return "d" if self.r.random() < 0.4 else self.lit()
+        k = self.r.integers(0, 12)
+        a, b = self.scalar(depth - 1), self.scalar(depth - 1)
+        if k == 0: return f"({a} + {b})"
+        if k == 1: return f"({a} - {b})"
+        if k == 2: return f"({a} * {b})"
+        if k == 3: return f"({a} / (abs({b}) + 0.5))"
+        if k == 4: return f"min({self.fl(a)}, {self.fl(b)})"
+        if k == 5: return f"clamp({self.fl(a)}, 0.25, 3)"
+        if k == 6: return f"mix({self.fl(a)}, {self.fl(b)}, 0.375)"
+        if k == 7: return f"{self.r.choice(['floor', 'fract', 'abs', 'ceil', 'sign'])}({self.fl(a)})"
+        if k == 8: return f"sqrt(abs({self.fl(a)}) + 0.125)"
+        if k == 9: return f"{self.vec(int(self.r.integers(2, 5)), depth - 1)}.{self.r.choice(['x', 'g', 'y', 'r'])}"
+        if k == 10: return f"smoothstep(0.5, 2.5, {self.fl(a)})"
+        return f"mod({self.fl(a)}, 1.75)"
+
+    def fl(self, e):
+        """function arguments are given as floats (GLSL 3.30 has no int overloads of these)"""
+        return f"float({e})"
+
+    def vec(self, n, depth):
+        if depth <= 0:
+            if n == 4 and self.r.random() < 0.4:
+                return "#%06x" % int(self.r.integers(0, 1 << 24))
+            return f"vec{n}(" + ", ".join(self.scalar(0) for _ in range(n)) + ")"
+        k = self.r.integers(0, 7)
+        if k == 0: return f"({self.vec(n, depth - 1)} * {self.scalar(depth - 1)})"
+        if k == 1: return f"({self.vec(n, depth - 1)} + {self.vec(n, depth - 1)})"
+        if k == 2: return f"mix({self.vec(n, depth - 1)}, {self.vec(n, depth - 1)}, {self.fl(self.scalar(depth - 1))})"
+        if k == 3 and n >= 3: return f"vec{n}({self.vec(n - 2, depth - 1) if n > 3 else self.scalar(depth - 1)}, {self.vec(2, depth - 1)})"
+        if k == 4: return f"vec{n}({self.fl(self.scalar(depth - 1))})"
+        if k == 5 and n < 4: return f"{self.vec(4, depth - 1)}.{'bgra'[:n] if self.r.random() < 0.5 else 'wzyx'[:n]}"
+        if k == 6: return f"clamp({self.vec(n, depth - 1)}, 0.0, 1.5)"
+        return f"vec{n}(" + ", ".join(self.scalar(depth - 1) for _ in range(n)) + ")"
+
+
+def test_random_expressions_agree_with_the_glsl_interpreter(tmp_path, built):
+    from oracle import glsl_interp as gi
+    from tests import emul
+    rng = np.random.default_rng(20260923)
+    gen = _Gen(rng)
+    xs = [0.0, 0.5, 1.5, 7.25, 31.5, 99.5]
+    checked = 0
+    for i in range(120):
+        expr = gen.vec(4, int(rng.integers(1, 4)))
+        d = tmp_path / f"e{i}"
+        d.mkdir()
+        (d / "rc.glsl").write_text("#request mod bars\n")
+        (d / "bars.glsl").write_text(f"#define COLOR {expr}\n")
+        try:
+            p = g.load_config([str(d)])
+        except g.GlavaError as e:
+            assert "more than 8 live" in str(e) or "longer than 64" in str(e), (expr, str(e))   # resource limits only
+            continue
+        frag = d / "e.frag"
+        frag.write_text("uniform float d;\nout vec4 fragment;\nvoid main() {\n    fragment = %s;\n}\n" % expr)
+        sh = gi.load_stage(str(frag), str(d))
+        for x in xs:
+            want = np.array([float(v) for v in sh.run({"d": gi.F32(x)}, 0, 0)["fragment"].v], np.float32)
+            got = emul.eval_color(p.bars_color_prog, x) if p.bars_color.mode == 2 else np.array(list(p.bars_color.lo), np.float32)
+            assert np.array_equal(got, want), (expr, x, got, want)
+        checked += 1
+    assert checked >= 90
