@@ -56,6 +56,7 @@ class Params(C.Structure):
         ("bars_color_prog", ColorProg), ("bars_outline_prog", ColorProg), ("radial_color_prog", ColorProg),
         ("graph_color_prog", ColorProg),
         ("clear_color", C.c_float * 4),
+        ("radial_bar_width_int", C.c_int), ("radial_bar_outline_width", C.c_float), ("radial_bar_outline", C.c_float * 4),
     ]
 
     def copy(self):

@@ -87,6 +87,7 @@ void fill_defaults(glava_b200_params* p, int module) {
     p->bars_color.mode = 0; hex3(p->bars_color.lo, 0x33, 0x66, 0xb2); hex3(p->bars_color.hi, 0xa0, 0xa0, 0xb2);
     p->bars_color.gradient = 80; p->bars_outline_mode = 0;
     p->radial_radius = 128; p->radial_line = 2; p->radial_line_half = 1; hex3(p->radial_outline, 0x33, 0x33, 0x33);
+    hex3(p->radial_bar_outline, 0x33, 0x33, 0x33); p->radial_bar_outline_width = 0; p->radial_bar_width_int = 0;   // radial.glsl:33-36, BAR_WIDTH 4.5
     p->radial_nbars = 160; p->radial_bar_width = 4.5f; p->radial_amplify = 300;
     p->radial_color.mode = 0; hex3(p->radial_color.lo, 0xcc, 0x33, 0x33); hex3(p->radial_color.hi, 0xcc, 0xa0, 0xa0);
     p->radial_color.gradient = 95; p->radial_rotate = kPI / 2; p->radial_bar_alias = 1.2f; p->radial_c_alias = 1.8f;
@@ -570,15 +571,17 @@ static void apply_defines(glava_b200_params* p, const Defs& d) {
                 p->radial_line_half = n.is_int ? (float) ((long) n.v / 2) : (float) n.v / 2.0f;   // radial/1.frag:52 (C_LINE / 2)
             }
             parse_plain_color(d, "OUTLINE", p->radial_outline);
-            geti(d, "NBARS", &p->radial_nbars); getf(d, "BAR_WIDTH", &p->radial_bar_width);
+            geti(d, "NBARS", &p->radial_nbars);
+            if (eval_num(d, "BAR_WIDTH", &n)) { p->radial_bar_width = (float) n.v; p->radial_bar_width_int = n.is_int ? 1 : 0; }
             getf(d, "AMPLIFY", &p->radial_amplify);
             parse_color_macro(d, "COLOR", &p->radial_color, &p->radial_color_prog, { "d" });
             if (p->radial_color.mode == 0 && eval_num(d, "GRADIENT", &n)) p->radial_color.gradient = (float) n.v;
             getf(d, "ROTATE", &p->radial_rotate); geti(d, "INVERT", &p->radial_invert);
             getf(d, "BAR_ALIAS_FACTOR", &p->radial_bar_alias); getf(d, "C_ALIAS_FACTOR", &p->radial_c_alias);
             getf(d, "CENTER_OFFSET_X", &p->radial_off_x); getf(d, "CENTER_OFFSET_Y", &p->radial_off_y);
-            if (eval_num(d, "BAR_OUTLINE_WIDTH", &n) && n.v > 0)
-                fail(GLAVA_B200_ECONFIG, "radial: BAR_OUTLINE_WIDTH > 0 (deprecated, radial.glsl:33-36) is not supported");
+            getf(d, "BAR_OUTLINE_WIDTH", &p->radial_bar_outline_width);                 // deprecated (radial.glsl:33-36)
+            memcpy(p->radial_bar_outline, p->radial_outline, sizeof(p->radial_bar_outline));   // `#define BAR_OUTLINE OUTLINE`
+            parse_plain_color(d, "BAR_OUTLINE", p->radial_bar_outline);
             break;
         case GLAVA_B200_MOD_CIRCLE:
             getf(d, "C_RADIUS", &p->circle_radius); getf(d, "C_LINE", &p->circle_line);

@@ -209,17 +209,22 @@ GLB_HD f4 apply_frag(f4 f, f4 c) {                                         // ra
 // its two possible final RGBA8 values, the bar it belongs to and its d (= distance - C_RADIUS).
 // raster_radial_kernel caches this per renderer (the same for every stream and frame).
 struct RadialGeo {
-    uint32_t lit;      // final value if the bar reaches this pixel (d <= v)
+    uint32_t lit;      // final value if the bar reaches this pixel (d <= v - BAR_OUTLINE_WIDTH)
     uint32_t unlit;    // final value otherwise (ring or 0)
     float    dR;       // d - C_RADIUS
     int      bar;      // -1: not on a bar; else (side << 16) | k with side 0 = audio_l, 1 = audio_r, pos = k / (NBARS/2)
+    uint32_t band;     // BAR_OUTLINE_WIDTH > 0 only: final value in the bar's end cap, v - BAR_OUTLINE_WIDTH < d <= v
 };
+// `BAR_WIDTH / 2` as radial/1.frag:62,79,88 evaluate it: an integer division when the macro is an integer literal
+GLB_HD float radial_bar_half(const glava_b200_params& p) {
+    return p.radial_bar_width_int ? (float) ((int) p.radial_bar_width / 2) : p.radial_bar_width / 2.0f;
+}
 GLB_HD uint32_t radial_finish(const glava_b200_params& p, f4 frag) {
     if (!p.premultiply_alpha) return blend_store(p, frag);                 // stage 1 blended, radial/2.frag skipped
     return premultiply8(pack8(frag));                                      // radial/2.frag
 }
 GLB_HD RadialGeo radial_geometry(const glava_b200_params& p, int x, int y) {
-    RadialGeo g = { 0u, 0u, 0.0f, -1 };
+    RadialGeo g = { 0u, 0u, 0.0f, -1, 0u };
     f4 frag = mk4(0, 0, 0, 0);
     float dx = ((float) x + 0.5f) - (float) (p.w / 2) + p.radial_off_x,
           dy = ((float) y + 0.5f) - (float) (p.h / 2) + p.radial_off_y;
@@ -235,7 +240,8 @@ GLB_HD RadialGeo radial_geometry(const glava_b200_params& p, int x, int y) {
         const float center = ((GLB_TWOPI / (float) p.radial_nbars) / 2.0f);
         float m = g_mod(theta, section);
         float ym = d * glm_sin(center - m);
-        if (fabsf(ym) < p.radial_bar_width / 2.0f) {
+        const float bw2 = radial_bar_half(p), ow = p.radial_bar_outline_width;
+        if (fabsf(ym) < bw2) {
             float idx = theta + p.radial_rotate;
             float dir = g_mod(fabsf(idx), GLB_TWOPI);
             if (dir > GLB_PI) idx = -g_sign(idx) * (GLB_TWOPI - dir);
@@ -243,9 +249,15 @@ GLB_HD RadialGeo radial_geometry(const glava_b200_params& p, int x, int y) {
             g.bar = ((idx > 0.0f ? 0 : 1) << 16) | (int) (fabsf(idx) / section);
             d -= R;
             g.dR = d;
-            f4 r = eval_color(p.radial_color, p.radial_color_prog, d);
-            r.a *= (((p.radial_bar_width / 2.0f) - fabsf(ym)) * p.radial_bar_alias);
+            // radial/1.frag:85-110: COLOR, or BAR_OUTLINE along the bar's sides and in its end cap when BAR_OUTLINE_WIDTH > 0
+            f4 r = (!(ow > 0.0f) || fabsf(ym) < bw2 - ow) ? eval_color(p.radial_color, p.radial_color_prog, d) : mk4a(p.radial_bar_outline);
+            r.a *= ((bw2 - fabsf(ym)) * p.radial_bar_alias);
             g.lit = radial_finish(p, apply_frag(frag, r));
+            if (ow > 0.0f) {
+                f4 o = mk4a(p.radial_bar_outline);
+                o.a *= ((bw2 - fabsf(ym)) * p.radial_bar_alias);
+                g.band = radial_finish(p, apply_frag(frag, o));
+            }
         }
     }
     // neither ring nor lit bar: apply_frag(0, 0) = 0 and stage 2 keeps 0 — skip the arithmetic
@@ -262,7 +274,10 @@ GLB_HD float radial_bar_value(const glava_b200_params& p, const AudioTex& t, int
 GLB_HD uint32_t radial_px(const glava_b200_params& p, const AudioTex& t, int x, int y) {
     RadialGeo g = radial_geometry(p, x, y);
     if (g.bar < 0) return g.unlit;
-    return (g.dR <= radial_bar_value(p, t, g.bar)) ? g.lit : g.unlit;
+    const float v = radial_bar_value(p, t, g.bar);
+    if (!(p.radial_bar_outline_width > 0.0f)) return (g.dR <= v) ? g.lit : g.unlit;
+    if (g.dR <= v - p.radial_bar_outline_width) return g.lit;
+    return (g.dR <= v) ? g.band : g.unlit;
 }
 // conservative test: can pixel (x, y) be non-zero?  outside this disc radial_px() is exactly 0
 GLB_HD float radial_reach(const glava_b200_params& p) {

@@ -486,7 +486,7 @@ __global__ void polar_geo_kernel(int4* __restrict__ geo, int gx0, int gy0, int g
     const int x = gx0 + bx, y = gy0 + by;
     int4 out;
     if (p.module == GLAVA_B200_MOD_RADIAL) {
-        RadialGeo g = { 0u, 0u, 0.0f, -1 };
+        RadialGeo g = { 0u, 0u, 0.0f, -1, 0u };
         if (x < p.w) g = radial_geometry(p, x, y);
         out = make_int4((int) g.lit, (int) g.unlit, __float_as_int(g.dR), g.bar);
         // compact levels read by raster_radial_geo_kernel: 1-byte class code per pixel
@@ -619,7 +619,8 @@ int launch_raster(const glava_b200_params& p, const RasterArgs& a, void* stream)
     const bool fast_bars  = native && p.module == GLAVA_B200_MOD_BARS && !p.bars_mirror_yx && a.rowtab && (p.w & 3) == 0;
     const bool fast_graph = native && p.module == GLAVA_B200_MOD_GRAPH && a.rowtab;
     const bool fast_wave  = native && p.module == GLAVA_B200_MOD_WAVE;
-    const bool geo_radial = native && p.module == GLAVA_B200_MOD_RADIAL && a.geo && p.radial_nbars <= RADIAL_MAX_BARS;
+    const bool geo_radial = native && p.module == GLAVA_B200_MOD_RADIAL && a.geo && p.radial_nbars <= RADIAL_MAX_BARS
+                            && !(p.radial_bar_outline_width > 0.0f);      // the cache holds two values per pixel, the end cap needs three
     int bx = (fast_bars || fast_graph || fast_wave) ? pick_block_x(quads) : 128;
     if (bx > 256) bx = 256;
     // rows per CTA, measured on B200: bars 135 >= 270 > 540 (with the spectrum kernel co-running);

@@ -140,6 +140,11 @@ typedef struct {
      * it (blending is off and every stage writes every pixel); with premultiply_alpha == 0 (setopacity "none" / "xroot")
      * every module stage is blended over it with SRC_ALPHA / ONE_MINUS_SRC_ALPHA (render.c:1467-1470) */
     float clear_color[4];
+    /* radial.glsl details appended later (kept at the end so earlier offsets stay put) */
+    int   radial_bar_width_int;      /* BAR_WIDTH was written as an integer literal: the shader's `BAR_WIDTH / 2`
+                                        (radial/1.frag:62,79,88) is then an integer division */
+    float radial_bar_outline_width;  /* BAR_OUTLINE_WIDTH (deprecated, radial.glsl:33-36; default 0) */
+    float radial_bar_outline[4];     /* BAR_OUTLINE (default: OUTLINE) */
 } glava_b200_params;
 
 typedef struct glava_b200 glava_b200;    /* plays the role of struct glava_renderer (render.h:8-30) */

@@ -94,6 +94,7 @@ void orc_default_params(orc_params* p, int module, int n, int w, int h) {
     p->bars_color.gradient = 80; p->bars_outline_mode = 0;
     /* radial.glsl */
     p->radial_radius = 128; p->radial_line = 2; p->radial_line_half = 1; hex3(p->radial_outline, 0x33, 0x33, 0x33);
+    hex3(p->radial_bar_outline, 0x33, 0x33, 0x33); p->radial_bar_outline_width = 0; p->radial_bar_width_int = 0;
     p->radial_nbars = 160; p->radial_bar_width = 4.5f; p->radial_amplify = 300;
     p->radial_color.mode = 0; hex3(p->radial_color.lo, 0xcc, 0x33, 0x33); hex3(p->radial_color.hi, 0xcc, 0xa0, 0xa0);
     p->radial_color.gradient = 95; p->radial_rotate = G_PI / 2; p->radial_bar_alias = 1.2f; p->radial_c_alias = 1.8f;
@@ -594,7 +595,10 @@ static vec4 radial_px(const rctx* c, int x, int y) {                     /* radi
         const float center = ((G_TWOPI / (float) p->radial_nbars) / 2.0f);
         float m = g_mod(theta, section);
         float ym = d * G_SIN(center - m);
-        if (fabsf(ym) < p->radial_bar_width / 2.0f) {
+        /* `BAR_WIDTH / 2` (radial/1.frag:62,79,88) is an INTEGER division when the macro is an integer literal */
+        const float bw2 = p->radial_bar_width_int ? (float) ((int) p->radial_bar_width / 2) : p->radial_bar_width / 2.0f;
+        const float ow = p->radial_bar_outline_width;                    /* BAR_OUTLINE_WIDTH (deprecated, radial.glsl:33-36) */
+        if (fabsf(ym) < bw2) {
             float idx = theta + p->radial_rotate;
             float dir = g_mod(fabsf(idx), G_TWOPI);
             if (dir > G_PI) idx = -g_sign(idx) * (G_TWOPI - dir);
@@ -603,9 +607,16 @@ static vec4 radial_px(const rctx* c, int x, int y) {                     /* radi
             float v = smooth_audio(p, idx > 0.0f ? c->l : c->r, pos);
             v *= p->radial_amplify;
             d -= R;
-            if (d <= v) {                                                /* BAR_OUTLINE_WIDTH 0 */
-                vec4 r = eval_color(&p->radial_color, d);
-                r.a *= (((p->radial_bar_width / 2.0f) - fabsf(ym)) * p->radial_bar_alias);
+            if (d <= v - ow) {                                           /* radial/1.frag:85-99 */
+                vec4 r;
+                if (!(ow > 0.0f) || fabsf(ym) < bw2 - ow) r = eval_color(&p->radial_color, d);
+                else r = v4a(p->radial_bar_outline);
+                r.a *= ((bw2 - fabsf(ym)) * p->radial_bar_alias);
+                return apply_frag(frag, r);
+            }
+            if (ow > 0.0f && d <= v) {                                   /* radial/1.frag:100-110 */
+                vec4 r = v4a(p->radial_bar_outline);
+                r.a *= ((bw2 - fabsf(ym)) * p->radial_bar_alias);
                 return apply_frag(frag, r);
             }
         }

@@ -64,6 +64,12 @@ CASES = [
     ("circle_odd", "circle", {"C_RADIUS": "12", "AMPLIFY": "20"}, dict(circle_radius=12.0, circle_amplify=20.0), {}, (93, 51)),
     ("graph_odd", "graph", {"VSCALE": "40"}, dict(graph_vscale=40.0), {}, (95, 53)),
     ("wave_odd", "wave", {"AMPLIFY": "40"}, dict(wave_amplify=40.0), {}, (95, 53)),
+    # radial: `BAR_WIDTH / 2` is an integer division for an integer BAR_WIDTH; the deprecated bar outline (sides + end cap)
+    ("radial_intwidth", "radial", {"C_RADIUS": "12", "AMPLIFY": "30", "NBARS": "24", "BAR_WIDTH": "5"},
+     dict(radial_radius=12.0, radial_amplify=30.0, radial_nbars=24, radial_bar_width=5.0, radial_bar_width_int=1), {}),
+    ("radial_outline", "radial", {"C_RADIUS": "12", "AMPLIFY": "30", "NBARS": "24", "BAR_WIDTH": "5.5", "BAR_OUTLINE_WIDTH": "1", "BAR_OUTLINE": "vec4(0.125490, 1.0, 0.250980, 1.0)"},
+     dict(radial_radius=12.0, radial_amplify=30.0, radial_nbars=24, radial_bar_width=5.5, radial_bar_outline_width=1.0,
+          radial_bar_outline=[0.125490, 1.0, 0.250980, 1.0]), {}),
     # setopacity "none": every stage blended (SRC_ALPHA, ONE_MINUS_SRC_ALPHA) over the glClear colour, premultiply stages skipped
     ("radial_nopremult", "radial", {"C_RADIUS": "12", "AMPLIFY": "30", "NBARS": "40"},
      dict(radial_radius=12.0, radial_amplify=30.0, radial_nbars=40, premultiply_alpha=0), {"premultiply_alpha": 0}),

@@ -64,7 +64,8 @@ def test_product_arithmetic_equals_the_reference_shader_frames(orc_pm, gold, cas
 
 def _native_cases():
     """non-native opacity (GL blending over the clear colour) runs in tests/test_zz_gpu_blend.py"""
-    return [c for c in _cases() if not (c.endswith("_blend") or c.endswith("_blend_opaque") or c.endswith("_nopremult"))]
+    return [c for c in _cases() if not (c.endswith("_blend") or c.endswith("_blend_opaque") or c.endswith("_nopremult")
+                                        or c == "radial_outline")]          # (per-pixel radial kernel: same file)
 
 
 @pytest.mark.gpu
@@ -194,6 +195,14 @@ USER_CONFIGS = {
 #define ROTATE (PI / 4)
 #define INVERT 1
 """,
+    "radial:outline": """
+#define C_RADIUS 10
+#define NBARS 20
+#define BAR_WIDTH 5
+#define AMPLIFY 25
+#define BAR_OUTLINE_WIDTH 1.5
+#define OUTLINE #4080c0
+""",
     "circle": """
 #define C_RADIUS 14
 #define C_LINE 2
@@ -222,6 +231,7 @@ USER_CONFIGS = {
 @pytest.mark.skipif(not os.path.isdir(REF_SHADERS), reason="reference tree not present")
 @pytest.mark.parametrize("module", sorted(USER_CONFIGS))
 def test_config_reader_agrees_with_the_shaders_on_a_user_config(orc, tmp_path, module, built):
+    key, module = module, module.split(":")[0]
     """a user's <module>.glsl goes (a) through glava_b200_load_config -> parameters -> oracle raster and (b) as text through
     the reference's shaders in the interpreter: same pixels.  Covers colour literals / mix() gradients / constant
     vec4 colours / integer vs float macro values / parenthesised arithmetic in #defines."""
@@ -230,7 +240,7 @@ def test_config_reader_agrees_with_the_shaders_on_a_user_config(orc, tmp_path, m
     user = tmp_path / "user"
     user.mkdir()
     (user / "rc.glsl").write_text("#request mod %s\n#request setbufsize %d\n#request setgeometry 0 0 %d %d\n" % (module, n, w, h))
-    (user / (module + ".glsl")).write_text(USER_CONFIGS[module])
+    (user / (module + ".glsl")).write_text(USER_CONFIGS[key])
     p = g.load_config([str(user), REF_SHADERS])
     assert p.module_name == module and (p.w, p.h, p.n) == (w, h, n)
     op = params_from(p)

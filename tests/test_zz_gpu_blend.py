@@ -52,3 +52,28 @@ def test_full_size_non_native_frame(orc_pm, built):
     for y0, y1 in ((0, 4), (100, 104), (298, 304), (1076, 1080)):
         assert np.array_equal(got[y0:y1], orc_pm.raster(op, tl, tr, rows=(y0, y1))[y0:y1])
     assert (got[1079, 0] == [13, 13, 26, 255]).all()
+
+
+def test_radial_bar_outline_through_the_per_pixel_kernel(orc_pm, built):
+    """BAR_OUTLINE_WIDTH > 0 (deprecated, radial.glsl:33-36): three values per pixel, so launch_raster leaves the geometry
+    cache for the per-pixel radial kernel"""
+    from tests import emul
+    z = np.load(os.path.join(GOLDEN, "glsl_golden.npz"))
+    case = "radial_outline"
+    w, h = (int(v) for v in z[f"{case}_size"])
+    p = g.default_params("radial", n=N, w=w, h=h, **json.loads(str(z[f"{case}_params"])))
+    tl, tr, want = z[f"{case}_tl"], z[f"{case}_tr"], z[f"{case}_frame"]
+    with g.Renderer(p, batch=2) as r:
+        r.raster_textures(np.stack([tl, tr]), np.stack([tr, tl]))
+        got = r.readback(0)
+    assert np.array_equal(got, emul.raster(p, tl, tr))
+    assert np.array_equal(got, orc_pm.raster(params_from(p), tl, tr))
+    assert int(np.abs(got.astype(int) - want.astype(int)).max()) <= 1 and (got != want).any(axis=2).sum() <= 0.002 * w * h
+    big = g.default_params("radial", n=4096, w=1280, h=720, radial_bar_outline_width=2.0, radial_bar_outline=[1.0, 1.0, 0.0, 1.0])
+    rng = np.random.default_rng(3)
+    op = params_from(big)
+    tl = orc_pm.smooth_pass(op, (rng.random(4096) ** 2 * 65535).astype(np.uint16)); tr = tl[::-1].copy()
+    with g.Renderer(big, batch=1) as r:
+        r.raster_textures(tl[None], tr[None])
+        got = r.readback(0)
+    assert np.array_equal(got, orc_pm.raster(op, tl, tr))
