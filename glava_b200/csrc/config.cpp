@@ -596,7 +596,7 @@ static void apply_defines(glava_b200_params* p, const Defs& d) {
             geti(d, "DRAW_OUTLINE", &p->graph_draw_outline); geti(d, "DRAW_HIGHLIGHT", &p->graph_draw_highlight);
             parse_plain_color(d, "OUTLINE", p->graph_outline); geti(d, "INVERT", &p->graph_invert);
             if (eval_num(d, "ANTI_ALIAS", &n) && n.v != 0) fail(GLAVA_B200_ECONFIG, "graph: ANTI_ALIAS 1 (graph/3.frag) is not supported");
-            if (eval_num(d, "JOIN_CHANNELS", &n) && n.v != 0) fail(GLAVA_B200_ECONFIG, "graph: JOIN_CHANNELS 1 is not supported");
+            geti(d, "JOIN_CHANNELS", &p->graph_join_channels);
             break;
         case GLAVA_B200_MOD_WAVE:
             getf(d, "MIN_THICKNESS", &p->wave_min_thickness); getf(d, "MAX_THICKNESS", &p->wave_max_thickness);

@@ -437,7 +437,10 @@ GLB_HD float graph_column_coord(const glava_b200_params& p, int x, int* chan) {
     else             { *chan = 1; idx = p.graph_direction < 0 ? (-fx + W) : (fx - half_w); }
     return idx / half_w;
 }
-GLB_HD float graph_height(const glava_b200_params& p, const AudioTex& t, int x) {
+// JOIN = JOIN_CHANNELS (graph/1.frag:93-96,126): towards the centre the two halves are pulled to `middle`, the mean of the
+// left channel's last and the right channel's first sample, along a smoothstep of the centre taper.  pow(fact, 3) and
+// pow(fact, 2) are evaluated as exact products (GLSL leaves pow's precision open).
+template <bool JOIN> GLB_HD float graph_height_t(const glava_b200_params& p, const AudioTex& t, int x) {
     float fx = (float) x, W = (float) p.w;
     float pixel = 1.0f / W;
     int chan;
@@ -445,9 +448,17 @@ GLB_HD float graph_height(const glava_b200_params& p, const AudioTex& t, int x) 
     float s = sample_audio_adj(t, chan ? t.r : t.l, coord, pixel);
     s *= p.graph_vscale;
     float fact = g_clamp((fabsf((float) (p.w / 2) - fx) / W) * 48.0f, 0.0f, 1.0f);
-    s *= fact;
+    if (JOIN) {
+        const float middle = (p.graph_vscale * (sample_audio_adj(t, t.l, 1.0f, pixel) + sample_audio_adj(t, t.r, 0.0f, pixel))) / 2.0f;
+        fact = (-2.0f * ((fact * fact) * fact)) + (3.0f * (fact * fact));
+        s = (fact * s) + ((1.0f - fact) * middle);
+    } else s *= fact;
     s *= g_clamp((g_min(fx, W - fx) / W) * 48.0f, 0.0f, 1.0f);
     return s;
+}
+GLB_HD float graph_height(const glava_b200_params& p, const AudioTex& t, int x) { return graph_height_t<false>(p, t, x); }
+GLB_HD float graph_height_any(const glava_b200_params& p, const AudioTex& t, int x) {
+    return p.graph_join_channels ? graph_height_t<true>(p, t, x) : graph_height_t<false>(p, t, x);
 }
 GLB_HD float graph_d(const glava_b200_params& p, int y) { return p.graph_invert > 0 ? (float) p.h - (float) y : (float) y; }
 template <bool NATIVE> GLB_HD uint32_t graph_row_t(const glava_b200_params& p, int y) {
@@ -508,7 +519,7 @@ GLB_HD uint32_t graph_px_cols(const glava_b200_params& p, const float s3[3], con
     return graph_px_cols_t<true>(p, s3, row3, x, y);
 }
 GLB_HD uint32_t graph_px(const glava_b200_params& p, const AudioTex& t, int x, int y) {
-    float s3[3] = { x > 0 ? graph_height(p, t, x - 1) : 0.0f, graph_height(p, t, x), x + 1 < p.w ? graph_height(p, t, x + 1) : 0.0f };
+    float s3[3] = { x > 0 ? graph_height_any(p, t, x - 1) : 0.0f, graph_height_any(p, t, x), x + 1 < p.w ? graph_height_any(p, t, x + 1) : 0.0f };
     if (!p.premultiply_alpha) {
         uint32_t rowb[3] = { y > 0 ? graph_row_t<false>(p, y - 1) : 0u, graph_row_t<false>(p, y), y + 1 < p.h ? graph_row_t<false>(p, y + 1) : 0u };
         return graph_px_cols_t<false>(p, s3, rowb, x, y);

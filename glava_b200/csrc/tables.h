@@ -51,6 +51,10 @@ inline bool build_need_list(const glava_b200_params& p, std::vector<int>* lists 
                 int chan; float c = graph_column_coord(p, x, &chan);
                 hit(chan, g_max(c - pixel, 0.0f)); hit(chan, c); hit(chan, g_min(c + pixel, 1.0f));
             }
+            if (p.graph_join_channels) {                 // `middle` (graph/1.frag:126): audio_l around 1, audio_r around 0
+                hit(0, g_max(1.0f - pixel, 0.0f)); hit(0, 1.0f); hit(0, g_min(1.0f + pixel, 1.0f));
+                hit(1, g_max(0.0f - pixel, 0.0f)); hit(1, 0.0f); hit(1, g_min(0.0f + pixel, 1.0f));
+            }
             break;
         }
         case GLAVA_B200_MOD_WAVE:

@@ -145,6 +145,7 @@ typedef struct {
                                         (radial/1.frag:62,79,88) is then an integer division */
     float radial_bar_outline_width;  /* BAR_OUTLINE_WIDTH (deprecated, radial.glsl:33-36; default 0) */
     float radial_bar_outline[4];     /* BAR_OUTLINE (default: OUTLINE) */
+    int   graph_join_channels;       /* JOIN_CHANNELS (graph.glsl:23): the two halves meet at a common height in the middle */
 } glava_b200_params;
 
 typedef struct glava_b200 glava_b200;    /* plays the role of struct glava_renderer (render.h:8-30) */

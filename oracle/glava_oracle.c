@@ -27,12 +27,14 @@
 #define G_SIN(x)      glm_sin(x)
 #define G_ATAN2(y, x) glm_atan2(y, x)
 #define G_LOG(x)      glm_log(x)
+#define G_POW(x, k)   ((k) == 3 ? ((x) * (x)) * (x) : (x) * (x))   /* gl_math has no pow: exact products for the two integer powers used */
 const char* orc_math_kind(void) { return "product-gl_math"; }
 #else
 #define G_SIN(x)      sinf(x)
 static float orc_atan2f(float y, float x) { return (x == 0.0f && y == 0.0f) ? 0.0f : atan2f(y, x); }
 #define G_ATAN2(y, x) orc_atan2f(y, x)
 #define G_LOG(x)      logf(x)
+#define G_POW(x, k)   powf((x), (float) (k))
 const char* orc_math_kind(void) { return "libm"; }
 #endif
 
@@ -667,7 +669,11 @@ static float graph_height(const rctx* c, int x) {                        /* grap
     float s = smooth_audio_adj(p, tex, idx / half_w, pixel);
     s *= p->graph_vscale;
     float fact = g_clamp((fabsf((float) (p->w / 2) - fx) / W) * 48.0f, 0.0f, 1.0f);
-    s *= fact;                                                           /* JOIN_CHANNELS 0 */
+    if (p->graph_join_channels) {                                        /* graph/1.frag:93-96,126 */
+        float middle = (p->graph_vscale * (smooth_audio_adj(p, c->l, 1.0f, pixel) + smooth_audio_adj(p, c->r, 0.0f, pixel))) / 2.0f;
+        fact = (-2.0f * G_POW(fact, 3)) + (3.0f * G_POW(fact, 2));
+        s = (fact * s) + ((1.0f - fact) * middle);
+    } else s *= fact;
     s *= g_clamp((g_min(fx, W - fx) / W) * 48.0f, 0.0f, 1.0f);
     return s;
 }

@@ -189,3 +189,16 @@ def test_lazy_k5_tables_give_the_oracle_texels(orc_pm, module, n, w, h, built):
 def test_circle_has_no_need_list(built):
     p = g.default_params("circle", n=1024, w=320, h=240, lazy_smooth=1)
     assert emul.lazy_k5(p, 0, 0, _tex(1024, 1))[0] is None
+
+
+def test_need_list_covers_the_join_channels_middle_taps(built):
+    """JOIN_CHANNELS samples audio_l around coordinate 1 and audio_r around 0 for `middle` (graph/1.frag:126)"""
+    n, w = 1024, 320
+    av = np.arange(n, dtype=np.uint16)
+    plain = g.default_params("graph", n=n, w=w, h=200, lazy_smooth=1)
+    join = g.default_params("graph", n=n, w=w, h=200, lazy_smooth=1, graph_join_channels=1)
+    for chan, texel in ((0, int(np.rint((1 - 1 / w) * n))), (1, 0), (1, int(np.rint(1 / w * n)))):
+        idx, _ = emul.lazy_k5(join, chan, 0, av)
+        assert texel in idx.tolist(), (chan, texel)
+    ia, _ = emul.lazy_k5(plain, 0, 0, av); ib, _ = emul.lazy_k5(join, 0, 0, av)
+    assert set(ia.tolist()) <= set(ib.tolist())

@@ -77,3 +77,28 @@ def test_radial_bar_outline_through_the_per_pixel_kernel(orc_pm, built):
         r.raster_textures(tl[None], tr[None])
         got = r.readback(0)
     assert np.array_equal(got, orc_pm.raster(op, tl, tr))
+
+
+def test_graph_join_channels(orc_pm, built):
+    """JOIN_CHANNELS 1 (graph/1.frag:93-96,126): generic kernel; the lazy K5 need-list must hold the texels `middle` samples"""
+    from tests import emul
+    z = np.load(os.path.join(GOLDEN, "glsl_golden.npz"))
+    case = "graph_join"
+    w, h = (int(v) for v in z[f"{case}_size"])
+    p = g.default_params("graph", n=N, w=w, h=h, **json.loads(str(z[f"{case}_params"])))
+    tl, tr, want = z[f"{case}_tl"], z[f"{case}_tr"], z[f"{case}_frame"]
+    with g.Renderer(p, batch=1) as r:
+        r.raster_textures(tl[None], tr[None])
+        got = r.readback(0)
+    assert np.array_equal(got, emul.raster(p, tl, tr))
+    assert int(np.abs(got.astype(int) - want.astype(int)).max()) <= 1 and (got != want).any(axis=2).sum() <= 0.002 * w * h
+    # whole pipeline, lazy K5 (only the sampled texels are smoothed) against full K5: identical frames
+    frames = []
+    for lazy in (0, 1):
+        q = g.default_params("graph", n=1024, w=320, h=200, graph_join_channels=1, lazy_smooth=lazy)
+        rings = g.StreamRings(2, 1024)
+        with g.Renderer(q, batch=2) as r:
+            for _ in range(6):
+                rings.advance(); r.update(rings.lb, rings.rb, True)
+            frames.append([r.readback(0), r.readback(1)])
+    assert np.array_equal(frames[0][0], frames[1][0]) and np.array_equal(frames[0][1], frames[1][1]) and frames[0][0].any()
