@@ -245,7 +245,22 @@ class Reference:
         L.ref_wrange.argtypes = [vp, C.c_size_t]
         L.ref_parse_color.argtypes = [C.c_char_p, vp]
         L.ref_smooth.argtypes = [vp, C.c_size_t, C.c_float, C.c_float]
+        if hasattr(L, "ref_ext_process"):
+            L.ref_ext_process.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int,
+                                          C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
         self.L = L
+
+    def ext_process(self, path, cd, cfd, dd, binds=None, avg_frames=5):
+        """the reference's own glsl_ext.c on one file -> (processed source, [[request, arg, ...], ...]); raises ValueError
+        when the reference reports a parse error (it would have called glava_abort)"""
+        out = C.create_string_buffer(1 << 21); req = C.create_string_buffer(1 << 16)
+        arr = (C.c_char_p * (len(binds) + 1))(*[b.encode() for b in binds], None) if binds else None
+        rc = self.L.ref_ext_process(path.encode(), cd.encode(), cfd.encode() if cfd else None, dd.encode(), arr, avg_frames,
+                                    out, len(out), req, len(req))
+        if rc == 1:
+            raise ValueError("the reference rejected %s (parse_error -> glava_abort)" % path)
+        assert rc == 0, rc
+        return out.value.decode(), [ln.split("|") for ln in req.value.decode().splitlines()]
 
     def chan(self, p):
         return self.L.ref_chan_new(p.fft_scale, p.fft_cutoff, p.gravity_step, p.ur, p.avg_frames, p.avg_window)
