@@ -595,7 +595,7 @@ static void apply_defines(glava_b200_params* p, const Defs& d) {
             if (p->graph_color.mode == 0 && eval_num(d, "GRADIENT", &n)) p->graph_color.gradient = (float) n.v;
             geti(d, "DRAW_OUTLINE", &p->graph_draw_outline); geti(d, "DRAW_HIGHLIGHT", &p->graph_draw_highlight);
             parse_plain_color(d, "OUTLINE", p->graph_outline); geti(d, "INVERT", &p->graph_invert);
-            if (eval_num(d, "ANTI_ALIAS", &n) && n.v != 0) fail(GLAVA_B200_ECONFIG, "graph: ANTI_ALIAS 1 (graph/3.frag) is not supported");
+            geti(d, "ANTI_ALIAS", &p->graph_anti_alias);
             geti(d, "JOIN_CHANNELS", &p->graph_join_channels);
             break;
         case GLAVA_B200_MOD_WAVE:

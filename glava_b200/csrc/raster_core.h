@@ -518,7 +518,60 @@ template <bool NATIVE> GLB_HD uint32_t graph_px_cols_t(const glava_b200_params& 
 GLB_HD uint32_t graph_px_cols(const glava_b200_params& p, const float s3[3], const uint32_t row3[3], int x, int y) {
     return graph_px_cols_t<true>(p, s3, row3, x, y);
 }
+// ---- graph/3.frag (ANTI_ALIAS 1): the step between neighbouring columns of the line is faded --------------------------
+// Evaluated per pixel without a surface: S(x, y) below is the previous stage's value re-derived from the column heights.
+// graph/4.frag (premultiply) tests `#if ANTI_ALIAS == 0` without including graph.glsl — the macro is undefined there, the
+// test is true and the stage is always disabled — so stage 3 is the last one, in native mode too.
+template <bool NATIVE> struct GraphCols {            // heights of columns x-2 .. x+2 around the pixel's column
+    const glava_b200_params& p; int x; float h5[5];
+    GLB_HD uint32_t S(int col, int y) const {         // stage-2 (or stage-1) surface value, 0 outside (texelFetch)
+        if (col < 0 || y < 0 || col >= p.w || y >= p.h) return 0u;
+        const int k = col - x + 2;                    // slot of `col` in h5 (callers stay within x-1 .. x+1)
+        const float s3[3] = { h5[k - 1], h5[k], h5[k + 1] };
+        const uint32_t row3[3] = { y > 0 ? graph_row_t<NATIVE>(p, y - 1) : 0u, graph_row_t<NATIVE>(p, y),
+                                   y + 1 < p.h ? graph_row_t<NATIVE>(p, y + 1) : 0u };
+        return graph_px_cols_t<NATIVE>(p, s3, row3, col, y);
+    }
+    GLB_HD float up(float xf, float oy) const {       // get_col_height_up, graph/3.frag:21-44
+        float y = oy;
+        if (p.graph_invert > 0) { while (y >= 0.0f) { if ((S((int) xf, (int) y) >> 24) == 0u) { y += 1.0f; break; } y -= 1.0f; } }
+        else { while (y < (float) p.h) { if ((S((int) xf, (int) y) >> 24) == 0u) { y -= 1.0f; break; } y += 1.0f; } }
+        return y;
+    }
+    GLB_HD float down(float xf, float oy) const {     // get_col_height_down, graph/3.frag:48-69
+        float y = oy;
+        if (p.graph_invert > 0) { while (y < (float) p.h) { if ((S((int) xf, (int) y) >> 24) != 0u) break; y += 1.0f; } }
+        else { while (y >= 0.0f) { if ((S((int) xf, (int) y) >> 24) != 0u) break; y -= 1.0f; } }
+        return y;
+    }
+};
+template <bool NATIVE> GLB_HD uint32_t graph_px_aa(const glava_b200_params& p, const AudioTex& t, int x, int y) {
+    GraphCols<NATIVE> c = { p, x, { 0.0f, 0.0f, 0.0f, 0.0f, 0.0f } };
+    for (int k = 0; k < 5; ++k) { const int col = x - 2 + k; if (col >= 0 && col < p.w) c.h5[k] = graph_height_any(p, t, col); }
+    const float X = (float) x + 0.5f, Y = (float) y + 0.5f;               // default (half-integer) gl_FragCoord
+    const uint32_t own = c.S(x, y);
+    f4 f = unpack8(own);
+    if (f.a <= 0.0f) {
+        bool left_done = false;
+        float h2 = 0.0f, a_fact = 0.0f;
+        if ((c.S((int) (X - 1.0f), y) >> 24) != 0u) {                     // ivec2(-0.5) = 0: column 0 tests itself
+            const float h1 = c.up(X - 1.0f, Y);
+            h2 = c.down(X, Y);
+            f = unpack8(c.S(x, (int) h2));
+            a_fact = g_clamp(fabsf((h1 - Y) / (h2 - h1)), 0.0f, 1.0f);
+            left_done = true;
+        }
+        if ((c.S((int) (X + 1.0f), y) >> 24) != 0u) {
+            if (!left_done) { h2 = c.down(X, Y); f = unpack8(c.S(x, (int) h2)); }
+            const float h3 = c.up(X + 1.0f, Y);
+            a_fact = g_max(a_fact, g_clamp(fabsf((h3 - Y) / (h2 - h3)), 0.0f, 1.0f));
+        }
+        f.a *= a_fact;
+    }
+    return stage_store<NATIVE>(p, f);
+}
 GLB_HD uint32_t graph_px(const glava_b200_params& p, const AudioTex& t, int x, int y) {
+    if (p.graph_anti_alias) return p.premultiply_alpha ? graph_px_aa<true>(p, t, x, y) : graph_px_aa<false>(p, t, x, y);
     float s3[3] = { x > 0 ? graph_height_any(p, t, x - 1) : 0.0f, graph_height_any(p, t, x), x + 1 < p.w ? graph_height_any(p, t, x + 1) : 0.0f };
     if (!p.premultiply_alpha) {
         uint32_t rowb[3] = { y > 0 ? graph_row_t<false>(p, y - 1) : 0u, graph_row_t<false>(p, y), y + 1 < p.h ? graph_row_t<false>(p, y + 1) : 0u };

@@ -617,7 +617,7 @@ int launch_raster(const glava_b200_params& p, const RasterArgs& a, void* stream)
     // with GL blending (premultiply_alpha == 0) every stage output is blended over the clear colour: generic kernel.
     const bool native = p.premultiply_alpha != 0;
     const bool fast_bars  = native && p.module == GLAVA_B200_MOD_BARS && !p.bars_mirror_yx && a.rowtab && (p.w & 3) == 0;
-    const bool fast_graph = native && p.module == GLAVA_B200_MOD_GRAPH && a.rowtab && !p.graph_join_channels;
+    const bool fast_graph = native && p.module == GLAVA_B200_MOD_GRAPH && a.rowtab && !p.graph_join_channels && !p.graph_anti_alias;
     const bool fast_wave  = native && p.module == GLAVA_B200_MOD_WAVE;
     const bool geo_radial = native && p.module == GLAVA_B200_MOD_RADIAL && a.geo && p.radial_nbars <= RADIAL_MAX_BARS
                             && !(p.radial_bar_outline_width > 0.0f);      // the cache holds two values per pixel, the end cap needs three

@@ -146,6 +146,7 @@ typedef struct {
     float radial_bar_outline_width;  /* BAR_OUTLINE_WIDTH (deprecated, radial.glsl:33-36; default 0) */
     float radial_bar_outline[4];     /* BAR_OUTLINE (default: OUTLINE) */
     int   graph_join_channels;       /* JOIN_CHANNELS (graph.glsl:23): the two halves meet at a common height in the middle */
+    int   graph_anti_alias;          /* ANTI_ALIAS (graph.glsl:19): graph/3.frag fades the column steps of the line */
 } glava_b200_params;
 
 typedef struct glava_b200 glava_b200;    /* plays the role of struct glava_renderer (render.h:8-30) */

@@ -763,6 +763,54 @@ static inline vec4 neigh_avg(const surf* s, int x, int y, int half_integer_coord
 }
 static inline vec4 premultiply(vec4 f) { return v4(f.r * f.a, f.g * f.a, f.b * f.a, f.a); }  /* premultiply.frag:12-15 */
 
+/* graph/3.frag:19-105 (ANTI_ALIAS 1), default half-integer gl_FragCoord.  S = the previous stage's surface.  graph/4.frag
+ * (premultiply) tests `#if ANTI_ALIAS == 0` WITHOUT including graph.glsl: the macro is undefined there, evaluates to 0 and
+ * the stage is always disabled — stage 3 is the final one, in native mode too. */
+static float aa_up(const orc_params* p, const surf* S, float x, float oy) {      /* get_col_height_up, :21-44 */
+    float y = oy;
+    if (p->graph_invert > 0) {
+        while (y >= 0.0f) { if (sfetch(S, (int) x, (int) y).a <= 0.0f) { y += 1.0f; break; } y -= 1.0f; }
+    } else {
+        while (y < (float) S->h) { if (sfetch(S, (int) x, (int) y).a <= 0.0f) { y -= 1.0f; break; } y += 1.0f; }
+    }
+    return y;
+}
+static float aa_down(const orc_params* p, const surf* S, float x, float oy) {    /* get_col_height_down, :48-69 */
+    float y = oy;
+    if (p->graph_invert > 0) {
+        while (y < (float) S->h) { if (sfetch(S, (int) x, (int) y).a > 0.0f) break; y += 1.0f; }
+    } else {
+        while (y >= 0.0f) { if (sfetch(S, (int) x, (int) y).a > 0.0f) break; y -= 1.0f; }
+    }
+    return y;
+}
+static void graph_anti_alias(const orc_params* p, const surf* S, uint32_t* dst, int y0, int y1) {
+    for (int yi = y0; yi < y1; ++yi) {
+        for (int xi = 0; xi < S->w; ++xi) {
+            const float X = (float) xi + 0.5f, Y = (float) yi + 0.5f;
+            vec4 f = sfetch(S, (int) X, (int) Y);
+            if (f.a <= 0.0f) {
+                int left_done = 0;
+                float h2 = 0.0f, a_fact = 0.0f;
+                if (sfetch(S, (int) (X - 1.0f), (int) Y).a > 0.0f) {
+                    float h1 = aa_up(p, S, X - 1.0f, Y);
+                    h2 = aa_down(p, S, X, Y);
+                    f = sfetch(S, (int) X, (int) h2);
+                    a_fact = g_clamp(fabsf((h1 - Y) / (h2 - h1)), 0.0f, 1.0f);
+                    left_done = 1;
+                }
+                if (sfetch(S, (int) (X + 1.0f), (int) Y).a > 0.0f) {
+                    if (!left_done) { h2 = aa_down(p, S, X, Y); f = sfetch(S, (int) X, (int) h2); }
+                    float h3 = aa_up(p, S, X + 1.0f, Y);
+                    a_fact = g_max(a_fact, g_clamp(fabsf((h3 - Y) / (h2 - h3)), 0.0f, 1.0f));
+                }
+                f.a *= a_fact;
+            }
+            dst[(size_t) yi * S->w + xi] = store8(p, f);
+        }
+    }
+}
+
 void orc_raster_rows(const orc_params* p, const uint16_t* tl, const uint16_t* tr, uint8_t* out, int y0, int y1) {
     rctx c = { p, tl, tr };
     const int w = p->w, h = p->h;
@@ -771,6 +819,11 @@ void orc_raster_rows(const orc_params* p, const uint16_t* tl, const uint16_t* tr
     int stencil = (p->module == ORC_MOD_CIRCLE && p->circle_smooth) ||
                   (p->module == ORC_MOD_GRAPH && (p->graph_draw_outline || p->graph_draw_highlight)) ||
                   (p->module == ORC_MOD_WAVE);
+    /* graph ANTI_ALIAS 1 (graph/3.frag) walks whole columns of the previous stage: render the full surface, then the walk */
+    const int aa = p->module == ORC_MOD_GRAPH && p->graph_anti_alias;
+    const int out_y0 = y0, out_y1 = y1;
+    uint32_t* full = NULL;
+    if (aa) { full = malloc(sizeof(uint32_t) * (size_t) w * (size_t) h); dst = full; y0 = 0; y1 = h; }
     int sy0 = stencil ? (y0 > 0 ? y0 - 1 : 0) : y0, sy1 = stencil ? (y1 < h ? y1 + 1 : h) : y1;
     uint32_t* s1 = malloc(sizeof(uint32_t) * (size_t) w * (size_t) (sy1 - sy0));
     for (int y = sy0; y < sy1; ++y)
@@ -827,6 +880,11 @@ void orc_raster_rows(const orc_params* p, const uint16_t* tl, const uint16_t* tr
         }
     }
     free(s1);
+    if (aa) {
+        surf S2 = { full, w, h, 0, h };
+        graph_anti_alias(p, &S2, (uint32_t*) out, out_y0, out_y1);
+        free(full);
+    }
 }
 
 void orc_raster(const orc_params* p, const uint16_t* tl, const uint16_t* tr, uint8_t* out) {

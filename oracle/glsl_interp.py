@@ -392,6 +392,12 @@ class Parser:
             step = self.expr() if self.peek() != ")" else None
             self.expect(")")
             return ("for", init, cond, step, self.stmt())
+        if p == "while":
+            self.next(); self.expect("("); c = self.expr(); self.expect(")")
+            return ("for", None, c, None, self.stmt())
+        if p in ("break", "continue"):
+            self.next(); self.expect(";")
+            return (p,)
         if p == "return":
             self.next()
             e = None if self.peek() == ";" else self.expr()
@@ -655,6 +661,14 @@ class Sampler2D:
         return Vec("vec4", [F32(F32(c) / F32(255.0)) for c in self.fn(x, y)])
 
 
+class Break(Exception):
+    pass
+
+
+class Continue(Exception):
+    pass
+
+
 class Return(Exception):
     def __init__(self, v):
         self.v = v
@@ -775,13 +789,22 @@ class Shader:
                 if init is not None:
                     self.exec(init)
                 while cond is None or self.ev(cond):
-                    self.exec(body)
+                    try:
+                        self.exec(body)
+                    except Break:
+                        break
+                    except Continue:
+                        pass
                     if step is not None:
                         self.ev(step)
             finally:
                 self.scopes.pop()
         elif kind == "return":
             raise Return(self.ev(node[1]) if node[1] is not None else None)
+        elif kind == "break":
+            raise Break()
+        elif kind == "continue":
+            raise Continue()
         else:
             raise SyntaxError(kind)
 

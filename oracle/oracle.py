@@ -42,7 +42,7 @@ class OrcParams(C.Structure):
         ("graph_invert", C.c_int),
         ("wave_min_thickness", C.c_float), ("wave_max_thickness", C.c_float), ("wave_base_color", C.c_float * 4),
         ("wave_amplify", C.c_float), ("wave_outline", C.c_float * 4),
-        ("graph_join_channels", C.c_int), ("radial_bar_width_int", C.c_int), ("radial_bar_outline_width", C.c_float), ("radial_bar_outline", C.c_float * 4),
+        ("graph_join_channels", C.c_int), ("graph_anti_alias", C.c_int), ("radial_bar_width_int", C.c_int), ("radial_bar_outline_width", C.c_float), ("radial_bar_outline", C.c_float * 4),
         ("clear_color", C.c_float * 4),
     ]
 

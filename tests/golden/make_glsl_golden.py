@@ -64,6 +64,10 @@ CASES = [
     ("circle_odd", "circle", {"C_RADIUS": "12", "AMPLIFY": "20"}, dict(circle_radius=12.0, circle_amplify=20.0), {}, (93, 51)),
     ("graph_odd", "graph", {"VSCALE": "40"}, dict(graph_vscale=40.0), {}, (95, 53)),
     ("wave_odd", "wave", {"AMPLIFY": "40"}, dict(wave_amplify=40.0), {}, (95, 53)),
+    # graph/3.frag: column-walking anti-alias stage (graph/4.frag never runs: its `#if ANTI_ALIAS == 0` sees an undefined macro)
+    ("graph_aa", "graph", {"VSCALE": "42", "ANTI_ALIAS": "1"}, dict(graph_vscale=42.0, graph_anti_alias=1), {}),
+    ("graph_aa_invert", "graph", {"VSCALE": "38", "ANTI_ALIAS": "1", "INVERT": "1", "DRAW_OUTLINE": "1"},
+     dict(graph_vscale=38.0, graph_anti_alias=1, graph_invert=1, graph_draw_outline=1), {}),
     ("graph_join", "graph", {"VSCALE": "42", "JOIN_CHANNELS": "1"}, dict(graph_vscale=42.0, graph_join_channels=1), {}),
     # radial: `BAR_WIDTH / 2` is an integer division for an integer BAR_WIDTH; the deprecated bar outline (sides + end cap)
     ("radial_intwidth", "radial", {"C_RADIUS": "12", "AMPLIFY": "30", "NBARS": "24", "BAR_WIDTH": "5"},

@@ -57,7 +57,7 @@ def test_product_arithmetic_equals_the_reference_shader_frames(orc_pm, gold, cas
     tl, tr, want = gold[f"{case}_tl"], gold[f"{case}_tr"], gold[f"{case}_frame"]
     got = emul.raster(p, tl, tr)
     assert _lsb(got, want) <= 1 and (got != want).any(axis=2).sum() <= 0.002 * want.shape[0] * want.shape[1], case
-    if module in ("bars", "graph", "wave", "circle") and not p.bars_mirror_yx and p.premultiply_alpha and not p.graph_join_channels:
+    if module in ("bars", "graph", "wave", "circle") and not p.bars_mirror_yx and p.premultiply_alpha and not p.graph_join_channels and not p.graph_anti_alias:
         assert np.array_equal(emul.raster(p, tl, tr, fast=True), got)                      # the kernels' hoisted evaluation (native
                                                                                            # opacity only: launch_raster's rule)
 
@@ -65,7 +65,7 @@ def test_product_arithmetic_equals_the_reference_shader_frames(orc_pm, gold, cas
 def _native_cases():
     """non-native opacity (GL blending over the clear colour) runs in tests/test_zz_gpu_blend.py"""
     return [c for c in _cases() if not (c.endswith("_blend") or c.endswith("_blend_opaque") or c.endswith("_nopremult")
-                                        or c in ("radial_outline", "graph_join"))]   # (per-pixel kernels: same file)
+                                        or c in ("radial_outline", "graph_join", "graph_aa", "graph_aa_invert"))]   # (per-pixel kernels: same file)
 
 
 @pytest.mark.gpu

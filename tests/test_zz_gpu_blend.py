@@ -102,3 +102,24 @@ def test_graph_join_channels(orc_pm, built):
                 rings.advance(); r.update(rings.lb, rings.rb, True)
             frames.append([r.readback(0), r.readback(1)])
     assert np.array_equal(frames[0][0], frames[1][0]) and np.array_equal(frames[0][1], frames[1][1]) and frames[0][0].any()
+
+
+@pytest.mark.parametrize("case", ["graph_aa", "graph_aa_invert"])
+def test_graph_anti_alias_stage(orc_pm, case, built):
+    """ANTI_ALIAS 1 (graph/3.frag): per-pixel column walks in the generic kernel; exact (no transcendental on this path)"""
+    z = np.load(os.path.join(GOLDEN, "glsl_golden.npz"))
+    w, h = (int(v) for v in z[f"{case}_size"])
+    p = g.default_params("graph", n=N, w=w, h=h, **json.loads(str(z[f"{case}_params"])))
+    tl, tr, want = z[f"{case}_tl"], z[f"{case}_tr"], z[f"{case}_frame"]
+    with g.Renderer(p, batch=2) as r:
+        r.raster_textures(np.stack([tl, tr]), np.stack([tr, tl]))
+        got, swapped = r.readback(0), r.readback(1)
+    assert np.array_equal(got, want) and np.array_equal(swapped, orc_pm.raster(params_from(p), tr, tl))
+    big = g.default_params("graph", n=2048, w=1280, h=720, graph_anti_alias=1)
+    op = params_from(big)
+    rng = np.random.default_rng(2)
+    tl = orc_pm.smooth_pass(op, (rng.random(2048) ** 2 * 65535).astype(np.uint16)); tr = orc_pm.smooth_pass(op, (rng.random(2048) ** 3 * 65535).astype(np.uint16))
+    with g.Renderer(big, batch=1) as r:
+        r.raster_textures(tl[None], tr[None])
+        got = r.readback(0)
+    assert np.array_equal(got, orc_pm.raster(op, tl, tr))
