@@ -407,8 +407,8 @@ GLB_HD float circle_reach(const glava_b200_params& p) {
 }
 // non-native: stage 2 (when C_SMOOTH) is blended like stage 1, stage 3 (premultiply) is skipped
 GLB_HD uint32_t circle_finish_blend(const glava_b200_params& p, uint32_t own, const uint32_t nb[6]) {
-    if (!p.circle_smooth) return own;                                      // circle/2.frag disabled: stage 1 is the frame
-    return blend_store(p, (own >> 24) == 0u ? neigh_avg(nb) : unpack8(own));
+    // with C_SMOOTH 0 circle/2.frag is not disabled, it copies its input (:12): one more blend over the clear colour
+    return blend_store(p, (p.circle_smooth && (own >> 24) == 0u) ? neigh_avg(nb) : unpack8(own));
 }
 template <bool NATIVE> GLB_HD uint32_t circle_px_t(const glava_b200_params& p, const AudioTex& t, int x, int y) {
     uint32_t nb[6] = { 0, 0, 0, 0, 0, 0 };

@@ -842,8 +842,10 @@ void orc_raster_rows(const orc_params* p, const uint16_t* tl, const uint16_t* tr
                     if (p->circle_smooth) {                                 /* circle/2.frag:14-32 */
                         vec4 avg = neigh_avg(&S, x, y, 1);
                         if (f.a == 0.0f) f = avg;
-                        px = store8(p, f); f = unpack8(px);
                     }
+                    /* with C_SMOOTH 0 the stage is NOT disabled: it copies its input (circle/2.frag:12) — the identity
+                     * natively, one more blend over the clear colour otherwise */
+                    px = store8(p, f); f = unpack8(px);
                     if (p->premultiply_alpha) px = pack8(premultiply(f));   /* circle/3.frag */
                     break;
                 }

@@ -1,0 +1,99 @@
+"""Randomised differential over the module option space (test infrastructure; needs the reference tree).
+
+For every seed: a random user <module>.glsl (integer AND float spellings of the numeric macros, #rrggbb / #rrggbbaa / vec4
+colours, every option flag), sometimes `setopacity "none"` with a random `setbgf`, sometimes `setmirror`.  The SAME text goes
+  (a) through the reference's own module shaders in oracle/glsl_interp.py (what GLava would render),
+  (b) through the product's config reader -> parameters -> the C oracle, and
+  (c) through the config reader -> the host build of the product's raster arithmetic (tests/emul).
+(a) == (b) must hold exactly; (c) within 1 LSB on a handful of pixels (the product's own sin / atan / log polynomials).
+
+    python tools/fuzz_module_configs.py 0 200        # seeds [0, 200)
+
+Found with it: circle/2.frag is a pass-through, not a disabled stage, when C_SMOOTH is 0 (one more blend in non-native
+opacity).  tests/test_module_config_fuzz.py runs a fixed slice of seeds in the CPU tier."""
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import glava_b200 as g
+from oracle import glsl_interp as gi
+from oracle.oracle import Oracle, params_from
+from tests import emul
+REF="/root/reference/shaders/glava"
+orc=Oracle("libm")
+
+def num(rng, lo, hi, int_ok=True):
+    if int_ok and rng.random()<0.5: return str(int(rng.integers(int(np.ceil(lo)), int(hi)+1)))
+    return "%.2f" % rng.uniform(lo,hi)
+def col(rng):
+    k=rng.integers(0,3)
+    if k==0: return "#%06x" % int(rng.integers(0,1<<24))
+    if k==1: return "#%08x" % int(rng.integers(0,1<<32))
+    return "vec4(%.2f, %.2f, %.2f, %.2f)" % tuple(rng.uniform(0,1,4))
+def gen(rng, module):
+    L=[]
+    D=lambda k,v: L.append(f"#define {k} {v}")
+    if module=="bars":
+        D("BAR_WIDTH", num(rng,1,6)); D("BAR_GAP", num(rng,0,3)); D("BAR_OUTLINE_WIDTH", num(rng,0,2)); D("AMPLIFY", num(rng,10,40))
+        D("GRADIENT", num(rng,5,40)); D("COLOR", f"mix({col(rng)}, {col(rng)}, clamp(d / GRADIENT, 0, 1))")
+        if rng.random()<0.5: D("BAR_OUTLINE", col(rng))
+        for k in ("DIRECTION","INVERT","FLIP","MIRROR_YX"): D(k, int(rng.integers(0,2)))
+    if module=="radial":
+        D("C_RADIUS", num(rng,4,10)); D("C_LINE", num(rng,1,4)); D("OUTLINE", col(rng)); D("NBARS", int(rng.integers(4,30))*2)
+        D("BAR_WIDTH", num(rng,1,5)); D("AMPLIFY", num(rng,8,25)); D("GRADIENT", num(rng,4,20))
+        D("COLOR", f"mix({col(rng)}, {col(rng)}, clamp(d / GRADIENT, 0, 1))"); D("ROTATE", rng.choice(["(PI / 2)","0","1.3","(TWOPI / 5)"]))
+        D("INVERT", int(rng.integers(0,2))); D("BAR_ALIAS_FACTOR", num(rng,0.5,2,False)); D("C_ALIAS_FACTOR", num(rng,0.5,2.5,False))
+        D("CENTER_OFFSET_X", num(rng,-4,4)); D("CENTER_OFFSET_Y", num(rng,-3,3)); D("BAR_OUTLINE_WIDTH", rng.choice(["0","0","1","0.5"]))
+    if module=="circle":
+        D("C_RADIUS", num(rng,4,10)); D("C_LINE", num(rng,1,3)); D("OUTLINE", col(rng)); D("AMPLIFY", num(rng,5,20))
+        D("ROTATE", rng.choice(["(PI / 2)","0","2.1"])); D("INVERT", int(rng.integers(0,2))); D("C_FILL", int(rng.integers(0,2))); D("C_SMOOTH", int(rng.integers(0,2)))
+    if module=="graph":
+        D("VSCALE", num(rng,10,40)); D("DIRECTION", rng.choice(["1","-1"])); D("GRADIENT", num(rng,5,30))
+        D("COLOR", f"mix({col(rng)}, {col(rng)}, clamp(pos / GRADIENT, 0, 1))")
+        for k in ("DRAW_OUTLINE","DRAW_HIGHLIGHT","ANTI_ALIAS","INVERT"): D(k, int(rng.integers(0,2)))
+        D("JOIN_CHANNELS", int(rng.random()<0.25)); D("OUTLINE", col(rng))
+    if module=="wave":
+        D("MIN_THICKNESS", num(rng,1,2)); D("MAX_THICKNESS", num(rng,2,6)); D("BASE_COLOR", col(rng)); D("AMPLIFY", num(rng,10,60)); D("OUTLINE", col(rng))
+    return "\n".join(L)+"\n"
+
+def run(seed, module, w, h, n=128, native=True):
+    rng=np.random.default_rng(seed)
+    text=gen(rng, module)
+    d=tempfile.mkdtemp()
+    rc=f"#request mod {module}\n#request setbufsize 256\n#request setgeometry 0 0 {w} {h}\n"
+    clear=(0,0,0,0)
+    if not native:
+        clear=tuple(float(np.float32(v)) for v in rng.uniform(0,1,4))
+        rc+='#request setopacity "none"\n#request setbgf %r %r %r %r\n' % clear
+    if rng.random()<0.3: rc+="#request setmirror true\n"
+    open(d+"/rc.glsl","w").write(rc); open(f"{d}/{module}.glsl","w").write(text)
+    p=g.load_config([d, REF])
+    n=p.n
+    op=params_from(p)
+    tl=orc.smooth_pass(op,(rng.random(n)**2*65535).astype(np.uint16)); tr=orc.smooth_pass(op,(rng.random(n)**3*65535).astype(np.uint16))
+    if module=="wave": tl=np.clip(tl.astype(int)//4+24576,0,65535).astype(np.uint16)
+    hdr=dict(premultiply_alpha=p.premultiply_alpha, channels=p.channels)
+    prog=gi.ModuleProgram(REF, module, w, h, tl, tr, config_dir=d, clear_color=clear, **hdr)
+    want=np.array([[prog.pixel(x,y) for x in range(w)] for y in range(h)],np.uint8)
+    o=orc.raster(op,tl,tr); e=emul.raster(p,tl,tr)
+    return text, want, o, e
+
+if __name__=="__main__":
+    bad=0; t0=time.time()
+    for seed in range(int(sys.argv[1]), int(sys.argv[2])):
+        module=["bars","radial","circle","graph","wave"][seed%5]
+        w,h=[(40,28),(41,27),(38,30)][seed%3]
+        try:
+            text,want,o,e=run(seed,module,w,h,native=(seed%4!=3))
+        except Exception as ex:
+            print(seed,module,"EXC",repr(ex)[:300]); bad+=1; continue
+        do=(o!=want).any(axis=2).sum(); de=(e!=want).any(axis=2).sum(); lsb=int(np.abs(e.astype(int)-want.astype(int)).max())
+        flag = "" if do==0 and lsb<=1 and de<=0.005*w*h else "  <<<<<<"
+        if flag: bad+=1
+        print(seed,module,(w,h),"oracle!=shader:",do,"product!=shader:",de,"lsb",lsb,flag, flush=True)
+        if flag: print(text)
+    print("bad",bad,"time",time.time()-t0)
