@@ -202,3 +202,24 @@ def test_need_list_covers_the_join_channels_middle_taps(built):
         assert texel in idx.tolist(), (chan, texel)
     ia, _ = emul.lazy_k5(plain, 0, 0, av); ib, _ = emul.lazy_k5(join, 0, 0, av)
     assert set(ia.tolist()) <= set(ib.tolist())
+
+
+def test_update_chain_random_parameters(orc_pm, built):
+    """product spectrum arithmetic vs the (reference-pinned) oracle over random parameters, both pipelines"""
+    rng = np.random.default_rng(77)
+    for trial in range(24):
+        n = int(rng.choice([256, 1024, 2048]))
+        p = g.default_params("bars", n=n, accel_fft=int(trial % 2), avg_window=int(rng.integers(0, 2)),
+                             avg_frames=int(rng.integers(1, 9)), fft_scale=float(rng.uniform(0.5, 20)),
+                             fft_cutoff=float(rng.uniform(0.0, 1.2)), gravity_step=float(rng.uniform(0.0, 12)),
+                             ur=float(rng.uniform(20, 250)), smooth_factor=float(rng.uniform(0.005, 0.06)),
+                             sample_mode=int(rng.integers(0, 3)), round_formula=int(rng.integers(0, 3)))
+        op = params_from(p)
+        oc = OracleChannel(orc_pm, op); ec = emul.Channel(p)
+        amp = float(rng.choice([0.004, 0.05, 0.3]))
+        for _ in range(n // 256 + 9):
+            x = (rng.standard_normal(n) * amp).astype(np.float32)
+            s0, t0 = oc.update(x); s1, t1 = ec.update(x)
+        peak = max(np.abs(s0).max(), 1e-30)
+        assert np.abs(s0 - s1).max() / peak <= 1e-5, (trial, n)
+        assert np.abs(t0.astype(int) - t1.astype(int)).max() <= 2, (trial, n)

@@ -111,3 +111,27 @@ def test_gravity_decays_monotonically(orc):
         assert np.allclose((prev - cur)[falling], g, atol=1e-6)
         assert np.all(cur[~falling] >= -g - 1e-7)
         prev = cur
+
+
+def test_live_reference_bit_exact_random_parameters(orc, ref):
+    """the same, over random setfftscale / setfftcutoff / setgravitystep / ur / setavgframes / setavgwindow and input
+    regimes (silence, clipping-level, tiny, a DC offset, an impulse): 40 parameter sets x 7 updates, bit for bit"""
+    from oracle.oracle import OracleChannel
+    rng = np.random.default_rng(2026)
+    for trial in range(40):
+        n = int(rng.choice([256, 512, 1024, 4096]))
+        p = orc.default_params("bars", n=n, accel_fft=0, smooth_pass=0, avg_window=int(rng.integers(0, 2)),
+                               avg_frames=int(rng.integers(1, 9)), fft_scale=float(rng.uniform(0.5, 20)),
+                               fft_cutoff=float(rng.uniform(0.0, 1.2)), gravity_step=float(rng.uniform(0.0, 12)),
+                               ur=float(rng.uniform(20, 250)))
+        rc = ref.chan(p)
+        oc = OracleChannel(orc, p)
+        for k in range(7):
+            regime = int(rng.integers(0, 6))
+            x = (rng.standard_normal(n) * [0.15, 0.5, 1e-6, 0.0, 0.05, 0.0][regime]).astype(np.float32)
+            if regime == 4:
+                x += np.float32(0.3)
+            if regime == 5:
+                x[int(rng.integers(0, n))] = np.float32(0.5)
+            spec, _ = oc.update(x)
+            assert np.array_equal(_bits(spec), _bits(ref.update_a(rc, x))), (trial, n, k, regime)
