@@ -20,12 +20,14 @@ def fuzz(built):
     return m
 
 
-# 207 / 267: circle, C_SMOOTH 0, non-native opacity (the pass-through stage 2); 131: a 1-LSB radial pixel; the rest: a spread
-@pytest.mark.parametrize("seed", [207, 267, 131] + list(range(40, 70)))
+# 207 / 267: circle, C_SMOOTH 0, non-native opacity (the pass-through stage 2); 131: a 1-LSB radial pixel; 5 / 12 / 26 / 33:
+# setsmoothpass false with a random smooth_parameters.glsl (the tap loop runs in the module shader); the rest: a spread
+@pytest.mark.parametrize("seed", [207, 267, 131, 5, 12, 26, 33] + list(range(40, 66)))
 def test_random_module_config(fuzz, seed):
     module = ["bars", "radial", "circle", "graph", "wave"][seed % 5]
     w, h = [(40, 28), (41, 27), (38, 30)][seed % 3]
-    text, want, oracle, product = fuzz.run(seed, module, w, h, native=(seed % 4 != 3))
+    text, want, oracle, product = fuzz.run(seed, module, w, h, native=(seed % 4 != 3),
+                                           smooth_in_shader=(seed % 7 == 5 and module in ("bars", "radial", "circle", "graph")))
     assert want.any(), text
     assert np.array_equal(oracle, want), (seed, module, text)
     assert int(np.abs(product.astype(int) - want.astype(int)).max()) <= 1, (seed, module, text)

@@ -60,7 +60,7 @@ def gen(rng, module):
         D("MIN_THICKNESS", num(rng,1,2)); D("MAX_THICKNESS", num(rng,2,6)); D("BASE_COLOR", col(rng)); D("AMPLIFY", num(rng,10,60)); D("OUTLINE", col(rng))
     return "\n".join(L)+"\n"
 
-def run(seed, module, w, h, n=128, native=True):
+def run(seed, module, w, h, n=128, native=True, smooth_in_shader=False):
     rng=np.random.default_rng(seed)
     text=gen(rng, module)
     d=tempfile.mkdtemp()
@@ -70,13 +70,27 @@ def run(seed, module, w, h, n=128, native=True):
         clear=tuple(float(np.float32(v)) for v in rng.uniform(0,1,4))
         rc+='#request setopacity "none"\n#request setbgf %r %r %r %r\n' % clear
     if rng.random()<0.3: rc+="#request setmirror true\n"
+    hdr_extra = {}
+    if smooth_in_shader:
+        # setsmoothpass false: the module shader runs smooth_audio()'s tap loop itself (_PRE_SMOOTHED_AUDIO 0) with the
+        # user's smooth_parameters.glsl
+        sf = float(np.float32(rng.uniform(0.01, 0.05)))
+        sp = "#request setsmoothpass false\n#request setsmoothfactor %r\n" % sf
+        sp += "#define SAMPLE_MODE %s\n#define ROUND_FORMULA %s\n" % (rng.choice(["average", "maximum", "hybrid"]), rng.choice(["sinusoidal", "linear", "circular"]))
+        sp += "#define SAMPLE_SCALE %s\n#define SAMPLE_RANGE %s\n#define SAMPLE_HYBRID_WEIGHT %s\n" % (num(rng, 4, 10), num(rng, 0.5, 0.95, False), num(rng, 0.3, 0.9, False))
+        open(d+"/smooth_parameters.glsl","w").write(sp)
+        hdr_extra = dict(pre_smoothed=0, smooth_factor=sf)
     open(d+"/rc.glsl","w").write(rc); open(f"{d}/{module}.glsl","w").write(text)
     p=g.load_config([d, REF])
     n=p.n
     op=params_from(p)
-    tl=orc.smooth_pass(op,(rng.random(n)**2*65535).astype(np.uint16)); tr=orc.smooth_pass(op,(rng.random(n)**3*65535).astype(np.uint16))
+    if smooth_in_shader:
+        tl=(rng.random(n)**2*65535).astype(np.uint16); tr=(rng.random(n)**3*65535).astype(np.uint16)
+    else:
+        tl=orc.smooth_pass(op,(rng.random(n)**2*65535).astype(np.uint16)); tr=orc.smooth_pass(op,(rng.random(n)**3*65535).astype(np.uint16))
     if module=="wave": tl=np.clip(tl.astype(int)//4+24576,0,65535).astype(np.uint16)
-    hdr=dict(premultiply_alpha=p.premultiply_alpha, channels=p.channels)
+    hdr=dict(premultiply_alpha=p.premultiply_alpha, channels=p.channels, **hdr_extra)
+    assert p.smooth_pass == (0 if smooth_in_shader else 1)
     prog=gi.ModuleProgram(REF, module, w, h, tl, tr, config_dir=d, clear_color=clear, **hdr)
     want=np.array([[prog.pixel(x,y) for x in range(w)] for y in range(h)],np.uint8)
     o=orc.raster(op,tl,tr); e=emul.raster(p,tl,tr)
@@ -88,7 +102,7 @@ if __name__=="__main__":
         module=["bars","radial","circle","graph","wave"][seed%5]
         w,h=[(40,28),(41,27),(38,30)][seed%3]
         try:
-            text,want,o,e=run(seed,module,w,h,native=(seed%4!=3))
+            text,want,o,e=run(seed,module,w,h,native=(seed%4!=3),smooth_in_shader=(seed%7==5 and module in ('bars','radial','circle','graph')))
         except Exception as ex:
             print(seed,module,"EXC",repr(ex)[:300]); bad+=1; continue
         do=(o!=want).any(axis=2).sum(); de=(e!=want).any(axis=2).sum(); lsb=int(np.abs(e.astype(int)-want.astype(int)).max())
