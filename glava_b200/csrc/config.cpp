@@ -472,6 +472,51 @@ static bool apply_request(Loader& L, const std::vector<std::string>& t, const ch
 // switch is sticky for the rest of the including file and inherited by the included one, as in the reference.
 struct IncCtx { std::string cd, cfd, dd; bool has_cfd, has_dd; };
 
+// ---- `#if` / `#ifdef` / `#elif` / `#else` / `#endif` / `#undef` around the `#define`s of a config file ---------------------
+// GLava's own preprocessing (glsl_ext.c) does not look at these — `#request` and `#include` lines act wherever they stand —
+// but the GLSL compiler that later sees the text does, so they decide which `#define` of a user's <module>.glsl counts.
+// Integer expressions as the GLSL preprocessor evaluates them: literals, macros (expanded recursively, undefined -> 0),
+// defined(X) / defined X, ! - + * / % < > <= >= == != && || and parentheses.
+struct IfExpr {
+    const char* s; const Defs* defs; int depth; bool ok;
+    void ws() { while (*s && isspace((unsigned char) *s)) ++s; }
+    bool eat(const char* t) { ws(); size_t n = strlen(t); if (strncmp(s, t, n) == 0) { s += n; return true; } return false; }
+    long primary() {
+        ws();
+        if (eat("(")) { long v = lor(); if (!eat(")")) ok = false; return v; }
+        if (eat("!")) return !primary();
+        if (*s == '-') { ++s; return -primary(); }
+        if (*s == '+') { ++s; return primary(); }
+        if (isdigit((unsigned char) *s)) { char* e; long v = strtol(s, &e, 0); s = e; while (*s == 'u' || *s == 'U') ++s; return v; }
+        if (isalpha((unsigned char) *s) || *s == '_') {
+            std::string id; while (isalnum((unsigned char) *s) || *s == '_') id += *s++;
+            if (id == "defined") {
+                const bool paren = eat("("); ws();
+                std::string name; while (isalnum((unsigned char) *s) || *s == '_') name += *s++;
+                if (paren && !eat(")")) ok = false;
+                return defs->count(name) ? 1 : 0;
+            }
+            auto it = defs->find(id);
+            if (it == defs->end() || depth > 8) return 0;                 // an undefined identifier evaluates to 0
+            const std::string body = strip_bind(it->second);
+            IfExpr sub { body.c_str(), defs, depth + 1, true };
+            long v = sub.lor(); sub.ws();
+            if (!sub.ok || *sub.s) ok = false;                            // e.g. a float or a colour: not an #if operand
+            return v;
+        }
+        ok = false; return 0;
+    }
+    long mul() { long a = primary(); for (;;) { if (eat("*")) a *= primary(); else if (eat("/")) { long b = primary(); if (!b) { ok = false; return 0; } a /= b; }
+                                                 else if (eat("%")) { long b = primary(); if (!b) { ok = false; return 0; } a %= b; } else return a; } }
+    long add() { long a = mul(); for (;;) { ws(); if (*s == '+') { ++s; a += mul(); } else if (*s == '-') { ++s; a -= mul(); } else return a; } }
+    long rel() { long a = add(); for (;;) { if (eat("<=")) a = a <= add(); else if (eat(">=")) a = a >= add(); else if (eat("<")) a = a < add();
+                                             else if (eat(">")) a = a > add(); else return a; } }
+    long eq()  { long a = rel(); for (;;) { if (eat("==")) a = a == rel(); else if (eat("!=")) a = a != rel(); else return a; } }
+    long land() { long a = eq(); while (eat("&&")) { long b = eq(); a = a && b; } return a; }
+    long lor() { long a = land(); while (eat("||")) { long b = land(); a = a || b; } return a; }
+};
+struct CondFrame { bool parent, taken, active; };
+
 // scan a config file: dispatch `#request`s, collect `#define`s (later definitions override,
 // the effect of glsl_ext.c:143-159's auto-#undef), follow `#include`s
 static bool scan_file(Loader& L, const std::string& path, Defs* defs, bool requests, IncCtx ctx, int depth = 0, bool optional = true) {
@@ -485,11 +530,52 @@ static bool scan_file(Loader& L, const std::string& path, Defs* defs, bool reque
     src = strip_comments(src);
     std::istringstream is(src);
     std::string line; int ln = 0;
+    std::vector<CondFrame> cond;                         // conditional nesting of THIS file (an #if cannot span an #include)
+    auto live = [&]() { return cond.empty() || cond.back().active; };
+    auto word = [](const std::string& b, const char* w) {
+        const size_t n = strlen(w);
+        return b.compare(0, n, w) == 0 && (b.size() == n || !(isalnum((unsigned char) b[n]) || b[n] == '_'));
+    };
+    auto eval_if = [&](const std::string& e, bool* out) {
+        if (!defs) { *out = true; return true; }
+        IfExpr x { e.c_str(), defs, 0, true };
+        const long v = x.lor(); x.ws();
+        if (!x.ok || *x.s) { fail(GLAVA_B200_ECONFIG, "[%s:%d] cannot evaluate '#if %s'", path.c_str(), ln, e.c_str()); return false; }
+        *out = v != 0; return true;
+    };
     while (std::getline(is, line)) {
         ++ln;
         std::string t = trim(line);
         if (t.empty() || t[0] != '#') continue;
         std::string body = trim(t.substr(1));
+        if (word(body, "ifdef") || word(body, "ifndef") || word(body, "if")) {
+            bool v = false;
+            if (live()) {
+                if (word(body, "if")) { if (!eval_if(trim(body.substr(2)), &v)) return false; }
+                else {
+                    const bool neg = word(body, "ifndef");
+                    const std::string name = trim(body.substr(neg ? 6 : 5));
+                    v = defs ? ((defs->count(name) != 0) != neg) : true;
+                }
+            }
+            cond.push_back({ live(), v, live() && v });
+            continue;
+        }
+        if (word(body, "elif") || word(body, "else")) {
+            if (cond.empty()) { fail(GLAVA_B200_ECONFIG, "[%s:%d] #%s without #if", path.c_str(), ln, word(body, "else") ? "else" : "elif"); return false; }
+            CondFrame& f = cond.back();
+            bool v = true;
+            if (word(body, "elif") && f.parent && !f.taken) { if (!eval_if(trim(body.substr(4)), &v)) return false; }
+            f.active = f.parent && !f.taken && v;
+            f.taken = f.taken || f.active;
+            continue;
+        }
+        if (word(body, "endif")) {
+            if (cond.empty()) { fail(GLAVA_B200_ECONFIG, "[%s:%d] #endif without #if", path.c_str(), ln); return false; }
+            cond.pop_back();
+            continue;
+        }
+        if (word(body, "undef")) { if (defs && live()) defs->erase(trim(body.substr(5))); continue; }
         if (body.compare(0, 7, "request") == 0 && requests) {
             if (!apply_request(L, tokenize(body.substr(7)), path.c_str(), ln)) return false;
         } else if (body.compare(0, 7, "include") == 0) {
@@ -506,7 +592,7 @@ static bool scan_file(Loader& L, const std::string& path, Defs* defs, bool reque
                 target = target.substr(1); ctx.cd = ctx.dd;
             }
             if (!scan_file(L, ctx.cd + "/" + target, defs, requests, ctx, depth + 1, false)) return false;
-        } else if (body.compare(0, 6, "define") == 0 && defs) {
+        } else if (body.compare(0, 6, "define") == 0 && defs && live()) {
             std::string rest = trim(body.substr(6));
             size_t i = 0; while (i < rest.size() && (isalnum((unsigned char) rest[i]) || rest[i] == '_')) ++i;
             if (i == 0) continue;

@@ -185,3 +185,22 @@ def test_setbg_and_setbgf(tmp_path, built):
     assert list(p.clear_color) == [0.25, 0.5, 0.75, 1.0] and p.premultiply_alpha == 0
     with pytest.raises(g.GlavaError, match="Invalid value for `setbg` request: 'zz0000'"):
         g.load_config(requests=["setbg zz0000"])
+
+
+def test_conditionals_select_defines_but_not_requests(tmp_path, built):
+    """#if / #ifdef / #elif / #else / #endif / #undef are the GLSL compiler's business: they pick among #defines, while
+    glsl_ext.c runs `#request` (and `#include`) lines wherever they stand"""
+    (tmp_path / "rc.glsl").write_text("#request mod graph\n")
+    (tmp_path / "graph.glsl").write_text(
+        "#define MODE 3\n#if MODE == 1\n#define VSCALE 100\n#elif MODE >= 3\n#define VSCALE 250\n#else\n#define VSCALE 1\n#endif\n"
+        "#ifdef NOPE\n#define DRAW_OUTLINE 1\n#request setavgframes 9\n#else\n#define DRAW_OUTLINE 0\n#endif\n"
+        "#define INVERT 1\n#undef INVERT\n#if defined(INVERT) || !defined(MODE)\n#define DIRECTION -1\n#endif\n")
+    p = g.load_config([str(tmp_path)])
+    assert p.graph_vscale == 250 and p.graph_draw_outline == 0 and p.graph_invert == 0 and p.graph_direction == 1
+    assert p.avg_frames == 9                                             # the request inside the dead branch still ran
+    (tmp_path / "graph.glsl").write_text("#if VSCALE >\n#define VSCALE 2\n#endif\n")
+    with pytest.raises(g.GlavaError, match="cannot evaluate '#if VSCALE >'"):
+        g.load_config([str(tmp_path)])
+    (tmp_path / "graph.glsl").write_text("#define VSCALE 2\n#endif\n")
+    with pytest.raises(g.GlavaError, match="#endif without #if"):
+        g.load_config([str(tmp_path)])

@@ -195,6 +195,32 @@ USER_CONFIGS = {
 #define ROTATE (PI / 4)
 #define INVERT 1
 """,
+    "bars:conditionals": """
+#define FANCY 2
+#ifdef FANCY
+#define BAR_WIDTH 3
+#else
+#define BAR_WIDTH 7
+#endif
+#if FANCY > 1 && !defined(NOPE)
+#define BAR_GAP 2
+#elif FANCY == 1
+#define BAR_GAP 5
+#else
+#define BAR_GAP 0
+#endif
+#ifndef AMPLIFY_OVERRIDE
+#undef AMPLIFY
+#define AMPLIFY (FANCY * 15)
+#endif
+#if 0
+#define COLOR #ff0000
+#define BAR_WIDTH 1
+#endif
+#if (FANCY - 2) || defined FANCY
+#define BAR_OUTLINE_WIDTH 0
+#endif
+""",
     "radial:outline": """
 #define C_RADIUS 10
 #define NBARS 20

@@ -150,3 +150,14 @@ def test_include_directory_rules(ref, tmp_path, built):
     # rc.glsl itself is read without a config / defaults dir (render.c:1356-1361): '@' is an error there, ':' is inert
     with pytest.raises(ValueError):
         ref.ext_process(str(user / "rc.glsl"), str(user), None, None or str(user) + "/nonexistent")
+
+
+def test_requests_inside_a_dead_conditional_still_run(ref, tmp_path, built):
+    """glsl_ext.c does not evaluate #if / #ifdef: a `#request` acts wherever it stands; only the #defines are the GLSL
+    compiler's to select — the config reader follows both halves"""
+    (tmp_path / "rc.glsl").write_text("#request mod graph\n")
+    (tmp_path / "graph.glsl").write_text("#ifdef NOPE\n#request setavgframes 9\n#define VSCALE 77\n#endif\n#if 0\n#request setgravitystep 2.5\n#endif\n")
+    text, reqs = ref.ext_process(str(tmp_path / "graph.glsl"), str(tmp_path), None, str(tmp_path))
+    assert ["setavgframes", "9"] in reqs and ["setgravitystep", "2.5"] in reqs and "#ifdef NOPE" in text
+    p = g.load_config([str(tmp_path)])
+    assert p.avg_frames == 9 and p.gravity_step == 2.5 and p.graph_vscale == 300
