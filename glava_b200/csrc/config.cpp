@@ -406,7 +406,13 @@ static bool apply_request(Loader& L, const std::vector<std::string>& t, const ch
     else if (name == "setavgwindow") { if (!need(1) || !as_b(1, &b)) return false; p->avg_window = b; }
     else if (name == "setgravitystep") { if (!need(1)) return false; p->gravity_step = as_f(1); }
     else if (name == "setsmoothpass") { if (!need(1) || !as_b(1, &b)) return false; p->smooth_pass = b; }
-    else if (name == "setsmoothfactor") { if (!need(1)) return false; p->smooth_factor = as_f(1); }
+    else if (name == "setsmoothfactor") {
+        // the shaders never see the request's float: rd_new prints it into the injected header as
+        // "#define _SMOOTH_FACTOR %.6f" (render.c:315-324), so the effective factor is that 6-decimal literal
+        if (!need(1)) return false;
+        char buf[64]; snprintf(buf, sizeof(buf), "%.6f", (double) as_f(1));
+        p->smooth_factor = strtof(buf, nullptr);
+    }
     else if (name == "setfftscale") { if (!need(1)) return false; p->fft_scale = as_f(1); }
     else if (name == "setfftcutoff") { if (!need(1)) return false; p->fft_cutoff = as_f(1); }
     else if (name == "setbufscale") { if (!need(1)) return false; p->bufscale = as_int(1); }          // render.c:1178

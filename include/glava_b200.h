@@ -79,7 +79,8 @@ typedef struct {
     int   accel_fft;          /* setaccelfft      rc.glsl:211 — 0: pipeline A (render.c:2149-2156 float
                                  chain), 1: pipeline B (R16 passes, render.c:2188-2267) */
     int   smooth_pass;        /* setsmoothpass    :78 */
-    float smooth_factor;      /* setsmoothfactor  :72 */
+    float smooth_factor;      /* setsmoothfactor  :72 — as the shaders see it: the "%.6f" literal of the injected
+                                 `#define _SMOOTH_FACTOR` (render.c:315-324); the config reader rounds accordingly */
     float sample_range;       /* #define SAMPLE_RANGE :42 */
     float sample_scale;       /* #define SAMPLE_SCALE :37 */
     float hybrid_weight;      /* #define SAMPLE_HYBRID_WEIGHT :34 */

@@ -204,3 +204,10 @@ def test_conditionals_select_defines_but_not_requests(tmp_path, built):
     (tmp_path / "graph.glsl").write_text("#define VSCALE 2\n#endif\n")
     with pytest.raises(g.GlavaError, match="#endif without #if"):
         g.load_config([str(tmp_path)])
+
+
+def test_setsmoothfactor_is_the_six_decimal_literal_of_the_injected_header(built):
+    """render.c:315-324: the shaders get `#define _SMOOTH_FACTOR %.6f`, not the request's float"""
+    assert g.load_config(requests=["setsmoothfactor 0.0438713878"]).smooth_factor == np.float32("0.043871")
+    assert g.load_config(requests=["setsmoothfactor 0.0123456789"]).smooth_factor == np.float32("0.012346")
+    assert g.load_config().smooth_factor == np.float32(0.025)

@@ -330,3 +330,35 @@ def test_pipeline_b_chain_through_the_reference_pass_shaders(orc, F, win, built)
         got = run(k5, {"tex": gi.Sampler1D(tex), "sz": n, "w": n})                    # K5
         assert np.abs(got.astype(int) - tex_o.astype(int)).max() <= 1, (F, win, u)
         assert (got != tex_o).mean() < 0.02
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SHADERS), reason="reference tree not present")
+def test_k5_random_smooth_parameters_through_smooth_pass_frag(orc, orc_pm, tmp_path, built):
+    """smooth_pass.frag (K5) run from the reference's text with a random user smooth_parameters.glsl and setsmoothfactor,
+    against the oracle and the product arithmetic (direct evaluation and the precomputed tap table): R16 texels within
+    2 / 3 LSB16 (3e-5 / 5e-5 of full scale; the serial tap sums round differently by an ulp here and there)"""
+    from oracle import glsl_interp as gi
+    from tests import emul
+    rng = np.random.default_rng(31)
+    n = 256
+    for trial in range(10):
+        mode = str(rng.choice(["average", "maximum", "hybrid"])); formula = str(rng.choice(["sinusoidal", "linear"]))
+        scale, rng_, hyb = float(np.float32(rng.uniform(4, 10))), float(np.float32(rng.uniform(0.5, 0.95))), float(np.float32(rng.uniform(0.3, 0.9)))
+        # (a window narrower than one texel gives weight 0 and the shader returns 0 / 0: which texels hit that knife edge
+        # depends on the last ulp of log() — any two GL implementations disagree there; the draw stays clear of it)
+        sf = float(np.float32(rng.uniform(0.025, 0.06)))
+        user = tmp_path / f"u{trial}"
+        user.mkdir()
+        (user / "rc.glsl").write_text("#request setbufsize 256\n")
+        (user / "smooth_parameters.glsl").write_text(      # (a setsmoothfactor in rc.glsl would lose to smooth_parameters.glsl:72)
+            f"#request setsmoothfactor {sf!r}\n#define SAMPLE_MODE {mode}\n#define ROUND_FORMULA {formula}\n#define SAMPLE_SCALE {scale!r}\n"
+            f"#define SAMPLE_RANGE {rng_!r}\n#define SAMPLE_HYBRID_WEIGHT {hyb!r}\n")
+        p = g.load_config([str(user), REF_SHADERS])
+        p.n = n
+        assert (p.sample_mode, p.round_formula) == (MODES[mode], FORMULAS[formula]) and p.smooth_factor == np.float32("%.6f" % sf)      # `#define _SMOOTH_FACTOR %.6f`
+        tex = (rng.random(n) ** 2 * 65535).astype(np.uint16)
+        sh = gi.load_stage(os.path.join(REF_SHADERS, "util", "smooth_pass.frag"), REF_SHADERS, None, config_dir=str(user), smooth_factor=sf)
+        want = np.array([gi.unorm16(sh.run({"tex": gi.Sampler1D(tex), "sz": n, "w": n}, x, 0)["fragment"].v[0]) for x in range(n)], np.uint16)
+        assert want.any()
+        assert _lsb(orc.smooth_pass(params_from(p), tex), want) <= 2, (trial, mode, formula)
+        assert _lsb(emul.smooth(p, tex), want) <= 3 and _lsb(emul.k5_table(p, tex), want) <= 3, (trial, mode, formula)
