@@ -21,8 +21,9 @@ def fuzz(built):
 
 
 # 207 / 267: circle, C_SMOOTH 0, non-native opacity (the pass-through stage 2); 131: a 1-LSB radial pixel; 5 / 12 / 26 / 33:
-# setsmoothpass false with a random smooth_parameters.glsl (the tap loop runs in the module shader); the rest: a spread
-@pytest.mark.parametrize("seed", [207, 267, 131, 5, 12, 26, 33] + list(range(40, 66)))
+# setsmoothpass false with a random smooth_parameters.glsl (the tap loop runs in the module shader); 166 / 586 / 803 / 985:
+# the same with a smooth factor whose "%.6f" header literal differs from the request's float; the rest: a spread
+@pytest.mark.parametrize("seed", [207, 267, 131, 5, 12, 26, 33, 166, 586, 803, 985] + list(range(40, 66)))
 def test_random_module_config(fuzz, seed):
     module = ["bars", "radial", "circle", "graph", "wave"][seed % 5]
     w, h = [(40, 28), (41, 27), (38, 30)][seed % 3]

@@ -10,7 +10,8 @@ colours, every option flag), sometimes `setopacity "none"` with a random `setbgf
     python tools/fuzz_module_configs.py 0 200        # seeds [0, 200)
 
 Found with it: circle/2.frag is a pass-through, not a disabled stage, when C_SMOOTH is 0 (one more blend in non-native
-opacity).  tests/test_module_config_fuzz.py runs a fixed slice of seeds in the CPU tier."""
+opacity), and setsmoothfactor reaches the shaders as the "%.6f" literal of the injected header.
+tests/test_module_config_fuzz.py runs a fixed slice of seeds in the CPU tier."""
 import os
 import sys
 import tempfile
