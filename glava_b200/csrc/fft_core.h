@@ -22,8 +22,12 @@
 
 #if defined(__CUDACC__)
 #define GLB_HD __host__ __device__ __forceinline__
+// the rarely-taken heavy paths (colour-program interpreter, graph anti-alias walks, the generic per-pixel dispatcher): real
+// calls on the device, so that the fallback kernels do not inline several copies of them (compile time, code size)
+#define GLB_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define GLB_HD inline
+#define GLB_HD_NOINLINE static inline
 #endif
 
 namespace glb {

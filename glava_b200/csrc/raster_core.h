@@ -40,7 +40,7 @@ GLB_HD float cop_smoothstep(float e0, float e1, float x) {
     return (t * t) * (3.0f - (2.0f * t));
 }
 GLB_HD float& cop_lane(f4& r, int k) { return k == 0 ? r.r : (k == 1 ? r.g : (k == 2 ? r.b : r.a)); }
-GLB_HD f4 eval_color_prog(const glava_b200_color_prog& c, float x) {
+GLB_HD_NOINLINE f4 eval_color_prog(const glava_b200_color_prog& c, float x) {
     f4 reg[GLAVA_B200_COLOR_REGS];
     for (int i = 0; i < GLAVA_B200_COLOR_REGS; ++i) reg[i] = mk4(0.0f, 0.0f, 0.0f, 0.0f);
     const int n = c.n_ops < GLAVA_B200_COLOR_OPS ? c.n_ops : GLAVA_B200_COLOR_OPS;
@@ -545,7 +545,7 @@ template <bool NATIVE> struct GraphCols {            // heights of columns x-2 .
         return y;
     }
 };
-template <bool NATIVE> GLB_HD uint32_t graph_px_aa(const glava_b200_params& p, const AudioTex& t, int x, int y) {
+template <bool NATIVE> GLB_HD_NOINLINE uint32_t graph_px_aa(const glava_b200_params& p, const AudioTex& t, int x, int y) {
     GraphCols<NATIVE> c = { p, x, { 0.0f, 0.0f, 0.0f, 0.0f, 0.0f } };
     for (int k = 0; k < 5; ++k) { const int col = x - 2 + k; if (col >= 0 && col < p.w) c.h5[k] = graph_height_any(p, t, col); }
     const float X = (float) x + 0.5f, Y = (float) y + 0.5f;               // default (half-integer) gl_FragCoord
@@ -658,7 +658,7 @@ GLB_HD uint32_t test_px(const glava_b200_params& p) {
 }
 
 // generic per-pixel dispatcher
-GLB_HD uint32_t module_px(const glava_b200_params& p, const AudioTex& t, int x, int y) {
+GLB_HD_NOINLINE uint32_t module_px(const glava_b200_params& p, const AudioTex& t, int x, int y) {
     switch (p.module) {
         case GLAVA_B200_MOD_BARS:   return bars_px(p, t, x, y);
         case GLAVA_B200_MOD_RADIAL: return radial_px(p, t, x, y);
