@@ -257,6 +257,7 @@ struct glava_b200_fifo {
     std::vector<int> fds;
     std::vector<std::vector<unsigned char>> pend;   // bytes read so far towards each stream's next chunk
     std::vector<size_t> have;
+    std::vector<char> awaited;           // delivered in the previous tick (or never ticked yet): this tick waits for it
     std::vector<pollfd> pfds;
     std::vector<int> pmap;
     int timeout_ms;
@@ -275,7 +276,7 @@ extern "C" glava_b200_fifo* glava_b200_fifo_open(const char* const* sources, int
     glava_b200_fifo* f = new glava_b200_fifo();
     f->batch = batch; f->chunk_bytes = samplesz;
     f->timeout_ms = 50; f->measured = false; f->last = timespec{}; f->staging[0] = f->staging[1] = nullptr; f->cur = 0;
-    f->fds.assign(batch, -1); f->have.assign(batch, 0);
+    f->fds.assign(batch, -1); f->have.assign(batch, 0); f->awaited.assign(batch, 1);
     f->pend.assign(batch, std::vector<unsigned char>(samplesz, 0));
     for (int s = 0; s < batch; ++s) {
         const char* path = sources[s] ? sources[s] : "/tmp/mpd.fifo";                 // fifo.c:24-26
@@ -295,26 +296,35 @@ extern "C" int glava_b200_fifo_gather(glava_b200_fifo* f, int16_t* chunks, uint8
     if (!f || !chunks) return fail(GLAVA_B200_EINVAL, "glava_b200_fifo_gather: null argument");
     timespec start; clock_gettime(CLOCK_MONOTONIC, &start);
     const size_t cb = f->chunk_bytes;
-    int complete = 0;
-    for (int s = 0; s < f->batch; ++s) complete += f->have[s] == cb ? 1 : 0;
-    while (complete < f->batch) {
-        // drain what is readable right now
+    // A tick waits only for the streams that delivered in the previous tick: a stream that has gone silent costs one
+    // deadline, after that it contributes zeros without holding the others up (in the reference every stream has its own
+    // thread and its own timeout); it rejoins as soon as a whole chunk of it is readable.  If nobody delivered last time,
+    // everybody is awaited.
+    bool any_awaited = false;
+    for (int s = 0; s < f->batch; ++s) any_awaited |= f->awaited[s] != 0;
+    auto pending = [&]() {
+        int n = 0;
+        for (int s = 0; s < f->batch; ++s) n += ((f->awaited[s] || !any_awaited) && f->have[s] < cb) ? 1 : 0;
+        return n;
+    };
+    for (;;) {
+        // drain what is readable right now (every stream, awaited or not)
         bool progress = false;
         for (int s = 0; s < f->batch; ++s) {
             while (f->have[s] < cb) {
                 const ssize_t got = read(f->fds[s], f->pend[s].data() + f->have[s], cb - f->have[s]);
-                if (got > 0) { f->have[s] += (size_t) got; progress = true; if (f->have[s] == cb) ++complete; }
+                if (got > 0) { f->have[s] += (size_t) got; progress = true; }
                 else break;                                   // 0: no writer (yet); -1/EAGAIN: empty
             }
         }
-        if (complete == f->batch) break;
+        if (pending() == 0) break;
         timespec now; clock_gettime(CLOCK_MONOTONIC, &now);
         const long left = f->timeout_ms - elapsed_ms(start, now);
         if (left <= 0) break;
         if (progress) continue;
         f->pfds.clear(); f->pmap.clear();
         for (int s = 0; s < f->batch; ++s)
-            if (f->have[s] < cb) { f->pfds.push_back(pollfd{ f->fds[s], POLLIN, 0 }); f->pmap.push_back(s); }
+            if ((f->awaited[s] || !any_awaited) && f->have[s] < cb) { f->pfds.push_back(pollfd{ f->fds[s], POLLIN, 0 }); f->pmap.push_back(s); }
         const int pr = poll(f->pfds.data(), (nfds_t) f->pfds.size(), (int) left);
         if (pr < 0 && errno != EINTR) return fail(GLAVA_B200_ECONFIG, "FIFO backend: poll() failed (%s)", strerror(errno));
         if (pr > 0) {
@@ -333,6 +343,7 @@ extern "C" int glava_b200_fifo_gather(glava_b200_fifo* f, int16_t* chunks, uint8
         const bool ok = f->have[s] == cb;
         if (ok) { memcpy(out, f->pend[s].data(), cb); f->have[s] = 0; ++delivered; }
         else memset(out, 0, cb);                              // fifo.c:67-79: silence slides zeros in
+        f->awaited[s] = ok ? 1 : 0;
         if (fresh) fresh[s] = ok ? 1 : 0;
     }
     if (delivered > 0) {                                      // fifo.c:82-87: deadline follows the producer's cadence

@@ -85,7 +85,9 @@ glava_b200_fifo* glava_b200_fifo_open(const char* const* sources, int batch, siz
 /* One tick.  chunks: [batch][samplesz / 2] int16 (interleaved L,R; samplesz / 4 frames per stream).  Waits until
  * every stream has a whole chunk or the deadline passes — 50 ms at first, then the measured time between the last
  * two ticks that carried data + 1 ms (fifo.c:40,82-87).  Streams without a whole chunk get zeros (their partial
- * bytes stay queued for the next tick); fresh (may be NULL) receives one 0/1 byte per stream.
+ * bytes stay queued for the next tick); fresh (may be NULL) receives one 0/1 byte per stream.  Only streams that
+ * delivered in the previous tick are waited for (a stream that went silent costs one deadline, then it stops holding
+ * the batch up — the reference gives every stream its own thread and timeout — and rejoins when it has a chunk).
  * Returns the number of streams that delivered data, or a negative GLAVA_B200_E* (poll failure). */
 int glava_b200_fifo_gather(glava_b200_fifo* f, int16_t* chunks, uint8_t* fresh);
 int glava_b200_fifo_timeout_ms(const glava_b200_fifo* f);       /* current deadline length */

@@ -266,3 +266,33 @@ def test_batch_feeder_collect_copies_only_modified_streams(built):
         assert np.array_equal(lb[1], l1) and np.array_equal(rb[1], r1) and (lb[0] == 7).all() and (rb[2] == 8).all()
         assert not ab.collect(lb, rb).any()                                              # the flag was cleared (glava.c:535)
         assert ab.stream(2).rate == 22050 and ab.stream(2).source == b"stream-2"
+
+
+def test_a_silent_stream_costs_one_deadline_then_stops_holding_the_batch_up(built, tmp_path):
+    """every stream of the reference has its own thread and timeout; in the batched gather a stream that went silent is
+    awaited for one deadline and then contributes zeros without delaying the others — and rejoins when it has a chunk"""
+    batch, samplesz, ticks = 3, 512, 12
+    paths = _pipes(tmp_path, batch)
+    rng = np.random.default_rng(8)
+    sent = rng.integers(-32768, 32767, size=(ticks, 2, samplesz // 2), dtype=np.int16)
+    with audio.FifoReader(paths, samplesz) as fr:
+        fds = [os.open(p, os.O_WRONLY) for p in paths]
+        try:
+            for s in range(2):
+                os.write(fds[s], sent[:, s].tobytes())                   # streams 0 and 1: all their chunks queued; 2: nothing
+            t0 = time.time()
+            chunks, fresh = fr.gather()                                  # first tick: everybody is awaited -> one full deadline
+            first = time.time() - t0
+            assert fresh.tolist() == [True, True, False] and 0.045 <= first < 1.0
+            for t in range(1, ticks - 1):
+                t0 = time.time()
+                chunks, fresh = fr.gather()
+                assert time.time() - t0 < 0.03, t                        # no waiting for the silent stream any more
+                assert fresh.tolist() == [True, True, False] and np.array_equal(chunks[:2], sent[t]) and not chunks[2].any()
+            late = rng.integers(-32768, 32767, samplesz // 2, dtype=np.int16)
+            os.write(fds[2], late.tobytes())                             # the silent stream comes back
+            chunks, fresh = fr.gather()
+            assert fresh.all() and np.array_equal(chunks[2], late) and np.array_equal(chunks[:2], sent[ticks - 1])
+        finally:
+            for fd in fds:
+                os.close(fd)
