@@ -11,7 +11,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 
 @pytest.mark.parametrize("module", ["bars", "radial", "graph", "wave", "circle"])
 def test_pipe_apply_recolours_a_running_renderer(orc_pm, built, module):
-    n, w, h = 1024, 256, 192
+    n, (w, h) = 1024, ((640, 480) if module in ("radial", "circle") else (256, 192))     # C_RADIUS 128 needs the room
     req = [f"setbufsize {n}", f"setgeometry 0 0 {w} {h}"]
     rng = np.random.default_rng(8)
     with g.Pipe(["fg", "bg"], requests=req, force_module=module) as pipe:
