@@ -31,6 +31,25 @@ static float hex_channel(unsigned v) {
     snprintf(buf, sizeof(buf), "%.6f", (double) ((float) v / (float) 255));
     return strtof(buf, nullptr);
 }
+// ext_parse_color with two digits per component (glsl_ext.c:88-122) as `setbg` and the `--pipe` colour values use it: optional
+// `0x`, up to 8 hex digits, each complete pair sets one component to e / 255 (no "%.6f" detour), components the string does
+// not reach keep their value, a trailing odd digit is dropped; false on a non-hex character.
+bool parse_hex_components(const char* s, float* out[4]) {
+    size_t len = strlen(s);
+    if (len >= 2 && s[0] == '0' && (s[1] == 'x' || s[1] == 'X')) { s += 2; len -= 2; }
+    unsigned acc = 0; int have = 0, comp = 0;
+    for (size_t k = 0; k < len && k < 8; ++k) {
+        const char c = s[k];
+        unsigned v;
+        if (c >= 'a' && c <= 'f') v = (unsigned) (c - 'a') + 10;
+        else if (c >= 'A' && c <= 'F') v = (unsigned) (c - 'A') + 10;
+        else if (c >= '0' && c <= '9') v = (unsigned) (c - '0');
+        else return false;
+        acc = (acc << 4) | v;
+        if (++have == 2) { *out[comp++] = (float) acc / (float) 255; acc = 0; have = 0; }
+    }
+    return true;
+}
 bool parse_hex_color(const char* s, float out[4], bool literal_rounding) {
     if (s[0] == '#') ++s;
     if (s[0] == '0' && (s[1] == 'x' || s[1] == 'X')) s += 2;             // glsl_ext.c:92-95
@@ -438,18 +457,10 @@ static bool apply_request(Loader& L, const std::vector<std::string>& t, const ch
         // ext_parse_color (glsl_ext.c:88-122): two hex digits per component, optional 0x, up to 8 digits; components the
         // string does not reach keep their value (`setbg ff0000` leaves the alpha at its default 0)
         if (!need(1)) return false;
-        const char* h = t[1].c_str();
-        size_t len = strlen(h);
-        if (len >= 2 && h[0] == '0' && (h[1] == 'x' || h[1] == 'X')) { h += 2; len -= 2; }
-        unsigned acc = 0; int have = 0, comp = 0;
-        for (size_t k = 0; k < len && k < 8; ++k) {
-            const char c = h[k]; unsigned v;
-            if (c >= 'a' && c <= 'f') v = (unsigned) (c - 'a') + 10;
-            else if (c >= 'A' && c <= 'F') v = (unsigned) (c - 'A') + 10;
-            else if (c >= '0' && c <= '9') v = (unsigned) (c - '0');
-            else { fail(GLAVA_B200_ECONFIG, "Invalid value for `setbg` request: '%s'", t[1].c_str()); return false; }
-            acc = (acc << 4) | v;
-            if (++have == 2) { p->clear_color[comp++] = (float) acc / (float) 255; acc = 0; have = 0; }
+        float* comp[4] = { &p->clear_color[0], &p->clear_color[1], &p->clear_color[2], &p->clear_color[3] };
+        if (!parse_hex_components(t[1].c_str(), comp)) {
+            fail(GLAVA_B200_ECONFIG, "Invalid value for `setbg` request: '%s'", t[1].c_str());
+            return false;
         }
     }
     else if (name == "setbgf") {                                           // render.c:1092-1099

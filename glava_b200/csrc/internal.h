@@ -19,6 +19,7 @@ void fill_defaults(glava_b200_params* p, int module);
 int  module_from_name(const char* name);
 const char* module_name(int id);
 bool parse_hex_color(const char* s, float out[4], bool literal_rounding);
+bool parse_hex_components(const char* s, float* out[4]);
 int  load_config(glava_b200_params* out, const char* const* paths, const char* entry,
                  const char* const* requests, const char* force_module, const char* const* binds);
 int  validate_params(const glava_b200_params* p);

@@ -29,24 +29,6 @@ struct Bind {
     bool b; int i; float f[4];      // value the uniform holds
 };
 
-// hex digits -> colour components, two digits per component, up to 8 digits; `0x` prefix ignored.  Components the string
-// does not reach keep their value.  (ext_parse_color with elem_sz 2.)
-bool hex_components(const char* s, float* out[4]) {
-    size_t len = strlen(s);
-    if (len >= 2 && s[0] == '0' && (s[1] == 'x' || s[1] == 'X')) { s += 2; len -= 2; }
-    unsigned acc = 0; int have = 0, comp = 0;
-    for (size_t t = 0; t < len && t < 8; ++t) {
-        const char c = s[t];
-        unsigned v;
-        if (c >= 'a' && c <= 'f') v = (unsigned) (c - 'a') + 10;
-        else if (c >= 'A' && c <= 'F') v = (unsigned) (c - 'A') + 10;
-        else if (c >= '0' && c <= '9') v = (unsigned) (c - '0');
-        else return false;
-        acc = (acc << 4) | v;
-        if (++have == 2) { *out[comp++] = (float) acc / (float) 255; acc = 0; have = 0; }
-    }
-    return true;
-}
 }  // namespace
 
 struct glava_b200_pipe {
@@ -157,7 +139,7 @@ static int pipe_line(glava_b200_pipe* p, std::string text) {
             if (v[0] == '#') {
                 p->parsed.f[0] = p->parsed.f[1] = p->parsed.f[2] = 0.0f; p->parsed.f[3] = 1.0f;
                 float* ptrs[4] = { &p->parsed.f[0], &p->parsed.f[1], &p->parsed.f[2], &p->parsed.f[3] };
-                if (hex_components(v + 1, ptrs)) ready = true;
+                if (parse_hex_components(v + 1, ptrs)) ready = true;
                 else fail(GLAVA_B200_ECONFIG, "Bad format for color string: \"%s\"", v);
             } else ready = EOF != sscanf(v, "%f,%f,%f,%f", &p->parsed.f[0], &p->parsed.f[1], &p->parsed.f[2], &p->parsed.f[3]);
             break;
