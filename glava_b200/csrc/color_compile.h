@@ -6,8 +6,8 @@
 // eval_color_prog() runs (on the device when the row-colour tables / the polar geometry cache are built, per pixel in
 // the generic kernels).  Supported: the per-pixel variable (`d`; `pos` in graph), int / float literals, `#rrggbb[aa]`,
 // other object-like config macros (expanded textually, as the preprocessor does), + - * / and unary minus, swizzles,
-// vec2 / vec3 / vec4 / float constructors, and mix clamp smoothstep min max mod step abs floor ceil fract sqrt sin cos log
-// sign.  Integer sub-expressions are folded with C semantics (`1 / 2` is 0) and convert to float where they meet one.
+// vec2 / vec3 / vec4 / float constructors, comparisons, && || ! and ?: on scalars, `true` / `false`, and mix clamp smoothstep
+// min max mod step abs floor ceil fract sqrt sin cos log sign.  Integer sub-expressions are folded with C semantics (`1 / 2` is 0) and convert to float where they meet one.
 // Anything else is a config error naming the offending token.
 #ifndef GLAVA_B200_COLOR_COMPILE_H
 #define GLAVA_B200_COLOR_COMPILE_H
@@ -72,7 +72,11 @@ struct ColorCompiler {
                 size_t j = i + 1; while (j < s.size() && isxdigit((unsigned char) s[j]) && j - i - 1 < 8) ++j;
                 out->push_back({ 'h', s.substr(i, j - i) }); i = j; continue;
             }
-            if (strchr("()+-*/,.", c)) { out->push_back({ 'p', std::string(1, c) }); ++i; continue; }
+            if (i + 1 < s.size()) {
+                const std::string two = s.substr(i, 2);
+                if (two == "<=" || two == ">=" || two == "==" || two == "!=" || two == "&&" || two == "||") { out->push_back({ 'p', two }); i += 2; continue; }
+            }
+            if (strchr("()+-*/,.<>!?:", c)) { out->push_back({ 'p', std::string(1, c) }); ++i; continue; }
             return fail_at(std::string("unexpected character '") + c + "'");
         }
         return true;
@@ -104,7 +108,80 @@ struct ColorCompiler {
     }
 
     // ---- parser ----------------------------------------------------------------------------------------------------
+    // precedence, lowest first: ?:  ||  &&  == !=  < > <= >=  + -  * /  unary  postfix
     bool expr(Val* out) {
+        if (!lor(out)) return false;
+        if (!eat("?")) return true;
+        Val a, b;
+        if (!expr(&a)) return false;
+        if (!eat(":")) return fail_at("expected ':'");
+        if (!expr(&b)) return false;
+        if (out->reg < 0) {                                   // constant condition: the branch is chosen here
+            const bool take_a = out->ival != 0;
+            release(take_a ? b : a); *out = take_a ? a : b;
+            return true;
+        }
+        if (out->width != 1) return fail_at("the condition of ?: is not a scalar");
+        if (!materialise(&a) || !materialise(&b)) return false;
+        if (a.width != b.width) return fail_at("the branches of ?: have different types");
+        if (!emit(GLAVA_B200_COP_SELECT, a.reg, a.reg, b.reg, (float) out->reg)) return false;
+        release(*out); release(b);
+        *out = a;
+        return true;
+    }
+    bool logic(int op, Val* l, Val r) {                       // && ||: folded when both sides are constants
+        if (l->reg < 0 && r.reg < 0) { l->ival = op == GLAVA_B200_COP_AND ? (l->ival && r.ival) : (l->ival || r.ival); return true; }
+        if (!materialise(l) || !materialise(&r)) return false;
+        if (l->width != 1 || r.width != 1) return fail_at("&& / || on a vector");
+        if (!emit(op, l->reg, l->reg, r.reg, 0.0f)) return false;
+        release(r);
+        return true;
+    }
+    bool lor(Val* out) {
+        if (!land(out)) return false;
+        while (eat("||")) { Val r; if (!land(&r) || !logic(GLAVA_B200_COP_OR, out, r)) return false; }
+        return true;
+    }
+    bool land(Val* out) {
+        if (!equality(out)) return false;
+        while (eat("&&")) { Val r; if (!equality(&r) || !logic(GLAVA_B200_COP_AND, out, r)) return false; }
+        return true;
+    }
+    bool compare(const char* op, Val* l, Val r) {
+        const std::string o = op;
+        if (l->reg < 0 && r.reg < 0) {
+            const long a = l->ival, b = r.ival;
+            l->ival = o == "<" ? a < b : o == ">" ? a > b : o == "<=" ? a <= b : o == ">=" ? a >= b : o == "==" ? a == b : a != b;
+            return true;
+        }
+        if (!materialise(l) || !materialise(&r)) return false;
+        if (l->width != 1 || r.width != 1) return fail_at(std::string("'") + op + "' on a vector");
+        const bool swap = o == ">" || o == ">=";
+        const int code = (o == "<" || o == ">") ? GLAVA_B200_COP_LT : (o == "<=" || o == ">=") ? GLAVA_B200_COP_LE
+                       : o == "==" ? GLAVA_B200_COP_EQ : GLAVA_B200_COP_NE;
+        if (!emit(code, l->reg, swap ? r.reg : l->reg, swap ? l->reg : r.reg, 0.0f)) return false;
+        release(r);
+        return true;
+    }
+    bool equality(Val* out) {
+        if (!relational(out)) return false;
+        for (;;) {
+            const char* op = is_p("==") ? "==" : is_p("!=") ? "!=" : nullptr;
+            if (!op) return true;
+            ++pos;
+            Val r; if (!relational(&r) || !compare(op, out, r)) return false;
+        }
+    }
+    bool relational(Val* out) {
+        if (!additive(out)) return false;
+        for (;;) {
+            const char* op = is_p("<=") ? "<=" : is_p(">=") ? ">=" : is_p("<") ? "<" : is_p(">") ? ">" : nullptr;
+            if (!op) return true;
+            ++pos;
+            Val r; if (!additive(&r) || !compare(op, out, r)) return false;
+        }
+    }
+    bool additive(Val* out) {
         if (!term(out)) return false;
         for (;;) {
             int op;
@@ -141,6 +218,11 @@ struct ColorCompiler {
             return emit(GLAVA_B200_COP_NEG, out->reg, out->reg, 0, 0.0f);
         }
         if (eat("+")) return unary(out);
+        if (eat("!")) {
+            if (!unary(out)) return false;
+            if (out->reg < 0) { out->ival = !out->ival; return true; }
+            return emit(GLAVA_B200_COP_NOT, out->reg, out->reg, 0, 0.0f);
+        }
         if (!primary(out)) return false;
         while (is_p(".")) {                                  // swizzle
             ++pos;
@@ -219,6 +301,7 @@ struct ColorCompiler {
             *out = { r, 1, false, 0 };
             return emit(GLAVA_B200_COP_VAR, r, 0, 0, 0.0f);
         }
+        if (id == "true" || id == "false") { *out = { -1, 1, true, id == "true" ? 1 : 0 }; return true; }
         if (id == "PI" || id == "TWOPI") {                    // bars/1.frag:33-34 etc.: literals of the module shaders
             const int r = alloc(); if (r < 0) return false;
             *out = { r, 1, false, 0 };

@@ -82,6 +82,14 @@ GLB_HD_NOINLINE f4 eval_color_prog(const glava_b200_color_prog& c, float x) {
             case GLAVA_B200_COP_MIX:   GLB_COP3((v * (1.0f - u)) + (w * u));
             case GLAVA_B200_COP_CLAMP: GLB_COP3(g_min(g_max(v, w), u));
             case GLAVA_B200_COP_SMOOTHSTEP: GLB_COP3(cop_smoothstep(v, w, u));
+            case GLAVA_B200_COP_LT:    GLB_COP2(v < w ? 1.0f : 0.0f);
+            case GLAVA_B200_COP_LE:    GLB_COP2(v <= w ? 1.0f : 0.0f);
+            case GLAVA_B200_COP_EQ:    GLB_COP2(v == w ? 1.0f : 0.0f);
+            case GLAVA_B200_COP_NE:    GLB_COP2(v != w ? 1.0f : 0.0f);
+            case GLAVA_B200_COP_AND:   GLB_COP2((v != 0.0f && w != 0.0f) ? 1.0f : 0.0f);
+            case GLAVA_B200_COP_OR:    GLB_COP2((v != 0.0f || w != 0.0f) ? 1.0f : 0.0f);
+            case GLAVA_B200_COP_NOT:   GLB_COP1(v != 0.0f ? 0.0f : 1.0f);
+            case GLAVA_B200_COP_SELECT: GLB_COP3(u != 0.0f ? v : w);
             default: break;
         }
     }

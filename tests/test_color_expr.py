@@ -95,7 +95,9 @@ def test_textual_macro_expansion_and_integer_folding(tmp_path, built):
     ("#define COLOR vec3(d, 0, 0)", "not a vec4"),
     ("#define COLOR vec4(d, 0, 0)", "component count mismatch"),
     ("#define COLOR vec4(1, 0, 0, 1) + vec2(d)", "different vector sizes"),
-    ("#define COLOR vec4(d > 1 ? 1 : 0, 0, 0, 1)", "unexpected character '>'"),
+    ("#define COLOR vec4(d % 2, 0, 0, 1)", "unexpected character '%'"),
+    ("#define COLOR vec4(1) > vec4(0) ? vec4(1) : vec4(0)", "'>' on a vector"),
+    ("#define COLOR d > 1 ? vec4(1) : vec3(0)", "have different types"),
     ("#define COLOR vec4(d.y, 0, 0, 1)", "swizzle '.y' out of range"),
     ("#define COLOR vec4(1 / 0, d, 0, 1)", "integer division by zero"),
 ])
@@ -135,7 +137,7 @@ class _Gen:
     def scalar(self, depth):
         if depth <= 0:
             return "d" if self.r.random() < 0.4 else self.lit()
-        k = self.r.integers(0, 12)
+        k = self.r.integers(0, 13)
         a, b = self.scalar(depth - 1), self.scalar(depth - 1)
         if k == 0: return f"({a} + {b})"
         if k == 1: return f"({a} - {b})"
@@ -148,6 +150,11 @@ class _Gen:
         if k == 8: return f"sqrt(abs({self.fl(a)}) + 0.125)"
         if k == 9: return f"{self.vec(int(self.r.integers(2, 5)), depth - 1)}.{self.r.choice(['x', 'g', 'y', 'r'])}"
         if k == 10: return f"smoothstep(0.5, 2.5, {self.fl(a)})"
+        if self.r.random() < 0.5:
+            c, e = self.scalar(depth - 1), self.scalar(depth - 1)
+            cond = self.r.choice([f"{a} {self.r.choice(['<', '>', '<=', '>=', '==', '!='])} {b}",
+                                  f"({a} < {b} && {c} >= 1) || !({e} > 2)", f"!({a} <= {b})", "true", "2 > 3"])
+            return f"(({cond}) ? {self.fl(c)} : {self.fl(e)})"
         return f"mod({self.fl(a)}, 1.75)"
 
     def fl(self, e):
