@@ -59,7 +59,9 @@ void* fifo_entry(void* data) {
     audio_data* audio = (audio_data*) data;
     const size_t hop = audio->sample_sz / 4;                 // frames per ring update
     std::vector<int16_t> buf(hop * 2, 0);                    // one read() worth: sample_sz / 2 int16 (fifo.c:38)
-    int fd = open(audio->source, O_RDONLY);
+    // O_NONBLOCK: the reference's open() blocks until a writer appears, which also makes its thread unjoinable until then;
+    // here a FIFO without a writer simply reads as silence (zero slides at the poll cadence, on rings that are zero anyway)
+    int fd = open(audio->source, O_RDONLY | O_NONBLOCK);
     if (fd == -1) {
         // the reference exit()s here (fifo.c:45-48); a library reports through the abort hook and ends the thread
         fail(GLAVA_B200_ECONFIG, "failed to open FIFO audio source \"%s\": %s", audio->source, strerror(errno));
@@ -69,6 +71,7 @@ void* fifo_entry(void* data) {
     int timeout = 50;
     timespec last = {}, now = {};
     bool measured = false;
+    auto silence = [&]() { ring_push(audio, hop, [](size_t, float* l, float* r) { *l = 0.0f; *r = 0.0f; }); };
     while (true) {
         const int pr = poll(&pfd, 1, timeout);
         if (pr < 0) {
@@ -77,21 +80,28 @@ void* fifo_entry(void* data) {
             break;
         }
         if (pr == 0) {
-            ring_push(audio, hop, [](size_t, float* l, float* r) { *l = 0.0f; *r = 0.0f; });
+            silence();
         } else {
             // one read per wake-up, whatever it returns; a short read leaves the tail of `buf` as it was (fifo.c:81)
-            ssize_t got = read(fd, buf.data(), buf.size() * sizeof(int16_t));
-            (void) got;
-            clock_gettime(CLOCK_REALTIME, measured ? &now : &last);
-            if (measured) { timeout = (int) elapsed_ms(last, now) + 1; last = now; }
-            else measured = true;
-            const int channels = audio->channels;
-            const int16_t* in = buf.data();
-            ring_push(audio, hop, [in, channels](size_t i, float* l, float* r) {
-                const int a = in[2 * i], b = in[2 * i + 1];
-                if (channels == 1) { const float m = (float) ((a + b) / 2) / (float) 65535; *l = m; *r = m; }
-                else if (channels == 2) { *l = (float) a / (float) 65535; *r = (float) b / (float) 65535; }
-            });
+            const ssize_t got = read(fd, buf.data(), buf.size() * sizeof(int16_t));
+            if (got <= 0) {
+                // every writer has gone (POLLHUP, read() == 0).  The reference spins here, sliding its stale buffer in at
+                // full speed; this backend treats it as silence at the poll cadence instead
+                timespec nap = { timeout / 1000, (long) (timeout % 1000) * 1000000L };
+                nanosleep(&nap, nullptr);
+                silence();
+            } else {
+                clock_gettime(CLOCK_REALTIME, measured ? &now : &last);
+                if (measured) { timeout = (int) elapsed_ms(last, now) + 1; last = now; }
+                else measured = true;
+                const int channels = audio->channels;
+                const int16_t* in = buf.data();
+                ring_push(audio, hop, [in, channels](size_t i, float* l, float* r) {
+                    const int a = in[2 * i], b = in[2 * i + 1];
+                    if (channels == 1) { const float m = (float) ((a + b) / 2) / (float) 65535; *l = m; *r = m; }
+                    else if (channels == 2) { *l = (float) a / (float) 65535; *r = (float) b / (float) 65535; }
+                });
+            }
         }
         if (__atomic_load_n(&audio->terminate, __ATOMIC_SEQ_CST) == 1) break;
     }

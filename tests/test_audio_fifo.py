@@ -296,3 +296,27 @@ def test_a_silent_stream_costs_one_deadline_then_stops_holding_the_batch_up(buil
         finally:
             for fd in fds:
                 os.close(fd)
+
+
+def test_native_backend_without_a_writer_is_silence_and_stays_joinable(built, tmp_path):
+    """the reference's thread sits in open() until a writer appears (and cannot be joined until then), and spins on a FIFO
+    whose writer has exited; the native backend reads both situations as silence at the poll cadence"""
+    paths = _pipes(tmp_path, 2)
+    n = 1024
+    lb = np.ones((2, n), np.float32); rb = np.ones_like(lb)
+    t0 = time.time()
+    with audio.AudioBatch("fifo", paths, 2, n, samplesz=256) as ab:
+        time.sleep(0.13)                                                 # > 2 poll timeouts of 50 ms, nobody writes
+        assert ab.collect(lb, rb).all() and not lb.any() and not rb.any()
+        fd = os.open(paths[0], os.O_WRONLY)
+        os.write(fd, np.full(128, 1000, np.int16).tobytes())
+        deadline = time.time() + 5
+        while not (ab.collect(lb, rb)[0] and lb[0].any()):
+            assert time.time() < deadline
+            time.sleep(0.002)
+        os.close(fd)                                                     # writer gone: POLLHUP from now on
+        time.sleep(0.05)
+        c0 = time.process_time()
+        time.sleep(0.2)
+        assert time.process_time() - c0 < 0.15                           # no busy loop on the hung-up FIFO
+    assert time.time() - t0 < 3.0                                        # stop() joined both threads promptly
