@@ -7,7 +7,7 @@
 // the generic kernels).  Supported: the per-pixel variable (`d`; `pos` in graph), int / float literals, `#rrggbb[aa]`,
 // other object-like config macros (expanded textually, as the preprocessor does), + - * / and unary minus, swizzles,
 // vec2 / vec3 / vec4 / float constructors, comparisons, && || ! and ?: on scalars, `true` / `false`, and mix clamp smoothstep
-// min max mod step abs floor ceil fract sqrt sin cos log sign.  Integer sub-expressions are folded with C semantics (`1 / 2` is 0) and convert to float where they meet one.
+// min max mod step abs floor ceil fract sqrt sin cos log log2 exp exp2 pow sign.  Integer sub-expressions are folded with C semantics (`1 / 2` is 0) and convert to float where they meet one.
 // Anything else is a config error naming the offending token.
 #ifndef GLAVA_B200_COLOR_COMPILE_H
 #define GLAVA_B200_COLOR_COMPILE_H
@@ -346,7 +346,8 @@ struct ColorCompiler {
             { "abs", 1, GLAVA_B200_COP_ABS }, { "floor", 1, GLAVA_B200_COP_FLOOR }, { "ceil", 1, GLAVA_B200_COP_CEIL },
             { "fract", 1, GLAVA_B200_COP_FRACT }, { "sqrt", 1, GLAVA_B200_COP_SQRT }, { "sin", 1, GLAVA_B200_COP_SIN },
             { "cos", 1, GLAVA_B200_COP_COS }, { "log", 1, GLAVA_B200_COP_LOG }, { "sign", 1, GLAVA_B200_COP_SIGN },
-            { "trunc", 1, GLAVA_B200_COP_TRUNC },
+            { "trunc", 1, GLAVA_B200_COP_TRUNC }, { "exp", 1, GLAVA_B200_COP_EXP }, { "exp2", 1, GLAVA_B200_COP_EXP2 },
+            { "log2", 1, GLAVA_B200_COP_LOG2 }, { "pow", 2, GLAVA_B200_COP_POW },
             { "min", 2, GLAVA_B200_COP_MIN }, { "max", 2, GLAVA_B200_COP_MAX }, { "mod", 2, GLAVA_B200_COP_MOD },
             { "step", 2, GLAVA_B200_COP_STEP },
             { "mix", 3, GLAVA_B200_COP_MIX }, { "clamp", 3, GLAVA_B200_COP_CLAMP }, { "smoothstep", 3, GLAVA_B200_COP_SMOOTHSTEP },

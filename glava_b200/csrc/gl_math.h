@@ -158,4 +158,43 @@ GLM_FN float glm_log(float x) {
     return glm_fma(fe, 0.693359375f, r);
 }
 
+/* e^x (Cephes expf scheme: x = n ln2 + r, degree-5 polynomial, exact scaling by 2^n); overflow -> +inf, underflow -> 0 */
+GLM_FN float glm_exp(float x) {
+    if (x != x) return x;
+    if (x > 88.7228317f) return glm_u2f(0x7f800000u);
+    if (x < -103.278929f) return 0.0f;
+    const float n = glm_rint(glm_mul(x, 1.44269504088896341f));
+    float r = glm_fma(n, -0.693359375f, x);
+    r = glm_fma(n, 2.12194440e-4f, r);
+    const float z = glm_mul(r, r);
+    float p = glm_fma(r, 1.9875691500e-4f, 1.3981999507e-3f);
+    p = glm_fma(r, p, 8.3334519073e-3f);
+    p = glm_fma(r, p, 4.1665795894e-2f);
+    p = glm_fma(r, p, 1.6666665459e-1f);
+    p = glm_fma(r, p, 5.0000001201e-1f);
+    float y = glm_add(glm_fma(p, z, r), 1.0f);
+    /* y * 2^n in two exact steps (n may exceed one exponent field's reach near the ends of the range) */
+    int k = (int) n;
+    const int k1 = k / 2; k -= k1;
+    y = glm_mul(y, glm_u2f((uint32_t) (k1 + 127) << 23));
+    return glm_mul(y, glm_u2f((uint32_t) (k + 127) << 23));
+}
+/* 2^x: the integer part is exact, the fraction goes through glm_exp */
+GLM_FN float glm_exp2(float x) {
+    if (x != x) return x;
+    if (x > 128.0f) return glm_u2f(0x7f800000u);
+    if (x < -150.0f) return 0.0f;
+    const float n = glm_rint(x);
+    float y = glm_exp(glm_mul(glm_add(x, -n), 0.693147180559945309f));   /* |x - n| <= 0.5, the subtraction is exact */
+    int k = (int) n;
+    const int k1 = k / 2; k -= k1;
+    y = glm_mul(y, glm_u2f((uint32_t) (k1 + 127) << 23));
+    return glm_mul(y, glm_u2f((uint32_t) (k + 127) << 23));
+}
+/* x^y for x > 0 as GLSL defines it (exp2(y * log2(x)) up to precision; undefined for x < 0): exp(y * log(x)); 0^y = 0 for y > 0 */
+GLM_FN float glm_pow(float x, float y) {
+    if (x == 0.0f) return y > 0.0f ? 0.0f : glm_u2f(0x7fc00000u);
+    return glm_exp(glm_mul(y, glm_log(x)));
+}
+
 #endif /* GLAVA_B200_GL_MATH_H */

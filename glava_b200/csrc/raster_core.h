@@ -90,6 +90,10 @@ GLB_HD_NOINLINE f4 eval_color_prog(const glava_b200_color_prog& c, float x) {
             case GLAVA_B200_COP_OR:    GLB_COP2((v != 0.0f || w != 0.0f) ? 1.0f : 0.0f);
             case GLAVA_B200_COP_NOT:   GLB_COP1(v != 0.0f ? 0.0f : 1.0f);
             case GLAVA_B200_COP_SELECT: GLB_COP3(u != 0.0f ? v : w);
+            case GLAVA_B200_COP_EXP:   GLB_COP1(glm_exp(v));
+            case GLAVA_B200_COP_EXP2:  GLB_COP1(glm_exp2(v));
+            case GLAVA_B200_COP_LOG2:  GLB_COP1(glm_log(v) * 1.44269504088896341f);
+            case GLAVA_B200_COP_POW:   GLB_COP2(glm_pow(v, w));
             default: break;
         }
     }

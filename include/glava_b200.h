@@ -60,6 +60,8 @@ enum { GLAVA_B200_COP_SPLAT = 0,   /* dst = imm in every lane                   
        GLAVA_B200_COP_LT, GLAVA_B200_COP_LE, GLAVA_B200_COP_EQ, GLAVA_B200_COP_NE,   /* dst = (a op b) ? 1 : 0  (> and >= swap operands) */
        GLAVA_B200_COP_AND, GLAVA_B200_COP_OR, GLAVA_B200_COP_NOT,                    /* on 0 / 1 values                                  */
        GLAVA_B200_COP_SELECT,      /* dst = c != 0 ? a : b,                  c = reg[(int) imm]  */
+       GLAVA_B200_COP_EXP, GLAVA_B200_COP_EXP2, GLAVA_B200_COP_LOG2,                 /* dst = f(a)               */
+       GLAVA_B200_COP_POW,         /* dst = pow(a, b)                                            */
        GLAVA_B200_COP_COUNT };
 #define GLAVA_B200_COLOR_OPS  64
 #define GLAVA_B200_COLOR_REGS 8

@@ -614,6 +614,7 @@ BUILTINS = {
     "sin": lambda x: componentwise(_m1("sinf"), x), "cos": lambda x: componentwise(_m1("cosf"), x),
     "tan": lambda x: componentwise(_m1("tanf"), x),
     "log": lambda x: componentwise(_m1("logf"), x), "exp": lambda x: componentwise(_m1("expf"), x),
+    "log2": lambda x: componentwise(_m1("log2f"), x), "exp2": lambda x: componentwise(_m1("exp2f"), x),
     "sqrt": lambda x: componentwise(lambda v: F32(np.sqrt(v)), x),
     "floor": lambda x: componentwise(_m1("floorf"), x), "ceil": lambda x: componentwise(_m1("ceilf"), x),
     "round": lambda x: componentwise(_round_even, x), "trunc": lambda x: componentwise(_m1("truncf"), x),

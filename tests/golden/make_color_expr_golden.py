@@ -42,6 +42,11 @@ CASES = {
 #define GRADIENT 14
 #define COLOR vec4(abs(sin(d / 7.0)), clamp(1 - d / GRADIENT, 0.2, 1), fract(d * 0.125), 1.0)
 """),
+    "graph_pow": ("graph", (96, 54), """
+#define VSCALE 42
+#define DRAW_HIGHLIGHT 0
+#define COLOR vec4(pow(pos / 30, 0.5), exp(-pos / 20), exp2(-pos / 16) * (pos > 12 ? 1.0 : 0.5), log2(pos + 2) / 5)
+"""),
     "graph_expr": ("graph", (96, 54), """
 #define VSCALE 42
 #define GRADIENT 25
