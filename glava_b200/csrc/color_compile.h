@@ -7,7 +7,7 @@
 // the generic kernels).  Supported: the per-pixel variable (`d`; `pos` in graph), int / float literals, `#rrggbb[aa]`,
 // other object-like config macros (expanded textually, as the preprocessor does), + - * / and unary minus, swizzles,
 // vec2 / vec3 / vec4 / float constructors, comparisons, && || ! and ?: on scalars, `true` / `false`, and mix clamp smoothstep
-// min max mod step abs floor ceil fract sqrt sin cos log log2 exp exp2 pow sign.  Integer sub-expressions are folded with C semantics (`1 / 2` is 0) and convert to float where they meet one.
+// min max mod step abs floor ceil fract sqrt sin cos log log2 exp exp2 pow tan atan sign.  Integer sub-expressions are folded with C semantics (`1 / 2` is 0) and convert to float where they meet one.
 // Anything else is a config error naming the offending token.
 #ifndef GLAVA_B200_COLOR_COMPILE_H
 #define GLAVA_B200_COLOR_COMPILE_H
@@ -347,11 +347,17 @@ struct ColorCompiler {
             { "fract", 1, GLAVA_B200_COP_FRACT }, { "sqrt", 1, GLAVA_B200_COP_SQRT }, { "sin", 1, GLAVA_B200_COP_SIN },
             { "cos", 1, GLAVA_B200_COP_COS }, { "log", 1, GLAVA_B200_COP_LOG }, { "sign", 1, GLAVA_B200_COP_SIGN },
             { "trunc", 1, GLAVA_B200_COP_TRUNC }, { "exp", 1, GLAVA_B200_COP_EXP }, { "exp2", 1, GLAVA_B200_COP_EXP2 },
-            { "log2", 1, GLAVA_B200_COP_LOG2 }, { "pow", 2, GLAVA_B200_COP_POW },
+            { "log2", 1, GLAVA_B200_COP_LOG2 }, { "pow", 2, GLAVA_B200_COP_POW }, { "tan", 1, GLAVA_B200_COP_TAN },
+            { "atan", 2, GLAVA_B200_COP_ATAN2 },
             { "min", 2, GLAVA_B200_COP_MIN }, { "max", 2, GLAVA_B200_COP_MAX }, { "mod", 2, GLAVA_B200_COP_MOD },
             { "step", 2, GLAVA_B200_COP_STEP },
             { "mix", 3, GLAVA_B200_COP_MIX }, { "clamp", 3, GLAVA_B200_COP_CLAMP }, { "smoothstep", 3, GLAVA_B200_COP_SMOOTHSTEP },
         };
+        if (fn == "atan" && a.size() == 1) {                     // atan(x) = atan(x, 1)
+            const int r = alloc(); if (r < 0) return false;
+            if (!emit(GLAVA_B200_COP_SPLAT, r, 0, 0, 1.0f)) return false;
+            a.push_back({ r, 1, false, 0 });
+        }
         for (const Fn& f : fns) {
             if (fn != f.name) continue;
             if ((int) a.size() != f.nargs) return fail_at(fn + "(): expected " + std::to_string(f.nargs) + " argument(s)");

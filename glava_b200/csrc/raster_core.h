@@ -94,6 +94,8 @@ GLB_HD_NOINLINE f4 eval_color_prog(const glava_b200_color_prog& c, float x) {
             case GLAVA_B200_COP_EXP2:  GLB_COP1(glm_exp2(v));
             case GLAVA_B200_COP_LOG2:  GLB_COP1(glm_log(v) * 1.44269504088896341f);
             case GLAVA_B200_COP_POW:   GLB_COP2(glm_pow(v, w));
+            case GLAVA_B200_COP_ATAN2: GLB_COP2(glm_atan2(v, w));
+            case GLAVA_B200_COP_TAN:   GLB_COP1(glm_sin(v) / glm_sin(v + (GLB_PI / 2.0f)));
             default: break;
         }
     }

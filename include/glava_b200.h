@@ -62,6 +62,8 @@ enum { GLAVA_B200_COP_SPLAT = 0,   /* dst = imm in every lane                   
        GLAVA_B200_COP_SELECT,      /* dst = c != 0 ? a : b,                  c = reg[(int) imm]  */
        GLAVA_B200_COP_EXP, GLAVA_B200_COP_EXP2, GLAVA_B200_COP_LOG2,                 /* dst = f(a)               */
        GLAVA_B200_COP_POW,         /* dst = pow(a, b)                                            */
+       GLAVA_B200_COP_ATAN2,       /* dst = atan(a, b); atan(x) is compiled as atan(x, 1)        */
+       GLAVA_B200_COP_TAN,         /* dst = sin(a) / cos(a)                                      */
        GLAVA_B200_COP_COUNT };
 #define GLAVA_B200_COLOR_OPS  64
 #define GLAVA_B200_COLOR_REGS 8

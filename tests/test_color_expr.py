@@ -90,7 +90,8 @@ def test_textual_macro_expansion_and_integer_folding(tmp_path, built):
 
 
 @pytest.mark.parametrize("text,msg", [
-    ("#define COLOR vec4(tan(d), 0, 0, 1)", "function 'tan' is not available"),
+    ("#define COLOR vec4(texture(audio_l, d).r, 0, 0, 1)", "'audio_l' is not available"),
+    ("#define COLOR vec4(length(vec2(d)), 0, 0, 1)", "function 'length' is not available"),
     ("#define COLOR vec4(v, 0, 0, 1)", "'v' is not available to a colour expression"),
     ("#define COLOR vec3(d, 0, 0)", "not a vec4"),
     ("#define COLOR vec4(d, 0, 0)", "component count mismatch"),
@@ -223,3 +224,12 @@ def test_exp_exp2_log2_pow_accuracy(tmp_path, built):
                 worst[k] = max(worst[k], abs(float(got[k]) - float(np.float32(want[k]))) / float(np.spacing(np.float32(abs(want[k])))))
     assert worst[0] <= 1 and worst[1] <= 1 and worst[2] <= 2 and worst[3] <= 32, worst
     assert emul.eval_color(p.bars_color_prog, 200.0)[0] == np.inf and emul.eval_color(p.bars_color_prog, -200.0)[0] == 0.0
+
+
+def test_tan_and_atan(tmp_path, built):
+    from tests import emul
+    p = g.load_config(_cfg(tmp_path, "bars", "#define COLOR vec4(tan(d), atan(d), atan(d, 2.0), atan(2.0, d))\n"))
+    for x in np.linspace(-1.4, 1.4, 57):
+        got = emul.eval_color(p.bars_color_prog, float(x)).astype(np.float64)
+        want = np.array([np.tan(x), np.arctan(x), np.arctan2(x, 2.0), np.arctan2(2.0, x)])
+        assert np.allclose(got, want, rtol=3e-6, atol=3e-7), (x, got, want)
