@@ -722,6 +722,17 @@ int load_config(glava_b200_params* out, const char* const* paths, const char* en
     }
     struct BindScope { BindScope(const std::map<std::string, std::string>* m) { g_binds = m; } ~BindScope() { g_binds = nullptr; } } scope(&bind_map);
     fill_defaults(out, GLAVA_B200_MOD_BARS);
+    if (paths && paths[0]) {
+        // With a configuration directory the starting point is rd_new's own initialisers (render.c:876-934), not the
+        // values the shipped rc.glsl requests: a user rc.glsl that leaves a request out gets THESE (8192 samples at
+        // 22000 Hz, 6 average frames, interpolation ON, a 500 x 400 window ...).  paths == NULL keeps the shipped set.
+        out->n = 8192; out->rate_request = 22000; out->samplesize_request = 1024;
+        out->avg_frames = 6; out->avg_window = 1; out->gravity_step = 4.2f; out->interpolate = 1;
+        out->smooth_factor = 0.025f; out->smooth_distance = 0.01f; out->smooth_ratio = 4.0f;
+        out->premultiply_alpha = 1; out->accel_fft = 1; out->smooth_pass = 1; out->fft_scale = 10.2f; out->fft_cutoff = 0.3f;
+        out->w = 500; out->h = 400; out->bufscale = 1; out->channels = 2;
+        out->clear_color[0] = out->clear_color[1] = out->clear_color[2] = out->clear_color[3] = 0.0f;
+    }
     Loader L { out, "bars", false, false };
     if (force_module) { L.module = force_module; L.module_forced = true; }
     std::vector<std::string> dirs;
@@ -758,8 +769,12 @@ int load_config(glava_b200_params* out, const char* const* paths, const char* en
         IncCtx dctx { dd, entry_dir, dd, true, true };
         IncCtx cctx { entry_dir, entry_dir, dd, true, true };
         for (const std::string& f : { std::string("smooth_parameters.glsl"), L.module + ".glsl" }) {
-            if (!scan_file(L, dd + "/" + f, &defs, true, dctx)) return GLAVA_B200_ECONFIG;
-            if (!scan_file(L, entry_dir + "/" + f, &defs, true, cctx)) return GLAVA_B200_ECONFIG;
+            // smooth_parameters.glsl's `#request`s only count when a MODULE shader includes util/smooth.glsl (all but
+            // wave/1.frag do): util/smooth_pass.frag includes it too, but rd_new ignores them while loading that shader
+            // (`loading_smooth_pass`, render.c:1186-1215, 1634-1642).  Its #defines reach the smoothing pass either way.
+            const bool reqs = !(f == "smooth_parameters.glsl" && L.module == "wave");
+            if (!scan_file(L, dd + "/" + f, &defs, reqs, dctx)) return GLAVA_B200_ECONFIG;
+            if (!scan_file(L, entry_dir + "/" + f, &defs, reqs, cctx)) return GLAVA_B200_ECONFIG;
         }
     }
     else if (!bind_map.empty()) {

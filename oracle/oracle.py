@@ -289,3 +289,79 @@ class Reference:
         out = np.zeros(4, np.float32); out[3] = 1.0
         ok = self.L.ref_parse_color(s.encode(), out.ctypes.data)
         return bool(ok), out
+
+
+class ReferenceRenderer:
+    """The reference's own rd_new / rd_update (render.c), run on a null OpenGL driver and a null window backend
+    (oracle/ref_shim.c): what rd_new reads from a configuration, and the float buffers rd_update uploads as the audio
+    textures — the outcome of its transform chain, buffer scaling and keyframe interpolation as IT orchestrates them."""
+
+    INTS = ("bufsize", "rate", "samplesize", "mirror_input", "avg_frames", "avg_window", "smooth_pass", "accel_fft",
+            "interpolate", "bufscale", "premultiply_alpha", "framerate", "w", "h", "stages", "copy_desktop")
+    FLOATS = ("fft_scale", "fft_cutoff", "gravity_step", "smooth_factor", "smooth_distance", "smooth_ratio",
+              "clear_r", "clear_g", "clear_b", "clear_a", "ur", "fr")
+    _L = None
+
+    @classmethod
+    def lib(cls):
+        if cls._L is None:
+            path = os.path.join(HERE, "_ref", "libglava_ref_rd.so")
+            if not os.path.exists(path):
+                return None
+            try:
+                L = C.CDLL(path)                       # needs an executable stack (GNU nested-function trampolines)
+            except OSError:
+                return None
+            cp, vp = C.c_char_p, C.c_void_p
+            L.ref_rd_new.restype = vp
+            L.ref_rd_new.argtypes = [C.POINTER(cp), cp, C.POINTER(cp)]
+            L.ref_rd_config.argtypes = [vp, vp, vp]
+            L.ref_rd_update.argtypes = [vp, vp, vp, C.c_size_t, C.c_int]
+            L.ref_rd_upload.argtypes = [vp, C.c_int, C.POINTER(C.c_int), vp, C.c_int]
+            L.ref_rd_set_rates.argtypes = [vp, C.c_float, C.c_float]
+            L.ref_rd_destroy.argtypes = [vp]
+            cls._L = L
+        return cls._L
+
+    def __init__(self, paths, entry="rc.glsl", requests=()):
+        L = self.lib()
+        assert L is not None
+        pa = (C.c_char_p * (len(paths) + 1))(*[p.encode() for p in paths], None)
+        rq = (C.c_char_p * (len(requests) + 1))(*[r.encode() for r in requests], None)
+        self.L = L
+        self.h = L.ref_rd_new(pa, entry.encode(), rq)
+        if not self.h:
+            raise ValueError("the reference aborted in rd_new")
+        self.cfg = self.config()
+        self.lb = np.zeros(self.cfg["bufsize"], np.float32)            # glava.c:487-494: lb / rb persist across frames
+        self.rb = np.zeros(self.cfg["bufsize"], np.float32)
+
+    def config(self):
+        ints = (C.c_int * 16)(); floats = (C.c_float * 12)()
+        self.L.ref_rd_config(self.h, ints, floats)
+        d = dict(zip(self.INTS, list(ints)))
+        d.update(zip(self.FLOATS, [float(np.float32(v)) for v in floats]))
+        return d
+
+    def set_rates(self, ur, fr):
+        self.L.ref_rd_set_rates(self.h, ur, fr)
+
+    def frame(self, pcm_l=None, pcm_r=None):
+        """one iteration of glava.c:523-539: copy new PCM into lb / rb when there is some (modified), rd_update;
+        -> {0: floats uploaded for audio_l, 1: ... audio_r} (the LAST upload of each texture in this frame)"""
+        modified = pcm_l is not None
+        if modified:
+            self.lb[:] = pcm_l; self.rb[:] = pcm_r
+        k = self.L.ref_rd_update(self.h, self.lb.ctypes.data, self.rb.ctypes.data, self.lb.shape[0], 1 if modified else 0)
+        if k < 0:
+            raise ValueError("the reference aborted in rd_update")
+        out = {}
+        for i in range(k):
+            which = C.c_int(); buf = np.zeros(self.lb.shape[0], np.float32)
+            w = self.L.ref_rd_upload(self.h, i, C.byref(which), buf.ctypes.data, buf.shape[0])
+            out[which.value] = buf[:w].copy()
+        return out
+
+    def close(self):
+        if self.h:
+            self.L.ref_rd_destroy(self.h); self.h = None

@@ -191,3 +191,150 @@ int ref_ext_process(const char* path, const char* cd, const char* cfd, const cha
     free(src);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * rd_new / rd_update FOR REAL, with a null OpenGL driver and a null window backend.
+ *
+ * Every gl* the renderer calls is a glad function pointer; here they point at stubs that hand out object ids, report
+ * success, and record what update_1d_tex() uploads (render.c:521-524) — the float buffer rd_update hands to GL as the
+ * audio texture of a bind, i.e. the result of the reference's own transform chain, buffer scaling and keyframe
+ * interpolation as rd_update orchestrates them (render.c:1743-2417).  A window backend "null" is registered the way
+ * glx_wcb / glfw_wcb register themselves.  rd_new then reads rc.glsl and the module through its own request handlers
+ * (render.c:1033-1314), so the fields of `struct gl_data` afterwards are the reference's reading of a config.
+ * What this cannot show: anything the GLSL passes compute (no shader runs; a "compiled" stage is never disabled).
+ * ------------------------------------------------------------------------------------------------------------------ */
+static GLuint ng_next_id = 1;
+static GLuint ng_bound_1d = 0;
+static void   ng_noop(void) {}
+static GLenum ng_get_error(void) { return GL_NO_ERROR; }
+static GLuint ng_create_shader(GLenum type) { (void) type; return ng_next_id++; }
+static GLuint ng_create_program(void) { return ng_next_id++; }
+static void   ng_gen(GLsizei n, GLuint* out) { for (GLsizei i = 0; i < n; ++i) out[i] = ng_next_id++; }
+static GLint  ng_uniform_location(GLuint p, const GLchar* name) { (void) p; (void) name; return 1; }
+static void   ng_get_objectiv(GLuint o, GLenum pname, GLint* out) { (void) o; *out = (pname == GL_INFO_LOG_LENGTH) ? 0 : GL_TRUE; }
+static void   ng_get_integerv(GLenum pname, GLint* out) { (void) pname; *out = 1024; }
+static GLenum ng_fb_status(GLenum target) { (void) target; return GL_FRAMEBUFFER_COMPLETE; }
+static void   ng_bind_texture(GLenum target, GLuint tex) { if (target == GL_TEXTURE_1D) ng_bound_1d = tex; }
+
+#define NG_MAX_UPLOADS 64
+static struct { GLuint tex; int width; float* data; } ng_uploads[NG_MAX_UPLOADS];
+static int ng_upload_count = 0;
+static void ng_clear_uploads(void) {
+    for (int i = 0; i < ng_upload_count; ++i) free(ng_uploads[i].data);
+    ng_upload_count = 0;
+}
+static void ng_tex_image_1d(GLenum target, GLint level, GLint ifmt, GLsizei width, GLint border, GLenum format, GLenum type, const void* pixels) {
+    (void) target; (void) level; (void) ifmt; (void) border; (void) format;
+    if (!pixels || type != GL_FLOAT || ng_upload_count == NG_MAX_UPLOADS) return;     /* bind_1d_fbo allocates with NULL */
+    ng_uploads[ng_upload_count].tex = ng_bound_1d;
+    ng_uploads[ng_upload_count].width = (int) width;
+    ng_uploads[ng_upload_count].data = malloc(sizeof(float) * (size_t) width);
+    memcpy(ng_uploads[ng_upload_count].data, pixels, sizeof(float) * (size_t) width);
+    ++ng_upload_count;
+}
+
+static void ng_install(void) {
+#define NG_NOOP(fn) glad_##fn = (__typeof__(glad_##fn)) ng_noop
+    NG_NOOP(glUniform1i); NG_NOOP(glUseProgram); NG_NOOP(glViewport); NG_NOOP(glBindFramebuffer); NG_NOOP(glTexParameteri);
+    NG_NOOP(glDisable); NG_NOOP(glActiveTexture); NG_NOOP(glEnable); NG_NOOP(glBindVertexArray); NG_NOOP(glUniform1f);
+    NG_NOOP(glBindFragDataLocation); NG_NOOP(glAttachShader); NG_NOOP(glUniform2i); NG_NOOP(glEnableVertexAttribArray);
+    NG_NOOP(glDisableVertexAttribArray); NG_NOOP(glBlendEquation); NG_NOOP(glBindBuffer); NG_NOOP(glVertexAttribPointer);
+    NG_NOOP(glUniform4f); NG_NOOP(glUniform3f); NG_NOOP(glUniform2f); NG_NOOP(glTextureBarrierNV); NG_NOOP(glTexImage2D);
+    NG_NOOP(glShaderSource); NG_NOOP(glReadPixels); NG_NOOP(glLinkProgram); NG_NOOP(glGetShaderInfoLog); NG_NOOP(glGetProgramInfoLog);
+    NG_NOOP(glFramebufferTexture2D); NG_NOOP(glFramebufferTexture1D); NG_NOOP(glDrawArrays); NG_NOOP(glCompileShader);
+    NG_NOOP(glClearColor); NG_NOOP(glClear); NG_NOOP(glBufferData); NG_NOOP(glBlendFunc);
+#undef NG_NOOP
+    glad_glGetError = ng_get_error;
+    glad_glCreateShader = ng_create_shader; glad_glCreateProgram = ng_create_program;
+    glad_glGenTextures = ng_gen; glad_glGenFramebuffers = ng_gen; glad_glGenVertexArrays = ng_gen; glad_glGenBuffers = ng_gen;
+    glad_glGetUniformLocation = ng_uniform_location;
+    glad_glGetShaderiv = ng_get_objectiv; glad_glGetProgramiv = ng_get_objectiv;
+    glad_glGetIntegerv = ng_get_integerv; glad_glCheckFramebufferStatus = ng_fb_status;
+    glad_glBindTexture = ng_bind_texture; glad_glTexImage1D = ng_tex_image_1d;
+}
+
+/* ---- window backend "null" (struct gl_wcb, render.h:66-104) ---- */
+static int nw_geom[4] = { 0, 0, 800, 600 };
+static bool  nw_offscreen(void) { return false; }
+static void  nw_init(void) {}
+static void* nw_create_and_bind(const char* name, const char* class, const char* type, const char** states, size_t states_sz,
+                                int w, int h, int x, int y, int major, int minor, bool clickthrough, bool offscreen) {
+    (void) name; (void) class; (void) type; (void) states; (void) states_sz; (void) major; (void) minor; (void) clickthrough; (void) offscreen;
+    nw_geom[0] = x; nw_geom[1] = y; nw_geom[2] = w; nw_geom[3] = h;
+    ng_install();
+    glad_instantiated = true;
+    return nw_geom;
+}
+static bool  nw_false(void* p) { (void) p; return false; }
+static bool  nw_true(void* p) { (void) p; return true; }
+static void  nw_void(void* p) { (void) p; }
+static void  nw_terminate(void) {}
+static void  nw_get_pos(void* p, int* x, int* y) { (void) p; *x = nw_geom[0]; *y = nw_geom[1]; }
+static void  nw_get_fbsize(void* p, int* w, int* h) { (void) p; *w = nw_geom[2]; *h = nw_geom[3]; }
+static void  nw_set_geometry(void* p, int x, int y, int w, int h) { (void) p; nw_geom[0] = x; nw_geom[1] = y; nw_geom[2] = w; nw_geom[3] = h; }
+static void  nw_set_int(int v) { (void) v; }
+static void  nw_set_bool(bool v) { (void) v; }
+static double nw_get_time(void* p) { (void) p; return 0.0; }            /* frame time 0: gl->ur / gl->fr stay what the test sets */
+static void  nw_set_time(void* p, double t) { (void) p; (void) t; }
+static void  nw_set_visible(void* p, bool v) { (void) p; (void) v; }
+static const char* nw_environment(void) { return NULL; }
+static struct gl_wcb ref_null_wcb = {
+    .name = "null", .offscreen = nw_offscreen, .init = nw_init, .create_and_bind = nw_create_and_bind,
+    .should_close = nw_false, .should_render = nw_true, .bg_changed = nw_false, .swap_buffers = nw_void, .raise = nw_void,
+    .destroy = nw_void, .terminate = nw_terminate, .get_pos = nw_get_pos, .get_fbsize = nw_get_fbsize,
+    .set_geometry = nw_set_geometry, .set_swap = nw_set_int, .set_floating = nw_set_bool, .set_decorated = nw_set_bool,
+    .set_focused = nw_set_bool, .set_maximized = nw_set_bool, .set_transparent = nw_set_bool, .get_time = nw_get_time,
+    .set_time = nw_set_time, .set_visible = nw_set_visible, .get_environment = nw_environment
+};
+
+static jmp_buf ref_rd_jmp;
+static void ref_rd_abort(void) { longjmp(ref_rd_jmp, 1); }
+
+/* rd_new (render.h:53-57) with backend "null", no --pipe binds.  NULL when the reference aborted. */
+void* ref_rd_new(const char** paths, const char* entry, const char** requests) {
+    if (wcbs_idx == 0) register_wcb(&ref_null_wcb);
+    static struct rd_bind no_binds[1] = { { .name = NULL } };
+    void (*saved)(void) = glava_abort;
+    struct glava_renderer* r = NULL;
+    glava_abort = ref_rd_abort;
+    if (setjmp(ref_rd_jmp) == 0) r = rd_new(paths, entry, requests, "null", no_binds, STDIN_TYPE_NONE, false, false, false);
+    glava_abort = saved;
+    return r;
+}
+
+/* what the reference read from the configuration (struct glava_renderer, render.h:8-30; struct gl_data, render.c:166-207) */
+void ref_rd_config(void* rp, int* ints /* [16] */, float* floats /* [12] */) {
+    struct glava_renderer* r = rp; struct gl_data* gl = r->gl;
+    ints[0] = (int) r->bufsize_request; ints[1] = (int) r->rate_request; ints[2] = (int) r->samplesize_request; ints[3] = r->mirror_input;
+    ints[4] = (int) gl->avg_frames; ints[5] = gl->avg_window; ints[6] = gl->smooth_pass; ints[7] = gl->accel_fft;
+    ints[8] = gl->interpolate; ints[9] = (int) gl->bufscale; ints[10] = gl->premultiply_alpha; ints[11] = gl->rate;
+    ints[12] = gl->geometry[2]; ints[13] = gl->geometry[3]; ints[14] = (int) gl->stages_sz; ints[15] = gl->copy_desktop;
+    floats[0] = gl->fft_scale; floats[1] = gl->fft_cutoff; floats[2] = gl->gravity_step; floats[3] = gl->smooth_factor;
+    floats[4] = gl->smooth_distance; floats[5] = gl->smooth_ratio;
+    floats[6] = gl->clear_color.r; floats[7] = gl->clear_color.g; floats[8] = gl->clear_color.b; floats[9] = gl->clear_color.a;
+    floats[10] = gl->ur; floats[11] = gl->fr;
+}
+void ref_rd_set_rates(void* rp, float ur, float fr) { struct gl_data* gl = ((struct glava_renderer*) rp)->gl; gl->ur = ur; gl->fr = fr; }
+
+/* one rd_update (render.h:58-59).  lb / rb are transformed IN PLACE, as in the reference.  Returns the number of audio
+ * texture uploads recorded during the call (fetch them with ref_rd_upload), or -1 when the reference aborted. */
+int ref_rd_update(void* rp, float* lb, float* rb, size_t bsz, int modified) {
+    ng_clear_uploads();
+    void (*saved)(void) = glava_abort;
+    int rc = 0;
+    glava_abort = ref_rd_abort;
+    if (setjmp(ref_rd_jmp) == 0) { rd_time(rp); rd_update(rp, lb, rb, bsz, modified != 0); }
+    else rc = -1;
+    glava_abort = saved;
+    return rc < 0 ? rc : ng_upload_count;
+}
+/* upload `idx` of the last update: which (0 = audio_l, 1 = audio_r, 2 = another texture), its width, its floats */
+int ref_rd_upload(void* rp, int idx, int* which, float* out, int cap) {
+    struct gl_data* gl = ((struct glava_renderer*) rp)->gl;
+    if (idx < 0 || idx >= ng_upload_count) return -1;
+    *which = ng_uploads[idx].tex == gl->audio_tex_l ? 0 : (ng_uploads[idx].tex == gl->audio_tex_r ? 1 : 2);
+    const int w = ng_uploads[idx].width;
+    memcpy(out, ng_uploads[idx].data, sizeof(float) * (size_t) (w < cap ? w : cap));
+    return w;
+}
+void ref_rd_destroy(void* rp) { rd_destroy(rp); }

@@ -1,0 +1,185 @@
+"""The reference's OWN rd_new / rd_update (glava/render.c compiled where it lies) on a null OpenGL driver and a null
+window backend (oracle/ref_shim.c, oracle/_ref/libglava_ref_rd.so):
+
+* what rd_new's request handlers make of a configuration — rc.glsl, smooth_parameters.glsl, CLI requests — against the
+  product's config reader, field by field;
+* what rd_update uploads as the audio textures over a sequence of frames — transform chain, `modified` handling, buffer
+  scaling, keyframe interpolation as the reference orchestrates them — against the oracle's restatement (orc_stream_*),
+  which is what the kernels are tested against.
+
+Needs the reference tree (the shipped shaders are what rd_new loads) and an executable stack (skipped otherwise)."""
+import os
+
+import numpy as np
+import pytest
+
+import glava_b200 as g
+from oracle.oracle import OracleStream, OrcExt, ReferenceRenderer, params_from
+
+REF_SHADERS = "/root/reference/shaders/glava"
+pytestmark = [pytest.mark.skipif(not os.path.isdir(REF_SHADERS), reason="reference tree not present"), pytest.mark.timeout(300)]
+
+
+@pytest.fixture(scope="module")
+def rd(built):
+    if ReferenceRenderer.lib() is None:
+        pytest.skip("oracle/_ref/libglava_ref_rd.so not built or not loadable (needs an executable stack)")
+    return ReferenceRenderer
+
+
+def _user_dir(path, files):
+    """a user configuration directory the way `glava --copy-config` lays it out: the user's own files, symlinks to the
+    installed shaders / modules for everything else (render.c:1318-1320)"""
+    path.mkdir()
+    for name, text in files.items():
+        (path / name).write_text(text)
+    for entry in os.listdir(REF_SHADERS):
+        if entry not in files:
+            os.symlink(os.path.join(REF_SHADERS, entry), path / entry)
+    return str(path)
+
+
+def _unorm16(v):
+    v = np.asarray(v, np.float32)
+    q = (v * np.float32(65535.0) + np.float32(0.5)).astype(np.float32)
+    with np.errstate(invalid="ignore"):
+        return np.where(v > 0, np.where(v < 1, q.astype(np.int64), 65535), 0).astype(np.uint16)
+
+
+CONFIGS = [
+    ("shipped", "", "", []),
+    ("user rc", '#request mod radial\n#request setbufsize 2048\n#request setgeometry 5 6 640 360\n#request setopacity "none"\n'
+     "#request setbg 10203040\n#request setmirror true\n#request setsamplerate 44100\n#request setsamplesize 512\n"
+     "#request setaccelfft false\n#request setinterpolate true\n#request setbufscale 2\n#request setframerate 120\n", "", []),
+    ("user smooth parameters", "#request mod graph\n",
+     "#request setfftscale 7.5\n#request setfftcutoff 0.45\n#request setavgframes 3\n#request setavgwindow false\n"
+     "#request setgravitystep 2.25\n#request setsmoothfactor 0.0438713878\n#request setsmoothpass false\n", []),
+    # one CLI request per run: rd_new reuses one `struct glsl_ext` for all of them and ext_free() leaves its destructor list
+    # dangling, so a second `--request` corrupts the reference's heap (render.c:1415-1435, glsl_ext.c:124-136)
+    ("cli request wins", "#request mod wave\n#request setbufsize 1024\n", "", ["setbufsize 8192"]),
+    ("cli setbgf", "#request mod wave\n", "", ["setbgf 0.25 0.5 0.75 1.0"]),
+    ("cli xroot", "#request mod circle\n#request setsmooth 0.02\n#request setsmoothratio 3.5\n", "", ['setopacity "xroot"']),
+    ("rc leaves everything to rd_new's initialisers", "#request mod bars\n", "", []),
+]
+
+
+@pytest.mark.parametrize("name,rc,sp,requests", CONFIGS, ids=[c[0] for c in CONFIGS])
+def test_config_reader_reads_what_rd_new_reads(rd, tmp_path, name, rc, sp, requests):
+    paths = [REF_SHADERS]
+    if rc or sp:
+        files = {"rc.glsl": rc or "#request mod bars\n"}
+        if sp:
+            files["smooth_parameters.glsl"] = sp
+        paths = [_user_dir(tmp_path / "user", files), REF_SHADERS]
+    r = rd(paths, requests=requests)
+    try:
+        c = r.cfg
+        p = g.load_config(paths, requests=requests)
+        assert (p.n, p.rate_request, p.samplesize_request) == (c["bufsize"], c["rate"], c["samplesize"])
+        assert p.channels == (1 if c["mirror_input"] else 2)
+        assert (p.avg_frames, p.avg_window, p.smooth_pass, p.accel_fft) == (c["avg_frames"], c["avg_window"], c["smooth_pass"], c["accel_fft"])
+        assert (p.interpolate, p.bufscale, p.premultiply_alpha) == (c["interpolate"], c["bufscale"], c["premultiply_alpha"])
+        assert (p.w, p.h) == (c["w"], c["h"])
+        for ours, theirs in (("fft_scale", "fft_scale"), ("fft_cutoff", "fft_cutoff"), ("gravity_step", "gravity_step"),
+                             ("smooth_distance", "smooth_distance"), ("smooth_ratio", "smooth_ratio")):
+            assert getattr(p, ours) == np.float32(c[theirs]), ours
+        assert p.smooth_factor == np.float32("%.6f" % c["smooth_factor"])     # the shaders get the "%.6f" literal (render.c:315-324)
+        assert list(p.clear_color) == [np.float32(c[k]) for k in ("clear_r", "clear_g", "clear_b", "clear_a")]
+        if c["framerate"] > 0:
+            assert p.fr == c["framerate"]
+    finally:
+        r.close()
+
+
+def _chain_case(rd, tmp_path, extra_rc, ur, fr, pattern, seed):
+    """pipeline A with the R16 texture taken straight from the upload (setsmoothpass false): reference uploads vs oracle"""
+    paths = [_user_dir(tmp_path / "u", {"rc.glsl": "#request mod bars\n#request setbufsize 1024\n#request setaccelfft false\n" + extra_rc,
+                                        "smooth_parameters.glsl": "#request setsmoothpass false\n"}), REF_SHADERS]
+    r = rd(paths)
+    try:
+        p = g.load_config(paths)
+        assert p.smooth_pass == 0 and p.accel_fft == 0
+        p.ur = ur
+        ext = OrcExt(bufscale=p.bufscale, interpolate=p.interpolate, fr=fr, transform_smooth=0, smooth_distance=0.01, smooth_ratio=4.0)
+        from oracle.oracle import Oracle
+        orc = Oracle("libm")
+        st = OracleStream(orc, params_from(p), ext)
+        r.set_rates(ur, fr)
+        rng = np.random.default_rng(seed)
+        n = p.n
+        checked = 0
+        pushed = 0                                        # keyframes pushed so far (render.c:2347-2353)
+        for k, modified in enumerate(pattern):
+            if modified:
+                amp = [0.15, 0.02, 0.4][k % 3]
+                pl = (rng.standard_normal(n) * amp).astype(np.float32); pr = (rng.standard_normal(n) * amp).astype(np.float32)
+                up = r.frame(pl, pr)
+                sl, sr, tl, tr = st.update(pl, pr, True)
+            else:
+                up = r.frame()
+                sl, sr, tl, tr = st.update(np.zeros(n, np.float32), np.zeros(n, np.float32), False)
+            assert set(up) >= {0, 1}, (k, up.keys())
+            assert up[0].shape[0] == st.n
+            interp_active = bool(p.interpolate) and ur / fr <= 0.9
+            settled = pushed >= 2
+            pushed += 1 if modified else 0
+            if interp_active and not settled:
+                continue      # the reference lerps between malloc'd, never initialised keyframe buffers until two have been pushed
+            if p.bufscale > 1 and not modified and not (p.interpolate and ur / fr <= 0.9):
+                # Known deviation, deliberately not reproduced: with setbufscale > 1 the reference's transforms run on a
+                # stack copy (nlb / nrb, render.c:1765-1790) that is gone by the next frame, so a frame without new audio
+                # uploads the RAW box-averaged PCM — one untransformed frame flashes.  Oracle and product re-show the last
+                # spectrum, as the reference itself does when bufscale is 1 (lb / rb keep the transformed data).
+                assert np.array_equal(up[0], orc.bufscale(r.lb, p.bufscale)) and not np.array_equal(_unorm16(up[0]), tl)
+                checked += 1
+                continue
+            assert np.array_equal(_unorm16(up[0]), tl) and np.array_equal(_unorm16(up[1]), tr), (k, modified)
+            if modified and not (p.interpolate and ur / fr <= 0.9):
+                assert np.array_equal(up[0], sl) and np.array_equal(up[1], sr), k      # the float chain result itself, bit for bit
+            checked += 1
+        return checked
+    finally:
+        r.close()
+
+
+def test_transform_chain_and_modified_handling(rd, tmp_path):
+    assert _chain_case(rd, tmp_path, "", 86.1328125, 86.1328125, [1, 1, 0, 1, 0, 0, 1, 1, 1, 0, 1], 1) == 11
+
+
+def test_buffer_scaling(rd, tmp_path):
+    assert _chain_case(rd, tmp_path, "#request setbufscale 2\n", 86.1328125, 86.1328125, [1, 1, 1, 0, 1, 1], 2) == 6
+    (tmp_path / "b").mkdir()
+    assert _chain_case(rd, tmp_path / "b", "#request setbufscale 4\n", 50.0, 50.0, [1, 0, 1, 1], 3) == 4
+
+
+def test_keyframe_interpolation(rd, tmp_path):
+    # ur / fr = 0.25: three interpolated frames between updates; output runs one update late (rc.glsl:129-130)
+    assert _chain_case(rd, tmp_path, "#request setinterpolate true\n", 30.0, 120.0, [1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 0, 0, 1, 0], 4) == 11   # 5 unsettled frames skipped
+    (tmp_path / "b").mkdir()
+    # ur / fr > 0.9: the reference switches interpolation off for the frame (render.c:1761-1763)
+    assert _chain_case(rd, tmp_path / "b", "#request setinterpolate true\n", 100.0, 105.0, [1, 0, 1, 1, 0, 1], 5) == 6
+    (tmp_path / "c").mkdir()
+    assert _chain_case(rd, tmp_path / "c", "#request setinterpolate true\n#request setbufscale 2\n", 40.0, 100.0, [1, 0, 1, 0, 0, 1, 0, 1], 6) == 5
+
+
+def test_pipeline_b_uploads_transform_fft_only(rd, tmp_path):
+    """setaccelfft true (shipped): on a modified frame rd_update uploads transform_fft's output and leaves gravity / average
+    to the GL passes (render.c:2131-2180) — the oracle's `spec` in pipeline B is that buffer, bit for bit; interpolation is
+    forced off for such a bind (render.c:2161-2168) even though rd_new's initialiser has it on"""
+    from oracle.oracle import Oracle
+    paths = [_user_dir(tmp_path / "u", {"rc.glsl": "#request mod bars\n#request setbufsize 2048\n"}), REF_SHADERS]
+    r = rd(paths)
+    try:
+        p = g.load_config(paths)
+        assert p.accel_fft == 1 and p.interpolate == 1 and r.cfg["interpolate"] == 1
+        p.ur = 30.0
+        st = OracleStream(Oracle("libm"), params_from(p), OrcExt(bufscale=1, interpolate=1, fr=120.0, transform_smooth=0, smooth_distance=0.01, smooth_ratio=4.0))
+        r.set_rates(30.0, 120.0)
+        rng = np.random.default_rng(9)
+        for k in range(5):
+            pl = (rng.standard_normal(p.n) * 0.2).astype(np.float32); pr = (rng.standard_normal(p.n) * 0.2).astype(np.float32)
+            up = r.frame(pl, pr)
+            sl, sr, _, _ = st.update(pl, pr, True)
+            assert np.array_equal(up[0], sl) and np.array_equal(up[1], sr), k
+    finally:
+        r.close()
