@@ -183,3 +183,91 @@ def test_pipeline_b_uploads_transform_fft_only(rd, tmp_path):
             assert np.array_equal(up[0], sl) and np.array_equal(up[1], sr), k
     finally:
         r.close()
+
+
+def test_wave_chain_window_wrange(rd, tmp_path):
+    """wave/1.frag:7-10 binds audio_l only, with the transforms "window" (a no-op) and "wrange": the uploaded buffer is
+    (pcm + 1) / 2 (render.c:773-781); keyframe interpolation stays available to it (no fft transform on the bind)"""
+    from oracle.oracle import Oracle
+    for extra, ur, fr, pattern in (("#request setinterpolate false\n", 86.0, 86.0, [1, 1, 0, 1]),
+                                   ("", 30.0, 120.0, [1, 0, 1, 0, 0, 1, 0, 0, 0, 1, 0])):       # rd_new's initialiser: interpolation on
+        d = tmp_path / ("w%d" % len(pattern))
+        paths = [_user_dir(d, {"rc.glsl": "#request mod wave\n#request setbufsize 1024\n" + extra}), REF_SHADERS]
+        cli = ["setsmoothpass false"]             # (smooth_parameters.glsl cannot switch it off for wave; one CLI request can)
+        r = rd(paths, requests=cli)
+        try:
+            p = g.load_config(paths, requests=cli)
+            assert p.smooth_pass == 0 and r.cfg["smooth_pass"] == 0
+            p.ur = ur
+            st = OracleStream(Oracle("libm"), params_from(p), OrcExt(bufscale=1, interpolate=p.interpolate, fr=fr, transform_smooth=0,
+                                                                     smooth_distance=0.01, smooth_ratio=4.0))
+            r.set_rates(ur, fr)
+            rng = np.random.default_rng(13)
+            pushed = 0
+            for k, modified in enumerate(pattern):
+                if modified:
+                    pl = (rng.standard_normal(p.n) * 0.2).astype(np.float32)
+                    up = r.frame(pl, pl)
+                    sl, _, tl, _ = st.update(pl, pl, True)
+                else:
+                    up = r.frame()
+                    sl, _, tl, _ = st.update(np.zeros(p.n, np.float32), np.zeros(p.n, np.float32), False)
+                assert 0 in up and 1 not in up                               # audio_r is not bound by this module
+                active = bool(p.interpolate) and ur / fr <= 0.9
+                settled = pushed >= 2
+                pushed += 1 if modified else 0
+                if active and not settled:
+                    continue
+                assert np.array_equal(_unorm16(up[0]), tl), (extra, k, modified)     # lerped or not: what the texture holds
+                if modified and not active:
+                    assert np.array_equal(up[0], sl), (extra, k)
+                    assert np.array_equal(up[0], (pl + np.float32(1.0)) / np.float32(2.0))
+        finally:
+            r.close()
+
+
+def test_random_configs_against_rd_new(rd, tmp_path):
+    """random rc.glsl / smooth_parameters.glsl request sets (each request present or left to rd_new's initialiser, in random
+    order, some repeated): the product's reader and the real rd_new agree on every field"""
+    rng = np.random.default_rng(55)
+
+    def pick(name, maker, prob=0.6):
+        return [f"#request {name} {maker()}"] if rng.random() < prob else []
+
+    for trial in range(24):
+        module = str(rng.choice(["bars", "radial", "circle", "graph", "wave"]))
+        b = lambda: str(rng.choice(["true", "false", "t", "f", "1", "0"]))                  # noqa: E731
+        rc = [f"#request mod {module}"]
+        rc += pick("setbufsize", lambda: str(rng.choice([512, 1024, "0x800", 4096, 8192])))
+        rc += pick("setgeometry", lambda: "%d %d %d %d" % tuple(rng.integers(100, 2000, 4)))
+        rc += pick("setopacity", lambda: '"%s"' % rng.choice(["native", "none", "xroot"]))
+        rc += pick("setmirror", b) + pick("setaccelfft", b) + pick("setinterpolate", b)
+        rc += pick("setsamplerate", lambda: str(rng.choice([22050, 44100, 48000]))) + pick("setsamplesize", lambda: str(rng.choice([256, 512, 1024])))
+        rc += pick("setbufscale", lambda: str(rng.choice([1, 2])), 0.3) + pick("setframerate", lambda: str(rng.choice([0, 60, 144])))
+        rc += pick("setbg", lambda: "%08x" % int(rng.integers(0, 1 << 32)), 0.4) + pick("setbgf", lambda: "%.3f %.3f %.3f %.3f" % tuple(rng.random(4)), 0.3)
+        rc += pick("setsmooth", lambda: "%.4f" % rng.uniform(0.005, 0.05), 0.3) + pick("setsmoothratio", lambda: "%.2f" % rng.uniform(1, 6), 0.3)
+        rc += pick("setbufsize", lambda: str(rng.choice([1024, 2048])), 0.2)                # a later request overrides
+        tail = rc[1:]; rng.shuffle(tail); rc = rc[:1] + tail
+        sp = pick("setfftscale", lambda: "%.3f" % rng.uniform(1, 20)) + pick("setfftcutoff", lambda: "%.3f" % rng.uniform(0, 1))
+        sp += pick("setavgframes", lambda: str(int(rng.integers(1, 9)))) + pick("setavgwindow", b) + pick("setgravitystep", lambda: "%.3f" % rng.uniform(0, 10))
+        sp += pick("setsmoothfactor", lambda: "%.7f" % rng.uniform(0.005, 0.08)) + pick("setsmoothpass", b)
+        files = {"rc.glsl": "\n".join(rc) + "\n"}
+        if sp and rng.random() < 0.8:
+            files["smooth_parameters.glsl"] = "\n".join(sp) + "\n"
+        paths = [_user_dir(tmp_path / f"t{trial}", files), REF_SHADERS]
+        r = rd(paths)
+        try:
+            c = r.cfg
+            p = g.load_config(paths)
+            got = dict(bufsize=p.n, rate=p.rate_request, samplesize=p.samplesize_request, mirror_input=2 - p.channels,
+                       avg_frames=p.avg_frames, avg_window=p.avg_window, smooth_pass=p.smooth_pass, accel_fft=p.accel_fft,
+                       interpolate=p.interpolate, bufscale=p.bufscale, premultiply_alpha=p.premultiply_alpha, w=p.w, h=p.h)
+            assert got == {k: c[k] for k in got}, (trial, files)
+            for ours, theirs in (("fft_scale", "fft_scale"), ("fft_cutoff", "fft_cutoff"), ("gravity_step", "gravity_step"),
+                                 ("smooth_distance", "smooth_distance"), ("smooth_ratio", "smooth_ratio")):
+                assert getattr(p, ours) == np.float32(c[theirs]), (trial, ours, files)
+            assert p.smooth_factor == np.float32("%.6f" % c["smooth_factor"]), (trial, files)
+            assert list(p.clear_color) == [np.float32(c[k]) for k in ("clear_r", "clear_g", "clear_b", "clear_a")], (trial, files)
+            assert (p.fr if c["framerate"] > 0 else 0) == max(c["framerate"], 0) or c["framerate"] <= 0
+        finally:
+            r.close()
