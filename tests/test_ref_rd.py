@@ -271,3 +271,38 @@ def test_random_configs_against_rd_new(rd, tmp_path):
             assert (p.fr if c["framerate"] > 0 else 0) == max(c["framerate"], 0) or c["framerate"] <= 0
         finally:
             r.close()
+
+
+def test_smooth_transform_after_fft_forces_the_cpu_order_chain(rd, tmp_path):
+    """a module whose bind lists "smooth" after "fft" (render.c:1218-1286): under setaccelfft the reference can no longer
+    leave gravity / average to the GL passes and runs fft -> gravity -> average -> smooth on the CPU (render.c:2143-2154);
+    the uploaded buffer is the oracle's transform_smooth chain, NaN head included"""
+    from oracle.oracle import Oracle
+    src = open(os.path.join(REF_SHADERS, "bars", "1.frag")).read()
+    for ch in ("audio_l", "audio_r"):
+        anchor = f'#request transform {ch} "avg"\n'
+        assert anchor in src
+        src = src.replace(anchor, anchor + f'#request transform {ch} "smooth"\n')
+    d = tmp_path / "u"
+    paths = [_user_dir(d, {"rc.glsl": "#request mod bars\n#request setbufsize 1024\n#request setinterpolate false\n"
+                                     "#request setsmooth 0.02\n#request setsmoothratio 3.0\n"}), REF_SHADERS]
+    os.unlink(d / "bars"); (d / "bars").mkdir()                           # a private copy of the module with the extra transform
+    for f in os.listdir(os.path.join(REF_SHADERS, "bars")):
+        (d / "bars" / f).write_text(src if f == "1.frag" else open(os.path.join(REF_SHADERS, "bars", f)).read())
+    r = rd(paths)
+    try:
+        p = g.load_config(paths)
+        assert p.accel_fft == 1 and p.smooth_distance == np.float32(0.02) and p.smooth_ratio == np.float32(3.0)
+        p.ur = 86.1328125
+        st = OracleStream(Oracle("libm"), params_from(p), OrcExt(bufscale=1, interpolate=0, fr=0.0, transform_smooth=1,
+                                                                 smooth_distance=p.smooth_distance, smooth_ratio=p.smooth_ratio))
+        r.set_rates(86.1328125, 86.1328125)
+        rng = np.random.default_rng(17)
+        for k in range(7):
+            pl = (rng.standard_normal(p.n) * 0.2).astype(np.float32); pr = (rng.standard_normal(p.n) * 0.2).astype(np.float32)
+            up = r.frame(pl, pr)
+            sl, sr, _, _ = st.update(pl, pr, True)
+            assert np.array_equal(up[0], sl, equal_nan=True) and np.array_equal(up[1], sr, equal_nan=True), k
+            assert np.isnan(up[0][0])                                      # transform_smooth's b[0] = 0 / 0 (render.c:694-718)
+    finally:
+        r.close()
