@@ -57,7 +57,7 @@ class Params(C.Structure):
         ("graph_color_prog", ColorProg),
         ("clear_color", C.c_float * 4),
         ("radial_bar_width_int", C.c_int), ("radial_bar_outline_width", C.c_float), ("radial_bar_outline", C.c_float * 4),
-        ("graph_join_channels", C.c_int), ("graph_anti_alias", C.c_int),
+        ("graph_join_channels", C.c_int), ("graph_anti_alias", C.c_int), ("shader_pre_smoothed", C.c_int),
     ]
 
     def copy(self):

@@ -593,13 +593,21 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
     ra.batch = r->batch; ra.slots = r->slots; ra.stream0 = 0;
     ra.geo = r->d_geo; ra.gx0 = r->geo_box[0]; ra.gy0 = r->geo_box[1]; ra.gw = r->geo_box[2]; ra.gh = r->geo_box[3];
     ra.texmm = nullptr;
-    if (p.module == GLAVA_B200_MOD_CIRCLE && r->d_geo && !r->no_texmm) {
+    // params.shader_pre_smoothed: the module's stage-1 shader believes something else about its textures than what the
+    // K5 pass did.  Only the raster launch sees that belief (as its smooth_pass); everything before it follows the real one.
+    glava_b200_params pr_store;
+    const glava_b200_params* pr = &p;
+    if (p.shader_pre_smoothed) {
+        pr_store = p; pr_store.smooth_pass = p.shader_pre_smoothed == 1 ? 1 : 0; pr = &pr_store;
+        if (p.module == GLAVA_B200_MOD_CIRCLE) ra.geo = nullptr;          // the circle cache is laid out for the consistent case
+    }
+    if (p.module == GLAVA_B200_MOD_CIRCLE && ra.geo && !r->no_texmm) {
         if ((rc = launch_texmm(p, ra.tex, r->d_texmm, r->batch * 2, r->stream)) != 0) return rc;
         ++r->launches;
         ra.texmm = r->d_texmm;
     }
     if (r->timing && (rc = timing_mark(r->ev_ras, r->stream)) != 0) return rc;
-    if ((rc = launch_raster(p, ra, r->stream)) != 0) return rc;
+    if ((rc = launch_raster(*pr, ra, r->stream)) != 0) return rc;
     if (r->timing && (rc = timing_mark(r->ev_ras, r->stream)) != 0) return rc;
     CU(cudaEventRecord(r->ev_raster_done[b], r->stream));
     {

@@ -754,6 +754,7 @@ int load_config(glava_b200_params* out, const char* const* paths, const char* en
             if (!apply_request(L, tokenize(r), "--request", i + 1)) return GLAVA_B200_ECONFIG;
         }
     }
+    const int pre_module_smooth_pass = out->smooth_pass;   // what the module's stage-1 header will say (see below)
     int mod = module_from_name(L.module.c_str());
     if (mod < 0) {
         fail(GLAVA_B200_ECONFIG, "Could not find module '%s' (B200 path implements: bars radial circle graph wave test)", L.module.c_str());
@@ -796,9 +797,13 @@ int load_config(glava_b200_params* out, const char* const* paths, const char* en
             default: break;
         }
     }
-    // CLI requests are applied last in the reference too (after module load they would hit
-    // `loading_smooth_pass` guards); re-apply so they win over smooth_parameters.glsl.
-    if (requests) for (int i = 0; requests[i]; ++i) apply_request(L, tokenize(requests[i]), "--request", i + 1);
+    // (CLI requests are NOT applied again: in the reference they run once, between rc.glsl and the module load
+    // (render.c:1415-1435), so a request that smooth_parameters.glsl also makes — setsmoothfactor, setavgframes,
+    // setsmoothpass, setfftscale ... — is overridden by it for every module but wave.  Checked against rd_new.)
+    // The module's first shader is compiled with a header built BEFORE its own includes ran their requests
+    // (shaderload: EBIND list at render.c:284-293, ext_process at :312): its `_PRE_SMOOTHED_AUDIO` is smooth_pass as of
+    // the end of rc.glsl + CLI, while the K5 pass follows the final smooth_pass.
+    if (!dirs.empty() && pre_module_smooth_pass != out->smooth_pass) out->shader_pre_smoothed = pre_module_smooth_pass ? 1 : 2;
     apply_defines(out, defs);
     if (has_error()) return GLAVA_B200_ECONFIG;
     out->ur = (float) out->rate_request / (float) (out->samplesize_request / 4);
@@ -815,6 +820,8 @@ int validate_params(const glava_b200_params* p) {
     if (p->channels != 1 && p->channels != 2) return bad("channels");
     if (p->sample_mode < 0 || p->sample_mode > 2 || p->round_formula < 0 || p->round_formula > 2) return bad("sample mode / round formula");
     if (p->radial_nbars < 2) return bad("NBARS");
+    if (p->shader_pre_smoothed < 0 || p->shader_pre_smoothed > 2 || (p->shader_pre_smoothed == 1 && p->smooth_pass) ||
+        (p->shader_pre_smoothed == 2 && !p->smooth_pass)) return bad("shader_pre_smoothed contradicts smooth_pass");
     const glava_b200_color* cols[3] = { &p->bars_color, &p->radial_color, &p->graph_color };
     const glava_b200_color_prog* progs[4] = { &p->bars_color_prog, &p->radial_color_prog, &p->graph_color_prog, &p->bars_outline_prog };
     for (int i = 0; i < 3; ++i) {

@@ -23,7 +23,7 @@ struct alignas(8) TapEntry { int idx; float w; };   // one tap of the K5 smoothi
 // Lazy K5: the texels the module's fragment shader can sample, built with the SAME coordinate helpers the kernels
 // use (raster_core.h).  Returns false when every texel may be needed (circle: continuous angle -> position).
 inline bool build_need_list(const glava_b200_params& p, std::vector<int>* lists /* [2] */) {
-    if (!p.smooth_pass) return false;
+    if (!p.smooth_pass || p.shader_pre_smoothed == 2) return false;   // (2: the shader smooths the K5 output again, any texel)
     std::vector<char> mark[2];
     mark[0].assign(p.n + 1, 0); mark[1].assign(p.n + 1, 0);
     auto hit = [&](int chan, float coord) {

@@ -155,6 +155,12 @@ typedef struct {
     float radial_bar_outline[4];     /* BAR_OUTLINE (default: OUTLINE) */
     int   graph_join_channels;       /* JOIN_CHANNELS (graph.glsl:23): the two halves meet at a common height in the middle */
     int   graph_anti_alias;          /* ANTI_ALIAS (graph.glsl:19): graph/3.frag fades the column steps of the line */
+    int   shader_pre_smoothed;       /* what the module's stage-1 shader believes about its audio textures
+                                        (`_PRE_SMOOTHED_AUDIO`): 0 = what smooth_pass says (consistent), 1 = "already smoothed"
+                                        although the K5 pass is off, 2 = "raw" although K5 ran (smoothed twice).  The reference
+                                        gets into 1 / 2 when smooth_parameters.glsl flips setsmoothpass: the module's first
+                                        shader header is built before its includes' requests run (render.c:284-293, 312);
+                                        the config reader reproduces that */
 } glava_b200_params;
 
 typedef struct glava_b200 glava_b200;    /* plays the role of struct glava_renderer (render.h:8-30) */

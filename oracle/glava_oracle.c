@@ -270,9 +270,12 @@ void orc_smooth_pass(const orc_params* p, const uint16_t* in, uint16_t* out) {
 }
 
 /* the sampler the module shaders use: smooth_audio() of smooth.glsl with
- * _PRE_SMOOTHED_AUDIO = smooth_pass (render.c:292) */
+ * _PRE_SMOOTHED_AUDIO = smooth_pass (render.c:292) — as of the moment the stage-1 header was built: shaderload forms the
+ * EBIND list before the shader's own includes run their requests (render.c:284-293 vs :312), so a setsmoothpass inside
+ * smooth_parameters.glsl changes what the K5 pass does but not what the module's first shader believes */
 static inline float smooth_audio(const orc_params* p, const uint16_t* tex, float idx) {
-    if (p->smooth_pass) return fetch16(tex, p->n, (int) g_round(idx * (float) p->n));
+    const int believed = p->shader_pre_smoothed ? (p->shader_pre_smoothed == 1) : p->smooth_pass;
+    if (believed) return fetch16(tex, p->n, (int) g_round(idx * (float) p->n));
     return smooth_audio_raw(p, tex, p->n, idx);
 }
 static inline float smooth_audio_adj(const orc_params* p, const uint16_t* tex, float idx, float pixel) {

@@ -69,6 +69,7 @@ typedef struct {
     float wave_min_thickness, wave_max_thickness, wave_base_color[4], wave_amplify, wave_outline[4];
     int   graph_join_channels;       /* JOIN_CHANNELS (graph.glsl:23) */
     int   graph_anti_alias;          /* ANTI_ALIAS (graph.glsl:19): graph/3.frag */
+    int   shader_pre_smoothed;       /* the stage-1 header's _PRE_SMOOTHED_AUDIO when it contradicts smooth_pass: 1 = "smoothed", 2 = "raw" (0: consistent) */
     int   radial_bar_width_int;      /* BAR_WIDTH written as an integer literal: `BAR_WIDTH / 2` divides in integers */
     float radial_bar_outline_width, radial_bar_outline[4];   /* BAR_OUTLINE_WIDTH, BAR_OUTLINE (deprecated, radial.glsl:33-36) */
     float clear_color[4];            /* setbg / setbgf (render.c:1062-1099); only visible when premultiply_alpha == 0 */

@@ -42,7 +42,7 @@ class OrcParams(C.Structure):
         ("graph_invert", C.c_int),
         ("wave_min_thickness", C.c_float), ("wave_max_thickness", C.c_float), ("wave_base_color", C.c_float * 4),
         ("wave_amplify", C.c_float), ("wave_outline", C.c_float * 4),
-        ("graph_join_channels", C.c_int), ("graph_anti_alias", C.c_int), ("radial_bar_width_int", C.c_int), ("radial_bar_outline_width", C.c_float), ("radial_bar_outline", C.c_float * 4),
+        ("graph_join_channels", C.c_int), ("graph_anti_alias", C.c_int), ("shader_pre_smoothed", C.c_int), ("radial_bar_width_int", C.c_int), ("radial_bar_outline_width", C.c_float), ("radial_bar_outline", C.c_float * 4),
         ("clear_color", C.c_float * 4),
     ]
 
@@ -320,6 +320,8 @@ class ReferenceRenderer:
             L.ref_rd_upload.argtypes = [vp, C.c_int, C.POINTER(C.c_int), vp, C.c_int]
             L.ref_rd_set_rates.argtypes = [vp, C.c_float, C.c_float]
             L.ref_rd_destroy.argtypes = [vp]
+            L.ref_rd_source.restype = C.c_char_p
+            L.ref_rd_source.argtypes = [C.c_int]
             cls._L = L
         return cls._L
 
@@ -329,9 +331,12 @@ class ReferenceRenderer:
         pa = (C.c_char_p * (len(paths) + 1))(*[p.encode() for p in paths], None)
         rq = (C.c_char_p * (len(requests) + 1))(*[r.encode() for r in requests], None)
         self.L = L
+        L.ref_rd_clear_sources()
         self.h = L.ref_rd_new(pa, entry.encode(), rq)
         if not self.h:
             raise ValueError("the reference aborted in rd_new")
+        # every text rd_new handed to glShaderSource, in load order: vertex + fragment per module stage, then the util passes
+        self.sources = [L.ref_rd_source(i).decode() for i in range(L.ref_rd_source_count())]
         self.cfg = self.config()
         self.lb = np.zeros(self.cfg["bufsize"], np.float32)            # glava.c:487-494: lb / rb persist across frames
         self.rb = np.zeros(self.cfg["bufsize"], np.float32)

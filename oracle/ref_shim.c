@@ -216,6 +216,23 @@ static void   ng_get_integerv(GLenum pname, GLint* out) { (void) pname; *out = 1
 static GLenum ng_fb_status(GLenum target) { (void) target; return GL_FRAMEBUFFER_COMPLETE; }
 static void   ng_bind_texture(GLenum target, GLuint tex) { if (target == GL_TEXTURE_1D) ng_bound_1d = tex; }
 
+/* the text rd_new hands to the GLSL compiler (glShaderSource, render.c:335-337): injected header + glsl_ext output */
+#define NG_MAX_SOURCES 64
+static char* ng_sources[NG_MAX_SOURCES];
+static int   ng_source_count = 0;
+static void ng_shader_source(GLuint shader, GLsizei count, const GLchar* const* strings, const GLint* lengths) {
+    (void) shader;
+    if (ng_source_count == NG_MAX_SOURCES || count < 1) return;
+    const size_t len = lengths ? (size_t) lengths[0] : strlen(strings[0]);
+    ng_sources[ng_source_count] = malloc(len + 1);
+    memcpy(ng_sources[ng_source_count], strings[0], len);
+    ng_sources[ng_source_count][len] = '\0';
+    ++ng_source_count;
+}
+int ref_rd_source_count(void) { return ng_source_count; }
+const char* ref_rd_source(int idx) { return (idx >= 0 && idx < ng_source_count) ? ng_sources[idx] : NULL; }
+void ref_rd_clear_sources(void) { for (int i = 0; i < ng_source_count; ++i) free(ng_sources[i]); ng_source_count = 0; }
+
 #define NG_MAX_UPLOADS 64
 static struct { GLuint tex; int width; float* data; } ng_uploads[NG_MAX_UPLOADS];
 static int ng_upload_count = 0;
@@ -240,7 +257,7 @@ static void ng_install(void) {
     NG_NOOP(glBindFragDataLocation); NG_NOOP(glAttachShader); NG_NOOP(glUniform2i); NG_NOOP(glEnableVertexAttribArray);
     NG_NOOP(glDisableVertexAttribArray); NG_NOOP(glBlendEquation); NG_NOOP(glBindBuffer); NG_NOOP(glVertexAttribPointer);
     NG_NOOP(glUniform4f); NG_NOOP(glUniform3f); NG_NOOP(glUniform2f); NG_NOOP(glTextureBarrierNV); NG_NOOP(glTexImage2D);
-    NG_NOOP(glShaderSource); NG_NOOP(glReadPixels); NG_NOOP(glLinkProgram); NG_NOOP(glGetShaderInfoLog); NG_NOOP(glGetProgramInfoLog);
+    NG_NOOP(glReadPixels); NG_NOOP(glLinkProgram); NG_NOOP(glGetShaderInfoLog); NG_NOOP(glGetProgramInfoLog);
     NG_NOOP(glFramebufferTexture2D); NG_NOOP(glFramebufferTexture1D); NG_NOOP(glDrawArrays); NG_NOOP(glCompileShader);
     NG_NOOP(glClearColor); NG_NOOP(glClear); NG_NOOP(glBufferData); NG_NOOP(glBlendFunc);
 #undef NG_NOOP
@@ -251,6 +268,7 @@ static void ng_install(void) {
     glad_glGetShaderiv = ng_get_objectiv; glad_glGetProgramiv = ng_get_objectiv;
     glad_glGetIntegerv = ng_get_integerv; glad_glCheckFramebufferStatus = ng_fb_status;
     glad_glBindTexture = ng_bind_texture; glad_glTexImage1D = ng_tex_image_1d;
+    glad_glShaderSource = (__typeof__(glad_glShaderSource)) ng_shader_source;
 }
 
 /* ---- window backend "null" (struct gl_wcb, render.h:66-104) ---- */

@@ -171,7 +171,7 @@ void emul_eval_color(const glava_b200_color_prog* prog, float x, float out[4]) {
 // per-pixel reference semantics (raster_generic_kernel)
 void emul_raster(const glava_b200_params* pp, const uint16_t* tl, const uint16_t* tr, uint8_t* out, int y0, int y1) {
     const glava_b200_params& p = *pp;
-    AudioTex t; t.l = tl; t.r = tr; t.n = p.n; t.pre_smoothed = p.smooth_pass; t.sp = smooth_params(p);
+    AudioTex t; t.l = tl; t.r = tr; t.n = p.n; t.pre_smoothed = p.shader_pre_smoothed ? (p.shader_pre_smoothed == 1) : p.smooth_pass;   /* capi.cu run_update: the raster launch's view */ t.sp = smooth_params(p);
     uint32_t* dst = reinterpret_cast<uint32_t*>(out);
     for (int y = y0; y < y1; ++y) for (int x = 0; x < p.w; ++x) dst[(size_t) y * p.w + x] = module_px(p, t, x, y);
 }
@@ -179,7 +179,7 @@ void emul_raster(const glava_b200_params* pp, const uint16_t* tl, const uint16_t
 // hoisted evaluation exactly as raster_bars_kernel / raster_graph_kernel / raster_wave_kernel do it
 int emul_raster_fast(const glava_b200_params* pp, const uint16_t* tl, const uint16_t* tr, uint8_t* out) {
     const glava_b200_params& p = *pp;
-    AudioTex t; t.l = tl; t.r = tr; t.n = p.n; t.pre_smoothed = p.smooth_pass; t.sp = smooth_params(p);
+    AudioTex t; t.l = tl; t.r = tr; t.n = p.n; t.pre_smoothed = p.shader_pre_smoothed ? (p.shader_pre_smoothed == 1) : p.smooth_pass;   /* capi.cu run_update: the raster launch's view */ t.sp = smooth_params(p);
     uint32_t* dst = reinterpret_cast<uint32_t*>(out);
     if (p.module == GLAVA_B200_MOD_BARS && !p.bars_mirror_yx) {
         std::vector<BarsCol> col(p.w);

@@ -21,14 +21,15 @@ def fuzz(built):
 
 
 # 207 / 267: circle, C_SMOOTH 0, non-native opacity (the pass-through stage 2); 131: a 1-LSB radial pixel; 5 / 12 / 26 / 33:
-# setsmoothpass false with a random smooth_parameters.glsl (the tap loop runs in the module shader); 166 / 586 / 803 / 985:
+# setsmoothpass flipped in rc.glsl and / or a random smooth_parameters.glsl (the three consistent / stale-header variants of
+# tools/fuzz_module_configs.py); 166 / 586 / 803 / 985:
 # the same with a smooth factor whose "%.6f" header literal differs from the request's float; the rest: a spread
 @pytest.mark.parametrize("seed", [207, 267, 131, 5, 12, 26, 33, 166, 586, 803, 985] + list(range(40, 66)))
 def test_random_module_config(fuzz, seed):
     module = ["bars", "radial", "circle", "graph", "wave"][seed % 5]
     w, h = [(40, 28), (41, 27), (38, 30)][seed % 3]
     text, want, oracle, product = fuzz.run(seed, module, w, h, native=(seed % 4 != 3),
-                                           smooth_in_shader=(seed % 7 == 5 and module in ("bars", "radial", "circle", "graph")))
+                                           smooth_in_shader=((1 + seed // 7 % 3) if (seed % 7 == 5 and module in ("bars", "radial", "circle", "graph")) else False))
     assert want.any(), text
     assert np.array_equal(oracle, want), (seed, module, text)
     assert int(np.abs(product.astype(int) - want.astype(int)).max()) <= 1, (seed, module, text)

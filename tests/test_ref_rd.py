@@ -306,3 +306,32 @@ def test_smooth_transform_after_fft_forces_the_cpu_order_chain(rd, tmp_path):
             assert np.isnan(up[0][0])                                      # transform_smooth's b[0] = 0 / 0 (render.c:694-718)
     finally:
         r.close()
+
+
+@pytest.mark.parametrize("rc_extra,sp,state", [
+    ("", "", (1, 0)),                                                                       # shipped: consistent
+    ("#request setsmoothpass false\n", "#request setsmoothpass false\n", (0, 0)),           # off everywhere: shader smooths
+    ("", "#request setsmoothpass false\n", (0, 1)),                                         # off where the shipped config sets it
+    ("#request setsmoothpass false\n", "", (1, 2)),                                         # off in rc.glsl only: smoothed twice
+])
+def test_stage1_header_is_built_before_its_includes_run_their_requests(rd, tmp_path, rc_extra, sp, state):
+    """shaderload forms `#define _PRE_SMOOTHED_AUDIO ...` (EBIND list, render.c:284-293) before ext_process runs the shader's
+    own includes (:312): the module's FIRST shader believes smooth_pass as of the end of rc.glsl, the K5 pass follows the final
+    value.  (params.smooth_pass, params.shader_pre_smoothed) must say exactly that."""
+    import re
+    files = {"rc.glsl": "#request mod bars\n" + rc_extra}
+    if sp:
+        files["smooth_parameters.glsl"] = open(os.path.join(REF_SHADERS, "smooth_parameters.glsl")).read() + sp
+    paths = [_user_dir(tmp_path / "u", files), REF_SHADERS]
+    r = rd(paths)
+    try:
+        p = g.load_config(paths)
+        assert (p.smooth_pass, p.shader_pre_smoothed) == state
+        assert r.cfg["smooth_pass"] == p.smooth_pass                                        # whether K5 runs
+        stage1 = next(s for s in r.sources if "BAR_WIDTH" in s)                              # bars/1.frag, the first shader loaded
+        believed = int(re.search(r"#define _PRE_SMOOTHED_AUDIO (\d)", stage1).group(1))
+        assert believed == ((p.shader_pre_smoothed == 1) if p.shader_pre_smoothed else p.smooth_pass)
+        k5 = next(s for s in r.sources if "smooth_audio(tex, sz" in s)                       # util/smooth_pass.frag is loaded later
+        assert "#define _PRE_SMOOTHED_AUDIO %d" % p.smooth_pass in k5
+    finally:
+        r.close()

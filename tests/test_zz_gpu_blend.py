@@ -123,3 +123,23 @@ def test_graph_anti_alias_stage(orc_pm, case, built):
         r.raster_textures(tl[None], tr[None])
         got = r.readback(0)
     assert np.array_equal(got, orc_pm.raster(op, tl, tr))
+
+
+@pytest.mark.parametrize("module", ["bars", "radial", "circle", "graph"])
+def test_stage1_shader_belief_about_its_textures(orc_pm, module, built):
+    """params.shader_pre_smoothed: the raster launch sees the module shader's (possibly stale) `_PRE_SMOOTHED_AUDIO`, not the
+    K5 decision.  On the same textures, "believes smoothed although K5 is off" renders like smooth_pass = 1, and "believes raw
+    although K5 ran" like smooth_pass = 0."""
+    n, w, h = 512, 320, 200
+    rng = np.random.default_rng(6)
+    tl = (rng.random(n) ** 2 * 65535).astype(np.uint16); tr = (rng.random(n) ** 3 * 65535).astype(np.uint16)
+    frames = {}
+    for key, over in (("on", dict(smooth_pass=1)), ("off", dict(smooth_pass=0)),
+                      ("stale_on", dict(smooth_pass=0, shader_pre_smoothed=1)), ("stale_off", dict(smooth_pass=1, shader_pre_smoothed=2))):
+        p = g.default_params(module, n=n, w=w, h=h, **over)
+        with g.Renderer(p, batch=1) as r:
+            r.raster_textures(tl[None], tr[None])
+            frames[key] = r.readback(0)
+        assert np.array_equal(frames[key], orc_pm.raster(params_from(p), tl, tr)), (module, key)
+    assert np.array_equal(frames["stale_on"], frames["on"]) and np.array_equal(frames["stale_off"], frames["off"])
+    assert not np.array_equal(frames["on"], frames["off"])

@@ -72,26 +72,35 @@ def run(seed, module, w, h, n=128, native=True, smooth_in_shader=False):
         rc+='#request setopacity "none"\n#request setbgf %r %r %r %r\n' % clear
     if rng.random()<0.3: rc+="#request setmirror true\n"
     hdr_extra = {}
+    want_state = None
     if smooth_in_shader:
-        # setsmoothpass false: the module shader runs smooth_audio()'s tap loop itself (_PRE_SMOOTHED_AUDIO 0) with the
-        # user's smooth_parameters.glsl
+        # setsmoothpass and the module's belief about its textures.  The stage-1 header (`_PRE_SMOOTHED_AUDIO`) is built from
+        # smooth_pass as of the end of rc.glsl, BEFORE the shader's own includes run smooth_parameters.glsl's requests
+        # (render.c:284-293 vs :312), while the K5 pass follows the final value:
+        #   variant 0  false in rc.glsl and in smooth_parameters.glsl -> shader smooths the raw texture itself   (0, 0)
+        #   variant 1  false only in smooth_parameters.glsl           -> shader believes "smoothed", K5 is off   (0, 1)
+        #   variant 2  false only in rc.glsl                          -> K5 runs AND the shader smooths again    (1, 2)
+        variant = int(smooth_in_shader) - 1 if smooth_in_shader is not True else 0
         sf = float(np.float32(rng.uniform(0.01, 0.05)))
-        sp = "#request setsmoothpass false\n#request setsmoothfactor %r\n" % sf
+        final = "true" if variant == 2 else "false"
+        sp = "#request setsmoothpass %s\n#request setsmoothfactor %r\n" % (final, sf)
         sp += "#define SAMPLE_MODE %s\n#define ROUND_FORMULA %s\n" % (rng.choice(["average", "maximum", "hybrid"]), rng.choice(["sinusoidal", "linear", "circular"]))
         sp += "#define SAMPLE_SCALE %s\n#define SAMPLE_RANGE %s\n#define SAMPLE_HYBRID_WEIGHT %s\n" % (num(rng, 4, 10), num(rng, 0.5, 0.95, False), num(rng, 0.3, 0.9, False))
         open(d+"/smooth_parameters.glsl","w").write(sp)
-        hdr_extra = dict(pre_smoothed=0, smooth_factor=sf)
+        if variant != 1: rc += "#request setsmoothpass false\n"
+        hdr_extra = dict(pre_smoothed=1 if variant == 1 else 0, smooth_factor=sf)
+        want_state = [(0, 0), (0, 1), (1, 2)][variant]
     open(d+"/rc.glsl","w").write(rc); open(f"{d}/{module}.glsl","w").write(text)
     p=g.load_config([d, REF])
     n=p.n
     op=params_from(p)
-    if smooth_in_shader:
+    if smooth_in_shader and want_state != (1, 2):
         tl=(rng.random(n)**2*65535).astype(np.uint16); tr=(rng.random(n)**3*65535).astype(np.uint16)
     else:
         tl=orc.smooth_pass(op,(rng.random(n)**2*65535).astype(np.uint16)); tr=orc.smooth_pass(op,(rng.random(n)**3*65535).astype(np.uint16))
     if module=="wave": tl=np.clip(tl.astype(int)//4+24576,0,65535).astype(np.uint16)
     hdr=dict(premultiply_alpha=p.premultiply_alpha, channels=p.channels, **hdr_extra)
-    assert p.smooth_pass == (0 if smooth_in_shader else 1)
+    assert (p.smooth_pass, p.shader_pre_smoothed) == (want_state or (1, 0)), (p.smooth_pass, p.shader_pre_smoothed, want_state)
     prog=gi.ModuleProgram(REF, module, w, h, tl, tr, config_dir=d, clear_color=clear, **hdr)
     want=np.array([[prog.pixel(x,y) for x in range(w)] for y in range(h)],np.uint8)
     o=orc.raster(op,tl,tr); e=emul.raster(p,tl,tr)
@@ -103,7 +112,7 @@ if __name__=="__main__":
         module=["bars","radial","circle","graph","wave"][seed%5]
         w,h=[(40,28),(41,27),(38,30)][seed%3]
         try:
-            text,want,o,e=run(seed,module,w,h,native=(seed%4!=3),smooth_in_shader=(seed%7==5 and module in ('bars','radial','circle','graph')))
+            text,want,o,e=run(seed,module,w,h,native=(seed%4!=3),smooth_in_shader=((1 + seed // 7 % 3) if (seed%7==5 and module in ('bars','radial','circle','graph')) else False))
         except Exception as ex:
             print(seed,module,"EXC",repr(ex)[:300]); bad+=1; continue
         do=(o!=want).any(axis=2).sum(); de=(e!=want).any(axis=2).sum(); lsb=int(np.abs(e.astype(int)-want.astype(int)).max())
