@@ -335,3 +335,42 @@ def test_stage1_header_is_built_before_its_includes_run_their_requests(rd, tmp_p
         assert "#define _PRE_SMOOTHED_AUDIO %d" % p.smooth_pass in k5
     finally:
         r.close()
+
+
+@pytest.mark.parametrize("module", ["bars", "radial", "circle", "graph", "wave", "test"])
+def test_interpreter_consumes_what_rd_new_hands_to_the_glsl_compiler(rd, module):
+    """every fragment shader text the real rd_new passes to glShaderSource — injected header (render.c:315-327) + glsl_ext
+    output — preprocesses to the same token stream as the interpreter's own pipeline (header_macros + ext_process) for the
+    same file: module stages in order, then util/smooth_pass, gravity_pass, average_pass, pass.  Stages that `#error
+    __disablestage` do so on both sides."""
+    from oracle import glsl_interp as gi
+    r = rd([REF_SHADERS], requests=[f"mod {module}"])
+    try:
+        frags = r.sources[0::2]                                            # a raw vertex shader follows every fragment shader
+        avg = r.cfg["avg_frames"]                                          # 5 from smooth_parameters.glsl; wave never reads it: 6
+        assert avg == (6 if module == "wave" else 5)
+        files = []
+        k = 1
+        while os.path.exists(os.path.join(REF_SHADERS, module, f"{k}.frag")):
+            files.append(os.path.join(REF_SHADERS, module, f"{k}.frag")); k += 1
+        files += [os.path.join(REF_SHADERS, "util", f) for f in ("smooth_pass.frag", "gravity_pass.frag", "average_pass.frag", "pass.frag")]
+        assert len(frags) == len(files), (len(frags), files)
+        for path, real in zip(files, frags):
+            def tokens(lines, predefine):
+                pp = gi.Preprocessor()
+                if predefine:
+                    gi.header_macros(pp, avg_frames=avg)
+                try:
+                    return [t for t in pp.run(lines) if t[1] not in ("#",)]
+                except gi.DisabledStage:
+                    return "disabled"
+            cd = os.path.dirname(path)
+            mine = tokens(gi.ext_process(path, gi.ExtCtx(cd, REF_SHADERS, REF_SHADERS, {"_AVG_FRAMES": avg}, fallback=REF_SHADERS)), True)
+            theirs = tokens(gi._strip_comments(real).split("\n"), False)
+            if mine == "disabled" or theirs == "disabled":
+                assert mine == theirs, path
+                continue
+            # the real header declares `uniform <type> STDIN;` inside `#if USE_STDIN == 1` (inactive) and nothing else beyond macros
+            assert mine == theirs, (path, next((i, a, b) for i, (a, b) in enumerate(zip(mine, theirs)) if a != b))
+    finally:
+        r.close()
