@@ -210,7 +210,42 @@ static GLenum ng_get_error(void) { return GL_NO_ERROR; }
 static GLuint ng_create_shader(GLenum type) { (void) type; return ng_next_id++; }
 static GLuint ng_create_program(void) { return ng_next_id++; }
 static void   ng_gen(GLsizei n, GLuint* out) { for (GLsizei i = 0; i < n; ++i) out[i] = ng_next_id++; }
-static GLint  ng_uniform_location(GLuint p, const GLchar* name) { (void) p; (void) name; return 1; }
+/* uniform locations: one id per distinct name, so that writes to the `--pipe` uniforms (`_IN_<name>`, render.c:2071-2100) can
+ * be told apart and recorded */
+#define NG_MAX_NAMES 128
+static char* ng_names[NG_MAX_NAMES];
+static int   ng_name_count = 0;
+static GLint ng_uniform_location(GLuint p, const GLchar* name) {
+    (void) p;
+    for (int i = 0; i < ng_name_count; ++i) if (!strcmp(ng_names[i], name)) return i + 1;
+    if (ng_name_count == NG_MAX_NAMES) return 0;
+    ng_names[ng_name_count] = strdup(name);
+    return ++ng_name_count;
+}
+#define NG_MAX_PIPE_WRITES 256
+static struct { int loc, count, is_int; float v[4]; } ng_pipe_writes[NG_MAX_PIPE_WRITES];
+static int ng_pipe_write_count = 0;
+static void ng_record_uniform(GLint loc, int count, int is_int, float a, float b, float c, float d) {
+    if (loc < 1 || loc > ng_name_count || strncmp(ng_names[loc - 1], "_IN_", 4) != 0 || ng_pipe_write_count == NG_MAX_PIPE_WRITES) return;
+    ng_pipe_writes[ng_pipe_write_count].loc = loc; ng_pipe_writes[ng_pipe_write_count].count = count;
+    ng_pipe_writes[ng_pipe_write_count].is_int = is_int;
+    ng_pipe_writes[ng_pipe_write_count].v[0] = a; ng_pipe_writes[ng_pipe_write_count].v[1] = b;
+    ng_pipe_writes[ng_pipe_write_count].v[2] = c; ng_pipe_writes[ng_pipe_write_count].v[3] = d;
+    ++ng_pipe_write_count;
+}
+static void ng_uniform1i(GLint loc, GLint v) { ng_record_uniform(loc, 1, 1, (float) v, 0, 0, 0); }
+static void ng_uniform1f(GLint loc, GLfloat a) { ng_record_uniform(loc, 1, 0, a, 0, 0, 0); }
+static void ng_uniform2f(GLint loc, GLfloat a, GLfloat b) { ng_record_uniform(loc, 2, 0, a, b, 0, 0); }
+static void ng_uniform3f(GLint loc, GLfloat a, GLfloat b, GLfloat c) { ng_record_uniform(loc, 3, 0, a, b, c, 0); }
+static void ng_uniform4f(GLint loc, GLfloat a, GLfloat b, GLfloat c, GLfloat d) { ng_record_uniform(loc, 4, 0, a, b, c, d); }
+int ref_rd_pipe_write_count(void) { return ng_pipe_write_count; }
+/* write `idx` since the last ref_rd_update: the uniform's name (without `_IN_`), component count (-1: an int / bool), values */
+const char* ref_rd_pipe_write(int idx, int* count, float* vals) {
+    if (idx < 0 || idx >= ng_pipe_write_count) return NULL;
+    *count = ng_pipe_writes[idx].is_int ? -1 : ng_pipe_writes[idx].count;
+    memcpy(vals, ng_pipe_writes[idx].v, sizeof(float) * 4);
+    return ng_names[ng_pipe_writes[idx].loc - 1] + 4;
+}
 static void   ng_get_objectiv(GLuint o, GLenum pname, GLint* out) { (void) o; *out = (pname == GL_INFO_LOG_LENGTH) ? 0 : GL_TRUE; }
 static void   ng_get_integerv(GLenum pname, GLint* out) { (void) pname; *out = 1024; }
 static GLenum ng_fb_status(GLenum target) { (void) target; return GL_FRAMEBUFFER_COMPLETE; }
@@ -252,15 +287,17 @@ static void ng_tex_image_1d(GLenum target, GLint level, GLint ifmt, GLsizei widt
 
 static void ng_install(void) {
 #define NG_NOOP(fn) glad_##fn = (__typeof__(glad_##fn)) ng_noop
-    NG_NOOP(glUniform1i); NG_NOOP(glUseProgram); NG_NOOP(glViewport); NG_NOOP(glBindFramebuffer); NG_NOOP(glTexParameteri);
-    NG_NOOP(glDisable); NG_NOOP(glActiveTexture); NG_NOOP(glEnable); NG_NOOP(glBindVertexArray); NG_NOOP(glUniform1f);
+    NG_NOOP(glUseProgram); NG_NOOP(glViewport); NG_NOOP(glBindFramebuffer); NG_NOOP(glTexParameteri);
+    NG_NOOP(glDisable); NG_NOOP(glActiveTexture); NG_NOOP(glEnable); NG_NOOP(glBindVertexArray);
     NG_NOOP(glBindFragDataLocation); NG_NOOP(glAttachShader); NG_NOOP(glUniform2i); NG_NOOP(glEnableVertexAttribArray);
     NG_NOOP(glDisableVertexAttribArray); NG_NOOP(glBlendEquation); NG_NOOP(glBindBuffer); NG_NOOP(glVertexAttribPointer);
-    NG_NOOP(glUniform4f); NG_NOOP(glUniform3f); NG_NOOP(glUniform2f); NG_NOOP(glTextureBarrierNV); NG_NOOP(glTexImage2D);
+    NG_NOOP(glTextureBarrierNV); NG_NOOP(glTexImage2D);
     NG_NOOP(glReadPixels); NG_NOOP(glLinkProgram); NG_NOOP(glGetShaderInfoLog); NG_NOOP(glGetProgramInfoLog);
     NG_NOOP(glFramebufferTexture2D); NG_NOOP(glFramebufferTexture1D); NG_NOOP(glDrawArrays); NG_NOOP(glCompileShader);
     NG_NOOP(glClearColor); NG_NOOP(glClear); NG_NOOP(glBufferData); NG_NOOP(glBlendFunc);
 #undef NG_NOOP
+    glad_glUniform1i = ng_uniform1i; glad_glUniform1f = ng_uniform1f; glad_glUniform2f = ng_uniform2f;
+    glad_glUniform3f = ng_uniform3f; glad_glUniform4f = ng_uniform4f;
     glad_glGetError = ng_get_error;
     glad_glCreateShader = ng_create_shader; glad_glCreateProgram = ng_create_program;
     glad_glGenTextures = ng_gen; glad_glGenFramebuffers = ng_gen; glad_glGenVertexArrays = ng_gen; glad_glGenBuffers = ng_gen;
@@ -305,6 +342,7 @@ static struct gl_wcb ref_null_wcb = {
     .set_time = nw_set_time, .set_visible = nw_set_visible, .get_environment = nw_environment
 };
 
+static const char* bind_types_name(int t) { return bind_types[t].n; }
 static jmp_buf ref_rd_jmp;
 static void ref_rd_abort(void) { longjmp(ref_rd_jmp, 1); }
 
@@ -316,6 +354,22 @@ void* ref_rd_new(const char** paths, const char* entry, const char** requests) {
     struct glava_renderer* r = NULL;
     glava_abort = ref_rd_abort;
     if (setjmp(ref_rd_jmp) == 0) r = rd_new(paths, entry, requests, "null", no_binds, STDIN_TYPE_NONE, false, false, false);
+    glava_abort = saved;
+    return r;
+}
+
+/* the same with `--pipe NAME[:TYPE]` binds (glava.c:338-411 builds exactly this array): types as STDIN_TYPE_* (render.h:32-38) */
+void* ref_rd_new_binds(const char** paths, const char* entry, const char** requests, const char** bind_names, const int* bind_types) {
+    if (wcbs_idx == 0) register_wcb(&ref_null_wcb);
+    static struct rd_bind binds[17];
+    size_t nb = 0;
+    for (; bind_names && bind_names[nb] && nb < 16; ++nb)
+        binds[nb] = (struct rd_bind) { .name = bind_names[nb], .stype = bind_types_name(bind_types[nb]), .type = bind_types[nb] };
+    binds[nb] = (struct rd_bind) { .name = NULL };
+    void (*saved)(void) = glava_abort;
+    struct glava_renderer* r = NULL;
+    glava_abort = ref_rd_abort;
+    if (setjmp(ref_rd_jmp) == 0) r = rd_new(paths, entry, requests, "null", binds, STDIN_TYPE_NONE, false, false, false);
     glava_abort = saved;
     return r;
 }
@@ -338,6 +392,7 @@ void ref_rd_set_rates(void* rp, float ur, float fr) { struct gl_data* gl = ((str
  * texture uploads recorded during the call (fetch them with ref_rd_upload), or -1 when the reference aborted. */
 int ref_rd_update(void* rp, float* lb, float* rb, size_t bsz, int modified) {
     ng_clear_uploads();
+    ng_pipe_write_count = 0;
     void (*saved)(void) = glava_abort;
     int rc = 0;
     glava_abort = ref_rd_abort;

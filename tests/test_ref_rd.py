@@ -374,3 +374,39 @@ def test_interpreter_consumes_what_rd_new_hands_to_the_glsl_compiler(rd, module)
             assert mine == theirs, (path, next((i, a, b) for i, (a, b) in enumerate(zip(mine, theirs)) if a != b))
     finally:
         r.close()
+
+
+def test_pipe_line_parser_against_the_one_inside_rd_update(rd, built):
+    """the `--pipe` stdin parser is part of rd_update (render.c:1846-2005): the real one gets a pipe as stdin and one line per
+    frame (oracle/ref_pipe_driver.py, a subprocess); the uniform writes it makes are what glava_b200_pipe_feed must store"""
+    import json
+    import subprocess
+    import sys
+    binds = [["fg", "vec4"], ["bg", "vec4"], ["amp", "float"], ["on", "bool"], ["k", "int"], ["p2", "vec2"], ["p3", "vec3"]]
+    lines = ["fg = #ff8000", "  bg=#10203040   ", "fg = 0.5, 0.25,1,0.75", "#0xabcdef", "a = 3.5", "= #000000ff", "on = true", "on = 0",
+             "on = TRUE", "on = False", "on = maybe", "k = 42abc", "k = -7", "p2 = 1.5,2.5", "p2 = 9", "p3 = 1,2,3", "p3 = 4", "nope = 1",
+             "fg =   ", "bg = #12x456", "amp = 1e3", "amp=-0.125", "f = 1,2", "b = #80", "bg = #123", "0.1,0.2,0.3,0.4", "amp = abc",
+             "p = 7,8", "fg=#FFFFFFFF", "k=0x10", "on=1"]
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_pipe_driver.py"),
+                          json.dumps({"shaders": REF_SHADERS, "binds": binds, "lines": lines})], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-2000:]
+    ref = json.loads(next(ln for ln in out.stdout.splitlines() if ln.startswith("RESULT "))[7:])
+    assert len(ref) == len(lines)
+    with g.Pipe([f"{n}:{t}" for n, t in binds]) as pipe:
+        width = {"vec4": 4, "vec3": 3, "vec2": 2, "float": 1}
+        for line, writes in zip(lines, ref):
+            before = pipe.binds()
+            changed = pipe.feed(line + "\n")
+            after = pipe.binds()
+            assert changed == (1 if writes else 0), (line, writes)
+            for name, (typ, val) in after.items():
+                hit = [w for w in writes if w[0] == name]
+                if not hit:
+                    assert val == before[name][1], (line, name)          # untouched by this line
+                    continue
+                _, count, vals = hit[0]
+                if typ in ("bool", "int"):
+                    assert count == -1 and val[0] == vals[0], (line, name, val, vals)
+                else:
+                    assert count == width[typ] and list(val[:count]) == [np.float32(v) for v in vals[:count]], (line, name, val, vals)
