@@ -163,7 +163,7 @@ def test_fifo_gather_chunks_silence_partial_and_cadence(built, orc, tmp_path):
             os.write(fds[1], raw[:300]); os.write(fds[1], raw[300:])
             t0 = time.time()
             chunks, fresh = fr.gather()
-            assert time.time() - t0 < 0.04 and fresh.all() and np.array_equal(chunks, sent[1])
+            assert time.time() - t0 < 0.045 and fresh.all() and np.array_equal(chunks, sent[1])
             assert 1 <= fr.timeout_ms <= 500                             # deadline now follows the producer (fifo.c:82-87)
             # tick 3: half a chunk only -> silence this tick, the bytes stay queued ...
             raw = sent[2, 1].tobytes()
@@ -287,7 +287,7 @@ def test_a_silent_stream_costs_one_deadline_then_stops_holding_the_batch_up(buil
             for t in range(1, ticks - 1):
                 t0 = time.time()
                 chunks, fresh = fr.gather()
-                assert time.time() - t0 < 0.03, t                        # no waiting for the silent stream any more
+                assert time.time() - t0 < 0.045, t                       # no waiting for the silent stream any more
                 assert fresh.tolist() == [True, True, False] and np.array_equal(chunks[:2], sent[t]) and not chunks[2].any()
             late = rng.integers(-32768, 32767, samplesz // 2, dtype=np.int16)
             os.write(fds[2], late.tobytes())                             # the silent stream comes back
