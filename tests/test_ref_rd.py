@@ -410,3 +410,22 @@ def test_pipe_line_parser_against_the_one_inside_rd_update(rd, built):
                     assert count == -1 and val[0] == vals[0], (line, name, val, vals)
                 else:
                     assert count == width[typ] and list(val[:count]) == [np.float32(v) for v in vals[:count]], (line, name, val, vals)
+
+
+@pytest.mark.parametrize("args,ours", [
+    (["--pipe=1abc"], lambda: g.Pipe(["1abc"])), (["--pipe=a-b"], lambda: g.Pipe(["a-b"])), (["--pipe=:vec4"], lambda: g.Pipe([":vec4"])),
+    (["--pipe=x:mat4"], lambda: g.Pipe(["x:mat4"])), (["--pipe=fg", "--pipe=fg:float"], lambda: g.Pipe(["fg", "fg:float"])),
+    (["--audio=nope"], lambda: __import__("glava_b200").audio.find_backend("nope")),
+])
+def test_argument_errors_word_for_word(rd, args, ours):
+    """what the reference's glava_entry prints when it rejects `--pipe NAME[:TYPE]` / `--audio NAME` is what the library
+    reports for the same argument"""
+    import subprocess
+    import sys
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_entry_driver.py")] + args, capture_output=True, text=True, timeout=60)
+    theirs = out.stderr.strip()
+    assert theirs and out.returncode != 0
+    with pytest.raises(g.GlavaError) as e:
+        ours()
+    assert str(e.value).strip() == theirs
