@@ -275,8 +275,25 @@ static void ng_clear_uploads(void) {
     for (int i = 0; i < ng_upload_count; ++i) free(ng_uploads[i].data);
     ng_upload_count = 0;
 }
+/* whole-program runs (ref_glava_entry): every float upload that differs from the previous one of the same texture is
+ * appended to a file as {int32 texture id, int32 width, float[width]} */
+static FILE*  ng_log_file = NULL;
+static float* ng_log_last[2] = { NULL, NULL };
+static GLuint ng_log_tex[2] = { 0, 0 };
+static int    ng_log_width[2] = { 0, 0 };
+static void ng_log_upload(GLuint tex, int width, const float* data) {
+    int slot = (ng_log_tex[0] == tex || ng_log_tex[0] == 0) ? 0 : 1;
+    if (ng_log_tex[slot] != 0 && ng_log_tex[slot] != tex) return;                     /* a third texture: not an audio bind */
+    if (ng_log_last[slot] && ng_log_width[slot] == width && !memcmp(ng_log_last[slot], data, sizeof(float) * (size_t) width)) return;
+    ng_log_tex[slot] = tex; ng_log_width[slot] = width;
+    ng_log_last[slot] = realloc(ng_log_last[slot], sizeof(float) * (size_t) width);
+    memcpy(ng_log_last[slot], data, sizeof(float) * (size_t) width);
+    int32_t hdr[2] = { (int32_t) tex, (int32_t) width };
+    fwrite(hdr, sizeof(hdr), 1, ng_log_file); fwrite(data, sizeof(float), (size_t) width, ng_log_file); fflush(ng_log_file);
+}
 static void ng_tex_image_1d(GLenum target, GLint level, GLint ifmt, GLsizei width, GLint border, GLenum format, GLenum type, const void* pixels) {
     (void) target; (void) level; (void) ifmt; (void) border; (void) format;
+    if (pixels && type == GL_FLOAT && ng_log_file) { ng_log_upload(ng_bound_1d, (int) width, pixels); return; }
     if (!pixels || type != GL_FLOAT || ng_upload_count == NG_MAX_UPLOADS) return;     /* bind_1d_fbo allocates with NULL */
     ng_uploads[ng_upload_count].tex = ng_bound_1d;
     ng_uploads[ng_upload_count].width = (int) width;
@@ -321,6 +338,9 @@ static void* nw_create_and_bind(const char* name, const char* class, const char*
     return nw_geom;
 }
 static bool  nw_false(void* p) { (void) p; return false; }
+static double nw_close_at = 0.0;                         /* whole-program runs: the window "closes" at this CLOCK_MONOTONIC time */
+static double nw_now(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (double) t.tv_sec + 1e-9 * (double) t.tv_nsec; }
+static bool  nw_should_close(void* p) { (void) p; return nw_close_at > 0.0 && nw_now() >= nw_close_at; }
 static bool  nw_true(void* p) { (void) p; return true; }
 static void  nw_void(void* p) { (void) p; }
 static void  nw_terminate(void) {}
@@ -335,7 +355,7 @@ static void  nw_set_visible(void* p, bool v) { (void) p; (void) v; }
 static const char* nw_environment(void) { return NULL; }
 static struct gl_wcb ref_null_wcb = {
     .name = "null", .offscreen = nw_offscreen, .init = nw_init, .create_and_bind = nw_create_and_bind,
-    .should_close = nw_false, .should_render = nw_true, .bg_changed = nw_false, .swap_buffers = nw_void, .raise = nw_void,
+    .should_close = nw_should_close, .should_render = nw_true, .bg_changed = nw_false, .swap_buffers = nw_void, .raise = nw_void,
     .destroy = nw_void, .terminate = nw_terminate, .get_pos = nw_get_pos, .get_fbsize = nw_get_fbsize,
     .set_geometry = nw_set_geometry, .set_swap = nw_set_int, .set_floating = nw_set_bool, .set_decorated = nw_set_bool,
     .set_focused = nw_set_bool, .set_maximized = nw_set_bool, .set_transparent = nw_set_bool, .get_time = nw_get_time,
@@ -411,3 +431,18 @@ int ref_rd_upload(void* rp, int idx, int* which, float* out, int cap) {
     return w;
 }
 void ref_rd_destroy(void* rp) { rd_destroy(rp); }
+
+
+/* The whole program: glava_entry (glava/glava.c:291-577) — argument parsing, rd_new, the audio backend thread (fifo.c), the
+ * frame loop with its locked ring copy (glava.c:523-552), rd_update — on the null driver, for `run_ms` milliseconds, logging the
+ * audio texture uploads to `log_path`.  argv as for the `glava` binary (a "--backend=null" is what selects the null window). */
+int ref_glava_entry(int argc, char** argv, long run_ms, const char* log_path) {
+    if (wcbs_idx == 0) register_wcb(&ref_null_wcb);
+    ng_log_file = fopen(log_path, "wb");
+    if (!ng_log_file) return -1;
+    nw_close_at = nw_now() + 1e-3 * (double) run_ms;
+    glava_entry(argc, argv, NULL);
+    fclose(ng_log_file); ng_log_file = NULL;
+    nw_close_at = 0.0;
+    return 0;
+}

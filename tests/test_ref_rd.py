@@ -429,3 +429,56 @@ def test_argument_errors_word_for_word(rd, args, ours):
     with pytest.raises(g.GlavaError) as e:
         ours()
     assert str(e.value).strip() == theirs
+
+
+def test_whole_program_fifo_to_uploads(rd, orc, tmp_path):
+    """The whole reference program — glava_entry's argument parsing, rd_new, fifo.c's audio thread on a real named pipe, the
+    frame loop's locked ring copy (glava.c:523-552), rd_update with the shipped setaccelfft — on the null driver for half a
+    second (oracle/ref_program_driver.py).  Every frame that saw new audio uploads transform_fft of the rings as they stood;
+    the oracle's FIFO ingest + transform_fft over the same bytes must reproduce those uploads bit for bit, in order, for both
+    channels.  (Frames without new audio re-transform their buffer in place — the reference's own artefact — and are ignored.)"""
+    import json
+    import subprocess
+    import sys
+    n, samplesz, nchunks = 4096, 1024, 12                                # 16 hops per ring: the chunks stay visible for 16 slides
+    hop = samplesz // 4
+    cfg = tmp_path / "cfg" / "glava"
+    cfg.parent.mkdir()
+    fifo = str(tmp_path / "audio.fifo")
+    os.mkfifo(fifo)
+    _user_dir(cfg, {"rc.glsl": f'#request mod bars\n#request setbufsize {n}\n#request setsamplesize {samplesz}\n#request setsource "{fifo}"\n'
+                               "#request setprintframes false\n#request setframerate 0\n"})
+    rng = np.random.default_rng(3)
+    chunks = rng.integers(-20000, 20000, size=(nchunks, hop * 2), dtype=np.int16)
+    np.save(tmp_path / "chunks.npy", chunks)
+    log = str(tmp_path / "uploads.bin")
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = dict(config_home=str(tmp_path / "cfg"), fifo=fifo, chunks_file=str(tmp_path / "chunks.npy"), run_ms=500, log=log, hold=0.4)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_program_driver.py"), json.dumps(spec)],
+                         capture_output=True, text=True, timeout=120)
+    assert "DONE 0" in out.stdout, out.stderr[-2000:]
+    raw = open(log, "rb").read()
+    recs, off = [], 0
+    while off < len(raw):
+        tex, w = np.frombuffer(raw, np.int32, 2, off); off += 8
+        recs.append((int(tex), raw[off:off + 4 * int(w)])); off += 4 * int(w)
+        assert w == n
+    # ring states the audio thread goes through: the chunks, then zero slides once the FIFO runs dry (fifo.c:67-79)
+    p = orc.default_params("bars", n=n)
+    rl = np.zeros(n, np.float32); rr = np.zeros(n, np.float32)
+    want = {}
+    for k in range(nchunks + 3 * (n // hop)):
+        orc.fifo_ingest(rl, rr, chunks[k] if k < nchunks else np.zeros(hop * 2, np.int16), 2)
+        want.setdefault(orc.fft_f32(p, rl).tobytes(), ("l", k)); want.setdefault(orc.fft_f32(p, rr).tobytes(), ("r", k))
+    seen = {"l": [], "r": []}
+    tex_of = {}
+    for tex, data in recs:
+        hit = want.get(data) if any(data) else None                        # (the silent ring's spectrum is the same for both channels)
+        if hit:
+            seen[hit[0]].append(hit[1]); tex_of.setdefault(hit[0], set()).add(tex)
+    for ch in "lr":
+        ks = [k for i, k in enumerate(seen[ch]) if i == 0 or k != seen[ch][i - 1]]   # (the all-zero ring recurs)
+        assert len(ks) >= 3 and ks == sorted(set(ks)), (ch, ks)           # several audio frames, strictly in the audio thread's order
+        assert len(tex_of[ch]) == 1                                        # always the same texture object
+    assert seen["l"] == seen["r"] and tex_of["l"] != tex_of["r"]           # both channels of every frame, from the same ring state
+    assert max(seen["l"]) >= nchunks - 1                                   # the last chunk made it to the screen
