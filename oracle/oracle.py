@@ -231,8 +231,17 @@ class Reference:
 
     @staticmethod
     def available():
+        """built (or shipped prebuilt) AND loadable — a library that does not load must read as "absent", not kill the
+        worker pools of bench.py's reference arm"""
         build()
-        return os.path.exists(os.path.join(HERE, "_ref", "libglava_ref.so"))
+        path = os.path.join(HERE, "_ref", "libglava_ref.so")
+        if not os.path.exists(path):
+            return False
+        try:
+            C.CDLL(path)
+            return True
+        except OSError:
+            return False
 
     def __init__(self):
         L = C.CDLL(os.path.join(HERE, "_ref", "libglava_ref.so"))

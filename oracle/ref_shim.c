@@ -433,6 +433,7 @@ int ref_rd_upload(void* rp, int idx, int* which, float* out, int cap) {
 void ref_rd_destroy(void* rp) { rd_destroy(rp); }
 
 
+#ifdef GLAVA_REF_WITH_PROGRAM   /* only oracle/_ref/libglava_ref_rd.so links glava.c + fifo.c */
 /* The whole program: glava_entry (glava/glava.c:291-577) — argument parsing, rd_new, the audio backend thread (fifo.c), the
  * frame loop with its locked ring copy (glava.c:523-552), rd_update — on the null driver, for `run_ms` milliseconds, logging the
  * audio texture uploads to `log_path`.  argv as for the `glava` binary (a "--backend=null" is what selects the null window). */
@@ -446,3 +447,4 @@ int ref_glava_entry(int argc, char** argv, long run_ms, const char* log_path) {
     nw_close_at = 0.0;
     return 0;
 }
+#endif
