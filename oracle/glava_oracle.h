@@ -2,17 +2,20 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load this library.  The product (libglava_b200.so) never links or calls it.
  *
- * Parity status: the SPECTRUM half (and transform_smooth) is pinned against the reference's
- * own compiled code (oracle/_ref, built from /root/reference/glava/render.c by oracle/Makefile)
- * and the golden vectors generated from it (tests/golden/).  The RASTER half and the GL
- * passes K2 / K4 / K5 restate GLSL; no GL implementation is available in this image, so
- * they are pinned one level down: oracle/glsl_interp.py EXECUTES the reference's own shader
- * sources (with GLava's source extensions and injected header) in float32, and this
- * restatement equals its frames bit for bit (tests/golden/glsl_golden.npz: 24 module
- * configurations, the three SAMPLE_MODEs of smooth_pass.frag, gravity / average / pass;
- * plus the `test` module's #55000055 known answer, shaders/glava/test_rc.glsl:27).  What
- * GLSL leaves implementation-defined (transcendental ulps, round() ties, out-of-range
- * texelFetch, unorm rounding) is fixed by convention, not by the reference.
+ * Parity status.  Pinned against the reference's OWN code, compiled where it lies by oracle/Makefile into oracle/_ref/:
+ *   - the transforms (render.c transform_fft / gravity / average / wrange / smooth): bit for bit, live and through the golden
+ *     vectors generated from them (tests/golden/);
+ *   - the FIFO ring update (fifo.c's audio thread on real named pipes);
+ *   - rd_update's orchestration — transform chain, `modified`, setbufscale, keyframe interpolation, the "smooth" transform,
+ *     pipeline B's upload — and rd_new's reading of configurations: both run for real on a null OpenGL driver
+ *     (libglava_ref_rd.so), the whole program included (glava_entry with fifo.c on a named pipe).
+ * The RASTER half and the GL passes K2 / K4 / K5 restate GLSL; no GL implementation is available in this image, so they are
+ * pinned one level down: oracle/glsl_interp.py EXECUTES the reference's own shader sources in float32 — its input is
+ * token-identical to the texts rd_new hands to glShaderSource — and this restatement equals its frames bit for bit
+ * (tests/golden/glsl_golden.npz: 36 module configurations, smooth_pass.frag's modes, gravity / average / pass; a 1000-seed
+ * randomised config differential; the `test` module's #55000055 known answer, shaders/glava/test_rc.glsl:27).  What GLSL and
+ * GL leave implementation-defined (transcendental ulps, round() ties, out-of-range texelFetch, unorm and blend rounding) is
+ * fixed by convention, not by the reference: that part alone is "parity unpinned".
  */
 #ifndef GLAVA_ORACLE_H
 #define GLAVA_ORACLE_H
