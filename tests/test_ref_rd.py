@@ -431,7 +431,8 @@ def test_argument_errors_word_for_word(rd, args, ours):
     assert str(e.value).strip() == theirs
 
 
-def test_whole_program_fifo_to_uploads(rd, orc, tmp_path):
+@pytest.mark.parametrize("mirror", [False, True])
+def test_whole_program_fifo_to_uploads(rd, orc, tmp_path, mirror):
     """The whole reference program — glava_entry's argument parsing, rd_new, fifo.c's audio thread on a real named pipe, the
     frame loop's locked ring copy (glava.c:523-552), rd_update with the shipped setaccelfft — on the null driver for half a
     second (oracle/ref_program_driver.py).  Every frame that saw new audio uploads transform_fft of the rings as they stood;
@@ -447,7 +448,7 @@ def test_whole_program_fifo_to_uploads(rd, orc, tmp_path):
     fifo = str(tmp_path / "audio.fifo")
     os.mkfifo(fifo)
     _user_dir(cfg, {"rc.glsl": f'#request mod bars\n#request setbufsize {n}\n#request setsamplesize {samplesz}\n#request setsource "{fifo}"\n'
-                               "#request setprintframes false\n#request setframerate 0\n"})
+                               "#request setprintframes false\n#request setframerate 0\n" + ("#request setmirror true\n" if mirror else "")})
     rng = np.random.default_rng(3)
     chunks = rng.integers(-20000, 20000, size=(nchunks, hop * 2), dtype=np.int16)
     np.save(tmp_path / "chunks.npy", chunks)
@@ -468,14 +469,23 @@ def test_whole_program_fifo_to_uploads(rd, orc, tmp_path):
     rl = np.zeros(n, np.float32); rr = np.zeros(n, np.float32)
     want = {}
     for k in range(nchunks + 3 * (n // hop)):
-        orc.fifo_ingest(rl, rr, chunks[k] if k < nchunks else np.zeros(hop * 2, np.int16), 2)
+        orc.fifo_ingest(rl, rr, chunks[k] if k < nchunks else np.zeros(hop * 2, np.int16), 1 if mirror else 2)   # glava.c:504
         want.setdefault(orc.fft_f32(p, rl).tobytes(), ("l", k)); want.setdefault(orc.fft_f32(p, rr).tobytes(), ("r", k))
     seen = {"l": [], "r": []}
     tex_of = {}
+    by_tex = {}
     for tex, data in recs:
         hit = want.get(data) if any(data) else None                        # (the silent ring's spectrum is the same for both channels)
         if hit:
             seen[hit[0]].append(hit[1]); tex_of.setdefault(hit[0], set()).add(tex)
+            by_tex.setdefault(tex, []).append(hit[1])
+    if mirror:
+        # setmirror: fifo.c writes the integer mean of L and R into BOTH rings (fifo.c:98-102): the two audio textures get
+        # the same uploads, each equal to the oracle's mono ingest
+        assert np.array_equal(rl, rr) and len(by_tex) == 2
+        a, b = by_tex.values()
+        assert a == b and len(set(a)) >= 3 and a == sorted(a) and max(a) >= nchunks - 1
+        return
     for ch in "lr":
         ks = [k for i, k in enumerate(seen[ch]) if i == 0 or k != seen[ch][i - 1]]   # (the all-zero ring recurs)
         assert len(ks) >= 3 and ks == sorted(set(ks)), (ch, ks)           # several audio frames, strictly in the audio thread's order
