@@ -23,6 +23,17 @@ class Fake:
             self.frames[s] = emul.raster(self.params, tl[s], tr[s])
         self._launch += 1
     def readback(self, s=0, out=None): return self.frames[s]
+    # update() / textures(): the oracle's whole-rd_update restatement stands in for the spectrum kernels (script logic only)
+    def update(self, lb, rb=None, modified=True):
+        from oracle.oracle import Oracle, OracleStream, ext_from, params_from
+        if not hasattr(self, "_streams"):
+            o = Oracle("pm")
+            self._streams = [OracleStream(o, params_from(self.params), ext_from(self.params)) for _ in range(self.batch)]
+        rb = lb if rb is None else rb
+        self._tex = [st.update(lb[s], rb[s], modified)[2:] for s, st in enumerate(self._streams)]
+        self.nsz = self._streams[0].n
+    def textures(self):
+        return np.stack([t[0] for t in self._tex]), np.stack([t[1] for t in self._tex])
     def reconfigure(self, p): self.params = p.copy(); self._launch += 1
     @property
     def launch_count(self): return self._launch
@@ -40,5 +51,5 @@ def fake_apply(self, renderer):
     self._last = self.binds(); renderer.reconfigure(self.params())
 api.Pipe.apply = fake_apply
 sys.exit(pytest.main(["-x", "-q", "-m", "gpu", "-p", "no:cacheprovider",
-                      ROOT + "/tests/test_zz_gpu_blend.py", ROOT + "/tests/test_zz_gpu_color_expr.py", ROOT + "/tests/test_zz_gpu_pipe.py", ROOT + "/tests/test_glsl_golden.py",
+                      ROOT + "/tests/test_zz_gpu_blend.py", ROOT + "/tests/test_zz_gpu_color_expr.py", ROOT + "/tests/test_zz_gpu_pipe.py", ROOT + "/tests/test_glsl_golden.py", ROOT + "/tests/test_zz_rd_golden.py",
                       "-k", "not lazy and not test_graph_join_channels"]))
