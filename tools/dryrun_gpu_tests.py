@@ -32,6 +32,7 @@ class Fake:
         rb = lb if rb is None else rb
         self._tex = [st.update(lb[s], rb[s], modified)[2:] for s, st in enumerate(self._streams)]
         self.nsz = self._streams[0].n
+        self.frames = [emul.raster(self.params, t[0], t[1]) for t in self._tex]
     def textures(self):
         return np.stack([t[0] for t in self._tex]), np.stack([t[1] for t in self._tex])
     def reconfigure(self, p): self.params = p.copy(); self._launch += 1
@@ -52,4 +53,4 @@ def fake_apply(self, renderer):
 api.Pipe.apply = fake_apply
 sys.exit(pytest.main(["-x", "-q", "-m", "gpu", "-p", "no:cacheprovider",
                       ROOT + "/tests/test_zz_gpu_blend.py", ROOT + "/tests/test_zz_gpu_color_expr.py", ROOT + "/tests/test_zz_gpu_pipe.py", ROOT + "/tests/test_glsl_golden.py", ROOT + "/tests/test_zz_rd_golden.py",
-                      "-k", "not lazy and not test_graph_join_channels"]))
+                      ]))
