@@ -23,7 +23,13 @@ def main(spec):
 
     def writer():
         fd = os.open(spec["fifo"], os.O_WRONLY)                            # returns once fifo.c's thread has opened its end
-        os.write(fd, chunks.tobytes())                                     # everything at once: no poll timeout in between
+        pace = spec.get("pace_ms", 0)
+        if pace:                                                           # one chunk at a time: the frame loop sees every ring state
+            for c in chunks:
+                os.write(fd, c.tobytes())
+                threading.Event().wait(pace / 1000.0)
+        else:
+            os.write(fd, chunks.tobytes())                                 # everything at once: no poll timeout in between
         threading.Event().wait(spec.get("hold", 0.6))                      # keep the writer open while the frames run
         os.close(fd)
     t = threading.Thread(target=writer, daemon=True)

@@ -492,3 +492,92 @@ def test_whole_program_fifo_to_uploads(rd, orc, tmp_path, mirror):
         assert len(tex_of[ch]) == 1                                        # always the same texture object
     assert seen["l"] == seen["r"] and tex_of["l"] != tex_of["r"]           # both channels of every frame, from the same ring state
     assert max(seen["l"]) >= nchunks - 1                                   # the last chunk made it to the screen
+
+
+def test_whole_program_cpu_chain_state_by_state(rd, orc, tmp_path):
+    """the whole program with setaccelfft false: the writer paces its chunks, so the (much faster) frame loop sees EVERY ring
+    state; each distinct upload must then be the oracle's fft -> gravity -> average chain advanced by exactly one ring update —
+    the next chunk, or a zero slide where fifo.c's poll timed out in between (the log tells which).  `ur` stays at rd_new's
+    initialiser 1.0 on the null window's clock, so gravity falls by setgravitystep per update."""
+    import json
+    import subprocess
+    import sys
+    from oracle.oracle import OracleChannel
+    n, samplesz, nchunks = 2048, 1024, 24
+    hop = samplesz // 4
+    cfg = tmp_path / "cfg" / "glava"
+    cfg.parent.mkdir()
+    fifo = str(tmp_path / "audio.fifo")
+    os.mkfifo(fifo)
+    _user_dir(cfg, {"rc.glsl": f'#request mod bars\n#request setbufsize {n}\n#request setsamplesize {samplesz}\n#request setsource "{fifo}"\n'
+                               "#request setprintframes false\n#request setframerate 0\n#request setaccelfft false\n#request setinterpolate false\n"})
+    rng = np.random.default_rng(21)
+    chunks = rng.integers(-20000, 20000, size=(nchunks, hop * 2), dtype=np.int16)
+    np.save(tmp_path / "chunks.npy", chunks)
+    log = str(tmp_path / "uploads.bin")
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = dict(config_home=str(tmp_path / "cfg"), fifo=fifo, chunks_file=str(tmp_path / "chunks.npy"), run_ms=600, log=log, hold=1.5, pace_ms=8)
+    # (hold > run: once the writer exits, fifo.c spins on POLLHUP re-sliding its stale read buffer — not part of this check)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_program_driver.py"), json.dumps(spec)],
+                         capture_output=True, text=True, timeout=120)
+    assert "DONE 0" in out.stdout, out.stderr[-2000:]
+    raw = open(log, "rb").read()
+    per_tex, off = {}, 0
+    while off < len(raw):
+        tex, w = np.frombuffer(raw, np.int32, 2, off); off += 8
+        per_tex.setdefault(int(tex), []).append(np.frombuffer(raw, np.float32, int(w), off).copy()); off += 4 * int(w)
+    assert len(per_tex) == 2
+    p = orc.default_params("bars", n=n, accel_fft=0, smooth_pass=0, avg_frames=5, ur=1.0)
+    zero = np.zeros(hop * 2, np.int16)
+    matched_channels = 0
+    for uploads in per_tex.values():
+        for side in (0, 1):                                                # which ring this texture shows
+            ring = [np.zeros(n, np.float32), np.zeros(n, np.float32)]
+            ch = OracleChannel(orc, p)
+            nxt, steps, ok = 0, 0, True
+            # leading records: the never-initialised lb of glava.c:487-490 until the first ring update arrives
+            start = next((i for i, u in enumerate(uploads) if _step_matches(orc, p, ring, chunks[0], side, u)), None)
+            if start is None:
+                continue
+            for u in uploads[start:]:
+                # one ring update per logged upload as a rule; two when the frame loop was held up for a moment (it then
+                # transforms only the later state — the earlier one never reaches gravity / average, here neither)
+                singles = ([("c", 1)] if nxt < nchunks else []) + [("z", 0)]
+                doubles = [a + b for a in ("c", "z") for b in ("c", "z")]
+                hit = None
+                for seq in [t[0] for t in singles] + doubles:
+                    r2 = [ring[0].copy(), ring[1].copy()]
+                    k = nxt
+                    if seq.count("c") > nchunks - nxt:
+                        continue
+                    for step in seq:
+                        orc.fifo_ingest(r2[0], r2[1], chunks[k] if step == "c" else zero, 2)
+                        k += step == "c"
+                    if np.array_equal(_replay(orc, p, getattr(ch, "_log", []), r2[side]), u):
+                        hit = (seq, r2, k)
+                        break
+                if hit is None:
+                    ok = False
+                    break
+                ring, nxt = hit[1], hit[2]
+                ch._log = getattr(ch, "_log", []) + [ring[side].copy()]
+                steps += len(hit[0])
+            if ok and steps >= nchunks and nxt == nchunks:
+                matched_channels += 1
+    assert matched_channels == 2                                           # one texture follows the left ring, the other the right
+
+
+def _replay(orc, p, log, ring_now):
+    """the chain's result after the logged ring states followed by `ring_now` (OracleChannel has no copy: replay)"""
+    from oracle.oracle import OracleChannel
+    ch = OracleChannel(orc, p)
+    out = None
+    for state in list(log) + [ring_now]:
+        out, _ = ch.update(state)
+    return out
+
+
+def _step_matches(orc, p, ring, chunk, side, upload):
+    r2 = [ring[0].copy(), ring[1].copy()]
+    orc.fifo_ingest(r2[0], r2[1], chunk, 2)
+    return np.array_equal(_replay(orc, p, [], r2[side]), upload)
