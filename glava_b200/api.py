@@ -106,6 +106,9 @@ def lib():
     L.glava_b200_host_free.argtypes = [vp]
     L.glava_b200_update.argtypes = [vp, vp, vp, C.c_size_t, i32]
     L.glava_b200_update_device.argtypes = [vp, vp, vp, C.c_size_t, i32]
+    L.glava_b200_update_masked.argtypes = [vp, vp, vp, C.c_size_t, vp]
+    L.glava_b200_update_device_masked.argtypes = [vp, vp, vp, C.c_size_t, vp]
+    L.glava_b200_update_rings_masked.argtypes = [vp, vp]
     L.glava_b200_ingest_fifo.argtypes = [vp, vp, i32]
     L.glava_b200_update_rings.argtypes = [vp, i32]
     L.glava_b200_sync.argtypes = [vp]
@@ -273,6 +276,29 @@ class Renderer:
             assert rb.shape == lb.shape
             rp = rb.ctypes.data
         _check(self._L.glava_b200_update(self._h, lb.ctypes.data, rp, self.params.n, 1 if modified else 0))
+        self._after_update()
+
+    def _mask(self, modified):
+        m = np.ascontiguousarray(np.asarray(modified) != 0, dtype=np.uint8)
+        assert m.shape == (self.batch,), m.shape
+        return m
+
+    def update_masked(self, lb, rb, modified):
+        """per-stream `modified` flags ([batch] booleans): glava.c:528-537 per stream"""
+        lb = np.ascontiguousarray(lb, dtype=np.float32); rb = np.ascontiguousarray(rb, dtype=np.float32)
+        assert lb.shape == (self.batch, self.params.n) and rb.shape == lb.shape
+        m = self._mask(modified)
+        _check(self._L.glava_b200_update_masked(self._h, lb.ctypes.data, rb.ctypes.data, self.params.n, m.ctypes.data))
+        self._after_update()
+
+    def update_device_masked(self, d_lb, d_rb, modified):
+        m = self._mask(modified)
+        _check(self._L.glava_b200_update_device_masked(self._h, d_lb, d_rb, self.params.n, m.ctypes.data))
+        self._after_update()
+
+    def update_rings_masked(self, modified):
+        m = self._mask(modified)
+        _check(self._L.glava_b200_update_rings_masked(self._h, m.ctypes.data))
         self._after_update()
 
     def _after_update(self):

@@ -153,6 +153,7 @@ struct glava_b200_audio {
     std::vector<char> started;
     float* ring_l; float* ring_r;        // [batch][bufsz] backing store of audio_out_l / _r
     float* lb; float* rb;                // [batch][bufsz] frame-loop copies handed to glava_b200_update (lazily allocated)
+    std::vector<uint8_t> mask;           // [batch] this frame's per-stream `modified`
     bool lb_pinned;
 };
 
@@ -234,9 +235,13 @@ extern "C" int glava_b200_audio_frame(glava_b200_audio* a, glava_b200* r) {
         a->lb_pinned = true;
         memset(a->lb, 0, bytes); memset(a->rb, 0, bytes);    // glava.c:491-494: silence until the first ring update
     }
-    const int modified = glava_b200_audio_collect(a, a->lb, a->rb, nullptr);
+    // glava.c:528-537 decides per renderer — here per stream — whether rd_update runs the chain (`modified`) or only
+    // re-rasters: the per-stream flags go down to the spectrum kernel (a stream whose backend thread did not tick keeps
+    // its gravity / average state)
+    a->mask.resize((size_t) a->batch);
+    const int modified = glava_b200_audio_collect(a, a->lb, a->rb, a->mask.data());
     if (modified < 0) return modified;
-    return glava_b200_update(r, a->lb, a->rb, a->bufsz, modified > 0 ? 1 : 0);
+    return glava_b200_update_masked(r, a->lb, a->rb, a->bufsz, a->mask.data());
 }
 
 extern "C" struct audio_data* glava_b200_audio_stream(glava_b200_audio* a, int stream) {

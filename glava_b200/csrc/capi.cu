@@ -94,6 +94,11 @@ struct glava_b200 {
     uint16_t* d_av;             // pre-smoothing textures [batch*2][n] (full-plane K5 runs as its own kernel)
     uint8_t* d_fb;
     unsigned long long updates;
+    // per-stream `modified` masks (glava_b200_update_masked): once streams have advanced unevenly, every stream has its
+    // own average-ring cursor; words {bit 31 = modified, low bits = cursor} go to the device through a small pinned ring
+    bool desync;
+    std::vector<uint32_t> cursor;          // [batch] modified updates of that stream so far, mod avg_frames (valid once desync)
+    uint32_t* h_umask[4]; uint32_t* d_umask[4]; cudaEvent_t ev_umask[4]; int umask_cur;
     uint64_t launches;
     std::vector<void*> allocs;
     // optional per-kernel device timing (glava_b200_set_timing): events around each launch
@@ -392,6 +397,8 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     r->out_stream = nullptr; r->d_stage[0] = r->d_stage[1] = nullptr; r->stage_bytes = 0; r->out_cur = 0;
     for (int i = 0; i < 2; ++i) { r->ev_stage_ready[i] = nullptr; r->ev_stage_free[i] = nullptr; }
     r->updates = 0; r->launches = 0; r->timing = false;
+    r->desync = false; r->umask_cur = 0;
+    for (int i = 0; i < 4; ++i) { r->h_umask[i] = nullptr; r->d_umask[i] = nullptr; r->ev_umask[i] = nullptr; }
     if (build(r) != 0) { glava_b200_destroy(r); return nullptr; }
     return r;
 }
@@ -408,6 +415,11 @@ void glava_b200_destroy(glava_b200* r) {
     for (void* p : r->allocs) cudaFree(p);
     if (r->d_chunks) cudaFree(r->d_chunks);
     for (int i = 0; i < 2; ++i) { if (r->ev_copied[i]) cudaEventDestroy(r->ev_copied[i]); if (r->ev_free[i]) cudaEventDestroy(r->ev_free[i]); }
+    for (int i = 0; i < 4; ++i) {
+        if (r->h_umask[i]) cudaFreeHost(r->h_umask[i]);
+        if (r->d_umask[i]) cudaFree(r->d_umask[i]);
+        if (r->ev_umask[i]) cudaEventDestroy(r->ev_umask[i]);
+    }
     if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
     if (r->out_stream) { cudaStreamSynchronize(r->out_stream); cudaStreamDestroy(r->out_stream); }
     for (int i = 0; i < 2; ++i) {
@@ -491,8 +503,46 @@ static int apply_resize(glava_b200* r, int w, int h) {
 //                          texture half it overwrites)
 //   raster(i)   waits for: spectrum(i)
 // so raster(i) and spectrum(i+1) run concurrently: one is HBM-store bound, the other latency bound.
-static int run_update(glava_b200* r, const float* d_l, const float* d_r, int modified, bool raster_only = false) {
+// Per-stream mask -> device words.  Returns the device array for this update (nullptr: every stream modified in lock step).
+static int stage_umask(glava_b200* r, const uint8_t* mask, const uint32_t** d_out) {
+    const int F = r->p.avg_frames;
+    if (!r->desync) {                                           // first uneven update: every stream starts from the shared cursor
+        r->cursor.assign((size_t) r->batch, (uint32_t) (r->updates % (unsigned long long) F));
+        r->desync = true;
+    }
+    const int k = r->umask_cur;
+    if (!r->h_umask[k]) {
+        CU(cudaHostAlloc((void**) &r->h_umask[k], (size_t) r->batch * 4, cudaHostAllocDefault));
+        CU(cudaMalloc((void**) &r->d_umask[k], (size_t) r->batch * 4));
+        CU(cudaEventCreateWithFlags(&r->ev_umask[k], cudaEventDisableTiming));
+    } else {
+        CU(cudaEventSynchronize(r->ev_umask[k]));               // the copy that last read this pinned buffer (4 updates ago)
+    }
+    for (int s = 0; s < r->batch; ++s) {
+        const bool m = !mask || mask[s];
+        r->h_umask[k][s] = (m ? 0x80000000u : 0u) | r->cursor[s];
+        if (m) r->cursor[s] = (r->cursor[s] + 1u) % (uint32_t) F;
+    }
+    CU(cudaMemcpyAsync(r->d_umask[k], r->h_umask[k], (size_t) r->batch * 4, cudaMemcpyHostToDevice, r->spec_stream));
+    CU(cudaEventRecord(r->ev_umask[k], r->spec_stream));
+    r->umask_cur = (k + 1) & 3;
+    *d_out = r->d_umask[k];
+    return 0;
+}
+
+// `mask` (may be null): one byte per stream, non-zero = that stream has new audio (glava.c:528-537 per renderer).
+static int run_update(glava_b200* r, const float* d_l, const float* d_r, int modified, bool raster_only = false,
+                      const uint8_t* mask = nullptr) {
     int rc;
+    if (mask && !raster_only) {
+        int cnt = 0;
+        for (int s = 0; s < r->batch; ++s) cnt += mask[s] ? 1 : 0;
+        modified = cnt > 0;
+        if (cnt == 0 || cnt == r->batch) mask = nullptr;        // nobody / everybody: the plain forms
+        else if (r->interp_on)
+            return fail(GLAVA_B200_EINVAL, "per-stream modified masks are not available with keyframe interpolation active "
+                                           "(setinterpolate): the keyframe rotation is per renderer; update the streams in lock step");
+    } else mask = nullptr;
     if (unsigned long long req = r->sizereq.exchange(0)) {                  // render.c:1811-1815: at the start of a frame
         if ((rc = apply_resize(r, (int) ((req >> 32) & 0x7fffffffu), (int) (req & 0xffffffffu))) != 0) return rc;
     }
@@ -526,6 +576,8 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
         a.tap_ku = r->tap_ku;
         a.csr = (a.need && a.tap_tab) ? r->d_csr : nullptr; a.csr_bytes = r->csr_bytes; a.csr_idx_off = r->csr_idx_off; a.csr_off_off = r->csr_off_off;
         a.batch = r->batch; a.update = r->updates;
+        a.umask = nullptr; a.tex_prev = tex_half(r, r->tex_cur);
+        if (mask || r->desync) { if ((rc = stage_umask(r, mask, &a.umask)) != 0) return rc; }
         const int F = p.avg_frames;
         for (int f = 0; f < F; ++f) {
             // pipeline A: window_frame(f, avg_frames - 1) -> cos(TWOPI*f/F - 1), double (render.c:661,766)
@@ -547,7 +599,7 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
             ++r->launches;
         }
         if (r->post_chain && p.transform_smooth) {                          // render.c:694-718, after the module's chain
-            if ((rc = launch_transform_smooth(chain_out, p.n, r->d_ts_tab, r->ts_asz, r->ts_lim, planes, r->spec_stream)) != 0) return rc;
+            if ((rc = launch_transform_smooth(chain_out, p.n, r->d_ts_tab, r->ts_asz, r->ts_lim, planes, r->spec_stream, a.umask)) != 0) return rc;
             ++r->launches;
         }
         if (!r->post_chain) {
@@ -617,10 +669,19 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
     return 0;
 }
 
+static int update_host(glava_b200* r, const float* lb, const float* rb, size_t bsz, int modified, const uint8_t* mask);
+
 int glava_b200_update(glava_b200* r, const float* lb, const float* rb, size_t bsz, int modified) {
     clear_error();
     if (!r || !lb) return fail(GLAVA_B200_EINVAL, "glava_b200_update: null argument");
+    return update_host(r, lb, rb, bsz, modified, nullptr);
+}
+
+static int update_host(glava_b200* r, const float* lb, const float* rb, size_t bsz, int modified, const uint8_t* mask) {
     if (bsz != (size_t) r->n_in) return fail(GLAVA_B200_EINVAL, "glava_b200_update: bsz %zu != setbufsize %d", bsz, r->n_in);
+    // rd_update always gets both rings (render.h:58); only `wave` ignores rb (wave/1.frag:7 samples audio_l alone)
+    if (modified && !rb && r->p.module != GLAVA_B200_MOD_WAVE)
+        return fail(GLAVA_B200_EINVAL, "glava_b200_update: module '%s' reads both channels, rb is null", module_name(r->p.module));
     CU(cudaSetDevice(r->device));
     size_t bytes = (size_t) r->batch * bsz * 4;
     const int b = r->stage_cur;
@@ -630,12 +691,12 @@ int glava_b200_update(glava_b200* r, const float* lb, const float* rb, size_t bs
         // copy has completed, so — like rd_update — the caller may reuse lb / rb immediately.
         CU(cudaStreamWaitEvent(r->copy_stream, r->ev_free[b], 0));
         CU(cudaMemcpyAsync(r->d_pcm[b][0], lb, bytes, cudaMemcpyHostToDevice, r->copy_stream));
-        if (rb && r->p.module != GLAVA_B200_MOD_WAVE)
+        if (r->p.module != GLAVA_B200_MOD_WAVE)
             CU(cudaMemcpyAsync(r->d_pcm[b][1], rb, bytes, cudaMemcpyHostToDevice, r->copy_stream));
         CU(cudaEventRecord(r->ev_copied[b], r->copy_stream));
         CU(cudaStreamWaitEvent(r->spec_stream, r->ev_copied[b], 0));
     }
-    int rc = run_update(r, r->d_pcm[b][0], r->d_pcm[b][1], modified);
+    int rc = run_update(r, r->d_pcm[b][0], r->d_pcm[b][1], modified, false, mask);
     if (rc) return rc;
     if (modified) {
         CU(cudaEventRecord(r->ev_free[b], r->spec_stream));
@@ -645,11 +706,38 @@ int glava_b200_update(glava_b200* r, const float* lb, const float* rb, size_t bs
     return 0;
 }
 
+int glava_b200_update_masked(glava_b200* r, const float* lb, const float* rb, size_t bsz, const uint8_t* modified) {
+    clear_error();
+    if (!r || !lb || !modified) return fail(GLAVA_B200_EINVAL, "glava_b200_update_masked: null argument");
+    int any = 0;
+    for (int s = 0; s < r->batch; ++s) any |= modified[s];
+    return update_host(r, lb, rb, bsz, any ? 1 : 0, modified);
+}
+
+int glava_b200_update_device_masked(glava_b200* r, const float* d_lb, const float* d_rb, size_t bsz, const uint8_t* modified) {
+    clear_error();
+    if (!r || !d_lb || !modified) return fail(GLAVA_B200_EINVAL, "glava_b200_update_device_masked: null argument");
+    if (bsz != (size_t) r->n_in) return fail(GLAVA_B200_EINVAL, "glava_b200_update_device_masked: bsz %zu != setbufsize %d", bsz, r->n_in);
+    if (((uintptr_t) d_lb & 15) || ((uintptr_t) d_rb & 15)) return fail(GLAVA_B200_EINVAL, "device PCM pointers must be 16-byte aligned");
+    if (!d_rb && r->p.module != GLAVA_B200_MOD_WAVE) return fail(GLAVA_B200_EINVAL, "glava_b200_update_device_masked: module '%s' reads both channels, d_rb is null", module_name(r->p.module));
+    CU(cudaSetDevice(r->device));
+    return run_update(r, d_lb, d_rb ? d_rb : d_lb, 1, false, modified);
+}
+
+int glava_b200_update_rings_masked(glava_b200* r, const uint8_t* modified) {
+    clear_error();
+    if (!r || !modified) return fail(GLAVA_B200_EINVAL, "glava_b200_update_rings_masked: null argument");
+    CU(cudaSetDevice(r->device));
+    return run_update(r, r->d_ring[r->ring_cur][0], r->d_ring[r->ring_cur][1], 1, false, modified);
+}
+
 int glava_b200_update_device(glava_b200* r, const float* d_lb, const float* d_rb, size_t bsz, int modified) {
     clear_error();
     if (!r || !d_lb) return fail(GLAVA_B200_EINVAL, "glava_b200_update_device: null argument");
     if (bsz != (size_t) r->n_in) return fail(GLAVA_B200_EINVAL, "glava_b200_update_device: bsz %zu != setbufsize %d", bsz, r->n_in);
     if (((uintptr_t) d_lb & 15) || ((uintptr_t) d_rb & 15)) return fail(GLAVA_B200_EINVAL, "device PCM pointers must be 16-byte aligned");
+    if (modified && !d_rb && r->p.module != GLAVA_B200_MOD_WAVE)
+        return fail(GLAVA_B200_EINVAL, "glava_b200_update_device: module '%s' reads both channels, d_rb is null", module_name(r->p.module));
     CU(cudaSetDevice(r->device));
     return run_update(r, d_lb, d_rb ? d_rb : d_lb, modified);
 }

@@ -63,6 +63,12 @@ struct SpectrumArgs {
     int       skip_tex;         // 1: produce `spec` only (transform_smooth / keyframe lerp / upload / K5 follow as kernels)
     int       batch;
     unsigned long long update;  // number of modified updates before this one (ring cursor)
+    // per-stream `modified` (glava.c:528-537 decides per renderer, i.e. per stream): nullptr = every stream is modified and
+    // shares the cursor `update % F`; else one word per stream, bit 31 = this stream has new audio, low 16 bits = its own
+    // ring cursor (modified updates of THAT stream so far, mod F).  An unmodified stream's state is left alone and its
+    // texture is carried from `tex_prev` (the half of the double buffer the previous raster read) into `tex`.
+    const uint32_t* umask;      // [batch]
+    const uint16_t* tex_prev;   // [batch*2][n]
     double    avg_w_a[GLB_MAX_AVG_FRAMES];   // pipeline A weights, oldest first (render.c:661,766)
     float     avg_w_b[GLB_MAX_AVG_FRAMES];   // pipeline B weights, newest first (average_pass.frag:41)
     int       avg_b_windowed;                // average_pass.frag:27-29,38-42
@@ -110,7 +116,8 @@ int spectrum_threads(int n);
 // chain_kernels.cu: optional stages of rd_update (bufscale, transform_smooth, keyframe lerp + R16 upload)
 int launch_bufscale(const float* in_l, const float* in_r, float* out_l, float* out_r, int batch, int n_in, int k,
                     int channels, void* stream);
-int launch_transform_smooth(float* d_planes, int n, const void* d_tab, int asz, int lim, int count, void* stream);
+int launch_transform_smooth(float* d_planes, int n, const void* d_tab, int asz, int lim, int count, void* stream,
+                            const uint32_t* d_umask = nullptr);   // d_umask: SpectrumArgs::umask, planes of unmodified streams are skipped
 int launch_upload(const float* d_s, const float* d_e, float mod, uint16_t* d_out, size_t total, void* stream);
 
 }  // namespace glb

@@ -125,6 +125,21 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
   for (int u = blockIdx.x; u < units; u += gridDim.x) {
     const int c = IS_FFT ? u : 2 * u, ch = c & 1;
     const size_t plane = (size_t) c * N;
+    // per-stream `modified` (glava.c:528-537, render.c:2268-2272): a stream without new audio keeps its gravity / average
+    // state and shows its previous texture again
+    const uint32_t um = a.umask ? __ldg(a.umask + (c >> 1)) : 0x80000000u;
+    const int cursor = a.umask ? (int) (um & 0xffffu) : (int) (a.update % (unsigned long long) F);
+    if (!(um >> 31)) {
+        mbar_wait(bar, parity); parity ^= 1u;        // (the prefetched ring is not used)
+        if (!a.skip_tex && a.tex_prev) {
+            const uint4* src = reinterpret_cast<const uint4*>(a.tex_prev + plane);
+            uint4* dst = reinterpret_cast<uint4*>(a.tex + plane);
+            for (int i = tid; i < N / 8; i += T) dst[i] = src[i];
+        }
+        __syncthreads();
+        if (tid == 0 && u + (int) gridDim.x < units) issue_load(u + gridDim.x);
+        continue;
+    }
     if (IS_FFT && p.accel_fft) {
         // while the PCM load is in flight: pull this plane's gravity / average state (1 + F planes of
         // u16, HBM-resident) towards L2, so the epilogue's loads after the FFT are L2 hits
@@ -152,7 +167,7 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
         if (!p.accel_fft) {
             // --- pipeline A: render.c:2149-2156 --------------------------------------------------
             const float g = p.gravity_step * (1.0f / p.ur);
-            const int newest = (int) (a.update % (unsigned long long) F);
+            const int newest = cursor;
             for (int n = tid; n < N; n += T) {
                 cpx z = buf[fft_pad(n >> 1)];
                 float v = fft_post((n & 1) ? z.y : z.x, n, N, p.fft_scale, p.fft_cutoff);
@@ -173,7 +188,7 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
         } else {
             // --- pipeline B: render.c:2177-2267 ---------------------------------------------------
             const float diff = p.gravity_step * (1.0f / p.ur);
-            const int out_idx = (int) (a.update % (unsigned long long) F);
+            const int out_idx = cursor;
             const int epi_n = (a.epi_n > 0 && a.epi_n < N) ? ((a.epi_n + T - 1) / T) * T : N;
             float*    const spec = a.spec + plane;
             uint16_t* const grs  = a.gr_store + plane;
@@ -368,6 +383,7 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
     }
     __syncthreads();                                 // `av` may be overwritten by the next unit's epilogue
   }
+  if (tab_pending) mbar_wait(bar2, parity2);          // (every unit of this CTA was skipped: do not exit under an in-flight bulk copy)
 }
 
 int spectrum_threads(int n) {

@@ -228,7 +228,8 @@ void  glava_b200_host_free(void* p);
 /* rd_update (render.h:58-59; render.c:1743-2417), batched.
  *   lb, rb : HOST, [batch][bsz] float32, ring contents oldest-first, exactly what glava.c:528-537
  *            memcpy's into lb/rb for one stream.  NOT modified (the reference transforms them in
- *            place, render.c:2140-2180).  rb is ignored by `wave` (audio_l only, wave/1.frag:7).
+ *            place, render.c:2140-2180).  rb is ignored by `wave` (audio_l only, wave/1.frag:7); for every
+ *            other module a NULL rb with modified != 0 is GLAVA_B200_EINVAL.
  *   bsz    : must equal params.n (setbufsize; with setbufscale k the spectrum has n / k entries)
  *   modified: as rd_update's flag; 0 re-rasters the last spectrum (render.c:2268-2272), or, with keyframe
  *            interpolation active, the next interpolated one
@@ -239,6 +240,17 @@ void  glava_b200_host_free(void* p);
 int glava_b200_update(glava_b200* r, const float* lb, const float* rb, size_t bsz, int modified);
 /* same with DEVICE pointers (inputs already resident in HBM) */
 int glava_b200_update_device(glava_b200* r, const float* d_lb, const float* d_rb, size_t bsz, int modified);
+
+/* Per-stream `modified` (glava.c:528-537 tests the flag of ITS audio thread; in a batch every stream has its own):
+ * modified[s] != 0 = stream s has new audio and runs the whole chain; a stream with 0 keeps its gravity / average state
+ * untouched and is re-rastered from its previous texture, exactly what rd_update(modified = false) does for it
+ * (render.c:2122, 2268-2272).  All zero / all non-zero are the plain calls above.  After the first uneven update every
+ * stream carries its own average-ring cursor; plain modified = 1 calls keep working.  lb / rb rows of unmodified
+ * streams are not read by the kernels.  Not available (GLAVA_B200_EINVAL) for an uneven mask while keyframe
+ * interpolation is active (setinterpolate with ur / fr <= 0.9: the keyframe rotation belongs to the renderer). */
+int glava_b200_update_masked(glava_b200* r, const float* lb, const float* rb, size_t bsz, const uint8_t* modified /* [batch] */);
+int glava_b200_update_device_masked(glava_b200* r, const float* d_lb, const float* d_rb, size_t bsz, const uint8_t* modified);
+int glava_b200_update_rings_masked(glava_b200* r, const uint8_t* modified);
 
 /* FIFO-compatible ingest (fifo.c:89-110): `frames` new interleaved int16 L,R frames per stream,
  * HOST [batch][frames*2]; slides every stream's device-resident ring and converts s16/65535.f

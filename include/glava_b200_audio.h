@@ -70,7 +70,10 @@ glava_b200_audio* glava_b200_audio_start(const char* backend, const char* const*
  * Returns the number of streams copied; modified_out (may be NULL) receives one 0/1 byte per stream. */
 int glava_b200_audio_collect(glava_b200_audio* a, float* lb, float* rb, uint8_t* modified_out);
 /* one frame of glava.c:523-539 for the batch: collect into the handle's pinned [batch][bufsz] blocks, then
- * glava_b200_update(r, lb, rb, bufsz, modified = any stream modified).  Returns the update's status. */
+ * glava_b200_update_masked(r, lb, rb, bufsz, per-stream modified): a stream whose backend thread ticked runs the
+ * whole chain, the others are re-rastered from their last texture with their state untouched — free-running
+ * backends give what one GLava process per stream gives.  (With keyframe interpolation active an uneven frame is
+ * GLAVA_B200_EINVAL, see glava_b200_update_masked.)  Returns the update's status. */
 int glava_b200_audio_frame(glava_b200_audio* a, glava_b200* r);
 struct audio_data* glava_b200_audio_stream(glava_b200_audio* a, int stream);
 /* glava.c:563-572: terminate = 1, join every thread, free sources and rings. */

@@ -448,3 +448,231 @@ int ref_glava_entry(int argc, char** argv, long run_ms, const char* log_path) {
     return 0;
 }
 #endif
+
+
+#ifdef GLAVA_REF_WITH_GL   /* only oracle/_ref/libglava_ref_gl.so */
+/* ------------------------------------------------------------------------------------------------------------------
+ * rd_new / rd_update WITH A REAL OpenGL: Mesa 18.1.9 llvmpipe — GLava's stated software floor (README.md:121).
+ *
+ * The image ships no system GL, but Nsight Compute bundles Mesa's "libgl-xlib" software GL (llvmpipe + softpipe).  It
+ * wants an X display only to describe a visual; oracle/fakex/fake_x11.c supplies that without a server.  A window
+ * backend "mesa" (offscreen, like the OBS plug-in's use of glava_tex) creates an OpenGL 3.3 core context on a pbuffer
+ * and loads glad from glXGetProcAddress; from there on EVERYTHING is the reference's: its config reader, its CPU
+ * transforms, its GL 1-D passes (pass / gravity / average / smooth fragment shaders), its module stages — compiled by
+ * Mesa's GLSL compiler and rasterised by llvmpipe.  The final stage lands in gl->off_sfbo (render.c:1603-1611), which
+ * ref_gl_frame reads back with glReadPixels.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#include <dlfcn.h>
+
+static void* mg_dpy = NULL;
+static void* (*mg_gpa)(const char*) = NULL;
+static void* mg_ctx = NULL;
+static unsigned long mg_pbuffer = 0;
+static int mg_geom[4] = { 0, 0, 800, 600 };
+static char mg_error[512];
+
+const char* ref_gl_error(void) { return mg_error; }
+
+/* libX11 / libXext stand-ins first (RTLD_GLOBAL, so that libGL's DT_NEEDED entries resolve to them by soname), then Mesa */
+int ref_gl_load(const char* fakex_dir, const char* libgl_path) {
+    if (mg_gpa) return 0;
+    char path[1024];
+    snprintf(path, sizeof(path), "%s/libX11.so.6", fakex_dir);
+    void* x11 = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+    if (!x11) { snprintf(mg_error, sizeof(mg_error), "%s", dlerror()); return -1; }
+    snprintf(path, sizeof(path), "%s/libXext.so.6", fakex_dir);
+    if (!dlopen(path, RTLD_NOW | RTLD_GLOBAL)) { snprintf(mg_error, sizeof(mg_error), "%s", dlerror()); return -1; }
+    void* gl = dlopen(libgl_path, RTLD_NOW | RTLD_GLOBAL);
+    if (!gl) { snprintf(mg_error, sizeof(mg_error), "%s", dlerror()); return -1; }
+    void* (*fdpy)(void) = (void* (*)(void)) dlsym(x11, "fakex_display");
+    mg_gpa = (void* (*)(const char*)) dlsym(gl, "glXGetProcAddressARB");
+    if (!fdpy || !mg_gpa) { snprintf(mg_error, sizeof(mg_error), "fakex_display / glXGetProcAddressARB not found"); mg_gpa = NULL; return -1; }
+    mg_dpy = fdpy();
+    return 0;
+}
+
+static int mg_no_barrier = 0;
+static void mg_texture_barrier(void) { glFinish(); }
+int ref_gl_barrier_substituted(void) { return mg_no_barrier; }
+static void (*mg_real_draw)(GLenum, GLint, GLsizei) = NULL;
+static void mg_trace_draw(GLenum mode, GLint first, GLsizei count) {      /* REF_GL_TRACE_DRAWS=1: state at every draw */
+    GLint fbo = 0, prog = 0, vp[4] = { 0 }, blend = 0, eq = 0, unit = 0, t1d = 0, db = 0;
+    glGetIntegerv(GL_DRAW_FRAMEBUFFER_BINDING, &fbo); glGetIntegerv(GL_CURRENT_PROGRAM, &prog); glGetIntegerv(GL_VIEWPORT, vp);
+    glGetIntegerv(GL_BLEND, &blend); glGetIntegerv(GL_BLEND_EQUATION_RGB, &eq); glGetIntegerv(GL_ACTIVE_TEXTURE, &unit);
+    glGetIntegerv(GL_TEXTURE_BINDING_1D, &t1d); glGetIntegerv(GL_DRAW_BUFFER, &db);
+    const GLenum st = glCheckFramebufferStatus(GL_DRAW_FRAMEBUFFER);
+    mg_real_draw(mode, first, count);
+    if (vp[3] == 1) {
+        unsigned short px[4] = { 0 }; static float fx[65536];
+        GLint rfb = 0; glGetIntegerv(GL_READ_FRAMEBUFFER_BINDING, &rfb);
+        glBindFramebuffer(GL_READ_FRAMEBUFFER, fbo);
+        glReadPixels(0, 0, 4, 1, GL_RED, GL_UNSIGNED_SHORT, px);
+        glBindFramebuffer(GL_READ_FRAMEBUFFER, rfb);
+        glGetTexImage(GL_TEXTURE_1D, 0, GL_RED, GL_FLOAT, fx);
+        fprintf(stderr, "   target now %u %u %u %u | bound 1-D texture starts %g %g\n", px[0], px[1], px[2], px[3], fx[0], fx[1]);
+    }
+    fprintf(stderr, "[draw] fbo %d (status %x, draw buffer %x) prog %d viewport %d %d %d %d blend %d eq %x unit %d tex1d %d err %x\n",
+            fbo, st, db, prog, vp[0], vp[1], vp[2], vp[3], blend, eq, unit - GL_TEXTURE0, t1d, glGetError());
+}
+static bool  mw_offscreen(void) { return true; }
+static void* mw_create_and_bind(const char* name, const char* class, const char* type, const char** states, size_t states_sz,
+                                int w, int h, int x, int y, int major, int minor, bool clickthrough, bool offscreen) {
+    (void) name; (void) class; (void) type; (void) states; (void) states_sz; (void) clickthrough; (void) offscreen;
+    mg_geom[0] = x; mg_geom[1] = y; mg_geom[2] = w; mg_geom[3] = h;
+    if (!mg_gpa) { fprintf(stderr, "ref_gl: ref_gl_load was not called\n"); glava_abort(); }
+    if (!mg_ctx) {
+        void** (*choose)(void*, int, const int*, int*) = (void** (*)(void*, int, const int*, int*)) mg_gpa("glXChooseFBConfig");
+        void*  (*mkpb)(void*, void*, const int*) = (void* (*)(void*, void*, const int*)) mg_gpa("glXCreatePbuffer");
+        void*  (*mkctx)(void*, void*, void*, int, const int*) = (void* (*)(void*, void*, void*, int, const int*)) mg_gpa("glXCreateContextAttribsARB");
+        const int fbattr[] = { 0x8010 /* GLX_DRAWABLE_TYPE */, 0x4 | 0x1 /* PBUFFER | WINDOW */, 0x8011 /* GLX_RENDER_TYPE */, 0x1 /* RGBA */,
+                               8 /* RED */, 8, 9, 8, 10, 8, 11 /* ALPHA */, 8, 12 /* DEPTH */, 0, 5 /* DOUBLEBUFFER */, 0, 0 };
+        int n = 0;
+        void** cfgs = choose(mg_dpy, 0, fbattr, &n);
+        if (!cfgs || n < 1) { fprintf(stderr, "ref_gl: no GLX framebuffer configuration\n"); glava_abort(); }
+        const int pbattr[] = { 0x8041 /* GLX_PBUFFER_WIDTH */, 16, 0x8040 /* GLX_PBUFFER_HEIGHT */, 16, 0 };
+        mg_pbuffer = (unsigned long) mkpb(mg_dpy, cfgs[0], pbattr);
+        const int cattr[] = { 0x2091 /* MAJOR */, major, 0x2092 /* MINOR */, minor, 0x9126 /* PROFILE_MASK */, 0x1 /* core, as glx_wcb.c asks */, 0 };
+        mg_ctx = mkctx(mg_dpy, cfgs[0], NULL, 1, cattr);
+        if (!mg_ctx) { fprintf(stderr, "ref_gl: glXCreateContextAttribsARB(%d.%d core) failed\n", major, minor); glava_abort(); }
+    }
+    int (*mkcur)(void*, unsigned long, unsigned long, void*) = (int (*)(void*, unsigned long, unsigned long, void*)) mg_gpa("glXMakeContextCurrent");
+    if (!mkcur(mg_dpy, mg_pbuffer, mg_pbuffer, mg_ctx)) { fprintf(stderr, "ref_gl: glXMakeContextCurrent failed\n"); glava_abort(); }
+    if (!glad_instantiated) {
+        if (!gladLoadGLLoader((GLADloadproc) mg_gpa)) { fprintf(stderr, "ref_gl: glad could not load OpenGL\n"); glava_abort(); }
+        glad_instantiated = true;
+    }
+    /* render.c:2217 calls glTextureBarrierNV unconditionally (in-place gravity pass on one texture).  This Mesa does not
+     * advertise GL_NV_texture_barrier for llvmpipe, so glad leaves the pointer NULL and the reference would jump to 0.
+     * llvmpipe flushes a scene that renders to a resource before a later draw samples that resource, which is all the
+     * barrier asks for; glFinish() stands in for it. */
+    if (!glad_glTextureBarrierNV) { mg_no_barrier = 1; glad_glTextureBarrierNV = mg_texture_barrier; }
+    if (getenv("REF_GL_TRACE_DRAWS")) { mg_real_draw = glad_glDrawArrays; glad_glDrawArrays = mg_trace_draw; }
+    return mg_geom;
+}
+static void  mw_get_pos(void* p, int* x, int* y) { (void) p; *x = mg_geom[0]; *y = mg_geom[1]; }
+static void  mw_get_fbsize(void* p, int* w, int* h) { (void) p; *w = mg_geom[2]; *h = mg_geom[3]; }
+static void  mw_set_geometry(void* p, int x, int y, int w, int h) { (void) p; mg_geom[0] = x; mg_geom[1] = y; mg_geom[2] = w; mg_geom[3] = h; }
+static struct gl_wcb ref_mesa_wcb = {
+    .name = "mesa", .offscreen = mw_offscreen, .init = nw_init, .create_and_bind = mw_create_and_bind,
+    .should_close = nw_false, .should_render = nw_true, .bg_changed = nw_false, .swap_buffers = nw_void, .raise = nw_void,
+    .destroy = nw_void, .terminate = nw_terminate, .get_pos = mw_get_pos, .get_fbsize = mw_get_fbsize,
+    .set_geometry = mw_set_geometry, .set_swap = nw_set_int, .set_floating = nw_set_bool, .set_decorated = nw_set_bool,
+    .set_focused = nw_set_bool, .set_maximized = nw_set_bool, .set_transparent = nw_set_bool, .get_time = nw_get_time,
+    .set_time = nw_set_time, .set_visible = nw_set_visible, .get_environment = nw_environment
+};
+
+const char* ref_gl_strings(int which) {
+    return (const char*) glGetString(which == 0 ? GL_VERSION : which == 1 ? GL_RENDERER : GL_SHADING_LANGUAGE_VERSION);
+}
+
+/* rd_new with the real GL.  NULL when the reference aborted (shader compile errors are printed by the reference). */
+void* ref_gl_new(const char** paths, const char* entry, const char** requests) {
+    bool have = false;
+    for (size_t t = 0; t < wcbs_idx; ++t) have |= wcbs[t] == &ref_mesa_wcb;
+    if (!have) register_wcb(&ref_mesa_wcb);
+    static struct rd_bind no_binds[1] = { { .name = NULL } };
+    void (*saved)(void) = glava_abort;
+    struct glava_renderer* r = NULL;
+    glava_abort = ref_rd_abort;
+    if (setjmp(ref_rd_jmp) == 0) r = rd_new(paths, entry, requests, "mesa", no_binds, STDIN_TYPE_NONE, false, false, false);
+    glava_abort = saved;
+    return r;
+}
+void ref_gl_size(void* rp, int* w, int* h) { (void) rp; *w = mg_geom[2]; *h = mg_geom[3]; }
+
+/* One rd_update (lb / rb transformed in place, as in the reference), then the frame: RGBA8, row 0 = bottom.
+ * returns 0, or -1 when the reference aborted */
+int ref_gl_frame(void* rp, float* lb, float* rb, size_t bsz, int modified, unsigned char* rgba) {
+    struct glava_renderer* r = rp; struct gl_data* gl = r->gl;
+    void (*saved)(void) = glava_abort;
+    int rc = 0;
+    glava_abort = ref_rd_abort;
+    if (setjmp(ref_rd_jmp) == 0) { rd_time(rp); rd_update(rp, lb, rb, bsz, modified != 0); }
+    else rc = -1;
+    glava_abort = saved;
+    if (rc == 0 && rgba) {
+        glBindFramebuffer(GL_READ_FRAMEBUFFER, gl->off_sfbo.fbo);
+        glPixelStorei(GL_PACK_ALIGNMENT, 1);
+        glReadPixels(0, 0, mg_geom[2], mg_geom[3], GL_RGBA, GL_UNSIGNED_BYTE, rgba);
+        glBindFramebuffer(GL_READ_FRAMEBUFFER, 0);
+    }
+    return rc;
+}
+
+/* The 1-D texture stage 1 samples for audio_l (which = 0) / audio_r (1) after the last rd_update, as R16 texels:
+ * the smooth pass' output, or the average / gravity / raw upload when later passes are off.  returns the width, or -1 */
+int ref_gl_texture(void* rp, int which, unsigned short* out, int cap) {
+    struct glava_renderer* r = rp; struct gl_data* gl = r->gl;
+    if (gl->stages_sz == 0) return -1;
+    struct gl_sfbo* st = &gl->stages[0];
+    for (size_t b = 0; b < st->binds_sz; ++b) {
+        struct gl_bind* bd = &st->binds[b];
+        if (bd->src_type != (which ? SRC_AUDIO_R : SRC_AUDIO_L)) continue;
+        GLuint tex = which ? gl->audio_tex_r : gl->audio_tex_l;
+        if (bd->optimize_fft) { tex = bd->gr_store.tex; if (gl->avg_frames > 1) tex = bd->av.tex; }
+        if (gl->smooth_pass) tex = bd->sm.tex;
+        GLint w = 0;
+        glBindTexture(GL_TEXTURE_1D, tex);
+        glGetTexLevelParameteriv(GL_TEXTURE_1D, 0, GL_TEXTURE_WIDTH, &w);
+        if (w < 1 || w > cap) return -1;
+        glPixelStorei(GL_PACK_ALIGNMENT, 1);
+        glGetTexImage(GL_TEXTURE_1D, 0, GL_RED, GL_UNSIGNED_SHORT, out);
+        return (int) w;
+    }
+    return -1;
+}
+/* any 1-D texture of a bind, for looking at the passes one by one: stage 0, bind of audio_l / audio_r,
+ * what = 0 upload (transform_fft output), 1 gr_store (K1 / K2), 2 av (K4), 3 sm (K5), 4.. gr.out[what - 4] (K3 ring) */
+int ref_gl_pass_texture(void* rp, int which, int what, unsigned short* out, int cap) {
+    struct glava_renderer* r = rp; struct gl_data* gl = r->gl;
+    if (gl->stages_sz == 0) return -1;
+    struct gl_sfbo* st = &gl->stages[0];
+    for (size_t b = 0; b < st->binds_sz; ++b) {
+        struct gl_bind* bd = &st->binds[b];
+        if (bd->src_type != (which ? SRC_AUDIO_R : SRC_AUDIO_L)) continue;
+        GLuint tex = 0;
+        switch (what) {
+            case 0: tex = which ? gl->audio_tex_r : gl->audio_tex_l; break;
+            case 1: tex = bd->gr_store.tex; break;
+            case 2: tex = bd->av.tex; break;
+            case 3: tex = bd->sm.tex; break;
+            default: if (bd->gr.out && (size_t) (what - 4) < bd->gr.out_sz) tex = bd->gr.out[what - 4].tex; break;
+        }
+        if (!tex) return -1;
+        GLint w = 0;
+        glBindTexture(GL_TEXTURE_1D, tex);
+        glGetTexLevelParameteriv(GL_TEXTURE_1D, 0, GL_TEXTURE_WIDTH, &w);
+        if (w < 1 || w > cap) return -1;
+        glPixelStorei(GL_PACK_ALIGNMENT, 1);
+        glGetTexImage(GL_TEXTURE_1D, 0, GL_RED, GL_UNSIGNED_SHORT, out);
+        return (int) w;
+    }
+    return -1;
+}
+/* the shader tree packed into this library by the build (oracle/pack_shaders.py) -> files under `dir`; returns the
+ * number of files written, -1 on an I/O error */
+#include <sys/stat.h>
+extern const unsigned char ref_shader_blob[];
+extern const unsigned long ref_shader_blob_size;
+int ref_gl_unpack_shaders(const char* dir) {
+    const unsigned char* p = ref_shader_blob;
+    unsigned count; memcpy(&count, p, 4); p += 4;
+    for (unsigned i = 0; i < count; ++i) {
+        unsigned short plen; memcpy(&plen, p, 2); p += 2;
+        char path[2048];
+        int base = snprintf(path, sizeof(path), "%s/", dir);
+        if (base < 0 || (size_t) base + plen + 1 > sizeof(path)) return -1;
+        memcpy(path + base, p, plen); path[base + plen] = '\0'; p += plen;
+        unsigned size; memcpy(&size, p, 4); p += 4;
+        for (char* q = path + base; *q; ++q) if (*q == '/') { *q = '\0'; mkdir(path, 0755); *q = '/'; }
+        FILE* f = fopen(path, "wb");
+        if (!f) return -1;
+        if (size && fwrite(p, 1, size, f) != size) { fclose(f); return -1; }
+        fclose(f); p += size;
+    }
+    return (int) count;
+}
+int ref_gl_get_error(void) { return (int) glGetError(); }
+int ref_gl_stage_count(void* rp) { return (int) ((struct glava_renderer*) rp)->gl->stages_sz; }
+void ref_gl_destroy(void* rp) { rd_destroy(rp); }
+#endif

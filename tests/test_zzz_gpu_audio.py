@@ -57,14 +57,14 @@ def test_audio_frame_equals_update_with_the_collected_rings(built):
             g.Renderer(p, batch=batch) as r, g.Renderer(p, batch=batch) as r2:
         while len(be.streams) < batch:
             time.sleep(0.001)
-        for step in range(5):
-            modified = False
+        for step in range(7):
+            mask = np.zeros(batch, bool)
             for s in range(batch):
                 if step != 2 and (step + s) % 3 != 1:                     # step 2: nobody publishes -> modified = 0 re-raster
                     lb[s] = (rng.random(n, np.float32) - 0.5) * 0.2; rb[s] = (rng.random(n, np.float32) - 0.5) * 0.2
-                    be.publish(s, lb[s], rb[s]); modified = True
+                    be.publish(s, lb[s], rb[s]); mask[s] = True
             ab.frame(r)
-            r2.update(lb, rb, modified)
+            r2.update_masked(lb, rb, mask)                                # glava.c:528-537 per stream: only those that ticked run the chain
         r.sync(); r2.sync()
         a, b = r.spectrum(), r2.spectrum()
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[0].any()
