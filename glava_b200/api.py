@@ -69,6 +69,39 @@ class Params(C.Structure):
     def module_name(self):
         return MODULES[self.module]
 
+    def to_dict(self):
+        """JSON-serialisable copy (nested structs as dicts, arrays as lists); floats survive exactly"""
+        def conv(v):
+            if isinstance(v, ColorProg):                         # only the instructions in use
+                return {"n_ops": v.n_ops, "result": v.result, "ops": [conv(v.ops[i]) for i in range(v.n_ops)]}
+            if isinstance(v, C.Structure):
+                return {n: conv(getattr(v, n)) for n, _t in v._fields_}
+            if isinstance(v, C.Array):
+                return [conv(x) for x in v]
+            return v
+        return conv(self)
+
+    @classmethod
+    def from_dict(cls, d):
+        def fill(dst, src):
+            for n, _t in dst._fields_:
+                if n not in src:
+                    continue
+                cur = getattr(dst, n)
+                if isinstance(cur, C.Structure):
+                    fill(cur, src[n])
+                elif isinstance(cur, C.Array):
+                    for i, x in enumerate(src[n]):
+                        if isinstance(cur[i], C.Structure):
+                            fill(cur[i], x)
+                        else:
+                            cur[i] = x
+                else:
+                    setattr(dst, n, src[n])
+        q = cls()
+        fill(q, d)
+        return q
+
 
 _lib = None
 

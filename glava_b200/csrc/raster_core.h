@@ -114,14 +114,22 @@ GLB_HD uint32_t premultiply8(uint32_t px) {                              // util
 // ---- non-native opacity (`setopacity "none"` / "xroot": premultiply_alpha == 0) --------------------------------------
 // The reference then enables GL_BLEND with glBlendFunc(GL_SRC_ALPHA, GL_ONE_MINUS_SRC_ALPHA) for every module stage
 // (render.c:1467-1470), each drawn into a target glClear'd to the `setbg` colour (render.c:1700, 2028), and skips the
-// premultiply stages (util/premultiply.frag:2-4).  Fixed-function blending restated in float32: fragment clamped to [0, 1],
-// destination read back from the RGBA8 target, C = Cs * As + Cd * (1 - As) for all four channels, each op rounded.
+// premultiply stages (util/premultiply.frag:2-4).  Blending happens in the target's own 8-bit normalised fixed point, as
+// llvmpipe does it (tests/golden/llvmpipe_golden.npz: the reference's non-native-opacity frames are reproduced bit for bit):
+// the fragment is converted to unorm8 first, then C = mul_norm(Cs, As) + mul_norm(Cd, 255 - As) per channel, alpha
+// included, saturating; mul_norm(a, b) = (t + (t >> 8)) >> 8 with t = a * b + 128 (a * b / 255 rounded).
 // NATIVE = true is the shipped mode and compiles to exactly the code it was before this existed.
+GLB_HD uint32_t mul_norm8(uint32_t a, uint32_t b) { const uint32_t t = a * b + 128u; return (t + (t >> 8)) >> 8; }
 GLB_HD uint32_t blend_store(const glava_b200_params& p, f4 s) {
-    s = mk4(g_clamp(s.r, 0.0f, 1.0f), g_clamp(s.g, 0.0f, 1.0f), g_clamp(s.b, 0.0f, 1.0f), g_clamp(s.a, 0.0f, 1.0f));
-    const f4 d = unpack8(pack8(mk4a(p.clear_color)));
-    const float k = 1.0f - s.a;
-    return pack8(mk4((s.r * s.a) + (d.r * k), (s.g * s.a) + (d.g * k), (s.b * s.a) + (d.b * k), (s.a * s.a) + (d.a * k)));
+    const uint32_t S = pack8(s), D = pack8(mk4a(p.clear_color));
+    const uint32_t a = S >> 24, ia = 255u - a;
+    uint32_t out = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t r = mul_norm8((S >> (8 * c)) & 255u, a) + mul_norm8((D >> (8 * c)) & 255u, ia);
+        out |= (r > 255u ? 255u : r) << (8 * c);
+    }
+    return out;
 }
 template <bool NATIVE> GLB_HD uint32_t stage_store(const glava_b200_params& p, f4 s) { return NATIVE ? pack8(s) : blend_store(p, s); }
 template <bool NATIVE> GLB_HD uint32_t stage_bg(const glava_b200_params& p) { return NATIVE ? 0u : blend_store(p, mk4(0.0f, 0.0f, 0.0f, 0.0f)); }

@@ -19,9 +19,16 @@ GLB_HD float g_min(float a, float b) { return b < a ? b : a; }
 GLB_HD float g_max(float a, float b) { return a < b ? b : a; }
 GLB_HD float g_mod(float x, float y) { return x - y * floorf(x / y); }
 GLB_HD float g_sign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
-// float -> unorm store, NaN -> 0
-GLB_HD uint32_t unorm8(float c)  { return c > 0.0f ? (c < 1.0f ? (uint32_t) (c * 255.0f + 0.5f) : 255u) : 0u; }
-GLB_HD uint32_t unorm16(float c) { return c > 0.0f ? (c < 1.0f ? (uint32_t) (c * 65535.0f + 0.5f) : 65535u) : 0u; }
+// float -> unorm store: clamp, then ONE rounding of the float32 product, ties to even (Mesa's _mesa_float_to_unorm; the
+// llvmpipe goldens pin it: the reference's R16 uploads are reproduced bit for bit), NaN -> 0.
+// cvt.rni on the device, lrintf on the host (default rounding mode): the same bits.
+#if defined(__CUDA_ARCH__)
+GLB_HD uint32_t g_rne(float v) { return (uint32_t) __float2int_rn(v); }
+#else
+GLB_HD uint32_t g_rne(float v) { return (uint32_t) lrintf(v); }
+#endif
+GLB_HD uint32_t unorm8(float c)  { return c > 0.0f ? (c < 1.0f ? g_rne(c * 255.0f) : 255u) : 0u; }
+GLB_HD uint32_t unorm16(float c) { return c > 0.0f ? (c < 1.0f ? g_rne(c * 65535.0f) : 65535u) : 0u; }
 // unorm fetch = (float) u / MAX, correctly rounded.  Computed as a reciprocal multiply plus one
 // fma residual correction, which equals the IEEE quotient for every u in range
 // (exhaustively checked: tests/test_emul_parity.py::test_unorm_fetch_is_exact_division).

@@ -8,7 +8,8 @@
  *   - mod(x, y)  = x - y * floor(x / y)
  *   - round(x)   = nearest, ties to even
  *   - mix(a,b,t) = a * (1 - t) + b * t
- *   - float -> unorm8/unorm16 store = (int)(clamp(c, 0, 1) * MAX + 0.5f), NaN -> 0
+ *   - float -> unorm8/unorm16 store = lrintf(clamp(c, 0, 1) * MAX): ONE rounding, ties to even (round 1 used
+ *     (int)(c * MAX + 0.5f), whose second float rounding is off by one in a band around every half), NaN -> 0
  *   - unorm -> float fetch          = (float) u / MAX
  *   - texelFetch outside [0, size)  = 0 (llvmpipe behaviour; undefined in GL)
  *   - texture() on the 1-D audio textures: NEAREST + REPEAT (render.c:510-518)
@@ -47,9 +48,10 @@ static inline float g_max(float a, float b) { return a < b ? b : a; }
 static inline float g_mod(float x, float y) { return x - y * floorf(x / y); }
 static inline float g_sign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
 static inline float g_round(float x) { return rintf(x); }
-/* clamp + round-half-up; a NaN input (0/0 weight in K5) stores 0 */
-static inline uint32_t unorm8(float c)  { return c > 0.0f ? (c < 1.0f ? (uint32_t) (c * 255.0f + 0.5f) : 255u) : 0u; }
-static inline uint16_t unorm16(float c) { return c > 0.0f ? (c < 1.0f ? (uint16_t) (c * 65535.0f + 0.5f) : 65535u) : 0u; }
+/* clamp, then the float32 product rounded to nearest-even (Mesa's _mesa_float_to_unorm; pinned by the llvmpipe goldens:
+ * the reference's uploads are reproduced bit for bit); a NaN input (0/0 weight in K5) stores 0 */
+static inline uint32_t unorm8(float c)  { return c > 0.0f ? (c < 1.0f ? (uint32_t) lrintf(c * 255.0f) : 255u) : 0u; }
+static inline uint16_t unorm16(float c) { return c > 0.0f ? (c < 1.0f ? (uint16_t) lrintf(c * 65535.0f) : 65535u) : 0u; }
 static inline float from8(uint32_t u)  { return (float) u / 255.0f; }
 static inline float from16(uint16_t u) { return (float) u / 65535.0f; }
 
@@ -715,15 +717,28 @@ static vec4 wave_px(const rctx* c, int x, int y) {                       /* wave
 
 /* What a stage's `fragment` becomes in its RGBA8 target.  setopacity "native": blending is off (render.c:1467-1470), plain
  * unorm8 conversion.  Any other opacity: GL_BLEND with glBlendFunc(GL_SRC_ALPHA, GL_ONE_MINUS_SRC_ALPHA) over the target
- * glClear'd to the `setbg` colour (render.c:1700, 2028) — fixed-function blending restated in float32: source clamped to
- * [0, 1], destination read back from the 8-bit target, C = Cs * As + Cd * (1 - As) on all four channels. */
+ * glClear'd to the `setbg` colour (render.c:1700, 2028) — fixed-function blending in unorm8 fixed point (below). */
 static inline float clamp01(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
 static uint32_t store8(const orc_params* p, vec4 s) {
     if (p->premultiply_alpha) return pack8(s);
     s = v4(clamp01(s.r), clamp01(s.g), clamp01(s.b), clamp01(s.a));
-    vec4 d = unpack8(pack8(v4a(p->clear_color)));
-    float k = 1.0f - s.a;
-    return pack8(v4((s.r * s.a) + (d.r * k), (s.g * s.a) + (d.g * k), (s.b * s.a) + (d.b * k), (s.a * s.a) + (d.a * k)));
+    /* Blending happens in the target's own 8-bit normalised fixed point (llvmpipe's unorm8 blend; pinned by the llvmpipe
+     * goldens, where every non-native-opacity frame is reproduced bit for bit): the fragment is converted to unorm8 FIRST,
+     * then  C = mul_norm(Cs, As) + mul_norm(Cd, 255 - As)  per channel (alpha included), saturating;
+     * mul_norm(a, b) = (t + (t >> 8)) >> 8 with t = a * b + 128, i.e. a * b / 255 rounded. */
+    {
+        const uint32_t S = pack8(s), D = pack8(v4a(p->clear_color));
+        const uint32_t a = S >> 24;
+        uint32_t out = 0;
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t v1 = (S >> (8 * c)) & 255u, v0 = (D >> (8 * c)) & 255u;
+            uint32_t t1 = v1 * a + 128u;         t1 = (t1 + (t1 >> 8)) >> 8;
+            uint32_t t0 = v0 * (255u - a) + 128u; t0 = (t0 + (t0 >> 8)) >> 8;
+            uint32_t r = t1 + t0; if (r > 255u) r = 255u;
+            out |= r << (8 * c);
+        }
+        return out;
+    }
 }
 
 static uint32_t stage1(const rctx* c, int x, int y) {

@@ -10,7 +10,8 @@ operand order, stage chaining and RGBA8 / R16 quantisation all come from the ref
 
 What it does not take from the reference (because GLSL leaves it to the implementation) is fixed as in DESIGN.md 4.3:
 float = binary32 with every operation rounded; transcendentals = this host's libm (sinf, cosf, atan2f, logf, powf ...);
-round() = nearest-even; texelFetch outside the texture = 0; unorm stores = floor(clamp(c) * MAX + 0.5).
+round() = nearest-even; texelFetch outside the texture = 0; unorm stores = rint(float32(clamp(c) * MAX)), ties to even
+(what Mesa does: tests/golden/llvmpipe_golden.npz, the reference on a real llvmpipe, pins it).
 
 Only tests/ and tests/golden/make_glsl_golden.py use this file; it needs /root/reference at run time, so everything that
 must run elsewhere goes through the golden vectors that script commits.
@@ -895,7 +896,7 @@ def unorm8(c):
         return 0
     if not c < 1.0:
         return 255
-    return int(F32(F32(F32(c) * F32(255.0)) + F32(0.5)))
+    return int(np.rint(F32(F32(c) * F32(255.0))))              # one rounding of the float32 product, ties to even (Mesa)
 
 
 def unorm16(c):
@@ -904,7 +905,7 @@ def unorm16(c):
         return 0
     if not c < 1.0:
         return 65535
-    return int(F32(F32(F32(c) * F32(65535.0)) + F32(0.5)))
+    return int(np.rint(F32(F32(c) * F32(65535.0))))
 
 
 def header_macros(pp, smooth_factor=0.025, avg_frames=5, avg_window=1, premultiply_alpha=1, channels=2, pre_smoothed=1):
@@ -944,8 +945,7 @@ class ModuleProgram:
         self.w, self.h = w, h
         # setopacity other than "native" (premultiply_alpha = 0): every stage is drawn with GL_BLEND enabled,
         # glBlendFunc(GL_SRC_ALPHA, GL_ONE_MINUS_SRC_ALPHA), over the target glClear'd to `setbg` (render.c:1467-1470,
-        # 1700, 2028).  Fixed-function blending restated in float32: fragment clamped to [0, 1], destination read back from
-        # the RGBA8 target, every operation individually rounded.
+        # 1700, 2028).  Blending in the target's unorm8 fixed point, as llvmpipe does it (pinned by llvmpipe_golden.npz).
         self.blend = hdr.get("premultiply_alpha", 1) == 0
         self.clear8 = tuple(unorm8(F32(c)) for c in clear_color)
         self.stages = []
@@ -971,11 +971,14 @@ class ModuleProgram:
             g = self.stages[k].run(u, x, y)
             frag = [to_float(v) for v in g["fragment"].v]
             if self.blend:
-                src = [min(max(v, F32(0.0)), F32(1.0)) for v in frag]
-                dst = [F32(F32(d) / F32(255.0)) for d in self.clear8]
-                a = src[3]
-                k1 = F32(F32(1.0) - a)
-                frag = [F32(F32(src[i] * a) + F32(dst[i] * k1)) for i in range(4)]
+                # unorm8 fixed-point blend (llvmpipe): mul_norm(Cs, As) + mul_norm(Cd, 255 - As), saturating
+                def mul_norm(p, q):
+                    t = p * q + 128
+                    return (t + (t >> 8)) >> 8
+                s8 = [unorm8(v) for v in frag]
+                a = s8[3]
+                c[key] = tuple(min(mul_norm(s8[i], a) + mul_norm(self.clear8[i], 255 - a), 255) for i in range(4))
+                return c[key]
             c[key] = tuple(unorm8(v) for v in frag)
         return c[key]
 

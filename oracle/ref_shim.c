@@ -520,7 +520,16 @@ static void* mw_create_and_bind(const char* name, const char* class, const char*
     (void) name; (void) class; (void) type; (void) states; (void) states_sz; (void) clickthrough; (void) offscreen;
     mg_geom[0] = x; mg_geom[1] = y; mg_geom[2] = w; mg_geom[3] = h;
     if (!mg_gpa) { fprintf(stderr, "ref_gl: ref_gl_load was not called\n"); glava_abort(); }
-    if (!mg_ctx) {
+    {
+        /* a fresh context per renderer, as every GLava process has: rd_new relies on GL's initial state (blending off,
+         * ...) and e.g. `setopacity "none"` leaves GL_BLEND enabled behind */
+        if (mg_ctx) {
+            int (*mkcur0)(void*, unsigned long, unsigned long, void*) = (int (*)(void*, unsigned long, unsigned long, void*)) mg_gpa("glXMakeContextCurrent");
+            void (*destroy)(void*, void*) = (void (*)(void*, void*)) mg_gpa("glXDestroyContext");
+            mkcur0(mg_dpy, 0, 0, NULL);
+            destroy(mg_dpy, mg_ctx);
+            mg_ctx = NULL;
+        }
         void** (*choose)(void*, int, const int*, int*) = (void** (*)(void*, int, const int*, int*)) mg_gpa("glXChooseFBConfig");
         void*  (*mkpb)(void*, void*, const int*) = (void* (*)(void*, void*, const int*)) mg_gpa("glXCreatePbuffer");
         void*  (*mkctx)(void*, void*, void*, int, const int*) = (void* (*)(void*, void*, void*, int, const int*)) mg_gpa("glXCreateContextAttribsARB");
@@ -530,7 +539,7 @@ static void* mw_create_and_bind(const char* name, const char* class, const char*
         void** cfgs = choose(mg_dpy, 0, fbattr, &n);
         if (!cfgs || n < 1) { fprintf(stderr, "ref_gl: no GLX framebuffer configuration\n"); glava_abort(); }
         const int pbattr[] = { 0x8041 /* GLX_PBUFFER_WIDTH */, 16, 0x8040 /* GLX_PBUFFER_HEIGHT */, 16, 0 };
-        mg_pbuffer = (unsigned long) mkpb(mg_dpy, cfgs[0], pbattr);
+        if (!mg_pbuffer) mg_pbuffer = (unsigned long) mkpb(mg_dpy, cfgs[0], pbattr);
         const int cattr[] = { 0x2091 /* MAJOR */, major, 0x2092 /* MINOR */, minor, 0x9126 /* PROFILE_MASK */, 0x1 /* core, as glx_wcb.c asks */, 0 };
         mg_ctx = mkctx(mg_dpy, cfgs[0], NULL, 1, cattr);
         if (!mg_ctx) { fprintf(stderr, "ref_gl: glXCreateContextAttribsARB(%d.%d core) failed\n", major, minor); glava_abort(); }

@@ -128,7 +128,7 @@ def test_chain_core_keyframe_upload_bit_exact(orc, built):
     rng = np.random.default_rng(13)
     s = (rng.random(1024) * 1.2 - 0.1).astype(np.float32); e = (rng.random(1024) * 1.2 - 0.1).astype(np.float32)
     s[5] = np.nan
-    q = lambda v: np.where(v > 0, np.where(v < 1, (v * np.float32(65535.0) + np.float32(0.5)).astype(np.int64), 65535), 0).astype(np.uint16)
+    q = lambda v: np.where(v > 0, np.where(v < 1, np.rint((v * np.float32(65535.0)).astype(np.float32)).astype(np.int64), 65535), 0).astype(np.uint16)
     ur, fr = np.float32(86.1328125), np.float32(240.0)
     for k in (0, 1, 2, 5):
         with np.errstate(invalid="ignore"):

@@ -72,7 +72,7 @@ def test_stream_interpolation_shows_an_update_one_update_late(orc):
         specs.append(plain.update(lb, rb, True)[0])
         frames = [st.update(lb, rb, True)[2]] + [st.update(lb, rb, False)[2] for _ in range(3)]
         texs.append(frames)
-    q = lambda v: np.where(v > 0, np.where(v < 1, (v * np.float32(65535.0) + np.float32(0.5)).astype(np.int64), 65535), 0).astype(np.uint16)
+    q = lambda v: np.where(v > 0, np.where(v < 1, np.rint((v * np.float32(65535.0)).astype(np.float32)).astype(np.int64), 65535), 0).astype(np.uint16)
     # kcounter is reset AFTER a modified frame (render.c:2380-2383), so with 3 sub-frames per update the modifier runs
     # 0, 1/4, 2/4 on the sub-frames and 3/4 on the next modified frame, whose lerp still uses the old keyframes
     zero = np.zeros(1024, np.float32)

@@ -36,7 +36,7 @@ def test_pipeline_a_matches_reference_golden(orc, n):
         if u == 12:
             assert np.array_equal(_bits(orc.fft_f32(p, ring)), _bits(gold["raw_fft_12"]))
             # texture = GL_R16 upload of the float result (render.c:521-524)
-            want = np.clip(spec, 0, 1).astype(np.float32) * np.float32(65535) + np.float32(0.5)
+            want = np.rint((np.clip(spec, 0, 1).astype(np.float32) * np.float32(65535)).astype(np.float32))
             assert np.array_equal(tex, want.astype(np.uint16))
 
 

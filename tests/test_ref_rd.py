@@ -41,7 +41,7 @@ def _user_dir(path, files):
 
 def _unorm16(v):
     v = np.asarray(v, np.float32)
-    q = (v * np.float32(65535.0) + np.float32(0.5)).astype(np.float32)
+    q = np.rint((v * np.float32(65535.0)).astype(np.float32))       # GL's float -> R16: one rounding, ties to even (Mesa; llvmpipe goldens)
     with np.errstate(invalid="ignore"):
         return np.where(v > 0, np.where(v < 1, q.astype(np.int64), 65535), 0).astype(np.uint16)
 

@@ -52,5 +52,5 @@ def fake_apply(self, renderer):
     self._last = self.binds(); renderer.reconfigure(self.params())
 api.Pipe.apply = fake_apply
 sys.exit(pytest.main(["-x", "-q", "-m", "gpu", "-p", "no:cacheprovider",
-                      ROOT + "/tests/test_zz_gpu_blend.py", ROOT + "/tests/test_zz_gpu_color_expr.py", ROOT + "/tests/test_zz_gpu_pipe.py", ROOT + "/tests/test_glsl_golden.py", ROOT + "/tests/test_zz_rd_golden.py",
+                      ROOT + "/tests/test_zz_gpu_blend.py", ROOT + "/tests/test_zz_gpu_color_expr.py", ROOT + "/tests/test_zz_gpu_pipe.py", ROOT + "/tests/test_glsl_golden.py", ROOT + "/tests/test_zz_rd_golden.py", ROOT + "/tests/test_llvmpipe_golden.py",
                       ]))
