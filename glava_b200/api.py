@@ -137,6 +137,12 @@ def lib():
     L.glava_b200_host_alloc.restype = vp
     L.glava_b200_host_alloc.argtypes = [C.c_size_t]
     L.glava_b200_host_free.argtypes = [vp]
+    L.glava_b200_host_alloc_on.restype = vp
+    L.glava_b200_host_alloc_on.argtypes = [C.c_size_t, i32]
+    L.glava_b200_device_numa_node.argtypes = [i32]
+    L.glava_b200_bind_thread_to_device.argtypes = [i32]
+    L.glava_b200_set_async_input.argtypes = [vp, i32]
+    L.glava_b200_wait_input.argtypes = [vp]
     L.glava_b200_update.argtypes = [vp, vp, vp, C.c_size_t, i32]
     L.glava_b200_update_device.argtypes = [vp, vp, vp, C.c_size_t, i32]
     L.glava_b200_update_masked.argtypes = [vp, vp, vp, C.c_size_t, vp]
@@ -272,11 +278,12 @@ class Pipe:
 _pinned = []
 
 
-def pinned_empty(shape, dtype):
-    """numpy array backed by cudaHostAlloc'd (pinned) memory; lives until process exit."""
+def pinned_empty(shape, dtype, device=None):
+    """numpy array backed by pinned host memory on the NUMA node of `device` (default: the current CUDA device);
+    lives until process exit."""
     dtype = np.dtype(dtype)
     nbytes = int(np.prod(shape)) * dtype.itemsize
-    ptr = lib().glava_b200_host_alloc(nbytes)
+    ptr = lib().glava_b200_host_alloc(nbytes) if device is None else lib().glava_b200_host_alloc_on(nbytes, int(device))
     if not ptr:
         raise GlavaError("pinned allocation failed")
     buf = (C.c_byte * nbytes).from_address(ptr)
@@ -357,6 +364,12 @@ class Renderer:
     def update_rings(self, modified=True):
         _check(self._L.glava_b200_update_rings(self._h, 1 if modified else 0))
         self._after_update()
+
+    def set_async_input(self, enable=True):
+        _check(self._L.glava_b200_set_async_input(self._h, 1 if enable else 0))
+
+    def wait_input(self):
+        _check(self._L.glava_b200_wait_input(self._h))
 
     def sync(self):
         _check(self._L.glava_b200_sync(self._h))

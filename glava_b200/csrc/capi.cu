@@ -12,6 +12,12 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <sched.h>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -72,6 +78,7 @@ struct glava_b200 {
     // inputs
     float* d_pcm[2][2];         // H2D staging for glava_b200_update, double-buffered  [2][batch][n] x {l, r}
     int    stage_cur;
+    bool   async_input; int last_in;   // glava_b200_set_async_input: update() does not wait for its H2D copy
     cudaStream_t copy_stream;   // H2D of update i+1 overlaps the kernels of update i
     // asynchronous frame read-back: D2D into a staging frame on the raster stream (microseconds), D2H from there on its
     // own stream — the PCIe copy of frame i runs under raster i+1 instead of in front of it
@@ -156,15 +163,102 @@ int glava_b200_load_config_binds(glava_b200_params* out, const char* const* path
     return load_config(out, paths, entry, requests, force_module, binds);
 }
 
-void* glava_b200_host_alloc(size_t bytes) {
+// ---- NUMA placement of pinned host memory -----------------------------------------------------------------------------
+// On a two-socket box (the 8-GPU B200 node: GPUs 0-3 behind socket 0, 4-7 behind socket 1) a pinned buffer on the other
+// socket makes every H2D / D2H DMA cross the inter-socket link; eight ranks doing so together was what collapsed round 1's
+// end-to-end scaling.  Pinned buffers are therefore page-placed on the NUMA node of the device they feed: anonymous
+// mapping + mbind(MPOL_BIND) + first touch + cudaHostRegister.  No libnuma in the image: the raw syscall.
+static std::mutex g_host_mu;
+static std::map<void*, size_t> g_host_maps;          // mmap'd + registered blocks (everything else came from cudaHostAlloc)
+
+static int device_numa_node(int device) {
+    char bus[32] = { 0 };
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (char* c = bus; *c; ++c) if (*c >= 'A' && *c <= 'Z') *c = (char) (*c - 'A' + 'a');
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+
+extern "C" {
+
+int glava_b200_device_numa_node(int device) { return device_numa_node(device); }
+
+// Pin the calling thread to the CPUs of the device's NUMA node (what `numactl --cpunodebind` does for a one-rank-per-GPU
+// process).  Returns the node, or -1 when the topology is not exposed (nothing changed).
+int glava_b200_bind_thread_to_device(int device) {
+    const int node = device_numa_node(device);
+    if (node < 0) return -1;
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    FILE* f = fopen(path, "r");
+    if (!f) return -1;
+    cpu_set_t set; CPU_ZERO(&set);
+    int a = 0, b = 0, any = 0;
+    while (fscanf(f, "%d", &a) == 1) {
+        b = a;
+        int ch = fgetc(f);
+        if (ch == '-') { if (fscanf(f, "%d", &b) != 1) b = a; ch = fgetc(f); }
+        for (int c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET(c, &set); any = 1; }
+        if (ch != ',') break;
+    }
+    fclose(f);
+    if (!any || sched_setaffinity(0, sizeof(set), &set) != 0) return -1;
+    return node;
+}
+
+void* glava_b200_host_alloc_on(size_t bytes, int device) {
+    if (bytes == 0) bytes = 16;
+    const int node = getenv("GLAVA_B200_NO_NUMA") ? -1 : device_numa_node(device);
+    if (node >= 0 && node < 64) {
+        const size_t page = (size_t) sysconf(_SC_PAGESIZE);
+        const size_t len = (bytes + page - 1) / page * page;
+        void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (p != MAP_FAILED) {
+            unsigned long mask = 1ul << node;
+            const long rc = syscall(SYS_mbind, p, len, 2 /* MPOL_BIND */, &mask, 64ul, 0u);
+            if (rc == 0) {
+                for (size_t o = 0; o < len; o += page) ((volatile char*) p)[o] = 0;      // first touch: the pages now exist on `node`
+                if (cudaHostRegister(p, len, cudaHostRegisterPortable) == cudaSuccess) {
+                    std::lock_guard<std::mutex> lk(g_host_mu);
+                    g_host_maps[p] = len;
+                    return p;
+                }
+                cudaGetLastError();
+            }
+            munmap(p, len);
+        }
+    }
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
         fail(GLAVA_B200_ECUDA, "cudaHostAlloc(%zu) failed", bytes);
         return nullptr;
     }
     return p;
 }
-void glava_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
+void* glava_b200_host_alloc(size_t bytes) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    return glava_b200_host_alloc_on(bytes, dev);
+}
+void glava_b200_host_free(void* p) {
+    if (!p) return;
+    size_t len = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_host_mu);
+        auto it = g_host_maps.find(p);
+        if (it != g_host_maps.end()) { len = it->second; g_host_maps.erase(it); }
+    }
+    if (len) { cudaHostUnregister(p); munmap(p, len); }
+    else cudaFreeHost(p);
+}
+
+}  // extern "C"
 
 static void dev_free(glava_b200* r, void* ptr) {
     if (!ptr) return;
@@ -397,7 +491,7 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     r->out_stream = nullptr; r->d_stage[0] = r->d_stage[1] = nullptr; r->stage_bytes = 0; r->out_cur = 0;
     for (int i = 0; i < 2; ++i) { r->ev_stage_ready[i] = nullptr; r->ev_stage_free[i] = nullptr; }
     r->updates = 0; r->launches = 0; r->timing = false;
-    r->desync = false; r->umask_cur = 0;
+    r->desync = false; r->umask_cur = 0; r->async_input = false; r->last_in = -1;
     for (int i = 0; i < 4; ++i) { r->h_umask[i] = nullptr; r->d_umask[i] = nullptr; r->ev_umask[i] = nullptr; }
     if (build(r) != 0) { glava_b200_destroy(r); return nullptr; }
     return r;
@@ -701,8 +795,25 @@ static int update_host(glava_b200* r, const float* lb, const float* rb, size_t b
     if (modified) {
         CU(cudaEventRecord(r->ev_free[b], r->spec_stream));
         r->stage_cur = b ^ 1;
-        CU(cudaEventSynchronize(r->ev_copied[b]));
+        r->last_in = b;
+        if (!r->async_input) CU(cudaEventSynchronize(r->ev_copied[b]));
     }
+    return 0;
+}
+
+// Double-buffer contract for the host rings (instead of rd_update's "consumed on return"): with async input enabled
+// glava_b200_update* return as soon as the copy is ENQUEUED; the caller keeps lb / rb untouched until
+// glava_b200_wait_input() — in practice it alternates between two sets of rings, and the host never blocks on a copy.
+int glava_b200_set_async_input(glava_b200* r, int enable) {
+    if (!r) return fail(GLAVA_B200_EINVAL, "null argument");
+    r->async_input = enable != 0;
+    return 0;
+}
+int glava_b200_wait_input(glava_b200* r) {
+    if (!r) return fail(GLAVA_B200_EINVAL, "null argument");
+    if (r->last_in < 0) return 0;
+    CU(cudaSetDevice(r->device));
+    CU(cudaEventSynchronize(r->ev_copied[r->last_in]));
     return 0;
 }
 

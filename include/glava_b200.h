@@ -222,8 +222,15 @@ const char* glava_b200_module_name(const glava_b200* r);
 
 /* Pinned host memory for the PCM rings handed to glava_b200_update (so the H2D copy is a
  * true async DMA).  Plain malloc'd memory is accepted too, just slower. */
-void* glava_b200_host_alloc(size_t bytes);
+void* glava_b200_host_alloc(size_t bytes);                 /* placed on the NUMA node of the CURRENT CUDA device */
+void* glava_b200_host_alloc_on(size_t bytes, int device);  /* ... of `device` (anonymous mapping + mbind + cudaHostRegister;
+                                                              plain cudaHostAlloc when the topology is not exposed or
+                                                              GLAVA_B200_NO_NUMA is set) */
 void  glava_b200_host_free(void* p);
+/* NUMA helpers for one-process-per-GPU callers: the node a device hangs off (-1: unknown), and pinning the calling
+ * thread to that node's CPUs (what `numactl --cpunodebind` would do; returns the node or -1, nothing changed). */
+int   glava_b200_device_numa_node(int device);
+int   glava_b200_bind_thread_to_device(int device);
 
 /* rd_update (render.h:58-59; render.c:1743-2417), batched.
  *   lb, rb : HOST, [batch][bsz] float32, ring contents oldest-first, exactly what glava.c:528-537
@@ -238,6 +245,11 @@ void  glava_b200_host_free(void* p);
  * stream.  Returns once the host buffers have been consumed (they may be reused immediately) and the
  * kernels are enqueued; call glava_b200_sync to wait for the frame. */
 int glava_b200_update(glava_b200* r, const float* lb, const float* rb, size_t bsz, int modified);
+/* Double-buffer contract for callers that must not block: after glava_b200_set_async_input(r, 1) the update calls return
+ * once the H2D copy is ENQUEUED; lb / rb must stay untouched until glava_b200_wait_input(r) (or the next glava_b200_sync).
+ * A caller alternating between two sets of rings never waits on a copy. */
+int glava_b200_set_async_input(glava_b200* r, int enable);
+int glava_b200_wait_input(glava_b200* r);
 /* same with DEVICE pointers (inputs already resident in HBM) */
 int glava_b200_update_device(glava_b200* r, const float* d_lb, const float* d_rb, size_t bsz, int modified);
 

@@ -65,6 +65,7 @@ def lib():
     L.ref_gl_size.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
     L.ref_gl_destroy.argtypes = [vp]
     L.ref_gl_unpack_shaders.argtypes = [cp]
+    L.ref_gl_finish.restype = None
     L.ref_rd_set_rates.argtypes = [vp, C.c_float, C.c_float]
     L.ref_rd_config.argtypes = [vp, vp, vp]
     if L.ref_gl_load(os.path.join(HERE, "_ref", "fakex").encode(), mesa.encode()) != 0:
@@ -158,6 +159,9 @@ class ReferenceGL:
         if rc != 0:
             raise ValueError("the reference aborted in rd_update")
         return img
+
+    def finish(self):
+        self.L.ref_gl_finish()
 
     def texture(self, which):
         """the R16 texels stage 1 samples for audio_l (0) / audio_r (1)"""

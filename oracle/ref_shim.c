@@ -681,6 +681,7 @@ int ref_gl_unpack_shaders(const char* dir) {
     }
     return (int) count;
 }
+void ref_gl_finish(void) { glFinish(); }           /* llvmpipe rasterises on worker threads: the frame is complete after this */
 int ref_gl_get_error(void) { return (int) glGetError(); }
 int ref_gl_stage_count(void* rp) { return (int) ((struct glava_renderer*) rp)->gl->stages_sz; }
 void ref_gl_destroy(void* rp) { rd_destroy(rp); }
