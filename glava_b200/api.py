@@ -141,6 +141,24 @@ def lib():
     L.glava_b200_host_alloc_on.argtypes = [C.c_size_t, i32]
     L.glava_b200_device_numa_node.argtypes = [i32]
     L.glava_b200_bind_thread_to_device.argtypes = [i32]
+    L.glava_b200_shard_range.argtypes = [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
+    L.glava_b200_new_sharded.restype = vp
+    L.glava_b200_new_sharded.argtypes = [C.POINTER(Params), i32, C.c_uint64]
+    L.glava_b200_new_sharded_devices.restype = vp
+    L.glava_b200_new_sharded_devices.argtypes = [C.POINTER(Params), i32, C.POINTER(i32), i32]
+    L.glava_b200_sharded_destroy.argtypes = [vp]
+    L.glava_b200_sharded_shards.argtypes = [vp]
+    L.glava_b200_sharded_batch.argtypes = [vp]
+    L.glava_b200_sharded_shard.restype = vp
+    L.glava_b200_sharded_shard.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.glava_b200_sharded_update.argtypes = [vp, vp, vp, C.c_size_t, vp]
+    L.glava_b200_sharded_rerender.argtypes = [vp]
+    L.glava_b200_sharded_ingest_fifo.argtypes = [vp, vp, i32]
+    L.glava_b200_sharded_sync.argtypes = [vp]
+    L.glava_b200_sharded_readback.argtypes = [vp, i32, vp]
+    L.glava_b200_sharded_frame_device.restype = vp
+    L.glava_b200_sharded_frame_device.argtypes = [vp, i32, C.POINTER(i32)]
+    L.glava_b200_sharded_textures.argtypes = [vp, vp, vp]
     L.glava_b200_set_async_input.argtypes = [vp, i32]
     L.glava_b200_wait_input.argtypes = [vp]
     L.glava_b200_update.argtypes = [vp, vp, vp, C.c_size_t, i32]
@@ -480,6 +498,77 @@ class Renderer:
     def close(self):
         if getattr(self, "_h", None):
             self._L.glava_b200_destroy(self._h)
+            self._h = None
+
+    def __enter__(self): return self
+    def __exit__(self, *a): self.close()
+    def __del__(self):
+        try: self.close()
+        except Exception: pass
+
+
+class ShardedRenderer:
+    """One handle for a batch spread over several GPUs of a node (glava_b200_new_sharded): contiguous stream blocks, one
+    worker thread per device, no inter-device traffic.  devices: list of CUDA ordinals (may repeat), or None = all visible."""
+
+    def __init__(self, params, batch, devices=None):
+        self._L = lib()
+        if devices is None:
+            self._h = self._L.glava_b200_new_sharded(C.byref(params), int(batch), 0)
+        else:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            self._h = self._L.glava_b200_new_sharded_devices(C.byref(params), int(batch), arr, len(devices))
+        if not self._h:
+            raise GlavaError(self._L.glava_b200_last_error().decode(errors="replace"))
+        self.params = params.copy()
+        self.batch = int(batch)
+
+    @property
+    def shards(self):
+        """[(device, first_stream, count)]"""
+        out = []
+        for k in range(self._L.glava_b200_sharded_shards(self._h)):
+            d, f, c = C.c_int(), C.c_int(), C.c_int()
+            self._L.glava_b200_sharded_shard(self._h, k, C.byref(d), C.byref(f), C.byref(c))
+            out.append((d.value, f.value, c.value))
+        return out
+
+    def update(self, lb, rb, modified=None):
+        lb = np.ascontiguousarray(lb, dtype=np.float32); rb = np.ascontiguousarray(rb, dtype=np.float32)
+        assert lb.shape == (self.batch, self.params.n) and rb.shape == lb.shape
+        m = None
+        if modified is not None:
+            m = np.ascontiguousarray(np.asarray(modified) != 0, dtype=np.uint8)
+            assert m.shape == (self.batch,)
+        _check(self._L.glava_b200_sharded_update(self._h, lb.ctypes.data, rb.ctypes.data, self.params.n, m.ctypes.data if m is not None else None))
+
+    def rerender(self):
+        _check(self._L.glava_b200_sharded_rerender(self._h))
+
+    def ingest_fifo(self, chunks):
+        chunks = np.ascontiguousarray(chunks, dtype=np.int16)
+        assert chunks.ndim == 2 and chunks.shape[0] == self.batch and chunks.shape[1] % 2 == 0
+        _check(self._L.glava_b200_sharded_ingest_fifo(self._h, chunks.ctypes.data, chunks.shape[1] // 2))
+
+    def sync(self):
+        _check(self._L.glava_b200_sharded_sync(self._h))
+
+    def readback(self, stream, out=None):
+        p = self.params
+        if out is None:
+            out = np.empty((p.h, p.w, 4), dtype=np.uint8)
+        _check(self._L.glava_b200_sharded_readback(self._h, int(stream), out.ctypes.data))
+        return out
+
+    def textures(self):
+        n = self.params.n // max(self.params.bufscale, 1)
+        l = np.empty((self.batch, n), dtype=np.uint16); r = np.empty_like(l)
+        _check(self._L.glava_b200_sharded_textures(self._h, l.ctypes.data, r.ctypes.data))
+        return l, r
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.glava_b200_sharded_destroy(self._h)
             self._h = None
 
     def __enter__(self): return self

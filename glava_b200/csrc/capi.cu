@@ -92,6 +92,9 @@ struct glava_b200 {
     double* d_window; float* d_twiddle; void* d_rowtab; int* d_need; int need_count;
     TapEntry* d_tap_tab; int* d_tap_cnt; float* d_tap_wsum; int tap_max; int epi_n;
     K5Table k5; void* d_k5_blk; void* d_k5_ent; void* d_k5_wsum;   // full-plane K5 tap table (null: evaluate taps in the kernel)
+    // need-list K5 as its own kernel (one table per channel): the serial per-texel sums run at full occupancy on
+    // (texel, plane) pairs instead of on a sixth of the threads of one spectrum CTA
+    K5Table k5n[2]; void* d_k5n[2][4]; bool k5_split_lazy;
     unsigned char* d_csr; int csr_bytes, csr_idx_off, csr_off_off;   // the same taps, texel-major, for the shared-memory path
     void* d_geo; int geo_box[4];   // polar geometry cache (radial / circle), see raster_kernels.cu
     uint32_t* d_texmm;             // circle: per-plane {min, max} of the sampled texture, refreshed before each raster
@@ -188,6 +191,11 @@ static int device_numa_node(int device) {
 extern "C" {
 
 int glava_b200_device_numa_node(int device) { return device_numa_node(device); }
+int glava_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
 
 // Pin the calling thread to the CPUs of the device's NUMA node (what `numactl --cpunodebind` does for a one-rank-per-GPU
 // process).  Returns the node, or -1 when the topology is not exposed (nothing changed).
@@ -266,25 +274,38 @@ static void dev_free(glava_b200* r, void* ptr) {
     cudaFree(ptr);
 }
 
+// Upload a K5 tap table (tables.h) for k5_table_kernel; slots = {blk, ent, wsum, out} device pointers owned by the handle.
+static int upload_k5_table(glava_b200* r, const K5TableHost& t, K5Table* out, void** slots, bool with_out) {
+    static_assert(sizeof(K5Blk) == sizeof(int4) && sizeof(K5Ent) == sizeof(int2), "table records are read as int4 / int2");
+    int rc;
+    if ((rc = dev_alloc(r, &slots[0], t.blk.size() * sizeof(K5Blk), false)) != 0) return rc;
+    if ((rc = dev_alloc(r, &slots[1], (t.ent.empty() ? 1 : t.ent.size()) * sizeof(K5Ent), false)) != 0) return rc;
+    if ((rc = dev_alloc(r, &slots[2], t.wsum.size() * sizeof(float), false)) != 0) return rc;
+    CU(cudaMemcpyAsync(slots[0], t.blk.data(), t.blk.size() * sizeof(K5Blk), cudaMemcpyHostToDevice, r->stream));
+    if (!t.ent.empty()) CU(cudaMemcpyAsync(slots[1], t.ent.data(), t.ent.size() * sizeof(K5Ent), cudaMemcpyHostToDevice, r->stream));
+    CU(cudaMemcpyAsync(slots[2], t.wsum.data(), t.wsum.size() * sizeof(float), cudaMemcpyHostToDevice, r->stream));
+    if (with_out) {
+        if ((rc = dev_alloc(r, &slots[3], (t.out.empty() ? 1 : t.out.size()) * sizeof(int), false)) != 0) return rc;
+        if (!t.out.empty()) CU(cudaMemcpyAsync(slots[3], t.out.data(), t.out.size() * sizeof(int), cudaMemcpyHostToDevice, r->stream));
+    }
+    CU(cudaStreamSynchronize(r->stream));
+    out->blk = (const int4*) slots[0]; out->ent = (const int2*) slots[1]; out->wsum = (const float*) slots[2];
+    out->out = with_out ? (const int*) slots[3] : nullptr;
+    out->count = (int) t.out.size(); out->max_span = t.max_span;
+    out->smem_bytes = K5_S_PLANES * t.max_span * (int) sizeof(float);
+    return 0;
+}
+
 // Full-plane K5 (every texel wanted: lazy_smooth = 0, circle, the optional-stage path): the taps of ALL n output
 // texels (tables.h build_k5_table_host), uploaded for k5_table_kernel.
 static int build_k5_table(glava_b200* r) {
     K5TableHost t;
     build_k5_table_host(r->p, &t);
-    const size_t smem = (size_t) K5_S_PLANES * t.max_span * sizeof(float);
-    if (smem > 200 * 1024 || t.ent.size() * sizeof(K5Ent) > ((size_t) 256 << 20)) return 0;   // keep the in-kernel evaluation
-    static_assert(sizeof(K5Blk) == sizeof(int4) && sizeof(K5Ent) == sizeof(int2), "table records are read as int4 / int2");
-    int rc;
-    if ((rc = dev_alloc(r, &r->d_k5_blk, t.blk.size() * sizeof(K5Blk), false)) != 0) return rc;
-    if ((rc = dev_alloc(r, &r->d_k5_ent, (t.ent.empty() ? 1 : t.ent.size()) * sizeof(K5Ent), false)) != 0) return rc;
-    if ((rc = dev_alloc(r, &r->d_k5_wsum, t.wsum.size() * sizeof(float), false)) != 0) return rc;
-    CU(cudaMemcpyAsync(r->d_k5_blk, t.blk.data(), t.blk.size() * sizeof(K5Blk), cudaMemcpyHostToDevice, r->stream));
-    if (!t.ent.empty()) CU(cudaMemcpyAsync(r->d_k5_ent, t.ent.data(), t.ent.size() * sizeof(K5Ent), cudaMemcpyHostToDevice, r->stream));
-    CU(cudaMemcpyAsync(r->d_k5_wsum, t.wsum.data(), t.wsum.size() * sizeof(float), cudaMemcpyHostToDevice, r->stream));
-    CU(cudaStreamSynchronize(r->stream));
-    r->k5.blk = (const int4*) r->d_k5_blk; r->k5.ent = (const int2*) r->d_k5_ent; r->k5.wsum = (const float*) r->d_k5_wsum;
-    r->k5.smem_bytes = (int) smem;
-    return 0;
+    if ((size_t) 2 * t.max_span * sizeof(float) > 200 * 1024 || t.ent.size() * sizeof(K5Ent) > ((size_t) 256 << 20)) return 0;   // keep the in-kernel evaluation
+    void* slots[4] = { nullptr, nullptr, nullptr, nullptr };
+    int rc = upload_k5_table(r, t, &r->k5, slots, false);
+    r->d_k5_blk = slots[0]; r->d_k5_ent = slots[1]; r->d_k5_wsum = slots[2];
+    return rc;
 }
 
 // Everything derived from the parameters that does not depend on the audio: the lazy-K5 need-list and tap
@@ -297,6 +318,8 @@ static int build_tables(glava_b200* r) {
     dev_free(r, r->d_k5_blk); dev_free(r, r->d_k5_ent); dev_free(r, r->d_k5_wsum);
     r->d_k5_blk = r->d_k5_ent = r->d_k5_wsum = nullptr; memset(&r->k5, 0, sizeof(r->k5));
     dev_free(r, r->d_csr); r->d_csr = nullptr; r->csr_bytes = r->csr_idx_off = r->csr_off_off = 0;
+    for (int c = 0; c < 2; ++c) { for (int i = 0; i < 4; ++i) { dev_free(r, r->d_k5n[c][i]); r->d_k5n[c][i] = nullptr; } memset(&r->k5n[c], 0, sizeof(K5Table)); }
+    r->k5_split_lazy = false;
     r->d_need = nullptr; r->need_count = 0; r->d_tap_tab = nullptr; r->d_tap_cnt = nullptr; r->d_tap_wsum = nullptr;
     r->tap_max = 0; r->epi_n = 0; r->d_geo = nullptr; r->geo_box[0] = r->geo_box[1] = r->geo_box[2] = r->geo_box[3] = 0;
     if (p.transform_smooth) {
@@ -331,11 +354,30 @@ static int build_tables(glava_b200* r) {
                 // When one channel's blob is small enough for two CTAs per SM to hold it in shared memory next to the FFT
                 // buffers, the kernel's serial per-texel sums read their taps from there (no L2 round trips on the chain).
                 const int base = spectrum_smem_bytes(p.n);
-                if (base > 0 && base + t.blob <= (size_t) 112 * 1024 && !getenv("GLAVA_B200_NO_SMEM_TAPS")) {
+                const bool fits = base > 0 && base + t.blob <= (size_t) 112 * 1024 && !getenv("GLAVA_B200_NO_SMEM_TAPS");
+                if (fits) {
                     if ((rc = dev_alloc(r, (void**) &r->d_csr, t.csr.size(), false)) != 0) return rc;
                     CU(cudaMemcpyAsync(r->d_csr, t.csr.data(), t.csr.size(), cudaMemcpyHostToDevice, r->stream));
                     CU(cudaStreamSynchronize(r->stream));
                     r->csr_bytes = (int) t.blob; r->csr_idx_off = (int) t.idx_off; r->csr_off_off = (int) t.off_off;
+                }
+                // Need-list K5 as its own kernel.  Inside the spectrum kernel a texel's serial sum occupies one thread of a
+                // CTA whose other threads wait at the barrier (ncu at setbufsize 8192: 52 % of all warp samples sit at that
+                // barrier); as a kernel over (texel, plane) pairs the same sums run at full occupancy, eight planes sharing
+                // every tap load.  Default: whenever the taps do not fit shared memory next to the FFT (setbufsize >= 8192 at
+                // 1080p); GLAVA_B200_K5_SPLIT=1 / 0 forces it on / off.
+                const char* ks = getenv("GLAVA_B200_K5_SPLIT");
+                const bool want_split = ks ? atoi(ks) != 0 : !fits;
+                if (want_split) {
+                    bool ok = true;
+                    for (int c = 0; c < 2 && ok; ++c) {
+                        if (lists[c].empty()) continue;
+                        K5TableHost th;
+                        build_k5_table_for(p, lists[c], &th);
+                        if ((size_t) 2 * th.max_span * sizeof(float) > 200 * 1024) { ok = false; break; }
+                        if ((rc = upload_k5_table(r, th, &r->k5n[c], r->d_k5n[c], true)) != 0) return rc;
+                    }
+                    r->k5_split_lazy = ok;
                 }
             }
         }
@@ -484,6 +526,8 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     r->d_tap_tab = nullptr; r->d_tap_cnt = nullptr; r->d_tap_wsum = nullptr; r->tap_max = 0; r->epi_n = 0;
     r->d_csr = nullptr; r->csr_bytes = r->csr_idx_off = r->csr_off_off = 0;
     r->d_k5_blk = r->d_k5_ent = r->d_k5_wsum = nullptr; memset(&r->k5, 0, sizeof(r->k5));
+    for (int c = 0; c < 2; ++c) { for (int i = 0; i < 4; ++i) r->d_k5n[c][i] = nullptr; memset(&r->k5n[c], 0, sizeof(K5Table)); }
+    r->k5_split_lazy = false;
     r->d_geo = nullptr; r->geo_box[0] = r->geo_box[1] = r->geo_box[2] = r->geo_box[3] = 0;
     r->d_spec = r->d_applied = r->d_ring_f = nullptr; r->d_gr_store = r->d_ring_u = r->d_tex = nullptr; r->d_av = nullptr; r->d_texmm = nullptr; r->d_fb = nullptr;
     for (int i = 0; i < 2; ++i) { r->d_pcm[i][0] = r->d_pcm[i][1] = nullptr; r->ev_copied[i] = r->ev_free[i] = nullptr; }
@@ -664,9 +708,10 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
         a.pcm_l = d_l; a.pcm_r = d_r; a.window = r->d_window; a.twiddle = r->d_twiddle;
         a.spec = chain_out; a.skip_tex = r->post_chain ? 1 : 0; a.applied = r->d_applied; a.ring_f = r->d_ring_f;
         a.gr_store = r->d_gr_store; a.ring_u = r->d_ring_u; a.tex = tex_half(r, b);
-        a.need = (p.lazy_smooth && r->d_need) ? r->d_need : nullptr; a.need_count = r->need_count;
+        const bool split_lazy = r->k5_split_lazy && p.lazy_smooth && r->d_need && !r->post_chain && p.smooth_pass;
+        a.need = (p.lazy_smooth && r->d_need && !split_lazy) ? r->d_need : nullptr; a.need_count = r->need_count;
         a.tap_tab = a.need ? r->d_tap_tab : nullptr; a.tap_cnt = r->d_tap_cnt; a.tap_wsum = r->d_tap_wsum; a.tap_max = r->tap_max;
-        a.epi_n = a.need ? r->epi_n : 0;
+        a.epi_n = (a.need || split_lazy) ? r->epi_n : 0;
         a.tap_ku = r->tap_ku;
         a.csr = (a.need && a.tap_tab) ? r->d_csr : nullptr; a.csr_bytes = r->csr_bytes; a.csr_idx_off = r->csr_idx_off; a.csr_off_off = r->csr_off_off;
         a.batch = r->batch; a.update = r->updates;
@@ -684,9 +729,16 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
         if (r->timing && (rc = timing_mark(r->ev_spec, r->spec_stream)) != 0) return rc;
         // full-plane smoothing (every texel wanted): the spectrum kernel exports the pre-smoothing texture and
         // a second kernel smooths all planes, sharing the tap weights between planes
-        const bool split_k5 = p.smooth_pass && !a.need && !r->post_chain && !r->fused_k5;
-        a.av_out = split_k5 ? r->d_av : nullptr;
+        const bool split_k5 = p.smooth_pass && !a.need && !r->post_chain && !r->fused_k5 && !split_lazy;
+        a.av_out = (split_k5 || split_lazy) ? r->d_av : nullptr;
         if ((rc = launch_spectrum(p, a, is_fft, r->spec_stream)) != 0) return rc;
+        if (split_lazy) {
+            for (int c = 0; c < 2; ++c) {
+                if (!r->k5n[c].blk || r->k5n[c].count == 0) continue;
+                if ((rc = launch_smooth_only(p, r->d_av, a.tex, r->batch, r->spec_stream, &r->k5n[c], 2, c)) != 0) return rc;
+                ++r->launches;
+            }
+        }
         if (split_k5) {
             // wave uses plane 0 of each stream only; smoothing the (zero) odd planes too keeps the launch simple
             if ((rc = launch_smooth_only(p, r->d_av, a.tex, r->batch * 2, r->spec_stream, &r->k5)) != 0) return rc;

@@ -94,15 +94,20 @@ int launch_spectrum(const glava_b200_params& p, const SpectrumArgs& a, bool is_f
 struct K5Table {
     const int4*  blk;      // [n / K5_BLOCK] {first entry, taps per texel (padded), first input index, input span}
     const int2*  ent;      // entries {input index - first input index, weight bits}
-    const float* wsum;     // [n] sum of a texel's weights in loop order
-    int smem_bytes;        // dynamic shared memory the kernel needs: K5_S * max span * sizeof(float)
+    const float* wsum;     // [count] sum of an output's weights in loop order
+    int smem_bytes;        // dynamic shared memory the kernel needs: planes per CTA * max span * sizeof(float)
+    const int* out;        // [count] texel each output position writes (nullptr: position = texel, count = n)
+    int count;             // outputs (need-list tables: the texels the module samples; full table: n)
+    int max_span;
 };
 #ifndef K5_BLOCK
 #define K5_BLOCK 128
 #endif
 #define K5_S_PLANES 8        // planes that share one tap (K5_S in spectrum_kernels.cu)
+// planes handled: plane(i) = i * plane_stride + plane_offset for i in [0, count) — stride 2 / offset ch walks one channel's
+// planes of the interleaved [batch][2] layout (need-list tables differ per channel)
 int launch_smooth_only(const glava_b200_params& p, const uint16_t* d_in, uint16_t* d_out, int count, void* stream,
-                       const K5Table* table = nullptr);
+                       const K5Table* table = nullptr, int plane_stride = 1, int plane_offset = 0);
 int launch_raster(const glava_b200_params& p, const RasterArgs& a, void* stream);
 int launch_bars_rowtab(const glava_b200_params& p, void* d_rowtab, void* stream);
 // geometry cache of the polar modules: box = {x0, y0, w, h}; returns bytes needed when d_geo == nullptr

@@ -43,9 +43,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // ---------------------------------------------------------------------------------------------
 // spectrum kernel
-template <int LOG2N> struct SpecCfg {
+constexpr int spec_default_threads(int log2n) {
+    const int m8 = (1 << log2n) / 16;
+    return m8 < 128 ? 128 : (m8 > 512 ? 512 : m8);   // (1024 threads at N = 16384 was measured 2x slower)
+}
+template <int LOG2N, int TT = 0> struct SpecCfg {
     static constexpr int N = 1 << LOG2N, M = N / 2;
-    static constexpr int T = (M / 8 < 128) ? 128 : ((M / 8 > 512) ? 512 : M / 8);   // (1024 threads at N = 16384 was measured 2x slower)
+    static constexpr int T = TT > 0 ? TT : spec_default_threads(LOG2N);
     static constexpr int BUF_CPX = fft_padded_size(M);
     // cpx buffer (also the raw-PCM staging area, N floats = M cpx) | u16 av[N] | mbarrier
     static constexpr int OFF_AV  = ((BUF_CPX * 8 + 15) / 16) * 16;
@@ -53,7 +57,7 @@ template <int LOG2N> struct SpecCfg {
     static constexpr int SMEM    = OFF_BAR + 16;
     // resident CTAs per SM the register allocation must allow: the kernel waits on memory a lot (TMA load,
     // state loads), so occupancy is worth more than the last registers (128 regs -> 2 CTAs/SM was measured)
-    static constexpr int MIN_CTAS = T >= 512 ? 1 : 3;   // T = 512 (N >= 8192): capping at 64 registers spills in the FFT passes and was measured slower
+    static constexpr int MIN_CTAS = T >= 512 ? 1 : (T * (N / 16 / T > 1 ? 2 : 1) > 256 ? 2 : 3);   // T = 512: capping at 64 registers spills in the FFT passes and was measured slower
 };
 
 template <int M, int T, int NS, class Loader>
@@ -74,10 +78,10 @@ __device__ __forceinline__ void run_passes(cpx* buf, Loader first_loader, const 
 
 extern __shared__ __align__(16) unsigned char glb_smem[];
 
-template <int LOG2N, bool IS_FFT>
-__global__ void __launch_bounds__(SpecCfg<LOG2N>::T, SpecCfg<LOG2N>::MIN_CTAS)
+template <int LOG2N, bool IS_FFT, int TT = 0>
+__global__ void __launch_bounds__((SpecCfg<LOG2N, TT>::T), (SpecCfg<LOG2N, TT>::MIN_CTAS))
 spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ glava_b200_params p) {
-    using C = SpecCfg<LOG2N>;
+    using C = SpecCfg<LOG2N, TT>;
     constexpr int N = C::N, M = C::M, T = C::T;
     const int tid = threadIdx.x;
 
@@ -374,7 +378,8 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
             // all n texels wanted: export the pre-smoothing texture; k5_planes_kernel (below) smooths it,
             // sharing every tap weight between several planes instead of recomputing it per plane
             uint16_t* dst = a.av_out + plane;
-            for (int x = tid; x < N; x += T) dst[x] = av[x];
+            const int lim = (a.epi_n > 0 && a.epi_n < N) ? a.epi_n : N;     // need-list K5 downstream: only the bins its taps reach
+            for (int x = tid; x < lim; x += T) dst[x] = av[x];
         } else {
             for (int x = tid; x < N; x += T) tex[x] = (uint16_t) smooth_pass_texel(sp, av, N, x);
         }
@@ -403,10 +408,10 @@ int spectrum_smem_bytes(int n) {
     }
 }
 
-template <int LOG2N, bool IS_FFT>
+template <int LOG2N, bool IS_FFT, int TT = 0>
 static int launch_spectrum_t(const glava_b200_params& p, const SpectrumArgs& a, cudaStream_t st) {
-    using C = SpecCfg<LOG2N>;
-    auto kern = spectrum_kernel<LOG2N, IS_FFT>;
+    using C = SpecCfg<LOG2N, TT>;
+    auto kern = spectrum_kernel<LOG2N, IS_FFT, TT>;
     // Residency cap (tuning aid, off): the kernel co-runs with the raster kernel (capi.cu run_update) and
     // at full occupancy (5 CTAs x 256 threads x 48 registers per SM) takes most of the register file.
     // Requesting more dynamic shared memory than needed caps it at `cap` CTAs per SM.  Measured on B200
@@ -446,6 +451,14 @@ static int launch_spectrum_t(const glava_b200_params& p, const SpectrumArgs& a, 
 int launch_spectrum(const glava_b200_params& p, const SpectrumArgs& a, bool is_fft, void* stream) {
     cudaStream_t st = (cudaStream_t) stream;
 #define GLB_CASE(L) case (1 << L): return is_fft ? launch_spectrum_t<L, true>(p, a, st) : launch_spectrum_t<L, false>(p, a, st);
+    // the large sizes also exist with 256 threads per CTA (two butterflies per thread and pass, 2 CTAs per SM instead of one
+    // of 512): GLAVA_B200_SPEC_T=256 selects them
+    static int tsel = -1;
+    if (tsel < 0) { tsel = 0; if (const char* e = getenv("GLAVA_B200_SPEC_T")) tsel = atoi(e); }
+    if (tsel == 256 && is_fft) {
+        if (p.n == 8192)  return launch_spectrum_t<13, true, 256>(p, a, st);
+        if (p.n == 16384) return launch_spectrum_t<14, true, 256>(p, a, st);
+    }
     switch (p.n) {
         GLB_CASE(8) GLB_CASE(9) GLB_CASE(10) GLB_CASE(11) GLB_CASE(12) GLB_CASE(13) GLB_CASE(14)
         default: return fail(GLAVA_B200_EINVAL, "unsupported setbufsize %d", p.n);
@@ -502,58 +515,78 @@ k5_planes_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, in
 // The same pass from the precomputed table (K5Table): no log / divide / sine per tap, the staged input converted to
 // float once; per tap one coalesced 8-byte load, then per plane a shared-memory fetch, a multiply and the ordered add.
 static_assert(K5_S == K5_S_PLANES && K5_XT == K5_BLOCK, "K5 table layout and kernel tile must agree");
-template <bool AVG_ONLY>
+template <bool AVG_ONLY, int S>
 __global__ void __launch_bounds__(K5_BLOCK)
 k5_table_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int n, int count, const K5Table tb,
-                const SmoothParams sp) {
-    float* seg = reinterpret_cast<float*>(glb_smem);                  // [K5_S][span] texels as float
+                const SmoothParams sp, int plane_stride, int plane_offset) {
+    float* seg = reinterpret_cast<float*>(glb_smem);                  // [S][span] texels as float
     const int4 d = __ldg(tb.blk + blockIdx.x);
     const int base = d.x, taps = d.y, lo = d.z, span = d.w;
-    const int pl0 = blockIdx.y * K5_S, npl = min(K5_S, count - pl0);
-    for (int i = threadIdx.x; i < K5_S * span; i += K5_BLOCK) {
+    const int pl0 = blockIdx.y * S, npl = min(S, count - pl0);
+    for (int i = threadIdx.x; i < S * span; i += K5_BLOCK) {
         const int pl = i / span, k = i - pl * span;
-        seg[i] = pl < npl ? from16(in[(size_t) (pl0 + pl) * n + lo + k]) : 0.0f;
+        seg[i] = pl < npl ? from16(in[((size_t) (pl0 + pl) * plane_stride + plane_offset) * n + lo + k]) : 0.0f;
     }
     __syncthreads();
-    const int x = blockIdx.x * K5_BLOCK + threadIdx.x;
-    if (x >= n) return;
-    SmoothAcc acc[K5_S];
+    const int e = blockIdx.x * K5_BLOCK + threadIdx.x;               // output position
+    if (e >= tb.count) return;
+    const int x = tb.out ? __ldg(tb.out + e) : e;                     // texel it writes
+    SmoothAcc acc[S];
 #pragma unroll
-    for (int s = 0; s < K5_S; ++s) acc[s].init();
+    for (int s = 0; s < S; ++s) acc[s].init();
     const int2* col = tb.ent + base + threadIdx.x;
     for (int j = 0; j < taps; ++j) {
-        const int2 e = __ldg(col + (size_t) j * K5_BLOCK);
-        const float w = __int_as_float(e.y);
+        const int2 t = __ldg(col + (size_t) j * K5_BLOCK);
+        const float w = __int_as_float(t.y);
 #pragma unroll
-        for (int s = 0; s < K5_S; ++s) {
-            const float v = seg[s * span + e.x] * w;
+        for (int s = 0; s < S; ++s) {
+            const float v = seg[s * span + t.x] * w;
             acc[s].avg += v;
             if (!AVG_ONLY) { if (acc[s].vmax < v) acc[s].vmax = v; }
         }
     }
-    const float weight = __ldg(tb.wsum + x);
+    const float weight = __ldg(tb.wsum + e);
 #pragma unroll
-    for (int s = 0; s < K5_S; ++s) {
+    for (int s = 0; s < S; ++s) {
         acc[s].weight = weight;
-        if (s < npl) out[(size_t) (pl0 + s) * n + x] = (uint16_t) unorm16(acc[s].result(sp));
+        if (s < npl) out[((size_t) (pl0 + s) * plane_stride + plane_offset) * n + x] = (uint16_t) unorm16(acc[s].result(sp));
     }
 }
 
-int launch_smooth_only(const glava_b200_params& p, const uint16_t* d_in, uint16_t* d_out, int count, void* stream,
-                       const K5Table* table) {
-    if (table && table->blk) {
-        const SmoothParams sp = smooth_params(p);
-        auto kern = sp.sample_mode == 0 ? k5_table_kernel<true> : k5_table_kernel<false>;
-        if (table->smem_bytes > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, table->smem_bytes);
-            if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "cudaFuncSetAttribute(k5 table): %s", cudaGetErrorString(e));
-        }
-        dim3 grid((p.n + K5_BLOCK - 1) / K5_BLOCK, (count + K5_S - 1) / K5_S);
-        kern<<<grid, K5_BLOCK, table->smem_bytes, (cudaStream_t) stream>>>(d_in, d_out, p.n, count, *table, sp);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "smooth (table) kernel launch: %s", cudaGetErrorString(e));
-        return 0;
+template <bool AVG_ONLY, int S>
+static int launch_k5_table_t(const glava_b200_params& p, const uint16_t* d_in, uint16_t* d_out, int count, cudaStream_t st,
+                             const K5Table& tb, int plane_stride, int plane_offset) {
+    const SmoothParams sp = smooth_params(p);
+    auto kern = k5_table_kernel<AVG_ONLY, S>;
+    const int smem = S * tb.max_span * (int) sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "cudaFuncSetAttribute(k5 table): %s", cudaGetErrorString(e));
     }
+    dim3 grid((tb.count + K5_BLOCK - 1) / K5_BLOCK, (count + S - 1) / S);
+    kern<<<grid, K5_BLOCK, smem, st>>>(d_in, d_out, p.n, count, tb, sp, plane_stride, plane_offset);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "smooth (table) kernel launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int launch_smooth_only(const glava_b200_params& p, const uint16_t* d_in, uint16_t* d_out, int count, void* stream,
+                       const K5Table* table, int plane_stride, int plane_offset) {
+    if (table && table->blk) {
+        // planes per CTA share every tap's index / weight load: as many as the staged spans leave room for
+        const bool avg = smooth_params(p).sample_mode == 0;
+        cudaStream_t st = (cudaStream_t) stream;
+        const size_t per_plane = (size_t) table->max_span * sizeof(float);
+        if (8 * per_plane <= 200 * 1024)
+            return avg ? launch_k5_table_t<true, 8>(p, d_in, d_out, count, st, *table, plane_stride, plane_offset)
+                       : launch_k5_table_t<false, 8>(p, d_in, d_out, count, st, *table, plane_stride, plane_offset);
+        if (4 * per_plane <= 200 * 1024)
+            return avg ? launch_k5_table_t<true, 4>(p, d_in, d_out, count, st, *table, plane_stride, plane_offset)
+                       : launch_k5_table_t<false, 4>(p, d_in, d_out, count, st, *table, plane_stride, plane_offset);
+        return avg ? launch_k5_table_t<true, 2>(p, d_in, d_out, count, st, *table, plane_stride, plane_offset)
+                   : launch_k5_table_t<false, 2>(p, d_in, d_out, count, st, *table, plane_stride, plane_offset);
+    }
+    if (plane_stride != 1 || plane_offset != 0) return fail(GLAVA_B200_EINVAL, "smooth pass: strided planes need a tap table");
     // worst-case span: the last block's taps, bounded by the whole plane
     const SmoothParams sp = smooth_params(p);
     const float fn = (float) p.n;

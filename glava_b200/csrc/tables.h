@@ -151,24 +151,29 @@ struct alignas(8)  K5Ent { int idx; int wbits; };          // input index - lo, 
 struct K5TableHost {
     std::vector<K5Blk> blk;        // [ceil(n / K5_BLOCK)]
     std::vector<K5Ent> ent;        // per block [taps][K5_BLOCK], padded with {0, +0.0f}
-    std::vector<float> wsum;       // [n]
+    std::vector<float> wsum;       // [outputs]
+    std::vector<int> out;          // [outputs] texel each output position writes
     int max_span = 1;
 };
 
-inline void build_k5_table_host(const glava_b200_params& p, K5TableHost* t) {
+// Taps of the output texels `outs` (any subset of [0, n), in this order), in blocks of K5_BLOCK outputs.
+// wsum / the kernel's thread index run over POSITIONS in `outs`; out[] maps a position back to its texel.
+inline void build_k5_table_for(const glava_b200_params& p, const std::vector<int>& outs, K5TableHost* t) {
     const SmoothParams sp = smooth_params(p);
-    const int n = p.n, nblk = (n + K5_BLOCK - 1) / K5_BLOCK;
-    t->blk.assign((size_t) nblk, K5Blk { 0, 0, 0, 1 });
+    const int n = p.n, cnt = (int) outs.size(), nblk = (cnt + K5_BLOCK - 1) / K5_BLOCK;
+    t->blk.assign((size_t) (nblk > 0 ? nblk : 1), K5Blk { 0, 0, 0, 1 });
     t->ent.clear();
-    t->wsum.assign((size_t) n, 0.0f);
+    t->wsum.assign((size_t) (cnt > 0 ? cnt : 1), 0.0f);
+    t->out = outs;
     t->max_span = 1;
     std::vector<std::vector<TapEntry>> taps(K5_BLOCK);
     for (int b = 0; b < nblk; ++b) {
         int lo = n, hi = -1; size_t longest = 0;
         for (int k = 0; k < K5_BLOCK; ++k) {
             taps[k].clear();
-            const int x = b * K5_BLOCK + k;
-            if (x >= n) continue;
+            const int e = b * K5_BLOCK + k;
+            if (e >= cnt) continue;
+            const int x = outs[e];
             float weight = 0.0f;
             smooth_enumerate(sp, n, ((float) x + 0.5f) / (float) n, [&](int i, float w) {
                 weight += w;
@@ -177,7 +182,7 @@ inline void build_k5_table_host(const glava_b200_params& p, K5TableHost* t) {
                 taps[k].push_back(TapEntry { inside ? i : -1, inside ? w : 0.0f });
                 if (inside) { if (i < lo) lo = i; if (i > hi) hi = i; }
             });
-            t->wsum[x] = weight;
+            t->wsum[e] = weight;
             if (taps[k].size() > longest) longest = taps[k].size();
         }
         if (hi < lo) { lo = 0; hi = 0; }
@@ -193,6 +198,11 @@ inline void build_k5_table_host(const glava_b200_params& p, K5TableHost* t) {
                 t->ent[base + j * K5_BLOCK + k] = K5Ent { te.idx >= 0 ? te.idx - lo : 0, wbits };
             }
     }
+}
+inline void build_k5_table_host(const glava_b200_params& p, K5TableHost* t) {   // every texel of the plane
+    std::vector<int> all((size_t) p.n);
+    for (int i = 0; i < p.n; ++i) all[i] = i;
+    build_k5_table_for(p, all, t);
 }
 
 }  // namespace glb

@@ -306,6 +306,31 @@ void* glava_b200_frame_event(const glava_b200* r);
 const void* glava_b200_frame_device(const glava_b200* r, int stream);
 int   glava_b200_framebuffer_ipc(glava_b200* r, void* handle, size_t handle_bytes);
 
+/* ---- one handle for a batch spread over several GPUs of a node (csrc/sharded.cpp) -------------------------------------
+ * The streams of a batch are independent (one GLava process each, in the reference), so the batch is cut into contiguous
+ * blocks, one per device — glava_b200_shard_range: counts differ by at most one — and nothing crosses between devices (no
+ * collective, NCCL unused).  One worker thread per device, pinned to the device's NUMA node; every call below is issued
+ * on all shards concurrently.  lb / rb / chunks / modified / textures are indexed by GLOBAL stream, [batch][...].
+ *   device_mask: bit d = CUDA device d takes a shard (0 = every visible device).  _devices: explicit ordinals (an
+ *   ordinal may repeat: several shards on one device).  Error behaviour as everywhere: 0 / negative code + abort hook;
+ *   the message names the failing device and its stream block. */
+typedef struct glava_b200_sharded glava_b200_sharded;
+int  glava_b200_device_count(void);
+int  glava_b200_shard_range(int batch, int shards, int k, int* first_stream, int* count);
+glava_b200_sharded* glava_b200_new_sharded(const glava_b200_params* params, int batch, uint64_t device_mask);
+glava_b200_sharded* glava_b200_new_sharded_devices(const glava_b200_params* params, int batch, const int* devices, int n);
+void glava_b200_sharded_destroy(glava_b200_sharded* s);
+int  glava_b200_sharded_shards(const glava_b200_sharded* s);
+int  glava_b200_sharded_batch(const glava_b200_sharded* s);
+glava_b200* glava_b200_sharded_shard(const glava_b200_sharded* s, int k, int* device, int* first_stream, int* count);
+int  glava_b200_sharded_update(glava_b200_sharded* s, const float* lb, const float* rb, size_t bsz, const uint8_t* modified /* NULL: all */);
+int  glava_b200_sharded_rerender(glava_b200_sharded* s);                                  /* rd_update(modified = false) */
+int  glava_b200_sharded_ingest_fifo(glava_b200_sharded* s, const int16_t* chunks, int frames);   /* ingest + update on the rings */
+int  glava_b200_sharded_sync(glava_b200_sharded* s);
+int  glava_b200_sharded_readback(glava_b200_sharded* s, int stream, uint8_t* rgba);
+const void* glava_b200_sharded_frame_device(glava_b200_sharded* s, int stream, int* device);
+int  glava_b200_sharded_textures(glava_b200_sharded* s, uint16_t* out_l, uint16_t* out_r);
+
 /* Stage-wise entry points (used by the parity tests; same kernels as the fused path). */
 int glava_b200_smooth_pass(glava_b200* r, const uint16_t* in, uint16_t* out, int count);      /* K5 on HOST [count][n] */
 int glava_b200_raster_textures(glava_b200* r, const uint16_t* tex_l, const uint16_t* tex_r);  /* HOST [batch][n] -> raster */

@@ -35,13 +35,15 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--module", default="bars")
+    ap.add_argument("--sizes", default="512,1024,2048,4096,8192,16384")
+    ap.add_argument("--quick", action="store_true", help="lazy pipeline-B only")
     a = ap.parse_args()
     if a.one:
         print(f"n={a.one}: {run(a.module, a.one, a.width, a.batch, 1, 1, reps=4):.1f} us")
         return
     rows = []
-    for n in (512, 1024, 2048, 4096, 8192, 16384):
-        for lazy, accel, smooth in ((1, 1, 1), (1, 1, 0), (0, 1, 1), (1, 0, 1)):
+    for n in [int(v) for v in a.sizes.split(",")]:
+        for lazy, accel, smooth in (((1, 1, 1),) if a.quick else ((1, 1, 1), (1, 1, 0), (0, 1, 1), (1, 0, 1))):
             us = run(a.module, n, a.width, a.batch, lazy, accel, smooth)
             pcm_mb = a.batch * 2 * n * 4 / 1e6
             rows.append(dict(n=n, lazy=lazy, accel=accel, smooth=smooth, us=us, pcm_gbs=pcm_mb / us * 1e3))
