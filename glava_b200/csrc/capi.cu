@@ -94,7 +94,7 @@ struct glava_b200 {
     K5Table k5; void* d_k5_blk; void* d_k5_ent; void* d_k5_wsum;   // full-plane K5 tap table (null: evaluate taps in the kernel)
     // need-list K5 as its own kernel (one table per channel): the serial per-texel sums run at full occupancy on
     // (texel, plane) pairs instead of on a sixth of the threads of one spectrum CTA
-    K5Table k5n[2]; void* d_k5n[2][4]; bool k5_split_lazy;
+    bool k5_split_lazy, csr_in_smem; int av_t_len;
     unsigned char* d_csr; int csr_bytes, csr_idx_off, csr_off_off;   // the same taps, texel-major, for the shared-memory path
     void* d_geo; int geo_box[4];   // polar geometry cache (radial / circle), see raster_kernels.cu
     uint32_t* d_texmm;             // circle: per-plane {min, max} of the sampled texture, refreshed before each raster
@@ -318,8 +318,7 @@ static int build_tables(glava_b200* r) {
     dev_free(r, r->d_k5_blk); dev_free(r, r->d_k5_ent); dev_free(r, r->d_k5_wsum);
     r->d_k5_blk = r->d_k5_ent = r->d_k5_wsum = nullptr; memset(&r->k5, 0, sizeof(r->k5));
     dev_free(r, r->d_csr); r->d_csr = nullptr; r->csr_bytes = r->csr_idx_off = r->csr_off_off = 0;
-    for (int c = 0; c < 2; ++c) { for (int i = 0; i < 4; ++i) { dev_free(r, r->d_k5n[c][i]); r->d_k5n[c][i] = nullptr; } memset(&r->k5n[c], 0, sizeof(K5Table)); }
-    r->k5_split_lazy = false;
+    r->k5_split_lazy = false; r->csr_in_smem = false; r->av_t_len = 0;
     r->d_need = nullptr; r->need_count = 0; r->d_tap_tab = nullptr; r->d_tap_cnt = nullptr; r->d_tap_wsum = nullptr;
     r->tap_max = 0; r->epi_n = 0; r->d_geo = nullptr; r->geo_box[0] = r->geo_box[1] = r->geo_box[2] = r->geo_box[3] = 0;
     if (p.transform_smooth) {
@@ -355,30 +354,16 @@ static int build_tables(glava_b200* r) {
                 // buffers, the kernel's serial per-texel sums read their taps from there (no L2 round trips on the chain).
                 const int base = spectrum_smem_bytes(p.n);
                 const bool fits = base > 0 && base + t.blob <= (size_t) 112 * 1024 && !getenv("GLAVA_B200_NO_SMEM_TAPS");
-                if (fits) {
-                    if ((rc = dev_alloc(r, (void**) &r->d_csr, t.csr.size(), false)) != 0) return rc;
-                    CU(cudaMemcpyAsync(r->d_csr, t.csr.data(), t.csr.size(), cudaMemcpyHostToDevice, r->stream));
-                    CU(cudaStreamSynchronize(r->stream));
-                    r->csr_bytes = (int) t.blob; r->csr_idx_off = (int) t.idx_off; r->csr_off_off = (int) t.off_off;
-                }
-                // Need-list K5 as its own kernel.  Inside the spectrum kernel a texel's serial sum occupies one thread of a
-                // CTA whose other threads wait at the barrier (ncu at setbufsize 8192: 52 % of all warp samples sit at that
-                // barrier); as a kernel over (texel, plane) pairs the same sums run at full occupancy, eight planes sharing
-                // every tap load.  Default: whenever the taps do not fit shared memory next to the FFT (setbufsize >= 8192 at
-                // 1080p); GLAVA_B200_K5_SPLIT=1 / 0 forces it on / off.
+                if ((rc = dev_alloc(r, (void**) &r->d_csr, t.csr.size(), false)) != 0) return rc;
+                CU(cudaMemcpyAsync(r->d_csr, t.csr.data(), t.csr.size(), cudaMemcpyHostToDevice, r->stream));
+                CU(cudaStreamSynchronize(r->stream));
+                r->csr_bytes = (int) t.blob; r->csr_idx_off = (int) t.idx_off; r->csr_off_off = (int) t.off_off;
+                r->csr_in_smem = fits;
+                // Need-list K5 as its own kernel (k5_need_kernel, lanes = streams): default whenever the taps do not fit shared
+                // memory next to the FFT (setbufsize >= 8192 at 1080p); GLAVA_B200_K5_SPLIT=1 / 0 forces it on / off.
                 const char* ks = getenv("GLAVA_B200_K5_SPLIT");
-                const bool want_split = ks ? atoi(ks) != 0 : !fits;
-                if (want_split) {
-                    bool ok = true;
-                    for (int c = 0; c < 2 && ok; ++c) {
-                        if (lists[c].empty()) continue;
-                        K5TableHost th;
-                        build_k5_table_for(p, lists[c], &th);
-                        if ((size_t) 2 * th.max_span * sizeof(float) > 200 * 1024) { ok = false; break; }
-                        if ((rc = upload_k5_table(r, th, &r->k5n[c], r->d_k5n[c], true)) != 0) return rc;
-                    }
-                    r->k5_split_lazy = ok;
-                }
+                r->k5_split_lazy = ks ? atoi(ks) != 0 : !fits;
+                r->av_t_len = t.epi_n > 0 ? t.epi_n : p.n;
             }
         }
     }
@@ -526,8 +511,7 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     r->d_tap_tab = nullptr; r->d_tap_cnt = nullptr; r->d_tap_wsum = nullptr; r->tap_max = 0; r->epi_n = 0;
     r->d_csr = nullptr; r->csr_bytes = r->csr_idx_off = r->csr_off_off = 0;
     r->d_k5_blk = r->d_k5_ent = r->d_k5_wsum = nullptr; memset(&r->k5, 0, sizeof(r->k5));
-    for (int c = 0; c < 2; ++c) { for (int i = 0; i < 4; ++i) r->d_k5n[c][i] = nullptr; memset(&r->k5n[c], 0, sizeof(K5Table)); }
-    r->k5_split_lazy = false;
+    r->k5_split_lazy = false; r->csr_in_smem = false; r->av_t_len = 0;
     r->d_geo = nullptr; r->geo_box[0] = r->geo_box[1] = r->geo_box[2] = r->geo_box[3] = 0;
     r->d_spec = r->d_applied = r->d_ring_f = nullptr; r->d_gr_store = r->d_ring_u = r->d_tex = nullptr; r->d_av = nullptr; r->d_texmm = nullptr; r->d_fb = nullptr;
     for (int i = 0; i < 2; ++i) { r->d_pcm[i][0] = r->d_pcm[i][1] = nullptr; r->ev_copied[i] = r->ev_free[i] = nullptr; }
@@ -713,7 +697,7 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
         a.tap_tab = a.need ? r->d_tap_tab : nullptr; a.tap_cnt = r->d_tap_cnt; a.tap_wsum = r->d_tap_wsum; a.tap_max = r->tap_max;
         a.epi_n = (a.need || split_lazy) ? r->epi_n : 0;
         a.tap_ku = r->tap_ku;
-        a.csr = (a.need && a.tap_tab) ? r->d_csr : nullptr; a.csr_bytes = r->csr_bytes; a.csr_idx_off = r->csr_idx_off; a.csr_off_off = r->csr_off_off;
+        a.csr = (a.need && a.tap_tab && r->csr_in_smem) ? r->d_csr : nullptr; a.csr_bytes = r->csr_bytes; a.csr_idx_off = r->csr_idx_off; a.csr_off_off = r->csr_off_off;
         a.batch = r->batch; a.update = r->updates;
         a.umask = nullptr; a.tex_prev = tex_half(r, r->tex_cur);
         if (mask || r->desync) { if ((rc = stage_umask(r, mask, &a.umask)) != 0) return rc; }
@@ -730,14 +714,13 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
         // full-plane smoothing (every texel wanted): the spectrum kernel exports the pre-smoothing texture and
         // a second kernel smooths all planes, sharing the tap weights between planes
         const bool split_k5 = p.smooth_pass && !a.need && !r->post_chain && !r->fused_k5 && !split_lazy;
-        a.av_out = (split_k5 || split_lazy) ? r->d_av : nullptr;
+        a.av_out = split_k5 ? r->d_av : nullptr;
+        a.av_t = split_lazy ? r->d_av : nullptr; a.av_t_len = r->av_t_len;     // (d_av is free in lazy mode: same bytes, transposed use)
         if ((rc = launch_spectrum(p, a, is_fft, r->spec_stream)) != 0) return rc;
         if (split_lazy) {
-            for (int c = 0; c < 2; ++c) {
-                if (!r->k5n[c].blk || r->k5n[c].count == 0) continue;
-                if ((rc = launch_smooth_only(p, r->d_av, a.tex, r->batch, r->spec_stream, &r->k5n[c], 2, c)) != 0) return rc;
-                ++r->launches;
-            }
+            if ((rc = launch_k5_need(p, r->d_av, r->av_t_len, a.tex, r->batch, is_fft ? 2 : 1, r->d_csr, r->csr_bytes, r->csr_idx_off,
+                                     r->csr_off_off, r->d_need, r->d_tap_wsum, r->need_count, r->spec_stream)) != 0) return rc;
+            ++r->launches;
         }
         if (split_k5) {
             // wave uses plane 0 of each stream only; smoothing the (zero) odd planes too keeps the launch simple

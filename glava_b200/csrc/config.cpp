@@ -208,6 +208,23 @@ static bool eval_num(const Defs& d, const char* name, Num* out) {
 }
 static void getf(const Defs& d, const char* name, float* dst) { Num n; if (eval_num(d, name, &n)) *dst = (float) n.v; }
 static void geti(const Defs& d, const char* name, int* dst) { Num n; if (eval_num(d, name, &n)) *dst = (int) n.v; }
+// A macro the module's shader tests in a preprocessor conditional (`where` = the shader line).  GLSL's preprocessor
+// evaluates integer constant expressions only: with a float spelling ("#define BAR_OUTLINE_WIDTH 0.5") the reference's
+// shader does not compile — Mesa: `preprocessor error: syntax error, unexpected OTHER` — and GLava aborts in shaderload
+// (render.c:352-377).  Same outcome here: a configuration error naming the macro.  (Seen when the llvmpipe harness first
+// compiled the fuzzer's configurations; the in-house interpreter had accepted them.)
+static bool getpp(const Defs& d, const char* name, const char* where, Num* out) {
+    if (!eval_num(d, name, out)) return false;
+    if (!out->is_int) {
+        fail(GLAVA_B200_ECONFIG, "'#define %s %s': %s tests this macro in a preprocessor #if, which takes integer constant "
+                                 "expressions only — the reference's shader fails to compile with a float here", name,
+             d.find(name)->second.c_str(), where);
+        return false;
+    }
+    return true;
+}
+static void getppi(const Defs& d, const char* name, const char* where, int* dst) { Num n; if (getpp(d, name, where, &n)) *dst = (int) n.v; }
+static void getppf(const Defs& d, const char* name, const char* where, float* dst) { Num n; if (getpp(d, name, where, &n)) *dst = (float) n.v; }
 
 // strip `@name:` pipe-bind prefix -> its default (glsl_ext.c:571-587 when no --pipe bind exists)
 // `--pipe` binds (glava.c:421-436, glsl_ext.c:516-591): "name" -> value the bound uniform currently holds.
@@ -642,7 +659,7 @@ static void apply_defines(glava_b200_params* p, const Defs& d) {
     switch (p->module) {
         case GLAVA_B200_MOD_BARS:
             getf(d, "BAR_WIDTH", &p->bars_width); getf(d, "BAR_GAP", &p->bars_gap);
-            getf(d, "BAR_OUTLINE_WIDTH", &p->bars_outline_width); getf(d, "AMPLIFY", &p->bars_amplify);
+            getppf(d, "BAR_OUTLINE_WIDTH", "bars/1.frag:116,127", &p->bars_outline_width); getf(d, "AMPLIFY", &p->bars_amplify);
             parse_color_macro(d, "COLOR", &p->bars_color, &p->bars_color_prog, { "d" });
             if (p->bars_color.mode == 0 && eval_num(d, "GRADIENT", &n)) p->bars_color.gradient = (float) n.v;
             if ((it = d.find("BAR_OUTLINE")) != d.end()) {
@@ -663,9 +680,12 @@ static void apply_defines(glava_b200_params* p, const Defs& d) {
                     }
                 }
             }
-            geti(d, "DIRECTION", &p->bars_direction); geti(d, "INVERT", &p->bars_invert);
-            geti(d, "FLIP", &p->bars_flip); geti(d, "MIRROR_YX", &p->bars_mirror_yx);
-            { int dm = 0; geti(d, "DISABLE_MONO", &dm); if (dm == 1) p->channels = 2; }          // bars/1.frag:36-38
+            getppi(d, "DIRECTION", "bars/1.frag:89,101", &p->bars_direction); getppi(d, "INVERT", "bars/1.frag:53,94,106", &p->bars_invert);
+            getppi(d, "FLIP", "bars/1.frag:59", &p->bars_flip); getppi(d, "MIRROR_YX", "bars/1.frag:38", &p->bars_mirror_yx);
+            { int dm = 0; getppi(d, "DISABLE_MONO", "bars/1.frag:32", &dm); if (dm == 1) p->channels = 2; }          // bars/1.frag:32-34
+            // USE_ALPHA (bars.glsl:16) changes nothing in the reference: bars/2.frag tests `#if USE_ALPHA == 0` WITHOUT including
+            // bars.glsl, the undefined macro evaluates as 0 and the premultiply stage is always disabled (pinned by the llvmpipe
+            // golden `bars_use_alpha`: a translucent COLOR with USE_ALPHA 1 renders un-premultiplied).  Read and ignored.
             break;
         case GLAVA_B200_MOD_RADIAL:
             getf(d, "C_RADIUS", &p->radial_radius);
@@ -679,10 +699,10 @@ static void apply_defines(glava_b200_params* p, const Defs& d) {
             getf(d, "AMPLIFY", &p->radial_amplify);
             parse_color_macro(d, "COLOR", &p->radial_color, &p->radial_color_prog, { "d" });
             if (p->radial_color.mode == 0 && eval_num(d, "GRADIENT", &n)) p->radial_color.gradient = (float) n.v;
-            getf(d, "ROTATE", &p->radial_rotate); geti(d, "INVERT", &p->radial_invert);
+            getf(d, "ROTATE", &p->radial_rotate); getppi(d, "INVERT", "radial/1.frag:67", &p->radial_invert);
             getf(d, "BAR_ALIAS_FACTOR", &p->radial_bar_alias); getf(d, "C_ALIAS_FACTOR", &p->radial_c_alias);
             getf(d, "CENTER_OFFSET_X", &p->radial_off_x); getf(d, "CENTER_OFFSET_Y", &p->radial_off_y);
-            getf(d, "BAR_OUTLINE_WIDTH", &p->radial_bar_outline_width);                 // deprecated (radial.glsl:33-36)
+            getppf(d, "BAR_OUTLINE_WIDTH", "radial/1.frag:87,101", &p->radial_bar_outline_width);   // deprecated (radial.glsl:33-36)
             memcpy(p->radial_bar_outline, p->radial_outline, sizeof(p->radial_bar_outline));   // `#define BAR_OUTLINE OUTLINE`
             parse_plain_color(d, "BAR_OUTLINE", p->radial_bar_outline);
             break;
@@ -690,15 +710,15 @@ static void apply_defines(glava_b200_params* p, const Defs& d) {
             getf(d, "C_RADIUS", &p->circle_radius); getf(d, "C_LINE", &p->circle_line);
             parse_plain_color(d, "OUTLINE", p->circle_outline);
             getf(d, "AMPLIFY", &p->circle_amplify); getf(d, "ROTATE", &p->circle_rotate);
-            geti(d, "INVERT", &p->circle_invert); geti(d, "C_FILL", &p->circle_fill); geti(d, "C_SMOOTH", &p->circle_smooth);
+            geti(d, "INVERT", &p->circle_invert); getppi(d, "C_FILL", "circle/1.frag:75", &p->circle_fill); getppi(d, "C_SMOOTH", "circle/2.frag:14", &p->circle_smooth);
             break;
         case GLAVA_B200_MOD_GRAPH:
-            getf(d, "VSCALE", &p->graph_vscale); geti(d, "DIRECTION", &p->graph_direction);
+            getf(d, "VSCALE", &p->graph_vscale); getppi(d, "DIRECTION", "graph/1.frag:67", &p->graph_direction);
             parse_color_macro(d, "COLOR", &p->graph_color, &p->graph_color_prog, { "pos", "d" });
             if (p->graph_color.mode == 0 && eval_num(d, "GRADIENT", &n)) p->graph_color.gradient = (float) n.v;
-            geti(d, "DRAW_OUTLINE", &p->graph_draw_outline); geti(d, "DRAW_HIGHLIGHT", &p->graph_draw_highlight);
-            parse_plain_color(d, "OUTLINE", p->graph_outline); geti(d, "INVERT", &p->graph_invert);
-            geti(d, "ANTI_ALIAS", &p->graph_anti_alias);
+            getppi(d, "DRAW_OUTLINE", "graph/2.frag:12,34", &p->graph_draw_outline); getppi(d, "DRAW_HIGHLIGHT", "graph/2.frag:12,39", &p->graph_draw_highlight);
+            parse_plain_color(d, "OUTLINE", p->graph_outline); getppi(d, "INVERT", "graph/1.frag:110", &p->graph_invert);
+            getppi(d, "ANTI_ALIAS", "graph/3.frag:15", &p->graph_anti_alias);
             geti(d, "JOIN_CHANNELS", &p->graph_join_channels);
             break;
         case GLAVA_B200_MOD_WAVE:

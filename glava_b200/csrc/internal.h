@@ -67,6 +67,10 @@ struct SpectrumArgs {
     // shares the cursor `update % F`; else one word per stream, bit 31 = this stream has new audio, low 16 bits = its own
     // ring cursor (modified updates of THAT stream so far, mod F).  An unmodified stream's state is left alone and its
     // texture is carried from `tex_prev` (the half of the double buffer the previous raster read) into `tex`.
+    // need-list K5 as its own kernel (k5_need_kernel): the pre-smoothing texels are exported TRANSPOSED, stream-minor,
+    // av_t[(ch * av_t_len + bin) * batch + stream] for bin < av_t_len, so that a warp whose lanes are 32 streams reads one
+    // coalesced run per tap; nullptr = not exported
+    uint16_t* av_t; int av_t_len;
     const uint32_t* umask;      // [batch]
     const uint16_t* tex_prev;   // [batch*2][n]
     double    avg_w_a[GLB_MAX_AVG_FRAMES];   // pipeline A weights, oldest first (render.c:661,766)
@@ -108,6 +112,11 @@ struct K5Table {
 // planes of the interleaved [batch][2] layout (need-list tables differ per channel)
 int launch_smooth_only(const glava_b200_params& p, const uint16_t* d_in, uint16_t* d_out, int count, void* stream,
                        const K5Table* table = nullptr, int plane_stride = 1, int plane_offset = 0);
+// need-list K5, lanes = streams: csr = the texel-major tap blobs of SpectrumArgs (per channel float w[] | u16 idx[] | int off[]),
+// need / wsum = [2][need_count]; av_t as exported by the spectrum kernel; writes tex[(stream * 2 + ch) * n + need[k]]
+int launch_k5_need(const glava_b200_params& p, const uint16_t* d_av_t, int av_t_len, uint16_t* d_tex, int batch, int channels,
+                   const unsigned char* d_csr, int csr_bytes, int csr_idx_off, int csr_off_off, const int* d_need,
+                   const float* d_wsum, int need_count, void* stream);
 int launch_raster(const glava_b200_params& p, const RasterArgs& a, void* stream);
 int launch_bars_rowtab(const glava_b200_params& p, void* d_rowtab, void* stream);
 // geometry cache of the polar modules: box = {x0, y0, w, h}; returns bytes needed when d_geo == nullptr

@@ -374,12 +374,15 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
                 int x = need[k];
                 if (x >= 0 && x < N) tex[x] = (uint16_t) smooth_pass_texel(sp, av, N, x);
             }
+        } else if (a.av_t) {
+            // need-list K5 downstream (k5_need_kernel): the bins its taps can reach, stream-minor
+            uint16_t* dst = a.av_t + (size_t) ch * a.av_t_len * a.batch + (c >> 1);
+            for (int x = tid; x < a.av_t_len; x += T) dst[(size_t) x * a.batch] = av[x];
         } else if (a.av_out) {
             // all n texels wanted: export the pre-smoothing texture; k5_planes_kernel (below) smooths it,
             // sharing every tap weight between several planes instead of recomputing it per plane
             uint16_t* dst = a.av_out + plane;
-            const int lim = (a.epi_n > 0 && a.epi_n < N) ? a.epi_n : N;     // need-list K5 downstream: only the bins its taps reach
-            for (int x = tid; x < lim; x += T) dst[x] = av[x];
+            for (int x = tid; x < N; x += T) dst[x] = av[x];
         } else {
             for (int x = tid; x < N; x += T) tex[x] = (uint16_t) smooth_pass_texel(sp, av, N, x);
         }
@@ -609,6 +612,80 @@ int launch_smooth_only(const glava_b200_params& p, const uint16_t* d_in, uint16_
     k5_planes_kernel<<<grid, K5_XT, smem, (cudaStream_t) stream>>>(d_in, d_out, p.n, count, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "smooth kernel launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Need-list K5, lanes = streams.  Inside the spectrum kernel a texel's serial sum occupies one thread of a CTA whose other
+// threads wait (ncu at setbufsize 8192: half of all warp samples sit at that barrier).  Here one WARP owns one sampled
+// texel of one channel for 32 streams: the tap list is the same for all of them, so a lane loads one {index, weight} of
+// the next 32 taps (two coalesced loads) and the warp walks them by shuffle broadcast; every tap is one coalesced 64-byte
+// read of the transposed pre-smoothing texels and the ordered multiply-add of smooth_audio() (smooth.glsl:33-37), per lane.
+// 2 x need_count x batch / 32 warps: the whole device is busy, no thread idles at a barrier, no table padding.
+#define K5N_WARPS 4
+template <int MODE>
+__global__ void __launch_bounds__(K5N_WARPS * 32)
+k5_need_kernel(const uint16_t* __restrict__ av_t, int av_t_len, uint16_t* __restrict__ tex, int n, int batch, int channels,
+               const unsigned char* __restrict__ csr, int csr_bytes, int csr_idx_off, int csr_off_off,
+               const int* __restrict__ need, const float* __restrict__ wsum, int need_count, const SmoothParams sp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int groups = (batch + 31) / 32;
+    // consecutive warps take consecutive texels of the same stream group: their tap windows overlap, L1 serves the re-reads
+    const int gw = blockIdx.x * K5N_WARPS + warp;
+    const int k = gw % need_count, g = (gw / need_count) % groups, ch = gw / (need_count * groups);
+    if (ch >= channels) return;
+    const int x = __ldg(need + (size_t) ch * need_count + k);
+    if (x < 0 || x >= n) return;
+    const int stream = g * 32 + lane;
+    const bool live = stream < batch;
+    const unsigned char* blob = csr + (size_t) ch * csr_bytes;
+    const float*    tw = reinterpret_cast<const float*>(blob);
+    const uint16_t* ti = reinterpret_cast<const uint16_t*>(blob + csr_idx_off);
+    const int*      to = reinterpret_cast<const int*>(blob + csr_off_off);
+    const int o0 = __ldg(to + k), o1 = __ldg(to + k + 1);
+    const uint16_t* col = av_t + (size_t) ch * av_t_len * batch + (live ? stream : 0);
+    SmoothAcc acc; acc.init();
+    for (int o = o0; o < o1; o += 32) {
+        const int mine = o + lane;
+        const int   my_i = mine < o1 ? (int) __ldg(ti + mine) : 0;
+        const float my_w = mine < o1 ? __ldg(tw + mine) : 0.0f;
+        const int cnt = min(32, o1 - o);
+        if (cnt == 32) {
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) {
+                const int i = __shfl_sync(0xffffffffu, my_i, j);
+                const float w = __shfl_sync(0xffffffffu, my_w, j);
+                const float t = from16(col[(size_t) i * batch]);          // (a tap outside the texture is stored as index 0, weight 0)
+                if (MODE == 0) acc.avg += t * w; else acc.add_noweight(t, w);
+            }
+        } else {
+            for (int j = 0; j < cnt; ++j) {
+                const int i = __shfl_sync(0xffffffffu, my_i, j);
+                const float w = __shfl_sync(0xffffffffu, my_w, j);
+                const float t = from16(col[(size_t) i * batch]);
+                if (MODE == 0) acc.avg += t * w; else acc.add_noweight(t, w);
+            }
+        }
+    }
+    acc.weight = __ldg(wsum + (size_t) ch * need_count + k);
+    if (live) tex[((size_t) stream * 2 + ch) * n + x] = (uint16_t) unorm16(acc.result(sp));
+}
+
+int launch_k5_need(const glava_b200_params& p, const uint16_t* d_av_t, int av_t_len, uint16_t* d_tex, int batch, int channels,
+                   const unsigned char* d_csr, int csr_bytes, int csr_idx_off, int csr_off_off, const int* d_need,
+                   const float* d_wsum, int need_count, void* stream) {
+    const SmoothParams sp = smooth_params(p);
+    const int groups = (batch + 31) / 32;
+    const long long warps = (long long) channels * need_count * groups;
+    const unsigned grid = (unsigned) ((warps + K5N_WARPS - 1) / K5N_WARPS);
+    if (grid == 0) return 0;
+    cudaStream_t st = (cudaStream_t) stream;
+#define GLB_K5N(M) k5_need_kernel<M><<<grid, K5N_WARPS * 32, 0, st>>>(d_av_t, av_t_len, d_tex, p.n, batch, channels, d_csr, csr_bytes, \
+                                                                        csr_idx_off, csr_off_off, d_need, d_wsum, need_count, sp)
+    if (sp.sample_mode == 0) GLB_K5N(0); else GLB_K5N(1);
+#undef GLB_K5N
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "need-list smooth kernel launch: %s", cudaGetErrorString(e));
     return 0;
 }
 

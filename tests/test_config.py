@@ -223,3 +223,20 @@ def test_setsmoothfactor_is_the_six_decimal_literal_of_the_injected_header(built
     assert g.load_config(requests=["setsmoothfactor 0.0438713878"]).smooth_factor == np.float32("0.043871")
     assert g.load_config(requests=["setsmoothfactor 0.0123456789"]).smooth_factor == np.float32("0.012346")
     assert g.load_config().smooth_factor == np.float32(0.025)
+
+
+def test_float_spelling_of_a_preprocessor_tested_macro_is_a_config_error(built, tmp_path):
+    """`#if BAR_OUTLINE_WIDTH > 0` (bars/1.frag:116): GLSL's preprocessor takes integer expressions only — with a float the
+    reference's shader does not compile (seen on Mesa llvmpipe) and GLava aborts; here: ECONFIG naming the macro"""
+    d = tmp_path / "cfg"; d.mkdir()
+    (d / "rc.glsl").write_text("#request mod bars\n")
+    (d / "bars.glsl").write_text("#define BAR_OUTLINE_WIDTH 0.5\n")
+    with pytest.raises(g.GlavaError, match="BAR_OUTLINE_WIDTH.*preprocessor"):
+        g.load_config([str(d)])
+    (d / "bars.glsl").write_text("#define BAR_OUTLINE_WIDTH 2\n#define USE_ALPHA 1\n")
+    p = g.load_config([str(d)])
+    assert p.bars_outline_width == 2.0          # USE_ALPHA is read and ignored: bars/2.frag never sees bars.glsl (llvmpipe golden)
+    (d / "rc.glsl").write_text("#request mod graph\n")
+    (d / "graph.glsl").write_text("#define DRAW_OUTLINE 1.0\n")
+    with pytest.raises(g.GlavaError, match="DRAW_OUTLINE"):
+        g.load_config([str(d)])

@@ -39,7 +39,9 @@ def gen(rng, module):
     L=[]
     D=lambda k,v: L.append(f"#define {k} {v}")
     if module=="bars":
-        D("BAR_WIDTH", num(rng,1,6)); D("BAR_GAP", num(rng,0,3)); D("BAR_OUTLINE_WIDTH", num(rng,0,2)); D("AMPLIFY", num(rng,10,40))
+        # BAR_OUTLINE_WIDTH is tested in `#if BAR_OUTLINE_WIDTH > 0` (bars/1.frag:116): integers only compile; the same draw
+        # as before is consumed (so the other macros of a seed stay what they were) and its integer part is kept
+        D("BAR_WIDTH", num(rng,1,6)); D("BAR_GAP", num(rng,0,3)); D("BAR_OUTLINE_WIDTH", str(int(float(num(rng,0,2))))); D("AMPLIFY", num(rng,10,40))
         D("GRADIENT", num(rng,5,40)); D("COLOR", f"mix({col(rng)}, {col(rng)}, clamp(d / GRADIENT, 0, 1))")
         if rng.random()<0.5: D("BAR_OUTLINE", col(rng))
         for k in ("DIRECTION","INVERT","FLIP","MIRROR_YX"): D(k, int(rng.integers(0,2)))
@@ -48,7 +50,7 @@ def gen(rng, module):
         D("BAR_WIDTH", num(rng,1,5)); D("AMPLIFY", num(rng,8,25)); D("GRADIENT", num(rng,4,20))
         D("COLOR", f"mix({col(rng)}, {col(rng)}, clamp(d / GRADIENT, 0, 1))"); D("ROTATE", rng.choice(["(PI / 2)","0","1.3","(TWOPI / 5)"]))
         D("INVERT", int(rng.integers(0,2))); D("BAR_ALIAS_FACTOR", num(rng,0.5,2,False)); D("C_ALIAS_FACTOR", num(rng,0.5,2.5,False))
-        D("CENTER_OFFSET_X", num(rng,-4,4)); D("CENTER_OFFSET_Y", num(rng,-3,3)); D("BAR_OUTLINE_WIDTH", rng.choice(["0","0","1","0.5"]))
+        D("CENTER_OFFSET_X", num(rng,-4,4)); D("CENTER_OFFSET_Y", num(rng,-3,3)); D("BAR_OUTLINE_WIDTH", (lambda c: {"0.5": "1"}.get(c, c))(str(rng.choice(["0","0","1","0.5"]))))   # (`#if BAR_OUTLINE_WIDTH > 0`, radial/1.frag:87: integers only)
     if module=="circle":
         D("C_RADIUS", num(rng,4,10)); D("C_LINE", num(rng,1,3)); D("OUTLINE", col(rng)); D("AMPLIFY", num(rng,5,20))
         D("ROTATE", rng.choice(["(PI / 2)","0","2.1"])); D("INVERT", int(rng.integers(0,2))); D("C_FILL", int(rng.integers(0,2))); D("C_SMOOTH", int(rng.integers(0,2)))
