@@ -167,6 +167,7 @@ def lib():
     L.glava_b200_update_device_masked.argtypes = [vp, vp, vp, C.c_size_t, vp]
     L.glava_b200_update_rings_masked.argtypes = [vp, vp]
     L.glava_b200_ingest_fifo.argtypes = [vp, vp, i32]
+    L.glava_b200_ingest_float.argtypes = [vp, vp, i32]
     L.glava_b200_update_rings.argtypes = [vp, i32]
     L.glava_b200_sync.argtypes = [vp]
     L.glava_b200_readback.argtypes = [vp, i32, vp]
@@ -378,6 +379,12 @@ class Renderer:
         chunks = np.ascontiguousarray(chunks, dtype=np.int16)
         assert chunks.ndim == 2 and chunks.shape[0] == self.batch and chunks.shape[1] % 2 == 0
         _check(self._L.glava_b200_ingest_fifo(self._h, chunks.ctypes.data, chunks.shape[1] // 2))
+
+    def ingest_float(self, chunks):
+        """PulseAudio semantics (pulse_input.c:146-174): float samples as they are, [batch][frames*2] interleaved"""
+        chunks = np.ascontiguousarray(chunks, dtype=np.float32)
+        assert chunks.ndim == 2 and chunks.shape[0] == self.batch and chunks.shape[1] % 2 == 0
+        _check(self._L.glava_b200_ingest_float(self._h, chunks.ctypes.data, chunks.shape[1] // 2))
 
     def update_rings(self, modified=True):
         _check(self._L.glava_b200_update_rings(self._h, 1 if modified else 0))

@@ -87,14 +87,14 @@ struct glava_b200 {
     cudaEvent_t ev_copied[2], ev_free[2];
     float* d_ring[2][2];        // FIFO rings, ping-pong                      [2][batch][n] x {l, r}
     int    ring_cur;
-    int16_t* d_chunks; size_t chunks_cap;
+    void* d_chunks; size_t chunks_cap;
     // constants
     double* d_window; float* d_twiddle; void* d_rowtab; int* d_need; int need_count;
     TapEntry* d_tap_tab; int* d_tap_cnt; float* d_tap_wsum; int tap_max; int epi_n;
     K5Table k5; void* d_k5_blk; void* d_k5_ent; void* d_k5_wsum;   // full-plane K5 tap table (null: evaluate taps in the kernel)
     // need-list K5 as its own kernel (one table per channel): the serial per-texel sums run at full occupancy on
     // (texel, plane) pairs instead of on a sixth of the threads of one spectrum CTA
-    bool k5_split_lazy, csr_in_smem; int av_t_len;
+    bool k5_split_lazy, csr_in_smem; int av_t_len; float* d_av_t;   // need-list K5 as its own kernel (k5_need_kernel)
     unsigned char* d_csr; int csr_bytes, csr_idx_off, csr_off_off;   // the same taps, texel-major, for the shared-memory path
     void* d_geo; int geo_box[4];   // polar geometry cache (radial / circle), see raster_kernels.cu
     uint32_t* d_texmm;             // circle: per-plane {min, max} of the sampled texture, refreshed before each raster
@@ -318,6 +318,7 @@ static int build_tables(glava_b200* r) {
     dev_free(r, r->d_k5_blk); dev_free(r, r->d_k5_ent); dev_free(r, r->d_k5_wsum);
     r->d_k5_blk = r->d_k5_ent = r->d_k5_wsum = nullptr; memset(&r->k5, 0, sizeof(r->k5));
     dev_free(r, r->d_csr); r->d_csr = nullptr; r->csr_bytes = r->csr_idx_off = r->csr_off_off = 0;
+    dev_free(r, r->d_av_t); r->d_av_t = nullptr;
     r->k5_split_lazy = false; r->csr_in_smem = false; r->av_t_len = 0;
     r->d_need = nullptr; r->need_count = 0; r->d_tap_tab = nullptr; r->d_tap_cnt = nullptr; r->d_tap_wsum = nullptr;
     r->tap_max = 0; r->epi_n = 0; r->d_geo = nullptr; r->geo_box[0] = r->geo_box[1] = r->geo_box[2] = r->geo_box[3] = 0;
@@ -364,6 +365,9 @@ static int build_tables(glava_b200* r) {
                 const char* ks = getenv("GLAVA_B200_K5_SPLIT");
                 r->k5_split_lazy = ks ? atoi(ks) != 0 : !fits;
                 r->av_t_len = t.epi_n > 0 ? t.epi_n : p.n;
+                if (r->k5_split_lazy) {
+                    if ((rc = dev_alloc(r, (void**) &r->d_av_t, (size_t) 2 * r->av_t_len * r->batch * sizeof(float), true)) != 0) return rc;
+                }
             }
         }
     }
@@ -511,7 +515,7 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     r->d_tap_tab = nullptr; r->d_tap_cnt = nullptr; r->d_tap_wsum = nullptr; r->tap_max = 0; r->epi_n = 0;
     r->d_csr = nullptr; r->csr_bytes = r->csr_idx_off = r->csr_off_off = 0;
     r->d_k5_blk = r->d_k5_ent = r->d_k5_wsum = nullptr; memset(&r->k5, 0, sizeof(r->k5));
-    r->k5_split_lazy = false; r->csr_in_smem = false; r->av_t_len = 0;
+    r->k5_split_lazy = false; r->csr_in_smem = false; r->av_t_len = 0; r->d_av_t = nullptr;
     r->d_geo = nullptr; r->geo_box[0] = r->geo_box[1] = r->geo_box[2] = r->geo_box[3] = 0;
     r->d_spec = r->d_applied = r->d_ring_f = nullptr; r->d_gr_store = r->d_ring_u = r->d_tex = nullptr; r->d_av = nullptr; r->d_texmm = nullptr; r->d_fb = nullptr;
     for (int i = 0; i < 2; ++i) { r->d_pcm[i][0] = r->d_pcm[i][1] = nullptr; r->ev_copied[i] = r->ev_free[i] = nullptr; }
@@ -714,13 +718,13 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
         // full-plane smoothing (every texel wanted): the spectrum kernel exports the pre-smoothing texture and
         // a second kernel smooths all planes, sharing the tap weights between planes
         const bool split_k5 = p.smooth_pass && !a.need && !r->post_chain && !r->fused_k5 && !split_lazy;
-        a.av_out = split_k5 ? r->d_av : nullptr;
-        a.av_t = split_lazy ? r->d_av : nullptr; a.av_t_len = r->av_t_len;     // (d_av is free in lazy mode: same bytes, transposed use)
+        a.av_out = (split_k5 || split_lazy) ? r->d_av : nullptr;
+        a.av_t_len = split_lazy ? r->av_t_len : 0;
         if ((rc = launch_spectrum(p, a, is_fft, r->spec_stream)) != 0) return rc;
         if (split_lazy) {
-            if ((rc = launch_k5_need(p, r->d_av, r->av_t_len, a.tex, r->batch, is_fft ? 2 : 1, r->d_csr, r->csr_bytes, r->csr_idx_off,
+            if ((rc = launch_k5_need(p, r->d_av, r->d_av_t, r->av_t_len, a.tex, r->batch, is_fft ? 2 : 1, r->d_csr, r->csr_bytes, r->csr_idx_off,
                                      r->csr_off_off, r->d_need, r->d_tap_wsum, r->need_count, r->spec_stream)) != 0) return rc;
-            ++r->launches;
+            r->launches += 2;
         }
         if (split_k5) {
             // wave uses plane 0 of each stream only; smoothing the (zero) odd planes too keeps the launch simple
@@ -888,12 +892,12 @@ int glava_b200_update_device(glava_b200* r, const float* d_lb, const float* d_rb
     return run_update(r, d_lb, d_rb ? d_rb : d_lb, modified);
 }
 
-int glava_b200_ingest_fifo(glava_b200* r, const int16_t* chunks, int frames) {
+static int ingest(glava_b200* r, const void* chunks, bool float_in, int frames, const char* who) {
     clear_error();
-    if (!r || !chunks) return fail(GLAVA_B200_EINVAL, "glava_b200_ingest_fifo: null argument");
-    if (frames < 1 || frames > r->n_in) return fail(GLAVA_B200_EINVAL, "glava_b200_ingest_fifo: frames %d out of range", frames);
+    if (!r || !chunks) return fail(GLAVA_B200_EINVAL, "%s: null argument", who);
+    if (frames < 1 || frames > r->n_in) return fail(GLAVA_B200_EINVAL, "%s: frames %d out of range", who, frames);
     CU(cudaSetDevice(r->device));
-    size_t bytes = (size_t) r->batch * frames * 2 * sizeof(int16_t);
+    size_t bytes = (size_t) r->batch * frames * 2 * (float_in ? sizeof(float) : sizeof(int16_t));
     if (bytes > r->chunks_cap) {
         CU(cudaStreamSynchronize(r->spec_stream));
         if (r->d_chunks) cudaFree(r->d_chunks);
@@ -904,13 +908,15 @@ int glava_b200_ingest_fifo(glava_b200* r, const int16_t* chunks, int frames) {
     // ordered with the spectrum kernels (they read the rings): same stream
     CU(cudaMemcpyAsync(r->d_chunks, chunks, bytes, cudaMemcpyHostToDevice, r->spec_stream));
     int cur = r->ring_cur, nxt = cur ^ 1;
-    int rc = launch_fifo_ingest(r->p_user, r->d_chunks, frames, r->d_ring[cur][0], r->d_ring[cur][1],
+    int rc = launch_fifo_ingest(r->p_user, r->d_chunks, float_in, frames, r->d_ring[cur][0], r->d_ring[cur][1],
                                 r->d_ring[nxt][0], r->d_ring[nxt][1], r->batch, r->spec_stream);
     if (rc) return rc;
     ++r->launches;
     r->ring_cur = nxt;
     return 0;
 }
+int glava_b200_ingest_fifo(glava_b200* r, const int16_t* chunks, int frames) { return ingest(r, chunks, false, frames, "glava_b200_ingest_fifo"); }
+int glava_b200_ingest_float(glava_b200* r, const float* chunks, int frames) { return ingest(r, chunks, true, frames, "glava_b200_ingest_float"); }
 
 int glava_b200_update_rings(glava_b200* r, int modified) {
     clear_error();

@@ -110,5 +110,30 @@ struct StockhamPass {
     }
 };
 
+// One butterfly of a pass, out of place: reads its R inputs through `ld`, writes its R outputs through `st`.  The
+// arithmetic (twiddle indices, DFT network) is StockhamPass's — the result does not depend on which thread runs which
+// butterfly, or on in-place / out-of-place — so the host emulation (tests/emul) stays valid for both kernels.
+template <int M, int R, int NS>
+struct StockhamButterfly {
+    static constexpr int NB = M / R;
+    template <class LoadFn, class StoreFn>
+    GLB_HD static void run(int j, LoadFn ld, StoreFn st, const cpx* __restrict__ tw) {
+        const int k = j & (NS - 1);
+        cpx u[R];
+#pragma unroll
+        for (int t = 0; t < R; ++t) {
+            cpx v = ld(j + t * NB);
+            if (NS > 1 && t > 0) v = cmul(v, tw[t * k * (M / (NS * R))]);
+            u[t] = v;
+        }
+        Dft<R>::run(u);
+        const int base = (j - k) * R + k;
+#pragma unroll
+        for (int t = 0; t < R; ++t) st(base + t * NS, u[t]);
+    }
+};
+// number of passes of an M-point transform with radices 8, 8, ..., (4 | 2)
+constexpr int fft_pass_count(int m) { int p = 0; while (m > 1) { m = m >= 8 ? m / 8 : 1; ++p; } return p; }
+
 }  // namespace glb
 #endif

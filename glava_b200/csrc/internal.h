@@ -67,10 +67,7 @@ struct SpectrumArgs {
     // shares the cursor `update % F`; else one word per stream, bit 31 = this stream has new audio, low 16 bits = its own
     // ring cursor (modified updates of THAT stream so far, mod F).  An unmodified stream's state is left alone and its
     // texture is carried from `tex_prev` (the half of the double buffer the previous raster read) into `tex`.
-    // need-list K5 as its own kernel (k5_need_kernel): the pre-smoothing texels are exported TRANSPOSED, stream-minor,
-    // av_t[(ch * av_t_len + bin) * batch + stream] for bin < av_t_len, so that a warp whose lanes are 32 streams reads one
-    // coalesced run per tap; nullptr = not exported
-    uint16_t* av_t; int av_t_len;
+    int av_t_len;               // > 0: av_out receives only the leading av_t_len bins (need-list K5 as its own kernel downstream)
     const uint32_t* umask;      // [batch]
     const uint16_t* tex_prev;   // [batch*2][n]
     double    avg_w_a[GLB_MAX_AVG_FRAMES];   // pipeline A weights, oldest first (render.c:661,766)
@@ -112,9 +109,9 @@ struct K5Table {
 // planes of the interleaved [batch][2] layout (need-list tables differ per channel)
 int launch_smooth_only(const glava_b200_params& p, const uint16_t* d_in, uint16_t* d_out, int count, void* stream,
                        const K5Table* table = nullptr, int plane_stride = 1, int plane_offset = 0);
-// need-list K5, lanes = streams: csr = the texel-major tap blobs of SpectrumArgs (per channel float w[] | u16 idx[] | int off[]),
+// need-list K5, lanes = streams (d_av [batch*2][n] u16 as exported by the spectrum kernel -> transposed float d_av_t): csr = the texel-major tap blobs of SpectrumArgs (per channel float w[] | u16 idx[] | int off[]),
 // need / wsum = [2][need_count]; av_t as exported by the spectrum kernel; writes tex[(stream * 2 + ch) * n + need[k]]
-int launch_k5_need(const glava_b200_params& p, const uint16_t* d_av_t, int av_t_len, uint16_t* d_tex, int batch, int channels,
+int launch_k5_need(const glava_b200_params& p, const uint16_t* d_av, float* d_av_t, int av_t_len, uint16_t* d_tex, int batch, int channels,
                    const unsigned char* d_csr, int csr_bytes, int csr_idx_off, int csr_off_off, const int* d_need,
                    const float* d_wsum, int need_count, void* stream);
 int launch_raster(const glava_b200_params& p, const RasterArgs& a, void* stream);
@@ -123,7 +120,7 @@ int launch_bars_rowtab(const glava_b200_params& p, void* d_rowtab, void* stream)
 size_t polar_geo_box(const glava_b200_params& p, int box[4]);
 int launch_texmm(const glava_b200_params& p, const uint16_t* d_tex, uint32_t* d_out, int planes, void* stream);
 int launch_polar_geo(const glava_b200_params& p, void* d_geo, const int box[4], void* stream);
-int launch_fifo_ingest(const glava_b200_params& p, const int16_t* d_chunks, int frames, const float* src_l, const float* src_r,
+int launch_fifo_ingest(const glava_b200_params& p, const void* d_chunks, bool float_in, int frames, const float* src_l, const float* src_r,
                        float* dst_l, float* dst_r, int batch, void* stream);
 int spectrum_smem_bytes(int n);
 int spectrum_threads(int n);

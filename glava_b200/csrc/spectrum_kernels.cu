@@ -47,17 +47,28 @@ constexpr int spec_default_threads(int log2n) {
     const int m8 = (1 << log2n) / 16;
     return m8 < 128 ? 128 : (m8 > 512 ? 512 : m8);   // (1024 threads at N = 16384 was measured 2x slower)
 }
-template <int LOG2N, int TT = 0> struct SpecCfg {
+// OOP = out-of-place passes between two buffers: one barrier per pass instead of two and a thread holds ONE butterfly in
+// registers at a time (in place it must hold all of its butterflies across the barrier: 116-124 registers at N >= 8192,
+// one 512-thread CTA per SM).  With half the registers and small CTAs several planes are resident per SM, their barrier
+// waits overlap, and the kernel co-resides with the raster kernel's CTAs instead of alternating with them.
+template <int LOG2N, int TT = 0, bool OOP = false> struct SpecCfg {
     static constexpr int N = 1 << LOG2N, M = N / 2;
     static constexpr int T = TT > 0 ? TT : spec_default_threads(LOG2N);
     static constexpr int BUF_CPX = fft_padded_size(M);
-    // cpx buffer (also the raw-PCM staging area, N floats = M cpx) | u16 av[N] | mbarrier
-    static constexpr int OFF_AV  = ((BUF_CPX * 8 + 15) / 16) * 16;
-    static constexpr int OFF_BAR = OFF_AV + N * 2;
+    static constexpr int BUF_BYTES = ((BUF_CPX * 8 + 15) / 16) * 16;
+    // in place:     cpx buffer (also the raw-PCM staging area, N floats = M cpx) | u16 av[N] | mbarriers
+    // out of place: buffer A (PCM lands here) | buffer B | mbarriers; av[N] lives in whichever buffer the result is NOT in
+    static constexpr int OFF_B   = BUF_BYTES;
+    static constexpr int OFF_AV  = BUF_BYTES;
+    static constexpr int OFF_BAR = OOP ? 2 * BUF_BYTES : OFF_AV + N * 2;
     static constexpr int SMEM    = OFF_BAR + 16;
+    static constexpr bool RESULT_IN_B = OOP && (fft_pass_count(M) % 2 == 1);
     // resident CTAs per SM the register allocation must allow: the kernel waits on memory a lot (TMA load,
     // state loads), so occupancy is worth more than the last registers (128 regs -> 2 CTAs/SM was measured)
-    static constexpr int MIN_CTAS = T >= 512 ? 1 : (T * (N / 16 / T > 1 ? 2 : 1) > 256 ? 2 : 3);   // T = 512: capping at 64 registers spills in the FFT passes and was measured slower
+    static constexpr int SMEM_CTAS = (220 * 1024) / SMEM < 1 ? 1 : (220 * 1024) / SMEM;
+    static constexpr int OOP_CTAS  = (1024 / T) < SMEM_CTAS ? (1024 / T) : SMEM_CTAS;       // <= 64 registers where shared memory allows
+    static constexpr int MIN_CTAS = OOP ? (OOP_CTAS < 1 ? 1 : OOP_CTAS)
+                                        : (T >= 512 ? 1 : (T * (N / 16 / T > 1 ? 2 : 1) > 256 ? 2 : 3));   // T = 512: capping at 64 registers spills in the FFT passes and was measured slower
 };
 
 template <int M, int T, int NS, class Loader>
@@ -75,19 +86,38 @@ __device__ __forceinline__ void run_passes(cpx* buf, Loader first_loader, const 
         run_passes<M, T, NS * R>(buf, first_loader, tw, tid);
     }
 }
+// out of place: src -> dst, one barrier, then the roles swap (the first pass reads the raw PCM through `first_loader`)
+template <int M, int T, int NS, class Loader>
+__device__ __forceinline__ void run_passes_oop(cpx* src, cpx* dst, Loader first_loader, const cpx* __restrict__ tw, int tid) {
+    constexpr int REM = M / NS;
+    if constexpr (REM > 1) {
+        constexpr int R = (REM >= 8) ? 8 : REM;
+        using B = StockhamButterfly<M, R, NS>;
+        auto st = [dst](int i, cpx v) { dst[fft_pad(i)] = v; };
+        for (int j = tid; j < B::NB; j += T) {
+            if constexpr (NS == 1) B::run(j, first_loader, st, tw);
+            else B::run(j, [src](int i) { return src[fft_pad(i)]; }, st, tw);
+        }
+        __syncthreads();
+        run_passes_oop<M, T, NS * R>(dst, src, first_loader, tw, tid);
+    }
+}
 
 extern __shared__ __align__(16) unsigned char glb_smem[];
 
-template <int LOG2N, bool IS_FFT, int TT = 0>
-__global__ void __launch_bounds__((SpecCfg<LOG2N, TT>::T), (SpecCfg<LOG2N, TT>::MIN_CTAS))
+template <int LOG2N, bool IS_FFT, int TT = 0, bool OOP = false>
+__global__ void __launch_bounds__((SpecCfg<LOG2N, TT, OOP>::T), (SpecCfg<LOG2N, TT, OOP>::MIN_CTAS))
 spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ glava_b200_params p) {
-    using C = SpecCfg<LOG2N, TT>;
+    using C = SpecCfg<LOG2N, TT, OOP>;
     constexpr int N = C::N, M = C::M, T = C::T;
     const int tid = threadIdx.x;
 
-    cpx*      buf = reinterpret_cast<cpx*>(glb_smem);
+    // buf = where the transform's result is read from; av = the R16 texels of the epilogue (out of place: in the other buffer)
+    cpx*      bufA = reinterpret_cast<cpx*>(glb_smem);
+    cpx*      bufB = reinterpret_cast<cpx*>(glb_smem + C::OFF_B);
+    cpx*      buf = (OOP && C::RESULT_IN_B) ? bufB : bufA;
     float*    raw = reinterpret_cast<float*>(glb_smem);
-    uint16_t* av  = reinterpret_cast<uint16_t*>(glb_smem + C::OFF_AV);
+    uint16_t* av  = OOP ? reinterpret_cast<uint16_t*>((IS_FFT && C::RESULT_IN_B) ? bufA : bufB) : reinterpret_cast<uint16_t*>(glb_smem + C::OFF_AV);
     uint64_t* bar = reinterpret_cast<uint64_t*>(glb_smem + C::OFF_BAR);
 
     // Persistent CTAs: work unit u = one (stream, channel) plane (wave: one stream, audio_l only,
@@ -166,7 +196,8 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
             cpx r = { (float) ((double) v.x * w.x), (float) ((double) v.y * w.y) };
             return r;
         };
-        run_passes<M, T, 1>(buf, first, reinterpret_cast<const cpx*>(a.twiddle), tid);
+        if constexpr (OOP) run_passes_oop<M, T, 1>(bufA, bufB, first, reinterpret_cast<const cpx*>(a.twiddle), tid);
+        else run_passes<M, T, 1>(buf, first, reinterpret_cast<const cpx*>(a.twiddle), tid);
 
         if (!p.accel_fft) {
             // --- pipeline A: render.c:2149-2156 --------------------------------------------------
@@ -290,9 +321,10 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
         }
     }
     __syncthreads();
-    // `raw`/`buf` are dead from here on: let the TMA engine fetch the next unit's PCM during K5
-    if (tid == 0 && u + (int) gridDim.x < units) issue_load(u + gridDim.x);
-    if (a.skip_tex) continue;                        // chain result only (`spec`): the texture is produced downstream
+    // `raw`/`buf` are dead from here on: let the TMA engine fetch the next unit's PCM during K5 (out of place, `av` may live
+    // in the landing buffer: the load is issued after K5)
+    if (!OOP && tid == 0 && u + (int) gridDim.x < units) issue_load(u + gridDim.x);
+    if (a.skip_tex) { if (OOP && tid == 0 && u + (int) gridDim.x < units) issue_load(u + gridDim.x); continue; }   // chain result only (`spec`): the texture is produced downstream
 
     // --- K5 smooth pass out of shared memory (render.c:2276-2303) ----------------------------------
     uint16_t* tex = a.tex + plane;
@@ -374,15 +406,13 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
                 int x = need[k];
                 if (x >= 0 && x < N) tex[x] = (uint16_t) smooth_pass_texel(sp, av, N, x);
             }
-        } else if (a.av_t) {
-            // need-list K5 downstream (k5_need_kernel): the bins its taps can reach, stream-minor
-            uint16_t* dst = a.av_t + (size_t) ch * a.av_t_len * a.batch + (c >> 1);
-            for (int x = tid; x < a.av_t_len; x += T) dst[(size_t) x * a.batch] = av[x];
         } else if (a.av_out) {
-            // all n texels wanted: export the pre-smoothing texture; k5_planes_kernel (below) smooths it,
-            // sharing every tap weight between several planes instead of recomputing it per plane
+            // export the pre-smoothing texture for a K5 kernel downstream: all n texels (k5_table_kernel / k5_planes_kernel
+            // smooth whole planes, sharing every tap weight between several planes), or only the leading av_t_len bins the
+            // need-list's taps can reach (av_transpose_kernel + k5_need_kernel)
             uint16_t* dst = a.av_out + plane;
-            for (int x = tid; x < N; x += T) dst[x] = av[x];
+            const int lim = a.av_t_len > 0 ? a.av_t_len : N;
+            for (int x = tid; x < lim; x += T) dst[x] = av[x];
         } else {
             for (int x = tid; x < N; x += T) tex[x] = (uint16_t) smooth_pass_texel(sp, av, N, x);
         }
@@ -390,6 +420,7 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
         for (int x = tid; x < N; x += T) tex[x] = av[x];
     }
     __syncthreads();                                 // `av` may be overwritten by the next unit's epilogue
+    if (OOP && tid == 0 && u + (int) gridDim.x < units) issue_load(u + gridDim.x);
   }
   if (tab_pending) mbar_wait(bar2, parity2);          // (every unit of this CTA was skipped: do not exit under an in-flight bulk copy)
 }
@@ -411,10 +442,10 @@ int spectrum_smem_bytes(int n) {
     }
 }
 
-template <int LOG2N, bool IS_FFT, int TT = 0>
+template <int LOG2N, bool IS_FFT, int TT = 0, bool OOP = false>
 static int launch_spectrum_t(const glava_b200_params& p, const SpectrumArgs& a, cudaStream_t st) {
-    using C = SpecCfg<LOG2N, TT>;
-    auto kern = spectrum_kernel<LOG2N, IS_FFT, TT>;
+    using C = SpecCfg<LOG2N, TT, OOP>;
+    auto kern = spectrum_kernel<LOG2N, IS_FFT, TT, OOP>;
     // Residency cap (tuning aid, off): the kernel co-runs with the raster kernel (capi.cu run_update) and
     // at full occupancy (5 CTAs x 256 threads x 48 registers per SM) takes most of the register file.
     // Requesting more dynamic shared memory than needed caps it at `cap` CTAs per SM.  Measured on B200
@@ -451,17 +482,25 @@ static int launch_spectrum_t(const glava_b200_params& p, const SpectrumArgs& a, 
     return 0;
 }
 
+// Variant selection: default = the measured-best one per size; GLAVA_B200_SPEC_OOP=0|1 and GLAVA_B200_SPEC_T=128|256|512
+// override it for tuning sweeps (tools/spec_probe.py).
+template <int L>
+static int launch_spectrum_fft(const glava_b200_params& p, const SpectrumArgs& a, cudaStream_t st, int oop, int tsel) {
+    if (oop) {
+        if (tsel == 128) return launch_spectrum_t<L, true, 128, true>(p, a, st);
+        if (tsel == 512) { if constexpr (L >= 13) return launch_spectrum_t<L, true, 512, true>(p, a, st); }
+        return launch_spectrum_t<L, true, 256, true>(p, a, st);
+    }
+    if (tsel == 256) { if constexpr (L >= 13) return launch_spectrum_t<L, true, 256, false>(p, a, st); }
+    return launch_spectrum_t<L, true, 0, false>(p, a, st);
+}
+
 int launch_spectrum(const glava_b200_params& p, const SpectrumArgs& a, bool is_fft, void* stream) {
     cudaStream_t st = (cudaStream_t) stream;
-#define GLB_CASE(L) case (1 << L): return is_fft ? launch_spectrum_t<L, true>(p, a, st) : launch_spectrum_t<L, false>(p, a, st);
-    // the large sizes also exist with 256 threads per CTA (two butterflies per thread and pass, 2 CTAs per SM instead of one
-    // of 512): GLAVA_B200_SPEC_T=256 selects them
-    static int tsel = -1;
+    static int tsel = -1, oop = -1;
     if (tsel < 0) { tsel = 0; if (const char* e = getenv("GLAVA_B200_SPEC_T")) tsel = atoi(e); }
-    if (tsel == 256 && is_fft) {
-        if (p.n == 8192)  return launch_spectrum_t<13, true, 256>(p, a, st);
-        if (p.n == 16384) return launch_spectrum_t<14, true, 256>(p, a, st);
-    }
+    if (oop < 0) { oop = 0; if (const char* e = getenv("GLAVA_B200_SPEC_OOP")) oop = atoi(e); }
+#define GLB_CASE(L) case (1 << L): return is_fft ? launch_spectrum_fft<L>(p, a, st, oop, tsel) : launch_spectrum_t<L, false>(p, a, st);
     switch (p.n) {
         GLB_CASE(8) GLB_CASE(9) GLB_CASE(10) GLB_CASE(11) GLB_CASE(12) GLB_CASE(13) GLB_CASE(14)
         default: return fail(GLAVA_B200_EINVAL, "unsupported setbufsize %d", p.n);
@@ -618,71 +657,111 @@ int launch_smooth_only(const glava_b200_params& p, const uint16_t* d_in, uint16_
 // ---------------------------------------------------------------------------------------------
 // Need-list K5, lanes = streams.  Inside the spectrum kernel a texel's serial sum occupies one thread of a CTA whose other
 // threads wait (ncu at setbufsize 8192: half of all warp samples sit at that barrier).  Here one WARP owns one sampled
-// texel of one channel for 32 streams: the tap list is the same for all of them, so a lane loads one {index, weight} of
-// the next 32 taps (two coalesced loads) and the warp walks them by shuffle broadcast; every tap is one coalesced 64-byte
-// read of the transposed pre-smoothing texels and the ordered multiply-add of smooth_audio() (smooth.glsl:33-37), per lane.
-// 2 x need_count x batch / 32 warps: the whole device is busy, no thread idles at a barrier, no table padding.
+// texel of one channel for 32 * S streams: the tap list is the same for all of them, so a lane loads one {index, weight}
+// of the next 32 taps (two coalesced loads) and the warp walks them by shuffle broadcast; per tap and stream one coalesced
+// read of the transposed pre-smoothing texels (exported as float: converted once by the producer, not once per tap) and the
+// ordered multiply-add of smooth_audio() (smooth.glsl:33-37).  S independent sums per lane share every broadcast.
+// [plane = stream * 2 + ch][bin] u16  ->  [ch][bin][stream] float (from16 applied once here, not once per tap): 32 x 32 tiles
+// through shared memory, both sides coalesced.  A plane-owning spectrum CTA could only write its own stream's column of the
+// transposed layout — 4-byte stores 4 KB apart, measured ~100 us at setbufsize 8192 — so the transposition is its own pass.
+__global__ void __launch_bounds__(256)
+av_transpose_kernel(const uint16_t* __restrict__ av, float* __restrict__ av_t, int n, int len, int batch) {
+    __shared__ float tile[32][33];
+    const int ch = blockIdx.z, b0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;             // 32 x 8
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int s = s0 + ty + 8 * r, b = b0 + tx;
+        tile[ty + 8 * r][tx] = (s < batch && b < len) ? from16(av[((size_t) s * 2 + ch) * n + b]) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int b = b0 + ty + 8 * r, s = s0 + tx;
+        if (b < len && s < batch) av_t[((size_t) ch * len + b) * batch + s] = tile[tx][ty + 8 * r];
+    }
+}
+
 #define K5N_WARPS 4
-template <int MODE>
+template <int MODE, int S>
 __global__ void __launch_bounds__(K5N_WARPS * 32)
-k5_need_kernel(const uint16_t* __restrict__ av_t, int av_t_len, uint16_t* __restrict__ tex, int n, int batch, int channels,
+k5_need_kernel(const float* __restrict__ av_t, int av_t_len, uint16_t* __restrict__ tex, int n, int batch, int channels,
                const unsigned char* __restrict__ csr, int csr_bytes, int csr_idx_off, int csr_off_off,
                const int* __restrict__ need, const float* __restrict__ wsum, int need_count, const SmoothParams sp) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int groups = (batch + 31) / 32;
+    const int groups = (batch + 32 * S - 1) / (32 * S);
     // consecutive warps take consecutive texels of the same stream group: their tap windows overlap, L1 serves the re-reads
     const int gw = blockIdx.x * K5N_WARPS + warp;
     const int k = gw % need_count, g = (gw / need_count) % groups, ch = gw / (need_count * groups);
     if (ch >= channels) return;
     const int x = __ldg(need + (size_t) ch * need_count + k);
     if (x < 0 || x >= n) return;
-    const int stream = g * 32 + lane;
-    const bool live = stream < batch;
+    const int stream0 = g * 32 * S + lane;
     const unsigned char* blob = csr + (size_t) ch * csr_bytes;
     const float*    tw = reinterpret_cast<const float*>(blob);
     const uint16_t* ti = reinterpret_cast<const uint16_t*>(blob + csr_idx_off);
     const int*      to = reinterpret_cast<const int*>(blob + csr_off_off);
     const int o0 = __ldg(to + k), o1 = __ldg(to + k + 1);
-    const uint16_t* col = av_t + (size_t) ch * av_t_len * batch + (live ? stream : 0);
-    SmoothAcc acc; acc.init();
+    // a lane past the batch reads column 0 (any valid address) and stores nothing
+    const float* col[S];
+#pragma unroll
+    for (int q = 0; q < S; ++q) col[q] = av_t + (size_t) ch * av_t_len * batch + (stream0 + 32 * q < batch ? stream0 + 32 * q : 0);
+    SmoothAcc acc[S];
+#pragma unroll
+    for (int q = 0; q < S; ++q) acc[q].init();
     for (int o = o0; o < o1; o += 32) {
         const int mine = o + lane;
-        const int   my_i = mine < o1 ? (int) __ldg(ti + mine) : 0;
+        const int   my_i = mine < o1 ? (int) __ldg(ti + mine) * batch : 0;     // (a tap outside the texture is stored as index 0, weight 0)
         const float my_w = mine < o1 ? __ldg(tw + mine) : 0.0f;
         const int cnt = min(32, o1 - o);
+        auto tap = [&](int j) {
+            const int i = __shfl_sync(0xffffffffu, my_i, j);
+            const float w = __shfl_sync(0xffffffffu, my_w, j);
+            float t[S];
+#pragma unroll
+            for (int q = 0; q < S; ++q) t[q] = __ldg(col[q] + i);
+#pragma unroll
+            for (int q = 0; q < S; ++q) { if (MODE == 0) acc[q].avg += t[q] * w; else acc[q].add_noweight(t[q], w); }
+        };
         if (cnt == 32) {
 #pragma unroll 8
-            for (int j = 0; j < 32; ++j) {
-                const int i = __shfl_sync(0xffffffffu, my_i, j);
-                const float w = __shfl_sync(0xffffffffu, my_w, j);
-                const float t = from16(col[(size_t) i * batch]);          // (a tap outside the texture is stored as index 0, weight 0)
-                if (MODE == 0) acc.avg += t * w; else acc.add_noweight(t, w);
-            }
+            for (int j = 0; j < 32; ++j) tap(j);
         } else {
-            for (int j = 0; j < cnt; ++j) {
-                const int i = __shfl_sync(0xffffffffu, my_i, j);
-                const float w = __shfl_sync(0xffffffffu, my_w, j);
-                const float t = from16(col[(size_t) i * batch]);
-                if (MODE == 0) acc.avg += t * w; else acc.add_noweight(t, w);
-            }
+            for (int j = 0; j < cnt; ++j) tap(j);
         }
     }
-    acc.weight = __ldg(wsum + (size_t) ch * need_count + k);
-    if (live) tex[((size_t) stream * 2 + ch) * n + x] = (uint16_t) unorm16(acc.result(sp));
+    const float weight = __ldg(wsum + (size_t) ch * need_count + k);
+#pragma unroll
+    for (int q = 0; q < S; ++q) {
+        acc[q].weight = weight;
+        const int stream = stream0 + 32 * q;
+        if (stream < batch) tex[((size_t) stream * 2 + ch) * n + x] = (uint16_t) unorm16(acc[q].result(sp));
+    }
 }
 
-int launch_k5_need(const glava_b200_params& p, const uint16_t* d_av_t, int av_t_len, uint16_t* d_tex, int batch, int channels,
+int launch_k5_need(const glava_b200_params& p, const uint16_t* d_av, float* d_av_t, int av_t_len, uint16_t* d_tex, int batch, int channels,
                    const unsigned char* d_csr, int csr_bytes, int csr_idx_off, int csr_off_off, const int* d_need,
                    const float* d_wsum, int need_count, void* stream) {
     const SmoothParams sp = smooth_params(p);
-    const int groups = (batch + 31) / 32;
+    cudaStream_t st = (cudaStream_t) stream;
+    {
+        dim3 tg((av_t_len + 31) / 32, (batch + 31) / 32, channels);
+        av_transpose_kernel<<<tg, 256, 0, st>>>(d_av, d_av_t, p.n, av_t_len, batch);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "transpose kernel launch: %s", cudaGetErrorString(e));
+    }
+    // streams per lane: 4 sums share every tap broadcast once the batch is large enough to still fill the device
+    const int S = batch >= 512 ? 4 : (batch >= 128 ? 2 : 1);
+    const int groups = (batch + 32 * S - 1) / (32 * S);
     const long long warps = (long long) channels * need_count * groups;
     const unsigned grid = (unsigned) ((warps + K5N_WARPS - 1) / K5N_WARPS);
     if (grid == 0) return 0;
-    cudaStream_t st = (cudaStream_t) stream;
-#define GLB_K5N(M) k5_need_kernel<M><<<grid, K5N_WARPS * 32, 0, st>>>(d_av_t, av_t_len, d_tex, p.n, batch, channels, d_csr, csr_bytes, \
-                                                                        csr_idx_off, csr_off_off, d_need, d_wsum, need_count, sp)
-    if (sp.sample_mode == 0) GLB_K5N(0); else GLB_K5N(1);
+#define GLB_K5N(M, SS) k5_need_kernel<M, SS><<<grid, K5N_WARPS * 32, 0, st>>>(d_av_t, av_t_len, d_tex, p.n, batch, channels, d_csr, csr_bytes, \
+                                                                              csr_idx_off, csr_off_off, d_need, d_wsum, need_count, sp)
+    const int m = sp.sample_mode == 0 ? 0 : 1;
+    if (S == 4) { if (m == 0) GLB_K5N(0, 4); else GLB_K5N(1, 4); }
+    else if (S == 2) { if (m == 0) GLB_K5N(0, 2); else GLB_K5N(1, 2); }
+    else { if (m == 0) GLB_K5N(0, 1); else GLB_K5N(1, 1); }
 #undef GLB_K5N
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "need-list smooth kernel launch: %s", cudaGetErrorString(e));
@@ -691,28 +770,39 @@ int launch_k5_need(const glava_b200_params& p, const uint16_t* d_av_t, int av_t_
 
 // ---------------------------------------------------------------------------------------------
 // FIFO ingest (fifo.c:89-110): slide + append, ping-pong between two ring buffers
-__global__ void fifo_ingest_kernel(const int16_t* __restrict__ chunks, int frames, int n, int channels,
+// FLOAT_IN: the samples are already float (PulseAudio backend, pulse_input.c:146-174: stored as they are, the mono mix is
+// (l + r) / 2 in float); otherwise int16 (fifo.c: s16 / 65535.f, integer mean for mono)
+template <bool FLOAT_IN>
+__global__ void fifo_ingest_kernel(const void* __restrict__ chunks, int frames, int n, int channels,
                                    const float* __restrict__ src_l, const float* __restrict__ src_r,
                                    float* __restrict__ dst_l, float* __restrict__ dst_r) {
     const int s = blockIdx.y;
     const size_t base = (size_t) s * n;
-    const int16_t* in = chunks + (size_t) s * frames * 2;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float l, r;
         if (i < n - frames) { l = src_l[base + i + frames]; r = src_r[base + i + frames]; }
         else {
-            int q = i - (n - frames);
-            int a = in[2 * q], b = in[2 * q + 1];
-            if (channels == 1) { float m = (float) ((a + b) / 2) / (float) 65535; l = m; r = m; }
-            else { l = (float) a / (float) 65535; r = (float) b / (float) 65535; }
+            const int q = i - (n - frames);
+            if (FLOAT_IN) {
+                const float* in = reinterpret_cast<const float*>(chunks) + (size_t) s * frames * 2;
+                const float a = in[2 * q], b = in[2 * q + 1];
+                if (channels == 1) { const float m = (a + b) / 2; l = m; r = m; }
+                else { l = a; r = b; }
+            } else {
+                const int16_t* in = reinterpret_cast<const int16_t*>(chunks) + (size_t) s * frames * 2;
+                const int a = in[2 * q], b = in[2 * q + 1];
+                if (channels == 1) { float m = (float) ((a + b) / 2) / (float) 65535; l = m; r = m; }
+                else { l = (float) a / (float) 65535; r = (float) b / (float) 65535; }
+            }
         }
         dst_l[base + i] = l; dst_r[base + i] = r;
     }
 }
-int launch_fifo_ingest(const glava_b200_params& p, const int16_t* d_chunks, int frames, const float* src_l, const float* src_r,
+int launch_fifo_ingest(const glava_b200_params& p, const void* d_chunks, bool float_in, int frames, const float* src_l, const float* src_r,
                        float* dst_l, float* dst_r, int batch, void* stream) {
     dim3 grid((p.n + 1023) / 1024, batch);
-    fifo_ingest_kernel<<<grid, 256, 0, (cudaStream_t) stream>>>(d_chunks, frames, p.n, p.channels, src_l, src_r, dst_l, dst_r);
+    if (float_in) fifo_ingest_kernel<true><<<grid, 256, 0, (cudaStream_t) stream>>>(d_chunks, frames, p.n, p.channels, src_l, src_r, dst_l, dst_r);
+    else fifo_ingest_kernel<false><<<grid, 256, 0, (cudaStream_t) stream>>>(d_chunks, frames, p.n, p.channels, src_l, src_r, dst_l, dst_r);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "fifo ingest kernel launch: %s", cudaGetErrorString(e));
     return 0;

@@ -269,6 +269,9 @@ int glava_b200_update_rings_masked(glava_b200* r, const uint8_t* modified);
  * (mono: integer mean first, fifo.c:98-102 when params.channels == 1).  Then
  * glava_b200_update_rings() runs the update on the resident rings. */
 int glava_b200_ingest_fifo(glava_b200* r, const int16_t* chunks, int frames);
+/* The PulseAudio backend's ring update (pulse_input.c:146-174): the samples are ALREADY float (PA_SAMPLE_FLOAT32NE, no
+ * / 65535), HOST [batch][frames*2] interleaved L,R; params.channels == 1 mixes (l + r) / 2 in float into both rings. */
+int glava_b200_ingest_float(glava_b200* r, const float* chunks, int frames);
 int glava_b200_update_rings(glava_b200* r, int modified);
 
 int glava_b200_sync(glava_b200* r);

@@ -70,3 +70,31 @@ def test_audio_frame_equals_update_with_the_collected_rings(built):
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[0].any()
         for s in range(batch):
             assert np.array_equal(r.readback(s), r2.readback(s))
+
+
+def test_float_ingest_follows_the_pulseaudio_ring_update(built):
+    """glava_b200_ingest_float = pulse_input.c:146-174: the samples are already float (no / 65535), slide by `frames`,
+    mono = (l + r) / 2 in float; the rings it leaves in HBM must render exactly what the same rings handed to
+    glava_b200_update render"""
+    n, batch, frames = 1024, 3, 256
+    rng = np.random.default_rng(17)
+    for channels in (2, 1):
+        p = g.default_params("bars", n=n, w=64, h=16, channels=channels)
+        rl = np.zeros((batch, n), np.float32); rr = np.zeros_like(rl)
+        with g.Renderer(p, batch=batch) as r, g.Renderer(p, batch=batch) as r2:
+            for _ in range(6):
+                chunk = ((rng.random((batch, frames * 2), np.float32) - 0.5) * 0.8).astype(np.float32)
+                r.ingest_float(chunk); r.update_rings(True)
+                a, b = chunk[:, 0::2], chunk[:, 1::2]
+                rl[:, :-frames] = rl[:, frames:]; rr[:, :-frames] = rr[:, frames:]
+                if channels == 1:
+                    m = ((a + b) / np.float32(2)).astype(np.float32)
+                    rl[:, -frames:] = m; rr[:, -frames:] = m
+                else:
+                    rl[:, -frames:] = a; rr[:, -frames:] = b
+                r2.update(rl, rr, True)
+            r.sync(); r2.sync()
+            x, y = r.spectrum(), r2.spectrum()
+            assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]) and x[0].any()
+            for s in range(batch):
+                assert np.array_equal(r.readback(s), r2.readback(s))

@@ -56,14 +56,18 @@ def run(module, n, w, h, batch, steps=16):
 
 def main():
     out = {"hbm_peak_gbs": PEAK, "points": []}
+    only = sys.argv[1:]          # optional filters "module:n:WxH" (e.g. bars:8192:1920x1080)
     pts = [("radial", 8192, 3840, 2160, 512)]
     for n in (512, 1024, 2048, 4096, 8192, 16384):
         for w, h in ((1280, 720), (1920, 1080), (3840, 2160), (7680, 4320)):
             pts.append(("bars", n, w, h, 1024))
     for mod in ("radial", "circle", "graph", "wave"):
         pts.append((mod, 4096, 1920, 1080, 1024))
+    if only:
+        pts = [pt for pt in pts if f"{pt[0]}:{pt[1]}:{pt[2]}x{pt[3]}" in only]
     for pt in pts:
         row = run(*pt)
+        row["whole_step_frac_of_hbm_peak"] = pt[4] * pt[2] * pt[3] * 4 / row["step_ms"] / 1e6 / PEAK
         out["points"].append(row)
         print(json.dumps(row), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
