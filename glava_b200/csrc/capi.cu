@@ -94,7 +94,7 @@ struct glava_b200 {
     K5Table k5; void* d_k5_blk; void* d_k5_ent; void* d_k5_wsum;   // full-plane K5 tap table (null: evaluate taps in the kernel)
     // need-list K5 as its own kernel (one table per channel): the serial per-texel sums run at full occupancy on
     // (texel, plane) pairs instead of on a sixth of the threads of one spectrum CTA
-    bool k5_split_lazy, csr_in_smem; int av_t_len; float* d_av_t;   // need-list K5 as its own kernel (k5_need_kernel)
+    bool k5_split_lazy, csr_in_smem, split_epilogue; int av_t_len; float* d_av_t; int spec_oop, spec_t;   // need-list K5 as its own kernel (k5_need_kernel)
     unsigned char* d_csr; int csr_bytes, csr_idx_off, csr_off_off;   // the same taps, texel-major, for the shared-memory path
     void* d_geo; int geo_box[4];   // polar geometry cache (radial / circle), see raster_kernels.cu
     uint32_t* d_texmm;             // circle: per-plane {min, max} of the sampled texture, refreshed before each raster
@@ -123,10 +123,10 @@ static void derive(glava_b200* r) {
     r->n_in = r->p_user.n;
     r->p.n = r->p_user.n / r->p_user.bufscale;
     const bool is_fft = r->p.module != GLAVA_B200_MOD_WAVE;
-    if (r->p.transform_smooth && is_fft) r->p.accel_fft = 0;
+    if (r->p.transform_smooth == 1 && is_fft) r->p.accel_fft = 0;           // (2 = "smooth" before "fft": applied to the PCM)
     const float fr = r->p.fr > 0.0f ? r->p.fr : r->p.ur;
     r->interp_on = r->p.interpolate && !(r->p.accel_fft && is_fft) && (r->p.ur / fr) <= 0.9f;
-    r->post_chain = r->p.transform_smooth || r->interp_on;
+    r->post_chain = r->p.transform_smooth == 1 || r->interp_on;
 }
 
 static int dev_alloc(glava_b200* r, void** out, size_t bytes, bool zero) {
@@ -421,7 +421,7 @@ static int build(glava_b200* r) {
         CU(cudaEventCreateWithFlags(&r->ev_free[i], cudaEventDisableTiming));
     }
     for (int i = 0; i < 2; ++i) for (int c = 0; c < 2; ++c) ALLOC(r->d_ring[i][c], (size_t) r->batch * n_in * 4, true);
-    if (r->p_user.bufscale > 1) { ALLOC(r->d_scaled[0], (size_t) r->batch * n * 4, true); ALLOC(r->d_scaled[1], (size_t) r->batch * n * 4, true); }
+    if (r->p_user.bufscale > 1 || r->p_user.transform_smooth == 2) { ALLOC(r->d_scaled[0], (size_t) r->batch * n * 4, true); ALLOC(r->d_scaled[1], (size_t) r->batch * n * 4, true); }
     if (r->interp_on) {
         for (int i = 0; i < 3; ++i) ALLOC(r->d_key[i], planes * n * 4, true);      // keyframes start at 0 (render.c:1681 calloc)
         r->key_start = 0; r->key_end = 1;
@@ -506,6 +506,9 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     r->sizereq.store(0);
     { const char* e = getenv("GLAVA_B200_TAP_KU"); r->tap_ku = e ? atoi(e) : 8; }
     r->fused_k5 = getenv("GLAVA_B200_FUSED_K5") != nullptr;
+    { const char* e = getenv("GLAVA_B200_SPLIT_EPI"); r->split_epilogue = e ? atoi(e) != 0 : false; }
+    { const char* e = getenv("GLAVA_B200_SPEC_OOP"); r->spec_oop = e ? atoi(e) : 0; }
+    { const char* e = getenv("GLAVA_B200_SPEC_T"); r->spec_t = e ? atoi(e) : 0; }
     r->no_texmm = getenv("GLAVA_B200_NO_TEXMM") != nullptr;
     r->kcounter = 0; r->d_scaled[0] = r->d_scaled[1] = nullptr; r->d_key[0] = r->d_key[1] = r->d_key[2] = nullptr;
     r->key_start = 0; r->key_end = 1; r->d_spec_cur = nullptr; r->d_ts_tab = nullptr; r->ts_asz = r->ts_lim = 0;
@@ -684,6 +687,19 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
         ++r->launches;
         d_l = r->d_scaled[0]; d_r = r->d_scaled[1];
     }
+    if (modified && p.transform_smooth == 2) {
+        // `#request transform <u> "smooth"` listed BEFORE "fft" (render.c:1218-1286): handle_audio applies it on the CPU to
+        // the (scaled) PCM ring, then meets "fft" and carries on as usual (render.c:2131-2156).  Here: on a copy of the
+        // rings (rd_update transforms the caller's buffers in place; this ABI leaves them alone)
+        const int chans = p.module == GLAVA_B200_MOD_WAVE ? 1 : 2;
+        const float* src[2] = { d_l, d_r };
+        for (int c = 0; c < chans; ++c) {
+            if (src[c] != r->d_scaled[c]) CU(cudaMemcpyAsync(r->d_scaled[c], src[c], (size_t) r->batch * p.n * 4, cudaMemcpyDeviceToDevice, r->spec_stream));
+            if ((rc = launch_transform_smooth(r->d_scaled[c], p.n, r->d_ts_tab, r->ts_asz, r->ts_lim, r->batch, r->spec_stream, nullptr, 0)) != 0) return rc;
+            ++r->launches;
+        }
+        d_l = r->d_scaled[0]; d_r = chans == 2 ? r->d_scaled[1] : r->d_scaled[0];
+    }
     float* chain_out = r->d_spec;                         // where the float chain result of this update goes
     if (r->interp_on) {
         int nxt = 0; while (nxt == r->key_start || nxt == r->key_end) ++nxt;
@@ -703,6 +719,7 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
         a.tap_ku = r->tap_ku;
         a.csr = (a.need && a.tap_tab && r->csr_in_smem) ? r->d_csr : nullptr; a.csr_bytes = r->csr_bytes; a.csr_idx_off = r->csr_idx_off; a.csr_off_off = r->csr_off_off;
         a.batch = r->batch; a.update = r->updates;
+        a.variant_oop = r->spec_oop; a.variant_t = r->spec_t;
         a.umask = nullptr; a.tex_prev = tex_half(r, r->tex_cur);
         if (mask || r->desync) { if ((rc = stage_umask(r, mask, &a.umask)) != 0) return rc; }
         const int F = p.avg_frames;
@@ -720,7 +737,17 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
         const bool split_k5 = p.smooth_pass && !a.need && !r->post_chain && !r->fused_k5 && !split_lazy;
         a.av_out = (split_k5 || split_lazy) ? r->d_av : nullptr;
         a.av_t_len = split_lazy ? r->av_t_len : 0;
+        // three-kernel form of the lazy pipeline-B update: transform_fft only in the plane-per-CTA kernel, the R16 state
+        // update as an elementwise kernel, K5 on (texel, stream) pairs.  (F = 1 has no ring: in-kernel form.)
+        const int epi8 = ((r->epi_n + 7) / 8) * 8;
+        const bool split_epi = split_lazy && is_fft && p.accel_fft && r->split_epilogue && epi8 > 0 && epi8 <= p.n && F >= 1;
+        a.fft_only = split_epi ? 1 : 0;
+        if (split_epi) a.epi_n = epi8;
         if ((rc = launch_spectrum(p, a, is_fft, r->spec_stream)) != 0) return rc;
+        if (split_epi) {
+            if ((rc = launch_epilogue_b(p, a, epi8, r->spec_stream)) != 0) return rc;
+            ++r->launches;
+        }
         if (split_lazy) {
             if ((rc = launch_k5_need(p, r->d_av, r->d_av_t, r->av_t_len, a.tex, r->batch, is_fft ? 2 : 1, r->d_csr, r->csr_bytes, r->csr_idx_off,
                                      r->csr_off_off, r->d_need, r->d_tap_wsum, r->need_count, r->spec_stream)) != 0) return rc;
@@ -731,7 +758,7 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
             if ((rc = launch_smooth_only(p, r->d_av, a.tex, r->batch * 2, r->spec_stream, &r->k5)) != 0) return rc;
             ++r->launches;
         }
-        if (r->post_chain && p.transform_smooth) {                          // render.c:694-718, after the module's chain
+        if (r->post_chain && p.transform_smooth == 1) {                     // render.c:694-718, after the module's chain
             if ((rc = launch_transform_smooth(chain_out, p.n, r->d_ts_tab, r->ts_asz, r->ts_lim, planes, r->spec_stream, a.umask)) != 0) return rc;
             ++r->launches;
         }

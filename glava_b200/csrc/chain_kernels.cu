@@ -38,9 +38,9 @@ int launch_bufscale(const float* in_l, const float* in_r, float* out_l, float* o
 // One CTA per plane: the lanes stage the plane's head in shared memory, one thread walks it.
 __global__ void __launch_bounds__(32)
 transform_smooth_kernel(float* __restrict__ planes, int n, const SmoothWin* __restrict__ tab, int asz, int lim,
-                        const uint32_t* __restrict__ umask) {
+                        const uint32_t* __restrict__ umask, int mask_shift) {
     extern __shared__ float ts_sm[];
-    if (umask && !(umask[blockIdx.x >> 1] >> 31)) return;      // stream without new audio: its buffer already holds the transformed result
+    if (umask && !(umask[blockIdx.x >> mask_shift] >> 31)) return;      // stream without new audio: its buffer already holds the transformed result
     float* b = planes + (size_t) blockIdx.x * n;
     for (int i = threadIdx.x; i < lim; i += 32) ts_sm[i] = b[i];
     __syncwarp();
@@ -50,13 +50,13 @@ transform_smooth_kernel(float* __restrict__ planes, int n, const SmoothWin* __re
 }
 
 int launch_transform_smooth(float* d_planes, int n, const void* d_tab, int asz, int lim, int count, void* stream,
-                            const uint32_t* d_umask) {
+                            const uint32_t* d_umask, int mask_shift) {
     const size_t smem = (size_t) lim * sizeof(float);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(transform_smooth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "transform_smooth smem attribute: %s", cudaGetErrorString(e));
     }
-    transform_smooth_kernel<<<count, 32, smem, (cudaStream_t) stream>>>(d_planes, n, (const SmoothWin*) d_tab, asz, lim, d_umask);
+    transform_smooth_kernel<<<count, 32, smem, (cudaStream_t) stream>>>(d_planes, n, (const SmoothWin*) d_tab, asz, lim, d_umask, mask_shift);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "transform_smooth kernel launch: %s", cudaGetErrorString(e));
     return 0;

@@ -862,6 +862,7 @@ int validate_params(const glava_b200_params* p) {
     if (p->bufscale < 1 || p->n % p->bufscale || p->n / p->bufscale < 256 || ((p->n / p->bufscale) & (p->n / p->bufscale - 1)))
         return bad("setbufsize / setbufscale must be a power of two >= 256");
     if (p->fr < 0.0f) return bad("fr must be >= 0");
+    if (p->transform_smooth < 0 || p->transform_smooth > 2) return bad("transform_smooth must be 0, 1 (after \"fft\") or 2 (before \"fft\")");
     if (p->transform_smooth && !(p->smooth_ratio > 0.0f)) return bad("setsmoothratio must be > 0");
     return GLAVA_B200_OK;
 }

@@ -67,6 +67,9 @@ struct SpectrumArgs {
     // shares the cursor `update % F`; else one word per stream, bit 31 = this stream has new audio, low 16 bits = its own
     // ring cursor (modified updates of THAT stream so far, mod F).  An unmodified stream's state is left alone and its
     // texture is carried from `tex_prev` (the half of the double buffer the previous raster read) into `tex`.
+    int variant_oop, variant_t; // kernel variant: out-of-place passes, threads per CTA (0 = the size's default)
+    int fft_only;               // 1: stop after transform_fft — `spec` (the leading epi_n bins) is all this launch produces; gravity /
+                                // average run as epilogue_b_kernel, K5 as k5_need_kernel (capi.cu run_update)
     int av_t_len;               // > 0: av_out receives only the leading av_t_len bins (need-list K5 as its own kernel downstream)
     const uint32_t* umask;      // [batch]
     const uint16_t* tex_prev;   // [batch*2][n]
@@ -114,6 +117,9 @@ int launch_smooth_only(const glava_b200_params& p, const uint16_t* d_in, uint16_
 int launch_k5_need(const glava_b200_params& p, const uint16_t* d_av, float* d_av_t, int av_t_len, uint16_t* d_tex, int batch, int channels,
                    const unsigned char* d_csr, int csr_bytes, int csr_idx_off, int csr_off_off, const int* d_need,
                    const float* d_wsum, int need_count, void* stream);
+// pipeline B epilogue as its own elementwise kernel: spec (transform_fft output) -> upload quantisation, K1 - K4 on the R16
+// state, pre-smoothing texels into av_out (leading `bins` of every plane; bins is a multiple of 8)
+int launch_epilogue_b(const glava_b200_params& p, const SpectrumArgs& a, int bins, void* stream);
 int launch_raster(const glava_b200_params& p, const RasterArgs& a, void* stream);
 int launch_bars_rowtab(const glava_b200_params& p, void* d_rowtab, void* stream);
 // geometry cache of the polar modules: box = {x0, y0, w, h}; returns bytes needed when d_geo == nullptr
@@ -128,7 +134,8 @@ int spectrum_threads(int n);
 int launch_bufscale(const float* in_l, const float* in_r, float* out_l, float* out_r, int batch, int n_in, int k,
                     int channels, void* stream);
 int launch_transform_smooth(float* d_planes, int n, const void* d_tab, int asz, int lim, int count, void* stream,
-                            const uint32_t* d_umask = nullptr);   // d_umask: SpectrumArgs::umask, planes of unmodified streams are skipped
+                            const uint32_t* d_umask = nullptr, int mask_shift = 1);   // d_umask: SpectrumArgs::umask, planes of unmodified
+                            // streams are skipped; stream of plane i = i >> mask_shift (1: interleaved [batch*2] planes, 0: one channel's [batch])
 int launch_upload(const float* d_s, const float* d_e, float mod, uint16_t* d_out, size_t total, void* stream);
 
 }  // namespace glb

@@ -199,6 +199,18 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
         if constexpr (OOP) run_passes_oop<M, T, 1>(bufA, bufB, first, reinterpret_cast<const cpx*>(a.twiddle), tid);
         else run_passes<M, T, 1>(buf, first, reinterpret_cast<const cpx*>(a.twiddle), tid);
 
+        if (a.fft_only) {
+            // transform_fft's tail only (render.c:842-846); the state update and K5 follow as full-occupancy kernels
+            const int lim = (a.epi_n > 0 && a.epi_n < N) ? a.epi_n : N;
+            float* const spec = a.spec + plane;
+            for (int n = tid; n < lim; n += T) {
+                cpx z = buf[fft_pad(n >> 1)];
+                spec[n] = fft_post((n & 1) ? z.y : z.x, n, N, p.fft_scale, p.fft_cutoff);
+            }
+            __syncthreads();
+            if (tid == 0 && u + (int) gridDim.x < units) issue_load(u + gridDim.x);
+            continue;
+        }
         if (!p.accel_fft) {
             // --- pipeline A: render.c:2149-2156 --------------------------------------------------
             const float g = p.gravity_step * (1.0f / p.ur);
@@ -497,9 +509,7 @@ static int launch_spectrum_fft(const glava_b200_params& p, const SpectrumArgs& a
 
 int launch_spectrum(const glava_b200_params& p, const SpectrumArgs& a, bool is_fft, void* stream) {
     cudaStream_t st = (cudaStream_t) stream;
-    static int tsel = -1, oop = -1;
-    if (tsel < 0) { tsel = 0; if (const char* e = getenv("GLAVA_B200_SPEC_T")) tsel = atoi(e); }
-    if (oop < 0) { oop = 0; if (const char* e = getenv("GLAVA_B200_SPEC_OOP")) oop = atoi(e); }
+    const int tsel = a.variant_t, oop = a.variant_oop;          // chosen per handle at creation (capi.cu)
 #define GLB_CASE(L) case (1 << L): return is_fft ? launch_spectrum_fft<L>(p, a, st, oop, tsel) : launch_spectrum_t<L, false>(p, a, st);
     switch (p.n) {
         GLB_CASE(8) GLB_CASE(9) GLB_CASE(10) GLB_CASE(11) GLB_CASE(12) GLB_CASE(13) GLB_CASE(14)
@@ -661,6 +671,83 @@ int launch_smooth_only(const glava_b200_params& p, const uint16_t* d_in, uint16_
 // of the next 32 taps (two coalesced loads) and the warp walks them by shuffle broadcast; per tap and stream one coalesced
 // read of the transposed pre-smoothing texels (exported as float: converted once by the producer, not once per tap) and the
 // ordered multiply-add of smooth_audio() (smooth.glsl:33-37).  S independent sums per lane share every broadcast.
+// Pipeline B's state update (render.c:2177-2267: R16 upload, K1 max, K2 gravity, K3 ring, K4 average) as an elementwise
+// kernel: one thread = 8 consecutive bins of one plane, every access a 16-byte vector (2 float4 of `spec`, one uint4 of each
+// R16 plane), 2 + 1 + (F - 1) independent loads in flight per thread, full occupancy.  Inside the spectrum kernel the same
+// work ran on the few warps of a plane's CTA behind the FFT's barriers: latency bound, 7x off the traffic it moves.
+// Arithmetic = the in-kernel epilogue's (gravity_b, newest-first weighted average), bit for bit.
+template <int FT>
+__global__ void __launch_bounds__(128)
+epilogue_b_kernel(const __grid_constant__ SpectrumArgs a, int n, int bins, int F, float diff) {
+    const int plane = blockIdx.y, g8 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n0 = g8 * 8;
+    if (n0 >= bins) return;
+    const uint32_t um = a.umask ? __ldg(a.umask + (plane >> 1)) : 0x80000000u;
+    if (!(um >> 31)) return;                                   // stream without new audio: state and texels stay
+    const int out_idx = a.umask ? (int) (um & 0xffffu) : (int) (a.update % (unsigned long long) F);
+    const size_t base = (size_t) plane * n + n0;
+    const float4 s0 = *reinterpret_cast<const float4*>(a.spec + base), s1 = *reinterpret_cast<const float4*>(a.spec + base + 4);
+    uint16_t* const grs = a.gr_store + base;
+    uint16_t* const ring = a.ring_u + (size_t) plane * F * n + n0;
+    const int FF = FT ? FT : F;
+    uint4 gold = *reinterpret_cast<const uint4*>(grs);
+    uint4 rg[FT ? FT : 1];
+    if (FT > 1) {
+#pragma unroll
+        for (int i = 1; i < FT; ++i) { int fr = out_idx - i; if (fr < 0) fr += FT; rg[i] = *reinterpret_cast<const uint4*>(ring + (size_t) fr * n); }
+    }
+    const float v[8] = { s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w };
+    const uint16_t* go = reinterpret_cast<const uint16_t*>(&gold);
+    uint4 gnew, tex;
+    uint16_t* gn = reinterpret_cast<uint16_t*>(&gnew); uint16_t* tx = reinterpret_cast<uint16_t*>(&tex);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const uint32_t gq = gravity_b(unorm16(v[e]), go[e], diff);
+        gn[e] = (uint16_t) gq;
+        uint32_t texel = gq;
+        if (FF > 1) {
+            float r = 0.0f;
+            if (FT > 1) {
+#pragma unroll
+                for (int i = 0; i < FT; ++i) {                 // t0 = most recent (render.c:2250-2255)
+                    const float t = from16(i == 0 ? gq : (uint32_t) reinterpret_cast<const uint16_t*>(&rg[i])[e]);
+                    if (a.avg_b_windowed) r += a.avg_w_b[i] * t; else r += t;
+                }
+            } else {
+                for (int i = 0; i < F; ++i) {
+                    int fr = out_idx - i; if (fr < 0) fr += F;
+                    const float t = from16(i == 0 ? gq : (uint32_t) ring[(size_t) fr * n + e]);
+                    if (a.avg_b_windowed) r += a.avg_w_b[i] * t; else r += t;
+                }
+            }
+            texel = unorm16(r / (float) FF);
+        }
+        tx[e] = (uint16_t) texel;
+    }
+    *reinterpret_cast<uint4*>(grs) = gnew;
+    if (FF > 1) *reinterpret_cast<uint4*>(ring + (size_t) out_idx * n) = gnew;
+    *reinterpret_cast<uint4*>(a.av_out + base) = tex;
+}
+
+int launch_epilogue_b(const glava_b200_params& p, const SpectrumArgs& a, int bins, void* stream) {
+    const int planes = a.batch * 2, F = p.avg_frames;
+    const float diff = p.gravity_step * (1.0f / p.ur);
+    dim3 grid((bins / 8 + 127) / 128, planes);
+    cudaStream_t st = (cudaStream_t) stream;
+#define GLB_EPI(FT) epilogue_b_kernel<FT><<<grid, 128, 0, st>>>(a, p.n, bins, F, diff)
+    switch (F) {
+        case 5: GLB_EPI(5); break;                              // shipped default (smooth_parameters.glsl:56)
+        case 6: GLB_EPI(6); break;                              // compiled-in default (render.c:912)
+        case 3: GLB_EPI(3); break;
+        case 4: GLB_EPI(4); break;
+        default: GLB_EPI(0); break;
+    }
+#undef GLB_EPI
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "epilogue kernel launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 // [plane = stream * 2 + ch][bin] u16  ->  [ch][bin][stream] float (from16 applied once here, not once per tap): 32 x 32 tiles
 // through shared memory, both sides coalesced.  A plane-owning spectrum CTA could only write its own stream's column of the
 // transposed layout — 4-byte stores 4 KB apart, measured ~100 us at setbufsize 8192 — so the transposition is its own pass.

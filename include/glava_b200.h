@@ -137,9 +137,11 @@ typedef struct {
                                  (render.c:2161-2168) */
     float fr;                 /* glava_b200_update calls per second, the reference's measured gl->fr
                                  (render.c:2386); setframerate when > 0; 0 = same as ur */
-    int   transform_smooth;   /* `#request transform <uniform> "smooth"` appended to the module's chain:
-                                 transform_smooth (render.c:694-718); forces the CPU-order chain (pipeline A,
-                                 render.c:2143-2154) */
+    int   transform_smooth;   /* `#request transform <uniform> "smooth"` (render.c:1218-1286; transform_smooth, render.c:694-718)
+                                 in the module's bind list — the module shaders are not read here, so the position is a parameter:
+                                 1 = after "fft" ... "avg": forces the CPU-order chain (pipeline A, render.c:2143-2154);
+                                 2 = BEFORE "fft": applied to the (scaled) PCM ring on the CPU side of handle_audio, the fft chain
+                                     and setaccelfft's GL passes follow unchanged (render.c:2131-2156) */
     float smooth_distance;    /* setsmooth       (render.c:917,1201) */
     float smooth_ratio;       /* setsmoothratio  (render.c:918,1204) */
     /* compiled colour expressions (mode 2 of the colour they belong to; n_ops == 0 otherwise) */

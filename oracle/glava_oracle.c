@@ -447,13 +447,13 @@ orc_stream* orc_stream_new(const orc_params* p, const orc_ext* x) {
     s->n_in = p->n; s->p.n = p->n / s->x.bufscale;
     s->is_fft = p->module != ORC_MOD_WAVE;
     /* a transform after "fft" makes the bind fall back to the CPU chain (render.c:2143-2154) */
-    if (s->x.transform_smooth && s->is_fft) s->p.accel_fft = 0;
+    if (s->x.transform_smooth == 1 && s->is_fft) s->p.accel_fft = 0;        /* (2 = "smooth" BEFORE "fft": applied to the PCM, the fft chain stays where it is) */
     /* interpolation is forced off when the fft chain is pushed to the GPU passes (render.c:2161-2168)
        and when the update rate is close to the frame rate (render.c:1761-1763) */
     float fr = s->x.fr > 0 ? s->x.fr : p->ur;
     s->x.fr = fr;
     s->interp_on = s->x.interpolate && !(s->p.accel_fft && s->is_fft) && (p->ur / fr) <= 0.9F;
-    s->post_chain = s->x.transform_smooth || s->interp_on;
+    s->post_chain = s->x.transform_smooth == 1 || s->interp_on;
     size_t n = (size_t) s->p.n;
     for (int c = 0; c < 2; ++c) {
         s->ch[c] = orc_chan_new(&s->p);
@@ -485,12 +485,19 @@ void orc_stream_update(orc_stream* s, const float* lb, const float* rb, int modi
         if (modified) {
             const float* src = in[c];
             if (s->x.bufscale > 1) { orc_bufscale(in[c], s->n_in, s->x.bufscale, s->scaled); src = s->scaled; }
+            if (s->x.transform_smooth == 2) {
+                /* `#request transform <u> "smooth"` listed BEFORE "fft" (render.c:1218-1286): handle_audio applies it on the
+                 * CPU to the (scaled) PCM, then meets "fft" and carries on as usual — GPU passes under setaccelfft
+                 * (render.c:2131-2156) */
+                if (src != s->scaled) { memcpy(s->scaled, src, sizeof(float) * (size_t) n); src = s->scaled; }
+                orc_transform_smooth(s->scaled, n, s->x.smooth_distance, s->x.smooth_ratio);
+            }
             if (!s->post_chain) {
                 orc_chan_update(s->ch[c], &s->p, src, s->is_fft, s->last[c], s->tex[c]);
             } else {
                 orc_params q = s->p; q.smooth_pass = 0;                     /* chain only; upload + K5 below */
                 orc_chan_update(s->ch[c], &q, src, s->is_fft, s->last[c], pre);
-                if (s->x.transform_smooth)
+                if (s->x.transform_smooth == 1)
                     orc_transform_smooth(s->last[c], n, s->x.smooth_distance, s->x.smooth_ratio);
             }
         }

@@ -163,3 +163,42 @@ def test_bad_arguments_fail_loudly(built):
         assert rc != 0 and b"bsz" in r._L.glava_b200_last_error()
     with pytest.raises(g.GlavaError):
         g.Renderer(g.default_params("bars", n=1000), batch=1)
+
+
+@pytest.mark.parametrize("n,w", [(1024, 320), (4096, 1920), (8192, 1920)])
+def test_kernel_variants_give_identical_textures_and_frames(built, monkeypatch, n, w):
+    """the spectrum path exists in several launch structures (tuning knobs): plane-per-CTA kernel with in-kernel
+    epilogue and K5; K5 as its own kernel over (texel, stream) pairs; the R16 state update as an elementwise kernel; FFT passes
+    in place / out of place, 128 / 256 threads.  All of them are the same arithmetic: textures and frames must be identical."""
+    batch = 70                                                    # not a multiple of 32: partial stream groups in k5_need_kernel
+    p = g.default_params("bars", n=n, w=w, h=32, lazy_smooth=1)
+    rng = np.random.default_rng(n)
+    seq = [((rng.random((batch, n), np.float32) - 0.5) * 0.4, (rng.random((batch, n), np.float32) - 0.5) * 0.4) for _ in range(7)]
+    masks = [None, None, rng.random(batch) < 0.5, None, rng.random(batch) < 0.5, None, None]
+
+    def run(env):
+        for k in ("GLAVA_B200_K5_SPLIT", "GLAVA_B200_SPLIT_EPI", "GLAVA_B200_SPEC_OOP", "GLAVA_B200_SPEC_T"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with g.Renderer(p, batch=batch) as r:
+            for (lb, rb), m in zip(seq, masks):
+                if m is None:
+                    r.update(lb, rb, True)
+                else:
+                    r.update_masked(lb, rb, m)
+            tl, tr = r.textures()
+            need = tl.any(axis=0) | tr.any(axis=0)                 # lazy: only the sampled texels are defined
+            return tl[:, need], tr[:, need], [r.readback(s) for s in (0, 33, batch - 1)], r.spectrum()
+
+    base = run({"GLAVA_B200_K5_SPLIT": "0"})
+    assert base[0].any()
+    for env in ({"GLAVA_B200_K5_SPLIT": "1"}, {"GLAVA_B200_K5_SPLIT": "1", "GLAVA_B200_SPLIT_EPI": "1"},
+                {"GLAVA_B200_K5_SPLIT": "1", "GLAVA_B200_SPLIT_EPI": "1", "GLAVA_B200_SPEC_OOP": "1", "GLAVA_B200_SPEC_T": "256"},
+                {"GLAVA_B200_K5_SPLIT": "0", "GLAVA_B200_SPEC_OOP": "1", "GLAVA_B200_SPEC_T": "128"}):
+        got = run(env)
+        assert np.array_equal(got[0], base[0]) and np.array_equal(got[1], base[1]), env
+        for a, b in zip(got[2], base[2]):
+            assert np.array_equal(a, b), env
+        if "GLAVA_B200_SPLIT_EPI" not in env:                      # (the three-kernel form writes only the bins that matter into `spec`)
+            assert np.array_equal(got[3][0], base[3][0]), env

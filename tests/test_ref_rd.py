@@ -308,6 +308,41 @@ def test_smooth_transform_after_fft_forces_the_cpu_order_chain(rd, tmp_path):
         r.close()
 
 
+@pytest.mark.parametrize("accel", ["true", "false"])
+def test_smooth_transform_before_fft_runs_on_the_pcm(rd, tmp_path, accel):
+    """a module whose bind lists "smooth" BEFORE "window" / "fft": handle_audio applies it on the CPU to the PCM ring, then
+    meets "fft" and carries on as usual — GL passes under setaccelfft (the upload is transform_fft of the smoothed ring),
+    the whole CPU chain otherwise (render.c:2131-2156).  transform_smooth = 2 in the oracle / product."""
+    from oracle.oracle import Oracle
+    src = open(os.path.join(REF_SHADERS, "bars", "1.frag")).read()
+    for ch in ("audio_l", "audio_r"):
+        anchor = f'#request transform {ch} "window"\n'
+        assert anchor in src
+        src = src.replace(anchor, f'#request transform {ch} "smooth"\n' + anchor)
+    d = tmp_path / "u"
+    paths = [_user_dir(d, {"rc.glsl": "#request mod bars\n#request setbufsize 1024\n#request setinterpolate false\n"
+                                     f"#request setaccelfft {accel}\n#request setsmooth 0.02\n#request setsmoothratio 3.0\n"}), REF_SHADERS]
+    os.unlink(d / "bars"); (d / "bars").mkdir()
+    for f in os.listdir(os.path.join(REF_SHADERS, "bars")):
+        (d / "bars" / f).write_text(src if f == "1.frag" else open(os.path.join(REF_SHADERS, "bars", f)).read())
+    r = rd(paths)
+    try:
+        p = g.load_config(paths)
+        assert p.accel_fft == (1 if accel == "true" else 0)
+        p.ur = 86.1328125
+        st = OracleStream(Oracle("libm"), params_from(p), OrcExt(bufscale=1, interpolate=0, fr=0.0, transform_smooth=2,
+                                                                 smooth_distance=p.smooth_distance, smooth_ratio=p.smooth_ratio))
+        r.set_rates(86.1328125, 86.1328125)
+        rng = np.random.default_rng(23)
+        for k in range(6):
+            pl = (rng.standard_normal(p.n) * 0.2).astype(np.float32); pr = (rng.standard_normal(p.n) * 0.2).astype(np.float32)
+            up = r.frame(pl, pr)
+            sl, sr, _, _ = st.update(pl, pr, True)
+            assert np.array_equal(up[0], sl, equal_nan=True) and np.array_equal(up[1], sr, equal_nan=True), k
+    finally:
+        r.close()
+
+
 @pytest.mark.parametrize("rc_extra,sp,state", [
     ("", "", (1, 0)),                                                                       # shipped: consistent
     ("#request setsmoothpass false\n", "#request setsmoothpass false\n", (0, 0)),           # off everywhere: shader smooths
