@@ -506,9 +506,12 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     r->sizereq.store(0);
     { const char* e = getenv("GLAVA_B200_TAP_KU"); r->tap_ku = e ? atoi(e) : 8; }
     r->fused_k5 = getenv("GLAVA_B200_FUSED_K5") != nullptr;
-    { const char* e = getenv("GLAVA_B200_SPLIT_EPI"); r->split_epilogue = e ? atoi(e) != 0 : false; }
-    { const char* e = getenv("GLAVA_B200_SPEC_OOP"); r->spec_oop = e ? atoi(e) : 0; }
-    { const char* e = getenv("GLAVA_B200_SPEC_T"); r->spec_t = e ? atoi(e) : 0; }
+    // Launch structure of the lazy pipeline-B update: wherever the need-list K5 runs as its own kernel (auto:
+    // setbufsize >= 8192) the R16 state update does too, and at 8192 the FFT passes run out of place with 256 threads —
+    // the measured optima (tools/variant_sweep.sh).  GLAVA_B200_SPLIT_EPI / _SPEC_OOP / _SPEC_T override.
+    { const char* e = getenv("GLAVA_B200_SPLIT_EPI"); r->split_epilogue = e ? atoi(e) != 0 : true; }
+    { const char* e = getenv("GLAVA_B200_SPEC_OOP"); r->spec_oop = e ? atoi(e) : (params->n == 8192 ? 1 : 0); }
+    { const char* e = getenv("GLAVA_B200_SPEC_T"); r->spec_t = e ? atoi(e) : (params->n == 8192 ? 256 : 0); }
     r->no_texmm = getenv("GLAVA_B200_NO_TEXMM") != nullptr;
     r->kcounter = 0; r->d_scaled[0] = r->d_scaled[1] = nullptr; r->d_key[0] = r->d_key[1] = r->d_key[2] = nullptr;
     r->key_start = 0; r->key_end = 1; r->d_spec_cur = nullptr; r->d_ts_tab = nullptr; r->ts_asz = r->ts_lim = 0;

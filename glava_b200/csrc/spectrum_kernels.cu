@@ -779,7 +779,8 @@ k5_need_kernel(const float* __restrict__ av_t, int av_t_len, uint16_t* __restric
     const int groups = (batch + 32 * S - 1) / (32 * S);
     // consecutive warps take consecutive texels of the same stream group: their tap windows overlap, L1 serves the re-reads
     const int gw = blockIdx.x * K5N_WARPS + warp;
-    const int k = gw % need_count, g = (gw / need_count) % groups, ch = gw / (need_count * groups);
+    // (the last texels of the list have the widest windows — scale_audio is log-like: they go first, the short ones fill the tail)
+    const int k = need_count - 1 - gw % need_count, g = (gw / need_count) % groups, ch = gw / (need_count * groups);
     if (ch >= channels) return;
     const int x = __ldg(need + (size_t) ch * need_count + k);
     if (x < 0 || x >= n) return;
@@ -799,22 +800,27 @@ k5_need_kernel(const float* __restrict__ av_t, int av_t_len, uint16_t* __restric
     for (int o = o0; o < o1; o += 32) {
         const int mine = o + lane;
         const int   my_i = mine < o1 ? (int) __ldg(ti + mine) * batch : 0;     // (a tap outside the texture is stored as index 0, weight 0)
-        const float my_w = mine < o1 ? __ldg(tw + mine) : 0.0f;
+        const float my_w = mine < o1 ? __ldg(tw + mine) : 0.0f;                 // (past the end of the list: index 0, weight 0 — adds +0)
         const int cnt = min(32, o1 - o);
-        auto tap = [&](int j) {
-            const int i = __shfl_sync(0xffffffffu, my_i, j);
-            const float w = __shfl_sync(0xffffffffu, my_w, j);
-            float t[S];
+        // groups of 8 taps: all 8 * S texel loads are issued before the first dependent add (the sums are serial, the
+        // loads are not); a short last group runs past the list with weight 0 only when that cannot change a bit
+        for (int j0 = 0; j0 < cnt; j0 += 8) {
+            float t[8][S], w[8];
 #pragma unroll
-            for (int q = 0; q < S; ++q) t[q] = __ldg(col[q] + i);
+            for (int j = 0; j < 8; ++j) {
+                const int i = __shfl_sync(0xffffffffu, my_i, j0 + j);
+                w[j] = __shfl_sync(0xffffffffu, my_w, j0 + j);
 #pragma unroll
-            for (int q = 0; q < S; ++q) { if (MODE == 0) acc[q].avg += t[q] * w; else acc[q].add_noweight(t[q], w); }
-        };
-        if (cnt == 32) {
-#pragma unroll 8
-            for (int j = 0; j < 32; ++j) tap(j);
-        } else {
-            for (int j = 0; j < cnt; ++j) tap(j);
+                for (int q = 0; q < S; ++q) t[j][q] = __ldg(col[q] + i);
+            }
+            const int live = min(8, cnt - j0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j < live) {
+#pragma unroll
+                    for (int q = 0; q < S; ++q) { if (MODE == 0) acc[q].avg += t[j][q] * w[j]; else acc[q].add_noweight(t[j][q], w[j]); }
+                }
+            }
         }
     }
     const float weight = __ldg(wsum + (size_t) ch * need_count + k);
@@ -838,7 +844,8 @@ int launch_k5_need(const glava_b200_params& p, const uint16_t* d_av, float* d_av
         if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "transpose kernel launch: %s", cudaGetErrorString(e));
     }
     // streams per lane: 4 sums share every tap broadcast once the batch is large enough to still fill the device
-    const int S = batch >= 512 ? 4 : (batch >= 128 ? 2 : 1);
+    int S = 1;                                                   // measured at batch 1024: occupancy beats sharing (S = 4 was 2x slower)
+    if (const char* e = getenv("GLAVA_B200_K5N_S")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) S = v; }
     const int groups = (batch + 32 * S - 1) / (32 * S);
     const long long warps = (long long) channels * need_count * groups;
     const unsigned grid = (unsigned) ((warps + K5N_WARPS - 1) / K5N_WARPS);

@@ -194,3 +194,32 @@ def test_frame_event_wait_and_device_pointers(built):
         assert r.frame_device(4) is None
         h = r.framebuffer_ipc()
         assert len(h) == 64 and any(h)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("accel", [0, 1])
+def test_smooth_before_fft_equals_the_oracle_stream(orc_pm, built, accel):
+    """transform_smooth = 2: "smooth" listed BEFORE "fft" in the module's bind (render.c:1218-1286) — transform_smooth on the
+    PCM ring, then the module's chain as usual (pinned against the reference's rd_update in tests/test_ref_rd.py)"""
+    from oracle.oracle import OracleStream, ext_from, params_from
+    n, batch = 1024, 3
+    p = g.default_params("bars", n=n, w=64, h=32, transform_smooth=2, smooth_distance=0.02, smooth_ratio=3.0, accel_fft=accel)
+    rng = np.random.default_rng(31 + accel)
+    sts = [OracleStream(orc_pm, params_from(p), ext_from(p)) for _ in range(batch)]
+    with g.Renderer(p, batch=batch) as r:
+        for _ in range(5):
+            lb = (rng.standard_normal((batch, n)) * 0.2).astype(np.float32); rb = (rng.standard_normal((batch, n)) * 0.2).astype(np.float32)
+            keep = lb.copy()
+            r.update(lb, rb, True)
+            want = [st.update(lb[s], rb[s], True) for s, st in enumerate(sts)]
+            assert np.array_equal(lb, keep)                                    # the caller's rings are left alone
+        sl, sr = r.spectrum(); tl, tr = r.textures()
+        for s in range(batch):
+            # transform_smooth leaves NaN in b[0] (0 / 0, render.c:694-718) and the FFT spreads it: WHICH outputs turn NaN
+            # depends on the butterfly network (the reference's Danielson-Lanczos loop multiplies by every twiddle, trivial
+            # ones included; the Stockham passes do not) — an artefact of a degenerate configuration, so only the bins that
+            # are finite on both sides are compared
+            ok = np.isfinite(want[s][0]) & np.isfinite(sl[s])
+            assert np.isnan(sl[s][0]) and np.isnan(want[s][0][0])
+            if ok.any():
+                assert np.abs(sl[s][ok] - want[s][0][ok]).max() <= 1e-5 * max(np.abs(want[s][0][ok]).max(), 1e-30)
