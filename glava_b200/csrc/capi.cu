@@ -97,6 +97,7 @@ struct glava_b200 {
     bool k5_split_lazy, csr_in_smem, split_epilogue; int av_t_len; float* d_av_t; int spec_oop, spec_t;   // need-list K5 as its own kernel (k5_need_kernel)
     unsigned char* d_csr; int csr_bytes, csr_idx_off, csr_off_off;   // the same taps, texel-major, for the shared-memory path
     void* d_geo; int geo_box[4];   // polar geometry cache (radial / circle), see raster_kernels.cu
+    void* d_ctile; int ctile_nx, ctile_count;   // circle: per-tile texel reference ranges (launch_circle_tiles)
     uint32_t* d_texmm;             // circle: per-plane {min, max} of the sampled texture, refreshed before each raster
     // state + outputs
     float* d_spec; float* d_applied; float* d_ring_f;
@@ -319,6 +320,7 @@ static int build_tables(glava_b200* r) {
     r->d_k5_blk = r->d_k5_ent = r->d_k5_wsum = nullptr; memset(&r->k5, 0, sizeof(r->k5));
     dev_free(r, r->d_csr); r->d_csr = nullptr; r->csr_bytes = r->csr_idx_off = r->csr_off_off = 0;
     dev_free(r, r->d_av_t); r->d_av_t = nullptr;
+    dev_free(r, r->d_ctile); r->d_ctile = nullptr; r->ctile_nx = r->ctile_count = 0;
     r->k5_split_lazy = false; r->csr_in_smem = false; r->av_t_len = 0;
     r->d_need = nullptr; r->need_count = 0; r->d_tap_tab = nullptr; r->d_tap_cnt = nullptr; r->d_tap_wsum = nullptr;
     r->tap_max = 0; r->epi_n = 0; r->d_geo = nullptr; r->geo_box[0] = r->geo_box[1] = r->geo_box[2] = r->geo_box[3] = 0;
@@ -383,6 +385,14 @@ static int build_tables(glava_b200* r) {
             if ((rc = dev_alloc(r, &r->d_geo, bytes, false)) != 0) return rc;
             if ((rc = launch_polar_geo(p, r->d_geo, r->geo_box, r->stream)) != 0) return rc;
             ++r->launches;
+            if (p.module == GLAVA_B200_MOD_CIRCLE && !getenv("GLAVA_B200_NO_CTILE")) {
+                int ntx = 0, nty = 0;
+                const size_t tb = circle_tile_bytes(p, &ntx, &nty);
+                if ((rc = dev_alloc(r, &r->d_ctile, tb, false)) != 0) return rc;
+                if ((rc = launch_circle_tiles(p, r->d_geo, r->geo_box, r->d_ctile, r->stream)) != 0) return rc;
+                r->ctile_nx = ntx; r->ctile_count = ntx * nty;
+                r->launches += 2;
+            }
         }
     }
     CU(cudaStreamSynchronize(r->stream));
@@ -465,7 +475,7 @@ static int build(glava_b200* r) {
     }
     ALLOC(r->d_tex, 2 * planes * n * 2, true);
     ALLOC(r->d_av, planes * n * 2, true);
-    ALLOC(r->d_texmm, planes * 2 * sizeof(uint32_t), true);          // double-buffered: spectrum i+1 writes one half while raster i reads the other
+    ALLOC(r->d_texmm, planes * GLB_TEXMM_STRIDE * sizeof(uint32_t), true);          // double-buffered: spectrum i+1 writes one half while raster i reads the other
     ALLOC(r->d_rowtab, (size_t) p.h * 8, true);
     // framebuffers: [slots][h][w] RGBA8
     size_t frame = (size_t) p.w * p.h * 4;
@@ -522,6 +532,7 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     r->d_csr = nullptr; r->csr_bytes = r->csr_idx_off = r->csr_off_off = 0;
     r->d_k5_blk = r->d_k5_ent = r->d_k5_wsum = nullptr; memset(&r->k5, 0, sizeof(r->k5));
     r->k5_split_lazy = false; r->csr_in_smem = false; r->av_t_len = 0; r->d_av_t = nullptr;
+    r->d_ctile = nullptr; r->ctile_nx = r->ctile_count = 0;
     r->d_geo = nullptr; r->geo_box[0] = r->geo_box[1] = r->geo_box[2] = r->geo_box[3] = 0;
     r->d_spec = r->d_applied = r->d_ring_f = nullptr; r->d_gr_store = r->d_ring_u = r->d_tex = nullptr; r->d_av = nullptr; r->d_texmm = nullptr; r->d_fb = nullptr;
     for (int i = 0; i < 2; ++i) { r->d_pcm[i][0] = r->d_pcm[i][1] = nullptr; r->ev_copied[i] = r->ev_free[i] = nullptr; }
@@ -807,7 +818,7 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
     ra.rowtab = (p.module == GLAVA_B200_MOD_BARS || p.module == GLAVA_B200_MOD_GRAPH) ? r->d_rowtab : nullptr;
     ra.batch = r->batch; ra.slots = r->slots; ra.stream0 = 0;
     ra.geo = r->d_geo; ra.gx0 = r->geo_box[0]; ra.gy0 = r->geo_box[1]; ra.gw = r->geo_box[2]; ra.gh = r->geo_box[3];
-    ra.texmm = nullptr;
+    ra.texmm = nullptr; ra.ctile = nullptr; ra.ctile_zero = nullptr; ra.ctile_nx = 0;
     // params.shader_pre_smoothed: the module's stage-1 shader believes something else about its textures than what the
     // K5 pass did.  Only the raster launch sees that belief (as its smooth_pass); everything before it follows the real one.
     glava_b200_params pr_store;
@@ -820,6 +831,7 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
         if ((rc = launch_texmm(p, ra.tex, r->d_texmm, r->batch * 2, r->stream)) != 0) return rc;
         ++r->launches;
         ra.texmm = r->d_texmm;
+        if (r->d_ctile) { ra.ctile = (const int4*) r->d_ctile; ra.ctile_zero = (const int*) ((const int4*) r->d_ctile + r->ctile_count); ra.ctile_nx = r->ctile_nx; }
     }
     if (r->timing && (rc = timing_mark(r->ev_ras, r->stream)) != 0) return rc;
     if ((rc = launch_raster(*pr, ra, r->stream)) != 0) return rc;

@@ -87,8 +87,13 @@ struct RasterArgs {
     // CircleGeo, 16 bytes each) over the bounding box of the disc that can be non-zero; may be null
     const void* geo;
     int       gx0, gy0, gw, gh;  // box origin and size in pixels (gx0, gw multiples of 4)
-    const uint32_t* texmm;       // circle: [batch*2][2] {min, max} texel of each plane of `tex` (may be null)
+    const uint32_t* texmm;       // circle: per plane of `tex` {min, max} followed by GLB_CIRCLE_NB bucket {min, max} pairs (may be null)
+    // circle: per 128 x 8 tile (+ 1-pixel halo) the range of texel indices its cells reference, {lo_l, hi_l, lo_r, hi_r}
+    // (lo > hi: none), and whether any reference is out of range (reads 0); audio-independent, built with the cache
+    const int4* ctile; const int* ctile_zero; int ctile_nx;
 };
+#define GLB_CIRCLE_NB 128                         // texel buckets per plane (n / 128 texels each)
+#define GLB_TEXMM_STRIDE (2 + 2 * GLB_CIRCLE_NB)  // u32 per plane
 
 // ---- kernel launchers (spectrum_kernels.cu, raster_kernels.cu); `stream` is a cudaStream_t passed as void* ------------------
 int launch_spectrum(const glava_b200_params& p, const SpectrumArgs& a, bool is_fft, void* stream);
@@ -126,6 +131,9 @@ int launch_bars_rowtab(const glava_b200_params& p, void* d_rowtab, void* stream)
 size_t polar_geo_box(const glava_b200_params& p, int box[4]);
 int launch_texmm(const glava_b200_params& p, const uint16_t* d_tex, uint32_t* d_out, int planes, void* stream);
 int launch_polar_geo(const glava_b200_params& p, void* d_geo, const int box[4], void* stream);
+// circle: the per-tile texel reference ranges from the finished cache; d_tiles = int4[ntx * nty] followed by int[ntx * nty]
+size_t circle_tile_bytes(const glava_b200_params& p, int* ntx, int* nty);
+int launch_circle_tiles(const glava_b200_params& p, const void* d_geo, const int box[4], void* d_tiles, void* stream);
 int launch_fifo_ingest(const glava_b200_params& p, const void* d_chunks, bool float_in, int frames, const float* src_l, const float* src_r,
                        float* dst_l, float* dst_r, int batch, void* stream);
 int spectrum_smem_bytes(int n);

@@ -309,9 +309,9 @@ raster_circle_kernel(const __grid_constant__ RasterArgs a, const __grid_constant
     float reach = circle_reach(p);
     float inner = p.circle_radius - p.circle_line / 2.0f - 2.0f;
     if (a.texmm) {
-        const uint32_t* mm = a.texmm + (size_t) stream * 4;             // {min, max} of plane l, {min, max} of plane r
-        const float f0 = from16(min(__ldg(mm + 0), __ldg(mm + 2))) * p.circle_amplify;
-        const float f1 = from16(max(__ldg(mm + 1), __ldg(mm + 3))) * p.circle_amplify;
+        const uint32_t* mm = a.texmm + (size_t) stream * 2 * GLB_TEXMM_STRIDE;     // plane l, then plane r: {min, max} first
+        const float f0 = from16(min(__ldg(mm + 0), __ldg(mm + GLB_TEXMM_STRIDE))) * p.circle_amplify;
+        const float f1 = from16(max(__ldg(mm + 1), __ldg(mm + GLB_TEXMM_STRIDE + 1))) * p.circle_amplify;
         const float vlo = fminf(fminf(f0, f1), 0.0f), vhi = fmaxf(fmaxf(f0, f1), 0.0f);
         const float hl3 = fabsf(p.circle_line) / 2.0f + 3.0f;
         reach = fminf(reach, p.circle_radius + vhi + hl3);
@@ -348,7 +348,32 @@ raster_circle_kernel(const __grid_constant__ RasterArgs a, const __grid_constant
         const float by0 = (float) (ty0 - 1) - cy, by1 = (float) (ty0 + CIRCLE_TH) - cy;
         const float ny = (by0 > 0.0f) ? by0 : ((by1 < 0.0f) ? -by1 : 0.0f);
         const float fym = fmaxf(fabsf(by0), fabsf(by1));
-        const bool tile_dead = (nx * nx + ny * ny > reach * reach) || (inner > 0.0f && fxm * fxm + fym * fym < inner * inner);
+        bool tile_dead = (nx * nx + ny * ny > reach * reach) || (inner > 0.0f && fxm * fxm + fym * fym < inner * inner);
+        if (!tile_dead && a.ctile && a.texmm) {
+            // the curve inside THIS tile's angular range: min / max over the texel buckets its cells can reference.  Every warp
+            // reduces the same few buckets (no barrier; the outcome is CTA-uniform by construction)
+            const int ti = (blockIdx.y * tiles_per_cta + it) * a.ctile_nx + blockIdx.x;
+            const int4 tr = __ldg(a.ctile + ti);
+            const int lane = threadIdx.x & 31, bs = t.n / GLB_CIRCLE_NB;
+            const uint32_t* ml = a.texmm + (size_t) stream * 2 * GLB_TEXMM_STRIDE + 2;
+            const uint32_t* mr = ml + GLB_TEXMM_STRIDE;
+            uint32_t lo = 65535u, hi = 0u;
+            bool any = __ldg(a.ctile_zero + ti) != 0;
+            if (any) lo = 0u;                                   // an out-of-range reference reads 0
+            if (tr.y >= tr.x) { any = true; for (int b = tr.x / bs + lane; b <= tr.y / bs; b += 32) { lo = min(lo, __ldg(ml + 2 * b)); hi = max(hi, __ldg(ml + 2 * b + 1)); } }
+            if (tr.w >= tr.z) { any = true; for (int b = tr.z / bs + lane; b <= tr.w / bs; b += 32) { lo = min(lo, __ldg(mr + 2 * b)); hi = max(hi, __ldg(mr + 2 * b + 1)); } }
+#pragma unroll
+            for (int k = 16; k > 0; k >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, k)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, k)); }
+            if (!any) tile_dead = true;                         // no cell of the tile (or its halo) can be lit
+            else {
+                if (hi < lo) hi = lo;
+                const float g0 = from16(lo) * p.circle_amplify, g1 = from16(hi) * p.circle_amplify;
+                const float tlo = fminf(g0, g1), thi = fmaxf(g0, g1);
+                const float hl3 = fabsf(p.circle_line) / 2.0f + 3.0f;
+                const float dnear = sqrtf(nx * nx + ny * ny) - p.circle_radius, dfar = sqrtf(fxm * fxm + fym * fym) - p.circle_radius;
+                if (dnear > thi + hl3 || (!p.circle_fill && dfar < tlo - hl3)) tile_dead = true;
+            }
+        }
         if (!tile_dead) {
             // (batching the geometry loads of a thread's 5-6 cells ahead of the dependent texel fetches was
             // measured slower: 64 -> 106 registers, half the resident warps)
@@ -436,19 +461,28 @@ raster_radial_kernel(const __grid_constant__ RasterArgs a, const __grid_constant
     }
 }
 
-// per-plane {min, max} of the R16 texture the module samples (circle: bounds the stream's annulus)
-__global__ void texmm_kernel(const uint16_t* __restrict__ tex, int n, uint32_t* __restrict__ out) {
+// per-plane {min, max} of the R16 texture the module samples (circle: bounds the stream's annulus), followed by the
+// {min, max} of GLB_CIRCLE_NB buckets of n / GLB_CIRCLE_NB consecutive texels (bounds a TILE's annulus: a tile's cells
+// reference a known range of texels, see circle_tile_kernel)
+__global__ void __launch_bounds__(256)
+texmm_kernel(const uint16_t* __restrict__ tex, int n, uint32_t* __restrict__ out) {
     __shared__ uint32_t smin[8], smax[8];
     const uint16_t* t = tex + (size_t) blockIdx.x * n;
+    uint32_t* o = out + (size_t) blockIdx.x * GLB_TEXMM_STRIDE;
+    const int per = n / 256;                                  // n >= 256: thread t covers [t * per, (t + 1) * per), two threads per bucket
     uint32_t lo = 65535u, hi = 0u;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) { const uint32_t v = t[i]; lo = min(lo, v); hi = max(hi, v); }
+    for (int i = 0; i < per; ++i) { const uint32_t v = t[threadIdx.x * per + i]; lo = min(lo, v); hi = max(hi, v); }
+    {
+        const uint32_t blo = min(lo, __shfl_xor_sync(0xffffffffu, lo, 1)), bhi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 1));
+        if ((threadIdx.x & 1) == 0) { o[2 + threadIdx.x] = blo; o[3 + threadIdx.x] = bhi; }      // bucket threadIdx.x / 2
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    for (int k = 16; k > 0; k >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, k)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, k)); }
     if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < (int) (blockDim.x >> 5); ++w) { lo = min(lo, smin[w]); hi = max(hi, smax[w]); }
-        out[2 * blockIdx.x] = lo; out[2 * blockIdx.x + 1] = hi;
+        for (int w = 1; w < 8; ++w) { lo = min(lo, smin[w]); hi = max(hi, smax[w]); }
+        o[0] = lo; o[1] = hi;
     }
 }
 int launch_texmm(const glava_b200_params& p, const uint16_t* d_tex, uint32_t* d_out, int planes, void* stream) {
@@ -516,6 +550,61 @@ int launch_polar_geo(const glava_b200_params& p, void* d_geo, const int box[4], 
     polar_geo_kernel<<<grid, 128, 0, (cudaStream_t) stream>>>(reinterpret_cast<int4*>(d_geo), box[0], box[1], box[2], box[3], p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "polar geometry kernel launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// circle: which texels can the cells of a 128 x 8 tile (+ its 1-pixel halo, read by stage 2) reference?  Audio-independent,
+// so it is reduced once from the finished cache; per frame and stream the buckets of texmm_kernel then bound the curve
+// INSIDE the tile's angular range, and a tile the curve cannot touch costs 4 KB of zero stores instead of 1300 cell
+// evaluations (the per-stream annulus alone keeps every tile between the base circle and the tallest peak alive).
+size_t circle_tile_bytes(const glava_b200_params& p, int* ntx, int* nty) {
+    *ntx = (p.w + CIRCLE_TW - 1) / CIRCLE_TW; *nty = (p.h + CIRCLE_TH - 1) / CIRCLE_TH;
+    return (size_t) *ntx * *nty * (sizeof(int4) + sizeof(int));
+}
+__global__ void circle_tile_init_kernel(int4* tiles, int* zero, int count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) { tiles[i] = make_int4(0x7fffffff, -1, 0x7fffffff, -1); zero[i] = 0; }
+}
+__global__ void circle_tile_kernel(const int4* __restrict__ geo, int gx0, int gy0, int gw, int gh, int4* tiles, int* zero, int ntx, int nty) {
+    const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y;
+    if (bx >= gw || by >= gh) return;
+    const int4 e = geo[(size_t) by * gw + bx];
+    if (e.y < 0) return;                                                   // the cell cannot be lit: it references nothing
+    int lo[2] = { 0x7fffffff, 0x7fffffff }, hi[2] = { -1, -1 }, z = 0;
+    const int refs[3] = { e.y, e.z, e.w };
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int ch = (refs[k] >> 30) & 1, i = refs[k] & 0x3fffffff;
+        if (i == 0x3fffffff) z = 1; else { lo[ch] = min(lo[ch], i); hi[ch] = max(hi[ch], i); }
+    }
+    const int x = gx0 + bx, y = gy0 + by;
+    int seen[4] = { -1, -1, -1, -1 }, ns = 0;
+    for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {                                 // every tile whose halo contains this cell
+            const int tx = (x + dx) / CIRCLE_TW, ty = (y + dy) / CIRCLE_TH;
+            if (x + dx < 0 || y + dy < 0 || tx >= ntx || ty >= nty) continue;
+            const int ti = ty * ntx + tx;
+            bool dup = false;
+            for (int q = 0; q < ns; ++q) dup |= seen[q] == ti;
+            if (dup) continue;
+            if (ns < 4) seen[ns++] = ti;
+            int* t = reinterpret_cast<int*>(tiles + ti);
+            if (hi[0] >= 0) { atomicMin(t + 0, lo[0]); atomicMax(t + 1, hi[0]); }
+            if (hi[1] >= 0) { atomicMin(t + 2, lo[1]); atomicMax(t + 3, hi[1]); }
+            if (z) atomicOr(zero + ti, 1);
+        }
+}
+int launch_circle_tiles(const glava_b200_params& p, const void* d_geo, const int box[4], void* d_tiles, void* stream) {
+    int ntx, nty;
+    circle_tile_bytes(p, &ntx, &nty);
+    int4* tiles = reinterpret_cast<int4*>(d_tiles);
+    int* zero = reinterpret_cast<int*>(tiles + (size_t) ntx * nty);
+    cudaStream_t st = (cudaStream_t) stream;
+    circle_tile_init_kernel<<<(ntx * nty + 255) / 256, 256, 0, st>>>(tiles, zero, ntx * nty);
+    dim3 grid((box[2] + 127) / 128, box[3]);
+    circle_tile_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const int4*>(d_geo), box[0], box[1], box[2], box[3], tiles, zero, ntx, nty);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "circle tile kernel launch: %s", cudaGetErrorString(e));
     return 0;
 }
 
