@@ -58,6 +58,7 @@ class Params(C.Structure):
         ("clear_color", C.c_float * 4),
         ("radial_bar_width_int", C.c_int), ("radial_bar_outline_width", C.c_float), ("radial_bar_outline", C.c_float * 4),
         ("graph_join_channels", C.c_int), ("graph_anti_alias", C.c_int), ("shader_pre_smoothed", C.c_int),
+        ("mirror_input", C.c_int),
     ]
 
     def copy(self):
@@ -163,6 +164,9 @@ def lib():
     L.glava_b200_wait_input.argtypes = [vp]
     L.glava_b200_update.argtypes = [vp, vp, vp, C.c_size_t, i32]
     L.glava_b200_update_device.argtypes = [vp, vp, vp, C.c_size_t, i32]
+    L.glava_b200_update_device_after.argtypes = [vp, vp, vp, C.c_size_t, i32, vp]
+    L.glava_b200_input_event.restype = vp
+    L.glava_b200_input_event.argtypes = [vp]
     L.glava_b200_update_masked.argtypes = [vp, vp, vp, C.c_size_t, vp]
     L.glava_b200_update_device_masked.argtypes = [vp, vp, vp, C.c_size_t, vp]
     L.glava_b200_update_rings_masked.argtypes = [vp, vp]
@@ -374,6 +378,15 @@ class Renderer:
         """d_lb, d_rb: integer device addresses of [batch][n] float32 (e.g. torch tensor.data_ptr())."""
         _check(self._L.glava_b200_update_device(self._h, d_lb, d_rb, self.params.n, 1 if modified else 0))
         self._after_update()
+
+    def update_device_after(self, d_lb, d_rb, modified, ready_event):
+        """update_device ordered after `ready_event` (a cudaEvent_t handle, e.g. torch.cuda.Event().cuda_event)"""
+        _check(self._L.glava_b200_update_device_after(self._h, d_lb, d_rb, self.params.n, 1 if modified else 0, ready_event))
+        self._after_update()
+
+    @property
+    def input_event(self):
+        return self._L.glava_b200_input_event(self._h)
 
     def ingest_fifo(self, chunks):
         chunks = np.ascontiguousarray(chunks, dtype=np.int16)

@@ -78,6 +78,7 @@ struct glava_b200 {
     // inputs
     float* d_pcm[2][2];         // H2D staging for glava_b200_update, double-buffered  [2][batch][n] x {l, r}
     int    stage_cur;
+    cudaEvent_t ev_input;       // glava_b200_input_event
     bool   async_input; int last_in;   // glava_b200_set_async_input: update() does not wait for its H2D copy
     cudaStream_t copy_stream;   // H2D of update i+1 overlaps the kernels of update i
     // asynchronous frame read-back: D2D into a staging frame on the raster stream (microseconds), D2H from there on its
@@ -540,7 +541,7 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     r->out_stream = nullptr; r->d_stage[0] = r->d_stage[1] = nullptr; r->stage_bytes = 0; r->out_cur = 0;
     for (int i = 0; i < 2; ++i) { r->ev_stage_ready[i] = nullptr; r->ev_stage_free[i] = nullptr; }
     r->updates = 0; r->launches = 0; r->timing = false;
-    r->desync = false; r->umask_cur = 0; r->async_input = false; r->last_in = -1;
+    r->desync = false; r->umask_cur = 0; r->async_input = false; r->last_in = -1; r->ev_input = nullptr;
     for (int i = 0; i < 4; ++i) { r->h_umask[i] = nullptr; r->d_umask[i] = nullptr; r->ev_umask[i] = nullptr; }
     if (build(r) != 0) { glava_b200_destroy(r); return nullptr; }
     return r;
@@ -563,6 +564,7 @@ void glava_b200_destroy(glava_b200* r) {
         if (r->d_umask[i]) cudaFree(r->d_umask[i]);
         if (r->ev_umask[i]) cudaEventDestroy(r->ev_umask[i]);
     }
+    if (r->ev_input) cudaEventDestroy(r->ev_input);
     if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
     if (r->out_stream) { cudaStreamSynchronize(r->out_stream); cudaStreamDestroy(r->out_stream); }
     for (int i = 0; i < 2; ++i) {
@@ -921,6 +923,24 @@ int glava_b200_update_rings_masked(glava_b200* r, const uint8_t* modified) {
     if (!r || !modified) return fail(GLAVA_B200_EINVAL, "glava_b200_update_rings_masked: null argument");
     CU(cudaSetDevice(r->device));
     return run_update(r, r->d_ring[r->ring_cur][0], r->d_ring[r->ring_cur][1], 1, false, modified);
+}
+
+// Ordering of glava_b200_update_device against the caller's own CUDA work.  The spectrum kernel reads d_lb / d_rb on an
+// internal non-blocking stream: hand over the event that marks "buffers written" (recorded on the producer's stream) and the
+// kernel waits for it on the device; glava_b200_input_event() is recorded after the kernel that last READ the buffers, so
+// the producer can cudaStreamWaitEvent on it before overwriting them.  Both are cudaEvent_t passed as void*.
+int glava_b200_update_device_after(glava_b200* r, const float* d_lb, const float* d_rb, size_t bsz, int modified, void* ready_event) {
+    if (!r) return fail(GLAVA_B200_EINVAL, "null argument");
+    CU(cudaSetDevice(r->device));
+    if (ready_event) CU(cudaStreamWaitEvent(r->spec_stream, (cudaEvent_t) ready_event, 0));
+    return glava_b200_update_device(r, d_lb, d_rb, bsz, modified);
+}
+void* glava_b200_input_event(glava_b200* r) {
+    if (!r) return nullptr;
+    if (!r->ev_input) { if (cudaEventCreateWithFlags(&r->ev_input, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; } }
+    cudaSetDevice(r->device);
+    cudaEventRecord(r->ev_input, r->spec_stream);          // after everything enqueued so far on the reading stream
+    return (void*) r->ev_input;
 }
 
 int glava_b200_update_device(glava_b200* r, const float* d_lb, const float* d_rb, size_t bsz, int modified) {

@@ -101,7 +101,7 @@ void fill_defaults(glava_b200_params* p, int module) {
     p->avg_frames = 5; p->avg_window = 1; p->accel_fft = 1; p->smooth_pass = 1;
     p->smooth_factor = 0.025f; p->sample_range = 0.9f; p->sample_scale = 8.0f;
     p->hybrid_weight = 0.65f; p->sample_mode = 0; p->round_formula = 0;
-    p->module = module; p->w = 800; p->h = 600; p->channels = 2; p->premultiply_alpha = 1;
+    p->module = module; p->w = 800; p->h = 600; p->channels = 2; p->mirror_input = 0; p->premultiply_alpha = 1;
     p->bars_width = 5; p->bars_gap = 1; p->bars_outline_width = 1; p->bars_amplify = 300;
     p->bars_color.mode = 0; hex3(p->bars_color.lo, 0x33, 0x66, 0xb2); hex3(p->bars_color.hi, 0xa0, 0xa0, 0xb2);
     p->bars_color.gradient = 80; p->bars_outline_mode = 0;
@@ -426,7 +426,7 @@ static bool apply_request(Loader& L, const std::vector<std::string>& t, const ch
     glava_b200_params* p = L.p;
     bool b;
     if (name == "mod") { if (!need(1)) return false; if (!L.module_forced) L.module = t[1]; }
-    else if (name == "setmirror") { if (!need(1) || !as_b(1, &b)) return false; p->channels = b ? 1 : 2; }
+    else if (name == "setmirror") { if (!need(1) || !as_b(1, &b)) return false; p->channels = b ? 1 : 2; p->mirror_input = b ? 1 : 0; }   // render.c:1054-1058: r->mirror_input AND gl->mirror_input
     else if (name == "setopacity") {
         if (!need(1)) return false;
         if (t[1] == "native") p->premultiply_alpha = 1;
@@ -750,7 +750,7 @@ int load_config(glava_b200_params* out, const char* const* paths, const char* en
         out->avg_frames = 6; out->avg_window = 1; out->gravity_step = 4.2f; out->interpolate = 1;
         out->smooth_factor = 0.025f; out->smooth_distance = 0.01f; out->smooth_ratio = 4.0f;
         out->premultiply_alpha = 1; out->accel_fft = 1; out->smooth_pass = 1; out->fft_scale = 10.2f; out->fft_cutoff = 0.3f;
-        out->w = 500; out->h = 400; out->bufscale = 1; out->channels = 2;
+        out->w = 500; out->h = 400; out->bufscale = 1; out->channels = 2; out->mirror_input = 0;
         out->clear_color[0] = out->clear_color[1] = out->clear_color[2] = out->clear_color[3] = 0.0f;
     }
     Loader L { out, "bars", false, false };

@@ -895,8 +895,9 @@ __global__ void fifo_ingest_kernel(const void* __restrict__ chunks, int frames, 
 int launch_fifo_ingest(const glava_b200_params& p, const void* d_chunks, bool float_in, int frames, const float* src_l, const float* src_r,
                        float* dst_l, float* dst_r, int batch, void* stream) {
     dim3 grid((p.n + 1023) / 1024, batch);
-    if (float_in) fifo_ingest_kernel<true><<<grid, 256, 0, (cudaStream_t) stream>>>(d_chunks, frames, p.n, p.channels, src_l, src_r, dst_l, dst_r);
-    else fifo_ingest_kernel<false><<<grid, 256, 0, (cudaStream_t) stream>>>(d_chunks, frames, p.n, p.channels, src_l, src_r, dst_l, dst_r);
+    const int chans = (p.mirror_input || p.channels == 1) ? 1 : 2;       // the AUDIO side's mono mix (setmirror), not the shader's _CHANNELS
+    if (float_in) fifo_ingest_kernel<true><<<grid, 256, 0, (cudaStream_t) stream>>>(d_chunks, frames, p.n, chans, src_l, src_r, dst_l, dst_r);
+    else fifo_ingest_kernel<false><<<grid, 256, 0, (cudaStream_t) stream>>>(d_chunks, frames, p.n, chans, src_l, src_r, dst_l, dst_r);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "fifo ingest kernel launch: %s", cudaGetErrorString(e));
     return 0;

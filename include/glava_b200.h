@@ -126,8 +126,12 @@ typedef struct {
     /* engine knobs (no reference equivalent) */
     int   fb_slots;           /* framebuffers resident per device; 0 = one per stream (default),
                                  K < batch = ring of K (stream s renders into slot s % K) */
-    int   lazy_smooth;        /* 1: K5 evaluates only the texels the module samples (same pixels,
-                                 texture read-back then holds only those texels); 0: all n texels */
+    int   lazy_smooth;        /* 1: K5 evaluates only the texels the module samples, and gravity / average state is kept only
+                                 for the bins those texels' taps reach (same pixels; glava_b200_textures() / _spectrum() then hold
+                                 only those texels / bins, the rest is stale or zero); 0: all n texels.  After a
+                                 glava_b200_reconfigure that widens the sampled set (AMPLIFY does not; BAR_WIDTH, geometry,
+                                 setsmoothfactor do), the newly reached bins start from the state they had when they were last
+                                 updated (zero at creation): their bars fade in over setavgframes updates, like a GLava restart */
     /* optional stages of rd_update that the shipped configuration leaves off */
     int   bufscale;           /* setbufscale (rc.glsl:236, deprecated): box-average `bufscale` PCM samples
                                  before anything else (render.c:1765-1790); textures then have n / bufscale texels */
@@ -163,6 +167,10 @@ typedef struct {
                                         gets into 1 / 2 when smooth_parameters.glsl flips setsmoothpass: the module's first
                                         shader header is built before its includes' requests run (render.c:284-293, 312);
                                         the config reader reproduces that */
+    int   mirror_input;              /* setmirror as the AUDIO side sees it (r->mirror_input, render.c:1054-1058: the backend mixes
+                                        both channels into one, fifo.c:98-102).  `channels` above is what the SHADER sees
+                                        (`_CHANNELS`), which bars' `DISABLE_MONO 1` turns back into 2 (bars/1.frag:32-34) while the
+                                        rings stay mono.  0 with channels == 1 is treated as 1 (older callers set only channels) */
 } glava_b200_params;
 
 typedef struct glava_b200 glava_b200;    /* plays the role of struct glava_renderer (render.h:8-30) */
@@ -252,8 +260,15 @@ int glava_b200_update(glava_b200* r, const float* lb, const float* rb, size_t bs
  * A caller alternating between two sets of rings never waits on a copy. */
 int glava_b200_set_async_input(glava_b200* r, int enable);
 int glava_b200_wait_input(glava_b200* r);
-/* same with DEVICE pointers (inputs already resident in HBM) */
+/* same with DEVICE pointers (inputs already resident in HBM).  The kernels read d_lb / d_rb (16-byte aligned) on an INTERNAL
+ * non-blocking stream: either the buffers are complete before the call and stay untouched until glava_b200_sync, or the
+ * caller orders its own stream with the two event hooks below. */
 int glava_b200_update_device(glava_b200* r, const float* d_lb, const float* d_rb, size_t bsz, int modified);
+/* ready_event: a cudaEvent_t (as void*) recorded on the producer's stream after d_lb / d_rb were written; the update waits
+ * for it on the device.  glava_b200_input_event(): a cudaEvent_t recorded after the kernels that READ the buffers of the
+ * updates issued so far — cudaStreamWaitEvent(producer, ev) before overwriting them. */
+int   glava_b200_update_device_after(glava_b200* r, const float* d_lb, const float* d_rb, size_t bsz, int modified, void* ready_event);
+void* glava_b200_input_event(glava_b200* r);
 
 /* Per-stream `modified` (glava.c:528-537 tests the flag of ITS audio thread; in a batch every stream has its own):
  * modified[s] != 0 = stream s has new audio and runs the whole chain; a stream with 0 keeps its gravity / average state
@@ -268,7 +283,7 @@ int glava_b200_update_rings_masked(glava_b200* r, const uint8_t* modified);
 
 /* FIFO-compatible ingest (fifo.c:89-110): `frames` new interleaved int16 L,R frames per stream,
  * HOST [batch][frames*2]; slides every stream's device-resident ring and converts s16/65535.f
- * (mono: integer mean first, fifo.c:98-102 when params.channels == 1).  Then
+ * (mono: integer mean first, fifo.c:98-102, when params.mirror_input — or, for callers that only set it, channels == 1).  Then
  * glava_b200_update_rings() runs the update on the resident rings. */
 int glava_b200_ingest_fifo(glava_b200* r, const int16_t* chunks, int frames);
 /* The PulseAudio backend's ring update (pulse_input.c:146-174): the samples are ALREADY float (PA_SAMPLE_FLOAT32NE, no

@@ -226,7 +226,7 @@ USER_CONFIGS = {
 #define NBARS 20
 #define BAR_WIDTH 5
 #define AMPLIFY 25
-#define BAR_OUTLINE_WIDTH 1.5
+#define BAR_OUTLINE_WIDTH 2
 #define OUTLINE #4080c0
 """,
     "circle": """

@@ -87,3 +87,46 @@ def test_async_readback_snapshots_each_frame_before_the_next_update_overwrites_i
         for i in range(steps):
             assert np.array_equal(bufs[i], want[i]), i
         assert not np.array_equal(want[0], want[2])                        # the frames do differ from step to step
+
+
+def _cudart():
+    import ctypes, glob, os, torch
+    for pat in ("libcudart.so", os.path.join(os.path.dirname(torch.__file__), "lib", "libcudart*.so*"), "/usr/local/cuda/lib64/libcudart.so*"):
+        for cand in ([pat] if "*" not in pat else sorted(glob.glob(pat))):
+            try:
+                return ctypes.CDLL(cand)
+            except OSError:
+                continue
+    pytest.skip("libcudart not loadable from Python")
+
+
+@pytest.mark.gpu
+def test_update_device_is_ordered_by_the_callers_events(built):
+    """glava_b200_update_device_after / glava_b200_input_event: a producer that fills the PCM buffers on its OWN stream and
+    overwrites them right after the call — without the two events the spectrum kernel (internal non-blocking stream) would
+    race with it; with them every update sees exactly the buffer content of its turn"""
+    import ctypes
+    import torch
+    n, batch, steps = 2048, 16, 12
+    p = g.default_params("bars", n=n, w=128, h=64)
+    rng = np.random.default_rng(77)
+    seq = [((rng.random((batch, n), np.float32) - 0.5) * 0.4, (rng.random((batch, n), np.float32) - 0.5) * 0.4) for _ in range(steps)]
+    prod = torch.cuda.Stream()
+    dl = torch.zeros(batch, n, device="cuda"); dr = torch.zeros(batch, n, device="cuda")
+    host = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()) for a, b in seq]
+    with g.Renderer(p, batch=batch) as r, g.Renderer(p, batch=batch) as ref:
+        for k in range(steps):
+            with torch.cuda.stream(prod):
+                # (torch has no wrapper for a foreign cudaEvent_t: wait on it through the runtime)
+                rt = _cudart()
+                rt.cudaStreamWaitEvent(ctypes.c_void_p(prod.cuda_stream), ctypes.c_void_p(r.input_event), 0)
+                dl.copy_(host[k][0], non_blocking=True); dr.copy_(host[k][1], non_blocking=True)
+                # burn some time on the producer stream so that an unordered consumer would read half-written buffers
+                for _ in range(4):
+                    dl.mul_(1.0); dr.mul_(1.0)
+                ready = torch.cuda.Event(); ready.record(prod)
+            r.update_device_after(dl.data_ptr(), dr.data_ptr(), True, ready.cuda_event)
+            ref.update(seq[k][0], seq[k][1], True)
+        r.sync(); ref.sync(); torch.cuda.synchronize()
+        a, b = r.textures(), ref.textures()
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[0].any()
