@@ -20,12 +20,17 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__inst_executed.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
-        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "lts__t_bytes.sum", "sm__cycles_elapsed.max"]
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "lts__t_bytes.sum", "sm__cycles_elapsed.max",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__shared_mem_per_block_dynamic",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct"]
 SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
 
 
 def main():
-    tag, launches, rep = sys.argv[1:4]
+    tag, launches = sys.argv[1:3]
+    reps = sys.argv[3:]
     out = os.path.join(ROOT, "profiles")
     os.makedirs(out, exist_ok=True)
     # ---- launch list -----------------------------------------------------------------------------
@@ -40,27 +45,32 @@ def main():
     total = sum(sum(v) for v in agg.values())
     share = {k: {"launches": len(v), "avg_us": sum(v) / len(v) / 1e3, "share_of_listed_time": sum(v) / total} for k, v in agg.items()}
     # ---- full capture ------------------------------------------------------------------------------
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rr = list(csv.reader(raw.splitlines()))
-    hdr, units = rr[0], rr[1]
     kernels = []
-    for r in rr[2:]:
-        d = {"kernel": r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").replace("glb::", "")}
-        for k in KEYS:
-            if k in hdr:
-                v, u = r[hdr.index(k)], units[hdr.index(k)]
-                try:
-                    v = float(v.replace(",", ""))
-                except ValueError:
-                    continue
-                if k.startswith("dram__bytes") or k.startswith("lts__t_bytes"):
-                    v *= SCALE.get(u, 1)
-                    u = "byte"
-                if k == "gpu__time_duration.sum":
-                    v *= SCALE.get(u, 1)
-                    u = "ms"
-                d[k] = {"value": v, "unit": u}
-        kernels.append(d)
+    rows_all = []
+    for rep in reps:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rr = list(csv.reader(raw.splitlines()))
+        if len(rr) < 3:
+            continue
+        rows_all.append((rr[0], rr[1], rr[2:], os.path.basename(rep)))
+    for hdr, units, body, repname in rows_all:
+      for r in body:
+          d = {"capture": repname, "kernel": r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").replace("glb::", "")}
+          for k in KEYS:
+              if k in hdr:
+                  v, u = r[hdr.index(k)], units[hdr.index(k)]
+                  try:
+                      v = float(v.replace(",", ""))
+                  except ValueError:
+                      continue
+                  if k.startswith("dram__bytes") or k.startswith("lts__t_bytes"):
+                      v *= SCALE.get(u, 1)
+                      u = "byte"
+                  if k == "gpu__time_duration.sum":
+                      v *= SCALE.get(u, 1)
+                      u = "ms"
+                  d[k] = {"value": v, "unit": u}
+          kernels.append(d)
     summary = {"tag": tag, "launch_list": share, "ncu_full": kernels,
                "note": "ncu times are cold-cache and serialised; compare kernel SHARES with bench.py, not absolutes"}
     json.dump(summary, open(os.path.join(out, f"{tag}_ncu_summary.json"), "w"), indent=1)
@@ -71,7 +81,7 @@ def main():
             f.write(f"| `{k}` | {v['launches']} | {v['avg_us']:.1f} | {v['share_of_listed_time']:.3f} |\n")
         f.write("\nFull capture (`ncu --set full --clock-control none --import-source on`):\n\n")
         for d in kernels:
-            f.write(f"## `{d['kernel']}`\n\n")
+            f.write(f"## `{d['kernel']}`  ({d.get('capture', '')})\n\n")
             for k in KEYS:
                 if k in d:
                     f.write(f"- {k} = {d[k]['value']:.6g} {d[k]['unit']}\n")
