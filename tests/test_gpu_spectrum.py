@@ -191,15 +191,15 @@ def test_kernel_variants_give_identical_textures_and_frames(built, monkeypatch, 
             need = tl.any(axis=0) | tr.any(axis=0)                 # lazy: only the sampled texels are defined
             return tl[:, need], tr[:, need], [r.readback(s) for s in (0, 33, batch - 1)], r.spectrum()
 
-    base = run({"GLAVA_B200_K5_SPLIT": "0"})
+    base = run({"GLAVA_B200_K5_SPLIT": "0", "GLAVA_B200_SPEC_OOP": "0", "GLAVA_B200_SPEC_T": "0"})
     assert base[0].any()
-    for env in ({"GLAVA_B200_K5_SPLIT": "1"}, {"GLAVA_B200_K5_SPLIT": "1", "GLAVA_B200_SPLIT_EPI": "1"},
+    for env in ({"GLAVA_B200_K5_SPLIT": "1", "GLAVA_B200_SPLIT_EPI": "0"}, {"GLAVA_B200_K5_SPLIT": "1", "GLAVA_B200_SPLIT_EPI": "1"},
                 {"GLAVA_B200_K5_SPLIT": "1", "GLAVA_B200_SPLIT_EPI": "1", "GLAVA_B200_SPEC_OOP": "1", "GLAVA_B200_SPEC_T": "256"},
-                {"GLAVA_B200_K5_SPLIT": "0", "GLAVA_B200_SPEC_OOP": "1", "GLAVA_B200_SPEC_T": "128"}):
+                {"GLAVA_B200_K5_SPLIT": "0", "GLAVA_B200_SPEC_OOP": "1", "GLAVA_B200_SPEC_T": "128"}, {}):      # {} = this size's defaults
         got = run(env)
         assert np.array_equal(got[0], base[0]) and np.array_equal(got[1], base[1]), env
         for a, b in zip(got[2], base[2]):
             assert np.array_equal(a, b), env
-        if "GLAVA_B200_SPLIT_EPI" not in env:                      # (the three-kernel form writes only the bins that matter into `spec`)
+        if env.get("GLAVA_B200_SPLIT_EPI") == "0":                 # (the three-kernel form writes only the bins that matter into `spec`)
             bad = np.argwhere(got[3][0] != base[3][0])
             assert len(bad) == 0, (env, len(bad), bad[:5].tolist(), got[3][0][tuple(bad[0])], base[3][0][tuple(bad[0])])
