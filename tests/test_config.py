@@ -240,3 +240,24 @@ def test_float_spelling_of_a_preprocessor_tested_macro_is_a_config_error(built, 
     (d / "graph.glsl").write_text("#define DRAW_OUTLINE 1.0\n")
     with pytest.raises(g.GlavaError, match="DRAW_OUTLINE"):
         g.load_config([str(d)])
+
+
+def test_setmirror_reaches_the_audio_side_even_when_bars_disables_mono(built, tmp_path):
+    """setmirror sets r->mirror_input (the backend mixes to mono, fifo.c:98-102) AND the shader's _CHANNELS (render.c:1054-1058,
+    :290); bars' DISABLE_MONO 1 turns only the shader back to two sides (bars/1.frag:32-34, llvmpipe golden `bars_disable_mono`)"""
+    d = tmp_path / "cfg"; d.mkdir()
+    (d / "rc.glsl").write_text("#request mod bars\n#request setmirror true\n")
+    p = g.load_config([str(d)])
+    assert (p.channels, p.mirror_input) == (1, 1)
+    (d / "bars.glsl").write_text("#define DISABLE_MONO 1\n")
+    p = g.load_config([str(d)])
+    assert (p.channels, p.mirror_input) == (2, 1)
+    assert g.default_params("bars").mirror_input == 0
+
+
+def test_params_survive_a_json_round_trip(built):
+    import json
+    from glava_b200.api import Params
+    p = g.default_params("radial", n=2048, w=321, h=123, radial_nbars=44)
+    q = Params.from_dict(json.loads(json.dumps(p.to_dict())))
+    assert bytes(p) == bytes(q)
