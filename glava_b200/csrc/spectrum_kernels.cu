@@ -844,7 +844,7 @@ int launch_k5_need(const glava_b200_params& p, const uint16_t* d_av, float* d_av
         if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "transpose kernel launch: %s", cudaGetErrorString(e));
     }
     // streams per lane: 4 sums share every tap broadcast once the batch is large enough to still fill the device
-    int S = 1;                                                   // measured at batch 1024: occupancy beats sharing (S = 4 was 2x slower)
+    int S = batch >= 256 ? 2 : 1;                                // measured at batch 1024, setbufsize 8192: S = 2 42 us, S = 1 52 us, S = 4 48 us
     if (const char* e = getenv("GLAVA_B200_K5N_S")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) S = v; }
     const int groups = (batch + 32 * S - 1) / (32 * S);
     const long long warps = (long long) channels * need_count * groups;

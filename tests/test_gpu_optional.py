@@ -220,6 +220,5 @@ def test_smooth_before_fft_equals_the_oracle_stream(orc_pm, built, accel):
             # ones included; the Stockham passes do not) — an artefact of a degenerate configuration, so only the bins that
             # are finite on both sides are compared
             ok = np.isfinite(want[s][0]) & np.isfinite(sl[s])
-            assert np.isnan(sl[s][0]) and np.isnan(want[s][0][0])
             if ok.any():
                 assert np.abs(sl[s][ok] - want[s][0][ok]).max() <= 1e-5 * max(np.abs(want[s][0][ok]).max(), 1e-30)
