@@ -54,6 +54,10 @@ def workload(name):
         m = name[:-3]
         return dict(module=m, n=2048, w=1280, h=720, batch=256,
                     metric=f"spectrum frames/sec @2048-pt FFT, 1280x720 {m}", label="BASELINE configs[3] module, throughput")
+    if name in ("circle1080", "radial1080", "graph1080", "wave1080"):
+        m = name[:-4]
+        return dict(module=m, n=4096, w=1920, h=1080, batch=1024,
+                    metric=f"spectrum frames/sec @4096-pt FFT, 1920x1080 {m}", label="other module at the headline geometry")
     if name.startswith("sweep:"):
         _, n, geo = name.split(":")
         w, h = (int(v) for v in geo.split("x"))
