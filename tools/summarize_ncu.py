@@ -48,7 +48,9 @@ def main():
     kernels = []
     rows_all = []
     for rep in reps:
-        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        # a capture (.ncu-rep), or its `ncu -i … --page raw --csv` export made on the GPU box (the reports themselves are too
+        # large to bring back: gpurun_out is capped at 64 MiB)
+        raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rr = list(csv.reader(raw.splitlines()))
         if len(rr) < 3:
             continue
