@@ -363,6 +363,10 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle.cpu_baseline import CpuBaseline, describe
+        try:                                                     # this process was pinned to the GPU's NUMA node: the reference gets
+            os.sched_setaffinity(0, range(os.cpu_count()))       # every host core of the box
+        except OSError:
+            pass
         fpw = max(1, int(round(2 * (1920 * 1080) / (W * H))))
         base = CpuBaseline(dict(module=MODULE, n=N, w=W, h=H), frames_per_worker=fpw)
         base.step()

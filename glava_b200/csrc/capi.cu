@@ -386,7 +386,10 @@ static int build_tables(glava_b200* r) {
             if ((rc = dev_alloc(r, &r->d_geo, bytes, false)) != 0) return rc;
             if ((rc = launch_polar_geo(p, r->d_geo, r->geo_box, r->stream)) != 0) return rc;
             ++r->launches;
-            if (p.module == GLAVA_B200_MOD_CIRCLE && !getenv("GLAVA_B200_NO_CTILE")) {
+            // per-tile annulus from bucketed texture min / max: measured a net LOSS at 1080p x 1024 streams, noise and
+            // synthetic-music input alike (529 k vs 548 k frames/s: the curve's halo keeps most tiles of the annulus alive and every
+            // live tile pays the bucket reduction) — kept behind GLAVA_B200_CTILE=1 so that the negative result is reproducible
+            if (p.module == GLAVA_B200_MOD_CIRCLE && getenv("GLAVA_B200_CTILE")) {
                 int ntx = 0, nty = 0;
                 const size_t tb = circle_tile_bytes(p, &ntx, &nty);
                 if ((rc = dev_alloc(r, &r->d_ctile, tb, false)) != 0) return rc;
