@@ -771,14 +771,14 @@ av_transpose_kernel(const uint16_t* __restrict__ av, float* __restrict__ av_t, i
 
 #define K5N_WARPS 4
 template <int MODE, int S>
-__global__ void __launch_bounds__(K5N_WARPS * 32)
+__global__ void __launch_bounds__(512)
 k5_need_kernel(const float* __restrict__ av_t, int av_t_len, uint16_t* __restrict__ tex, int n, int batch, int channels,
                const unsigned char* __restrict__ csr, int csr_bytes, int csr_idx_off, int csr_off_off,
                const int* __restrict__ need, const float* __restrict__ wsum, int need_count, const SmoothParams sp) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int groups = (batch + 32 * S - 1) / (32 * S);
     // consecutive warps take consecutive texels of the same stream group: their tap windows overlap, L1 serves the re-reads
-    const int gw = blockIdx.x * K5N_WARPS + warp;
+    const int gw = blockIdx.x * (blockDim.x >> 5) + warp;
     // (the last texels of the list have the widest windows — scale_audio is log-like: they go first, the short ones fill the tail)
     const int k = need_count - 1 - gw % need_count, g = (gw / need_count) % groups, ch = gw / (need_count * groups);
     if (ch >= channels) return;
@@ -848,9 +848,13 @@ int launch_k5_need(const glava_b200_params& p, const uint16_t* d_av, float* d_av
     if (const char* e = getenv("GLAVA_B200_K5N_S")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) S = v; }
     const int groups = (batch + 32 * S - 1) / (32 * S);
     const long long warps = (long long) channels * need_count * groups;
-    const unsigned grid = (unsigned) ((warps + K5N_WARPS - 1) / K5N_WARPS);
+    // warps per CTA = consecutive texels of one stream group: their tap windows overlap almost entirely, so the more of them
+    // share an SM's L1 the fewer reads go to L2 (the kernel moves 4 bytes per tap and lane: L2 bandwidth is its bound)
+    int wpc = K5N_WARPS;
+    if (const char* e = getenv("GLAVA_B200_K5N_WARPS")) { const int v = atoi(e); if (v >= 1 && v <= 16) wpc = v; }
+    const unsigned grid = (unsigned) ((warps + wpc - 1) / wpc);
     if (grid == 0) return 0;
-#define GLB_K5N(M, SS) k5_need_kernel<M, SS><<<grid, K5N_WARPS * 32, 0, st>>>(d_av_t, av_t_len, d_tex, p.n, batch, channels, d_csr, csr_bytes, \
+#define GLB_K5N(M, SS) k5_need_kernel<M, SS><<<grid, wpc * 32, 0, st>>>(d_av_t, av_t_len, d_tex, p.n, batch, channels, d_csr, csr_bytes, \
                                                                               csr_idx_off, csr_off_off, d_need, d_wsum, need_count, sp)
     const int m = sp.sample_mode == 0 ? 0 : 1;
     if (S == 4) { if (m == 0) GLB_K5N(0, 4); else GLB_K5N(1, 4); }
