@@ -414,21 +414,27 @@ raster_circle_kernel(const __grid_constant__ RasterArgs a, const __grid_constant
             __syncthreads();
         }
         const int y = ty0 + qy;
-        if (x < p.w && y < p.h) {
-            uint32_t px[4] = { 0u, 0u, 0u, 0u };
-            if (!tile_dead) {
+        if (tile_dead) {
+            if (x < p.w && y < p.h) { const uint32_t px[4] = { 0u, 0u, 0u, 0u }; store4(fb + (size_t) y * p.w, x, p.w, px); }
+        } else if (y < p.h) {
+            // live tile: a lane takes the pixels qx, qx + 32, qx + 64, qx + 96 of its row, so that the 7 tile reads per pixel
+            // are CONSECUTIVE across the warp.  With 4 adjacent pixels per lane (one 128-bit store) every one of those reads
+            // was a 4-way bank conflict — ncu: 32.3 M of 52.3 M shared-memory wavefronts of this kernel were conflict replays,
+            // and the kernel is issue bound; four coalesced 4-byte stores per lane cost far less than that.
+            uint32_t* row = fb + (size_t) y * p.w;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int lx = qx * 4 + k + 1, ly = qy + 1;
-                    // circle/2.frag's "- 1" taps at column 0 / row 0 read column 0 / row 0 (int(-0.5) = 0, see circle_px)
-                    const int lxm = (x + k > 0) ? lx - 1 : lx, lym = (y > 0) ? ly - 1 : ly;
-                    const uint32_t own = tile[ly][lx];
-                    const uint32_t nb[6] = { tile[ly][lx + 1], tile[ly + 1][lx + 1], tile[ly + 1][lx],
-                                             tile[ly][lxm], tile[lym][lxm], tile[lym][lx] };
-                    if (x + k < p.w) px[k] = ((own | nb[0] | nb[1] | nb[2] | nb[3] | nb[4] | nb[5]) == 0u) ? 0u : circle_finish(p, own, nb);
-                }
+            for (int k = 0; k < 4; ++k) {
+                const int cx = qx + 32 * k, gx = tx0 + cx;
+                if (gx >= p.w) continue;
+                const int lx = cx + 1, ly = qy + 1;
+                // circle/2.frag's "- 1" taps at column 0 / row 0 read column 0 / row 0 (int(-0.5) = 0, see circle_px)
+                const int lxm = (gx > 0) ? lx - 1 : lx, lym = (y > 0) ? ly - 1 : ly;
+                const uint32_t own = tile[ly][lx];
+                const uint32_t nb[6] = { tile[ly][lx + 1], tile[ly + 1][lx + 1], tile[ly + 1][lx],
+                                         tile[ly][lxm], tile[lym][lxm], tile[lym][lx] };
+                const uint32_t v = ((own | nb[0] | nb[1] | nb[2] | nb[3] | nb[4] | nb[5]) == 0u) ? 0u : circle_finish(p, own, nb);
+                __stcs(row + gx, v);
             }
-            store4(fb + (size_t) y * p.w, x, p.w, px);
         }
         if (!tile_dead) __syncthreads();             // the tile is rewritten by the next iteration
     }

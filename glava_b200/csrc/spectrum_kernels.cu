@@ -66,7 +66,7 @@ template <int LOG2N, int TT = 0, bool OOP = false> struct SpecCfg {
     // resident CTAs per SM the register allocation must allow: the kernel waits on memory a lot (TMA load,
     // state loads), so occupancy is worth more than the last registers (128 regs -> 2 CTAs/SM was measured)
     static constexpr int SMEM_CTAS = (220 * 1024) / SMEM < 1 ? 1 : (220 * 1024) / SMEM;
-    static constexpr int OOP_CTAS  = (1024 / T) < SMEM_CTAS ? (1024 / T) : SMEM_CTAS;       // <= 64 registers where shared memory allows
+    static constexpr int OOP_CTAS  = (1024 / T) < SMEM_CTAS ? (1024 / T) : SMEM_CTAS;       // (T = 1024: 1)       // <= 64 registers where shared memory allows
     static constexpr int MIN_CTAS = OOP ? (OOP_CTAS < 1 ? 1 : OOP_CTAS)
                                         : (T >= 512 ? 1 : (T * (N / 16 / T > 1 ? 2 : 1) > 256 ? 2 : 3));   // T = 512: capping at 64 registers spills in the FFT passes and was measured slower
 };
@@ -501,6 +501,7 @@ static int launch_spectrum_fft(const glava_b200_params& p, const SpectrumArgs& a
     if (oop) {
         if (tsel == 128) return launch_spectrum_t<L, true, 128, true>(p, a, st);
         if (tsel == 512) { if constexpr (L >= 13) return launch_spectrum_t<L, true, 512, true>(p, a, st); }
+        if (tsel == 1024) { if constexpr (L >= 14) return launch_spectrum_t<L, true, 1024, true>(p, a, st); }
         return launch_spectrum_t<L, true, 256, true>(p, a, st);
     }
     if (tsel == 256) { if constexpr (L >= 13) return launch_spectrum_t<L, true, 256, false>(p, a, st); }
@@ -844,7 +845,9 @@ int launch_k5_need(const glava_b200_params& p, const uint16_t* d_av, float* d_av
         if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "transpose kernel launch: %s", cudaGetErrorString(e));
     }
     // streams per lane: 4 sums share every tap broadcast once the batch is large enough to still fill the device
-    int S = batch >= 256 ? 2 : 1;                                // measured at batch 1024, setbufsize 8192: S = 2 42 us, S = 1 52 us, S = 4 48 us
+    // measured at batch 1024, setbufsize 8192, bars (2 x 159 texels): S = 2 42 us, S = 1 52 us, S = 4 48 us.  With few sampled
+    // texels (radial: ~90 per channel; ncu: 7.8 % warps active at S = 2) the device is not filled: one stream per lane there
+    int S = (batch >= 256 && (long long) channels * need_count * ((batch + 63) / 64) >= 148 * 24) ? 2 : 1;
     if (const char* e = getenv("GLAVA_B200_K5N_S")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) S = v; }
     const int groups = (batch + 32 * S - 1) / (32 * S);
     const long long warps = (long long) channels * need_count * groups;
