@@ -99,6 +99,7 @@ struct glava_b200 {
     unsigned char* d_csr; int csr_bytes, csr_idx_off, csr_off_off;   // the same taps, texel-major, for the shared-memory path
     void* d_geo; int geo_box[4];   // polar geometry cache (radial / circle), see raster_kernels.cu
     void* d_ctile; int ctile_nx, ctile_count;   // circle: per-tile texel reference ranges (launch_circle_tiles)
+    float* d_coltab; bool no_coltab;   // graph / wave: per-stream column table (launch_raster fills it), GLAVA_B200_NO_COLTAB
     uint32_t* d_texmm;             // circle: per-plane {min, max} of the sampled texture, refreshed before each raster
     // state + outputs
     float* d_spec; float* d_applied; float* d_ring_f;
@@ -481,6 +482,7 @@ static int build(glava_b200* r) {
     ALLOC(r->d_av, planes * n * 2, true);
     ALLOC(r->d_texmm, planes * GLB_TEXMM_STRIDE * sizeof(uint32_t), true);          // double-buffered: spectrum i+1 writes one half while raster i reads the other
     ALLOC(r->d_rowtab, (size_t) p.h * 8, true);
+    ALLOC(r->d_coltab, (size_t) r->batch * GLB_COLTAB_PLANES * p.w * sizeof(float), true);
     // framebuffers: [slots][h][w] RGBA8
     size_t frame = (size_t) p.w * p.h * 4;
     r->slots = (p.fb_slots > 0 && p.fb_slots < r->batch) ? p.fb_slots : r->batch;
@@ -527,6 +529,7 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     { const char* e = getenv("GLAVA_B200_SPEC_OOP"); r->spec_oop = e ? atoi(e) : (params->n == 8192 ? 1 : 0); }
     { const char* e = getenv("GLAVA_B200_SPEC_T"); r->spec_t = e ? atoi(e) : (params->n == 8192 ? 256 : 0); }
     r->no_texmm = getenv("GLAVA_B200_NO_TEXMM") != nullptr;
+    r->no_coltab = getenv("GLAVA_B200_NO_COLTAB") != nullptr;
     r->kcounter = 0; r->d_scaled[0] = r->d_scaled[1] = nullptr; r->d_key[0] = r->d_key[1] = r->d_key[2] = nullptr;
     r->key_start = 0; r->key_end = 1; r->d_spec_cur = nullptr; r->d_ts_tab = nullptr; r->ts_asz = r->ts_lim = 0;
     r->stream = nullptr; r->spec_stream = nullptr; r->tex_cur = 0; r->ring_cur = 0;
@@ -538,7 +541,7 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     r->k5_split_lazy = false; r->csr_in_smem = false; r->av_t_len = 0; r->d_av_t = nullptr;
     r->d_ctile = nullptr; r->ctile_nx = r->ctile_count = 0;
     r->d_geo = nullptr; r->geo_box[0] = r->geo_box[1] = r->geo_box[2] = r->geo_box[3] = 0;
-    r->d_spec = r->d_applied = r->d_ring_f = nullptr; r->d_gr_store = r->d_ring_u = r->d_tex = nullptr; r->d_av = nullptr; r->d_texmm = nullptr; r->d_fb = nullptr;
+    r->d_spec = r->d_applied = r->d_ring_f = nullptr; r->d_gr_store = r->d_ring_u = r->d_tex = nullptr; r->d_av = nullptr; r->d_texmm = nullptr; r->d_coltab = nullptr; r->d_fb = nullptr;
     for (int i = 0; i < 2; ++i) { r->d_pcm[i][0] = r->d_pcm[i][1] = nullptr; r->ev_copied[i] = r->ev_free[i] = nullptr; }
     r->stage_cur = 0; r->copy_stream = nullptr;
     r->out_stream = nullptr; r->d_stage[0] = r->d_stage[1] = nullptr; r->stage_bytes = 0; r->out_cur = 0;
@@ -636,11 +639,12 @@ static int apply_resize(glava_b200* r, int w, int h) {
     int rc = validate_params(&q);
     if (rc) return rc;
     if ((rc = sync_all(r)) != 0) return rc;
-    dev_free(r, r->d_fb); dev_free(r, r->d_rowtab);
-    r->d_fb = nullptr; r->d_rowtab = nullptr;
+    dev_free(r, r->d_fb); dev_free(r, r->d_rowtab); dev_free(r, r->d_coltab);
+    r->d_fb = nullptr; r->d_rowtab = nullptr; r->d_coltab = nullptr;
     r->p_user = q;
     derive(r);
     if ((rc = dev_alloc(r, (void**) &r->d_rowtab, (size_t) q.h * 8, true)) != 0) return rc;
+    if ((rc = dev_alloc(r, (void**) &r->d_coltab, (size_t) r->batch * GLB_COLTAB_PLANES * q.w * sizeof(float), true)) != 0) return rc;
     if ((rc = dev_alloc(r, (void**) &r->d_fb, (size_t) q.w * q.h * 4 * r->slots, true)) != 0) return rc;
     return build_tables(r);
 }
@@ -824,6 +828,7 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
     ra.batch = r->batch; ra.slots = r->slots; ra.stream0 = 0;
     ra.geo = r->d_geo; ra.gx0 = r->geo_box[0]; ra.gy0 = r->geo_box[1]; ra.gw = r->geo_box[2]; ra.gh = r->geo_box[3];
     ra.texmm = nullptr; ra.ctile = nullptr; ra.ctile_zero = nullptr; ra.ctile_nx = 0;
+    ra.coltab = r->no_coltab ? nullptr : r->d_coltab;
     // params.shader_pre_smoothed: the module's stage-1 shader believes something else about its textures than what the
     // K5 pass did.  Only the raster launch sees that belief (as its smooth_pass); everything before it follows the real one.
     glava_b200_params pr_store;
@@ -839,13 +844,11 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
         if (r->d_ctile) { ra.ctile = (const int4*) r->d_ctile; ra.ctile_zero = (const int*) ((const int4*) r->d_ctile + r->ctile_count); ra.ctile_nx = r->ctile_nx; }
     }
     if (r->timing && (rc = timing_mark(r->ev_ras, r->stream)) != 0) return rc;
-    if ((rc = launch_raster(*pr, ra, r->stream)) != 0) return rc;
+    int raster_launches = 0;
+    if ((rc = launch_raster(*pr, ra, r->stream, &raster_launches)) != 0) return rc;
     if (r->timing && (rc = timing_mark(r->ev_ras, r->stream)) != 0) return rc;
     CU(cudaEventRecord(r->ev_raster_done[b], r->stream));
-    {
-        const int chunk = r->slots < 32768 ? r->slots : 32768;          // see launch_raster
-        r->launches += (uint64_t) ((r->batch + chunk - 1) / chunk);
-    }
+    r->launches += (uint64_t) raster_launches;
     return 0;
 }
 

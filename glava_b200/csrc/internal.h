@@ -91,7 +91,11 @@ struct RasterArgs {
     // circle: per 128 x 8 tile (+ 1-pixel halo) the range of texel indices its cells reference, {lo_l, hi_l, lo_r, hi_r}
     // (lo > hi: none), and whether any reference is out of range (reads 0); audio-independent, built with the cache
     const int4* ctile; const int* ctile_zero; int ctile_nx;
+    // graph / wave: per-stream column table [batch][GLB_COLTAB_PLANES][w] floats, scratch that launch_raster fills on the
+    // raster stream right before the module kernel (graph: plane 0 = column height; wave: WaveCol's five fields); may be null
+    float* coltab;
 };
+#define GLB_COLTAB_PLANES 5
 #define GLB_CIRCLE_NB 128                         // texel buckets per plane (n / 128 texels each)
 #define GLB_TEXMM_STRIDE (2 + 2 * GLB_CIRCLE_NB)  // u32 per plane
 
@@ -125,7 +129,7 @@ int launch_k5_need(const glava_b200_params& p, const uint16_t* d_av, float* d_av
 // pipeline B epilogue as its own elementwise kernel: spec (transform_fft output) -> upload quantisation, K1 - K4 on the R16
 // state, pre-smoothing texels into av_out (leading `bins` of every plane; bins is a multiple of 8)
 int launch_epilogue_b(const glava_b200_params& p, const SpectrumArgs& a, int bins, void* stream);
-int launch_raster(const glava_b200_params& p, const RasterArgs& a, void* stream);
+int launch_raster(const glava_b200_params& p, const RasterArgs& a, void* stream, int* launched = nullptr);   // *launched += kernels launched
 int launch_bars_rowtab(const glava_b200_params& p, void* d_rowtab, void* stream);
 // geometry cache of the polar modules: box = {x0, y0, w, h}; returns bytes needed when d_geo == nullptr
 size_t polar_geo_box(const glava_b200_params& p, int box[4]);

@@ -28,6 +28,23 @@ __device__ __forceinline__ void store4(uint32_t* row, int x, int w, const uint32
     else for (int k = 0; k < 4 && x + k < w; ++k) row[x + k] = px[k];
 }
 
+// Rows [ya, yb) of a thread's quad are 0: when the rows are 16-byte aligned this is a bare pointer-increment loop of
+// independent 128-bit stores (the compiler unrolls it: several stores in flight per warp), the shape raster_bars_kernel
+// reaches the copy peak with.  The same loop written as store4(fb + y * w, ...) keeps a uniform branch on (w & 3) and a
+// 64-bit address recomputation around every store — graph / wave are 97 % zero rows and ran at 0.87 / 0.90 with it.
+__device__ __forceinline__ void zero_rows(uint32_t* fb, int x, int w, int ya, int yb) {
+    if ((w & 3) == 0) {
+        const int stride = w >> 2;
+        uint4* ptr = reinterpret_cast<uint4*>(fb) + (size_t) ya * stride + (x >> 2);
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 8
+        for (int y = ya; y < yb; ++y, ptr += stride) __stcs(ptr, zero);
+    } else {
+        const uint32_t zero4[4] = { 0u, 0u, 0u, 0u };
+        for (int y = ya; y < yb; ++y) store4(fb + (size_t) y * w, x, w, zero4);
+    }
+}
+
 // generic: every pixel through module_px() — reference semantics with no hoisting; also the
 // fallback for option combinations the specialised kernels do not cover.
 __global__ void __launch_bounds__(128)
@@ -159,7 +176,27 @@ __device__ __forceinline__ int graph_first_row(float lim, int off, int h) {
     return y;
 }
 
-__global__ void __launch_bounds__(256)
+// graph / wave: what a column contributes to its pixels depends on the audio through the column alone (graph: the height,
+// graph/1.frag:84-114; wave: wave/1.frag:17-31).  One thread per (stream, column) evaluates it once per update into the
+// column table; the raster kernels then start with six coalesced loads instead of six dependent texture samples per
+// thread and ROW BAND — which had forced whole-column CTAs (1080p: 2560 CTAs of 720 / 360 rows, 1.7 waves, 35 % warps
+// active, 0.86 of the copy peak).
+template <bool WAVE>
+__global__ void __launch_bounds__(128)
+column_table_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__ glava_b200_params p) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int stream = a.stream0 + blockIdx.y;
+    if (x >= p.w) return;
+    const AudioTex t = make_tex(p, a.tex, stream);
+    float* ct = a.coltab + (size_t) stream * GLB_COLTAB_PLANES * p.w;
+    if (WAVE) {
+        const WaveCol c = wave_column(p, t, x);
+        ct[x] = c.s; ct[p.w + x] = c.dmin; ct[2 * p.w + x] = c.dmax; ct[3 * p.w + x] = c.thick; ct[4 * p.w + x] = __uint_as_float(c.color);
+    } else ct[x] = graph_height(p, t, x);
+}
+
+template <bool TAB, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 raster_graph_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__ glava_b200_params p, int rows_per_cta) {
     const int stream = a.stream0 + blockIdx.z;
     const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -167,10 +204,11 @@ raster_graph_kernel(const __grid_constant__ RasterArgs a, const __grid_constant_
     const AudioTex t = make_tex(p, a.tex, stream);
     uint32_t* fb = reinterpret_cast<uint32_t*>(a.fb) + (size_t) (stream % a.slots) * p.w * p.h;
     float s[6];                                        // columns x-1 .. x+4
+    const float* __restrict__ ct = TAB ? a.coltab + (size_t) stream * GLB_COLTAB_PLANES * p.w : nullptr;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         int xc = x - 1 + k;
-        s[k] = (xc >= 0 && xc < p.w) ? graph_height(p, t, xc) : 0.0f;
+        s[k] = (xc >= 0 && xc < p.w) ? (TAB ? __ldg(ct + xc) : graph_height(p, t, xc)) : 0.0f;
     }
     float lo[4], hi[4]; bool inner_x[4];
 #pragma unroll
@@ -233,12 +271,12 @@ raster_graph_kernel(const __grid_constant__ RasterArgs a, const __grid_constant_
         } else full_rows(y, y + 1);
     }
     full_rows(b2, b3);
-    const uint32_t zero4[4] = { 0u, 0u, 0u, 0u };
-    for (int y = b3; y < y1; ++y) store4(fb + (size_t) y * p.w, x, p.w, zero4);
+    zero_rows(fb, x, p.w, b3, y1);
 }
 
 // wave: 6 column descriptors in registers
-__global__ void __launch_bounds__(256)
+template <bool TAB, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 raster_wave_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__ glava_b200_params p, int rows_per_cta) {
     const int stream = a.stream0 + blockIdx.z;
     const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -250,7 +288,11 @@ raster_wave_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__
     for (int k = 0; k < 6; ++k) {
         int xc = x - 1 + k;
         xc = xc < 0 ? 0 : (xc >= p.w ? p.w - 1 : xc);   // clamped columns are masked by wave_px_cols
-        c[k] = wave_column(p, t, xc);
+        if (TAB) {
+            const float* __restrict__ ct = a.coltab + (size_t) stream * GLB_COLTAB_PLANES * p.w + xc;
+            c[k].s = __ldg(ct); c[k].dmin = __ldg(ct + p.w); c[k].dmax = __ldg(ct + 2 * p.w); c[k].thick = __ldg(ct + 3 * p.w);
+            c[k].color = __float_as_uint(__ldg(ct + 4 * p.w));
+        } else c[k] = wave_column(p, t, xc);
     }
     // rows where any of a pixel's three columns can be lit (+-1 row for the stencil), conservative
     float ylo[4], yhi[4];
@@ -274,8 +316,7 @@ raster_wave_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__
         const unsigned m = __activemask();
         ra = __reduce_min_sync(m, ra); rb = __reduce_max_sync(m, rb);
     }
-    const uint32_t zero4[4] = { 0u, 0u, 0u, 0u };
-    for (int y = y0; y < ra; ++y) store4(fb + (size_t) y * p.w, x, p.w, zero4);
+    zero_rows(fb, x, p.w, y0, ra);
     for (int y = ra; y < rb; ++y) {
         const float fy = (float) y;
         uint32_t px[4];
@@ -287,7 +328,7 @@ raster_wave_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__
         }
         store4(fb + (size_t) y * p.w, x, p.w, px);
     }
-    for (int y = rb; y < y1; ++y) store4(fb + (size_t) y * p.w, x, p.w, zero4);
+    zero_rows(fb, x, p.w, rb, y1);
 }
 
 // circle: stage 1 (polar line test) is evaluated once per pixel of a tile + 1-pixel halo into shared
@@ -295,7 +336,7 @@ raster_wave_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__
 // annulus [C_RADIUS - C_LINE/2, C_RADIUS + AMPLIFY + ...] are exactly 0 and skip the maths.
 #define CIRCLE_TW 128
 #define CIRCLE_TH 8
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 raster_circle_kernel(const __grid_constant__ RasterArgs a, const __grid_constant__ glava_b200_params p, int tiles_per_cta) {
     __shared__ uint32_t tile[CIRCLE_TH + 2][CIRCLE_TW + 2];
     const int stream = a.stream0 + blockIdx.z;
@@ -376,7 +417,10 @@ raster_circle_kernel(const __grid_constant__ RasterArgs a, const __grid_constant
         }
         if (!tile_dead) {
             // (batching the geometry loads of a thread's 5-6 cells ahead of the dependent texel fetches was
-            // measured slower: 64 -> 106 registers, half the resident warps)
+            // measured slower: 64 -> 106 registers, half the resident warps.  Two cells per trip with all six texel
+            // fetches unconditional, 47 registers, was slower too — 0.772 against 0.821 of the copy peak: the live tiles
+            // are bound by instruction issue, not by the two dependent L2 round trips.  Per-row lit flags that let the
+            // finish phase skip empty 32-pixel segments changed nothing: 0.820 either way.  profiles/r2_circle_ab.txt)
             if (a.geo) {
                 // cached geometry: a cell is either outside the cache box (0) or a 16-byte entry with three
                 // texel references + d; entries that cannot be lit carry e0 = -1.  No per-cell float culling,
@@ -705,7 +749,7 @@ static int pick_block_x(int quads) {       // threads per row-segment: prefer an
     return 128;
 }
 
-int launch_raster(const glava_b200_params& p, const RasterArgs& a, void* stream) {
+int launch_raster(const glava_b200_params& p, const RasterArgs& a, void* stream, int* launched) {
     cudaStream_t st = (cudaStream_t) stream;
     const int quads = (p.w + 3) / 4;
     // The specialised kernels assume native opacity (a fragment left at vec4(0) stores 0, whole zero rows / discs are skipped);
@@ -720,8 +764,13 @@ int launch_raster(const glava_b200_params& p, const RasterArgs& a, void* stream)
     if (bx > 256) bx = 256;
     // rows per CTA, measured on B200: bars 135 >= 270 > 540 (with the spectrum kernel co-running);
     // graph / wave pay a per-thread column set-up, so whole columns (720 > 360 > 135); radial-from-cache 45 > 135
-    int rows = fast_bars ? 135 : ((fast_graph || fast_wave) ? 720 : (geo_radial ? 45 : 8));
+    // with the column table (a.coltab) their set-up is six loads and short bands win: graph 1080p x 1024 streams 30 rows 0.970 of the
+    // copy peak, 20: 0.965, 45: 0.937, 90: 0.891, 135: 0.859; wave 16 rows 1.017, 30: 0.994, 90: 0.949, 135: 0.936 (tools/gw_tune.py, profiles/r2_gw_tune.txt)
+    const bool coltab = a.coltab && (fast_graph || fast_wave);
+    int rows = fast_bars ? 135 : ((fast_graph || fast_wave) ? (coltab ? (fast_wave ? 16 : 30) : 720) : (geo_radial ? 45 : 8));
     // development overrides for tuning sweeps (tools/tune_raster.py); unset in normal use
+    int minb = 4;                                     // graph / wave with the column table: <= 64 registers (4 CTAs of 256; measured ahead) or 48 (5)
+    if (const char* e = getenv("GLAVA_B200_GW_MINB")) minb = atoi(e) == 5 ? 5 : 4;
     if (const char* e = getenv("GLAVA_B200_ROWS")) { int v = atoi(e); if (v > 0) rows = v; }
     if (const char* e = getenv("GLAVA_B200_BX")) { int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) bx = v; }
     if (rows > p.h) rows = p.h;
@@ -734,9 +783,24 @@ int launch_raster(const glava_b200_params& p, const RasterArgs& a, void* stream)
         RasterArgs b = a; b.stream0 = a.stream0 + s0;
         int nz = a.batch - s0 < chunk ? a.batch - s0 : chunk;
         dim3 grid((quads + bx - 1) / bx, (p.h + rows - 1) / rows, nz);
+        if (coltab) {
+            dim3 tg((p.w + 127) / 128, nz);
+            if (fast_wave) column_table_kernel<true><<<tg, 128, 0, st>>>(b, p);
+            else column_table_kernel<false><<<tg, 128, 0, st>>>(b, p);
+            if (launched) ++*launched;
+        }
+        if (launched) ++*launched;
         if (fast_bars) raster_bars_kernel<<<grid, bx, 0, st>>>(b, p, rows);
-        else if (fast_graph) raster_graph_kernel<<<grid, bx, 0, st>>>(b, p, rows);
-        else if (fast_wave) raster_wave_kernel<<<grid, bx, 0, st>>>(b, p, rows);
+        else if (fast_graph) {
+            if (!coltab) raster_graph_kernel<false, 1><<<grid, bx, 0, st>>>(b, p, rows);
+            else if (minb == 5) raster_graph_kernel<true, 5><<<grid, bx, 0, st>>>(b, p, rows);
+            else raster_graph_kernel<true, 4><<<grid, bx, 0, st>>>(b, p, rows);
+        }
+        else if (fast_wave) {
+            if (!coltab) raster_wave_kernel<false, 1><<<grid, bx, 0, st>>>(b, p, rows);
+            else if (minb == 5) raster_wave_kernel<true, 5><<<grid, bx, 0, st>>>(b, p, rows);
+            else raster_wave_kernel<true, 4><<<grid, bx, 0, st>>>(b, p, rows);
+        }
         else if (geo_radial) raster_radial_geo_kernel<<<grid, bx, 0, st>>>(b, p, rows);
         else if (native && p.module == GLAVA_B200_MOD_RADIAL) raster_radial_kernel<<<grid, bx, 0, st>>>(b, p, rows);
         else if (native && p.module == GLAVA_B200_MOD_CIRCLE) {
