@@ -95,6 +95,7 @@ struct glava_b200 {
     K5Table k5; void* d_k5_blk; void* d_k5_ent; void* d_k5_wsum;   // full-plane K5 tap table (null: evaluate taps in the kernel)
     // need-list K5 as its own kernel (one table per channel): the serial per-texel sums run at full occupancy on
     // (texel, plane) pairs instead of on a sixth of the threads of one spectrum CTA
+    void* d_need_blk; int need_nblk, need_max_rows;    // need-list K5 out of shared memory: blocks of sampled texels (tables.h build_need_blocks)
     bool k5_split_lazy, csr_in_smem, split_epilogue; int av_t_len; float* d_av_t; int spec_oop, spec_t;   // need-list K5 as its own kernel (k5_need_kernel)
     unsigned char* d_csr; int csr_bytes, csr_idx_off, csr_off_off;   // the same taps, texel-major, for the shared-memory path
     void* d_geo; int geo_box[4];   // polar geometry cache (radial / circle), see raster_kernels.cu
@@ -322,6 +323,7 @@ static int build_tables(glava_b200* r) {
     r->d_k5_blk = r->d_k5_ent = r->d_k5_wsum = nullptr; memset(&r->k5, 0, sizeof(r->k5));
     dev_free(r, r->d_csr); r->d_csr = nullptr; r->csr_bytes = r->csr_idx_off = r->csr_off_off = 0;
     dev_free(r, r->d_av_t); r->d_av_t = nullptr;
+    dev_free(r, r->d_need_blk); r->d_need_blk = nullptr; r->need_nblk = r->need_max_rows = 0;
     dev_free(r, r->d_ctile); r->d_ctile = nullptr; r->ctile_nx = r->ctile_count = 0;
     r->k5_split_lazy = false; r->csr_in_smem = false; r->av_t_len = 0;
     r->d_need = nullptr; r->need_count = 0; r->d_tap_tab = nullptr; r->d_tap_cnt = nullptr; r->d_tap_wsum = nullptr;
@@ -370,7 +372,19 @@ static int build_tables(glava_b200* r) {
                 r->k5_split_lazy = ks ? atoi(ks) != 0 : (!fits || p.n >= 4096);     // measured: also ahead at 4096 (759 k vs 753 k frames/s at the headline)
                 r->av_t_len = t.epi_n > 0 ? t.epi_n : p.n;
                 if (r->k5_split_lazy) {
-                    if ((rc = dev_alloc(r, (void**) &r->d_av_t, (size_t) 2 * r->av_t_len * r->batch * sizeof(float), true)) != 0) return rc;
+                    // blocks of sampled texels for the shared-memory form; GLAVA_B200_K5N_SMEM=0 keeps the L2 form (k5_need_kernel)
+                    NeedBlocks nb;
+                    int target = -105, tpb = 16;         // tile rows: 105 % of the tallest window (tables.h), or an absolute number / -per cent
+                    if (const char* e = getenv("GLAVA_B200_K5N_ROWS")) { const int v = atoi(e); if (v >= 32 || v < 0) target = v; }
+                    if (const char* e = getenv("GLAVA_B200_K5N_TPB")) { const int v = atoi(e); if (v >= 1) tpb = v; }
+                    build_need_blocks(t, p.n, target, tpb, &nb);
+                    const char* ke = getenv("GLAVA_B200_K5N_SMEM");
+                    if (nb.nblk > 0 && (size_t) nb.max_rows * 33 * sizeof(float) <= (size_t) 200 * 1024 && !(ke && atoi(ke) == 0)) {
+                        if ((rc = dev_alloc(r, &r->d_need_blk, nb.blk.size() * sizeof(int), false)) != 0) return rc;
+                        CU(cudaMemcpyAsync(r->d_need_blk, nb.blk.data(), nb.blk.size() * sizeof(int), cudaMemcpyHostToDevice, r->stream));
+                        CU(cudaStreamSynchronize(r->stream));
+                        r->need_nblk = nb.nblk; r->need_max_rows = nb.max_rows;
+                    } else if ((rc = dev_alloc(r, (void**) &r->d_av_t, (size_t) 2 * r->av_t_len * r->batch * sizeof(float), true)) != 0) return rc;
                 }
             }
         }
@@ -539,6 +553,7 @@ glava_b200* glava_b200_new(const glava_b200_params* params, int batch, int devic
     r->d_csr = nullptr; r->csr_bytes = r->csr_idx_off = r->csr_off_off = 0;
     r->d_k5_blk = r->d_k5_ent = r->d_k5_wsum = nullptr; memset(&r->k5, 0, sizeof(r->k5));
     r->k5_split_lazy = false; r->csr_in_smem = false; r->av_t_len = 0; r->d_av_t = nullptr;
+    r->d_need_blk = nullptr; r->need_nblk = r->need_max_rows = 0;
     r->d_ctile = nullptr; r->ctile_nx = r->ctile_count = 0;
     r->d_geo = nullptr; r->geo_box[0] = r->geo_box[1] = r->geo_box[2] = r->geo_box[3] = 0;
     r->d_spec = r->d_applied = r->d_ring_f = nullptr; r->d_gr_store = r->d_ring_u = r->d_tex = nullptr; r->d_av = nullptr; r->d_texmm = nullptr; r->d_coltab = nullptr; r->d_fb = nullptr;
@@ -772,9 +787,15 @@ static int run_update(glava_b200* r, const float* d_l, const float* d_r, int mod
             ++r->launches;
         }
         if (split_lazy) {
-            if ((rc = launch_k5_need(p, r->d_av, r->d_av_t, r->av_t_len, a.tex, r->batch, is_fft ? 2 : 1, r->d_csr, r->csr_bytes, r->csr_idx_off,
-                                     r->csr_off_off, r->d_need, r->d_tap_wsum, r->need_count, r->spec_stream)) != 0) return rc;
-            r->launches += 2;
+            if (r->d_need_blk) {
+                if ((rc = launch_k5_need_smem(p, r->d_av, a.tex, r->batch, is_fft ? 2 : 1, r->d_csr, r->csr_bytes, r->csr_idx_off, r->csr_off_off,
+                                              r->d_need, r->d_tap_wsum, r->need_count, r->d_need_blk, r->need_nblk, r->need_max_rows, r->spec_stream)) != 0) return rc;
+                r->launches += 1;
+            } else {
+                if ((rc = launch_k5_need(p, r->d_av, r->d_av_t, r->av_t_len, a.tex, r->batch, is_fft ? 2 : 1, r->d_csr, r->csr_bytes, r->csr_idx_off,
+                                         r->csr_off_off, r->d_need, r->d_tap_wsum, r->need_count, r->spec_stream)) != 0) return rc;
+                r->launches += 2;
+            }
         }
         if (split_k5) {
             // wave uses plane 0 of each stream only; smoothing the (zero) odd planes too keeps the launch simple

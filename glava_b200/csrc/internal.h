@@ -126,6 +126,11 @@ int launch_smooth_only(const glava_b200_params& p, const uint16_t* d_in, uint16_
 int launch_k5_need(const glava_b200_params& p, const uint16_t* d_av, float* d_av_t, int av_t_len, uint16_t* d_tex, int batch, int channels,
                    const unsigned char* d_csr, int csr_bytes, int csr_idx_off, int csr_off_off, const int* d_need,
                    const float* d_wsum, int need_count, void* stream);
+// the same need-list K5 from shared-memory tiles over blocks of sampled texels (tables.h build_need_blocks); reads the
+// [plane][bin] R16 texture directly
+int launch_k5_need_smem(const glava_b200_params& p, const uint16_t* d_av, uint16_t* d_tex, int batch, int channels,
+                        const unsigned char* d_csr, int csr_bytes, int csr_idx_off, int csr_off_off, const int* d_need,
+                        const float* d_wsum, int need_count, const void* d_blocks, int nblk, int max_rows, void* stream);
 // pipeline B epilogue as its own elementwise kernel: spec (transform_fft output) -> upload quantisation, K1 - K4 on the R16
 // state, pre-smoothing texels into av_out (leading `bins` of every plane; bins is a multiple of 8)
 int launch_epilogue_b(const glava_b200_params& p, const SpectrumArgs& a, int bins, void* stream);

@@ -771,7 +771,7 @@ av_transpose_kernel(const uint16_t* __restrict__ av, float* __restrict__ av_t, i
 }
 
 #define K5N_WARPS 4
-template <int MODE, int S>
+template <int MODE, int S, int D>
 __global__ void __launch_bounds__(512)
 k5_need_kernel(const float* __restrict__ av_t, int av_t_len, uint16_t* __restrict__ tex, int n, int batch, int channels,
                const unsigned char* __restrict__ csr, int csr_bytes, int csr_idx_off, int csr_off_off,
@@ -803,23 +803,24 @@ k5_need_kernel(const float* __restrict__ av_t, int av_t_len, uint16_t* __restric
         const int   my_i = mine < o1 ? (int) __ldg(ti + mine) * batch : 0;     // (a tap outside the texture is stored as index 0, weight 0)
         const float my_w = mine < o1 ? __ldg(tw + mine) : 0.0f;                 // (past the end of the list: index 0, weight 0 — adds +0)
         const int cnt = min(32, o1 - o);
-        // groups of 8 taps: all 8 * S texel loads are issued before the first dependent add (the sums are serial, the
-        // loads are not); a short last group runs past the list with weight 0 only when that cannot change a bit
-        for (int j0 = 0; j0 < cnt; j0 += 8) {
-            float t[8][S], w[8];
+        // groups of D taps: all D * S texel loads are issued before the first dependent add (the sums are serial, the
+        // loads are not); a short last group runs past the list with weight 0 only when that cannot change a bit.
+        // A warp's time is (taps / D) L2 round trips — the grid is about one wave of warps, so that chain IS the kernel's time
+        for (int j0 = 0; j0 < cnt; j0 += D) {
+            float t[D][S];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < D; ++j) {
                 const int i = __shfl_sync(0xffffffffu, my_i, j0 + j);
-                w[j] = __shfl_sync(0xffffffffu, my_w, j0 + j);
 #pragma unroll
                 for (int q = 0; q < S; ++q) t[j][q] = __ldg(col[q] + i);
             }
-            const int live = min(8, cnt - j0);
+            const int live = min(D, cnt - j0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (j < live) {
+            for (int j = 0; j < D; ++j) {
+                if (j < live) {                                            // (warp-uniform: the weight broadcast sits in the sum phase, D registers fewer)
+                    const float wj = __shfl_sync(0xffffffffu, my_w, j0 + j);
 #pragma unroll
-                    for (int q = 0; q < S; ++q) { if (MODE == 0) acc[q].avg += t[j][q] * w[j]; else acc[q].add_noweight(t[j][q], w[j]); }
+                    for (int q = 0; q < S; ++q) { if (MODE == 0) acc[q].avg += t[j][q] * wj; else acc[q].add_noweight(t[j][q], wj); }
                 }
             }
         }
@@ -831,6 +832,96 @@ k5_need_kernel(const float* __restrict__ av_t, int av_t_len, uint16_t* __restric
         const int stream = stream0 + 32 * q;
         if (stream < batch) tex[((size_t) stream * 2 + ch) * n + x] = (uint16_t) unorm16(acc[q].result(sp));
     }
+}
+
+// The same sums out of shared memory.  A CTA = (channel, 32 streams, block of sampled texels whose tap windows overlap:
+// tables.h build_need_blocks): the union of the block's windows is staged once, straight from the [plane][bin] R16 texture —
+// a warp reads a stream's bins with coalesced 32-bit loads, converts (from16, once per staged texel) and stores them
+// TRANSPOSED, tile[bin][stream] with a row stride of 33 floats, so that the tap loop's reads (lanes = streams) and these
+// writes (lanes = bins) are both conflict-free to 2-way.  No transposed copy in HBM, no av_transpose_kernel, and the tap
+// loop's traffic leaves L2: k5_need_kernel moved 4 bytes per tap and lane through L2 (ncu: 3.3 TB/s, its bound).
+template <int MODE>
+__global__ void __launch_bounds__(512)
+k5_need_smem_kernel(const uint16_t* __restrict__ av, uint16_t* __restrict__ tex, int n, int batch,
+                    const unsigned char* __restrict__ csr, int csr_bytes, int csr_idx_off, int csr_off_off,
+                    const int* __restrict__ need, const float* __restrict__ wsum, int need_count,
+                    const int4* __restrict__ blocks, int nblk, const SmoothParams sp) {
+    extern __shared__ float k5n_tile[];                                  // [rows][33]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int ch = blockIdx.z, g = blockIdx.y;
+    const int4 bk = __ldg(blocks + (size_t) ch * nblk + (nblk - 1 - blockIdx.x));      // the widest windows (last texels) first
+    const int k0 = bk.x, k1 = bk.y, lo = bk.z, rows = bk.w;
+    if (k1 <= k0) return;
+    for (int s = warp; s < 32; s += nwarps) {
+        const int stream = g * 32 + s;
+        if (stream < batch) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(av + ((size_t) stream * 2 + ch) * n + lo);   // n, lo even: 4-byte aligned
+            for (int c = lane; c < (rows >> 1); c += 32) {
+                const uint32_t u = __ldg(src + c);
+                k5n_tile[(2 * c) * 33 + s] = from16(u & 0xffffu);
+                k5n_tile[(2 * c + 1) * 33 + s] = from16(u >> 16);
+            }
+        } else {
+            for (int c = lane; c < rows; c += 32) k5n_tile[c * 33 + s] = 0.0f;      // lanes past the batch sum zeros and store nothing
+        }
+    }
+    __syncthreads();
+    const unsigned char* blob = csr + (size_t) ch * csr_bytes;
+    const float*    tw = reinterpret_cast<const float*>(blob);
+    const uint16_t* ti = reinterpret_cast<const uint16_t*>(blob + csr_idx_off);
+    const int*      to = reinterpret_cast<const int*>(blob + csr_off_off);
+    const int stream = g * 32 + lane;
+    const float* col = k5n_tile + lane;
+    // (issuing the tap-list chunk loads two chunks ahead of the sums, the first two before the tile is staged, measured
+    // SLOWER: 25 / 44 / 111 us against 22 / 37 / 82 us at setbufsize 4096 / 8192 / 16384 — profiles/r2_k5_smem_probe.txt)
+    for (int k = k1 - 1 - warp; k >= k0; k -= nwarps) {
+        const int x = __ldg(need + (size_t) ch * need_count + k);
+        if (x < 0 || x >= n) continue;
+        const int o0 = __ldg(to + k), o1 = __ldg(to + k + 1);
+        SmoothAcc acc; acc.init();
+        for (int o = o0; o < o1; o += 32) {
+            const int mine = o + lane;
+            // (a tap outside the texture is stored as index 0, weight 0: any row of the tile times +0 adds the same +0)
+            int my_r = 0; float my_w = 0.0f;
+            if (mine < o1) { my_r = (int) __ldg(ti + mine) - lo; my_r = my_r < 0 ? 0 : (my_r >= rows ? rows - 1 : my_r); my_r *= 33; my_w = __ldg(tw + mine); }
+            const int cnt = min(32, o1 - o);
+#pragma unroll 8
+            for (int j = 0; j < cnt; ++j) {
+                const int r = __shfl_sync(0xffffffffu, my_r, j);
+                const float w = __shfl_sync(0xffffffffu, my_w, j);
+                const float t = col[r];
+                if (MODE == 0) acc.avg += t * w; else acc.add_noweight(t, w);
+            }
+        }
+        acc.weight = __ldg(wsum + (size_t) ch * need_count + k);
+        if (stream < batch) tex[((size_t) stream * 2 + ch) * n + x] = (uint16_t) unorm16(acc.result(sp));
+    }
+}
+
+int launch_k5_need_smem(const glava_b200_params& p, const uint16_t* d_av, uint16_t* d_tex, int batch, int channels,
+                        const unsigned char* d_csr, int csr_bytes, int csr_idx_off, int csr_off_off, const int* d_need,
+                        const float* d_wsum, int need_count, const void* d_blocks, int nblk, int max_rows, void* stream) {
+    const SmoothParams sp = smooth_params(p);
+    cudaStream_t st = (cudaStream_t) stream;
+    if (nblk <= 0) return 0;
+    const size_t smem = (size_t) max_rows * 33 * sizeof(float);
+    int wpc = 16;
+    if (const char* e = getenv("GLAVA_B200_K5N_WARPS")) { const int v = atoi(e); if (v >= 1 && v <= 16) wpc = v; }
+    dim3 grid((unsigned) nblk, (unsigned) ((batch + 31) / 32), (unsigned) channels);
+    cudaError_t e;
+    if (sp.sample_mode == 0) {
+        if ((e = cudaFuncSetAttribute(k5_need_smem_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess)
+            return fail(GLAVA_B200_ECUDA, "need-list smooth kernel shared memory %zu: %s", smem, cudaGetErrorString(e));
+        k5_need_smem_kernel<0><<<grid, wpc * 32, smem, st>>>(d_av, d_tex, p.n, batch, d_csr, csr_bytes, csr_idx_off, csr_off_off, d_need, d_wsum,
+                                                             need_count, reinterpret_cast<const int4*>(d_blocks), nblk, sp);
+    } else {
+        if ((e = cudaFuncSetAttribute(k5_need_smem_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess)
+            return fail(GLAVA_B200_ECUDA, "need-list smooth kernel shared memory %zu: %s", smem, cudaGetErrorString(e));
+        k5_need_smem_kernel<1><<<grid, wpc * 32, smem, st>>>(d_av, d_tex, p.n, batch, d_csr, csr_bytes, csr_idx_off, csr_off_off, d_need, d_wsum,
+                                                             need_count, reinterpret_cast<const int4*>(d_blocks), nblk, sp);
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(GLAVA_B200_ECUDA, "need-list smooth kernel launch: %s", cudaGetErrorString(e));
+    return 0;
 }
 
 int launch_k5_need(const glava_b200_params& p, const uint16_t* d_av, float* d_av_t, int av_t_len, uint16_t* d_tex, int batch, int channels,
@@ -857,12 +948,14 @@ int launch_k5_need(const glava_b200_params& p, const uint16_t* d_av, float* d_av
     if (const char* e = getenv("GLAVA_B200_K5N_WARPS")) { const int v = atoi(e); if (v >= 1 && v <= 16) wpc = v; }
     const unsigned grid = (unsigned) ((warps + wpc - 1) / wpc);
     if (grid == 0) return 0;
-#define GLB_K5N(M, SS) k5_need_kernel<M, SS><<<grid, wpc * 32, 0, st>>>(d_av_t, av_t_len, d_tex, p.n, batch, channels, d_csr, csr_bytes, \
-                                                                              csr_idx_off, csr_off_off, d_need, d_wsum, need_count, sp)
-    const int m = sp.sample_mode == 0 ? 0 : 1;
-    if (S == 4) { if (m == 0) GLB_K5N(0, 4); else GLB_K5N(1, 4); }
-    else if (S == 2) { if (m == 0) GLB_K5N(0, 2); else GLB_K5N(1, 2); }
-    else { if (m == 0) GLB_K5N(0, 1); else GLB_K5N(1, 1); }
+#define GLB_K5N(M, SS, DD) k5_need_kernel<M, SS, DD><<<grid, wpc * 32, 0, st>>>(d_av_t, av_t_len, d_tex, p.n, batch, channels, d_csr, csr_bytes, \
+                                                                                  csr_idx_off, csr_off_off, d_need, d_wsum, need_count, sp)
+#define GLB_K5N_M(SS, DD) do { if (sp.sample_mode == 0) GLB_K5N(0, SS, DD); else GLB_K5N(1, SS, DD); } while (0)
+    // (D = taps in flight per lane and stream: 16 or 32 instead of 8 measured within 10 % — profiles/r2_k5_smem_probe.txt)
+    if (S == 4) GLB_K5N_M(4, 8);
+    else if (S == 2) GLB_K5N_M(2, 8);
+    else GLB_K5N_M(1, 8);
+#undef GLB_K5N_M
 #undef GLB_K5N
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(GLAVA_B200_ECUDA, "need-list smooth kernel launch: %s", cudaGetErrorString(e));

@@ -141,6 +141,54 @@ inline void build_lazy_tables(const glava_b200_params& p, const std::vector<int>
     }
 }
 
+// ---- need-list K5 out of shared memory (k5_need_smem_kernel) ----------------------------------------------------------
+// Adjacent sampled texels have almost the same tap window (bars 1080p @4096: 159 texels per channel, 9.2 k taps, all inside
+// 1536 bins): a block of texels whose windows' union fits a shared-memory tile is staged once per 32 streams and every
+// texel of the block sums out of the tile — the L2 traffic of the tap loop drops by taps / union.
+struct NeedBlocks {
+    int nblk = 0;                  // blocks per channel (the shorter channel is padded with empty blocks)
+    int max_rows = 0;              // tallest tile
+    std::vector<int> blk;          // [2][nblk] x {first entry, end entry, first bin (even), rows (even)}
+};
+// target_rows <= 0: -target_rows per cent of the tallest single window (at least 192 rows)
+inline void build_need_blocks(const LazyTables& t, int n, int target_rows, int texels_per_block, NeedBlocks* out) {
+    std::vector<int> per[2];
+    if (target_rows <= 0) {
+        NeedBlocks single;
+        build_need_blocks(t, n, 1, 1, &single);                  // one texel per block: max_rows = the tallest window
+        const long long want = (long long) single.max_rows * (target_rows < 0 ? -target_rows : 105) / 100;
+        target_rows = want > 192 ? (int) want : 192;
+    }
+    for (int c = 0; c < 2; ++c) {
+        const float* w = reinterpret_cast<const float*>(t.csr.data() + c * t.blob);
+        const uint16_t* ix = reinterpret_cast<const uint16_t*>(t.csr.data() + c * t.blob + t.idx_off);
+        const int* off = reinterpret_cast<const int*>(t.csr.data() + c * t.blob + t.off_off);
+        size_t k = 0;
+        while (k < t.cnt && t.need[c * t.cnt + k] >= 0) {
+            int lo = n, hi = -1, count = 0; const size_t k0 = k;
+            while (k < t.cnt && t.need[c * t.cnt + k] >= 0 && count < texels_per_block) {
+                int l = lo, h = hi;
+                for (int o = off[k]; o < off[k + 1]; ++o) {
+                    if (ix[o] == 0 && w[o] == 0.0f) continue;              // a tap outside the texture (or one that cannot count)
+                    if ((int) ix[o] < l) l = ix[o];
+                    if ((int) ix[o] > h) h = ix[o];
+                }
+                if (h < l) { l = l < n ? l : 0; h = h >= 0 ? h : 0; if (h < l) h = l; }
+                const int rows = ((h - (l & ~1) + 1) + 1) & ~1;
+                if (count > 0 && rows > target_rows) break;                  // (a single texel may exceed the target: its own block)
+                lo = l; hi = h; ++count; ++k;
+            }
+            const int lo2 = lo & ~1, rows = ((hi - lo2 + 1) + 1) & ~1;
+            per[c].push_back((int) k0); per[c].push_back((int) k); per[c].push_back(lo2); per[c].push_back(rows);
+            if (rows > out->max_rows) out->max_rows = rows;
+        }
+    }
+    const size_t nb = per[0].size() > per[1].size() ? per[0].size() / 4 : per[1].size() / 4;
+    out->nblk = (int) nb;
+    out->blk.assign(2 * nb * 4, 0);
+    for (int c = 0; c < 2; ++c) for (size_t i = 0; i < per[c].size(); ++i) out->blk[c * nb * 4 + i] = per[c][i];
+}
+
 // ---- full-plane K5 ----------------------------------------------------------------------------------------------------
 #ifndef K5_BLOCK
 #define K5_BLOCK 128

@@ -109,6 +109,8 @@ def lazy_k5(p, chan, path, av):
     av = np.ascontiguousarray(av, dtype=np.uint16)
     out = np.zeros(p.n, np.uint16); need = np.zeros(p.n, np.int32)
     cnt = lib().emul_lazy_k5(C.byref(p), chan, path, av.ctypes.data, out.ctypes.data, need.ctypes.data)
+    if cnt < -1:
+        raise AssertionError(f"blocks-of-texels walk: error {cnt} (emul.cpp emul_lazy_k5)")
     if cnt < 0:
         return None, None
     idx = need[:cnt].copy()

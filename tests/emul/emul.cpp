@@ -260,6 +260,44 @@ int emul_lazy_k5(const glava_b200_params* pp, int chan, int path, const uint16_t
     const SmoothParams sp = smooth_params(p);
     const int N = p.n;
     int written = 0;
+    if (path >= 2) {
+        // k5_need_smem_kernel: blocks of sampled texels (path = 2: default block shape; otherwise target rows = path, 3 texels
+        // per block), a tile of from16() values per block, tap rows clamped into the tile
+        NeedBlocks nb;
+        if (path == 2) build_need_blocks(t, N, 384, 16, &nb); else build_need_blocks(t, N, path, 3, &nb);
+        const unsigned char* blob = t.csr.data() + (size_t) chan * t.blob;
+        const float* tw = reinterpret_cast<const float*>(blob);
+        const uint16_t* ti = reinterpret_cast<const uint16_t*>(blob + t.idx_off);
+        const int* to = reinterpret_cast<const int*>(blob + t.off_off);
+        std::vector<char> seen(t.cnt, 0);
+        for (int b = 0; b < nb.nblk; ++b) {
+            const int* bk = nb.blk.data() + ((size_t) chan * nb.nblk + b) * 4;
+            const int k0 = bk[0], k1 = bk[1], lo = bk[2], rows = bk[3];
+            if (k1 <= k0) continue;
+            if ((lo & 1) || (rows & 1) || lo < 0 || lo + rows > N || rows > nb.max_rows) return -2;
+            std::vector<float> tile(rows);
+            for (int i = 0; i < rows; ++i) tile[i] = from16(av[lo + i]);
+            for (int k = k1 - 1; k >= k0; --k) {
+                const int x = t.need[chan * t.cnt + k];
+                if (x < 0 || x >= N) continue;
+                if (seen[k]) return -3;
+                seen[k] = 1;
+                SmoothAcc acc; acc.init();
+                for (int o = to[k]; o < to[k + 1]; ++o) {
+                    int r = (int) ti[o] - lo;
+                    if ((r < 0 || r >= rows) && !(ti[o] == 0 && tw[o] == 0.0f)) return -4;      // a counting tap outside its block's tile
+                    r = r < 0 ? 0 : (r >= rows ? rows - 1 : r);
+                    acc.add_noweight(tile[r], tw[o]);
+                }
+                acc.weight = t.wsum[chan * t.cnt + k];
+                out[x] = (uint16_t) unorm16(acc.result(sp));
+                if (need_out) need_out[written] = x;
+                ++written;
+            }
+        }
+        for (size_t k = 0; k < t.cnt; ++k) { const int x = t.need[chan * t.cnt + k]; if (x >= 0 && x < N && !seen[k]) return -5; }
+        return written;
+    }
     for (size_t k = 0; k < t.cnt; ++k) {                                   // kernel: thread k (+ T, ...)
         const int x = t.need[chan * t.cnt + k];
         if (x < 0 || x >= N) continue;

@@ -163,7 +163,8 @@ def test_full_plane_k5_table_wide_window(orc_pm, built):
                                           ("graph", 2048, 1280, 720), ("wave", 2048, 1280, 720)])
 def test_lazy_k5_tables_give_the_oracle_texels(orc_pm, module, n, w, h, built):
     """need-list + tap table: every texel the module samples equals the oracle's smooth pass there, through both table
-    layouts, and the pruning bound epi_n covers every input a tap reads"""
+    layouts and through the blocks-of-texels tiling (every counting tap inside its block's tile, every texel in exactly one
+    block), and the pruning bound epi_n covers every input a tap reads"""
     p = g.default_params(module, n=n, w=w, h=h, lazy_smooth=1)
     op = params_from(p)
     epi = emul.lazy_epi_n(p)
@@ -172,7 +173,7 @@ def test_lazy_k5_tables_give_the_oracle_texels(orc_pm, module, n, w, h, built):
         tex = _tex(n, 7 + chan)
         want = orc_pm.smooth_pass(op, tex)
         got = {}
-        for path in (0, 1):
+        for path in (0, 1, 2, 40):             # 2, 40: blocks of texels out of a tile (k5_need_smem_kernel), default / small blocks
             idx, val = emul.lazy_k5(p, chan, path, tex)
             if module == "wave" and chan == 1:
                 assert idx is not None and len(idx) == 0               # audio_r is never sampled (wave/1.frag:7)
@@ -181,6 +182,8 @@ def test_lazy_k5_tables_give_the_oracle_texels(orc_pm, module, n, w, h, built):
             got[path] = (idx, val)
         if got:
             assert np.array_equal(got[0][0], got[1][0])
+            for path in (2, 40):               # the same texels, widest windows first inside each block
+                assert np.array_equal(np.sort(got[path][0]), got[0][0]), (module, chan, path)
             # inputs at or beyond epi_n cannot influence a sampled texel
             tex2 = tex.copy(); tex2[epi:] = 0
             assert np.array_equal(emul.lazy_k5(p, chan, 1, tex2)[1], got[1][1])

@@ -168,8 +168,8 @@ def test_bad_arguments_fail_loudly(built):
 @pytest.mark.parametrize("n,w", [(1024, 320), (4096, 1920), (8192, 1920)])
 def test_kernel_variants_give_identical_textures_and_frames(built, monkeypatch, n, w):
     """the spectrum path exists in several launch structures (tuning knobs): plane-per-CTA kernel with in-kernel
-    epilogue and K5; K5 as its own kernel over (texel, stream) pairs; the R16 state update as an elementwise kernel; FFT passes
-    in place / out of place, 128 / 256 threads.  All of them are the same arithmetic: textures and frames must be identical."""
+    epilogue and K5; K5 as its own kernel over (texel, stream) pairs (through L2, or out of shared-memory tiles); the R16 state
+    update as an elementwise kernel; FFT passes in place / out of place, 128 / 256 threads.  All of them are the same arithmetic: textures and frames must be identical."""
     batch = 70                                                    # not a multiple of 32: partial stream groups in k5_need_kernel
     p = g.default_params("bars", n=n, w=w, h=32, lazy_smooth=1)
     rng = np.random.default_rng(n)
@@ -177,7 +177,8 @@ def test_kernel_variants_give_identical_textures_and_frames(built, monkeypatch, 
     masks = [None, None, rng.random(batch) < 0.5, None, rng.random(batch) < 0.5, None, None]
 
     def run(env):
-        for k in ("GLAVA_B200_K5_SPLIT", "GLAVA_B200_SPLIT_EPI", "GLAVA_B200_SPEC_OOP", "GLAVA_B200_SPEC_T"):
+        for k in ("GLAVA_B200_K5_SPLIT", "GLAVA_B200_SPLIT_EPI", "GLAVA_B200_SPEC_OOP", "GLAVA_B200_SPEC_T", "GLAVA_B200_K5N_SMEM",
+                  "GLAVA_B200_K5N_ROWS", "GLAVA_B200_K5N_TPB", "GLAVA_B200_K5N_WARPS"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -195,7 +196,12 @@ def test_kernel_variants_give_identical_textures_and_frames(built, monkeypatch, 
     assert base[0].any()
     for env in ({"GLAVA_B200_K5_SPLIT": "1", "GLAVA_B200_SPLIT_EPI": "0"}, {"GLAVA_B200_K5_SPLIT": "1", "GLAVA_B200_SPLIT_EPI": "1"},
                 {"GLAVA_B200_K5_SPLIT": "1", "GLAVA_B200_SPLIT_EPI": "1", "GLAVA_B200_SPEC_OOP": "1", "GLAVA_B200_SPEC_T": "256"},
-                {"GLAVA_B200_K5_SPLIT": "0", "GLAVA_B200_SPEC_OOP": "1", "GLAVA_B200_SPEC_T": "128"}, {}):      # {} = this size's defaults
+                {"GLAVA_B200_K5_SPLIT": "0", "GLAVA_B200_SPEC_OOP": "1", "GLAVA_B200_SPEC_T": "128"},
+                # K5 over (texel, stream) pairs: through L2 from a transposed copy / out of shared-memory tiles over blocks of texels
+                {"GLAVA_B200_K5_SPLIT": "1", "GLAVA_B200_K5N_SMEM": "0"},
+                {"GLAVA_B200_K5_SPLIT": "1", "GLAVA_B200_K5N_SMEM": "1"},
+                {"GLAVA_B200_K5_SPLIT": "1", "GLAVA_B200_K5N_SMEM": "1", "GLAVA_B200_K5N_ROWS": "64", "GLAVA_B200_K5N_TPB": "3", "GLAVA_B200_K5N_WARPS": "2"},
+                {}):                                                                                             # {} = this size's defaults
         got = run(env)
         assert np.array_equal(got[0], base[0]) and np.array_equal(got[1], base[1]), env
         for a, b in zip(got[2], base[2]):
