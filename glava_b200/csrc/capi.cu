@@ -496,7 +496,8 @@ static int build(glava_b200* r) {
     ALLOC(r->d_av, planes * n * 2, true);
     ALLOC(r->d_texmm, planes * GLB_TEXMM_STRIDE * sizeof(uint32_t), true);          // double-buffered: spectrum i+1 writes one half while raster i reads the other
     ALLOC(r->d_rowtab, (size_t) p.h * 8, true);
-    ALLOC(r->d_coltab, (size_t) r->batch * GLB_COLTAB_PLANES * p.w * sizeof(float), true);
+    if (p.module == GLAVA_B200_MOD_GRAPH || p.module == GLAVA_B200_MOD_WAVE)          // (the module of a handle never changes: reconfigure refuses)
+        ALLOC(r->d_coltab, (size_t) r->batch * GLB_COLTAB_PLANES * p.w * sizeof(float), true);
     // framebuffers: [slots][h][w] RGBA8
     size_t frame = (size_t) p.w * p.h * 4;
     r->slots = (p.fb_slots > 0 && p.fb_slots < r->batch) ? p.fb_slots : r->batch;
@@ -659,7 +660,8 @@ static int apply_resize(glava_b200* r, int w, int h) {
     r->p_user = q;
     derive(r);
     if ((rc = dev_alloc(r, (void**) &r->d_rowtab, (size_t) q.h * 8, true)) != 0) return rc;
-    if ((rc = dev_alloc(r, (void**) &r->d_coltab, (size_t) r->batch * GLB_COLTAB_PLANES * q.w * sizeof(float), true)) != 0) return rc;
+    if ((q.module == GLAVA_B200_MOD_GRAPH || q.module == GLAVA_B200_MOD_WAVE) &&
+        (rc = dev_alloc(r, (void**) &r->d_coltab, (size_t) r->batch * GLB_COLTAB_PLANES * q.w * sizeof(float), true)) != 0) return rc;
     if ((rc = dev_alloc(r, (void**) &r->d_fb, (size_t) q.w * q.h * 4 * r->slots, true)) != 0) return rc;
     return build_tables(r);
 }
