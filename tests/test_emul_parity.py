@@ -189,6 +189,22 @@ def test_lazy_k5_tables_give_the_oracle_texels(orc_pm, module, n, w, h, built):
             assert np.array_equal(emul.lazy_k5(p, chan, 1, tex2)[1], got[1][1])
 
 
+@pytest.mark.parametrize("module,n,w,h", [("bars", 8192, 1920, 1080), ("bars", 16384, 1920, 1080), ("radial", 8192, 3840, 2160),
+                                          ("graph", 4096, 1920, 1080), ("bars", 512, 1280, 720), ("bars", 256, 64, 16)])
+def test_need_list_blocks_at_the_sweep_sizes(orc_pm, module, n, w, h, built):
+    """the blocks-of-texels tiling (k5_need_smem_kernel) at the sizes of BASELINE configs[2] and [4]: default tile height, a
+    height below every window (one texel per block, tiles as tall as the window) and a tall one"""
+    p = g.default_params(module, n=n, w=w, h=h, lazy_smooth=1)
+    op = params_from(p)
+    for chan in (0, 1):
+        tex = _tex(n, 11 + chan)
+        want = orc_pm.smooth_pass(op, tex)
+        base = emul.lazy_k5(p, chan, 1, tex)
+        for path in (2, 4, 4000):
+            idx, val = emul.lazy_k5(p, chan, path, tex)
+            assert np.array_equal(np.sort(idx), base[0]) and np.array_equal(val, want[idx]), (module, n, chan, path)
+
+
 def test_circle_has_no_need_list(built):
     p = g.default_params("circle", n=1024, w=320, h=240, lazy_smooth=1)
     assert emul.lazy_k5(p, 0, 0, _tex(1024, 1))[0] is None
