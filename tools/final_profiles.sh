@@ -1,5 +1,6 @@
 #!/bin/bash
-# ncu evidence of the round (one GPU).  Reports are exported to CSV on the box and deleted (64 MiB cap on gpurun_out).
+# ncu evidence of the round (one GPU).  (tools/sass_segments.py wants the source page of a SINGLE-kernel capture:
+# ncu -k regex:spectrum_kernel … tools/spec_probe.py --one 8192, as for profiles/r2a_before_spectrum8192_stall_segments.txt.)  Reports are exported to CSV on the box and deleted (64 MiB cap on gpurun_out).
 set -x
 mkdir -p gpurun_out
 B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras"
@@ -14,11 +15,7 @@ cap() {   # name, kernel regex, skip, count, command...
   if [ "$5" != "" ]; then :; fi
 }
 cap r2_headline "raster_bars|spectrum_kernel|epilogue_b|av_transpose|k5_need" 15 5 $B
-ncu -i /tmp/r2_headline.ncu-rep --page source --csv > /tmp/r2_headline_source.csv 2>/dev/null
-python tools/sass_segments.py /tmp/r2_headline_source.csv > gpurun_out/r2_headline_stall_segments.txt 2>&1
 cap r2_radial4k "raster_radial_geo|spectrum_kernel|epilogue_b|av_transpose|k5_need" 15 5 $B --config radial4k
-ncu -i /tmp/r2_radial4k.ncu-rep --page source --csv > /tmp/r2_radial4k_source.csv 2>/dev/null
-python tools/sass_segments.py /tmp/r2_radial4k_source.csv > gpurun_out/r2_radial4k_stall_segments.txt 2>&1
 for m in circle graph wave; do cap r2_$m "raster_${m}|texmm" 4 2 $B --config ${m}1080; done
 cap r2_misc "k5_table|fifo_ingest" 0 2 python bench.py --steps 2 --warmup 3 --no-cpu-baseline
 ls -la gpurun_out
