@@ -12,8 +12,8 @@ stream-wise, no inter-GPU collective on the data path).  Other BASELINE configur
   sweep:<n>:<w>x<h>    one point of configs[4] (bars, 8192 streams over 8 GPUs = 1024 per GPU; framebuffer ring when
              1024 frames exceed the HBM budget); tools/sweep_configs.py runs the whole grid
 
-One step = one rd_update(modified=true) for every stream of the batch: fused spectrum kernel (window + FFT + log + gravity
-+ average + smoothing) and one frame per stream.
+One step = one rd_update(modified=true) for every stream of the batch: the spectrum path (window + FFT + log + gravity
++ average + smoothing: one kernel below setbufsize 4096, three from there up — DESIGN 4.1a) and one frame per stream.
 
   value  frames/s, inputs already resident in HBM (glava_b200_update_device)
   e2e    frames/s through the reference-facing C ABI with HOST buffers, the way GLava's FIFO backend feeds it (fifo.c:89-110):
