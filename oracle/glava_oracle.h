@@ -9,13 +9,24 @@
  *   - rd_update's orchestration — transform chain, `modified`, setbufscale, keyframe interpolation, the "smooth" transform,
  *     pipeline B's upload — and rd_new's reading of configurations: both run for real on a null OpenGL driver
  *     (libglava_ref_rd.so), the whole program included (glava_entry with fifo.c on a named pipe).
- * The RASTER half and the GL passes K2 / K4 / K5 restate GLSL; no GL implementation is available in this image, so they are
- * pinned one level down: oracle/glsl_interp.py EXECUTES the reference's own shader sources in float32 — its input is
- * token-identical to the texts rd_new hands to glShaderSource — and this restatement equals its frames bit for bit
- * (tests/golden/glsl_golden.npz: 36 module configurations, smooth_pass.frag's modes, gravity / average / pass; a 1000-seed
- * randomised config differential; the `test` module's #55000055 known answer, shaders/glava/test_rc.glsl:27).  What GLSL and
- * GL leave implementation-defined (transcendental ulps, round() ties, out-of-range texelFetch, unorm and blend rounding) is
- * fixed by convention, not by the reference: that part alone is "parity unpinned".
+ *   - the RASTER half and the GL passes K1 - K5 (round 2): the reference's own renderer — rd_new / rd_update, its pass /
+ *     gravity_pass / average_pass / smooth_pass.frag and the module shaders — run on a REAL OpenGL: Mesa 18.1.9 llvmpipe
+ *     (GLava's stated software floor, README.md:121), found inside the Nsight Compute bundle of this image and of the GPU
+ *     box and driven without an X server (oracle/ref_shim.c's "mesa" window backend, oracle/fakex/, oracle/ref_gl.py).
+ *     tests/golden/llvmpipe_golden.npz holds what it rendered for 58 configurations (every upload, every 1-D pass texture,
+ *     the final frames; BASELINE geometries, every module option, 30 random configurations); tests/test_llvmpipe_golden.py
+ *     replays them through this restatement pass by pass, re-generates them live wherever the harness loads, and — with
+ *     -m gpu — compares the kernels with them.  Result: uploads and every blended frame bit for bit; K1 - K4 bit for bit
+ *     except <= 2 texels per case by 1 LSB16; K5 <= 1 LSB16 (4 for ROUND_FORMULA circular: that llvmpipe's sqrt); native
+ *     frames <= 1 LSB with <= 8 counted hard-edge pixels per case — the places where GLSL leaves sin / cos / log / atan /
+ *     sqrt to the implementation.  Where this file's round-1 conventions differed from llvmpipe (unorm store rounding,
+ *     blend arithmetic) they were CHANGED to llvmpipe's.
+ *   - oracle/glsl_interp.py (round 1's stand-in for a GL: it EXECUTES the reference's shader sources in float32; its input
+ *     is token-identical to the texts rd_new hands to glShaderSource) is kept for exact single-stage textures and the
+ *     1000-seed randomised config differential (tests/golden/glsl_golden.npz, 36 module configurations; the `test`
+ *     module's #55000055 known answer, shaders/glava/test_rc.glsl:27); it is itself pinned to the llvmpipe goldens now.
+ * Not pinned by anything the reference can run: setbufsize 16384 on the GL side (GL_MAX_TEXTURE_SIZE of that Mesa is 8192 and
+ * bind_1d_fbo aborts) — checked against this restatement, which is pinned at every smaller size, and against float64.
  */
 #ifndef GLAVA_ORACLE_H
 #define GLAVA_ORACLE_H

@@ -1,7 +1,10 @@
 """TEST INFRASTRUCTURE — a small interpreter for the subset of GLSL that GLava's shipped shaders use.
 
-Why: the raster half of the reference is GLSL, and this image has no OpenGL to run it, so the C restatement in
-glava_oracle.c could not be pinned to the reference by running the reference.  This module closes most of that gap: it
+Why: the raster half of the reference is GLSL.  In round 1 no OpenGL had been found in this image, so the C restatement in
+glava_oracle.c could not be pinned by running the reference; this module closed most of that gap.  (Round 2 found a real one —
+Mesa llvmpipe inside the Nsight Compute bundle, oracle/ref_gl.py — and the reference itself now renders the goldens that pin
+the oracle, the kernels AND this interpreter: tests/golden/llvmpipe_golden.npz.  The interpreter stays for what a real GL
+cannot give: exact single-stage evaluation on chosen textures and the 1000-seed config differential.)  It
 reads the reference's OWN shader sources (shaders/glava/<module>/<n>.frag, util/*.frag, the module .glsl configs),
 applies GLava's source extensions (glsl_ext.c: `#include` with ':' / '@', `#request`, `#expand`, `#rrggbb` colour
 literals, `@name:default` binds, `#define` overriding) and the header GLava injects (render.c:284-327), runs a C
