@@ -1,8 +1,8 @@
 """Regression fixture for the RASTER half: frames of the C restatement (oracle, libm build) for every module at a small
-size, from seeded textures.  The reference ships no golden pixels and no GL is available to render its shaders
-("parity unpinned" apart from the #55000055 known answer), so this fixture does NOT pin the
-restatement to the reference — it freezes it, so that neither the oracle nor the kernels can drift unnoticed between
-rounds.  Regenerate only together with a deliberate change of the GLSL semantics:
+size, from seeded textures.  This fixture does NOT pin the restatement to the reference (tests/golden/llvmpipe_golden.npz
+does: the reference itself on Mesa llvmpipe) — it freezes the restatement's exact libm-build output, so
+that neither the oracle nor the kernels can drift unnoticed between rounds.  Regenerate only together with a deliberate
+change of the GLSL semantics (round 2 did: unorm rounding and blend arithmetic became llvmpipe's):
 
     python tests/golden/make_raster_regression.py
 """

@@ -1,8 +1,9 @@
 """Frames computed from the REFERENCE'S OWN SHADER TEXT (tests/golden/glsl_golden.npz, made by
 tests/golden/make_glsl_golden.py with oracle/glsl_interp.py) against the C restatement (oracle), the product arithmetic
-compiled for the host (tests/emul) and — -m gpu — the kernels.  This is what pins the raster half and the GL passes
-K2 / K4 / K5 to the reference: the interpreter takes macro precedence, int / float typing, operand order, stage chaining
-and quantisation from the .frag / .glsl files themselves."""
+compiled for the host (tests/emul) and — -m gpu — the kernels.  Round 1's pin of the raster half and the GL passes
+K2 / K4 / K5: the interpreter takes macro precedence, int / float typing, operand order, stage chaining and quantisation
+from the .frag / .glsl files themselves.  Since round 2 the pin is the reference itself on Mesa llvmpipe
+(tests/test_llvmpipe_golden.py); these frames stay as EXACT (same-libm) single-stage checks on chosen textures."""
 import ctypes as C
 import json
 import os
