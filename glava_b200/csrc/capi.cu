@@ -96,7 +96,7 @@ struct glava_b200 {
     // need-list K5 as its own kernel (one table per channel): the serial per-texel sums run at full occupancy on
     // (texel, plane) pairs instead of on a sixth of the threads of one spectrum CTA
     void* d_need_blk; int need_nblk, need_max_rows;    // need-list K5 out of shared memory: blocks of sampled texels (tables.h build_need_blocks)
-    bool k5_split_lazy, csr_in_smem, split_epilogue; int av_t_len; float* d_av_t; int spec_oop, spec_t;   // need-list K5 as its own kernel (k5_need_kernel)
+    bool k5_split_lazy, csr_in_smem, split_epilogue; int av_t_len; float* d_av_t; int spec_oop, spec_t;   // need-list K5 as its own kernel (k5_need_smem_kernel; k5_need_kernel + transposed copy as the fall-back)
     unsigned char* d_csr; int csr_bytes, csr_idx_off, csr_off_off;   // the same taps, texel-major, for the shared-memory path
     void* d_geo; int geo_box[4];   // polar geometry cache (radial / circle), see raster_kernels.cu
     void* d_ctile; int ctile_nx, ctile_count;   // circle: per-tile texel reference ranges (launch_circle_tiles)
@@ -366,7 +366,7 @@ static int build_tables(glava_b200* r) {
                 CU(cudaStreamSynchronize(r->stream));
                 r->csr_bytes = (int) t.blob; r->csr_idx_off = (int) t.idx_off; r->csr_off_off = (int) t.off_off;
                 r->csr_in_smem = fits;
-                // Need-list K5 as its own kernel (k5_need_kernel, lanes = streams): default whenever the taps do not fit shared
+                // Need-list K5 as its own kernel (k5_need_smem_kernel / k5_need_kernel, lanes = streams): default whenever the taps do not fit shared
                 // memory next to the FFT, and from setbufsize 4096 up anyway; GLAVA_B200_K5_SPLIT=1 / 0 forces it on / off.
                 const char* ks = getenv("GLAVA_B200_K5_SPLIT");
                 r->k5_split_lazy = ks ? atoi(ks) != 0 : (!fits || p.n >= 4096);     // measured: also ahead at 4096 (759 k vs 753 k frames/s at the headline)

@@ -69,7 +69,7 @@ struct SpectrumArgs {
     // texture is carried from `tex_prev` (the half of the double buffer the previous raster read) into `tex`.
     int variant_oop, variant_t; // kernel variant: out-of-place passes, threads per CTA (0 = the size's default)
     int fft_only;               // 1: stop after transform_fft — `spec` (the leading epi_n bins) is all this launch produces; gravity /
-                                // average run as epilogue_b_kernel, K5 as k5_need_kernel (capi.cu run_update)
+                                // average run as epilogue_b_kernel, K5 as k5_need_smem_kernel / k5_need_kernel (capi.cu run_update)
     int av_t_len;               // > 0: av_out receives only the leading av_t_len bins (need-list K5 as its own kernel downstream)
     const uint32_t* umask;      // [batch]
     const uint16_t* tex_prev;   // [batch*2][n]

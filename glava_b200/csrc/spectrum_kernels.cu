@@ -421,7 +421,7 @@ spectrum_kernel(const __grid_constant__ SpectrumArgs a, const __grid_constant__ 
         } else if (a.av_out) {
             // export the pre-smoothing texture for a K5 kernel downstream: all n texels (k5_table_kernel / k5_planes_kernel
             // smooth whole planes, sharing every tap weight between several planes), or only the leading av_t_len bins the
-            // need-list's taps can reach (av_transpose_kernel + k5_need_kernel)
+            // need-list's taps can reach (k5_need_smem_kernel, or av_transpose_kernel + k5_need_kernel)
             uint16_t* dst = a.av_out + plane;
             const int lim = a.av_t_len > 0 ? a.av_t_len : N;
             for (int x = tid; x < lim; x += T) dst[x] = av[x];
